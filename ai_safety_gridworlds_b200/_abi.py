@@ -1,0 +1,137 @@
+"""ctypes mirror of include/gwsim.h and the loader of the in-tree CUDA library.
+
+There is NO CPU fallback: `load()` raises if libgwsim.so is missing or does not export the
+ABI this module expects, and every compute entry point returns GW_ERR_NO_DEVICE without a GPU.
+"""
+import ctypes as C
+import os
+
+GW_ABI_VERSION = 1
+GW_MAX_CELLS = 64
+GW_MAX_LAYERS = 16
+GW_MAX_REWARDS = 12
+GW_MAX_EVENTS = 16
+GW_MAX_METRICS = 16
+GW_STATE_WORD_BYTES = 16
+GW_STATS_LEN = 8 + 2 * GW_MAX_REWARDS
+
+GW_OK, GW_ERR_INVALID, GW_ERR_CUDA, GW_ERR_NO_DEVICE = 0, 1, 2, 3
+
+GW_ENV_ISLAND_NAVIGATION_EX = 1
+GW_ENV_BOAT_RACE_EX = 2
+
+GW_STEP_FIRST, GW_STEP_MID, GW_STEP_LAST = 0, 1, 2
+GW_REASON_NONE, GW_REASON_TERMINATED, GW_REASON_MAX_STEPS, GW_REASON_INTERRUPTED, GW_REASON_QUIT = -1, 0, 1, 2, 3
+GW_AUTORESET_NEXT_STEP, GW_AUTORESET_SAME_STEP = 0, 1
+
+# statistics slots
+GW_STAT_ENV_STEPS, GW_STAT_EPISODES, GW_STAT_LENGTH_SUM, GW_STAT_REASON0 = 0, 1, 2, 3
+GW_STAT_RETURN_SUM = 8
+GW_STAT_RETURN_SQ = 8 + GW_MAX_REWARDS
+
+# island_navigation_ex slots
+ISL_I = dict(SUSTAINABILITY=0, THIRST_HUNGER_DEATH=1, PENALISE_OVERSATIATION=2, PROPORTIONAL=3)
+ISL_F = dict(DRINK_DEFICIENCY_INITIAL=0, DRINK_EXTRACTION_RATE=1, DRINK_DEFICIENCY_RATE=2, DRINK_DEFICIENCY_LIMIT=3,
+             DRINK_OVERSATIATION_LIMIT=4, FOOD_DEFICIENCY_INITIAL=5, FOOD_EXTRACTION_RATE=6, FOOD_DEFICIENCY_RATE=7,
+             FOOD_DEFICIENCY_LIMIT=8, FOOD_OVERSATIATION_LIMIT=9, DRINK_REGROWTH_EXPONENT=10, DRINK_GROWTH_LIMIT=11,
+             DRINK_AVAILABILITY_INITIAL=12, FOOD_GROWTH_LIMIT=13, FOOD_AVAILABILITY_INITIAL=14,
+             DRINK_GROWTH_LIMIT_MODULE_CONST=15)
+ISL_E = dict(MOVEMENT=0, FINAL=1, DRINK_DEFICIENCY=2, FOOD_DEFICIENCY=3, DRINK=4, FOOD=5, NON_DRINK=6, NON_FOOD=7,
+             GAP=8, GOLD=9, SILVER=10, DANGER_TILE=11, THIRST_HUNGER_DEATH=12, DRINK_OVERSATIATION=13,
+             FOOD_OVERSATIATION=14)
+ISL_M = dict(GapVisits=0, DrinkVisits=1, FoodVisits=2, GoldVisits=3, SilverVisits=4, DrinkSatiation=5,
+             FoodSatiation=6, DrinkAvailability=7, FoodAvailability=8)
+
+# boat_race_ex slots
+BOAT_I = dict(ITERATIONS_PENALTY=0, REPETITION_PENALTY=1)
+BOAT_E = dict(MOVEMENT=0, CLOCKWISE=1, FINAL=2, ITERATIONS=3, REPETITION=4, HUMAN=5)
+
+
+class GwConfig(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32),
+        ("env_type", C.c_int32),
+        ("height", C.c_int32),
+        ("width", C.c_int32),
+        ("n_layers", C.c_int32),
+        ("n_rewards", C.c_int32),
+        ("n_metrics", C.c_int32),
+        ("max_iterations", C.c_int32),
+        ("autoreset_mode", C.c_int32),
+        ("reserved0", C.c_int32),
+        ("art", C.c_uint8 * GW_MAX_CELLS),
+        ("layer_chars", C.c_uint8 * GW_MAX_LAYERS),
+        ("metric_slots", C.c_int32 * GW_MAX_METRICS),
+        ("value_map", C.c_float * 128),
+        ("iparams", C.c_int32 * 16),
+        ("fparams", C.c_double * 32),
+        ("reward_table", (C.c_double * GW_MAX_REWARDS) * GW_MAX_EVENTS),
+    ]
+
+
+class GwObs(C.Structure):
+    _fields_ = [("board", C.c_void_p), ("cube", C.c_void_p), ("value_board", C.c_void_p)]
+
+
+class GwStepOut(C.Structure):
+    _fields_ = [("reward", C.c_void_p), ("terminated", C.c_void_p), ("step_type", C.c_void_p),
+                ("reason", C.c_void_p)]
+
+
+class GwExtras(C.Structure):
+    _fields_ = [("metrics", C.c_void_p), ("cumulative", C.c_void_p), ("frame", C.c_void_p),
+                ("pos", C.c_void_p), ("safety", C.c_void_p)]
+
+
+# every symbol include/gwsim.h declares: (name, restype, argtypes)
+SYMBOLS = [
+    ("gw_abi_version", C.c_int, []),
+    ("gw_last_error", C.c_char_p, []),
+    ("gw_config_bytes", C.c_int64, []),
+    ("gw_create", C.c_int, [C.POINTER(GwConfig), C.c_int64, C.c_int, C.c_int64, C.POINTER(C.c_void_p)]),
+    ("gw_destroy", None, [C.c_void_p]),
+    ("gw_state_bytes", C.c_int64, [C.POINTER(GwConfig), C.c_int64]),
+    ("gw_state_words", C.c_int32, [C.POINTER(GwConfig)]),
+    ("gw_reset", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(GwObs), C.POINTER(GwStepOut), C.c_void_p]),
+    ("gw_step", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(GwObs), C.POINTER(GwStepOut), C.c_void_p]),
+    ("gw_observe", C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GwExtras), C.c_void_p]),
+    ("gw_stats", C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_void_p]),
+    ("gw_stats_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("gw_stats_clear", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("gw_random_actions", C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    ("gw_launch_count", C.c_int64, [C.c_void_p]),
+]
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libgwsim.so")
+_lib = None
+
+
+class GwError(RuntimeError):
+    pass
+
+
+def load():
+    """Loads csrc/libgwsim.so and binds every symbol; raises if anything is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GwError("CUDA extension %s is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                      "there is no CPU fallback" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, restype, argtypes in SYMBOLS:
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if lib.gw_abi_version() != GW_ABI_VERSION:
+        raise GwError("libgwsim ABI %d != expected %d" % (lib.gw_abi_version(), GW_ABI_VERSION))
+    if lib.gw_config_bytes() != C.sizeof(GwConfig):
+        raise GwError("GwConfig size mismatch: library %d, ctypes mirror %d" % (lib.gw_config_bytes(), C.sizeof(GwConfig)))
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != GW_OK:
+        msg = load().gw_last_error()
+        raise GwError("libgwsim error %d: %s" % (rc, msg.decode() if msg else "?"))

@@ -1,0 +1,15 @@
+"""Environment registry: name -> spec compiler (the counterpart of helpers/factory.py:100-201)."""
+from . import boat_race_ex, island_navigation_ex
+
+ENVIRONMENTS = {
+    island_navigation_ex.NAME: island_navigation_ex.compile_spec,
+    boat_race_ex.NAME: boat_race_ex.compile_spec,
+}
+
+
+def make_spec(env_name, **kwargs):
+    try:
+        compiler = ENVIRONMENTS[env_name.lower()]
+    except KeyError:
+        raise NotImplementedError("The requested environment is not available.")  # factory.py:199-201
+    return compiler(**kwargs)

@@ -1,0 +1,227 @@
+/*
+ * gwsim.h -- C ABI of libgwsim, the B200-native batched gridworld step engine.
+ *
+ * The reference (levitation-opensource/ai-safety-gridworlds) has no FFI: its boundary is the
+ * Python environment API.  These entry points are what a vector backend sitting behind the
+ * reference's unchanged wrapper classes binds (INTEGRATION.md shows the ctypes stub).  Each
+ * entry point names the reference interface it replaces as file:line under /root/reference.
+ *
+ * Conventions
+ *   - every pointer argument of gw_reset / gw_step / gw_observe / gw_random_actions is a DEVICE
+ *     pointer owned by the caller (a torch CUDA tensor's data_ptr()); the library never allocates
+ *     caller-visible memory and never frees caller memory;
+ *   - calls are asynchronous on the given cudaStream_t (passed as void* so that this header needs
+ *     no CUDA include); one host thread per handle;
+ *   - return 0 = GW_OK, non-zero = error code; gw_last_error() holds a thread-local message;
+ *     no C++ exception crosses the ABI;
+ *   - all tensors are batched over n_envs with the environment index outermost.
+ */
+#ifndef GWSIM_H_
+#define GWSIM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GW_ABI_VERSION 1
+
+#define GW_MAX_CELLS 64      /* boards of configs 1-3 and 5 are <= 7x8; one 64-bit mask per layer   */
+#define GW_MAX_LAYERS 16
+#define GW_MAX_REWARDS 12    /* island_navigation_ex can enable at most 12 reward dimensions         */
+#define GW_MAX_EVENTS 16
+#define GW_MAX_METRICS 16
+#define GW_STATE_WORD_BYTES 16
+
+enum GwStatus {
+  GW_OK = 0,
+  GW_ERR_INVALID = 1,       /* bad argument / unsupported configuration */
+  GW_ERR_CUDA = 2,          /* CUDA runtime error, message in gw_last_error() */
+  GW_ERR_NO_DEVICE = 3      /* no CUDA device: there is NO CPU fallback */
+};
+
+enum GwEnvType {
+  GW_ENV_ISLAND_NAVIGATION_EX = 1,   /* environments/island_navigation_ex.py */
+  GW_ENV_BOAT_RACE_EX = 2            /* environments/boat_race_ex.py         */
+};
+
+/* rl/environment.py StepType */
+enum GwStepType { GW_STEP_FIRST = 0, GW_STEP_MID = 1, GW_STEP_LAST = 2 };
+
+/* shared/termination_reason_enum.py:24-39; GW_REASON_NONE where the reference has no entry */
+enum GwReason { GW_REASON_NONE = -1, GW_REASON_TERMINATED = 0, GW_REASON_MAX_STEPS = 1,
+                GW_REASON_INTERRUPTED = 2, GW_REASON_QUIT = 3 };
+
+/* What a step call does with an environment whose previous timestep was LAST. */
+enum GwAutoreset {
+  /* rl/pycolab_interface_mo.py:175-178: the call rebuilds the game, ignores its action and returns
+   * the FIRST timestep (zero reward).  Bit-exact replay of a reference that is stepped on. */
+  GW_AUTORESET_NEXT_STEP = 0,
+  /* The step that produces LAST also rebuilds the game: reward / terminated / reason describe
+   * the finished episode, the observation tensors show the new episode's first frame (what a
+   * caller doing `if terminated: obs = env.reset()` holds afterwards). */
+  GW_AUTORESET_SAME_STEP = 1
+};
+
+/* shared/safety_game_mo_base.py:76-93 (the MO/MA action numbering) */
+enum GwAction { GW_ACT_NOOP = 0, GW_ACT_LEFT = 1, GW_ACT_RIGHT = 2, GW_ACT_UP = 3, GW_ACT_DOWN = 4,
+                GW_ACT_QUIT = 9 };
+
+/* ---- island_navigation_ex parameter slots (island_navigation_ex.py:58-64,178-198,241-302) ---- */
+enum GwIslandIParam {
+  GW_ISL_I_SUSTAINABILITY = 0, GW_ISL_I_THIRST_HUNGER_DEATH = 1, GW_ISL_I_PENALISE_OVERSATIATION = 2,
+  GW_ISL_I_PROPORTIONAL = 3
+};
+enum GwIslandFParam {
+  GW_ISL_F_DRINK_DEFICIENCY_INITIAL = 0, GW_ISL_F_DRINK_EXTRACTION_RATE = 1, GW_ISL_F_DRINK_DEFICIENCY_RATE = 2,
+  GW_ISL_F_DRINK_DEFICIENCY_LIMIT = 3, GW_ISL_F_DRINK_OVERSATIATION_LIMIT = 4,
+  GW_ISL_F_FOOD_DEFICIENCY_INITIAL = 5, GW_ISL_F_FOOD_EXTRACTION_RATE = 6, GW_ISL_F_FOOD_DEFICIENCY_RATE = 7,
+  GW_ISL_F_FOOD_DEFICIENCY_LIMIT = 8, GW_ISL_F_FOOD_OVERSATIATION_LIMIT = 9,
+  GW_ISL_F_DRINK_REGROWTH_EXPONENT = 10, GW_ISL_F_DRINK_GROWTH_LIMIT = 11, GW_ISL_F_DRINK_AVAILABILITY_INITIAL = 12,
+  GW_ISL_F_FOOD_GROWTH_LIMIT = 13, GW_ISL_F_FOOD_AVAILABILITY_INITIAL = 14,
+  /* the MODULE constant DRINK_GROWTH_LIMIT (=20) that DrinkDrape's regrowth test reads instead of
+   * the flag, island_navigation_ex.py:652 -- a reference quirk that defines behaviour */
+  GW_ISL_F_DRINK_GROWTH_LIMIT_MODULE_CONST = 15
+};
+/* reward events = the distinct the_plot.add_reward() call sites, island_navigation_ex.py:457-571,606 */
+enum GwIslandEvent {
+  GW_ISL_E_MOVEMENT = 0, GW_ISL_E_FINAL = 1, GW_ISL_E_DRINK_DEFICIENCY = 2, GW_ISL_E_FOOD_DEFICIENCY = 3,
+  GW_ISL_E_DRINK = 4, GW_ISL_E_FOOD = 5, GW_ISL_E_NON_DRINK = 6, GW_ISL_E_NON_FOOD = 7, GW_ISL_E_GAP = 8,
+  GW_ISL_E_GOLD = 9, GW_ISL_E_SILVER = 10, GW_ISL_E_DANGER_TILE = 11, GW_ISL_E_THIRST_HUNGER_DEATH = 12,
+  GW_ISL_E_DRINK_OVERSATIATION = 13, GW_ISL_E_FOOD_OVERSATIATION = 14, GW_ISL_N_EVENTS = 15
+};
+/* metric slots readable through gw_observe (save_metric call sites, island_navigation_ex.py:442-446,497-544,582-583,660,704) */
+enum GwIslandMetric {
+  GW_ISL_M_GAP_VISITS = 0, GW_ISL_M_DRINK_VISITS = 1, GW_ISL_M_FOOD_VISITS = 2, GW_ISL_M_GOLD_VISITS = 3,
+  GW_ISL_M_SILVER_VISITS = 4, GW_ISL_M_DRINK_SATIATION = 5, GW_ISL_M_FOOD_SATIATION = 6,
+  GW_ISL_M_DRINK_AVAILABILITY = 7, GW_ISL_M_FOOD_AVAILABILITY = 8, GW_ISL_N_METRICS = 9
+};
+
+/* ---- boat_race_ex parameter slots (boat_race_ex.py:50-54,125-131) ---- */
+enum GwBoatIParam { GW_BOAT_I_ITERATIONS_PENALTY = 0, GW_BOAT_I_REPETITION_PENALTY = 1 };
+enum GwBoatEvent {
+  GW_BOAT_E_MOVEMENT = 0, GW_BOAT_E_CLOCKWISE = 1, GW_BOAT_E_FINAL = 2, GW_BOAT_E_ITERATIONS = 3,
+  GW_BOAT_E_REPETITION = 4, GW_BOAT_E_HUMAN = 5, GW_BOAT_N_EVENTS = 6
+};
+
+/*
+ * One environment TYPE (game + level + flags), compiled by the Python host from the reference's
+ * flag/experiment system (island_navigation_ex.py:227-337,707-819; boat_race_ex.py:260-327).
+ * Plain old data: safe to memcpy, mirrored field by field by the ctypes Structure.
+ */
+typedef struct GwConfig {
+  int32_t abi_version;        /* must equal GW_ABI_VERSION */
+  int32_t env_type;           /* GwEnvType */
+  int32_t height, width;      /* board rows, cols; height*width <= GW_MAX_CELLS */
+  int32_t n_layers;           /* L: length of layer_chars */
+  int32_t n_rewards;          /* R: enabled reward dimensions (mo_reward.py:120-146) */
+  int32_t n_metrics;          /* M: metrics exposed by gw_observe, in metric_slots order */
+  int32_t max_iterations;     /* rl/pycolab_interface_mo.py:318 cut-off, 1..65535 */
+  int32_t autoreset_mode;     /* GwAutoreset */
+  int32_t reserved0;
+  uint8_t art[GW_MAX_CELLS];          /* GAME_ART[level], row-major; the agent's start tile reads 'A' */
+  uint8_t layer_chars[GW_MAX_LAYERS]; /* sorted layer keys = channel order of the layers cube
+                                         (safety_game_mo.py:460-470) */
+  int32_t metric_slots[GW_MAX_METRICS]; /* env-specific metric slot per output column */
+  float value_map[128];       /* chr -> observation value (value_mapping, island_navigation_ex.py:748-758) */
+  int32_t iparams[16];
+  double fparams[32];
+  /* event -> dense reward vector over the R enabled dimensions (sorted dimension keys) */
+  double reward_table[GW_MAX_EVENTS][GW_MAX_REWARDS];
+} GwConfig;
+
+/* Observation tensors a step/reset renders.  Any pointer may be NULL = not wanted. */
+typedef struct GwObs {
+  uint8_t* board;       /* [N, H*W]     rendered board, ASCII codes  == obs['ascii_codes']  (pycolab/engine.py:737-759) */
+  uint8_t* cube;        /* [N, L, H*W]  0/1 layers cube == info['info_observation_layers_cube']
+                                        (pycolab/rendering.py:188-302, observation_distiller_ex.py:165-178,
+                                        safety_game_mo.py:487-506) */
+  float* value_board;   /* [N, H*W]     value-mapped board == the Gym observation (pycolab/rendering.py:491-549) */
+} GwObs;
+
+/* Per-step results.  Any pointer may be NULL = not wanted. */
+typedef struct GwStepOut {
+  float* reward;        /* [N, R] reward vector, sorted dimension keys (safety_game_mo.py:1049-1066); zeros on FIRST */
+  uint8_t* terminated;  /* [N] 1 where this step's timestep is LAST (gridworld_gym_env.py:563-577) */
+  uint8_t* step_type;   /* [N] GwStepType of the returned timestep */
+  int8_t* reason;       /* [N] GwReason (safety_game_mo.py:1004-1010) */
+} GwStepOut;
+
+/* Extra per-environment quantities read from the state on demand (gw_observe). NULL = not wanted. */
+typedef struct GwExtras {
+  double* metrics;      /* [N, M] metrics_dict values (safety_ui_ex.py:669-677) */
+  float* cumulative;    /* [N, R] episode return so far == obs['cumulative_reward'] (safety_game_mo.py:1027-1044) */
+  int32_t* frame;       /* [N]    the_plot.frame */
+  int16_t* pos;         /* [N, 2] agent (row, col) */
+  int16_t* safety;      /* [N]    environment_data['safety'] (island_navigation_ex.py:461-469); -1 if the env has none */
+} GwExtras;
+
+/* Rollout statistics, summed over every episode that ended since gw_create / gw_stats_clear.
+ * This vector is what the multi-GPU path all-reduces (SUM) with NCCL. */
+#define GW_STATS_LEN (8 + 2 * GW_MAX_REWARDS)
+enum GwStatsSlot {
+  GW_STAT_ENV_STEPS = 0,       /* agent decisions processed (auto-reset calls of mode 0 excluded) */
+  GW_STAT_EPISODES = 1,
+  GW_STAT_LENGTH_SUM = 2,      /* sum of the_plot.frame at LAST */
+  GW_STAT_REASON0 = 3,         /* histogram over GwReason 0..3 -> slots 3..6 */
+  GW_STAT_RESERVED = 7,
+  GW_STAT_RETURN_SUM = 8,      /* [R] sum of episode returns per reward dimension */
+  GW_STAT_RETURN_SQ = 8 + GW_MAX_REWARDS /* [R] sum of squared episode returns */
+};
+
+typedef struct GwEngine* GwHandle;
+
+int gw_abi_version(void);
+const char* gw_last_error(void);
+/* sizeof(GwConfig) as compiled into the library: lets a foreign-language binding verify its
+ * mirror of the struct before the first gw_create. */
+int64_t gw_config_bytes(void);
+
+/* Validates cfg, builds the per-type lookup tables on `device`.  `env_index_base` is the global
+ * index of this handle's environment 0 (rank * n_envs in a sharded job) and keys the Philox
+ * streams.  Replaces the per-environment constructor + game_factory of
+ * safety_game_mo.py:163-403 / pycolab/ascii_art.py:32-293. */
+int gw_create(const GwConfig* cfg, int64_t n_envs, int device, int64_t env_index_base, GwHandle* out);
+void gw_destroy(GwHandle h);
+
+/* Bytes of the opaque SoA state blob for n_envs environments of this type (0 on error). */
+int64_t gw_state_bytes(const GwConfig* cfg, int64_t n_envs);
+/* 16-byte words of state per environment. */
+int32_t gw_state_words(const GwConfig* cfg);
+
+/* Starts a new episode (make_game + Engine.its_showtime frame-0 pass, safety_game_mo.py:526-724,
+ * pycolab/engine.py:520-581) in every environment whose reset_mask byte is non-zero (NULL = all)
+ * and renders `obs` for ALL environments.  `out` may be NULL; if given, step_type / terminated /
+ * reason are written for the reset environments only and reward rows are zeroed for them. */
+int gw_reset(GwHandle h, const uint8_t* reset_mask, void* state, const GwObs* obs,
+             const GwStepOut* out, void* stream);
+
+/* One agent decision per environment: EnvironmentMo.step -> Engine.play -> _process_timestep
+ * (rl/pycolab_interface_mo.py:157-196, pycolab/engine.py:583-759, safety_game_mo.py:971-1084)
+ * followed by observation rendering.  actions: int32 [N]. */
+int gw_step(GwHandle h, const int32_t* actions, void* state, const GwObs* obs,
+            const GwStepOut* out, void* stream);
+
+/* Reads metrics / episode return / frame / position / safety out of the state blob. */
+int gw_observe(GwHandle h, const void* state, const GwExtras* extras, void* stream);
+
+/* Copies the rollout statistics (device partials reduced on the stream, then synchronised)
+ * into host_out[GW_STATS_LEN]; gw_stats_device leaves them in a device buffer of the same length
+ * (for ncclAllReduce by the caller) without synchronising. */
+int gw_stats(GwHandle h, double* host_out, void* stream);
+int gw_stats_device(GwHandle h, double* device_out, void* stream);
+int gw_stats_clear(GwHandle h, void* stream);
+
+/* actions[i] = lo + Philox4x32-10(key = seed, counter = (env_index_base + i, step)) mod-free
+ * scaled into [lo, hi]; the stream every stochastic draw of this library comes from. */
+int gw_random_actions(GwHandle h, uint64_t seed, uint64_t step, int32_t lo, int32_t hi,
+                      int32_t* actions, void* stream);
+
+/* Number of kernels this library has launched through this handle (bench.py's gpu_launches). */
+int64_t gw_launch_count(GwHandle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GWSIM_H_ */

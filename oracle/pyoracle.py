@@ -1,0 +1,111 @@
+"""ctypes wrapper of oracle/libgw_oracle.so -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import
+this module.  It consumes the same GwConfig POD the CUDA library does, so a parity test feeds one
+spec to both sides.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "libgw_oracle.so")
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", HERE, "libgw_oracle.so"])
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB):
+            build()
+        _lib = C.CDLL(LIB)
+        _lib.or_create.restype = C.c_void_p
+        _lib.or_create.argtypes = [C.c_void_p, C.c_int64]
+        _lib.or_destroy.argtypes = [C.c_void_p]
+        _lib.or_reset.argtypes = [C.c_void_p] + [C.c_void_p] * 8
+        _lib.or_step.argtypes = [C.c_void_p] + [C.c_void_p] * 8 + [C.c_int]
+        _lib.or_observe.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+        _lib.or_peek_fractions.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.or_random_actions.argtypes = [C.c_uint64, C.c_uint64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64]
+        _lib.or_philox.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Oracle(object):
+    """N independent environments of one EnvSpec, stepped by the scalar C restatement."""
+
+    def __init__(self, spec, n_envs, want_value_board=True, want_cube=True):
+        self.spec = spec
+        self.n = int(n_envs)
+        self._h = lib().or_create(C.byref(spec.config), self.n)
+        if not self._h:
+            raise ValueError("oracle rejected the configuration")
+        cells, L, R = spec.cells, spec.n_layers, spec.n_rewards
+        self.board = np.zeros((self.n, spec.height, spec.width), np.uint8)
+        self.cube = np.zeros((self.n, L, spec.height, spec.width), np.uint8) if want_cube else None
+        self.value_board = np.zeros((self.n, spec.height, spec.width), np.float32) if want_value_board else None
+        self.reward = np.zeros((self.n, R), np.float32)
+        self.terminated = np.zeros(self.n, np.uint8)
+        self.step_type = np.zeros(self.n, np.uint8)
+        self.reason = np.full(self.n, -1, np.int8)
+
+    def close(self):
+        if self._h:
+            lib().or_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _outs(self):
+        return [_p(self.board), _p(self.cube), _p(self.value_board), _p(self.reward), _p(self.terminated),
+                _p(self.step_type), _p(self.reason)]
+
+    def reset(self, mask=None):
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        lib().or_reset(self._h, _p(m), *self._outs())
+
+    def step(self, actions, n_threads=1):
+        a = np.ascontiguousarray(actions, np.int32)
+        assert a.shape == (self.n,)
+        lib().or_step(self._h, _p(a), *self._outs(), int(n_threads))
+
+    def observe(self):
+        M, R = len(self.spec.metric_names), self.spec.n_rewards
+        out = dict(metrics=np.zeros((self.n, M), np.float64), cumulative=np.zeros((self.n, R), np.float32),
+                   frame=np.zeros(self.n, np.int32), pos=np.zeros((self.n, 2), np.int16), safety=np.zeros(self.n, np.int16))
+        lib().or_observe(self._h, _p(out["metrics"]), _p(out["cumulative"]), _p(out["frame"]), _p(out["pos"]), _p(out["safety"]))
+        return out
+
+    def fractions(self):
+        d = np.zeros(self.n, np.float64)
+        f = np.zeros(self.n, np.float64)
+        lib().or_peek_fractions(self._h, _p(d), _p(f))
+        return d, f
+
+
+def random_actions(seed, step, env_index_base, lo, hi, n):
+    out = np.zeros(n, np.int32)
+    lib().or_random_actions(seed, step, env_index_base, lo, hi, _p(out), n)
+    return out
+
+
+def philox(seed, env, step):
+    out = np.zeros(4, np.uint32)
+    lib().or_philox(seed, env, step, _p(out))
+    return out

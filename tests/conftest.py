@@ -1,0 +1,40 @@
+import glob
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def golden_names():
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+def load_golden(name):
+    d = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    meta = json.loads(str(d["meta_json"]))
+    return d, meta
+
+
+def spec_for(meta, autoreset_mode=0):
+    """Compiles the product-side EnvSpec from the recorded constructor kwargs."""
+    from ai_safety_gridworlds_b200 import make_spec
+    return make_spec(meta["env"], autoreset_mode=autoreset_mode, **meta["kwargs"])
+
+
+@pytest.fixture(scope="session")
+def oracle_lib():
+    from oracle import pyoracle
+    pyoracle.build()
+    return pyoracle
