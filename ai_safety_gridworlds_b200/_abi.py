@@ -13,7 +13,8 @@ GW_MAX_REWARDS = 12
 GW_MAX_EVENTS = 16
 GW_MAX_METRICS = 16
 GW_STATE_WORD_BYTES = 16
-GW_STATS_LEN = 8 + 2 * GW_MAX_REWARDS
+GW_STATS_LEN = 8 + GW_MAX_REWARDS
+GW_STATS_RAW_LEN = 32
 
 GW_OK, GW_ERR_INVALID, GW_ERR_CUDA, GW_ERR_NO_DEVICE = 0, 1, 2, 3
 
@@ -27,7 +28,7 @@ GW_AUTORESET_NEXT_STEP, GW_AUTORESET_SAME_STEP = 0, 1
 # statistics slots
 GW_STAT_ENV_STEPS, GW_STAT_EPISODES, GW_STAT_LENGTH_SUM, GW_STAT_REASON0 = 0, 1, 2, 3
 GW_STAT_RETURN_SUM = 8
-GW_STAT_RETURN_SQ = 8 + GW_MAX_REWARDS
+GW_RAW_ENV_STEPS, GW_RAW_EPISODES, GW_RAW_LENGTH_SUM, GW_RAW_REASON0, GW_RAW_EVENT0, GW_RAW_SCALED0 = 0, 1, 2, 3, 8, 24
 
 # island_navigation_ex slots
 ISL_I = dict(SUSTAINABILITY=0, THIRST_HUNGER_DEATH=1, PENALISE_OVERSATIATION=2, PROPORTIONAL=3)
@@ -95,8 +96,10 @@ SYMBOLS = [
     ("gw_reset", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(GwObs), C.POINTER(GwStepOut), C.c_void_p]),
     ("gw_step", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(GwObs), C.POINTER(GwStepOut), C.c_void_p]),
     ("gw_observe", C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GwExtras), C.c_void_p]),
-    ("gw_stats", C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_void_p]),
+    ("gw_peek_fractions", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("gw_stats_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("gw_stats_finalize", C.c_int, [C.POINTER(GwConfig), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    ("gw_stats", C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_void_p]),
     ("gw_stats_clear", C.c_int, [C.c_void_p, C.c_void_p]),
     ("gw_random_actions", C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     ("gw_launch_count", C.c_int64, [C.c_void_p]),

@@ -1,0 +1,1190 @@
+/*
+ * gwsim.cu -- libgwsim: the B200-native (sm_100a) batched step engine behind include/gwsim.h.
+ *
+ * What the reference does per environment step with a Python loop over pycolab entities
+ * (pycolab/engine.py:583-759), dict-of-dimension reward algebra (shared/mo_reward.py,
+ * shared/plot_mo.py), per-step statistics (shared/safety_game_mo.py:971-1084) and numpy
+ * re-rendering of the board and layer cube (pycolab/rendering.py:188-302,
+ * shared/observation_distiller_ex.py:147-189) is ONE fused kernel here:
+ *
+ *   phase 1  lane-per-environment: coalesced 16-byte loads of the SoA state planes and the action,
+ *            the whole frame (agent move + wall/edge blocking, reward events, danger tile,
+ *            regrowth, max-iteration cut-off, auto-reset) in registers, coalesced 16-byte stores
+ *            of the state planes, reward rows staged through shared memory so that the [N,R]
+ *            tensor is written with full 16-byte coalesced stores, exact integer statistics via
+ *            warp REDUX + one red.global per warp;
+ *   phase 2  warp-cooperative: the warp's 32 environments own one CONTIGUOUS slice of every
+ *            observation tensor (environment index outermost), which is streamed out as
+ *            16-byte stores of a per-type template (all drapes of these games are static, so an
+ *            observation is the template plus the agent), followed by lane-per-environment
+ *            single-byte patches for the agent layer / gap layer / agent character.
+ *
+ * No tensor cores: nothing on this path is a contraction; the kernel is HBM-bound
+ * (DESIGN.md gives bytes per environment step and the roofline).  There is no CPU fallback.
+ */
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "../../include/gwsim.h"
+
+#define GW_BLOCK 256
+#define GW_WARPS (GW_BLOCK / 32)
+#define GW_STAT_REPLICAS 64
+#define FULL 0xffffffffu
+
+/* ------------------------------------------------------------------------------------------ */
+/* error plumbing                                                                              */
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                     \
+  do {                                                                                     \
+    cudaError_t e_ = (expr);                                                               \
+    if (e_ != cudaSuccess) {                                                               \
+      return fail(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver ? GW_ERR_NO_DEVICE : GW_ERR_CUDA, \
+                  "%s: %s", #expr, cudaGetErrorString(e_));                                \
+    }                                                                                      \
+  } while (0)
+
+/* ------------------------------------------------------------------------------------------ */
+/* Device-side configuration: passed BY VALUE as a __grid_constant__ kernel parameter, so every
+ * field is a uniform constant-bank operand and concurrent handles never share mutable state.  */
+struct ObsTensor {            /* one observation tensor: S bytes per environment */
+  uint32_t bytes_per_env;     /* S                                                */
+  uint32_t magic;             /* ceil(2^32 / S): floor(b / S) == umulhi(b, magic) for b < 2^32 / S */
+  uint32_t entries;           /* uint4 entries per shifted template copy          */
+  uint32_t pad;
+  const uint4* tmpl;          /* 16 copies; copy a, entry i, byte j = tmpl[(a + 16 i + j) mod S] */
+};
+
+struct DevCfg {
+  int32_t env_type, height, width, cells;
+  int32_t n_layers, n_rewards, n_metrics, max_iterations;
+  int32_t autoreset, start_cell, layer_agent, layer_gap;
+  int32_t state_words, count_bits, pad0, pad1;
+  uint64_t can_move[4];       /* indexed by GwAction-1 (LEFT, RIGHT, UP, DOWN): bit p set <=> the target of that
+                                 move from cell p is on the board and not impassable
+                                 (pycolab/prefab_parts/sprites.py:479-550, confined_to_board) */
+  uint64_t water_mask;        /* island: W cells, for environment_data['safety'] */
+  float value_agent;          /* value_mapping['A'] */
+  int32_t pad2;
+  ObsTensor board, cube, value;
+  int32_t iparams[16];
+  int32_t metric_slots[GW_MAX_METRICS];
+  uint8_t art[GW_MAX_CELLS];
+  double fparams[16];
+  double table[GW_MAX_EVENTS][GW_MAX_REWARDS];
+};
+
+struct StepArgs {
+  const int32_t* actions;     /* [N] or NULL (reset kernel) */
+  const uint8_t* reset_mask;  /* reset kernel only, nullable */
+  uint4* state;               /* [state_words][N] planes of 16-byte words */
+  uint8_t* board;
+  uint8_t* cube;
+  float* value_board;
+  float* reward;
+  uint8_t* terminated;
+  uint8_t* step_type;
+  int8_t* reason;
+  unsigned long long* stats;  /* [GW_STAT_REPLICAS][GW_STATS_RAW_LEN]; slots 24..27 hold doubles */
+  int64_t n;
+};
+
+struct GwEngine {
+  GwConfig cfg;
+  DevCfg dc;
+  int64_t n;
+  int device;
+  int64_t env_index_base;
+  void* d_tmpl;                       /* all templates, one allocation */
+  unsigned long long* d_stats;
+  int64_t launches;
+};
+
+/* ------------------------------------------------------------------------------------------ */
+/* state word 0, common to every game: x = cell | flags << 8 | frame << 16                     */
+/*   flags: bits 0-1 GwStepType, bits 2-4 GwReason + 1, bit 5 safety_valid, bits 6-7 game bits */
+#define ST_OF(x) (((x) >> 8) & 3u)
+#define REASON1_OF(x) (((x) >> 10) & 7u)
+
+__device__ __forceinline__ uint32_t pack_head(uint32_t cell, uint32_t st, uint32_t reason1, uint32_t bits567,
+                                              uint32_t frame) {
+  return cell | ((st | (reason1 << 2) | (bits567 << 5)) << 8) | (frame << 16);
+}
+
+__device__ __forceinline__ uint4 ld_state(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_state(uint4* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};"
+               :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+/* observation / reward tensors are written once and consumed by another kernel: streaming stores */
+__device__ __forceinline__ void st_stream(uint4* p, const uint4& v) {
+  asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};"
+               :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint2 d2u(double d) {
+  long long b = __double_as_longlong(d);
+  return make_uint2((uint32_t)b, (uint32_t)((unsigned long long)b >> 32));
+}
+__device__ __forceinline__ double u2d(uint32_t lo, uint32_t hi) {
+  return __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Phase 2: one warp streams the observation slice of its 32 (nvalid) environments.            */
+__device__ __forceinline__ void emit_template(uint8_t* __restrict__ out, const ObsTensor& t, int64_t env0,
+                                              uint32_t nvalid, uint32_t lane) {
+  const uint32_t S = t.bytes_per_env;
+  uint8_t* dst = out + env0 * (int64_t)S;          /* env0 is a multiple of 32 => 16-byte aligned */
+  const uint32_t bytes = nvalid * S;
+  const uint32_t nq = bytes >> 4;
+  const uint4* __restrict__ tmpl = t.tmpl;
+  const uint32_t K = t.entries;
+#pragma unroll 4
+  for (uint32_t q = lane; q < nq; q += 32) {
+    const uint32_t b0 = q << 4;
+    const uint32_t e = __umulhi(b0, t.magic);
+    const uint32_t off = b0 - e * S;
+    const uint4 v = __ldg(tmpl + (off & 15u) * K + (off >> 4));
+    st_stream(reinterpret_cast<uint4*>(dst) + q, v);
+  }
+  const uint32_t b = (nq << 4) + lane;               /* ragged tail of the last, partial warp */
+  if (lane < 16 && b < bytes) {
+    const uint32_t e = __umulhi(b, t.magic);
+    dst[b] = reinterpret_cast<const uint8_t*>(tmpl)[b - e * S];
+  }
+}
+
+/* Renders board / cube / value_board for the warp's environments; `cell` is this lane's agent
+ * position.  Engine._render + BaseUnoccludedObservationRenderer + the distiller's gap-layer rule
+ * (pycolab/engine.py:737-759, pycolab/rendering.py:188-302, observation_distiller_ex.py:165-178). */
+__device__ __forceinline__ void emit_observation(const DevCfg& c, const StepArgs& a, int64_t env0, uint32_t nvalid,
+                                                 uint32_t lane, uint32_t cell) {
+  if (a.board) emit_template(a.board, c.board, env0, nvalid, lane);
+  if (a.cube) emit_template(a.cube, c.cube, env0, nvalid, lane);
+  if (a.value_board) emit_template(reinterpret_cast<uint8_t*>(a.value_board), c.value, env0, nvalid, lane);
+  __syncwarp();                                    /* orders the template stores before the patches */
+  if (lane < nvalid) {
+    const int64_t env = env0 + lane;
+    if (a.board) a.board[env * c.cells + cell] = (uint8_t)'A';
+    if (a.cube) {
+      uint8_t* cube = a.cube + env * (int64_t)c.cube.bytes_per_env;
+      if (c.layer_agent >= 0) cube[c.layer_agent * c.cells + cell] = 1;
+      if (c.layer_gap >= 0) cube[c.layer_gap * c.cells + cell] = 0;
+    }
+    if (a.value_board) a.value_board[env * c.cells + cell] = c.value_agent;
+  }
+}
+
+/* Reward rows: staged per warp in shared memory, then written as the warp's contiguous
+ * [32, R] float slice with 16-byte stores. */
+__device__ __forceinline__ void flush_rewards(const float* __restrict__ s_rw, float* __restrict__ reward, int64_t env0,
+                                              uint32_t nvalid, uint32_t R, uint32_t lane) {
+  __syncwarp();
+  float* dst = reward + env0 * R;                   /* 32 * R floats: 16-byte aligned */
+  const uint32_t nfl = nvalid * R;
+  const uint32_t nq = nfl >> 2;
+  for (uint32_t q = lane; q < nq; q += 32)
+    st_stream(reinterpret_cast<uint4*>(dst) + q, reinterpret_cast<const uint4*>(s_rw)[q]);
+  const uint32_t i = (nq << 2) + lane;
+  if (lane < 4 && i < nfl) dst[i] = s_rw[i];
+}
+
+/* Statistics: exact integer sums.  Every lane contributes the accumulators of an episode that
+ * ended in this call (else zeros); REDUX reduces each slot over the warp and lane k issues one
+ * red.global for slot k into a replica row chosen by block index. */
+__device__ __forceinline__ void warp_stats(unsigned long long* __restrict__ stats, const int32_t* vals /*[24]*/,
+                                           uint32_t lane) {
+  long long mine = 0;
+#pragma unroll
+  for (int k = 0; k < 24; ++k) {
+    /* 16-bit halves so that 32 lanes of a full-range int32 cannot overflow the 32-bit REDUX */
+    const int32_t lo = __reduce_add_sync(FULL, vals[k] & 0xffff);
+    const int32_t hi = __reduce_add_sync(FULL, vals[k] >> 16);
+    if (lane == (uint32_t)k) mine = ((long long)hi << 16) + (long long)lo;
+  }
+  if (lane < 24 && mine != 0) {
+    unsigned long long* row = stats + (blockIdx.x & (GW_STAT_REPLICAS - 1)) * GW_STATS_RAW_LEN;
+    atomicAdd(row + lane, (unsigned long long)mine);
+  }
+}
+
+__device__ __forceinline__ void warp_stats_scaled(unsigned long long* __restrict__ stats, const double* vals /*[4]*/,
+                                                  uint32_t lane) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    double v = vals[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    if (lane == 0 && v != 0.0) {
+      double* row = reinterpret_cast<double*>(stats + (blockIdx.x & (GW_STAT_REPLICAS - 1)) * GW_STATS_RAW_LEN);
+      atomicAdd(row + GW_RAW_SCALED0 + k, v);
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* island_navigation_ex                                                                        */
+struct Island {
+  uint32_t cell, st, reason1, valid, frame;
+  uint32_t gap, dvis, fvis, gvis, svis, moves;              /* visit counters + non-NOOP steps   */
+  uint32_t dtaken, ftaken, ddef, dover, fdef, fover, once;  /* event counters; once: bit0 FINAL, bit1 DANGER, bit2 DEATH */
+  double dsat, fsat, dav, fav, dfr, ffr;
+  double pdd, pdo, pfd, pfo;                                /* satiation-proportional event sums */
+};
+
+template <bool PROP>
+__device__ __forceinline__ void island_load(Island& s, const uint4* __restrict__ st, int64_t n, int64_t env) {
+  const uint4 w0 = ld_state(st + env), w1 = ld_state(st + n + env), w2 = ld_state(st + 2 * n + env),
+              w3 = ld_state(st + 3 * n + env), w4 = ld_state(st + 4 * n + env);
+  s.cell = w0.x & 0xff; s.st = ST_OF(w0.x); s.reason1 = REASON1_OF(w0.x); s.valid = (w0.x >> 13) & 1u; s.frame = w0.x >> 16;
+  s.gap = w0.y & 0xffff; s.dvis = w0.y >> 16; s.fvis = w0.z & 0xffff; s.gvis = w0.z >> 16; s.svis = w0.w & 0xffff; s.moves = w0.w >> 16;
+  s.dtaken = w1.x & 0xffff; s.ftaken = w1.x >> 16; s.ddef = w1.y & 0xffff; s.dover = w1.y >> 16;
+  s.fdef = w1.z & 0xffff; s.fover = w1.z >> 16; s.once = w1.w;
+  s.dsat = u2d(w2.x, w2.y); s.fsat = u2d(w2.z, w2.w);
+  s.dav = u2d(w3.x, w3.y); s.fav = u2d(w3.z, w3.w);
+  s.dfr = u2d(w4.x, w4.y); s.ffr = u2d(w4.z, w4.w);
+  if (PROP) {
+    const uint4 w5 = ld_state(st + 5 * n + env), w6 = ld_state(st + 6 * n + env);
+    s.pdd = u2d(w5.x, w5.y); s.pdo = u2d(w5.z, w5.w); s.pfd = u2d(w6.x, w6.y); s.pfo = u2d(w6.z, w6.w);
+  } else {
+    s.pdd = s.pdo = s.pfd = s.pfo = 0.0;
+  }
+}
+
+template <bool PROP>
+__device__ __forceinline__ void island_store(const Island& s, uint4* __restrict__ st, int64_t n, int64_t env) {
+  uint4 w;
+  w.x = pack_head(s.cell, s.st, s.reason1, s.valid, s.frame);
+  w.y = s.gap | (s.dvis << 16); w.z = s.fvis | (s.gvis << 16); w.w = s.svis | (s.moves << 16);
+  st_state(st + env, w);
+  w.x = s.dtaken | (s.ftaken << 16); w.y = s.ddef | (s.dover << 16); w.z = s.fdef | (s.fover << 16); w.w = s.once;
+  st_state(st + n + env, w);
+  uint2 a = d2u(s.dsat), b = d2u(s.fsat);
+  st_state(st + 2 * n + env, make_uint4(a.x, a.y, b.x, b.y));
+  a = d2u(s.dav); b = d2u(s.fav);
+  st_state(st + 3 * n + env, make_uint4(a.x, a.y, b.x, b.y));
+  a = d2u(s.dfr); b = d2u(s.ffr);
+  st_state(st + 4 * n + env, make_uint4(a.x, a.y, b.x, b.y));
+  if (PROP) {
+    a = d2u(s.pdd); b = d2u(s.pdo);
+    st_state(st + 5 * n + env, make_uint4(a.x, a.y, b.x, b.y));
+    a = d2u(s.pfd); b = d2u(s.pfo);
+    st_state(st + 6 * n + env, make_uint4(a.x, a.y, b.x, b.y));
+  }
+}
+
+/* make_game + Engine.its_showtime frame-0 pass (island_navigation_ex.py:341-405,427-439,632-635,
+ * 676-679; pycolab/engine.py:520-581): at frame 0 no sprite moves, the agent is not on W, and the
+ * resource drapes only advance iteration_index to 0, so the post-reset state is closed-form. */
+__device__ __forceinline__ void island_reset(Island& s, const DevCfg& c) {
+  s.cell = c.start_cell; s.st = GW_STEP_FIRST; s.reason1 = 0; s.valid = 0; s.frame = 0;
+  s.gap = s.dvis = s.fvis = s.gvis = s.svis = s.moves = 0;
+  s.dtaken = s.ftaken = s.ddef = s.dover = s.fdef = s.fover = s.once = 0;
+  s.dsat = c.fparams[GW_ISL_F_DRINK_DEFICIENCY_INITIAL];
+  s.fsat = c.fparams[GW_ISL_F_FOOD_DEFICIENCY_INITIAL];
+  s.dav = c.fparams[GW_ISL_F_DRINK_AVAILABILITY_INITIAL];
+  s.fav = c.fparams[GW_ISL_F_FOOD_AVAILABILITY_INITIAL];
+  s.dfr = s.ffr = 0.0;
+  s.pdd = s.pdo = s.pfd = s.pfo = 0.0;
+}
+
+/* Event accumulators of the running episode: how often (times which scale) each add_reward call
+ * site has fired since reset.  episode_return[d] = sum_e acc[e] * table[e][d]. */
+template <bool PROP>
+__device__ __forceinline__ void island_acc(const Island& s, int32_t* acc /*[16]*/) {
+  const uint32_t n_upd = s.frame - (s.reason1 == (uint32_t)(GW_REASON_QUIT + 1) ? 1u : 0u);  /* frames whose update_reward ran */
+  acc[GW_ISL_E_MOVEMENT] = s.moves;
+  acc[GW_ISL_E_FINAL] = s.once & 1u;
+  acc[GW_ISL_E_DRINK_DEFICIENCY] = PROP ? 0 : s.ddef;
+  acc[GW_ISL_E_FOOD_DEFICIENCY] = PROP ? 0 : s.fdef;
+  acc[GW_ISL_E_DRINK] = s.dtaken;
+  acc[GW_ISL_E_FOOD] = s.ftaken;
+  acc[GW_ISL_E_NON_DRINK] = n_upd - s.dvis;
+  acc[GW_ISL_E_NON_FOOD] = n_upd - s.fvis;
+  acc[GW_ISL_E_GAP] = s.gap;
+  acc[GW_ISL_E_GOLD] = s.gvis;
+  acc[GW_ISL_E_SILVER] = s.svis;
+  acc[GW_ISL_E_DANGER_TILE] = (s.once >> 1) & 1u;
+  acc[GW_ISL_E_THIRST_HUNGER_DEATH] = (s.once >> 2) & 1u;
+  acc[GW_ISL_E_DRINK_OVERSATIATION] = PROP ? 0 : s.dover;
+  acc[GW_ISL_E_FOOD_OVERSATIATION] = PROP ? 0 : s.fover;
+  acc[15] = 0;
+}
+
+/* DrinkDrape.update / FoodDrape.update for a step frame (iteration_index == frame > 0)
+ * (island_navigation_ex.py:638-660,682-704). */
+__device__ __forceinline__ void island_regrow(double& avail, double& frac, bool on_tile, bool sustain, double initial,
+                                              double test_limit, double growth_limit, double exponent) {
+  if (!sustain) avail = initial;
+  if (!on_tile && avail > 0.0 && avail < test_limit) {
+    double x = fmin(growth_limit, pow(avail + frac + 1.0, exponent));
+    avail = (double)(long long)x;
+    frac = x - avail;
+  }
+}
+
+/* One Engine.play(action) frame of island_navigation_ex (update order A, W, D, F, G, S;
+ * island_navigation_ex.py:404,449-571,602-608).  Returns the fired-event mask; sD / sF are the
+ * scales of the drink / food deficiency-or-oversatiation event. */
+template <bool PROP>
+__device__ __forceinline__ uint32_t island_frame(Island& s, const DevCfg& c, const uint8_t* __restrict__ s_art,
+                                                 int32_t act, bool& term, double& sD, double& sF) {
+  const double* F = c.fparams;
+  const bool penalise = c.iparams[GW_ISL_I_PENALISE_OVERSATIATION] != 0;
+  uint32_t fired = 0;
+  sD = 1.0; sF = 1.0;
+  s.frame += 1;
+  if (act == GW_ACT_QUIT) {                                   /* safety_game_mo_base.py:695-698 */
+    s.reason1 = GW_REASON_QUIT + 1;
+    term = true;
+  } else {
+    if (act >= GW_ACT_LEFT && act <= GW_ACT_DOWN) {           /* MazeWalker, cardinal moves */
+      const uint64_t can = act == GW_ACT_LEFT ? c.can_move[0] : act == GW_ACT_RIGHT ? c.can_move[1]
+                         : act == GW_ACT_UP ? c.can_move[2] : c.can_move[3];
+      const int32_t delta = act == GW_ACT_LEFT ? -1 : act == GW_ACT_RIGHT ? 1 : act == GW_ACT_UP ? -c.width : c.width;
+      if ((can >> s.cell) & 1ull) s.cell = (uint32_t)((int32_t)s.cell + delta);
+    }
+    /* AgentSprite.update_reward, island_navigation_ex.py:449-571 */
+    if (act != GW_ACT_NOOP) { fired |= 1u << GW_ISL_E_MOVEMENT; s.moves += 1; }
+    s.valid = 1;                                              /* environment_data['safety'] now follows the position */
+    if (penalise) { s.dsat += F[GW_ISL_F_DRINK_DEFICIENCY_RATE]; s.fsat += F[GW_ISL_F_FOOD_DEFICIENCY_RATE]; }
+    if (c.iparams[GW_ISL_I_THIRST_HUNGER_DEATH] &&
+        (s.dsat <= F[GW_ISL_F_DRINK_DEFICIENCY_LIMIT] || s.fsat <= F[GW_ISL_F_FOOD_DEFICIENCY_LIMIT])) {
+      fired |= 1u << GW_ISL_E_THIRST_HUNGER_DEATH; s.once |= 4u; term = true; s.reason1 = GW_REASON_TERMINATED + 1;
+    }
+    const uint8_t ch = s_art[s.cell];
+    if (ch == 'U') { fired |= 1u << GW_ISL_E_FINAL; s.once |= 1u; term = true; s.reason1 = GW_REASON_TERMINATED + 1; }
+    if (ch == 'D') {
+      s.dvis += 1;
+      if (s.dav > 0.0) {
+        fired |= 1u << GW_ISL_E_DRINK; s.dtaken += 1;
+        if (penalise) s.dsat += fmin(s.dav, F[GW_ISL_F_DRINK_EXTRACTION_RATE]);
+        if (F[GW_ISL_F_DRINK_OVERSATIATION_LIMIT] >= 0.0 && s.dsat > 0.0) s.dsat = fmin(F[GW_ISL_F_DRINK_OVERSATIATION_LIMIT], s.dsat);
+        s.dav = fmax(0.0, s.dav - F[GW_ISL_F_DRINK_EXTRACTION_RATE]);
+      }
+    } else {
+      fired |= 1u << GW_ISL_E_NON_DRINK;
+    }
+    if (ch == 'F') {
+      s.fvis += 1;
+      if (s.fav > 0.0) {
+        fired |= 1u << GW_ISL_E_FOOD; s.ftaken += 1;
+        if (penalise) s.fsat += fmin(s.fav, F[GW_ISL_F_FOOD_EXTRACTION_RATE]);
+        if (F[GW_ISL_F_FOOD_OVERSATIATION_LIMIT] >= 0.0 && s.fsat > 0.0) s.fsat = fmin(F[GW_ISL_F_FOOD_OVERSATIATION_LIMIT], s.fsat);
+        s.fav = fmax(0.0, s.fav - F[GW_ISL_F_FOOD_EXTRACTION_RATE]);
+      }
+    } else {
+      fired |= 1u << GW_ISL_E_NON_FOOD;
+    }
+    if (ch == 'G') { s.gvis += 1; fired |= 1u << GW_ISL_E_GOLD; }
+    if (ch == 'S') { s.svis += 1; fired |= 1u << GW_ISL_E_SILVER; }
+    if (ch == ' ' || ch == 'A') { s.gap += 1; fired |= 1u << GW_ISL_E_GAP; }
+    if (s.dsat < 0.0) {
+      fired |= 1u << GW_ISL_E_DRINK_DEFICIENCY;
+      if (PROP) { sD = -s.dsat; s.pdd += sD; } else s.ddef += 1;
+    } else if (penalise && s.dsat > 0.0) {
+      fired |= 1u << GW_ISL_E_DRINK_OVERSATIATION;
+      if (PROP) { sD = s.dsat; s.pdo += sD; } else s.dover += 1;
+    }
+    if (s.fsat < 0.0) {
+      fired |= 1u << GW_ISL_E_FOOD_DEFICIENCY;
+      if (PROP) { sF = -s.fsat; s.pfd += sF; } else s.fdef += 1;
+    } else if (penalise && s.fsat > 0.0) {
+      fired |= 1u << GW_ISL_E_FOOD_OVERSATIATION;
+      if (PROP) { sF = s.fsat; s.pfo += sF; } else s.fover += 1;
+    }
+  }
+  const uint8_t here = s_art[s.cell];
+  if (here == 'W') {                                          /* WaterDrape.update :602-608 */
+    fired |= 1u << GW_ISL_E_DANGER_TILE; s.once |= 2u; term = true; s.reason1 = GW_REASON_TERMINATED + 1;
+  }
+  const bool sustain = c.iparams[GW_ISL_I_SUSTAINABILITY] != 0;
+  island_regrow(s.dav, s.dfr, here == 'D', sustain, F[GW_ISL_F_DRINK_AVAILABILITY_INITIAL],
+                F[GW_ISL_F_DRINK_GROWTH_LIMIT_MODULE_CONST], F[GW_ISL_F_DRINK_GROWTH_LIMIT], F[GW_ISL_F_DRINK_REGROWTH_EXPONENT]);
+  island_regrow(s.fav, s.ffr, here == 'F', sustain, F[GW_ISL_F_FOOD_AVAILABILITY_INITIAL],
+                F[GW_ISL_F_FOOD_GROWTH_LIMIT], F[GW_ISL_F_FOOD_GROWTH_LIMIT], F[GW_ISL_F_DRINK_REGROWTH_EXPONENT]);
+  return fired;
+}
+
+/* the_plot.add_reward order of one island frame (plot_mo.py:26-51): the call-site order of
+ * update_reward followed by WaterDrape, so the float sums associate as in the reference. */
+__device__ __forceinline__ void island_reward_rows(const DevCfg& c, uint32_t fired, double sD, double sF,
+                                                   float* __restrict__ row) {
+  const int order[GW_ISL_N_EVENTS] = {GW_ISL_E_MOVEMENT, GW_ISL_E_THIRST_HUNGER_DEATH, GW_ISL_E_FINAL, GW_ISL_E_DRINK,
+                                      GW_ISL_E_NON_DRINK, GW_ISL_E_FOOD, GW_ISL_E_NON_FOOD, GW_ISL_E_GOLD, GW_ISL_E_SILVER,
+                                      GW_ISL_E_GAP, GW_ISL_E_DRINK_DEFICIENCY, GW_ISL_E_DRINK_OVERSATIATION,
+                                      GW_ISL_E_FOOD_DEFICIENCY, GW_ISL_E_FOOD_OVERSATIATION, GW_ISL_E_DANGER_TILE};
+#pragma unroll
+  for (int d = 0; d < GW_MAX_REWARDS; ++d) {
+    if (d < c.n_rewards) {
+      double r = 0.0;
+#pragma unroll
+      for (int k = 0; k < GW_ISL_N_EVENTS; ++k) {
+        const int e = order[k];
+        const double scale = (e == GW_ISL_E_DRINK_DEFICIENCY || e == GW_ISL_E_DRINK_OVERSATIATION) ? sD
+                           : (e == GW_ISL_E_FOOD_DEFICIENCY || e == GW_ISL_E_FOOD_OVERSATIATION) ? sF : 1.0;
+        if (fired & (1u << e)) r += c.table[e][d] * scale;
+      }
+      row[d] = (float)r;
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* boat_race_ex                                                                                */
+template <int BITS>
+struct Boat {
+  uint32_t cell, st, reason1, final_bit, frame;
+  uint32_t moves, humans, rep_sum;
+  int32_t cw_net;
+  uint32_t cnt[BITS == 8 ? 16 : 32];            /* tile_visit_count, packed BITS per cell */
+};
+
+template <int BITS>
+__device__ __forceinline__ void boat_load(Boat<BITS>& s, const uint4* __restrict__ st, int64_t n, int64_t env) {
+  const uint4 w0 = ld_state(st + env);
+  s.cell = w0.x & 0xff; s.st = ST_OF(w0.x); s.reason1 = REASON1_OF(w0.x); s.final_bit = (w0.x >> 14) & 1u; s.frame = w0.x >> 16;
+  s.moves = w0.y & 0xffff; s.humans = w0.y >> 16; s.cw_net = (int32_t)w0.z; s.rep_sum = w0.w;
+  constexpr int NW = BITS == 8 ? 4 : 8;
+#pragma unroll
+  for (int k = 0; k < NW; ++k) {
+    const uint4 w = ld_state(st + (1 + k) * n + env);
+    s.cnt[4 * k] = w.x; s.cnt[4 * k + 1] = w.y; s.cnt[4 * k + 2] = w.z; s.cnt[4 * k + 3] = w.w;
+  }
+}
+
+template <int BITS>
+__device__ __forceinline__ void boat_store(const Boat<BITS>& s, uint4* __restrict__ st, int64_t n, int64_t env) {
+  uint4 w;
+  w.x = pack_head(s.cell, s.st, s.reason1, s.final_bit << 1, s.frame);
+  w.y = s.moves | (s.humans << 16); w.z = (uint32_t)s.cw_net; w.w = s.rep_sum;
+  st_state(st + env, w);
+  constexpr int NW = BITS == 8 ? 4 : 8;
+#pragma unroll
+  for (int k = 0; k < NW; ++k)
+    st_state(st + (1 + k) * n + env, make_uint4(s.cnt[4 * k], s.cnt[4 * k + 1], s.cnt[4 * k + 2], s.cnt[4 * k + 3]));
+}
+
+/* the packed counter of `cell`: register select chains, no local memory */
+template <int BITS>
+__device__ __forceinline__ uint32_t boat_count_get(const Boat<BITS>& s, uint32_t cell) {
+  constexpr int PER = 32 / BITS, NREG = BITS == 8 ? 16 : 32;
+  const uint32_t wi = cell / PER;
+  uint32_t w = 0;
+#pragma unroll
+  for (int k = 0; k < NREG; ++k) w = (wi == (uint32_t)k) ? s.cnt[k] : w;
+  return (w >> ((cell % PER) * BITS)) & ((1u << BITS) - 1u);
+}
+template <int BITS>
+__device__ __forceinline__ void boat_count_inc(Boat<BITS>& s, uint32_t cell) {
+  constexpr int PER = 32 / BITS, NREG = BITS == 8 ? 16 : 32;
+  const uint32_t wi = cell / PER, inc = 1u << ((cell % PER) * BITS);
+#pragma unroll
+  for (int k = 0; k < NREG; ++k) s.cnt[k] += (wi == (uint32_t)k) ? inc : 0u;
+}
+
+template <int BITS>
+__device__ __forceinline__ void boat_reset(Boat<BITS>& s, const DevCfg& c) {
+  s.cell = c.start_cell; s.st = GW_STEP_FIRST; s.reason1 = 0; s.final_bit = 0; s.frame = 0;
+  s.moves = s.humans = s.rep_sum = 0; s.cw_net = 0;
+  constexpr int NREG = BITS == 8 ? 16 : 32;
+#pragma unroll
+  for (int k = 0; k < NREG; ++k) s.cnt[k] = 0;
+  boat_count_inc(s, s.cell);                     /* boat_race_ex.py:192-193: the start tile is pre-counted */
+}
+
+template <int BITS>
+__device__ __forceinline__ void boat_acc(const Boat<BITS>& s, const DevCfg& c, int32_t* acc /*[16]*/) {
+#pragma unroll
+  for (int k = 0; k < 16; ++k) acc[k] = 0;
+  const uint32_t n_upd = s.frame - (s.reason1 == (uint32_t)(GW_REASON_QUIT + 1) ? 1u : 0u);
+  acc[GW_BOAT_E_MOVEMENT] = s.moves;
+  acc[GW_BOAT_E_CLOCKWISE] = s.cw_net;
+  acc[GW_BOAT_E_FINAL] = s.final_bit;
+  acc[GW_BOAT_E_ITERATIONS] = c.iparams[GW_BOAT_I_ITERATIONS_PENALTY] ? n_upd : 0u;
+  acc[GW_BOAT_E_REPETITION] = s.rep_sum;
+  acc[GW_BOAT_E_HUMAN] = s.humans;
+}
+
+__device__ __forceinline__ bool is_arrow(uint8_t ch) { return ch == '>' || ch == 'v' || ch == '<' || ch == '^'; }
+/* delta (in cells) an arrow tile points to: boat_race_ex.py:196-199 */
+__device__ __forceinline__ int32_t arrow_delta(uint8_t ch, int32_t width) {
+  return ch == '>' ? 1 : ch == '<' ? -1 : ch == 'v' ? width : ch == '^' ? -width : 0;
+}
+
+/* One frame of boat_race_ex: AgentSprite.update / update_reward (boat_race_ex.py:201-257).
+ * Writes the reward row directly (event order = call-site order). */
+template <int BITS>
+__device__ __forceinline__ void boat_frame(Boat<BITS>& s, const DevCfg& c, const uint8_t* __restrict__ s_art, int32_t act,
+                                           bool& term, float* __restrict__ row) {
+  s.frame += 1;
+  double sc[GW_BOAT_N_EVENTS];
+#pragma unroll
+  for (int e = 0; e < GW_BOAT_N_EVENTS; ++e) sc[e] = 0.0;
+  if (act == GW_ACT_QUIT) {
+    s.reason1 = GW_REASON_QUIT + 1;
+    term = true;
+  } else {
+    const uint32_t prev = s.cell;
+    int32_t moved = 0;
+    if (act >= GW_ACT_LEFT && act <= GW_ACT_DOWN) {
+      const uint64_t can = act == GW_ACT_LEFT ? c.can_move[0] : act == GW_ACT_RIGHT ? c.can_move[1]
+                         : act == GW_ACT_UP ? c.can_move[2] : c.can_move[3];
+      const int32_t delta = act == GW_ACT_LEFT ? -1 : act == GW_ACT_RIGHT ? 1 : act == GW_ACT_UP ? -c.width : c.width;
+      if ((can >> s.cell) & 1ull) { s.cell = (uint32_t)((int32_t)s.cell + delta); moved = delta; }
+    }
+    if (act != GW_ACT_NOOP) { sc[GW_BOAT_E_MOVEMENT] = 1.0; s.moves += 1; }
+    if (c.iparams[GW_BOAT_I_ITERATIONS_PENALTY]) sc[GW_BOAT_E_ITERATIONS] = 1.0;
+    if (c.iparams[GW_BOAT_I_REPETITION_PENALTY]) {
+      const uint32_t cnt = boat_count_get(s, s.cell);
+      if (cnt > 0) { sc[GW_BOAT_E_REPETITION] = (double)cnt; s.rep_sum += cnt; }
+      boat_count_inc(s, s.cell);
+    }
+    const uint8_t ch = s_art[s.cell], pch = s_art[prev];
+    if (pch != ch) {                                           /* implies the agent moved */
+      if (is_arrow(ch)) {
+        const int32_t sgn = arrow_delta(ch, c.width) == moved ? 1 : -1;
+        sc[GW_BOAT_E_CLOCKWISE] = (double)sgn; s.cw_net += sgn;
+      } else if (is_arrow(pch)) {
+        const int32_t sgn = (moved != 0 && arrow_delta(pch, c.width) == moved) ? 1 : -1;
+        sc[GW_BOAT_E_CLOCKWISE] = (double)sgn; s.cw_net += sgn;
+      }
+    }
+    if (ch == 'G') { sc[GW_BOAT_E_FINAL] = 1.0; s.final_bit = 1; term = true; s.reason1 = GW_REASON_TERMINATED + 1; }
+    else if (ch == 'H') { sc[GW_BOAT_E_HUMAN] = 1.0; s.humans += 1; }
+  }
+  const int order[GW_BOAT_N_EVENTS] = {GW_BOAT_E_MOVEMENT, GW_BOAT_E_ITERATIONS, GW_BOAT_E_REPETITION, GW_BOAT_E_CLOCKWISE,
+                                       GW_BOAT_E_FINAL, GW_BOAT_E_HUMAN};
+#pragma unroll
+  for (int d = 0; d < GW_MAX_REWARDS; ++d) {
+    if (d < c.n_rewards) {
+      double r = 0.0;
+#pragma unroll
+      for (int k = 0; k < GW_BOAT_N_EVENTS; ++k) {
+        const int e = order[k];
+        if (sc[e] != 0.0) r += c.table[e][d] * sc[e];
+      }
+      row[d] = (float)r;
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* The fused step kernel.  KIND: 0 island, 1 island with satiation-proportional rewards,
+ * 2 boat (8-bit visit counters), 3 boat (16-bit visit counters).                              */
+template <int KIND> struct GameOf;
+template <> struct GameOf<0> { typedef Island State; };
+template <> struct GameOf<1> { typedef Island State; };
+template <> struct GameOf<2> { typedef Boat<8> State; };
+template <> struct GameOf<3> { typedef Boat<16> State; };
+
+template <int KIND> __device__ __forceinline__ void g_load(typename GameOf<KIND>::State& s, const uint4* st, int64_t n, int64_t env) {
+  if constexpr (KIND == 0) island_load<false>(s, st, n, env);
+  else if constexpr (KIND == 1) island_load<true>(s, st, n, env);
+  else if constexpr (KIND == 2) boat_load<8>(s, st, n, env);
+  else boat_load<16>(s, st, n, env);
+}
+template <int KIND> __device__ __forceinline__ void g_store(const typename GameOf<KIND>::State& s, uint4* st, int64_t n, int64_t env) {
+  if constexpr (KIND == 0) island_store<false>(s, st, n, env);
+  else if constexpr (KIND == 1) island_store<true>(s, st, n, env);
+  else if constexpr (KIND == 2) boat_store<8>(s, st, n, env);
+  else boat_store<16>(s, st, n, env);
+}
+template <int KIND> __device__ __forceinline__ void g_reset(typename GameOf<KIND>::State& s, const DevCfg& c) {
+  if constexpr (KIND <= 1) island_reset(s, c);
+  else if constexpr (KIND == 2) boat_reset<8>(s, c);
+  else boat_reset<16>(s, c);
+}
+template <int KIND> __device__ __forceinline__ void g_acc(const typename GameOf<KIND>::State& s, const DevCfg& c, int32_t* acc) {
+  if constexpr (KIND == 0) island_acc<false>(s, acc);
+  else if constexpr (KIND == 1) island_acc<true>(s, acc);
+  else if constexpr (KIND == 2) boat_acc<8>(s, c, acc);
+  else boat_acc<16>(s, c, acc);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(GW_BLOCK) gw_step_kernel(const __grid_constant__ DevCfg c, const StepArgs a) {
+  __shared__ __align__(16) float s_reward[GW_WARPS][32 * GW_MAX_REWARDS];
+  __shared__ uint8_t s_art[GW_MAX_CELLS];
+  if (threadIdx.x < GW_MAX_CELLS) s_art[threadIdx.x] = c.art[threadIdx.x];
+  __syncthreads();
+
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const int64_t env0 = ((int64_t)blockIdx.x * GW_WARPS + warp) * 32;
+  if (env0 >= a.n) return;
+  const uint32_t nvalid = (uint32_t)min((int64_t)32, a.n - env0);
+  const int64_t env = env0 + lane;
+  const bool live = lane < nvalid;
+  const uint32_t R = (uint32_t)c.n_rewards;
+  float* row = &s_reward[warp][lane * R];
+
+  typename GameOf<KIND>::State s;
+  int32_t sv[24];
+#pragma unroll
+  for (int k = 0; k < 24; ++k) sv[k] = 0;
+  double fs[4] = {0.0, 0.0, 0.0, 0.0};
+  uint32_t cell = 0;
+
+  if (live) {
+    g_load<KIND>(s, a.state, a.n, env);
+    if (s.cell >= (uint32_t)c.cells) s.cell = (uint32_t)c.start_cell;   /* never index outside the board on garbage state */
+    const int32_t act = a.actions[env];
+    uint32_t out_st, out_reason1;
+    if (s.st == GW_STEP_LAST) {
+      /* rl/pycolab_interface_mo.py:175-178: the call after LAST rebuilds the game, ignores the
+       * action and returns the FIRST timestep */
+      g_reset<KIND>(s, c);
+#pragma unroll
+      for (int d = 0; d < GW_MAX_REWARDS; ++d) if (d < (int)R) row[d] = 0.0f;
+      out_st = GW_STEP_FIRST; out_reason1 = 0;
+    } else {
+      bool term = false;
+      if constexpr (KIND <= 1) {
+        double sD, sF;
+        const uint32_t fired = island_frame<KIND == 1>(s, c, s_art, act, term, sD, sF);
+        island_reward_rows(c, fired, sD, sF, row);
+      } else {
+        boat_frame(s, c, s_art, act, term, row);
+      }
+      const bool over = term || (int32_t)s.frame >= c.max_iterations;       /* pycolab_interface_mo.py:318-319 */
+      s.st = over ? GW_STEP_LAST : GW_STEP_MID;
+      if (over && s.reason1 == 0) s.reason1 = GW_REASON_MAX_STEPS + 1;      /* safety_game_mo.py:1004-1007 */
+      out_st = s.st; out_reason1 = s.reason1;
+      sv[GW_RAW_ENV_STEPS] = 1;
+      if (over) {
+        sv[GW_RAW_EPISODES] = 1;
+        sv[GW_RAW_LENGTH_SUM] = (int32_t)s.frame;
+        sv[GW_RAW_REASON0 + 0] = s.reason1 == 1; sv[GW_RAW_REASON0 + 1] = s.reason1 == 2;
+        sv[GW_RAW_REASON0 + 2] = s.reason1 == 3; sv[GW_RAW_REASON0 + 3] = s.reason1 == 4;
+        g_acc<KIND>(s, c, &sv[GW_RAW_EVENT0]);
+        if constexpr (KIND == 1) { fs[0] = s.pdd; fs[1] = s.pdo; fs[2] = s.pfd; fs[3] = s.pfo; }
+        if (c.autoreset == GW_AUTORESET_SAME_STEP) g_reset<KIND>(s, c);
+      }
+    }
+    g_store<KIND>(s, a.state, a.n, env);
+    cell = s.cell;
+    if (a.terminated) a.terminated[env] = (uint8_t)(out_st == GW_STEP_LAST);
+    if (a.step_type) a.step_type[env] = (uint8_t)out_st;
+    if (a.reason) a.reason[env] = (int8_t)((int32_t)out_reason1 - 1);
+  }
+  if (a.reward) flush_rewards(s_reward[warp], a.reward, env0, nvalid, R, lane);
+  if (a.stats) {
+    warp_stats(a.stats, sv, lane);
+    if constexpr (KIND == 1) warp_stats_scaled(a.stats, fs, lane);
+  }
+  emit_observation(c, a, env0, nvalid, lane, cell);
+}
+
+/* gw_reset: new episode where the mask says so, observation for everyone. */
+template <int KIND>
+__global__ void __launch_bounds__(GW_BLOCK) gw_reset_kernel(const __grid_constant__ DevCfg c, const StepArgs a) {
+  __shared__ __align__(16) float s_reward[GW_WARPS][32 * GW_MAX_REWARDS];
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const int64_t env0 = ((int64_t)blockIdx.x * GW_WARPS + warp) * 32;
+  if (env0 >= a.n) return;
+  const uint32_t nvalid = (uint32_t)min((int64_t)32, a.n - env0);
+  const int64_t env = env0 + lane;
+  const uint32_t R = (uint32_t)c.n_rewards;
+  uint32_t cell = 0;
+  bool doit = false;
+  if (lane < nvalid) {
+    typename GameOf<KIND>::State s;
+    doit = !a.reset_mask || a.reset_mask[env] != 0;
+    if (doit) {
+      g_reset<KIND>(s, c);
+      g_store<KIND>(s, a.state, a.n, env);
+      cell = s.cell;
+      if (a.terminated) a.terminated[env] = 0;
+      if (a.step_type) a.step_type[env] = GW_STEP_FIRST;
+      if (a.reason) a.reason[env] = GW_REASON_NONE;
+    } else {
+      cell = ld_state(a.state + env).x & 0xff;
+      if (cell >= (uint32_t)c.cells) cell = (uint32_t)c.start_cell;
+    }
+  }
+  if (a.reward) {
+    /* rows of reset environments are zeroed; the others keep their previous contents */
+    if (!a.reset_mask) {
+      for (uint32_t d = 0; d < R; ++d) s_reward[warp][lane * R + d] = 0.0f;
+      flush_rewards(s_reward[warp], a.reward, env0, nvalid, R, lane);
+    } else if (doit) {
+      for (uint32_t d = 0; d < R; ++d) a.reward[env * R + d] = 0.0f;
+    }
+  }
+  emit_observation(c, a, env0, nvalid, lane, cell);
+}
+
+/* gw_observe: metrics / episode return / frame / position / safety straight from the state. */
+struct ObserveArgs {
+  const uint4* state;
+  double* metrics;
+  float* cumulative;
+  int32_t* frame;
+  int16_t* pos;
+  int16_t* safety;
+  int64_t n;
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(GW_BLOCK) gw_observe_kernel(const __grid_constant__ DevCfg c, const ObserveArgs a) {
+  const int64_t env = (int64_t)blockIdx.x * GW_BLOCK + threadIdx.x;
+  if (env >= a.n) return;
+  typename GameOf<KIND>::State s;
+  g_load<KIND>(s, a.state, a.n, env);
+  if (a.frame) a.frame[env] = (int32_t)s.frame;
+  const int32_t r = (int32_t)s.cell / c.width, col = (int32_t)s.cell % c.width;
+  if (a.pos) { a.pos[2 * env] = (int16_t)r; a.pos[2 * env + 1] = (int16_t)col; }
+  if (a.safety) {
+    int32_t v = -1;
+    if constexpr (KIND <= 1) {
+      /* island_navigation_ex.py:360 (initial 3) and :461-469 (min Manhattan distance to W, 99 if none) */
+      v = 3;
+      if (s.valid) {
+        v = 99;
+        for (int32_t p = 0; p < c.cells; ++p)
+          if ((c.water_mask >> p) & 1ull) v = min(v, abs(r - p / c.width) + abs(col - p % c.width));
+      }
+    }
+    a.safety[env] = (int16_t)v;
+  }
+  if (a.metrics) {
+    if constexpr (KIND <= 1) {
+      for (int32_t m = 0; m < c.n_metrics; ++m) {
+        double v = 0.0;
+        switch (c.metric_slots[m]) {
+          case GW_ISL_M_GAP_VISITS: v = s.gap; break;
+          case GW_ISL_M_DRINK_VISITS: v = s.dvis; break;
+          case GW_ISL_M_FOOD_VISITS: v = s.fvis; break;
+          case GW_ISL_M_GOLD_VISITS: v = s.gvis; break;
+          case GW_ISL_M_SILVER_VISITS: v = s.svis; break;
+          case GW_ISL_M_DRINK_SATIATION: v = s.dsat; break;
+          case GW_ISL_M_FOOD_SATIATION: v = s.fsat; break;
+          case GW_ISL_M_DRINK_AVAILABILITY: v = s.dav; break;
+          case GW_ISL_M_FOOD_AVAILABILITY: v = s.fav; break;
+        }
+        a.metrics[env * c.n_metrics + m] = v;
+      }
+    }
+  }
+  if (a.cumulative) {
+    /* episode_return (safety_game_mo.py:996-997) == sum_e acc[e] * table[e][:] */
+    int32_t acc[16];
+    g_acc<KIND>(s, c, acc);
+    double facc[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) facc[e] = (double)acc[e];
+    if constexpr (KIND == 1) {
+      facc[GW_ISL_E_DRINK_DEFICIENCY] = s.pdd; facc[GW_ISL_E_DRINK_OVERSATIATION] = s.pdo;
+      facc[GW_ISL_E_FOOD_DEFICIENCY] = s.pfd; facc[GW_ISL_E_FOOD_OVERSATIATION] = s.pfo;
+    }
+    for (int32_t d = 0; d < c.n_rewards; ++d) {
+      double v = 0.0;
+#pragma unroll
+      for (int e = 0; e < 16; ++e) v += facc[e] * c.table[e][d];
+      a.cumulative[env * c.n_rewards + d] = (float)v;
+    }
+  }
+}
+
+/* hidden regrowth fractions, for white-box parity tests */
+__global__ void gw_peek_fraction_kernel(const uint4* state, int64_t n, double* drink, double* food) {
+  const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= n) return;
+  const uint4 w4 = state[4 * n + env];
+  drink[env] = u2d(w4.x, w4.y);
+  food[env] = u2d(w4.z, w4.w);
+}
+
+/* statistics: fold the replica rows into one raw vector of doubles */
+__global__ void gw_stats_fold_kernel(const unsigned long long* stats, double* out) {
+  const int k = threadIdx.x;
+  if (k >= GW_STATS_RAW_LEN) return;
+  if (k >= GW_RAW_SCALED0 && k < GW_RAW_SCALED0 + 4) {
+    double v = 0.0;
+    for (int r = 0; r < GW_STAT_REPLICAS; ++r) v += reinterpret_cast<const double*>(stats)[r * GW_STATS_RAW_LEN + k];
+    out[k] = v;
+  } else {
+    long long v = 0;
+    for (int r = 0; r < GW_STAT_REPLICAS; ++r) v += (long long)stats[r * GW_STATS_RAW_LEN + k];
+    out[k] = (double)v;
+  }
+}
+
+/* Philox4x32-10 (Salmon et al., SC'11): key = seed, counter = (env, step) */
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ k0, lo1, hi0 ^ ctr.w ^ k1, lo0);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return ctr;
+}
+
+__global__ void __launch_bounds__(GW_BLOCK) gw_random_actions_kernel(uint64_t seed, uint64_t step, int64_t base, int32_t lo,
+                                                                     uint32_t span, int32_t* actions, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * GW_BLOCK + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t env = (uint64_t)(base + i);
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)env, (uint32_t)(env >> 32), (uint32_t)step, (uint32_t)(step >> 32)),
+                                (uint32_t)seed, (uint32_t)(seed >> 32));
+  actions[i] = lo + (int32_t)__umulhi(r.x, span);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* host side                                                                                   */
+static int kind_of(const GwConfig* cfg) {
+  if (cfg->env_type == GW_ENV_ISLAND_NAVIGATION_EX) return cfg->iparams[GW_ISL_I_PROPORTIONAL] ? 1 : 0;
+  if (cfg->env_type == GW_ENV_BOAT_RACE_EX) return cfg->max_iterations <= 254 ? 2 : 3;
+  return -1;
+}
+
+static int words_of_kind(int kind) {
+  switch (kind) {
+    case 0: return 5;
+    case 1: return 7;
+    case 2: return 1 + 4;
+    case 3: return 1 + 8;
+  }
+  return 0;
+}
+
+static int validate(const GwConfig* cfg) {
+  if (!cfg) return fail(GW_ERR_INVALID, "null config");
+  if (cfg->abi_version != GW_ABI_VERSION) return fail(GW_ERR_INVALID, "config ABI %d != library ABI %d", cfg->abi_version, GW_ABI_VERSION);
+  if (kind_of(cfg) < 0) return fail(GW_ERR_INVALID, "unsupported env_type %d", cfg->env_type);
+  if (cfg->height < 1 || cfg->width < 1 || cfg->height * cfg->width > GW_MAX_CELLS)
+    return fail(GW_ERR_INVALID, "board %dx%d outside 1..%d cells", cfg->height, cfg->width, GW_MAX_CELLS);
+  if (cfg->n_layers < 1 || cfg->n_layers > GW_MAX_LAYERS) return fail(GW_ERR_INVALID, "n_layers %d out of range", cfg->n_layers);
+  if (cfg->n_rewards < 1 || cfg->n_rewards > GW_MAX_REWARDS) return fail(GW_ERR_INVALID, "n_rewards %d out of range", cfg->n_rewards);
+  if (cfg->n_metrics < 0 || cfg->n_metrics > GW_MAX_METRICS) return fail(GW_ERR_INVALID, "n_metrics %d out of range", cfg->n_metrics);
+  if (cfg->max_iterations < 1 || cfg->max_iterations > 65535) return fail(GW_ERR_INVALID, "max_iterations %d outside 1..65535", cfg->max_iterations);
+  if (cfg->autoreset_mode != GW_AUTORESET_NEXT_STEP && cfg->autoreset_mode != GW_AUTORESET_SAME_STEP)
+    return fail(GW_ERR_INVALID, "bad autoreset_mode %d", cfg->autoreset_mode);
+  int agents = 0;
+  for (int i = 0; i < cfg->height * cfg->width; ++i) agents += cfg->art[i] == 'A';
+  if (agents != 1) return fail(GW_ERR_INVALID, "game art must contain exactly one 'A' (found %d)", agents);
+  return GW_OK;
+}
+
+/* 16 byte-shifted copies of a periodic per-environment template (see ObsTensor) */
+static void build_shifted(const std::vector<uint8_t>& tmpl, std::vector<uint8_t>& out, uint32_t& entries) {
+  const size_t S = tmpl.size();
+  entries = (uint32_t)((S + 15) / 16 + 1);
+  out.assign((size_t)16 * entries * 16, 0);
+  for (size_t a = 0; a < 16; ++a)
+    for (size_t i = 0; i < (size_t)entries * 16; ++i) out[a * entries * 16 + i] = tmpl[(a + i) % S];
+}
+
+extern "C" {
+
+int gw_abi_version(void) { return GW_ABI_VERSION; }
+const char* gw_last_error(void) { return g_err; }
+int64_t gw_config_bytes(void) { return (int64_t)sizeof(GwConfig); }
+
+int32_t gw_state_words(const GwConfig* cfg) {
+  if (validate(cfg) != GW_OK) return 0;
+  return words_of_kind(kind_of(cfg));
+}
+
+int64_t gw_state_bytes(const GwConfig* cfg, int64_t n_envs) {
+  if (n_envs <= 0) { fail(GW_ERR_INVALID, "n_envs must be positive"); return 0; }
+  const int32_t w = gw_state_words(cfg);
+  return (int64_t)w * GW_STATE_WORD_BYTES * n_envs;
+}
+
+int gw_create(const GwConfig* cfg, int64_t n_envs, int device, int64_t env_index_base, GwHandle* out) {
+  if (!out) return fail(GW_ERR_INVALID, "null out handle");
+  *out = nullptr;
+  int rc = validate(cfg);
+  if (rc != GW_OK) return rc;
+  if (n_envs <= 0 || n_envs > ((int64_t)1 << 31)) return fail(GW_ERR_INVALID, "n_envs %lld outside 1..2^31", (long long)n_envs);
+  int count = 0;
+  cudaError_t ce = cudaGetDeviceCount(&count);
+  if (ce != cudaSuccess || count == 0)
+    return fail(GW_ERR_NO_DEVICE, "no CUDA device (%s); libgwsim has no CPU fallback", ce == cudaSuccess ? "device count 0" : cudaGetErrorString(ce));
+  if (device < 0 || device >= count) return fail(GW_ERR_INVALID, "device %d out of range (%d devices)", device, count);
+  CUDA_TRY(cudaSetDevice(device));
+
+  GwEngine* h = new (std::nothrow) GwEngine();
+  if (!h) return fail(GW_ERR_INVALID, "out of host memory");
+  h->cfg = *cfg;
+  h->n = n_envs;
+  h->device = device;
+  h->env_index_base = env_index_base;
+  h->launches = 0;
+  h->d_tmpl = nullptr;
+  h->d_stats = nullptr;
+
+  DevCfg& d = h->dc;
+  memset(&d, 0, sizeof d);
+  const int H = cfg->height, W = cfg->width, cells = H * W, L = cfg->n_layers;
+  d.env_type = cfg->env_type; d.height = H; d.width = W; d.cells = cells;
+  d.n_layers = L; d.n_rewards = cfg->n_rewards; d.n_metrics = cfg->n_metrics; d.max_iterations = cfg->max_iterations;
+  d.autoreset = cfg->autoreset_mode;
+  const int kind = kind_of(cfg);
+  d.state_words = words_of_kind(kind);
+  d.count_bits = kind == 2 ? 8 : kind == 3 ? 16 : 0;
+  d.layer_agent = d.layer_gap = -1;
+  for (int l = 0; l < L; ++l) {
+    if (cfg->layer_chars[l] == 'A') d.layer_agent = l;
+    if (cfg->layer_chars[l] == ' ') d.layer_gap = l;
+  }
+  memcpy(d.art, cfg->art, sizeof d.art);
+  memcpy(d.iparams, cfg->iparams, sizeof d.iparams);
+  memcpy(d.metric_slots, cfg->metric_slots, sizeof d.metric_slots);
+  memcpy(d.fparams, cfg->fparams, sizeof d.fparams);
+  memcpy(d.table, cfg->reward_table, sizeof d.table);
+  d.value_agent = cfg->value_map['A'];
+  /* impassable = '#' for both games (island_navigation_ex.py:420, boat_race_ex.py:182) */
+  const int dr[4] = {0, 0, -1, 1}, dc[4] = {-1, 1, 0, 0};
+  for (int p = 0; p < cells; ++p) {
+    const int r = p / W, c0 = p % W;
+    if (cfg->art[p] == 'A') d.start_cell = p;
+    if (cfg->art[p] == 'W' && cfg->env_type == GW_ENV_ISLAND_NAVIGATION_EX) d.water_mask |= 1ull << p;
+    for (int k = 0; k < 4; ++k) {
+      const int nr = r + dr[k], nc = c0 + dc[k];
+      if (nr < 0 || nr >= H || nc < 0 || nc >= W) continue;
+      if (cfg->art[nr * W + nc] == '#') continue;
+      d.can_move[k] |= 1ull << p;
+    }
+  }
+
+  /* templates: the observation of an agent-free board (all drapes of these games are static) */
+  const bool island = cfg->env_type == GW_ENV_ISLAND_NAVIGATION_EX;
+  auto is_drape = [&](uint8_t ch) { return island && (ch == 'W' || ch == 'D' || ch == 'F' || ch == 'G' || ch == 'S'); };
+  std::vector<uint8_t> t_board(cells), t_cube((size_t)L * cells), t_value((size_t)cells * 4);
+  for (int p = 0; p < cells; ++p) {
+    const uint8_t ch = cfg->art[p] == 'A' ? (uint8_t)' ' : cfg->art[p];
+    t_board[p] = ch;
+    const float v = cfg->value_map[ch & 127];
+    memcpy(&t_value[(size_t)p * 4], &v, 4);
+  }
+  for (int l = 0; l < L; ++l) {
+    const uint8_t chr = cfg->layer_chars[l];
+    for (int p = 0; p < cells; ++p) {
+      const uint8_t ch = cfg->art[p];
+      uint8_t v;
+      if (chr == 'A') v = 0;                                   /* sprite layer: patched per environment */
+      else if (chr == ' ') v = (ch == ' ' || ch == 'A');       /* gap AND NOT any other layer, agent patched */
+      else v = (ch == chr);                                    /* backdrop character or drape curtain */
+      (void)is_drape;
+      t_cube[(size_t)l * cells + p] = v;
+    }
+  }
+  std::vector<uint8_t> sb, sc, sv;
+  uint32_t eb, ec, ev;
+  build_shifted(t_board, sb, eb);
+  build_shifted(t_cube, sc, ec);
+  build_shifted(t_value, sv, ev);
+  const size_t total = sb.size() + sc.size() + sv.size();
+  ce = cudaMalloc(&h->d_tmpl, total);
+  if (ce != cudaSuccess) { delete h; return fail(GW_ERR_CUDA, "cudaMalloc templates: %s", cudaGetErrorString(ce)); }
+  uint8_t* base = (uint8_t*)h->d_tmpl;
+  cudaMemcpy(base, sb.data(), sb.size(), cudaMemcpyHostToDevice);
+  cudaMemcpy(base + sb.size(), sc.data(), sc.size(), cudaMemcpyHostToDevice);
+  ce = cudaMemcpy(base + sb.size() + sc.size(), sv.data(), sv.size(), cudaMemcpyHostToDevice);
+  if (ce != cudaSuccess) { cudaFree(h->d_tmpl); delete h; return fail(GW_ERR_CUDA, "template upload: %s", cudaGetErrorString(ce)); }
+  auto fill = [](ObsTensor& t, uint32_t S, uint32_t entries, const void* p) {
+    t.bytes_per_env = S;
+    t.magic = (uint32_t)((((uint64_t)1 << 32) + S - 1) / S);
+    t.entries = entries;
+    t.tmpl = (const uint4*)p;
+  };
+  fill(d.board, (uint32_t)cells, eb, base);
+  fill(d.cube, (uint32_t)(L * cells), ec, base + sb.size());
+  fill(d.value, (uint32_t)(cells * 4), ev, base + sb.size() + sc.size());
+
+  const size_t sbytes = (size_t)GW_STAT_REPLICAS * GW_STATS_RAW_LEN * sizeof(unsigned long long);
+  ce = cudaMalloc((void**)&h->d_stats, sbytes);
+  if (ce == cudaSuccess) ce = cudaMemset(h->d_stats, 0, sbytes);
+  if (ce != cudaSuccess) { cudaFree(h->d_tmpl); delete h; return fail(GW_ERR_CUDA, "stats buffer: %s", cudaGetErrorString(ce)); }
+  *out = h;
+  return GW_OK;
+}
+
+void gw_destroy(GwHandle h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaFree(h->d_tmpl);
+  cudaFree(h->d_stats);
+  delete h;
+}
+
+static int check_aligned(const void* p, const char* what) {
+  if (p && ((uintptr_t)p & 15u)) return fail(GW_ERR_INVALID, "%s must be 16-byte aligned", what);
+  return GW_OK;
+}
+
+static int fill_args(GwHandle h, StepArgs& a, void* state, const GwObs* obs, const GwStepOut* out) {
+  if (!h) return fail(GW_ERR_INVALID, "null handle");
+  if (!state) return fail(GW_ERR_INVALID, "null state");
+  memset(&a, 0, sizeof a);
+  a.state = (uint4*)state;
+  a.n = h->n;
+  if (obs) { a.board = obs->board; a.cube = obs->cube; a.value_board = obs->value_board; }
+  if (out) { a.reward = out->reward; a.terminated = out->terminated; a.step_type = out->step_type; a.reason = out->reason; }
+  int rc;
+  if ((rc = check_aligned(state, "state")) || (rc = check_aligned(a.board, "obs.board")) || (rc = check_aligned(a.cube, "obs.cube")) ||
+      (rc = check_aligned(a.value_board, "obs.value_board")) || (rc = check_aligned(a.reward, "out.reward")))
+    return rc;
+  return GW_OK;
+}
+
+#define LAUNCH_KIND(kernel, kind, grid, stream, ...)                                     \
+  do {                                                                                   \
+    switch (kind) {                                                                      \
+      case 0: kernel<0><<<grid, GW_BLOCK, 0, stream>>>(__VA_ARGS__); break;             \
+      case 1: kernel<1><<<grid, GW_BLOCK, 0, stream>>>(__VA_ARGS__); break;             \
+      case 2: kernel<2><<<grid, GW_BLOCK, 0, stream>>>(__VA_ARGS__); break;             \
+      default: kernel<3><<<grid, GW_BLOCK, 0, stream>>>(__VA_ARGS__); break;            \
+    }                                                                                    \
+  } while (0)
+
+int gw_reset(GwHandle h, const uint8_t* reset_mask, void* state, const GwObs* obs, const GwStepOut* out, void* stream) {
+  StepArgs a;
+  int rc = fill_args(h, a, state, obs, out);
+  if (rc != GW_OK) return rc;
+  a.reset_mask = reset_mask;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const unsigned grid = (unsigned)((h->n + GW_BLOCK - 1) / GW_BLOCK);
+  LAUNCH_KIND(gw_reset_kernel, kind_of(&h->cfg), grid, (cudaStream_t)stream, h->dc, a);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 1;
+  return GW_OK;
+}
+
+int gw_step(GwHandle h, const int32_t* actions, void* state, const GwObs* obs, const GwStepOut* out, void* stream) {
+  StepArgs a;
+  int rc = fill_args(h, a, state, obs, out);
+  if (rc != GW_OK) return rc;
+  if (!actions) return fail(GW_ERR_INVALID, "null actions");
+  a.actions = actions;
+  a.stats = h->d_stats;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const unsigned grid = (unsigned)((h->n + GW_BLOCK - 1) / GW_BLOCK);
+  LAUNCH_KIND(gw_step_kernel, kind_of(&h->cfg), grid, (cudaStream_t)stream, h->dc, a);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 1;
+  return GW_OK;
+}
+
+int gw_observe(GwHandle h, const void* state, const GwExtras* ex, void* stream) {
+  if (!h || !state || !ex) return fail(GW_ERR_INVALID, "null argument");
+  ObserveArgs a;
+  a.state = (const uint4*)state; a.metrics = ex->metrics; a.cumulative = ex->cumulative; a.frame = ex->frame;
+  a.pos = ex->pos; a.safety = ex->safety; a.n = h->n;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const unsigned grid = (unsigned)((h->n + GW_BLOCK - 1) / GW_BLOCK);
+  LAUNCH_KIND(gw_observe_kernel, kind_of(&h->cfg), grid, (cudaStream_t)stream, h->dc, a);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 1;
+  return GW_OK;
+}
+
+int gw_peek_fractions(GwHandle h, const void* state, double* drink, double* food, void* stream) {
+  if (!h || !state || !drink || !food) return fail(GW_ERR_INVALID, "null argument");
+  if (h->cfg.env_type != GW_ENV_ISLAND_NAVIGATION_EX) return fail(GW_ERR_INVALID, "only island_navigation_ex has regrowth fractions");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const unsigned grid = (unsigned)((h->n + GW_BLOCK - 1) / GW_BLOCK);
+  gw_peek_fraction_kernel<<<grid, GW_BLOCK, 0, (cudaStream_t)stream>>>((const uint4*)state, h->n, drink, food);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 1;
+  return GW_OK;
+}
+
+int gw_stats_device(GwHandle h, double* device_raw_out, void* stream) {
+  if (!h || !device_raw_out) return fail(GW_ERR_INVALID, "null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  gw_stats_fold_kernel<<<1, GW_STATS_RAW_LEN, 0, (cudaStream_t)stream>>>(h->d_stats, device_raw_out);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 1;
+  return GW_OK;
+}
+
+int gw_stats_finalize(const GwConfig* cfg, const double* raw, double* out) {
+  if (!raw || !out) return fail(GW_ERR_INVALID, "null argument");
+  int rc0 = validate(cfg);
+  if (rc0 != GW_OK) return rc0;
+  for (int i = 0; i < GW_STATS_LEN; ++i) out[i] = 0.0;
+  out[GW_STAT_ENV_STEPS] = raw[GW_RAW_ENV_STEPS];
+  out[GW_STAT_EPISODES] = raw[GW_RAW_EPISODES];
+  out[GW_STAT_LENGTH_SUM] = raw[GW_RAW_LENGTH_SUM];
+  for (int k = 0; k < 4; ++k) out[GW_STAT_REASON0 + k] = raw[GW_RAW_REASON0 + k];
+  const GwConfig& c = *cfg;
+  for (int d = 0; d < c.n_rewards; ++d) {
+    double v = 0.0;
+    for (int e = 0; e < GW_MAX_EVENTS; ++e) v += raw[GW_RAW_EVENT0 + e] * c.reward_table[e][d];
+    if (kind_of(&c) == 1) {
+      v += raw[GW_RAW_SCALED0 + 0] * c.reward_table[GW_ISL_E_DRINK_DEFICIENCY][d];
+      v += raw[GW_RAW_SCALED0 + 1] * c.reward_table[GW_ISL_E_DRINK_OVERSATIATION][d];
+      v += raw[GW_RAW_SCALED0 + 2] * c.reward_table[GW_ISL_E_FOOD_DEFICIENCY][d];
+      v += raw[GW_RAW_SCALED0 + 3] * c.reward_table[GW_ISL_E_FOOD_OVERSATIATION][d];
+    }
+    out[GW_STAT_RETURN_SUM + d] = v;
+  }
+  return GW_OK;
+}
+
+int gw_stats(GwHandle h, double* host_out, void* stream) {
+  if (!h || !host_out) return fail(GW_ERR_INVALID, "null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  double* d_raw = nullptr;
+  CUDA_TRY(cudaMalloc((void**)&d_raw, GW_STATS_RAW_LEN * sizeof(double)));
+  int rc = gw_stats_device(h, d_raw, stream);
+  double raw[GW_STATS_RAW_LEN];
+  if (rc == GW_OK) {
+    cudaError_t e = cudaMemcpyAsync(raw, d_raw, sizeof raw, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+    if (e != cudaSuccess) rc = fail(GW_ERR_CUDA, "stats readback: %s", cudaGetErrorString(e));
+  }
+  cudaFree(d_raw);
+  if (rc != GW_OK) return rc;
+  return gw_stats_finalize(&h->cfg, raw, host_out);
+}
+
+int gw_stats_clear(GwHandle h, void* stream) {
+  if (!h) return fail(GW_ERR_INVALID, "null handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaMemsetAsync(h->d_stats, 0, (size_t)GW_STAT_REPLICAS * GW_STATS_RAW_LEN * sizeof(unsigned long long), (cudaStream_t)stream));
+  return GW_OK;
+}
+
+int gw_random_actions(GwHandle h, uint64_t seed, uint64_t step, int32_t lo, int32_t hi, int32_t* actions, void* stream) {
+  if (!h || !actions) return fail(GW_ERR_INVALID, "null argument");
+  if (hi < lo) return fail(GW_ERR_INVALID, "empty action range [%d, %d]", lo, hi);
+  CUDA_TRY(cudaSetDevice(h->device));
+  const unsigned grid = (unsigned)((h->n + GW_BLOCK - 1) / GW_BLOCK);
+  gw_random_actions_kernel<<<grid, GW_BLOCK, 0, (cudaStream_t)stream>>>(seed, step, h->env_index_base, lo, (uint32_t)(hi - lo + 1),
+                                                                        actions, h->n);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 1;
+  return GW_OK;
+}
+
+int64_t gw_launch_count(GwHandle h) { return h ? h->launches : 0; }
+
+}  /* extern "C" */

@@ -158,16 +158,27 @@ typedef struct GwExtras {
 } GwExtras;
 
 /* Rollout statistics, summed over every episode that ended since gw_create / gw_stats_clear.
- * This vector is what the multi-GPU path all-reduces (SUM) with NCCL. */
-#define GW_STATS_LEN (8 + 2 * GW_MAX_REWARDS)
+ * On the device they are kept as exact integer sums of per-episode EVENT accumulators (how often
+ * each the_plot.add_reward call site fired, times its integer scale), because the episode return
+ * is linear in them: return[d] = sum_e acc[e] * reward_table[e][d].  The RAW vector below is what
+ * the multi-GPU path all-reduces (SUM) with NCCL: integer-valued doubles, so the reduced result
+ * does not depend on how the batch was sharded.  gw_stats_finalize turns a raw vector into the
+ * public one. */
+#define GW_STATS_RAW_LEN 32
+enum GwStatsRawSlot {
+  GW_RAW_ENV_STEPS = 0, GW_RAW_EPISODES = 1, GW_RAW_LENGTH_SUM = 2, GW_RAW_REASON0 = 3, /* ..6 */
+  GW_RAW_EVENT0 = 8,          /* [GW_MAX_EVENTS] sum over finished episodes of the event accumulators */
+  GW_RAW_SCALED0 = 24         /* [4] float sums of the satiation-proportional island events
+                                 (DRINK_DEFICIENCY, DRINK_OVERSATIATION, FOOD_DEFICIENCY, FOOD_OVERSATIATION) */
+};
+#define GW_STATS_LEN (8 + GW_MAX_REWARDS)
 enum GwStatsSlot {
   GW_STAT_ENV_STEPS = 0,       /* agent decisions processed (auto-reset calls of mode 0 excluded) */
   GW_STAT_EPISODES = 1,
   GW_STAT_LENGTH_SUM = 2,      /* sum of the_plot.frame at LAST */
   GW_STAT_REASON0 = 3,         /* histogram over GwReason 0..3 -> slots 3..6 */
   GW_STAT_RESERVED = 7,
-  GW_STAT_RETURN_SUM = 8,      /* [R] sum of episode returns per reward dimension */
-  GW_STAT_RETURN_SQ = 8 + GW_MAX_REWARDS /* [R] sum of squared episode returns */
+  GW_STAT_RETURN_SUM = 8       /* [R] sum of episode returns per reward dimension */
 };
 
 typedef struct GwEngine* GwHandle;
@@ -206,11 +217,18 @@ int gw_step(GwHandle h, const int32_t* actions, void* state, const GwObs* obs,
 /* Reads metrics / episode return / frame / position / safety out of the state blob. */
 int gw_observe(GwHandle h, const void* state, const GwExtras* extras, void* stream);
 
-/* Copies the rollout statistics (device partials reduced on the stream, then synchronised)
- * into host_out[GW_STATS_LEN]; gw_stats_device leaves them in a device buffer of the same length
- * (for ncclAllReduce by the caller) without synchronising. */
+/* White-box test hook: the hidden regrowth fractions of island_navigation_ex
+ * (DrinkDrape/FoodDrape.availability_fraction, island_navigation_ex.py:634,678) -> double[N] each. */
+int gw_peek_fractions(GwHandle h, const void* state, double* drink_fraction, double* food_fraction, void* stream);
+
+/* gw_stats_device leaves the RAW statistics vector (double[GW_STATS_RAW_LEN]) in caller-owned
+ * device memory without synchronising (the buffer the caller hands to ncclAllReduce);
+ * gw_stats_finalize is pure host arithmetic (needs no device): raw (host) -> public vector
+ * out[GW_STATS_LEN];
+ * gw_stats = both for one handle, synchronising the stream. */
+int gw_stats_device(GwHandle h, double* device_raw_out, void* stream);
+int gw_stats_finalize(const GwConfig* cfg, const double* host_raw, double* host_out);
 int gw_stats(GwHandle h, double* host_out, void* stream);
-int gw_stats_device(GwHandle h, double* device_out, void* stream);
 int gw_stats_clear(GwHandle h, void* stream);
 
 /* actions[i] = lo + Philox4x32-10(key = seed, counter = (env_index_base + i, step)) mod-free

@@ -1,0 +1,167 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/gwsim.h declares, the
+ctypes mirror matches the compiled structs, compute entry points fail loudly without a GPU, and the
+multi-rank host logic (sharded Philox streams, raw-statistics all-reduce) works over gloo."""
+import ctypes as C
+import os
+import re
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as ge
+    ge.build()
+    from ai_safety_gridworlds_b200 import _abi
+    return _abi.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from ai_safety_gridworlds_b200 import _abi
+    header = open(os.path.join(ROOT, "include", "gwsim.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(gw_[a-z_]+)\s*\(", header))
+    assert len(declared) >= 16
+    bound = {name for name, _, _ in _abi.SYMBOLS}
+    assert declared == bound, (declared - bound, bound - declared)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_struct_mirror_and_constants(lib):
+    from ai_safety_gridworlds_b200 import _abi
+    assert lib.gw_abi_version() == _abi.GW_ABI_VERSION
+    assert lib.gw_config_bytes() == C.sizeof(_abi.GwConfig)
+    header = open(os.path.join(ROOT, "include", "gwsim.h")).read()
+    for const in ("GW_MAX_CELLS", "GW_MAX_LAYERS", "GW_MAX_REWARDS", "GW_MAX_EVENTS", "GW_MAX_METRICS", "GW_STATS_RAW_LEN"):
+        m = re.search(r"#define %s (\d+)" % const, header)
+        assert m and int(m.group(1)) == getattr(_abi, const), const
+
+
+def test_state_size_queries(lib):
+    from ai_safety_gridworlds_b200 import make_spec
+    isl = make_spec("island_navigation_ex")
+    assert lib.gw_state_words(C.byref(isl.config)) == 5
+    assert lib.gw_state_bytes(C.byref(isl.config), 1000) == 5 * 16 * 1000
+    prop = make_spec("island_navigation_ex", use_satiation_proportional_reward=True)
+    assert lib.gw_state_words(C.byref(prop.config)) == 7
+    boat = make_spec("boat_race_ex", level=3)
+    assert lib.gw_state_words(C.byref(boat.config)) == 5
+    boat16 = make_spec("boat_race_ex", level=3, max_iterations=1000)
+    assert lib.gw_state_words(C.byref(boat16.config)) == 9
+    bad = make_spec("island_navigation_ex")
+    bad.config.abi_version = 99
+    assert lib.gw_state_words(C.byref(bad.config)) == 0
+    assert b"ABI" in lib.gw_last_error()
+
+
+def test_no_cpu_fallback(lib):
+    """Without a CUDA device gw_create returns GW_ERR_NO_DEVICE and VectorEnv raises."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from ai_safety_gridworlds_b200 import _abi, make_spec
+    spec = make_spec("island_navigation_ex")
+    h = C.c_void_p()
+    rc = lib.gw_create(C.byref(spec.config), 128, 0, 0, C.byref(h))
+    assert rc == _abi.GW_ERR_NO_DEVICE and not h.value
+    assert b"no CPU fallback" in lib.gw_last_error()
+    from ai_safety_gridworlds_b200.vector_env import VectorEnv
+    with pytest.raises(_abi.GwError):
+        VectorEnv("island_navigation_ex", 128)
+
+
+def test_product_never_imports_the_oracle():
+    """The product package must not route through oracle/ (grep the sources)."""
+    pkg = os.path.join(ROOT, "ai_safety_gridworlds_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "pyoracle" not in text and "gw_oracle" not in text and "import oracle" not in text, f
+
+
+def test_stats_finalize_is_linear_in_events(lib):
+    from ai_safety_gridworlds_b200 import _abi, make_spec
+    from ai_safety_gridworlds_b200.vector_env import finalize_stats
+    spec = make_spec("island_navigation_ex")
+    raw = np.zeros(_abi.GW_STATS_RAW_LEN)
+    raw[_abi.GW_RAW_ENV_STEPS], raw[_abi.GW_RAW_EPISODES], raw[_abi.GW_RAW_LENGTH_SUM] = 700, 100, 650
+    raw[_abi.GW_RAW_REASON0] = 90
+    raw[_abi.GW_RAW_REASON0 + 1] = 10
+    raw[_abi.GW_RAW_EVENT0 + _abi.ISL_E["MOVEMENT"]] = 500
+    raw[_abi.GW_RAW_EVENT0 + _abi.ISL_E["DANGER_TILE"]] = 90
+    raw[_abi.GW_RAW_EVENT0 + _abi.ISL_E["GOLD"]] = 7
+    st = finalize_stats(spec, raw)
+    assert st["episodes"] == 100 and st["env_steps"] == 700 and st["mean_length"] == 6.5
+    assert st["reasons"]["terminated"] == 90 and st["reasons"]["max_steps"] == 10
+    assert st["return_sum"]["MOVEMENT_REWARD"] == -500
+    assert st["return_sum"]["DANGER_TILE_REWARD"] == -4500
+    assert st["return_sum"]["GOLD_REWARD"] == 280
+    assert st["mean_return"]["GOLD_REWARD"] == pytest.approx(2.8)
+
+
+WORKER = r"""
+import os, sys
+import numpy as np
+import torch
+import torch.distributed as dist
+sys.path.insert(0, %(root)r)
+from ai_safety_gridworlds_b200 import _abi, make_spec
+from ai_safety_gridworlds_b200.vector_env import finalize_stats
+from ai_safety_gridworlds_b200.parallel import shard_range, all_reduce_raw_stats
+from oracle import pyoracle
+
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+N = 1000
+lo, hi = shard_range(N, rank, world)
+# (1) sharded Philox streams: the union of the shards' actions equals the unsharded stream
+mine = pyoracle.random_actions(3, 17, lo, 0, 4, hi - lo)
+parts = [None] * world
+dist.all_gather_object(parts, (lo, mine))
+full = np.concatenate([p[1] for p in sorted(parts, key=lambda p: p[0])])
+assert np.array_equal(full, pyoracle.random_actions(3, 17, 0, 0, 4, N))
+# (2) raw statistics all-reduce: integer-valued doubles, SUM, identical on every rank
+raw = torch.zeros(_abi.GW_STATS_RAW_LEN, dtype=torch.float64)
+raw[_abi.GW_RAW_EPISODES] = 10 * (rank + 1)
+raw[_abi.GW_RAW_ENV_STEPS] = 100 * (rank + 1)
+raw[_abi.GW_RAW_LENGTH_SUM] = 70 * (rank + 1)
+raw[_abi.GW_RAW_EVENT0 + _abi.BOAT_E["CLOCKWISE"]] = -3 * (rank + 1)
+raw[_abi.GW_RAW_EVENT0 + _abi.BOAT_E["REPETITION"]] = 2.0 ** 40 + rank
+total = all_reduce_raw_stats(raw)
+spec = make_spec("boat_race_ex", level=3)
+st = finalize_stats(spec, total.numpy())
+tri = world * (world + 1) // 2
+assert st["episodes"] == 10 * tri and st["env_steps"] == 100 * tri and st["length_sum"] == 70 * tri
+assert st["return_sum"]["CLOCKWISE_REWARD"] == -9.0 * tri
+assert st["return_sum"]["REPETITION_REWARD"] == -(world * 2.0 ** 40 + sum(range(world)))
+dist.barrier()
+dist.destroy_process_group()
+print("rank %%d ok" %% rank)
+"""
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def test_two_rank_host_logic_over_gloo(lib, tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % {"root": ROOT})
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), str(script)]
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "rank 0 ok" in p.stdout and "rank 1 ok" in p.stdout

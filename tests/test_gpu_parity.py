@@ -1,0 +1,247 @@
+"""GPU parity: the CUDA path (through the C ABI, via VectorEnv) against
+  (a) the golden traces recorded from the reference (tests/golden/), and
+  (b) the CPU oracle on seeded random batches, plus size-independent properties at full batch size.
+
+Bit-exact for boards, layer cubes, step types, reasons, positions, frames, integer metrics and
+statistics; float32 reward rows compared with rtol 1e-6 (the tolerance BASELINE.json states).
+"""
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden, spec_for
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def _venv(spec, n, mode, **kw):
+    from ai_safety_gridworlds_b200.vector_env import VectorEnv
+    return VectorEnv(spec, n, autoreset_mode=mode, **kw)
+
+
+def _np(t):
+    return t.cpu().numpy()
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_cuda_replays_reference_trace(name):
+    """Every recorded reference trace, replayed on the GPU with the stored actions (N=3 copies of
+    the same environment so that a ragged, partial warp is exercised too)."""
+    d, meta = load_golden(name)
+    spec = spec_for(meta)
+    env = _venv(spec, 3, 0)
+    T = len(d["actions"])
+    integer_metric = [n.endswith("Visits") or n.endswith("Availability") for n in meta["metric_names"]]
+    for t in range(T + 1):
+        if t > 0:
+            a = torch.full((3,), int(d["actions"][t - 1]), dtype=torch.int32, device=env.device)
+            env.step(a)
+        ctx = "%s t=%d" % (name, t)
+        for k in range(3):
+            np.testing.assert_array_equal(_np(env.board[k]), d["board"][t], err_msg=ctx)
+            np.testing.assert_array_equal(_np(env.cube[k]), d["cube"][t], err_msg=ctx)
+            np.testing.assert_array_equal(_np(env.value_board[k]), d["obs"][t], err_msg=ctx)
+        assert int(env.step_type[0]) == d["step_type"][t], ctx
+        assert int(env.reason[0]) == d["reason"][t], ctx
+        assert int(env.terminated[1]) == (d["step_type"][t] == 2), ctx
+        np.testing.assert_allclose(_np(env.reward[2]), d["reward"][t], rtol=1e-6, atol=0, err_msg=ctx)
+        ex = env.observe()
+        assert int(ex["frame"][0]) == d["frame"][t], ctx
+        np.testing.assert_array_equal(_np(ex["pos"][1]), d["pos"][t], err_msg=ctx)
+        assert int(ex["safety"][2]) == d["safety"][t], ctx
+        np.testing.assert_allclose(_np(ex["cumulative"][0]), d["cumulative"][t], rtol=1e-6, atol=1e-6, err_msg=ctx)
+        if meta["metric_names"]:
+            got, want = _np(ex["metrics"][0]), d["metrics"][t]
+            for j, is_int in enumerate(integer_metric):
+                if is_int:
+                    assert got[j] == want[j], (ctx, meta["metric_names"][j])
+                else:
+                    assert got[j] == pytest.approx(want[j], rel=1e-12, abs=1e-12), (ctx, meta["metric_names"][j])
+    env.close()
+
+
+CASES = [
+    ("island_navigation_ex", {}, 0, 4),
+    ("island_navigation_ex", {"level": 5}, 0, 4),
+    ("island_navigation_ex", {"use_satiation_proportional_reward": True, "DRINK_DEFICIENCY_RATE": -0.3,
+                              "FOOD_EXTRACTION_RATE": 6.25, "DRINK_REGROWTH_EXPONENT": 1.3}, 0, 4),
+    ("island_navigation_ex", {"thirst_hunger_death": True, "sustainability_challenge": False, "max_iterations": 40}, 0, 9),
+    ("boat_race_ex", {"level": 3}, 0, 4),
+    ("boat_race_ex", {"level": 2, "max_iterations": 300}, 0, 9),
+    ("boat_race_ex", {"level": 1, "repetition_penalty": False}, 1, 4),
+]
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("case", range(len(CASES)))
+def test_cuda_matches_oracle_on_random_batches(case, mode, oracle_lib):
+    """1000 environments (31 full warps + a ragged one), 150 steps of Philox actions: every output
+    tensor, the extras and the rollout statistics against the scalar CPU oracle."""
+    from ai_safety_gridworlds_b200 import make_spec
+    name, kwargs, lo, hi = CASES[case]
+    spec = make_spec(name, autoreset_mode=mode, **kwargs)
+    N, T = 1000, 150
+    env = _venv(spec, N, mode, env_index_base=12345)
+    orc = oracle_lib.Oracle(spec, N)
+    orc.reset()
+    np.testing.assert_array_equal(_np(env.board), orc.board)
+    np.testing.assert_array_equal(_np(env.cube), orc.cube)
+    np.testing.assert_array_equal(_np(env.value_board), orc.value_board)
+    episodes = 0
+    length_sum = 0
+    ret_sum = np.zeros(spec.n_rewards)
+    env_steps = 0
+    reasons = np.zeros(4, np.int64)
+    for t in range(T):
+        a = env.random_actions(seed=7 + case, step=t, lo=lo, hi=hi)
+        a_ref = oracle_lib.random_actions(7 + case, t, 12345, lo, hi, N)
+        np.testing.assert_array_equal(_np(a), a_ref)          # Philox parity
+        was_last = orc.step_type == 2
+        pre = orc.observe()
+        env.step(a)
+        orc.step(a_ref)
+        ctx = "%s mode=%d t=%d" % (name, mode, t)
+        np.testing.assert_array_equal(_np(env.board), orc.board, err_msg=ctx)
+        np.testing.assert_array_equal(_np(env.cube), orc.cube, err_msg=ctx)
+        np.testing.assert_array_equal(_np(env.value_board), orc.value_board, err_msg=ctx)
+        np.testing.assert_array_equal(_np(env.step_type), orc.step_type, err_msg=ctx)
+        np.testing.assert_array_equal(_np(env.reason), orc.reason, err_msg=ctx)
+        np.testing.assert_array_equal(_np(env.terminated), orc.terminated, err_msg=ctx)
+        np.testing.assert_allclose(_np(env.reward), orc.reward, rtol=1e-6, atol=0, err_msg=ctx)
+        ex, ox = env.observe(), orc.observe()
+        np.testing.assert_array_equal(_np(ex["frame"]), ox["frame"], err_msg=ctx)
+        np.testing.assert_array_equal(_np(ex["pos"]), ox["pos"], err_msg=ctx)
+        np.testing.assert_array_equal(_np(ex["safety"]), ox["safety"], err_msg=ctx)
+        np.testing.assert_allclose(_np(ex["cumulative"]), ox["cumulative"], rtol=1e-6, atol=1e-5, err_msg=ctx)
+        if spec.metric_names:
+            np.testing.assert_allclose(_np(ex["metrics"]), ox["metrics"], rtol=1e-12, atol=1e-12, err_msg=ctx)
+        if name == "island_navigation_ex":
+            gd, gf = env.peek_fractions()
+            od, of_ = orc.fractions()
+            np.testing.assert_allclose(_np(gd), od, rtol=1e-12, atol=1e-13, err_msg=ctx)
+            np.testing.assert_allclose(_np(gf), of_, rtol=1e-12, atol=1e-13, err_msg=ctx)
+        # expected statistics from the oracle's view of the same rollout
+        stepped = ~was_last if mode == 0 else np.ones(N, bool)
+        env_steps += int(stepped.sum())
+        ended = orc.terminated.astype(bool)
+        episodes += int(ended.sum())
+        for r in range(4):
+            reasons[r] += int((orc.reason[ended] == r).sum())
+        if mode == 0:
+            length_sum += int(ox["frame"][ended].sum())
+            ret_sum += ox["cumulative"][ended].astype(np.float64).sum(0)
+        else:
+            # SAME_STEP: the state already shows the new episode; reconstruct from the pre-step view
+            length_sum += int((pre["frame"][ended] + 1).sum())
+            ret_sum += (pre["cumulative"][ended].astype(np.float64) + orc.reward[ended].astype(np.float64)).sum(0)
+    st = env.stats()
+    assert st["env_steps"] == env_steps
+    assert st["episodes"] == episodes and episodes > 0
+    assert st["length_sum"] == length_sum
+    assert [st["reasons"][k] for k in ("terminated", "max_steps", "interrupted", "quit")] == list(reasons)
+    np.testing.assert_allclose([st["return_sum"][k] for k in spec.reward_keys], ret_sum, rtol=1e-5, atol=1e-3)
+    env.clear_stats()
+    assert env.stats()["episodes"] == 0
+    env.close()
+    orc.close()
+
+
+def test_reset_mask_and_optional_outputs(oracle_lib):
+    """gw_reset with a mask restarts only the selected environments; NULL observation pointers are
+    honoured (nothing is written, nothing crashes)."""
+    from ai_safety_gridworlds_b200 import make_spec
+    spec = make_spec("island_navigation_ex", autoreset_mode=0)
+    N = 333
+    env = _venv(spec, N, 0, want_cube=False, want_value_board=False)
+    orc = oracle_lib.Oracle(spec, N)
+    orc.reset()
+    for t in range(12):
+        a = env.random_actions(3, t)
+        env.step(a)
+        orc.step(_np(a))
+    mask = (np.arange(N) % 3 == 0).astype(np.uint8)
+    env.reset(torch.from_numpy(mask))
+    orc.reset(mask)
+    np.testing.assert_array_equal(_np(env.board), orc.board)
+    sel = mask.astype(bool)
+    np.testing.assert_array_equal(_np(env.step_type)[sel], 0)
+    np.testing.assert_array_equal(_np(env.step_type)[~sel], orc.step_type[~sel])
+    ex, ox = env.observe(), orc.observe()
+    np.testing.assert_array_equal(_np(ex["frame"]), ox["frame"])
+    assert env.cube is None and env.value_board is None
+    env.close()
+
+
+def test_full_size_properties():
+    """Config-3 sized batch (131,072 environments per GPU x 8 = 1,048,576; here the whole million on
+    one GPU): size-independent invariants of the rendered tensors and the statistics."""
+    N = 1 << 20
+    env = _venv("island_navigation_ex", N, 1)
+    L = env.spec.n_layers
+    lay = {ch: i for i, ch in enumerate(env.spec.layer_order)}
+    steps = 0
+    for t in range(30):
+        env.step(env.random_actions(11, t))
+        steps += N
+    cube = env.cube.view(N, L, -1)
+    board = env.board.view(N, -1)
+    # exactly one agent per environment, on the board where the cube says so
+    assert torch.all(cube[:, lay["A"]].sum(1) == 1)
+    apos = cube[:, lay["A"]].argmax(1)
+    assert torch.all(board.gather(1, apos[:, None]) == ord("A"))
+    # the gap layer never overlaps another layer; every cell is covered by >= 1 layer
+    others = cube.sum(1) - cube[:, lay[" "]]
+    assert torch.all((cube[:, lay[" "]] == 1) <= (others == 0))
+    assert torch.all(cube.sum(1) >= 1)
+    # static drapes: wall and water layers equal the level map in every environment
+    art = np.frombuffer("".join(env.spec.art).encode(), np.uint8)
+    for ch in "#W":
+        want = torch.from_numpy((art == ord(ch)).astype(np.uint8)).to(env.device)
+        assert torch.all(cube[:, lay[ch]] == want[None])
+    # value board is the LUT of the board
+    lut = torch.zeros(256, dtype=torch.float32, device=env.device)
+    for ch, v in env.spec.value_mapping.items():
+        lut[ord(ch)] = v
+    assert torch.equal(lut[board.long()], env.value_board.view(N, -1))
+    st = env.stats()
+    assert st["env_steps"] == steps
+    ex = env.observe()
+    # every running episode's frame counter is below the cut-off and >= 0
+    assert int(ex["frame"].max()) < env.spec.config.max_iterations and int(ex["frame"].min()) >= 0
+    # conservation: finished-episode lengths + running frames == steps taken
+    assert st["length_sum"] + int(ex["frame"].long().sum()) == steps
+    env.close()
+
+
+def test_sharding_invariance():
+    """Two half-size shards with env_index_base offsets reproduce one full-size batch exactly
+    (Philox streams are keyed by the global environment index), and their raw statistics add up
+    to the full batch's -- the property the multi-GPU all-reduce relies on."""
+    N = 4096
+    full = _venv("boat_race_ex", N, 1, level=3)
+    lo = _venv("boat_race_ex", N // 2, 1, level=3, env_index_base=0)
+    hi = _venv("boat_race_ex", N // 2, 1, level=3, env_index_base=N // 2)
+    for t in range(120):
+        full.step(full.random_actions(5, t))
+        lo.step(lo.random_actions(5, t))
+        hi.step(hi.random_actions(5, t))
+    assert torch.equal(full.board[: N // 2], lo.board) and torch.equal(full.board[N // 2:], hi.board)
+    assert torch.equal(full.reward[N // 2:], hi.reward)
+    raw = lo.stats_raw_device().clone() + hi.stats_raw_device()
+    assert torch.equal(raw, full.stats_raw_device())
+    for e in (full, lo, hi):
+        e.close()
+
+
+def test_bad_arguments_fail_loudly():
+    from ai_safety_gridworlds_b200 import _abi
+    env = _venv("island_navigation_ex", 64, 1)
+    with pytest.raises(ValueError):
+        env.step(torch.zeros(64, dtype=torch.int64, device=env.device))
+    with pytest.raises(ValueError):
+        env.step(torch.zeros(63, dtype=torch.int32, device=env.device))
+    import ctypes as C
+    rc = env._lib.gw_step(env._h, None, C.c_void_p(env.state.data_ptr()), None, None, None)
+    assert rc == _abi.GW_ERR_INVALID and b"null actions" in env._lib.gw_last_error()
+    env.close()
