@@ -105,7 +105,8 @@ SYMBOLS = [
     ("gw_launch_count", C.c_int64, [C.c_void_p]),
 ]
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libgwsim.so")
+# GWSIM_LIB lets a developer A/B another in-tree build of the same ABI (kernel tuning experiments)
+LIB_PATH = os.environ.get("GWSIM_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libgwsim.so")
 _lib = None
 
 

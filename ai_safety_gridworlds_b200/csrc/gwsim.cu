@@ -27,6 +27,7 @@
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -35,7 +36,14 @@
 #include "../../include/gwsim.h"
 
 #define GW_BLOCK 256
+#ifndef GW_MIN_BLOCKS
+#define GW_MIN_BLOCKS 4      /* <= 64 registers per thread: 4 CTAs (32 warps) per SM */
+#endif
 #define GW_WARPS (GW_BLOCK / 32)
+#ifndef GW_PBLOCK
+#define GW_PBLOCK 128        /* persistent TMA kernel: 4 warps per CTA */
+#endif
+#define GW_PWARPS (GW_PBLOCK / 32)
 #define GW_STAT_REPLICAS 64
 #define FULL 0xffffffffu
 
@@ -82,10 +90,15 @@ struct DevCfg {
   uint64_t water_mask;        /* island: W cells, for environment_data['safety'] */
   float value_agent;          /* value_mapping['A'] */
   int32_t pad2;
+  const float* reward_lut;    /* island, non-proportional: [GW_LUT_ROWS][GW_MAX_REWARDS] reward rows */
   ObsTensor board, cube, value;
   int32_t iparams[16];
   int32_t metric_slots[GW_MAX_METRICS];
   uint8_t art[GW_MAX_CELLS];
+  /* per reward dimension d: the events with a non-zero table entry, in the_plot.add_reward call-site
+   * order, rw_evt[rw_start[d] .. rw_start[d + 1]) -- the reward row is a sparse sum over these */
+  uint8_t rw_start[GW_MAX_REWARDS + 4];
+  uint8_t rw_evt[GW_MAX_EVENTS * GW_MAX_REWARDS];
   double fparams[16];
   double table[GW_MAX_EVENTS][GW_MAX_REWARDS];
 };
@@ -114,6 +127,8 @@ struct GwEngine {
   void* d_tmpl;                       /* all templates, one allocation */
   unsigned long long* d_stats;
   int64_t launches;
+  int sm_count;
+  int step_impl;                      /* 0 = persistent TMA kernel (product), 1 = direct stores (GWSIM_STEP_IMPL=direct) */
 };
 
 /* ------------------------------------------------------------------------------------------ */
@@ -212,16 +227,56 @@ __device__ __forceinline__ void flush_rewards(const float* __restrict__ s_rw, fl
 
 /* Statistics: exact integer sums.  Every lane contributes the accumulators of an episode that
  * ended in this call (else zeros); REDUX reduces each slot over the warp and lane k issues one
- * red.global for slot k into a replica row chosen by block index. */
+ * red.global for slot k into a replica row chosen by block index.  Slots are classed per game so
+ * that the warp spends one REDUX per 16-bit counter, packs the 0/1 slots five to a REDUX (6-bit
+ * fields, 32 lanes) and splits only genuinely 32-bit slots. */
+enum { SC_ZERO = 0, SC_BIT = 1, SC_SMALL = 2 /* |v| < 2^17 */, SC_WIDE = 3 };
+
+__host__ __device__ constexpr int slot_class(int kind, int k) {
+  if (k == GW_RAW_ENV_STEPS || k == GW_RAW_EPISODES || (k >= GW_RAW_REASON0 && k < GW_RAW_REASON0 + 4)) return SC_BIT;
+  if (k == GW_RAW_LENGTH_SUM) return SC_SMALL;
+  if (k < GW_RAW_EVENT0) return SC_ZERO;
+  const int e = k - GW_RAW_EVENT0;
+  if (kind <= 1) {
+    if (e == GW_ISL_E_FINAL || e == GW_ISL_E_DANGER_TILE || e == GW_ISL_E_THIRST_HUNGER_DEATH) return SC_BIT;
+    if (kind == 1 && (e == GW_ISL_E_DRINK_DEFICIENCY || e == GW_ISL_E_FOOD_DEFICIENCY || e == GW_ISL_E_DRINK_OVERSATIATION ||
+                      e == GW_ISL_E_FOOD_OVERSATIATION)) return SC_ZERO;
+    return e < GW_ISL_N_EVENTS ? SC_SMALL : SC_ZERO;
+  }
+  if (e == GW_BOAT_E_FINAL) return SC_BIT;
+  if (e == GW_BOAT_E_REPETITION) return SC_WIDE;
+  return e < GW_BOAT_N_EVENTS ? SC_SMALL : SC_ZERO;
+}
+
+__host__ __device__ constexpr int bit_index(int kind, int k) {   /* rank of slot k among the SC_BIT slots */
+  int n = 0;
+  for (int j = 0; j < k; ++j) n += slot_class(kind, j) == SC_BIT;
+  return n;
+}
+
+template <int KIND>
 __device__ __forceinline__ void warp_stats(unsigned long long* __restrict__ stats, const int32_t* vals /*[24]*/,
                                            uint32_t lane) {
   long long mine = 0;
+  constexpr int NBITS = bit_index(KIND, 24), NPACK = (NBITS + 4) / 5;
+  uint32_t pack[NPACK > 0 ? NPACK : 1] = {0};
+#pragma unroll
+  for (int k = 0; k < 24; ++k)
+    if (slot_class(KIND, k) == SC_BIT) pack[bit_index(KIND, k) / 5] |= (uint32_t)(vals[k] & 1) << (6 * (bit_index(KIND, k) % 5));
+#pragma unroll
+  for (int w = 0; w < NPACK; ++w) pack[w] = __reduce_add_sync(FULL, pack[w]);
 #pragma unroll
   for (int k = 0; k < 24; ++k) {
-    /* 16-bit halves so that 32 lanes of a full-range int32 cannot overflow the 32-bit REDUX */
-    const int32_t lo = __reduce_add_sync(FULL, vals[k] & 0xffff);
-    const int32_t hi = __reduce_add_sync(FULL, vals[k] >> 16);
-    if (lane == (uint32_t)k) mine = ((long long)hi << 16) + (long long)lo;
+    if (slot_class(KIND, k) == SC_BIT) {
+      if (lane == (uint32_t)k) mine = (pack[bit_index(KIND, k) / 5] >> (6 * (bit_index(KIND, k) % 5))) & 63u;
+    } else if (slot_class(KIND, k) == SC_SMALL) {
+      const int32_t r = __reduce_add_sync(FULL, vals[k]);
+      if (lane == (uint32_t)k) mine = r;
+    } else if (slot_class(KIND, k) == SC_WIDE) {
+      const int32_t lo = __reduce_add_sync(FULL, vals[k] & 0xffff);
+      const int32_t hi = __reduce_add_sync(FULL, vals[k] >> 16);
+      if (lane == (uint32_t)k) mine = ((long long)hi << 16) + (long long)lo;
+    }
   }
   if (lane < 24 && mine != 0) {
     unsigned long long* row = stats + (blockIdx.x & (GW_STAT_REPLICAS - 1)) * GW_STATS_RAW_LEN;
@@ -254,9 +309,8 @@ struct Island {
 };
 
 template <bool PROP>
-__device__ __forceinline__ void island_load(Island& s, const uint4* __restrict__ st, int64_t n, int64_t env) {
-  const uint4 w0 = ld_state(st + env), w1 = ld_state(st + n + env), w2 = ld_state(st + 2 * n + env),
-              w3 = ld_state(st + 3 * n + env), w4 = ld_state(st + 4 * n + env);
+__device__ __forceinline__ void island_unpack(Island& s, const uint4* w) {
+  const uint4 w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
   s.cell = w0.x & 0xff; s.st = ST_OF(w0.x); s.reason1 = REASON1_OF(w0.x); s.valid = (w0.x >> 13) & 1u; s.frame = w0.x >> 16;
   s.gap = w0.y & 0xffff; s.dvis = w0.y >> 16; s.fvis = w0.z & 0xffff; s.gvis = w0.z >> 16; s.svis = w0.w & 0xffff; s.moves = w0.w >> 16;
   s.dtaken = w1.x & 0xffff; s.ftaken = w1.x >> 16; s.ddef = w1.y & 0xffff; s.dover = w1.y >> 16;
@@ -264,8 +318,8 @@ __device__ __forceinline__ void island_load(Island& s, const uint4* __restrict__
   s.dsat = u2d(w2.x, w2.y); s.fsat = u2d(w2.z, w2.w);
   s.dav = u2d(w3.x, w3.y); s.fav = u2d(w3.z, w3.w);
   s.dfr = u2d(w4.x, w4.y); s.ffr = u2d(w4.z, w4.w);
-  if (PROP) {
-    const uint4 w5 = ld_state(st + 5 * n + env), w6 = ld_state(st + 6 * n + env);
+  if constexpr (PROP) {
+    const uint4 w5 = w[5], w6 = w[6];
     s.pdd = u2d(w5.x, w5.y); s.pdo = u2d(w5.z, w5.w); s.pfd = u2d(w6.x, w6.y); s.pfo = u2d(w6.z, w6.w);
   } else {
     s.pdd = s.pdo = s.pfd = s.pfo = 0.0;
@@ -333,14 +387,27 @@ __device__ __forceinline__ void island_acc(const Island& s, int32_t* acc /*[16]*
 }
 
 /* DrinkDrape.update / FoodDrape.update for a step frame (iteration_index == frame > 0)
- * (island_navigation_ex.py:638-660,682-704). */
-__device__ __forceinline__ void island_regrow(double& avail, double& frac, bool on_tile, bool sustain, double initial,
-                                              double test_limit, double growth_limit, double exponent) {
-  if (!sustain) avail = initial;
-  if (!on_tile && avail > 0.0 && avail < test_limit) {
-    double x = fmin(growth_limit, pow(avail + frac + 1.0, exponent));
-    avail = (double)(long long)x;
-    frac = x - avail;
+ * (island_navigation_ex.py:638-660,682-704).  Both drapes use the DRINK regrowth exponent (a
+ * reference quirk), so one pow() call site serves whichever resource of this lane regrows; the
+ * second call only runs for lanes where both do. */
+__device__ __forceinline__ void island_regrow_both(Island& s, const DevCfg& c, uint8_t here) {
+  const double* F = c.fparams;
+  if (!c.iparams[GW_ISL_I_SUSTAINABILITY]) {
+    s.dav = F[GW_ISL_F_DRINK_AVAILABILITY_INITIAL];
+    s.fav = F[GW_ISL_F_FOOD_AVAILABILITY_INITIAL];
+  }
+  bool need_d = here != 'D' && s.dav > 0.0 && s.dav < F[GW_ISL_F_DRINK_GROWTH_LIMIT_MODULE_CONST];
+  bool need_f = here != 'F' && s.fav > 0.0 && s.fav < F[GW_ISL_F_FOOD_GROWTH_LIMIT];
+  const double expo = F[GW_ISL_F_DRINK_REGROWTH_EXPONENT];
+#pragma unroll 1
+  while (need_d || need_f) {
+    const bool do_d = need_d;
+    const double base = do_d ? s.dav + s.dfr + 1.0 : s.fav + s.ffr + 1.0;
+    const double limit = do_d ? F[GW_ISL_F_DRINK_GROWTH_LIMIT] : F[GW_ISL_F_FOOD_GROWTH_LIMIT];
+    const double x = fmin(limit, pow(base, expo));
+    const double whole = (double)(long long)x;
+    if (do_d) { s.dav = whole; s.dfr = x - whole; need_d = false; }
+    else { s.fav = whole; s.ffr = x - whole; need_f = false; }
   }
 }
 
@@ -419,35 +486,32 @@ __device__ __forceinline__ uint32_t island_frame(Island& s, const DevCfg& c, con
   if (here == 'W') {                                          /* WaterDrape.update :602-608 */
     fired |= 1u << GW_ISL_E_DANGER_TILE; s.once |= 2u; term = true; s.reason1 = GW_REASON_TERMINATED + 1;
   }
-  const bool sustain = c.iparams[GW_ISL_I_SUSTAINABILITY] != 0;
-  island_regrow(s.dav, s.dfr, here == 'D', sustain, F[GW_ISL_F_DRINK_AVAILABILITY_INITIAL],
-                F[GW_ISL_F_DRINK_GROWTH_LIMIT_MODULE_CONST], F[GW_ISL_F_DRINK_GROWTH_LIMIT], F[GW_ISL_F_DRINK_REGROWTH_EXPONENT]);
-  island_regrow(s.fav, s.ffr, here == 'F', sustain, F[GW_ISL_F_FOOD_AVAILABILITY_INITIAL],
-                F[GW_ISL_F_FOOD_GROWTH_LIMIT], F[GW_ISL_F_FOOD_GROWTH_LIMIT], F[GW_ISL_F_DRINK_REGROWTH_EXPONENT]);
+  island_regrow_both(s, c, here);
   return fired;
 }
 
-/* the_plot.add_reward order of one island frame (plot_mo.py:26-51): the call-site order of
- * update_reward followed by WaterDrape, so the float sums associate as in the reference. */
-__device__ __forceinline__ void island_reward_rows(const DevCfg& c, uint32_t fired, double sD, double sF,
-                                                   float* __restrict__ row) {
-  const int order[GW_ISL_N_EVENTS] = {GW_ISL_E_MOVEMENT, GW_ISL_E_THIRST_HUNGER_DEATH, GW_ISL_E_FINAL, GW_ISL_E_DRINK,
-                                      GW_ISL_E_NON_DRINK, GW_ISL_E_FOOD, GW_ISL_E_NON_FOOD, GW_ISL_E_GOLD, GW_ISL_E_SILVER,
-                                      GW_ISL_E_GAP, GW_ISL_E_DRINK_DEFICIENCY, GW_ISL_E_DRINK_OVERSATIATION,
-                                      GW_ISL_E_FOOD_DEFICIENCY, GW_ISL_E_FOOD_OVERSATIATION, GW_ISL_E_DANGER_TILE};
-#pragma unroll
-  for (int d = 0; d < GW_MAX_REWARDS; ++d) {
-    if (d < c.n_rewards) {
-      double r = 0.0;
-#pragma unroll
-      for (int k = 0; k < GW_ISL_N_EVENTS; ++k) {
-        const int e = order[k];
-        const double scale = (e == GW_ISL_E_DRINK_DEFICIENCY || e == GW_ISL_E_DRINK_OVERSATIATION) ? sD
-                           : (e == GW_ISL_E_FOOD_DEFICIENCY || e == GW_ISL_E_FOOD_OVERSATIATION) ? sF : 1.0;
-        if (fired & (1u << e)) r += c.table[e][d] * scale;
+/* The reward row of one frame: for each enabled dimension the sparse sum, in the_plot.add_reward
+ * call-site order (plot_mo.py:26-51), over the events that fired.  Summed in fp64 like the
+ * reference's mo_reward algebra, emitted as fp32.  SCALED: two events pairs carry a real scale
+ * (island: satiation-proportional deficiency / oversatiation of drink = sA, of food = sB;
+ * boat: repetition count = sA, clockwise sign = sB). */
+template <int KIND>
+__device__ __forceinline__ void reward_row(const DevCfg& c, uint32_t fired, double sA, double sB, float* __restrict__ row) {
+  for (int d = 0; d < c.n_rewards; ++d) {
+    double r = 0.0;
+    for (int j = c.rw_start[d]; j < c.rw_start[d + 1]; ++j) {
+      const int e = c.rw_evt[j];                       /* uniform: the lists are per type, not per lane */
+      double v = c.table[e][d];
+      if constexpr (KIND == 1) {
+        if (e == GW_ISL_E_DRINK_DEFICIENCY || e == GW_ISL_E_DRINK_OVERSATIATION) v *= sA;
+        else if (e == GW_ISL_E_FOOD_DEFICIENCY || e == GW_ISL_E_FOOD_OVERSATIATION) v *= sB;
+      } else if constexpr (KIND >= 2) {
+        if (e == GW_BOAT_E_REPETITION) v *= sA;
+        else if (e == GW_BOAT_E_CLOCKWISE) v *= sB;
       }
-      row[d] = (float)r;
+      if ((fired >> e) & 1u) r += v;
     }
+    row[d] = (float)r;
   }
 }
 
@@ -462,15 +526,14 @@ struct Boat {
 };
 
 template <int BITS>
-__device__ __forceinline__ void boat_load(Boat<BITS>& s, const uint4* __restrict__ st, int64_t n, int64_t env) {
-  const uint4 w0 = ld_state(st + env);
+__device__ __forceinline__ void boat_unpack(Boat<BITS>& s, const uint4* w) {
+  const uint4 w0 = w[0];
   s.cell = w0.x & 0xff; s.st = ST_OF(w0.x); s.reason1 = REASON1_OF(w0.x); s.final_bit = (w0.x >> 14) & 1u; s.frame = w0.x >> 16;
   s.moves = w0.y & 0xffff; s.humans = w0.y >> 16; s.cw_net = (int32_t)w0.z; s.rep_sum = w0.w;
   constexpr int NW = BITS == 8 ? 4 : 8;
 #pragma unroll
   for (int k = 0; k < NW; ++k) {
-    const uint4 w = ld_state(st + (1 + k) * n + env);
-    s.cnt[4 * k] = w.x; s.cnt[4 * k + 1] = w.y; s.cnt[4 * k + 2] = w.z; s.cnt[4 * k + 3] = w.w;
+    s.cnt[4 * k] = w[1 + k].x; s.cnt[4 * k + 1] = w[1 + k].y; s.cnt[4 * k + 2] = w[1 + k].z; s.cnt[4 * k + 3] = w[1 + k].w;
   }
 }
 
@@ -534,14 +597,13 @@ __device__ __forceinline__ int32_t arrow_delta(uint8_t ch, int32_t width) {
 }
 
 /* One frame of boat_race_ex: AgentSprite.update / update_reward (boat_race_ex.py:201-257).
- * Writes the reward row directly (event order = call-site order). */
+ * Returns the fired-event mask; sRep = repetition count, sCw = clockwise sign. */
 template <int BITS>
-__device__ __forceinline__ void boat_frame(Boat<BITS>& s, const DevCfg& c, const uint8_t* __restrict__ s_art, int32_t act,
-                                           bool& term, float* __restrict__ row) {
+__device__ __forceinline__ uint32_t boat_frame(Boat<BITS>& s, const DevCfg& c, const uint8_t* __restrict__ s_art, int32_t act,
+                                               bool& term, double& sRep, double& sCw) {
   s.frame += 1;
-  double sc[GW_BOAT_N_EVENTS];
-#pragma unroll
-  for (int e = 0; e < GW_BOAT_N_EVENTS; ++e) sc[e] = 0.0;
+  uint32_t fired = 0;
+  sRep = 0.0; sCw = 0.0;
   if (act == GW_ACT_QUIT) {
     s.reason1 = GW_REASON_QUIT + 1;
     term = true;
@@ -554,40 +616,24 @@ __device__ __forceinline__ void boat_frame(Boat<BITS>& s, const DevCfg& c, const
       const int32_t delta = act == GW_ACT_LEFT ? -1 : act == GW_ACT_RIGHT ? 1 : act == GW_ACT_UP ? -c.width : c.width;
       if ((can >> s.cell) & 1ull) { s.cell = (uint32_t)((int32_t)s.cell + delta); moved = delta; }
     }
-    if (act != GW_ACT_NOOP) { sc[GW_BOAT_E_MOVEMENT] = 1.0; s.moves += 1; }
-    if (c.iparams[GW_BOAT_I_ITERATIONS_PENALTY]) sc[GW_BOAT_E_ITERATIONS] = 1.0;
+    if (act != GW_ACT_NOOP) { fired |= 1u << GW_BOAT_E_MOVEMENT; s.moves += 1; }
+    if (c.iparams[GW_BOAT_I_ITERATIONS_PENALTY]) fired |= 1u << GW_BOAT_E_ITERATIONS;
     if (c.iparams[GW_BOAT_I_REPETITION_PENALTY]) {
       const uint32_t cnt = boat_count_get(s, s.cell);
-      if (cnt > 0) { sc[GW_BOAT_E_REPETITION] = (double)cnt; s.rep_sum += cnt; }
+      if (cnt > 0) { fired |= 1u << GW_BOAT_E_REPETITION; sRep = (double)cnt; s.rep_sum += cnt; }
       boat_count_inc(s, s.cell);
     }
     const uint8_t ch = s_art[s.cell], pch = s_art[prev];
     if (pch != ch) {                                           /* implies the agent moved */
-      if (is_arrow(ch)) {
-        const int32_t sgn = arrow_delta(ch, c.width) == moved ? 1 : -1;
-        sc[GW_BOAT_E_CLOCKWISE] = (double)sgn; s.cw_net += sgn;
-      } else if (is_arrow(pch)) {
-        const int32_t sgn = (moved != 0 && arrow_delta(pch, c.width) == moved) ? 1 : -1;
-        sc[GW_BOAT_E_CLOCKWISE] = (double)sgn; s.cw_net += sgn;
-      }
+      int32_t sgn = 0;
+      if (is_arrow(ch)) sgn = arrow_delta(ch, c.width) == moved ? 1 : -1;
+      else if (is_arrow(pch)) sgn = (moved != 0 && arrow_delta(pch, c.width) == moved) ? 1 : -1;
+      if (sgn != 0) { fired |= 1u << GW_BOAT_E_CLOCKWISE; sCw = (double)sgn; s.cw_net += sgn; }
     }
-    if (ch == 'G') { sc[GW_BOAT_E_FINAL] = 1.0; s.final_bit = 1; term = true; s.reason1 = GW_REASON_TERMINATED + 1; }
-    else if (ch == 'H') { sc[GW_BOAT_E_HUMAN] = 1.0; s.humans += 1; }
+    if (ch == 'G') { fired |= 1u << GW_BOAT_E_FINAL; s.final_bit = 1; term = true; s.reason1 = GW_REASON_TERMINATED + 1; }
+    else if (ch == 'H') { fired |= 1u << GW_BOAT_E_HUMAN; s.humans += 1; }
   }
-  const int order[GW_BOAT_N_EVENTS] = {GW_BOAT_E_MOVEMENT, GW_BOAT_E_ITERATIONS, GW_BOAT_E_REPETITION, GW_BOAT_E_CLOCKWISE,
-                                       GW_BOAT_E_FINAL, GW_BOAT_E_HUMAN};
-#pragma unroll
-  for (int d = 0; d < GW_MAX_REWARDS; ++d) {
-    if (d < c.n_rewards) {
-      double r = 0.0;
-#pragma unroll
-      for (int k = 0; k < GW_BOAT_N_EVENTS; ++k) {
-        const int e = order[k];
-        if (sc[e] != 0.0) r += c.table[e][d] * sc[e];
-      }
-      row[d] = (float)r;
-    }
-  }
+  return fired;
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -599,11 +645,28 @@ template <> struct GameOf<1> { typedef Island State; };
 template <> struct GameOf<2> { typedef Boat<8> State; };
 template <> struct GameOf<3> { typedef Boat<16> State; };
 
+/* the raw state words + action of one environment, as loaded (prefetchable one chunk ahead) */
+template <int KIND> struct Raw {
+  static constexpr int NW = KIND == 0 ? 5 : KIND == 1 ? 7 : KIND == 2 ? 5 : 9;
+  uint4 w[NW];
+  int32_t act;
+};
+template <int KIND> __device__ __forceinline__ void raw_load(Raw<KIND>& r, const uint4* __restrict__ st, int64_t n, int64_t env,
+                                                             const int32_t* __restrict__ actions) {
+#pragma unroll
+  for (int k = 0; k < Raw<KIND>::NW; ++k) r.w[k] = ld_state(st + (int64_t)k * n + env);
+  r.act = actions ? __ldg(actions + env) : 0;
+}
+template <int KIND> __device__ __forceinline__ void g_unpack(typename GameOf<KIND>::State& s, const Raw<KIND>& r) {
+  if constexpr (KIND == 0) island_unpack<false>(s, r.w);
+  else if constexpr (KIND == 1) island_unpack<true>(s, r.w);
+  else if constexpr (KIND == 2) boat_unpack<8>(s, r.w);
+  else boat_unpack<16>(s, r.w);
+}
 template <int KIND> __device__ __forceinline__ void g_load(typename GameOf<KIND>::State& s, const uint4* st, int64_t n, int64_t env) {
-  if constexpr (KIND == 0) island_load<false>(s, st, n, env);
-  else if constexpr (KIND == 1) island_load<true>(s, st, n, env);
-  else if constexpr (KIND == 2) boat_load<8>(s, st, n, env);
-  else boat_load<16>(s, st, n, env);
+  Raw<KIND> r;
+  raw_load<KIND>(r, st, n, env, nullptr);
+  g_unpack<KIND>(s, r);
 }
 template <int KIND> __device__ __forceinline__ void g_store(const typename GameOf<KIND>::State& s, uint4* st, int64_t n, int64_t env) {
   if constexpr (KIND == 0) island_store<false>(s, st, n, env);
@@ -623,8 +686,113 @@ template <int KIND> __device__ __forceinline__ void g_acc(const typename GameOf<
   else boat_acc<16>(s, c, acc);
 }
 
+/* island_navigation_ex without satiation-proportional rewards: every fired-event mask a frame
+ * can produce is one of 360 combinations (tile class x moved x drink state x food state x death),
+ * so the reward row is a table lookup.  The host builds the table with the same sparse
+ * call-order sum as reward_row, row by row, hence bit-identical results. */
+#define GW_LUT_ROWS 360
+__host__ __device__ __forceinline__ uint32_t island_lut_index(uint32_t fired) {
+  auto bit = [&](int e) { return (fired >> e) & 1u; };
+  const uint32_t tile = bit(GW_ISL_E_DRINK) ? 1u : bit(GW_ISL_E_FOOD) ? 3u : bit(GW_ISL_E_GOLD) ? 5u : bit(GW_ISL_E_SILVER) ? 6u
+                      : bit(GW_ISL_E_FINAL) ? 7u : bit(GW_ISL_E_DANGER_TILE) ? 8u : bit(GW_ISL_E_GAP) ? 0u
+                      : (bit(GW_ISL_E_NON_FOOD) && !bit(GW_ISL_E_NON_DRINK)) ? 2u
+                      : (bit(GW_ISL_E_NON_DRINK) && !bit(GW_ISL_E_NON_FOOD)) ? 4u : 9u;
+  const uint32_t ds = bit(GW_ISL_E_DRINK_DEFICIENCY) ? 1u : bit(GW_ISL_E_DRINK_OVERSATIATION) ? 2u : 0u;
+  const uint32_t fs = bit(GW_ISL_E_FOOD_DEFICIENCY) ? 1u : bit(GW_ISL_E_FOOD_OVERSATIATION) ? 2u : 0u;
+  return (((tile * 2u + bit(GW_ISL_E_MOVEMENT)) * 3u + ds) * 3u + fs) * 2u + bit(GW_ISL_E_THIRST_HUNGER_DEATH);
+}
+/* the inverse, host side: the fired mask of LUT row `idx` */
+static inline uint32_t island_lut_mask(uint32_t idx) {
+  const uint32_t death = idx % 2; idx /= 2;
+  const uint32_t fs = idx % 3; idx /= 3;
+  const uint32_t ds = idx % 3; idx /= 3;
+  const uint32_t moved = idx % 2; idx /= 2;
+  const uint32_t tile = idx;
+  uint32_t m = 0;
+  auto set = [&](int e) { m |= 1u << e; };
+  switch (tile) {
+    case 0: set(GW_ISL_E_GAP); set(GW_ISL_E_NON_DRINK); set(GW_ISL_E_NON_FOOD); break;
+    case 1: set(GW_ISL_E_DRINK); set(GW_ISL_E_NON_FOOD); break;
+    case 2: set(GW_ISL_E_NON_FOOD); break;
+    case 3: set(GW_ISL_E_FOOD); set(GW_ISL_E_NON_DRINK); break;
+    case 4: set(GW_ISL_E_NON_DRINK); break;
+    case 5: set(GW_ISL_E_GOLD); set(GW_ISL_E_NON_DRINK); set(GW_ISL_E_NON_FOOD); break;
+    case 6: set(GW_ISL_E_SILVER); set(GW_ISL_E_NON_DRINK); set(GW_ISL_E_NON_FOOD); break;
+    case 7: set(GW_ISL_E_FINAL); set(GW_ISL_E_NON_DRINK); set(GW_ISL_E_NON_FOOD); break;
+    case 8: set(GW_ISL_E_DANGER_TILE); set(GW_ISL_E_NON_DRINK); set(GW_ISL_E_NON_FOOD); break;
+    default: break;                               /* QUIT frame, walls: nothing tile-related fires */
+  }
+  if (moved) set(GW_ISL_E_MOVEMENT);
+  if (ds == 1) set(GW_ISL_E_DRINK_DEFICIENCY); else if (ds == 2) set(GW_ISL_E_DRINK_OVERSATIATION);
+  if (fs == 1) set(GW_ISL_E_FOOD_DEFICIENCY); else if (fs == 2) set(GW_ISL_E_FOOD_OVERSATIATION);
+  if (death) set(GW_ISL_E_THIRST_HUNGER_DEATH);
+  return m;
+}
+
+/* Phase 1 for one lane: EnvironmentMo.step + Engine.play + _process_timestep of environment
+ * `env` (rl/pycolab_interface_mo.py:157-196,308-319; pycolab/engine.py:583-759;
+ * safety_game_mo.py:971-1084).  Loads and stores the state planes, writes the reward row into the
+ * warp's shared-memory staging rows and the per-environment flags, fills this lane's statistics
+ * contribution, and returns the agent cell the observation must show. */
 template <int KIND>
-__global__ void __launch_bounds__(GW_BLOCK) gw_step_kernel(const __grid_constant__ DevCfg c, const StepArgs a) {
+__device__ __forceinline__ uint32_t step_lane(const DevCfg& c, const StepArgs& a, const uint8_t* __restrict__ s_art,
+                                              int64_t env, const Raw<KIND>& raw, float* __restrict__ row, int32_t* sv /*[24]*/,
+                                              double* fs /*[4]*/) {
+  const uint32_t R = (uint32_t)c.n_rewards;
+  typename GameOf<KIND>::State s;
+  g_unpack<KIND>(s, raw);
+  if (s.cell >= (uint32_t)c.cells) s.cell = (uint32_t)c.start_cell;   /* never index outside the board on garbage state */
+  const int32_t act = raw.act;
+  uint32_t out_st, out_reason1;
+  if (s.st == GW_STEP_LAST) {
+    /* rl/pycolab_interface_mo.py:175-178: the call after LAST rebuilds the game, ignores the
+     * action and returns the FIRST timestep */
+    g_reset<KIND>(s, c);
+    for (uint32_t d = 0; d < R; ++d) row[d] = 0.0f;
+    out_st = GW_STEP_FIRST; out_reason1 = 0;
+  } else {
+    bool term = false;
+    double sA, sB;
+    uint32_t fired;
+    if constexpr (KIND <= 1) fired = island_frame<KIND == 1>(s, c, s_art, act, term, sA, sB);
+    else fired = boat_frame(s, c, s_art, act, term, sA, sB);
+    if constexpr (KIND == 0) {
+      const float* __restrict__ lrow = c.reward_lut + island_lut_index(fired) * GW_MAX_REWARDS;
+      const float4 q0 = __ldg(reinterpret_cast<const float4*>(lrow)), q1 = __ldg(reinterpret_cast<const float4*>(lrow) + 1),
+                   q2 = __ldg(reinterpret_cast<const float4*>(lrow) + 2);
+      const float v[GW_MAX_REWARDS] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+#pragma unroll
+      for (int d = 0; d < GW_MAX_REWARDS; ++d) if (d < (int)R) row[d] = v[d];
+    } else {
+      reward_row<KIND>(c, fired, sA, sB, row);
+    }
+    const bool over = term || (int32_t)s.frame >= c.max_iterations;       /* pycolab_interface_mo.py:318-319 */
+    s.st = over ? GW_STEP_LAST : GW_STEP_MID;
+    if (over && s.reason1 == 0) s.reason1 = GW_REASON_MAX_STEPS + 1;      /* safety_game_mo.py:1004-1007 */
+    out_st = s.st; out_reason1 = s.reason1;
+    sv[GW_RAW_ENV_STEPS] = 1;
+    if (over) {
+      sv[GW_RAW_EPISODES] = 1;
+      sv[GW_RAW_LENGTH_SUM] = (int32_t)s.frame;
+      sv[GW_RAW_REASON0 + 0] = s.reason1 == 1; sv[GW_RAW_REASON0 + 1] = s.reason1 == 2;
+      sv[GW_RAW_REASON0 + 2] = s.reason1 == 3; sv[GW_RAW_REASON0 + 3] = s.reason1 == 4;
+      g_acc<KIND>(s, c, &sv[GW_RAW_EVENT0]);
+      if constexpr (KIND == 1) { fs[0] = s.pdd; fs[1] = s.pdo; fs[2] = s.pfd; fs[3] = s.pfo; }
+      if (c.autoreset == GW_AUTORESET_SAME_STEP) g_reset<KIND>(s, c);
+    }
+  }
+  g_store<KIND>(s, a.state, a.n, env);
+  if (a.terminated) a.terminated[env] = (uint8_t)(out_st == GW_STEP_LAST);
+  if (a.step_type) a.step_type[env] = (uint8_t)out_st;
+  if (a.reason) a.reason[env] = (int8_t)((int32_t)out_reason1 - 1);
+  return s.cell;
+}
+
+/* Direct-store variant: one warp = one 32-environment chunk, observation slices streamed with
+ * st.global.v4 straight from the (L1-resident) templates.  Kept for A/B measurements
+ * (GWSIM_STEP_IMPL=direct); the product path is gw_step_tma_kernel below. */
+template <int KIND>
+__global__ void __launch_bounds__(GW_BLOCK, GW_MIN_BLOCKS) gw_step_kernel(const __grid_constant__ DevCfg c, const StepArgs a) {
   __shared__ __align__(16) float s_reward[GW_WARPS][32 * GW_MAX_REWARDS];
   __shared__ uint8_t s_art[GW_MAX_CELLS];
   if (threadIdx.x < GW_MAX_CELLS) s_art[threadIdx.x] = c.art[threadIdx.x];
@@ -634,66 +802,195 @@ __global__ void __launch_bounds__(GW_BLOCK) gw_step_kernel(const __grid_constant
   const int64_t env0 = ((int64_t)blockIdx.x * GW_WARPS + warp) * 32;
   if (env0 >= a.n) return;
   const uint32_t nvalid = (uint32_t)min((int64_t)32, a.n - env0);
-  const int64_t env = env0 + lane;
-  const bool live = lane < nvalid;
   const uint32_t R = (uint32_t)c.n_rewards;
-  float* row = &s_reward[warp][lane * R];
 
-  typename GameOf<KIND>::State s;
   int32_t sv[24];
 #pragma unroll
   for (int k = 0; k < 24; ++k) sv[k] = 0;
   double fs[4] = {0.0, 0.0, 0.0, 0.0};
   uint32_t cell = 0;
-
-  if (live) {
-    g_load<KIND>(s, a.state, a.n, env);
-    if (s.cell >= (uint32_t)c.cells) s.cell = (uint32_t)c.start_cell;   /* never index outside the board on garbage state */
-    const int32_t act = a.actions[env];
-    uint32_t out_st, out_reason1;
-    if (s.st == GW_STEP_LAST) {
-      /* rl/pycolab_interface_mo.py:175-178: the call after LAST rebuilds the game, ignores the
-       * action and returns the FIRST timestep */
-      g_reset<KIND>(s, c);
-#pragma unroll
-      for (int d = 0; d < GW_MAX_REWARDS; ++d) if (d < (int)R) row[d] = 0.0f;
-      out_st = GW_STEP_FIRST; out_reason1 = 0;
-    } else {
-      bool term = false;
-      if constexpr (KIND <= 1) {
-        double sD, sF;
-        const uint32_t fired = island_frame<KIND == 1>(s, c, s_art, act, term, sD, sF);
-        island_reward_rows(c, fired, sD, sF, row);
-      } else {
-        boat_frame(s, c, s_art, act, term, row);
-      }
-      const bool over = term || (int32_t)s.frame >= c.max_iterations;       /* pycolab_interface_mo.py:318-319 */
-      s.st = over ? GW_STEP_LAST : GW_STEP_MID;
-      if (over && s.reason1 == 0) s.reason1 = GW_REASON_MAX_STEPS + 1;      /* safety_game_mo.py:1004-1007 */
-      out_st = s.st; out_reason1 = s.reason1;
-      sv[GW_RAW_ENV_STEPS] = 1;
-      if (over) {
-        sv[GW_RAW_EPISODES] = 1;
-        sv[GW_RAW_LENGTH_SUM] = (int32_t)s.frame;
-        sv[GW_RAW_REASON0 + 0] = s.reason1 == 1; sv[GW_RAW_REASON0 + 1] = s.reason1 == 2;
-        sv[GW_RAW_REASON0 + 2] = s.reason1 == 3; sv[GW_RAW_REASON0 + 3] = s.reason1 == 4;
-        g_acc<KIND>(s, c, &sv[GW_RAW_EVENT0]);
-        if constexpr (KIND == 1) { fs[0] = s.pdd; fs[1] = s.pdo; fs[2] = s.pfd; fs[3] = s.pfo; }
-        if (c.autoreset == GW_AUTORESET_SAME_STEP) g_reset<KIND>(s, c);
-      }
-    }
-    g_store<KIND>(s, a.state, a.n, env);
-    cell = s.cell;
-    if (a.terminated) a.terminated[env] = (uint8_t)(out_st == GW_STEP_LAST);
-    if (a.step_type) a.step_type[env] = (uint8_t)out_st;
-    if (a.reason) a.reason[env] = (int8_t)((int32_t)out_reason1 - 1);
+  if (lane < nvalid) {
+    Raw<KIND> raw;
+    raw_load<KIND>(raw, a.state, a.n, env0 + lane, a.actions);
+    cell = step_lane<KIND>(c, a, s_art, env0 + lane, raw, &s_reward[warp][lane * R], sv, fs);
   }
   if (a.reward) flush_rewards(s_reward[warp], a.reward, env0, nvalid, R, lane);
   if (a.stats) {
-    warp_stats(a.stats, sv, lane);
+    warp_stats<KIND>(a.stats, sv, lane);
     if constexpr (KIND == 1) warp_stats_scaled(a.stats, fs, lane);
   }
   emit_observation(c, a, env0, nvalid, lane, cell);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* The product step kernel: persistent warps + TMA bulk stores.
+ *
+ * Each warp owns a shared-memory staging buffer that holds, for 32 environments, the agent-free
+ * observation template of every requested tensor (written once per launch) plus 32 reward rows.
+ * Per 32-environment chunk the warp runs phase 1, moves the agent bytes in its staging buffer
+ * (un-patch the previous chunk's cells, patch the new ones: a handful of single-byte shared
+ * stores), and ONE lane hands the whole slice of each tensor -- 12 KB of cube, 1.5 KB of board,
+ * 1.3 KB of rewards for island_navigation_ex -- to the TMA engine with cp.async.bulk
+ * (shared -> global, SASS UBLKCP).  The SM issues ~30 instructions per chunk for what the direct
+ * variant needs ~450 for, and the stores drain while the warp computes its next chunk. */
+struct StageLayout {                 /* byte offsets inside one warp's staging buffer (128-byte aligned) */
+  uint32_t cube_off, board_off, value_off, reward_off, reward_bytes, warp_bytes;
+};
+
+__device__ __forceinline__ void fill_stage(uint8_t* __restrict__ dst, const ObsTensor& t, uint32_t lane) {
+  const uint32_t S = t.bytes_per_env, nq = (32u * S) >> 4;          /* 32 * S is a multiple of 16 */
+  for (uint32_t q = lane; q < nq; q += 32) {
+    const uint32_t b0 = q << 4;
+    const uint32_t off = b0 - __umulhi(b0, t.magic) * S;
+    reinterpret_cast<uint4*>(dst)[q] = __ldg(t.tmpl + (off & 15u) * t.entries + (off >> 4));
+  }
+}
+
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               :: "l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
+}
+
+/* per-lane statistics totals carried across the chunks of a persistent warp; reduced over the
+ * warp and pushed with red.global once per launch (or every GW_STAT_FLUSH chunks, so that the
+ * 32-bit per-lane totals cannot overflow) */
+#define GW_STAT_FLUSH 8192
+template <int KIND>
+__device__ __forceinline__ void stats_accumulate(int32_t* tot /*[24]*/, long long& wide, const int32_t* sv) {
+#pragma unroll
+  for (int k = 0; k < 24; ++k) {
+    if (slot_class(KIND, k) == SC_BIT || slot_class(KIND, k) == SC_SMALL) tot[k] += sv[k];
+    else if (slot_class(KIND, k) == SC_WIDE) wide += (long long)sv[k];
+  }
+}
+template <int KIND>
+__device__ __forceinline__ void stats_flush(unsigned long long* __restrict__ stats, int32_t* tot, long long& wide, uint32_t lane) {
+  long long mine = 0;
+#pragma unroll
+  for (int k = 0; k < 24; ++k) {
+    if (slot_class(KIND, k) == SC_BIT || slot_class(KIND, k) == SC_SMALL) {
+      const int32_t lo = __reduce_add_sync(FULL, tot[k] & 0xffff);
+      const int32_t hi = __reduce_add_sync(FULL, tot[k] >> 16);
+      if (lane == (uint32_t)k) mine = ((long long)hi << 16) + (long long)lo;
+      tot[k] = 0;
+    } else if (slot_class(KIND, k) == SC_WIDE) {
+      long long v = wide;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+      if (lane == (uint32_t)k) mine = v;
+      wide = 0;
+    }
+  }
+  if (lane < 24 && mine != 0) {
+    unsigned long long* row = stats + (blockIdx.x & (GW_STAT_REPLICAS - 1)) * GW_STATS_RAW_LEN;
+    atomicAdd(row + lane, (unsigned long long)mine);
+  }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(GW_PBLOCK) gw_step_tma_kernel(const __grid_constant__ DevCfg c, const StepArgs a,
+                                                                 const StageLayout L) {
+  extern __shared__ __align__(128) uint8_t stage[];
+  __shared__ uint8_t s_art[GW_MAX_CELLS];
+  __shared__ float s_val[GW_MAX_CELLS];          /* value-mapped template per cell (agent-free) */
+  if (threadIdx.x < GW_MAX_CELLS) {
+    s_art[threadIdx.x] = c.art[threadIdx.x];
+    s_val[threadIdx.x] = threadIdx.x < (uint32_t)c.cells ? reinterpret_cast<const float*>(c.value.tmpl)[threadIdx.x] : 0.0f;
+  }
+  __syncthreads();
+
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  uint8_t* wbuf = stage + warp * L.warp_bytes;
+  uint8_t* s_cube = wbuf + L.cube_off;
+  uint8_t* s_board = wbuf + L.board_off;
+  float* s_value = reinterpret_cast<float*>(wbuf + L.value_off);
+  if (a.cube) fill_stage(s_cube, c.cube, lane);
+  if (a.board) fill_stage(s_board, c.board, lane);
+  if (a.value_board) fill_stage(reinterpret_cast<uint8_t*>(s_value), c.value, lane);
+  __syncwarp();
+
+  const uint32_t R = (uint32_t)c.n_rewards, cells = (uint32_t)c.cells, Sc = c.cube.bytes_per_env;
+  const int64_t nchunks = (a.n + 31) >> 5;
+  const int64_t stride = (int64_t)gridDim.x * GW_PWARPS;
+  uint32_t staged_cell = 0xffffffffu;            /* the cell this lane's staged environment shows the agent on */
+  int32_t tot[24];
+#pragma unroll
+  for (int k = 0; k < 24; ++k) tot[k] = 0;
+  long long wide = 0;
+  double ftot[4] = {0.0, 0.0, 0.0, 0.0};
+  uint32_t since_flush = 0, parity = 0;
+
+  int64_t chunk = (int64_t)blockIdx.x * GW_PWARPS + warp;
+  Raw<KIND> next;
+  if (chunk < nchunks && (chunk << 5) + lane < a.n) raw_load<KIND>(next, a.state, a.n, (chunk << 5) + lane, a.actions);
+
+  for (; chunk < nchunks; chunk += stride) {
+    const int64_t env0 = chunk << 5;
+    const uint32_t nvalid = (uint32_t)min((int64_t)32, a.n - env0);
+    const Raw<KIND> raw = next;
+    {                                             /* software pipeline: the next chunk's state is in flight while this one computes */
+      const int64_t nenv = ((chunk + stride) << 5) + lane;
+      if (chunk + stride < nchunks && nenv < a.n) raw_load<KIND>(next, a.state, a.n, nenv, a.actions);
+    }
+    float* s_rw = reinterpret_cast<float*>(wbuf + L.reward_off + parity * L.reward_bytes);   /* double-buffered reward rows */
+    parity ^= 1u;
+
+    int32_t sv[24];
+#pragma unroll
+    for (int k = 0; k < 24; ++k) sv[k] = 0;
+    double fs[4] = {0.0, 0.0, 0.0, 0.0};
+    uint32_t cell = 0;
+    if (lane < nvalid) cell = step_lane<KIND>(c, a, s_art, env0 + lane, raw, s_rw + lane * R, sv, fs);
+    stats_accumulate<KIND>(tot, wide, sv);
+    if constexpr (KIND == 1) { ftot[0] += fs[0]; ftot[1] += fs[1]; ftot[2] += fs[2]; ftot[3] += fs[3]; }
+    if (++since_flush == GW_STAT_FLUSH) {
+      if (a.stats) stats_flush<KIND>(a.stats, tot, wide, lane);
+      since_flush = 0;
+    }
+
+    if (nvalid == 32) {
+      /* the TMA engine may still be reading the observation staging of the previous chunk */
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+      if (cell != staged_cell) {
+        if (staged_cell != 0xffffffffu) {         /* take the agent off the cell staged last time */
+          const uint8_t ch = s_art[staged_cell] == 'A' ? (uint8_t)' ' : s_art[staged_cell];
+          if (a.board) s_board[lane * cells + staged_cell] = ch;
+          if (a.cube) {
+            if (c.layer_agent >= 0) s_cube[lane * Sc + c.layer_agent * cells + staged_cell] = 0;
+            if (c.layer_gap >= 0) s_cube[lane * Sc + c.layer_gap * cells + staged_cell] = (uint8_t)(ch == ' ');
+          }
+          if (a.value_board) s_value[lane * cells + staged_cell] = s_val[staged_cell];
+        }
+        if (a.board) s_board[lane * cells + cell] = (uint8_t)'A';
+        if (a.cube) {
+          if (c.layer_agent >= 0) s_cube[lane * Sc + c.layer_agent * cells + cell] = 1;
+          if (c.layer_gap >= 0) s_cube[lane * Sc + c.layer_gap * cells + cell] = 0;
+        }
+        if (a.value_board) s_value[lane * cells + cell] = c.value_agent;
+        staged_cell = cell;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   /* generic-proxy writes -> visible to the TMA */
+      __syncwarp();
+      if (lane == 0) {
+        if (a.cube) bulk_store(a.cube + env0 * (int64_t)Sc, s_cube, 32u * Sc);
+        if (a.board) bulk_store(a.board + env0 * (int64_t)cells, s_board, 32u * cells);
+        if (a.value_board) bulk_store(a.value_board + env0 * (int64_t)cells, s_value, 128u * cells);
+        if (a.reward) bulk_store(a.reward + env0 * (int64_t)R, s_rw, 128u * R);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    } else {
+      /* the ragged last chunk: sizes need not be multiples of 16 bytes, use the direct stores */
+      if (a.reward) flush_rewards(s_rw, a.reward, env0, nvalid, R, lane);
+      emit_observation(c, a, env0, nvalid, lane, cell);
+    }
+  }
+  if (a.stats) {
+    stats_flush<KIND>(a.stats, tot, wide, lane);
+    if constexpr (KIND == 1) warp_stats_scaled(a.stats, ftot, lane);
+  }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  __syncwarp();
 }
 
 /* gw_reset: new episode where the mask says so, observation for everyone. */
@@ -899,6 +1196,31 @@ static void build_shifted(const std::vector<uint8_t>& tmpl, std::vector<uint8_t>
     for (size_t i = 0; i < (size_t)entries * 16; ++i) out[a * entries * 16 + i] = tmpl[(a + i) % S];
 }
 
+template <int KIND>
+static int launch_step_tma(GwHandle h, const StepArgs& a, cudaStream_t stream) {
+  auto up = [](uint32_t x) { return (x + 127u) & ~127u; };
+  const DevCfg& d = h->dc;
+  StageLayout L;
+  uint32_t off = 0;
+  L.cube_off = off; if (a.cube) off += up(32u * d.cube.bytes_per_env);
+  L.board_off = off; if (a.board) off += up(32u * d.board.bytes_per_env);
+  L.value_off = off; if (a.value_board) off += up(32u * d.value.bytes_per_env);
+  L.reward_off = off; L.reward_bytes = up(128u * (uint32_t)d.n_rewards); off += 2u * L.reward_bytes;
+  L.warp_bytes = off;
+  const size_t smem = (size_t)off * GW_PWARPS;
+  cudaError_t e = cudaFuncSetAttribute(gw_step_tma_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(GW_ERR_CUDA, "staging buffer of %zu bytes per CTA: %s", smem, cudaGetErrorString(e));
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gw_step_tma_kernel<KIND>, GW_PBLOCK, smem);
+  if (e != cudaSuccess || per_sm < 1) return fail(GW_ERR_CUDA, "occupancy query failed (%zu bytes of shared memory per CTA)", smem);
+  const int64_t nchunks = (h->n + 31) / 32;
+  int64_t grid = (nchunks + GW_PWARPS - 1) / GW_PWARPS;
+  const int64_t resident = (int64_t)per_sm * h->sm_count;
+  if (grid > resident) grid = resident;                     /* persistent: one wave, warps loop over chunks */
+  gw_step_tma_kernel<KIND><<<(unsigned)grid, GW_PBLOCK, smem, stream>>>(d, a, L);
+  return GW_OK;
+}
+
 extern "C" {
 
 int gw_abi_version(void) { return GW_ABI_VERSION; }
@@ -936,6 +1258,10 @@ int gw_create(const GwConfig* cfg, int64_t n_envs, int device, int64_t env_index
   h->device = device;
   h->env_index_base = env_index_base;
   h->launches = 0;
+  h->sm_count = 148;
+  cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+  const char* impl = getenv("GWSIM_STEP_IMPL");
+  h->step_impl = (impl && strcmp(impl, "direct") == 0) ? 1 : 0;
   h->d_tmpl = nullptr;
   h->d_stats = nullptr;
 
@@ -959,6 +1285,26 @@ int gw_create(const GwConfig* cfg, int64_t n_envs, int device, int64_t env_index
   memcpy(d.fparams, cfg->fparams, sizeof d.fparams);
   memcpy(d.table, cfg->reward_table, sizeof d.table);
   d.value_agent = cfg->value_map['A'];
+  {
+    /* the_plot.add_reward call-site order: island update_reward then WaterDrape
+     * (island_navigation_ex.py:455-571,606); boat update_reward (boat_race_ex.py:209-257) */
+    static const int isl_order[GW_ISL_N_EVENTS] = {
+        GW_ISL_E_MOVEMENT, GW_ISL_E_THIRST_HUNGER_DEATH, GW_ISL_E_FINAL, GW_ISL_E_DRINK, GW_ISL_E_NON_DRINK, GW_ISL_E_FOOD,
+        GW_ISL_E_NON_FOOD, GW_ISL_E_GOLD, GW_ISL_E_SILVER, GW_ISL_E_GAP, GW_ISL_E_DRINK_DEFICIENCY,
+        GW_ISL_E_DRINK_OVERSATIATION, GW_ISL_E_FOOD_DEFICIENCY, GW_ISL_E_FOOD_OVERSATIATION, GW_ISL_E_DANGER_TILE};
+    static const int boat_order[GW_BOAT_N_EVENTS] = {GW_BOAT_E_MOVEMENT, GW_BOAT_E_ITERATIONS, GW_BOAT_E_REPETITION,
+                                                     GW_BOAT_E_CLOCKWISE, GW_BOAT_E_FINAL, GW_BOAT_E_HUMAN};
+    const bool isl = cfg->env_type == GW_ENV_ISLAND_NAVIGATION_EX;
+    const int* order = isl ? isl_order : boat_order;
+    const int n_events = isl ? (int)GW_ISL_N_EVENTS : (int)GW_BOAT_N_EVENTS;
+    int pos = 0;
+    for (int dd = 0; dd < cfg->n_rewards; ++dd) {
+      d.rw_start[dd] = (uint8_t)pos;
+      for (int k = 0; k < n_events; ++k)
+        if (cfg->reward_table[order[k]][dd] != 0.0) d.rw_evt[pos++] = (uint8_t)order[k];
+    }
+    for (int dd = cfg->n_rewards; dd < GW_MAX_REWARDS + 4; ++dd) d.rw_start[dd] = (uint8_t)pos;
+  }
   /* impassable = '#' for both games (island_navigation_ex.py:420, boat_race_ex.py:182) */
   const int dr[4] = {0, 0, -1, 1}, dc[4] = {-1, 1, 0, 0};
   for (int p = 0; p < cells; ++p) {
@@ -974,8 +1320,6 @@ int gw_create(const GwConfig* cfg, int64_t n_envs, int device, int64_t env_index
   }
 
   /* templates: the observation of an agent-free board (all drapes of these games are static) */
-  const bool island = cfg->env_type == GW_ENV_ISLAND_NAVIGATION_EX;
-  auto is_drape = [&](uint8_t ch) { return island && (ch == 'W' || ch == 'D' || ch == 'F' || ch == 'G' || ch == 'S'); };
   std::vector<uint8_t> t_board(cells), t_cube((size_t)L * cells), t_value((size_t)cells * 4);
   for (int p = 0; p < cells; ++p) {
     const uint8_t ch = cfg->art[p] == 'A' ? (uint8_t)' ' : cfg->art[p];
@@ -991,7 +1335,6 @@ int gw_create(const GwConfig* cfg, int64_t n_envs, int device, int64_t env_index
       if (chr == 'A') v = 0;                                   /* sprite layer: patched per environment */
       else if (chr == ' ') v = (ch == ' ' || ch == 'A');       /* gap AND NOT any other layer, agent patched */
       else v = (ch == chr);                                    /* backdrop character or drape curtain */
-      (void)is_drape;
       t_cube[(size_t)l * cells + p] = v;
     }
   }
@@ -1000,13 +1343,28 @@ int gw_create(const GwConfig* cfg, int64_t n_envs, int device, int64_t env_index
   build_shifted(t_board, sb, eb);
   build_shifted(t_cube, sc, ec);
   build_shifted(t_value, sv, ev);
-  const size_t total = sb.size() + sc.size() + sv.size();
+  std::vector<float> lut((size_t)GW_LUT_ROWS * GW_MAX_REWARDS, 0.0f);
+  if (kind == 0) {
+    for (uint32_t idx = 0; idx < GW_LUT_ROWS; ++idx) {
+      const uint32_t mask = island_lut_mask(idx);
+      for (int dd = 0; dd < cfg->n_rewards; ++dd) {
+        double r = 0.0;
+        for (int j = d.rw_start[dd]; j < d.rw_start[dd + 1]; ++j)
+          if ((mask >> d.rw_evt[j]) & 1u) r += cfg->reward_table[d.rw_evt[j]][dd];
+        lut[(size_t)idx * GW_MAX_REWARDS + dd] = (float)r;
+      }
+    }
+  }
+  const size_t lut_bytes = lut.size() * sizeof(float);
+  const size_t total = sb.size() + sc.size() + sv.size() + lut_bytes;
   ce = cudaMalloc(&h->d_tmpl, total);
   if (ce != cudaSuccess) { delete h; return fail(GW_ERR_CUDA, "cudaMalloc templates: %s", cudaGetErrorString(ce)); }
   uint8_t* base = (uint8_t*)h->d_tmpl;
   cudaMemcpy(base, sb.data(), sb.size(), cudaMemcpyHostToDevice);
   cudaMemcpy(base + sb.size(), sc.data(), sc.size(), cudaMemcpyHostToDevice);
-  ce = cudaMemcpy(base + sb.size() + sc.size(), sv.data(), sv.size(), cudaMemcpyHostToDevice);
+  cudaMemcpy(base + sb.size() + sc.size(), sv.data(), sv.size(), cudaMemcpyHostToDevice);
+  ce = cudaMemcpy(base + sb.size() + sc.size() + sv.size(), lut.data(), lut_bytes, cudaMemcpyHostToDevice);
+  d.reward_lut = (const float*)(base + sb.size() + sc.size() + sv.size());
   if (ce != cudaSuccess) { cudaFree(h->d_tmpl); delete h; return fail(GW_ERR_CUDA, "template upload: %s", cudaGetErrorString(ce)); }
   auto fill = [](ObsTensor& t, uint32_t S, uint32_t entries, const void* p) {
     t.bytes_per_env = S;
@@ -1085,8 +1443,19 @@ int gw_step(GwHandle h, const int32_t* actions, void* state, const GwObs* obs, c
   a.actions = actions;
   a.stats = h->d_stats;
   CUDA_TRY(cudaSetDevice(h->device));
-  const unsigned grid = (unsigned)((h->n + GW_BLOCK - 1) / GW_BLOCK);
-  LAUNCH_KIND(gw_step_kernel, kind_of(&h->cfg), grid, (cudaStream_t)stream, h->dc, a);
+  const int kind = kind_of(&h->cfg);
+  if (h->step_impl == 1) {
+    const unsigned grid = (unsigned)((h->n + GW_BLOCK - 1) / GW_BLOCK);
+    LAUNCH_KIND(gw_step_kernel, kind, grid, (cudaStream_t)stream, h->dc, a);
+  } else {
+    switch (kind) {
+      case 0: rc = launch_step_tma<0>(h, a, (cudaStream_t)stream); break;
+      case 1: rc = launch_step_tma<1>(h, a, (cudaStream_t)stream); break;
+      case 2: rc = launch_step_tma<2>(h, a, (cudaStream_t)stream); break;
+      default: rc = launch_step_tma<3>(h, a, (cudaStream_t)stream); break;
+    }
+    if (rc != GW_OK) return rc;
+  }
   CUDA_TRY(cudaGetLastError());
   h->launches += 1;
   return GW_OK;
