@@ -44,6 +44,9 @@
 #define GW_PBLOCK 128        /* persistent TMA kernel: 4 warps per CTA */
 #endif
 #define GW_PWARPS (GW_PBLOCK / 32)
+#ifndef GW_GRAB
+#define GW_GRAB 1            /* chunks (of 32 environments) a warp claims per atomicAdd */
+#endif
 #define GW_STAT_REPLICAS 64
 #define FULL 0xffffffffu
 
@@ -115,6 +118,8 @@ struct StepArgs {
   uint8_t* step_type;
   int8_t* reason;
   unsigned long long* stats;  /* [GW_STAT_REPLICAS][GW_STATS_RAW_LEN]; slots 24..27 hold doubles */
+  unsigned long long* claim_counter;  /* dynamic chunk queue of the persistent kernel */
+  unsigned long long claim_base;
   int64_t n;
 };
 
@@ -126,6 +131,8 @@ struct GwEngine {
   int64_t env_index_base;
   void* d_tmpl;                       /* all templates, one allocation */
   unsigned long long* d_stats;
+  unsigned long long* d_claim;        /* chunk-queue counter (monotonic) */
+  unsigned long long claim_base;      /* its value once every launch issued so far has finished */
   int64_t launches;
   int sm_count;
   int step_impl;                      /* 0 = persistent TMA kernel (product), 1 = direct stores (GWSIM_STEP_IMPL=direct) */
@@ -911,7 +918,6 @@ __global__ void __launch_bounds__(GW_PBLOCK) gw_step_tma_kernel(const __grid_con
 
   const uint32_t R = (uint32_t)c.n_rewards, cells = (uint32_t)c.cells, Sc = c.cube.bytes_per_env;
   const int64_t nchunks = (a.n + 31) >> 5;
-  const int64_t stride = (int64_t)gridDim.x * GW_PWARPS;
   uint32_t staged_cell = 0xffffffffu;            /* the cell this lane's staged environment shows the agent on */
   int32_t tot[24];
 #pragma unroll
@@ -920,17 +926,32 @@ __global__ void __launch_bounds__(GW_PBLOCK) gw_step_tma_kernel(const __grid_con
   double ftot[4] = {0.0, 0.0, 0.0, 0.0};
   uint32_t since_flush = 0, parity = 0;
 
-  int64_t chunk = (int64_t)blockIdx.x * GW_PWARPS + warp;
+  /* Dynamic chunk queue: a warp claims GW_GRAB consecutive chunks at a time with one atomicAdd.
+   * Compared with a static grid-stride assignment this keeps the GPU-wide write front tight
+   * (warps cannot drift apart), which is worth ~12 % of DRAM write bandwidth on B200
+   * (scripts/wbw.cu: 6.28 -> 7.04 TB/s).  The counter is never reset: the host passes the value
+   * it has after all earlier launches (every warp makes exactly one failing claim per launch). */
+  const int64_t ngroups = (nchunks + GW_GRAB - 1) / GW_GRAB;
+  auto claim = [&]() -> int64_t {
+    unsigned long long v = 0;
+    if (lane == 0) v = atomicAdd(a.claim_counter, 1ull) - a.claim_base;
+    return (int64_t)__shfl_sync(FULL, v, 0);
+  };
+  int64_t group = claim();
   Raw<KIND> next;
-  if (chunk < nchunks && (chunk << 5) + lane < a.n) raw_load<KIND>(next, a.state, a.n, (chunk << 5) + lane, a.actions);
+  if (group < ngroups && ((group * GW_GRAB) << 5) + lane < a.n) raw_load<KIND>(next, a.state, a.n, ((group * GW_GRAB) << 5) + lane, a.actions);
 
-  for (; chunk < nchunks; chunk += stride) {
+  while (group < ngroups) {
+  const int64_t group_next = claim();            /* consumed at the end of this group: its latency is hidden */
+  for (int64_t chunk = group * GW_GRAB; chunk < min(nchunks, (group + 1) * GW_GRAB); ++chunk) {
     const int64_t env0 = chunk << 5;
     const uint32_t nvalid = (uint32_t)min((int64_t)32, a.n - env0);
     const Raw<KIND> raw = next;
     {                                             /* software pipeline: the next chunk's state is in flight while this one computes */
-      const int64_t nenv = ((chunk + stride) << 5) + lane;
-      if (chunk + stride < nchunks && nenv < a.n) raw_load<KIND>(next, a.state, a.n, nenv, a.actions);
+      int64_t nchunk = chunk + 1;
+      if (nchunk >= min(nchunks, (group + 1) * GW_GRAB)) nchunk = group_next < ngroups ? group_next * GW_GRAB : nchunks;
+      const int64_t nenv = (nchunk << 5) + lane;
+      if (nchunk < nchunks && nenv < a.n) raw_load<KIND>(next, a.state, a.n, nenv, a.actions);
     }
     float* s_rw = reinterpret_cast<float*>(wbuf + L.reward_off + parity * L.reward_bytes);   /* double-buffered reward rows */
     parity ^= 1u;
@@ -984,6 +1005,8 @@ __global__ void __launch_bounds__(GW_PBLOCK) gw_step_tma_kernel(const __grid_con
       if (a.reward) flush_rewards(s_rw, a.reward, env0, nvalid, R, lane);
       emit_observation(c, a, env0, nvalid, lane, cell);
     }
+  }
+  group = group_next;
   }
   if (a.stats) {
     stats_flush<KIND>(a.stats, tot, wide, lane);
@@ -1197,7 +1220,7 @@ static void build_shifted(const std::vector<uint8_t>& tmpl, std::vector<uint8_t>
 }
 
 template <int KIND>
-static int launch_step_tma(GwHandle h, const StepArgs& a, cudaStream_t stream) {
+static int launch_step_tma(GwHandle h, StepArgs& a, cudaStream_t stream) {
   auto up = [](uint32_t x) { return (x + 127u) & ~127u; };
   const DevCfg& d = h->dc;
   StageLayout L;
@@ -1216,8 +1239,12 @@ static int launch_step_tma(GwHandle h, const StepArgs& a, cudaStream_t stream) {
   const int64_t nchunks = (h->n + 31) / 32;
   int64_t grid = (nchunks + GW_PWARPS - 1) / GW_PWARPS;
   const int64_t resident = (int64_t)per_sm * h->sm_count;
-  if (grid > resident) grid = resident;                     /* persistent: one wave, warps loop over chunks */
+  if (grid > resident) grid = resident;                     /* persistent: one wave, warps claim chunk groups */
+  a.claim_counter = h->d_claim;
+  a.claim_base = h->claim_base;
   gw_step_tma_kernel<KIND><<<(unsigned)grid, GW_PBLOCK, smem, stream>>>(d, a, L);
+  /* every group is claimed once and every warp makes exactly one failing claim */
+  h->claim_base += (unsigned long long)((nchunks + GW_GRAB - 1) / GW_GRAB) + (unsigned long long)grid * GW_PWARPS;
   return GW_OK;
 }
 
@@ -1380,6 +1407,11 @@ int gw_create(const GwConfig* cfg, int64_t n_envs, int device, int64_t env_index
   ce = cudaMalloc((void**)&h->d_stats, sbytes);
   if (ce == cudaSuccess) ce = cudaMemset(h->d_stats, 0, sbytes);
   if (ce != cudaSuccess) { cudaFree(h->d_tmpl); delete h; return fail(GW_ERR_CUDA, "stats buffer: %s", cudaGetErrorString(ce)); }
+  h->d_claim = nullptr;
+  h->claim_base = 0;
+  ce = cudaMalloc((void**)&h->d_claim, sizeof(unsigned long long));
+  if (ce == cudaSuccess) ce = cudaMemset(h->d_claim, 0, sizeof(unsigned long long));
+  if (ce != cudaSuccess) { cudaFree(h->d_tmpl); cudaFree(h->d_stats); delete h; return fail(GW_ERR_CUDA, "claim counter: %s", cudaGetErrorString(ce)); }
   *out = h;
   return GW_OK;
 }
@@ -1389,6 +1421,7 @@ void gw_destroy(GwHandle h) {
   cudaSetDevice(h->device);
   cudaFree(h->d_tmpl);
   cudaFree(h->d_stats);
+  cudaFree(h->d_claim);
   delete h;
 }
 

@@ -299,7 +299,7 @@ def run_ours(args):
                 "bytes_per_env_step": bytes_per, "state_bytes_per_env": env.state_words * 16,
                 "autoreset": "same-step", "action_ring": ACTION_RING}),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": load_traffic(n), "peak_source": peak_src, "kernel": "gw_step_kernel<0>",
+                         "traffic": load_traffic(n), "peak_source": peak_src, "kernel": "gw_step_tma_kernel<0>",
                          "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": bytes_per * n},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                     "steps": e2e_steps, "returns": "value_board f32[48] + reward f32[10] + terminated u8 per env, pinned host"},

@@ -48,6 +48,90 @@ __global__ void k_fill_bulk(uint4* p, size_t n, int chunk_u4) {
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 }
+// non-persistent TMA: one CTA = one (or a few) bulk stores, then exit
+__global__ void k_fill_bulk_once(uint4* p, size_t n, int chunk_u4, int per_cta) {
+  extern __shared__ __align__(128) uint4 sm[];
+  for (int i = threadIdx.x; i < chunk_u4; i += blockDim.x) sm[i] = make_uint4(1, 2, 3, 4);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t saddr = (uint32_t)__cvta_generic_to_shared(sm);
+    for (int k = 0; k < per_cta; ++k) {
+      size_t c = (size_t)blockIdx.x * per_cta + k;
+      if (c * chunk_u4 < n)
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(p + c * chunk_u4), "r"(saddr), "r"(chunk_u4 * 16) : "memory");
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  }
+}
+// per-warp TMA: every warp of a persistent CTA owns a staging buffer and issues its own bulk stores
+__global__ void k_fill_bulk_warp(uint4* p, size_t n, int chunk_u4) {
+  extern __shared__ __align__(128) uint4 sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  uint4* my = sm + (size_t)warp * chunk_u4;
+  for (int i = lane; i < chunk_u4; i += 32) my[i] = make_uint4(1, 2, 3, 4);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  size_t nchunks = n / chunk_u4;
+  uint32_t saddr = (uint32_t)__cvta_generic_to_shared(my);
+  for (size_t c = (size_t)blockIdx.x * nw + warp; c < nchunks; c += (size_t)gridDim.x * nw) {
+    if (lane == 0) {
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(p + c * chunk_u4), "r"(saddr), "r"(chunk_u4 * 16) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    __syncwarp();
+  }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+// persistent per-warp TMA with a dynamic (atomic) chunk queue: keeps the write front tight
+__global__ void k_fill_bulk_dyn(uint4* p, size_t n, int chunk_u4, unsigned long long* counter, int grab) {
+  extern __shared__ __align__(128) uint4 sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint4* my = sm + (size_t)warp * chunk_u4;
+  for (int i = lane; i < chunk_u4; i += 32) my[i] = make_uint4(1, 2, 3, 4);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  size_t nchunks = n / chunk_u4;
+  uint32_t saddr = (uint32_t)__cvta_generic_to_shared(my);
+  while (true) {
+    unsigned long long c0 = 0;
+    if (lane == 0) c0 = atomicAdd(counter, (unsigned long long)grab);
+    c0 = __shfl_sync(0xffffffffu, c0, 0);
+    if (c0 >= nchunks) break;
+    for (int k = 0; k < grab && c0 + k < nchunks; ++k) {
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(p + (c0 + k) * chunk_u4), "r"(saddr), "r"(chunk_u4 * 16) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      __syncwarp();
+    }
+  }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+// persistent, static but BLOCKED assignment: warp w owns a contiguous range of chunks
+__global__ void k_fill_bulk_blocked(uint4* p, size_t n, int chunk_u4) {
+  extern __shared__ __align__(128) uint4 sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  uint4* my = sm + (size_t)warp * chunk_u4;
+  for (int i = lane; i < chunk_u4; i += 32) my[i] = make_uint4(1, 2, 3, 4);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  size_t nchunks = n / chunk_u4, tw = (size_t)gridDim.x * nw, gw = (size_t)blockIdx.x * nw + warp;
+  size_t per = (nchunks + tw - 1) / tw, lo = gw * per, hi = lo + per; if (hi > nchunks) hi = nchunks;
+  uint32_t saddr = (uint32_t)__cvta_generic_to_shared(my);
+  for (size_t c = lo; c < hi; ++c) {
+    if (lane == 0) {
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(p + c * chunk_u4), "r"(saddr), "r"(chunk_u4 * 16) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    __syncwarp();
+  }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
 __global__ void k_copy(const uint4* __restrict__ a, uint4* __restrict__ b, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, st = (size_t)gridDim.x * blockDim.x;
   for (; i < n; i += st) b[i] = a[i];
@@ -96,6 +180,28 @@ int main() {
       ms = timeit([&] { k_fill_bulk<<<g, 128, c * 16>>>(b, n, c); });
       printf("fill bulk (TMA) %5d B grid %4d %8.1f us %7.0f GB/s\n", c * 16, g, ms * 1e3, bytes / ms / 1e6);
     }
+  for (int c : {768, 1024}) for (int per : {1, 4}) {
+    cudaFuncSetAttribute(k_fill_bulk_once, cudaFuncAttributeMaxDynamicSharedMemorySize, c * 16);
+    unsigned g = (unsigned)((n / c + per - 1) / per);
+    ms = timeit([&] { k_fill_bulk_once<<<g, 128, c * 16>>>(b, n, c, per); });
+    printf("fill bulk once %5d B x%d grid %6u %8.1f us %7.0f GB/s\n", c * 16, per, g, ms * 1e3, bytes / ms / 1e6);
+  }
+  for (int c : {768, 1024}) for (int g : {148 * 3, 148 * 2}) {
+    cudaFuncSetAttribute(k_fill_bulk_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, c * 16 * 4);
+    ms = timeit([&] { k_fill_bulk_warp<<<g, 128, c * 16 * 4>>>(b, n, c); });
+    printf("fill bulk per-warp %5d B grid %4d %8.1f us %7.0f GB/s\n", c * 16, g, ms * 1e3, bytes / ms / 1e6);
+  }
+  unsigned long long* counter; CK(cudaMalloc(&counter, 8));
+  for (int c : {768}) for (int g : {148 * 3}) for (int grab : {1, 4, 16}) {
+    cudaFuncSetAttribute(k_fill_bulk_dyn, cudaFuncAttributeMaxDynamicSharedMemorySize, c * 16 * 4);
+    ms = timeit([&] { cudaMemsetAsync(counter, 0, 8); k_fill_bulk_dyn<<<g, 128, c * 16 * 4>>>(b, n, c, counter, grab); });
+    printf("fill bulk dynamic %5d B grid %4d grab %2d %8.1f us %7.0f GB/s\n", c * 16, g, grab, ms * 1e3, bytes / ms / 1e6);
+  }
+  for (int c : {768}) for (int g : {148 * 3}) {
+    cudaFuncSetAttribute(k_fill_bulk_blocked, cudaFuncAttributeMaxDynamicSharedMemorySize, c * 16 * 4);
+    ms = timeit([&] { k_fill_bulk_blocked<<<g, 128, c * 16 * 4>>>(b, n, c); });
+    printf("fill bulk blocked %5d B grid %4d %8.1f us %7.0f GB/s\n", c * 16, g, ms * 1e3, bytes / ms / 1e6);
+  }
   ms = timeit([&] { k_copy<<<148 * 16, 256>>>(a, b, n); }); printf("copy v4                         %8.1f us %7.0f GB/s (r+w)\n", ms * 1e3, 2.0 * bytes / ms / 1e6);
   ms = timeit([&] { cudaMemcpyAsync(b, a, bytes, cudaMemcpyDeviceToDevice); }); printf("cudaMemcpy D2D                  %8.1f us %7.0f GB/s (r+w)\n", ms * 1e3, 2.0 * bytes / ms / 1e6);
   ms = timeit([&] { k_read<<<148 * 16, 256>>>(a, n, out); }); printf("read v4                         %8.1f us %7.0f GB/s\n", ms * 1e3, bytes / ms / 1e6);
