@@ -81,7 +81,8 @@ class GwStepOut(C.Structure):
 
 class GwExtras(C.Structure):
     _fields_ = [("metrics", C.c_void_p), ("cumulative", C.c_void_p), ("frame", C.c_void_p),
-                ("pos", C.c_void_p), ("safety", C.c_void_p)]
+                ("pos", C.c_void_p), ("safety", C.c_void_p), ("average", C.c_void_p), ("scalars", C.c_void_p),
+                ("reward_in", C.c_void_p)]
 
 
 # every symbol include/gwsim.h declares: (name, restype, argtypes)

@@ -1063,6 +1063,9 @@ struct ObserveArgs {
   int32_t* frame;
   int16_t* pos;
   int16_t* safety;
+  float* average;
+  double* scalars;
+  const float* reward_in;
   int64_t n;
 };
 
@@ -1107,7 +1110,7 @@ __global__ void __launch_bounds__(GW_BLOCK) gw_observe_kernel(const __grid_const
       }
     }
   }
-  if (a.cumulative) {
+  if (a.cumulative || a.average || a.scalars) {
     /* episode_return (safety_game_mo.py:996-997) == sum_e acc[e] * table[e][:] */
     int32_t acc[16];
     g_acc<KIND>(s, c, acc);
@@ -1118,11 +1121,43 @@ __global__ void __launch_bounds__(GW_BLOCK) gw_observe_kernel(const __grid_const
       facc[GW_ISL_E_DRINK_DEFICIENCY] = s.pdd; facc[GW_ISL_E_DRINK_OVERSATIATION] = s.pdo;
       facc[GW_ISL_E_FOOD_DEFICIENCY] = s.pfd; facc[GW_ISL_E_FOOD_OVERSATIATION] = s.pfo;
     }
-    for (int32_t d = 0; d < c.n_rewards; ++d) {
+    double cum[GW_MAX_REWARDS], avg[GW_MAX_REWARDS], rew[GW_MAX_REWARDS];
+    const int32_t R = c.n_rewards;
+    for (int32_t d = 0; d < R; ++d) {
       double v = 0.0;
 #pragma unroll
       for (int e = 0; e < 16; ++e) v += facc[e] * c.table[e][d];
-      a.cumulative[env * c.n_rewards + d] = (float)v;
+      cum[d] = v;
+      avg[d] = v / (double)(s.frame + 1);                     /* safety_game_mo.py:1030 */
+      rew[d] = a.reward_in ? (double)a.reward_in[env * R + d] : 0.0;
+      if (a.cumulative) a.cumulative[env * R + d] = (float)v;
+      if (a.average) a.average[env * R + d] = (float)avg[d];
+    }
+    if (a.scalars) {
+      /* gini_coefficient (safety_game_mo.py:1645-1681): shift by the minimum, 0.5 * mean absolute
+       * difference / (mean + eps), times 100; np.var with ddof=0 (:1077-1079) */
+      auto gini = [&](const double* x) {
+        double mn = x[0];
+        for (int32_t i = 1; i < R; ++i) mn = fmin(mn, x[i]);
+        double mad = 0.0, mean = 0.0;
+        for (int32_t i = 0; i < R; ++i) {
+          mean += x[i] - mn;
+          for (int32_t j = 0; j < R; ++j) mad += fabs((x[i] - mn) - (x[j] - mn));
+        }
+        mad /= (double)(R * R);
+        mean /= (double)R;
+        return 0.5 * (mad / (mean + 2.220446049250313e-16)) * 100.0;
+      };
+      auto var = [&](const double* x) {
+        double mean = 0.0;
+        for (int32_t i = 0; i < R; ++i) mean += x[i];
+        mean /= (double)R;
+        double acc2 = 0.0;
+        for (int32_t i = 0; i < R; ++i) acc2 += (x[i] - mean) * (x[i] - mean);
+        return acc2 / (double)R;
+      };
+      double* o = a.scalars + env * 5;
+      o[0] = gini(rew); o[1] = gini(cum); o[2] = var(rew); o[3] = var(cum); o[4] = var(avg);
     }
   }
 }
@@ -1498,7 +1533,8 @@ int gw_observe(GwHandle h, const void* state, const GwExtras* ex, void* stream) 
   if (!h || !state || !ex) return fail(GW_ERR_INVALID, "null argument");
   ObserveArgs a;
   a.state = (const uint4*)state; a.metrics = ex->metrics; a.cumulative = ex->cumulative; a.frame = ex->frame;
-  a.pos = ex->pos; a.safety = ex->safety; a.n = h->n;
+  a.pos = ex->pos; a.safety = ex->safety; a.average = ex->average; a.scalars = ex->scalars; a.reward_in = ex->reward_in;
+  a.n = h->n;
   CUDA_TRY(cudaSetDevice(h->device));
   const unsigned grid = (unsigned)((h->n + GW_BLOCK - 1) / GW_BLOCK);
   LAUNCH_KIND(gw_observe_kernel, kind_of(&h->cfg), grid, (cudaStream_t)stream, h->dc, a);

@@ -1,0 +1,227 @@
+"""GridworldGymEnv: the reference's Gym/Gymnasium wrapper signature over the CUDA vector backend.
+
+Mirrors helpers/gridworld_gym_env.py of the reference (constructor :99-133, `step` :455-585,
+`reset` :588-674, info keys :54-64,397-450, action / observation spaces :753-981):
+
+  * `num_envs=None` (default) is the drop-in single environment: numpy outputs with the
+    reference's shapes and dtypes -- obs float32 [1,H,W] (or [2,H,W] with `use_transitions`),
+    reward float64 [R], `terminated` bool, `truncated` False, info dict -- and the reference's
+    stepping semantics (the call after a terminal step rebuilds the game, ignores its action and
+    returns the first observation, rl/pycolab_interface_mo.py:175-178);
+  * `num_envs=N` is the batched form: the same quantities as torch CUDA tensors with a leading
+    batch dimension and auto-reset inside the terminal step (the observation returned with
+    `terminated` is the new episode's first frame).
+
+gymnasium itself is not imported: the class is duck-typed, and the two space classes below carry
+what the reference's spaces expose.  Every step is one launch of the fused CUDA kernel; there is
+no CPU fallback.
+"""
+import numpy as np
+import torch
+
+from .. import _abi
+from ..envs import make_spec
+from ..vector_env import VectorEnv
+
+INFO_OBSERVED_REWARD = "observed_reward"
+INFO_DISCOUNT = "discount"
+INFO_OBSERVATION_COORDINATES = "info_observation_coordinates"
+INFO_OBSERVATION_LAYERS_DICT = "info_observation_layers_dict"
+INFO_OBSERVATION_LAYERS_ORDER = "info_observation_layers_order"
+INFO_OBSERVATION_LAYERS_CUBE = "info_observation_layers_cube"
+
+# constructor arguments of the reference wrapper that do not change what the kernel computes
+_WRAPPER_ONLY = ("render_animation_delay", "flatten_observations", "ascii_observation_format", "ascii_attributes_format",
+                 "attribute_coordinates_in_observation", "layers_in_attribute_observation", "occlusion_in_atribute_layers",
+                 "observable_attribute_categories", "observable_attribute_value_mapping", "use_multi_discrete_action_space",
+                 "agent_character", "np_random", "pre_reset_callback", "post_reset_callback", "pre_step_callback",
+                 "post_step_callback", "render_mode")
+
+
+class DiscreteActionSpace(object):
+    """gym.spaces.Discrete(n, start=min_action) as the reference builds it (gridworld_gym_env.py:885-896)."""
+
+    def __init__(self, min_action, max_action, seed=None):
+        self.min_action, self.max_action = int(min_action), int(max_action)
+        self.n, self.start = self.max_action - self.min_action + 1, self.min_action
+        self.shape, self.dtype = (), np.int64
+        self._rng = np.random.default_rng(seed)
+
+    def sample(self):
+        return int(self._rng.integers(self.min_action, self.max_action + 1))
+
+    def contains(self, x):
+        try:
+            return self.min_action <= int(x) <= self.max_action and int(x) == x
+        except (TypeError, ValueError):
+            return False
+
+    __contains__ = contains
+
+
+class BoardObservationSpace(object):
+    """The Box-like observation space of the value-mapped board (gridworld_gym_env.py:900-981)."""
+
+    def __init__(self, shape, low, high):
+        self.shape, self.dtype, self.low, self.high = tuple(shape), np.float32, float(low), float(high)
+
+    def contains(self, x):
+        x = np.asarray(x)
+        return x.shape == self.shape and bool(np.all(x >= self.low)) and bool(np.all(x <= self.high))
+
+    __contains__ = contains
+
+
+class GridworldGymEnv(object):
+    metadata = {"render.modes": ["ansi", "rgb_array"]}
+    reward_range = (-float("inf"), float("inf"))
+
+    def __init__(self, env_name, use_transitions=False, object_coordinates_in_observation=True, layers_in_observation=True,
+                 occlusion_in_layers=False, layers_order_in_cube=[], seed=None, num_envs=None, device=None, **kwargs):
+        for k in _WRAPPER_ONLY:
+            kwargs.pop(k, None)
+        if occlusion_in_layers:
+            raise NotImplementedError("occlusion_in_layers=True: the MO environments force it off (safety_game_mo_base.py)")
+        self._batched = num_envs is not None
+        n = int(num_envs) if self._batched else 1
+        mode = _abi.GW_AUTORESET_SAME_STEP if self._batched else _abi.GW_AUTORESET_NEXT_STEP
+        self._spec = make_spec(env_name, autoreset_mode=mode, **kwargs)      # raises NotImplementedError like factory.py:199-201
+        self._env = VectorEnv(self._spec, n, device=device, autoreset_mode=mode)
+        self._env_name = env_name
+        self._use_transitions = bool(use_transitions)
+        self._object_coordinates = bool(object_coordinates_in_observation)
+        self._layers_in_observation = bool(layers_in_observation)
+        order = list(layers_order_in_cube) if layers_order_in_cube else list(self._spec.layer_order)
+        unknown = [ch for ch in order if ch not in self._spec.layer_order]
+        if unknown:
+            raise ValueError("layers_order_in_cube names layers the environment does not have: %r" % unknown)
+        self._layers_order = order
+        self._layer_index = torch.tensor([self._spec.layer_order.index(ch) for ch in order], device=self._env.device)
+        lo, hi = self._spec.action_range
+        self.action_space = DiscreteActionSpace(lo, hi, seed)
+        vals = list(self._spec.value_mapping.values())
+        depth = 2 if self._use_transitions else 1
+        self.observation_space = BoardObservationSpace((depth, self._spec.height, self._spec.width), min(vals), max(vals))
+        self.num_envs = n
+        self._last_board = None
+        self._last_hidden = None
+        self._seed = seed
+
+    # ------------------------------------------------------------------ reference accessors
+    @property
+    def spec_(self):
+        return self._spec
+
+    @property
+    def vector_env(self):
+        return self._env
+
+    @property
+    def enabled_reward_dimension_keys(self):
+        return list(self._spec.reward_keys)
+
+    def seed(self, seed=None):
+        self._seed = seed
+        self.action_space = DiscreteActionSpace(self.action_space.min_action, self.action_space.max_action, seed)
+        return [seed]
+
+    def close(self):
+        self._env.close()
+
+    # ------------------------------------------------------------------ stepping
+    def reset(self, seed=None, return_info=False, options=None, *args, **kwargs):
+        if seed is not None:
+            self.seed(seed)
+        self._env.reset()
+        self._last_board = None
+        obs = self._observation()
+        info = self._compute_info(first=True)
+        return self._finish(obs, None, info)[::3]            # (obs, info)
+
+    def step(self, action, *args, **kwargs):
+        env = self._env
+        if self._batched:
+            a = action if torch.is_tensor(action) else torch.as_tensor(np.asarray(action), device=env.device)
+            a = a.to(device=env.device, dtype=torch.int32).contiguous()
+        else:
+            a = torch.tensor([int(np.asarray(action).item())], dtype=torch.int32, device=env.device)   # pycolab_interface_mo.py:164
+        env.step(a)
+        obs = self._observation()
+        info = self._compute_info(first=False)
+        obs, reward, terminated, info = self._finish(obs, env.reward, info)
+        truncated = torch.zeros_like(env.terminated, dtype=torch.bool) if self._batched else False   # gridworld_gym_env.py:576-577
+        return obs, reward, terminated, truncated, info
+
+    # ------------------------------------------------------------------ helpers
+    def _observation(self):
+        board = self._env.value_board.unsqueeze(1).clone()             # state = board[np.newaxis] is a copy (:525-536)
+        if self._use_transitions:
+            prev = board if self._last_board is None else self._last_board
+            self._last_board = board
+            return torch.cat([prev, board], dim=1)
+        return board
+
+    def _compute_info(self, first):
+        env, spec = self._env, self._spec
+        ex = env.observe()
+        info = {
+            "ascii_codes": env.board.clone(),
+            "cumulative_reward": ex["cumulative"].double(),
+            "average_reward": ex["average"].double(),
+            "gini_index": ex["scalars"][:, 0], "cumulative_gini_index": ex["scalars"][:, 1],
+            "mo_variance": ex["scalars"][:, 2], "cumulative_mo_variance": ex["scalars"][:, 3],
+            "average_mo_variance": ex["scalars"][:, 4],
+            "metrics_dict": {n: ex["metrics"][:, j] for j, n in enumerate(spec.metric_names)},
+            "extra_observations": {"termination_reason": env.reason.clone()},
+            "step_type": env.step_type.clone(),
+            "frame": ex["frame"], "agent_position": ex["pos"], "safety": ex["safety"],
+            INFO_DISCOUNT: self._discount(),
+        }
+        if self._layers_in_observation:
+            info[INFO_OBSERVATION_LAYERS_ORDER] = list(self._layers_order)
+            info[INFO_OBSERVATION_LAYERS_CUBE] = env.cube.index_select(1, self._layer_index).bool()
+        if self._object_coordinates:
+            info[INFO_OBSERVATION_COORDINATES] = None        # materialised lazily for the single-environment form
+        return info
+
+    def _discount(self):
+        """pycolab/plot.py:176-199: 0.0 after a game-initiated termination or QUIT, 1.0 otherwise; NaN
+        stands for the reference's None on a FIRST timestep."""
+        env = self._env
+        d = torch.ones(env.num_envs, dtype=torch.float64, device=env.device)
+        ended = (env.step_type == _abi.GW_STEP_LAST) & ((env.reason == _abi.GW_REASON_TERMINATED) | (env.reason == _abi.GW_REASON_QUIT))
+        d[ended] = 0.0
+        d[env.step_type == _abi.GW_STEP_FIRST] = float("nan")
+        return d
+
+    def _finish(self, obs, reward, info):
+        env = self._env
+        if self._batched:
+            r = None if reward is None else reward.double()
+            return obs, r, env.terminated.bool(), info
+        # drop-in single environment: numpy, reference shapes
+        def host(x):
+            if torch.is_tensor(x):
+                return x[0].cpu().numpy()
+            if isinstance(x, dict):
+                return {k: host(v) for k, v in x.items()}
+            return x
+        out = {k: host(v) for k, v in info.items()}
+        out["metrics_dict"] = {k: float(v) for k, v in out["metrics_dict"].items()}
+        tr = int(out["extra_observations"]["termination_reason"])
+        out["extra_observations"] = {"termination_reason": None if tr < 0 else tr}
+        d = float(out[INFO_DISCOUNT])
+        out[INFO_DISCOUNT] = None if np.isnan(d) else d
+        if self._object_coordinates and INFO_OBSERVATION_LAYERS_CUBE in out:
+            # per-layer (row, col) lists, like np.argwhere per layer (gridworld_gym_env.py:367-392)
+            cube = out[INFO_OBSERVATION_LAYERS_CUBE]
+            out[INFO_OBSERVATION_COORDINATES] = {ch: [tuple(int(v) for v in rc) for rc in np.argwhere(cube[i])]
+                                                 for i, ch in enumerate(self._layers_order)}
+        r = None if reward is None else reward[0].double().cpu().numpy()
+        return obs[0].cpu().numpy(), r, bool(env.terminated[0].item()), out
+
+    def render(self, mode="ansi"):
+        board = self._env.board[0].cpu().numpy()
+        if mode == "ansi":
+            return "\n".join("".join(chr(c) for c in row) for row in board)
+        raise NotImplementedError("render mode %r (RGB and curses rendering are out of scope, DESIGN.md section 7)" % mode)

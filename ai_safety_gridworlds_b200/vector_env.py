@@ -168,15 +168,20 @@ class VectorEnv(object):
 
     # ------------------------------------------------------------------ extras / statistics
     def observe(self):
-        """metrics_dict values, cumulative reward, frame, agent position, safety -- read from the state."""
+        """metrics_dict values, cumulative / average reward, frame, agent position, safety and the
+        Gini / variance scalars of _process_timestep (columns: gini_index, cumulative_gini_index,
+        mo_variance, cumulative_mo_variance, average_mo_variance) -- computed from the state."""
         N, M, R = self.num_envs, len(self.spec.metric_names), self.spec.n_rewards
         dev = self.device
         out = dict(metrics=torch.zeros((N, max(M, 1)), dtype=torch.float64, device=dev)[:, :M].contiguous() if M else None,
                    cumulative=torch.zeros((N, R), dtype=torch.float32, device=dev),
                    frame=torch.zeros((N,), dtype=torch.int32, device=dev),
                    pos=torch.zeros((N, 2), dtype=torch.int16, device=dev),
-                   safety=torch.zeros((N,), dtype=torch.int16, device=dev))
-        ex = _abi.GwExtras(_ptr(out["metrics"]), _ptr(out["cumulative"]), _ptr(out["frame"]), _ptr(out["pos"]), _ptr(out["safety"]))
+                   safety=torch.zeros((N,), dtype=torch.int16, device=dev),
+                   average=torch.zeros((N, R), dtype=torch.float32, device=dev),
+                   scalars=torch.zeros((N, 5), dtype=torch.float64, device=dev))
+        ex = _abi.GwExtras(_ptr(out["metrics"]), _ptr(out["cumulative"]), _ptr(out["frame"]), _ptr(out["pos"]), _ptr(out["safety"]),
+                           _ptr(out["average"]), _ptr(out["scalars"]), _ptr(self.reward))
         _abi.check(self._lib.gw_observe(self._h, _ptr(self.state), C.byref(ex), self._stream()))
         return out
 

@@ -155,6 +155,11 @@ typedef struct GwExtras {
   int32_t* frame;       /* [N]    the_plot.frame */
   int16_t* pos;         /* [N, 2] agent (row, col) */
   int16_t* safety;      /* [N]    environment_data['safety'] (island_navigation_ex.py:461-469); -1 if the env has none */
+  float* average;       /* [N, R] obs['average_reward'] = cumulative / (frame + 1) (safety_game_mo.py:1030) */
+  double* scalars;      /* [N, 5] gini_index, cumulative_gini_index, mo_variance, cumulative_mo_variance,
+                                  average_mo_variance (safety_game_mo.py:1071-1084,1645-1681); the two per-step
+                                  entries are computed from reward_in and need it */
+  const float* reward_in; /* [N, R] INPUT: the reward rows of the last step/reset call (GwStepOut.reward) */
 } GwExtras;
 
 /* Rollout statistics, summed over every episode that ended since gw_create / gw_stats_clear.

@@ -51,6 +51,9 @@ def test_cuda_replays_reference_trace(name):
         np.testing.assert_array_equal(_np(ex["pos"][1]), d["pos"][t], err_msg=ctx)
         assert int(ex["safety"][2]) == d["safety"][t], ctx
         np.testing.assert_allclose(_np(ex["cumulative"][0]), d["cumulative"][t], rtol=1e-6, atol=1e-6, err_msg=ctx)
+        np.testing.assert_allclose(_np(ex["average"][1]), d["average"][t], rtol=1e-6, atol=1e-6, err_msg=ctx)
+        # gini x2, variance x3 of _process_timestep (safety_game_mo.py:1071-1084), from float32 reward rows
+        np.testing.assert_allclose(_np(ex["scalars"][2]), d["scalars"][t], rtol=2e-5, atol=1e-4, err_msg=ctx)
         if meta["metric_names"]:
             got, want = _np(ex["metrics"][0]), d["metrics"][t]
             for j, is_int in enumerate(integer_metric):
