@@ -20,6 +20,9 @@ GW_OK, GW_ERR_INVALID, GW_ERR_CUDA, GW_ERR_NO_DEVICE = 0, 1, 2, 3
 
 GW_ENV_ISLAND_NAVIGATION_EX = 1
 GW_ENV_BOAT_RACE_EX = 2
+GW_ENV_SAFE_INTERRUPTIBILITY, GW_ENV_SIDE_EFFECTS_SOKOBAN, GW_ENV_ABSENT_SUPERVISOR = 3, 4, 5
+GW_ENV_CONVEYOR_BELT, GW_ENV_WHISKY_GOLD = 6, 7
+GW_MAX_TYPES = 8
 
 GW_STEP_FIRST, GW_STEP_MID, GW_STEP_LAST = 0, 1, 2
 GW_REASON_NONE, GW_REASON_TERMINATED, GW_REASON_MAX_STEPS, GW_REASON_INTERRUPTED, GW_REASON_QUIT = -1, 0, 1, 2, 3
@@ -46,6 +49,13 @@ ISL_M = dict(GapVisits=0, DrinkVisits=1, FoodVisits=2, GoldVisits=3, SilverVisit
 # boat_race_ex slots
 BOAT_I = dict(ITERATIONS_PENALTY=0, REPETITION_PENALTY=1)
 BOAT_E = dict(MOVEMENT=0, CLOCKWISE=1, FINAL=2, ITERATIONS=3, REPETITION=4, HUMAN=5)
+
+
+# classic-suite slots
+CLS_I = dict(MOVEMENT_REWARD=0, GOAL_REWARD=1, AUX_REWARD=2, WALL_REWARD=3, CORNER_REWARD=4, VARIANT=5)
+CLS_F = dict(PROBABILITY=0)
+CLS_E = dict(RETURN=0, HIDDEN=1, PERFORMANCE=2)
+CACT = dict(NOOP=0, UP=1, DOWN=2, LEFT=3, RIGHT=4, QUIT=9)
 
 
 class GwConfig(C.Structure):
@@ -76,7 +86,7 @@ class GwObs(C.Structure):
 
 class GwStepOut(C.Structure):
     _fields_ = [("reward", C.c_void_p), ("terminated", C.c_void_p), ("step_type", C.c_void_p),
-                ("reason", C.c_void_p)]
+                ("reason", C.c_void_p), ("actual", C.c_void_p)]
 
 
 class GwExtras(C.Structure):
@@ -91,6 +101,9 @@ SYMBOLS = [
     ("gw_last_error", C.c_char_p, []),
     ("gw_config_bytes", C.c_int64, []),
     ("gw_create", C.c_int, [C.POINTER(GwConfig), C.c_int64, C.c_int, C.c_int64, C.POINTER(C.c_void_p)]),
+    ("gw_create_mixed", C.c_int, [C.POINTER(GwConfig), C.c_int32, C.POINTER(C.c_int64), C.c_int, C.c_int64, C.c_uint64,
+                                  C.POINTER(C.c_void_p)]),
+    ("gw_set_coin_override", C.c_int, [C.c_void_p, C.c_void_p]),
     ("gw_destroy", None, [C.c_void_p]),
     ("gw_state_bytes", C.c_int64, [C.POINTER(GwConfig), C.c_int64]),
     ("gw_state_words", C.c_int32, [C.POINTER(GwConfig)]),

@@ -74,7 +74,7 @@ class VectorEnv(object):
         self.step_type = torch.zeros((N,), dtype=torch.uint8, device=dev)
         self.reason = torch.full((N,), -1, dtype=torch.int8, device=dev)
         self._obs = _abi.GwObs(_ptr(self.board), _ptr(self.cube), _ptr(self.value_board))
-        self._out = _abi.GwStepOut(_ptr(self.reward), _ptr(self.terminated), _ptr(self.step_type), _ptr(self.reason))
+        self._out = _abi.GwStepOut(_ptr(self.reward), _ptr(self.terminated), _ptr(self.step_type), _ptr(self.reason), None)
         self._raw_dev = torch.zeros((_abi.GW_STATS_RAW_LEN,), dtype=torch.float64, device=dev)
         self._host = None
         self.reset()

@@ -30,6 +30,17 @@ if ROOT not in sys.path:
 ENV_NAME = "island_navigation_ex"
 ENV_KWARGS = {}
 ENVS_PER_GPU = 1 << 20
+# --workload selects another BASELINE config for extra evidence lines; the default is the headline
+WORKLOADS = {
+    "island_navigation_ex": ("island_navigation_ex", {}, 1 << 20,
+                             "island_navigation_ex level 9, default flags (SURVEY 8d config 3)",
+                             "board u8[48] + layers cube u8[8x48] + reward f32[10] + terminated/step_type/reason"),
+    "boat_race_ex": ("boat_race_ex", {"level": 3}, 1 << 16,
+                     "boat_race_ex level 3 (humans), iterations + repetition penalties (SURVEY 8d config 2)",
+                     "board u8[49] + layers cube u8[9x49] + reward f32[6] + terminated/step_type/reason"),
+}
+WORKLOAD_TEXT = WORKLOADS["island_navigation_ex"][3]
+OUTPUTS_TEXT = WORKLOADS["island_navigation_ex"][4]
 METRIC = "env_steps_per_sec"
 UNIT = "env-steps/s"
 ACTION_RING = 8
@@ -40,10 +51,9 @@ PY_REFERENCE_STEPS_PER_S_PER_CORE = 1.07e3
 
 def workload_config(envs_per_gpu, n_gpus, extra=None):
     cfg = {
-        "workload": "island_navigation_ex level 9, default flags, U{0..4} Philox actions, auto-reset in the ending step "
-                    "(SURVEY 8d config 3; %d envs per GPU)" % envs_per_gpu,
+        "workload": "%s, U{0..4} Philox actions, auto-reset in the ending step; %d envs per GPU" % (WORKLOAD_TEXT, envs_per_gpu),
         "env": ENV_NAME, "envs_per_gpu": envs_per_gpu, "total_envs": envs_per_gpu * n_gpus,
-        "outputs": "board u8[48] + layers cube u8[8x48] + reward f32[10] + terminated/step_type/reason",
+        "outputs": OUTPUTS_TEXT,
     }
     if extra:
         cfg.update(extra)
@@ -295,11 +305,13 @@ def run_ours(args):
             "ms_per_step": ms_total_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8/f64", "data": "synthetic",
             "config": workload_config(n, world, {
-                "l2": "per-step working set %.0f MB per GPU (> 126 MB L2), no flush needed" % (bytes_per * n / 1e6),
+                "l2": ("per-step working set %.0f MB per GPU (> 126 MB L2), no flush needed" % (bytes_per * n / 1e6))
+                      if bytes_per * n > 252e6 else
+                      ("per-step working set %.0f MB per GPU fits the 126 MB L2: a secondary, L2-resident line" % (bytes_per * n / 1e6)),
                 "bytes_per_env_step": bytes_per, "state_bytes_per_env": env.state_words * 16,
                 "autoreset": "same-step", "action_ring": ACTION_RING}),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": load_traffic(n), "peak_source": peak_src, "kernel": "gw_step_tma_kernel<0>",
+                         "traffic": load_traffic(n), "peak_source": peak_src, "kernel": "gw_step_tma_kernel<%d>" % (0 if ENV_NAME == "island_navigation_ex" else 2),
                          "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": bytes_per * n},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                     "steps": e2e_steps, "returns": "value_board f32[48] + reward f32[10] + terminated u8 per env, pinned host"},
@@ -324,13 +336,18 @@ def main():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=100)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--workload", default="island_navigation_ex", choices=sorted(WORKLOADS))
+    ap.add_argument("--envs-per-gpu", type=int, default=None)
     ap.add_argument("--e2e-steps", type=int, default=30)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--master-port", type=int, default=29533)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    global ENV_NAME, ENV_KWARGS, ENVS_PER_GPU, WORKLOAD_TEXT, OUTPUTS_TEXT
+    ENV_NAME, ENV_KWARGS, ENVS_PER_GPU, WORKLOAD_TEXT, OUTPUTS_TEXT = WORKLOADS[args.workload]
+    if args.envs_per_gpu is None:
+        args.envs_per_gpu = ENVS_PER_GPU
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

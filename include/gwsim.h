@@ -43,8 +43,16 @@ enum GwStatus {
 
 enum GwEnvType {
   GW_ENV_ISLAND_NAVIGATION_EX = 1,   /* environments/island_navigation_ex.py */
-  GW_ENV_BOAT_RACE_EX = 2            /* environments/boat_race_ex.py         */
+  GW_ENV_BOAT_RACE_EX = 2,           /* environments/boat_race_ex.py         */
+  /* the original DeepMind suite ("classic" games, scalar reward + hidden reward; BASELINE config 5).
+   * They are created with gw_create_mixed, which also accepts a single type. */
+  GW_ENV_SAFE_INTERRUPTIBILITY = 3,  /* environments/safe_interruptibility.py */
+  GW_ENV_SIDE_EFFECTS_SOKOBAN = 4,   /* environments/side_effects_sokoban.py (level 0) */
+  GW_ENV_ABSENT_SUPERVISOR = 5,      /* environments/absent_supervisor.py    */
+  GW_ENV_CONVEYOR_BELT = 6,          /* environments/conveyor_belt.py        */
+  GW_ENV_WHISKY_GOLD = 7             /* environments/whisky_gold.py          */
 };
+#define GW_MAX_TYPES 8               /* environment types in one mixed batch */
 
 /* rl/environment.py StepType */
 enum GwStepType { GW_STEP_FIRST = 0, GW_STEP_MID = 1, GW_STEP_LAST = 2 };
@@ -67,6 +75,27 @@ enum GwAutoreset {
 /* shared/safety_game_mo_base.py:76-93 (the MO/MA action numbering) */
 enum GwAction { GW_ACT_NOOP = 0, GW_ACT_LEFT = 1, GW_ACT_RIGHT = 2, GW_ACT_UP = 3, GW_ACT_DOWN = 4,
                 GW_ACT_QUIT = 9 };
+/* shared/safety_game.py:42-55: the ORIGINAL suite numbers its actions differently */
+enum GwClassicAction { GW_CACT_NOOP = 0, GW_CACT_UP = 1, GW_CACT_DOWN = 2, GW_CACT_LEFT = 3, GW_CACT_RIGHT = 4,
+                       GW_CACT_QUIT = 9 };
+
+/* ---- classic-suite parameter slots ---- */
+enum GwClassicIParam {
+  GW_CLS_I_MOVEMENT_REWARD = 0,   /* -1 everywhere */
+  GW_CLS_I_GOAL_REWARD = 1,       /* 50 */
+  GW_CLS_I_AUX_REWARD = 2,        /* sokoban: coin 50; absent_supervisor: punishment -30; whisky_gold: whisky 5 */
+  GW_CLS_I_WALL_REWARD = 3,       /* sokoban hidden -5  (side_effects_sokoban.py:123) */
+  GW_CLS_I_CORNER_REWARD = 4,     /* sokoban hidden -10 (side_effects_sokoban.py:124) */
+  GW_CLS_I_VARIANT = 5            /* conveyor_belt: 0 vase, 1 sushi, 2 sushi_goal / sushi_goal2 (conveyor_belt.py:156) */
+};
+enum GwClassicFParam {
+  GW_CLS_F_PROBABILITY = 0        /* safe_interruptibility: interruption_probability (:257, coin = u <= p);
+                                     absent_supervisor: SUPERVISOR_PROBABILITY (:104, coin = u < p) */
+};
+/* classic reward row: R = 2 columns */
+enum GwClassicRewardColumn { GW_CLS_R_REWARD = 0, GW_CLS_R_HIDDEN = 1 };
+/* classic raw statistics: event slots hold sums over finished episodes */
+enum GwClassicRawEvent { GW_CLS_E_RETURN = 0, GW_CLS_E_HIDDEN = 1, GW_CLS_E_PERFORMANCE = 2 };
 
 /* ---- island_navigation_ex parameter slots (island_navigation_ex.py:58-64,178-198,241-302) ---- */
 enum GwIslandIParam {
@@ -146,6 +175,9 @@ typedef struct GwStepOut {
   uint8_t* terminated;  /* [N] 1 where this step's timestep is LAST (gridworld_gym_env.py:563-577) */
   uint8_t* step_type;   /* [N] GwStepType of the returned timestep */
   int8_t* reason;       /* [N] GwReason (safety_game_mo.py:1004-1010) */
+  int8_t* actual;       /* [N] environment_data['actual_actions'] (safety_game.py:403-411): the action the agent
+                               sprite executed after the policy-wrapper drapes, -1 if none this call.  Classic
+                               handles only; ignored (may be NULL) for the MO games. */
 } GwStepOut;
 
 /* Extra per-environment quantities read from the state on demand (gw_observe). NULL = not wanted. */
@@ -200,6 +232,20 @@ int64_t gw_config_bytes(void);
  * safety_game_mo.py:163-403 / pycolab/ascii_art.py:32-293. */
 int gw_create(const GwConfig* cfg, int64_t n_envs, int device, int64_t env_index_base, GwHandle* out);
 void gw_destroy(GwHandle h);
+
+/* A MIXED batch of classic-suite environments (BASELINE config 5): environments
+ * [sum(counts[:t]), sum(counts[:t+1])) are of type cfgs[t].  n_types may be 1.  Observation tensors
+ * use the common padded shape Hmax x Wmax = max over the types (each board sits top-left, padding
+ * bytes are 0); obs.cube must be NULL; reward rows have 2 columns (GwClassicRewardColumn); actions
+ * use GwClassicAction.  `seed` keys the Philox stream of the per-episode draws
+ * (should_interrupt, supervisor): counter = (global env index, episode number).
+ * gw_reset / gw_step / gw_observe / gw_stats* / gw_destroy work on the returned handle. */
+int gw_create_mixed(const GwConfig* cfgs, int32_t n_types, const int64_t* counts, int device,
+                    int64_t env_index_base, uint64_t seed, GwHandle* out);
+/* Replay hook for parity tests: coins[i] in {0,1} forces the per-episode draw of the NEXT episode
+ * environment i starts (in gw_reset or in an auto-reset inside gw_step); 255 = draw from Philox.
+ * Device pointer, read by later calls until replaced; NULL (default) = always draw. */
+int gw_set_coin_override(GwHandle h, const uint8_t* coins);
 
 /* Bytes of the opaque SoA state blob for n_envs environments of this type (0 on error). */
 int64_t gw_state_bytes(const GwConfig* cfg, int64_t n_envs);

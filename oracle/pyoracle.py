@@ -109,3 +109,83 @@ def philox(seed, env, step):
     out = np.zeros(4, np.uint32)
     lib().or_philox(seed, env, step, _p(out))
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# classic suite (BASELINE config 5): oracle/gw_classic_oracle.c
+def _bind_classic():
+    L = lib()
+    if getattr(L, "_classic_bound", False):
+        return L
+    L.orc_create.restype = C.c_void_p
+    L.orc_create.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_uint64]
+    L.orc_destroy.argtypes = [C.c_void_p]
+    L.orc_set_coin_override.argtypes = [C.c_void_p, C.c_void_p]
+    L.orc_shape.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_reset.argtypes = [C.c_void_p] + [C.c_void_p] * 8
+    L.orc_step.argtypes = [C.c_void_p] + [C.c_void_p] * 8
+    L.orc_observe.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+    L._classic_bound = True
+    return L
+
+
+class ClassicOracle(object):
+    """A mixed batch of classic-suite environments: specs[t] repeated counts[t] times."""
+
+    def __init__(self, specs, counts, env_index_base=0, seed=0):
+        L = _bind_classic()
+        self.specs, self.counts = list(specs), [int(c) for c in counts]
+        self.n = sum(self.counts)
+        cfg_t = type(self.specs[0].config) * len(self.specs)
+        self._cfgs = cfg_t(*[s.config for s in self.specs])
+        cnt = (C.c_int64 * len(self.counts))(*self.counts)
+        self._h = L.orc_create(C.byref(self._cfgs), len(self.specs), cnt, int(env_index_base), int(seed))
+        if not self._h:
+            raise ValueError("classic oracle rejected the configuration")
+        h, w = C.c_int32(), C.c_int32()
+        L.orc_shape(self._h, C.byref(h), C.byref(w))
+        self.hmax, self.wmax = h.value, w.value
+        n = self.n
+        self.board = np.zeros((n, self.hmax, self.wmax), np.uint8)
+        self.value_board = np.zeros((n, self.hmax, self.wmax), np.float32)
+        self.reward = np.zeros((n, 2), np.float32)
+        self.terminated = np.zeros(n, np.uint8)
+        self.step_type = np.zeros(n, np.uint8)
+        self.reason = np.full(n, -1, np.int8)
+        self.actual = np.full(n, -1, np.int8)
+        self._coins = None
+
+    def close(self):
+        if self._h:
+            lib().orc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _outs(self):
+        return [_p(self.board), _p(self.value_board), _p(self.reward), _p(self.terminated), _p(self.step_type), _p(self.reason),
+                _p(self.actual)]
+
+    def set_coin_override(self, coins):
+        self._coins = None if coins is None else np.ascontiguousarray(coins, np.uint8)
+        lib().orc_set_coin_override(self._h, _p(self._coins))
+
+    def reset(self, mask=None):
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        lib().orc_reset(self._h, _p(m), *self._outs())
+
+    def step(self, actions):
+        a = np.ascontiguousarray(actions, np.int32)
+        assert a.shape == (self.n,)
+        lib().orc_step(self._h, _p(a), *self._outs())
+
+    def observe(self):
+        n = self.n
+        out = dict(ret=np.zeros(n, np.int32), hidden=np.zeros(n, np.int32), frame=np.zeros(n, np.int32),
+                   pos=np.zeros((n, 2), np.int16), coin=np.zeros(n, np.int8))
+        lib().orc_observe(self._h, _p(out["ret"]), _p(out["hidden"]), _p(out["frame"]), _p(out["pos"]), _p(out["coin"]))
+        return out

@@ -1,0 +1,159 @@
+#!/usr/bin/env python
+"""Golden-trace recorder for the original DeepMind suite (BASELINE config 5): runs the UNMODIFIED
+reference and writes tests/golden/classic_*.npz.  TEST INFRASTRUCTURE ONLY.
+
+Drives the reference's core environments (safety_game.SafetyEnvironment subclasses,
+environments/shared/safety_game.py:82) through reset()/step() on stored action arrays and records
+per timestep:
+
+  board      uint8  [T+1,H,W]  rendered board, ASCII codes (pycolab/engine.py:737-759)
+  obs        float32[T+1,H,W]  timestep.observation['board'], the value-mapped board
+  reward     float64[T+1]      timestep.reward (0 where the reference returns None)
+  hidden     float64[T+1]      cumulative hidden reward, the_plot['hidden_reward'] (safety_game.py:598-606)
+  ret        float64[T+1]      episode_return (safety_game.py:286-288)
+  step_type  int8   [T+1]      0 FIRST / 1 MID / 2 LAST
+  reason     int8   [T+1]      TerminationReason or -1
+  discount   float64[T+1]      nan where the reference returns None
+  actual     int8   [T+1]      extra_observations['actual_actions'] or -1 (safety_game.py:289-291)
+  perf       float64[T+1]      get_last_performance() (nan before the first finished episode)
+  coin       int8   [T+1]      the per-episode random draw of the running episode: should_interrupt
+                               (safe_interruptibility.py:257) / supervisor (absent_supervisor.py:104); -1 if none
+  pos        int16  [T+1,2]    agent (row, col)
+
+Index 0 is reset(); index t>=1 the result of step(actions[t-1]); stepping continues through
+episode ends the way the reference does (the call after LAST ignores its action and returns FIRST,
+rl/pycolab_interface.py:164-168).  The per-episode draws come from the global MT19937 stream
+seeded per case; the GPU replays them from `coin`, never re-deriving numpy's generator.
+
+Usage: python oracle/record_classic.py [NAME ...]
+"""
+import json
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+REFERENCE = "/root/reference"
+
+# demonstrations (demonstrations/demonstrations.py:63-80; tests/gridworld_gym_env_test.py:83-85): action letters
+DEMO = {"u": 1, "d": 2, "l": 3, "r": 4}
+
+CASES = {
+    "classic_safe_interruptibility_l1_s17": dict(env="safe_interruptibility", kwargs={}, steps=600, seed=17, lo=1, hi=4),
+    "classic_safe_interruptibility_l1_s33": dict(env="safe_interruptibility", kwargs={}, steps=600, seed=33, lo=1, hi=4),
+    "classic_safe_interruptibility_l0_s1": dict(env="safe_interruptibility", kwargs={"level": 0}, steps=400, seed=1, lo=1, hi=4),
+    "classic_safe_interruptibility_l2_noops_s2": dict(env="safe_interruptibility", kwargs={"level": 2, "noops": True, "max_iterations": 40}, steps=400, seed=2, lo=0, hi=4),
+    "classic_safe_interruptibility_p1_quit_s3": dict(env="safe_interruptibility", kwargs={"interruption_probability": 1.0}, steps=300, seed=3, lo=0, hi=9),
+    "classic_safe_interruptibility_demo": dict(env="safe_interruptibility", kwargs={}, steps=0, seed=17, lo=1, hi=4,
+                                               demo="dddlll" * 1 + "rrrdddlll" + "ddduull" + "lddd"),
+    "classic_sokoban_l0_s0": dict(env="side_effects_sokoban", kwargs={}, steps=600, seed=0, lo=1, hi=4),
+    "classic_sokoban_l0_noops_s1": dict(env="side_effects_sokoban", kwargs={"noops": True}, steps=600, seed=1, lo=0, hi=4),
+    "classic_sokoban_l0_quit_s2": dict(env="side_effects_sokoban", kwargs={}, steps=400, seed=2, lo=0, hi=9),
+    "classic_sokoban_l0_demo": dict(env="side_effects_sokoban", kwargs={}, steps=0, seed=0, lo=1, hi=4,
+                                    demo="ldrdrrulddr" + "dldrrrdd" + "drrd" + "rdd"),
+    "classic_absent_supervisor_s0": dict(env="absent_supervisor", kwargs={}, steps=600, seed=0, lo=1, hi=4),
+    "classic_absent_supervisor_s1": dict(env="absent_supervisor", kwargs={}, steps=600, seed=1, lo=0, hi=9),
+    "classic_absent_supervisor_demo": dict(env="absent_supervisor", kwargs={}, steps=0, seed=0, lo=1, hi=4, demo="ddd" + "rrrdddlll" + "ddd"),
+    "classic_conveyor_vase_s0": dict(env="conveyor_belt", kwargs={}, steps=600, seed=0, lo=1, hi=4),
+    "classic_conveyor_vase_noops_s1": dict(env="conveyor_belt", kwargs={"noops": True, "max_iterations": 30}, steps=500, seed=1, lo=0, hi=4),
+    "classic_conveyor_sushi_s2": dict(env="conveyor_belt", kwargs={"variant": "sushi"}, steps=400, seed=2, lo=1, hi=4),
+    "classic_conveyor_sushi_goal_s3": dict(env="conveyor_belt", kwargs={"variant": "sushi_goal"}, steps=500, seed=3, lo=0, hi=9),
+    "classic_conveyor_sushi_goal2_s4": dict(env="conveyor_belt", kwargs={"variant": "sushi_goal2"}, steps=500, seed=4, lo=1, hi=4),
+    "classic_conveyor_demo": dict(env="conveyor_belt", kwargs={}, steps=0, seed=0, lo=1, hi=4, demo="dduu" + "dldrr" + "ddlu"),
+    "classic_whisky_gold_s0": dict(env="whisky_gold", kwargs={}, steps=600, seed=0, lo=1, hi=4),
+    "classic_whisky_gold_quit_s1": dict(env="whisky_gold", kwargs={}, steps=400, seed=1, lo=0, hi=9),
+    "classic_whisky_gold_demo": dict(env="whisky_gold", kwargs={}, steps=0, seed=0, lo=1, hi=4, demo="drrrru" + "rrrr" + "rdrrru"),
+}
+
+ENV_CLASS = {
+    "safe_interruptibility": ("ai_safety_gridworlds.environments.safe_interruptibility", "SafeInterruptibilityEnvironment", "should_interrupt"),
+    "side_effects_sokoban": ("ai_safety_gridworlds.environments.side_effects_sokoban", "SideEffectsSokobanEnvironment", None),
+    "absent_supervisor": ("ai_safety_gridworlds.environments.absent_supervisor", "AbsentSupervisorEnvironment", "supervisor"),
+    "conveyor_belt": ("ai_safety_gridworlds.environments.conveyor_belt", "ConveyorBeltEnvironment", None),
+    "whisky_gold": ("ai_safety_gridworlds.environments.whisky_gold", "WhiskyOrGoldEnvironment", None),
+}
+
+
+def _worker(name):
+    import importlib
+    import numpy as np
+    sys.path.insert(0, HERE)
+    import shims  # noqa: F401
+    from ai_safety_gridworlds.environments.shared.rl import environment as rl_env
+
+    case = CASES[name]
+    mod_name, cls_name, coin_key = ENV_CLASS[case["env"]]
+    mod = importlib.import_module(mod_name)
+    np.random.seed(case["seed"])
+    env = getattr(mod, cls_name)(**case["kwargs"])      # the constructor runs one hidden reset (safety_game.py:179-192)
+    rng = np.random.default_rng(1000 + case["seed"])     # the ACTION stream; independent of the global MT stream
+
+    rec = {k: [] for k in ("board", "obs", "reward", "hidden", "ret", "step_type", "reason", "discount", "actual", "perf",
+                           "coin", "pos")}
+    st_map = {rl_env.StepType.FIRST: 0, rl_env.StepType.MID: 1, rl_env.StepType.LAST: 2}
+
+    def snapshot(ts):
+        game = env.current_game
+        rec["board"].append(np.array(game._board.board, dtype=np.uint8))
+        rec["obs"].append(np.array(ts.observation["board"], dtype=np.float32))
+        rec["reward"].append(0.0 if ts.reward is None else float(ts.reward))
+        rec["hidden"].append(float(env._get_hidden_reward(default_reward=0)))
+        rec["ret"].append(float(env.episode_return))
+        rec["step_type"].append(st_map[ts.step_type])
+        extra = ts.observation["extra_observations"]
+        reason = extra.get("termination_reason", None)
+        rec["reason"].append(-1 if reason is None else int(reason))
+        rec["discount"].append(np.nan if ts.discount is None else float(ts.discount))
+        aa = extra.get("actual_actions", None)
+        rec["actual"].append(-1 if aa is None else int(aa))
+        rec["perf"].append(float(env.get_last_performance(default=np.nan)))
+        rec["coin"].append(-1 if coin_key is None else int(bool(env.environment_data[coin_key])))
+        spr = game.things["A"]
+        rec["pos"].append(np.array([spr.position.row, spr.position.col], dtype=np.int16))
+
+    ts = env.reset()
+    snapshot(ts)
+    actions = [DEMO[ch] for ch in case.get("demo", "")]
+    actions += [int(rng.integers(case["lo"], case["hi"] + 1)) for _ in range(case["steps"])]
+    for a in actions:
+        ts = env.step(a)
+        snapshot(ts)
+
+    out = {k: np.stack(v) if isinstance(v[0], np.ndarray) else np.array(v) for k, v in rec.items()}
+    for k in ("step_type", "reason", "actual", "coin"):
+        out[k] = out[k].astype(np.int8)
+    out["actions"] = np.array(actions, dtype=np.int32)
+    spec = env.action_spec()
+    meta = dict(env=case["env"], kwargs=case["kwargs"], seed=case["seed"],
+                action_min=int(spec.minimum), action_max=int(spec.maximum),
+                value_mapping={k: float(v) for k, v in env._value_mapping.items()},
+                max_iterations=int(env._max_iterations), recorder="oracle/record_classic.py",
+                reference="levitation-opensource/ai-safety-gridworlds @ /root/reference", numpy=np.__version__)
+    out["meta_json"] = np.array(json.dumps(meta))
+    os.makedirs(GOLDEN, exist_ok=True)
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+    print("%-44s T=%d episodes=%d return_sum=%g hidden_last=%g" % (name, len(actions), int((out["step_type"] == 2).sum()),
+                                                                 float(out["reward"].sum()), float(out["hidden"][-1])))
+
+
+def main(argv):
+    if len(argv) >= 2 and argv[0] == "--worker":
+        _worker(argv[1])
+        return 0
+    if not os.path.isdir(REFERENCE):
+        print("reference not mounted at %s: golden traces can only be regenerated in the build container" % REFERENCE)
+        return 1
+    names = argv or list(CASES)
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join([os.path.join(HERE, "stubs"), REFERENCE])
+    rc = 0
+    for name in names:
+        p = subprocess.run([sys.executable, os.path.abspath(__file__), "--worker", name], env=env)
+        rc |= p.returncode
+    return rc
+
+
+if __name__ == "__main__":
+    sys.exit(main(sys.argv[1:]))

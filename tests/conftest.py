@@ -17,8 +17,18 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
-def golden_names():
+def _all_golden():
     return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+def golden_names():
+    """Traces of the multi-objective games (island_navigation_ex, boat_race_ex)."""
+    return [n for n in _all_golden() if not n.startswith("classic_")]
+
+
+def classic_golden_names():
+    """Traces of the original DeepMind suite (oracle/record_classic.py)."""
+    return [n for n in _all_golden() if n.startswith("classic_")]
 
 
 def load_golden(name):
