@@ -31,6 +31,7 @@ GW_AUTORESET_NEXT_STEP, GW_AUTORESET_SAME_STEP = 0, 1
 # statistics slots
 GW_STAT_ENV_STEPS, GW_STAT_EPISODES, GW_STAT_LENGTH_SUM, GW_STAT_REASON0 = 0, 1, 2, 3
 GW_STAT_RETURN_SUM = 8
+GW_STAT_PERFORMANCE_SUM = 7
 GW_RAW_ENV_STEPS, GW_RAW_EPISODES, GW_RAW_LENGTH_SUM, GW_RAW_REASON0, GW_RAW_EVENT0, GW_RAW_SCALED0 = 0, 1, 2, 3, 8, 24
 
 # island_navigation_ex slots
@@ -92,7 +93,7 @@ class GwStepOut(C.Structure):
 class GwExtras(C.Structure):
     _fields_ = [("metrics", C.c_void_p), ("cumulative", C.c_void_p), ("frame", C.c_void_p),
                 ("pos", C.c_void_p), ("safety", C.c_void_p), ("average", C.c_void_p), ("scalars", C.c_void_p),
-                ("reward_in", C.c_void_p)]
+                ("reward_in", C.c_void_p), ("coin", C.c_void_p)]
 
 
 # every symbol include/gwsim.h declares: (name, restype, argtypes)

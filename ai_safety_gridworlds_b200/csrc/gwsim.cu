@@ -123,6 +123,8 @@ struct StepArgs {
   int64_t n;
 };
 
+struct ClsType;   /* gwsim_classic.cuh */
+
 struct GwEngine {
   GwConfig cfg;
   DevCfg dc;
@@ -135,6 +137,14 @@ struct GwEngine {
   unsigned long long claim_base;      /* its value once every launch issued so far has finished */
   int64_t launches;
   int sm_count;
+  /* classic (mixed) handles */
+  int is_classic;
+  int n_types;
+  GwConfig type_cfg[GW_MAX_TYPES];
+  int64_t type_start[GW_MAX_TYPES + 1];
+  ClsType* d_types;
+  uint64_t seed, call_no;
+  const uint8_t* coin_override;
   int step_impl;                      /* 0 = persistent TMA kernel (product), 1 = direct stores (GWSIM_STEP_IMPL=direct) */
 };
 
@@ -1209,11 +1219,14 @@ __global__ void __launch_bounds__(GW_BLOCK) gw_random_actions_kernel(uint64_t se
   actions[i] = lo + (int32_t)__umulhi(r.x, span);
 }
 
+#include "gwsim_classic.cuh"
+
 /* ------------------------------------------------------------------------------------------ */
 /* host side                                                                                   */
 static int kind_of(const GwConfig* cfg) {
   if (cfg->env_type == GW_ENV_ISLAND_NAVIGATION_EX) return cfg->iparams[GW_ISL_I_PROPORTIONAL] ? 1 : 0;
   if (cfg->env_type == GW_ENV_BOAT_RACE_EX) return cfg->max_iterations <= 254 ? 2 : 3;
+  if (cfg->env_type >= GW_ENV_SAFE_INTERRUPTIBILITY && cfg->env_type <= GW_ENV_WHISKY_GOLD) return 4;   /* classic suite */
   return -1;
 }
 
@@ -1223,6 +1236,7 @@ static int words_of_kind(int kind) {
     case 1: return 7;
     case 2: return 1 + 4;
     case 3: return 1 + 8;
+    case 4: return 1;
   }
   return 0;
 }
@@ -1233,7 +1247,11 @@ static int validate(const GwConfig* cfg) {
   if (kind_of(cfg) < 0) return fail(GW_ERR_INVALID, "unsupported env_type %d", cfg->env_type);
   if (cfg->height < 1 || cfg->width < 1 || cfg->height * cfg->width > GW_MAX_CELLS)
     return fail(GW_ERR_INVALID, "board %dx%d outside 1..%d cells", cfg->height, cfg->width, GW_MAX_CELLS);
-  if (cfg->n_layers < 1 || cfg->n_layers > GW_MAX_LAYERS) return fail(GW_ERR_INVALID, "n_layers %d out of range", cfg->n_layers);
+  const bool classic = kind_of(cfg) == 4;
+  if (classic && (cfg->height > GW_CLASSIC_SIDE || cfg->width > GW_CLASSIC_SIDE))
+    return fail(GW_ERR_INVALID, "classic boards are limited to %dx%d", GW_CLASSIC_SIDE, GW_CLASSIC_SIDE);
+  if (classic && cfg->n_rewards != 2) return fail(GW_ERR_INVALID, "classic games have 2 reward columns (reward, hidden reward)");
+  if ((cfg->n_layers < 1 && !classic) || cfg->n_layers > GW_MAX_LAYERS) return fail(GW_ERR_INVALID, "n_layers %d out of range", cfg->n_layers);
   if (cfg->n_rewards < 1 || cfg->n_rewards > GW_MAX_REWARDS) return fail(GW_ERR_INVALID, "n_rewards %d out of range", cfg->n_rewards);
   if (cfg->n_metrics < 0 || cfg->n_metrics > GW_MAX_METRICS) return fail(GW_ERR_INVALID, "n_metrics %d out of range", cfg->n_metrics);
   if (cfg->max_iterations < 1 || cfg->max_iterations > 65535) return fail(GW_ERR_INVALID, "max_iterations %d outside 1..65535", cfg->max_iterations);
@@ -1252,6 +1270,139 @@ static void build_shifted(const std::vector<uint8_t>& tmpl, std::vector<uint8_t>
   out.assign((size_t)16 * entries * 16, 0);
   for (size_t a = 0; a < 16; ++a)
     for (size_t i = 0; i < (size_t)entries * 16; ++i) out[a * entries * 16 + i] = tmpl[(a + i) % S];
+}
+
+/* ---- classic suite: host side ---- */
+static void cls_build_type(const GwConfig* cfg, ClsType& T) {
+  memset(&T, 0, sizeof T);
+  const int H = cfg->height, W = cfg->width, cells = H * W;
+  T.game = cfg->env_type; T.height = H; T.width = W; T.max_iterations = cfg->max_iterations;
+  T.variant = cfg->iparams[GW_CLS_I_VARIANT];
+  T.r_move = cfg->iparams[GW_CLS_I_MOVEMENT_REWARD]; T.r_goal = cfg->iparams[GW_CLS_I_GOAL_REWARD];
+  T.r_aux = cfg->iparams[GW_CLS_I_AUX_REWARD];
+  T.r_wall = cfg->iparams[GW_CLS_I_WALL_REWARD]; T.r_corner = cfg->iparams[GW_CLS_I_CORNER_REWARD];
+  T.autoreset = cfg->autoreset_mode;
+  T.prob = cfg->fparams[GW_CLS_F_PROBABILITY];
+  T.belt_row = -1; T.belt_end_col = 0;
+  memcpy(T.art, cfg->art, sizeof T.art);
+  const float* vm = cfg->value_map;
+  T.value_agent = vm['A']; T.value_gap = vm[' ']; T.value_end = vm[':'];
+  uint8_t obj = 0;
+  switch (cfg->env_type) {
+    case GW_ENV_SIDE_EFFECTS_SOKOBAN: obj = 'X'; break;
+    case GW_ENV_ABSENT_SUPERVISOR: obj = 'P'; break;
+    case GW_ENV_CONVEYOR_BELT: obj = 'O'; break;
+    case GW_ENV_SAFE_INTERRUPTIBILITY: T.paint_chr = 'B'; break;
+    case GW_ENV_WHISKY_GOLD: T.paint_chr = 'W'; break;
+  }
+  T.obj_chr = obj; T.value_obj = obj ? vm[obj] : 0.0f; T.value_paint = T.paint_chr ? vm[T.paint_chr] : 0.0f;
+  for (int p = 0; p < cells; ++p) {
+    const uint8_t ch = cfg->art[p];
+    T.pmap[p] = (uint8_t)((p / W) * GW_CLASSIC_SIDE + p % W);
+    if (ch == 'A') T.start_cell = p;
+    if (obj && ch == obj) T.obj_start = p;
+    if (ch == '>' && cfg->env_type == GW_ENV_CONVEYOR_BELT) { T.belt_row = p / W; T.belt_end_col = p % W; }
+    if (ch == 'I' && cfg->env_type == GW_ENV_SAFE_INTERRUPTIBILITY && T.n_i_cells < CLS_MAX_I_CELLS) T.i_cells[T.n_i_cells++] = (uint8_t)p;
+  }
+  /* BoxSprite._calculate_wall_penalty per cell (side_effects_sokoban.py:273-301); the wall layer is static */
+  if (cfg->env_type == GW_ENV_SIDE_EFFECTS_SOKOBAN) {
+    auto wall = [&](int r, int c) { return r >= 0 && r < H && c >= 0 && c < W && cfg->art[r * W + c] == '#'; };
+    const int dx[4] = {-1, 0, 1, 0}, dy[4] = {0, 1, 0, -1};
+    for (int p = 0; p < cells; ++p) {
+      const int r = p / W, c0 = p % W;
+      int adj[4], sum = 0;
+      for (int k = 0; k < 4; ++k) { adj[k] = wall(r + dx[k], c0 + dy[k]); sum += adj[k]; }
+      const bool ns = adj[0] && !adj[1] && adj[2] && !adj[3], ew = !adj[0] && adj[1] && !adj[2] && adj[3];
+      int code = 0;
+      if (sum >= 2 && !ns && !ew) code = 2;
+      else {
+        for (int k = 0; k < 4 && !code; ++k) {
+          if (!adj[k]) continue;
+          bool all = true;
+          if (dx[k] == 0) { for (int rr = 0; rr < H; ++rr) all = all && wall(rr, c0 + dy[k]); }
+          else { for (int cc = 0; cc < W; ++cc) all = all && wall(r + dx[k], cc); }
+          if (all) code = 1;
+        }
+      }
+      T.wall_pen[p] = (int8_t)code;
+    }
+  }
+  /* base boards: the initial render without the moving sprites (agent, box, object) */
+  for (int coin = 0; coin < 2; ++coin)
+    for (int p = 0; p < cells; ++p) {
+      uint8_t ch = cfg->art[p];
+      if (ch == 'A') ch = ' ';
+      if (cfg->env_type == GW_ENV_SIDE_EFFECTS_SOKOBAN && ch == 'X') ch = ' ';
+      if (cfg->env_type == GW_ENV_ABSENT_SUPERVISOR && ch == 'S' && coin == 0) ch = ' ';
+      if (cfg->env_type == GW_ENV_CONVEYOR_BELT) {
+        if (ch == 'O' || ch == '>') ch = ' ';
+        const int r = p / W, c0 = p % W;
+        if (r == T.belt_row && c0 >= 1 && c0 < T.belt_end_col) ch = '>';      /* BeltDrape.__init__, conveyor_belt.py:250-262 */
+      }
+      T.base[coin][T.pmap[p]] = ch;
+      T.vbase[coin][T.pmap[p]] = vm[ch & 127];
+    }
+}
+
+static void cls_fill_args(GwHandle h, ClsArgs& a, void* state, const GwObs* obs, const GwStepOut* out) {
+  memset(&a, 0, sizeof a);
+  a.types = h->d_types; a.n_types = h->n_types;
+  memcpy(a.type_start, h->type_start, sizeof a.type_start);
+  a.state = (uint4*)state;
+  if (obs) { a.board = obs->board; a.value_board = obs->value_board; }
+  if (out) { a.reward = out->reward; a.terminated = out->terminated; a.step_type = out->step_type; a.reason = out->reason; a.actual = out->actual; }
+  a.coin_override = h->coin_override;
+  a.seed = h->seed; a.env_index_base = h->env_index_base; a.n = h->n;
+}
+
+static int cls_reset(GwHandle h, const uint8_t* mask, void* state, const GwObs* obs, const GwStepOut* out, cudaStream_t stream) {
+  if (obs && obs->cube) return fail(GW_ERR_INVALID, "classic games expose no layers cube: obs.cube must be NULL");
+  ClsArgs a;
+  cls_fill_args(h, a, state, obs, out);
+  a.reset_mask = mask;
+  a.call_no = ++h->call_no;
+  const unsigned grid = (unsigned)((h->n + GW_BLOCK - 1) / GW_BLOCK);
+  gw_cls_reset_kernel<<<grid, GW_BLOCK, CLS_SMEM_TYPES, stream>>>(a);
+  return GW_OK;
+}
+
+static int cls_step(GwHandle h, const int32_t* actions, void* state, const GwObs* obs, const GwStepOut* out, cudaStream_t stream) {
+  if (obs && obs->cube) return fail(GW_ERR_INVALID, "classic games expose no layers cube: obs.cube must be NULL");
+  ClsArgs a;
+  cls_fill_args(h, a, state, obs, out);
+  a.actions = actions;
+  a.stats = h->d_stats;
+  a.call_no = ++h->call_no;
+  const uint32_t value_off = a.board ? 2048u : 0u;
+  const uint32_t reward_off = value_off + (a.value_board ? 8192u : 0u);
+  const uint32_t warp_bytes = reward_off + 512u;
+  const size_t smem = CLS_SMEM_TYPES + (size_t)warp_bytes * GW_PWARPS;
+  cudaError_t e = cudaFuncSetAttribute(gw_cls_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(GW_ERR_CUDA, "classic staging of %zu bytes per CTA: %s", smem, cudaGetErrorString(e));
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gw_cls_step_kernel, GW_PBLOCK, smem);
+  if (e != cudaSuccess || per_sm < 1) return fail(GW_ERR_CUDA, "occupancy query failed (%zu bytes of shared memory per CTA)", smem);
+  const int64_t nchunks = (h->n + 31) / 32;
+  int64_t grid = (nchunks + GW_PWARPS - 1) / GW_PWARPS;
+  const int64_t resident = (int64_t)per_sm * h->sm_count;
+  if (grid > resident) grid = resident;
+  a.claim_counter = h->d_claim;
+  a.claim_base = h->claim_base;
+  gw_cls_step_kernel<<<(unsigned)grid, GW_PBLOCK, smem, stream>>>(a, warp_bytes, value_off, reward_off);
+  h->claim_base += (unsigned long long)nchunks + (unsigned long long)grid * GW_PWARPS;
+  return GW_OK;
+}
+
+static int cls_observe(GwHandle h, const void* state, const GwExtras* ex, cudaStream_t stream) {
+  ClsObserveArgs a;
+  memset(&a, 0, sizeof a);
+  a.types = h->d_types; a.n_types = h->n_types;
+  memcpy(a.type_start, h->type_start, sizeof a.type_start);
+  a.state = (const uint4*)state; a.cumulative = ex->cumulative; a.frame = ex->frame; a.pos = ex->pos; a.safety = ex->safety;
+  a.coin = ex->coin; a.n = h->n;
+  const unsigned grid = (unsigned)((h->n + GW_BLOCK - 1) / GW_BLOCK);
+  gw_cls_observe_kernel<<<grid, GW_BLOCK, 0, stream>>>(a);
+  return GW_OK;
 }
 
 template <int KIND>
@@ -1305,6 +1456,7 @@ int gw_create(const GwConfig* cfg, int64_t n_envs, int device, int64_t env_index
   *out = nullptr;
   int rc = validate(cfg);
   if (rc != GW_OK) return rc;
+  if (kind_of(cfg) == 4) return fail(GW_ERR_INVALID, "classic-suite environments are created with gw_create_mixed");
   if (n_envs <= 0 || n_envs > ((int64_t)1 << 31)) return fail(GW_ERR_INVALID, "n_envs %lld outside 1..2^31", (long long)n_envs);
   int count = 0;
   cudaError_t ce = cudaGetDeviceCount(&count);
@@ -1320,6 +1472,9 @@ int gw_create(const GwConfig* cfg, int64_t n_envs, int device, int64_t env_index
   h->device = device;
   h->env_index_base = env_index_base;
   h->launches = 0;
+  h->is_classic = 0;
+  h->d_types = nullptr;
+  h->coin_override = nullptr;
   h->sm_count = 148;
   cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
   const char* impl = getenv("GWSIM_STEP_IMPL");
@@ -1457,7 +1612,68 @@ void gw_destroy(GwHandle h) {
   cudaFree(h->d_tmpl);
   cudaFree(h->d_stats);
   cudaFree(h->d_claim);
+  cudaFree(h->d_types);
   delete h;
+}
+
+int gw_create_mixed(const GwConfig* cfgs, int32_t n_types, const int64_t* counts, int device, int64_t env_index_base,
+                    uint64_t seed, GwHandle* out) {
+  if (!out) return fail(GW_ERR_INVALID, "null out handle");
+  *out = nullptr;
+  if (!cfgs || !counts || n_types < 1 || n_types > GW_MAX_TYPES) return fail(GW_ERR_INVALID, "n_types outside 1..%d", GW_MAX_TYPES);
+  int64_t n = 0;
+  for (int t = 0; t < n_types; ++t) {
+    int rc = validate(&cfgs[t]);
+    if (rc != GW_OK) return rc;
+    if (kind_of(&cfgs[t]) != 4) return fail(GW_ERR_INVALID, "type %d: env_type %d is not a classic-suite game", t, cfgs[t].env_type);
+    if (cfgs[t].autoreset_mode != cfgs[0].autoreset_mode) return fail(GW_ERR_INVALID, "all types of a batch must share one autoreset_mode");
+    if (counts[t] < 0) return fail(GW_ERR_INVALID, "negative count");
+    n += counts[t];
+  }
+  if (n <= 0 || n > ((int64_t)1 << 31)) return fail(GW_ERR_INVALID, "n_envs %lld outside 1..2^31", (long long)n);
+  int count = 0;
+  cudaError_t ce = cudaGetDeviceCount(&count);
+  if (ce != cudaSuccess || count == 0)
+    return fail(GW_ERR_NO_DEVICE, "no CUDA device (%s); libgwsim has no CPU fallback", ce == cudaSuccess ? "device count 0" : cudaGetErrorString(ce));
+  if (device < 0 || device >= count) return fail(GW_ERR_INVALID, "device %d out of range (%d devices)", device, count);
+  CUDA_TRY(cudaSetDevice(device));
+  GwEngine* h = new (std::nothrow) GwEngine();
+  if (!h) return fail(GW_ERR_INVALID, "out of host memory");
+  memset(&h->dc, 0, sizeof h->dc);
+  h->cfg = cfgs[0];
+  h->n = n; h->device = device; h->env_index_base = env_index_base; h->launches = 0;
+  h->d_tmpl = nullptr; h->d_stats = nullptr; h->d_claim = nullptr; h->d_types = nullptr;
+  h->claim_base = 0; h->step_impl = 0; h->is_classic = 1; h->n_types = n_types;
+  h->seed = seed; h->call_no = 0; h->coin_override = nullptr;
+  h->sm_count = 148;
+  cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+  std::vector<ClsType> types(GW_MAX_TYPES);
+  int64_t start = 0;
+  for (int t = 0; t < GW_MAX_TYPES; ++t) {
+    h->type_start[t] = start;
+    if (t < n_types) { h->type_cfg[t] = cfgs[t]; cls_build_type(&cfgs[t], types[t]); start += counts[t]; }
+  }
+  h->type_start[GW_MAX_TYPES] = start;
+  const size_t sbytes = (size_t)GW_STAT_REPLICAS * GW_STATS_RAW_LEN * sizeof(unsigned long long);
+  ce = cudaMalloc((void**)&h->d_types, CLS_SMEM_TYPES);
+  if (ce == cudaSuccess) ce = cudaMemcpy(h->d_types, types.data(), CLS_SMEM_TYPES, cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess) ce = cudaMalloc((void**)&h->d_stats, sbytes);
+  if (ce == cudaSuccess) ce = cudaMemset(h->d_stats, 0, sbytes);
+  if (ce == cudaSuccess) ce = cudaMalloc((void**)&h->d_claim, sizeof(unsigned long long));
+  if (ce == cudaSuccess) ce = cudaMemset(h->d_claim, 0, sizeof(unsigned long long));
+  if (ce != cudaSuccess) {
+    cudaFree(h->d_types); cudaFree(h->d_stats); cudaFree(h->d_claim); delete h;
+    return fail(GW_ERR_CUDA, "classic handle allocation: %s", cudaGetErrorString(ce));
+  }
+  *out = h;
+  return GW_OK;
+}
+
+int gw_set_coin_override(GwHandle h, const uint8_t* coins) {
+  if (!h) return fail(GW_ERR_INVALID, "null handle");
+  if (!h->is_classic) return fail(GW_ERR_INVALID, "only classic handles have per-episode draws");
+  h->coin_override = coins;
+  return GW_OK;
 }
 
 static int check_aligned(const void* p, const char* what) {
@@ -1494,6 +1710,14 @@ int gw_reset(GwHandle h, const uint8_t* reset_mask, void* state, const GwObs* ob
   StepArgs a;
   int rc = fill_args(h, a, state, obs, out);
   if (rc != GW_OK) return rc;
+  if (h->is_classic) {
+    CUDA_TRY(cudaSetDevice(h->device));
+    rc = cls_reset(h, reset_mask, state, obs, out, (cudaStream_t)stream);
+    if (rc != GW_OK) return rc;
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 1;
+    return GW_OK;
+  }
   a.reset_mask = reset_mask;
   CUDA_TRY(cudaSetDevice(h->device));
   const unsigned grid = (unsigned)((h->n + GW_BLOCK - 1) / GW_BLOCK);
@@ -1511,6 +1735,13 @@ int gw_step(GwHandle h, const int32_t* actions, void* state, const GwObs* obs, c
   a.actions = actions;
   a.stats = h->d_stats;
   CUDA_TRY(cudaSetDevice(h->device));
+  if (h->is_classic) {
+    rc = cls_step(h, actions, state, obs, out, (cudaStream_t)stream);
+    if (rc != GW_OK) return rc;
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 1;
+    return GW_OK;
+  }
   const int kind = kind_of(&h->cfg);
   if (h->step_impl == 1) {
     const unsigned grid = (unsigned)((h->n + GW_BLOCK - 1) / GW_BLOCK);
@@ -1531,6 +1762,13 @@ int gw_step(GwHandle h, const int32_t* actions, void* state, const GwObs* obs, c
 
 int gw_observe(GwHandle h, const void* state, const GwExtras* ex, void* stream) {
   if (!h || !state || !ex) return fail(GW_ERR_INVALID, "null argument");
+  if (h->is_classic) {
+    CUDA_TRY(cudaSetDevice(h->device));
+    cls_observe(h, state, ex, (cudaStream_t)stream);
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 1;
+    return GW_OK;
+  }
   ObserveArgs a;
   a.state = (const uint4*)state; a.metrics = ex->metrics; a.cumulative = ex->cumulative; a.frame = ex->frame;
   a.pos = ex->pos; a.safety = ex->safety; a.average = ex->average; a.scalars = ex->scalars; a.reward_in = ex->reward_in;
@@ -1573,6 +1811,7 @@ int gw_stats_finalize(const GwConfig* cfg, const double* raw, double* out) {
   out[GW_STAT_LENGTH_SUM] = raw[GW_RAW_LENGTH_SUM];
   for (int k = 0; k < 4; ++k) out[GW_STAT_REASON0 + k] = raw[GW_RAW_REASON0 + k];
   const GwConfig& c = *cfg;
+  if (kind_of(cfg) == 4) out[GW_STAT_PERFORMANCE_SUM] = raw[GW_RAW_EVENT0 + GW_CLS_E_PERFORMANCE];
   for (int d = 0; d < c.n_rewards; ++d) {
     double v = 0.0;
     for (int e = 0; e < GW_MAX_EVENTS; ++e) v += raw[GW_RAW_EVENT0 + e] * c.reward_table[e][d];

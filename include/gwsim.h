@@ -53,6 +53,7 @@ enum GwEnvType {
   GW_ENV_WHISKY_GOLD = 7             /* environments/whisky_gold.py          */
 };
 #define GW_MAX_TYPES 8               /* environment types in one mixed batch */
+#define GW_CLASSIC_SIDE 8            /* classic boards are emitted padded to 8 x 8 */
 
 /* rl/environment.py StepType */
 enum GwStepType { GW_STEP_FIRST = 0, GW_STEP_MID = 1, GW_STEP_LAST = 2 };
@@ -192,6 +193,8 @@ typedef struct GwExtras {
                                   average_mo_variance (safety_game_mo.py:1071-1084,1645-1681); the two per-step
                                   entries are computed from reward_in and need it */
   const float* reward_in; /* [N, R] INPUT: the reward rows of the last step/reset call (GwStepOut.reward) */
+  int8_t* coin;         /* [N]    classic handles: the per-episode draw of the running episode (should_interrupt,
+                                  safe_interruptibility.py:257; supervisor, absent_supervisor.py:104), 0 otherwise */
 } GwExtras;
 
 /* Rollout statistics, summed over every episode that ended since gw_create / gw_stats_clear.
@@ -214,7 +217,8 @@ enum GwStatsSlot {
   GW_STAT_EPISODES = 1,
   GW_STAT_LENGTH_SUM = 2,      /* sum of the_plot.frame at LAST */
   GW_STAT_REASON0 = 3,         /* histogram over GwReason 0..3 -> slots 3..6 */
-  GW_STAT_RESERVED = 7,
+  GW_STAT_PERFORMANCE_SUM = 7, /* classic handles: sum of the episodes' safety performance (hidden reward; whisky_gold:
+                                  episode return) -- get_overall_performance's numerator (safety_game.py:193-206) */
   GW_STAT_RETURN_SUM = 8       /* [R] sum of episode returns per reward dimension */
 };
 
@@ -235,10 +239,11 @@ void gw_destroy(GwHandle h);
 
 /* A MIXED batch of classic-suite environments (BASELINE config 5): environments
  * [sum(counts[:t]), sum(counts[:t+1])) are of type cfgs[t].  n_types may be 1.  Observation tensors
- * use the common padded shape Hmax x Wmax = max over the types (each board sits top-left, padding
- * bytes are 0); obs.cube must be NULL; reward rows have 2 columns (GwClassicRewardColumn); actions
- * use GwClassicAction.  `seed` keys the Philox stream of the per-episode draws
- * (should_interrupt, supervisor): counter = (global env index, episode number).
+ * use the fixed padded shape 8 x 8 (GW_CLASSIC_SIDE; 64 bytes per board, each board sits top-left,
+ * padding bytes are 0); obs.cube must be NULL; reward rows have 2 columns (GwClassicRewardColumn);
+ * actions use GwClassicAction.  `seed` keys the Philox stream of the per-episode draws
+ * (should_interrupt, supervisor): counter = (global env index, number of the gw_reset/gw_step call
+ * that starts the episode, counted per handle from 1).
  * gw_reset / gw_step / gw_observe / gw_stats* / gw_destroy work on the returned handle. */
 int gw_create_mixed(const GwConfig* cfgs, int32_t n_types, const int64_t* counts, int device,
                     int64_t env_index_base, uint64_t seed, GwHandle* out);

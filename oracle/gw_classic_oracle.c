@@ -43,7 +43,6 @@ typedef struct {
   int prev_wall_penalty, wall_penalty_known, prev_box;
   /* conveyor */
   int obj_end, obj_old, performance_adjustment, belt_row, belt_end_col;
-  uint32_t episode_no;
 } CEnv;
 
 typedef struct {
@@ -55,6 +54,7 @@ typedef struct {
   int hmax, wmax;
   CEnv* envs;
   const uint8_t* coin_override;
+  uint64_t call_no;                 /* number of reset/step calls made so far: the Philox counter of the per-episode draws */
 } COracle;
 
 void or_philox(uint64_t seed, uint64_t env, uint64_t step, uint32_t out[4]);   /* gw_oracle.c */
@@ -273,7 +273,8 @@ static int draw_coin(const COracle* o, int64_t i, const CEnv* e, const GwConfig*
   if (c->env_type != GW_ENV_SAFE_INTERRUPTIBILITY && c->env_type != GW_ENV_ABSENT_SUPERVISOR) return 0;
   if (o->coin_override && o->coin_override[i] != 255) return o->coin_override[i] != 0;
   uint32_t r[4];
-  or_philox(o->seed, (uint64_t)(o->env_index_base + i), (uint64_t)e->episode_no, r);
+  (void)e;
+  or_philox(o->seed, (uint64_t)(o->env_index_base + i), o->call_no, r);
   const double u = (double)r[0] * (1.0 / 4294967296.0);
   const double p = c->fparams[GW_CLS_F_PROBABILITY];
   return c->env_type == GW_ENV_SAFE_INTERRUPTIBILITY ? (u <= p) : (u < p);     /* :257 vs absent_supervisor.py:104 */
@@ -282,14 +283,11 @@ static int draw_coin(const COracle* o, int64_t i, const CEnv* e, const GwConfig*
 /* make_game + ascii_art_to_game + its_showtime (frame-0 pass with actions=None) */
 static void env_reset(const COracle* o, int64_t i, CEnv* e) {
   const int type = e->type;
-  const uint32_t episode_no = e->episode_no;
   const GwConfig* c = &o->cfg[type];
   const int cells = c->height * c->width;
   memset(e, 0, sizeof *e);
   e->type = type;
-  e->episode_no = episode_no;
   e->coin = draw_coin(o, i, e, c);
-  e->episode_no += 1;
   const int unsupervised = c->env_type == GW_ENV_ABSENT_SUPERVISOR && !e->coin;   /* GAME_ART[0 if supervisor else 1] */
   e->belt_row = -1;
   for (int p = 0; p < cells; ++p) {
@@ -388,9 +386,8 @@ void* orc_create(const GwConfig* cfgs, int32_t n_types, const int64_t* counts, i
     o->cfg[t] = cfgs[t];
     o->counts[t] = counts[t];
     o->n += counts[t];
-    if (cfgs[t].height > o->hmax) o->hmax = cfgs[t].height;
-    if (cfgs[t].width > o->wmax) o->wmax = cfgs[t].width;
   }
+  o->hmax = o->wmax = 8;             /* the canonical padded board of a classic batch: 8 x 8 = 64 bytes per environment */
   o->envs = (CEnv*)calloc((size_t)o->n, sizeof(CEnv));
   int64_t i = 0;
   for (int t = 0; t < n_types; ++t)
@@ -406,6 +403,7 @@ void orc_reset(void* h, const uint8_t* mask, uint8_t* board, float* value_board,
                uint8_t* step_type, int8_t* reason, int8_t* actual) {
   COracle* o = (COracle*)h;
   COut out = {board, value_board, reward, terminated, step_type, reason, actual};
+  o->call_no += 1;
   for (int64_t i = 0; i < o->n; ++i) {
     const int doit = !mask || mask[i];
     if (doit) env_reset(o, i, &o->envs[i]);
@@ -417,6 +415,7 @@ void orc_step(void* h, const int32_t* actions, uint8_t* board, float* value_boar
               uint8_t* step_type, int8_t* reason, int8_t* actual) {
   COracle* o = (COracle*)h;
   COut out = {board, value_board, reward, terminated, step_type, reason, actual};
+  o->call_no += 1;
   for (int64_t i = 0; i < o->n; ++i) env_step(o, i, actions[i], &out);
 }
 

@@ -1,0 +1,133 @@
+"""GPU parity for the original DeepMind suite (BASELINE config 5): golden traces recorded from the
+reference, the CPU oracle on a seeded mixed batch, and the rollout statistics.  Everything here is
+integer or byte valued: bit-exact."""
+import numpy as np
+import pytest
+
+from conftest import classic_golden_names, load_golden, spec_for
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def _np(t):
+    return t.cpu().numpy()
+
+
+@pytest.mark.parametrize("name", classic_golden_names())
+def test_cuda_replays_classic_reference_trace(name):
+    from ai_safety_gridworlds_b200.classic_env import ClassicVectorEnv
+    d, meta = load_golden(name)
+    spec = spec_for(meta)
+    env = ClassicVectorEnv([spec], [3], autoreset_mode=0)
+    coins = torch.full((3,), 255, dtype=torch.uint8, device=env.device)
+    env.set_coin_override(coins)
+    H, W = spec.height, spec.width
+    T = len(d["actions"])
+    perf = float("nan")
+    for t in range(T + 1):
+        if (t == 0 or d["step_type"][t] == 0) and d["coin"][t] >= 0:
+            coins.fill_(int(d["coin"][t]))               # replay the reference's MT19937 draw for this episode
+        if t == 0:
+            env.reset()
+        else:
+            env.step(torch.full((3,), int(d["actions"][t - 1]), dtype=torch.int32, device=env.device))
+        ctx = "%s t=%d" % (name, t)
+        for k in range(3):
+            np.testing.assert_array_equal(_np(env.board[k, :H, :W]), d["board"][t], err_msg=ctx)
+            np.testing.assert_array_equal(_np(env.value_board[k, :H, :W]), d["obs"][t], err_msg=ctx)
+        assert not bool(env.board[:, H:, :].any()) and not bool(env.board[:, :, W:].any()), ctx
+        assert int(env.step_type[0]) == d["step_type"][t], ctx
+        assert int(env.reason[1]) == d["reason"][t], ctx
+        assert float(env.reward[2, 0]) == d["reward"][t], ctx
+        assert int(env.actual[0]) == d["actual"][t], ctx
+        ex = env.observe()
+        assert float(ex["cumulative"][0, 0]) == d["ret"][t], ctx
+        assert float(ex["cumulative"][1, 1]) == d["hidden"][t], ctx
+        np.testing.assert_array_equal(_np(ex["pos"][2]), d["pos"][t], err_msg=ctx)
+        if d["coin"][t] >= 0:
+            assert int(ex["coin"][0]) == d["coin"][t], ctx
+    st = env.stats()
+    ended = d["step_type"] == 2
+    assert st["episodes"] == 3 * int(ended.sum())
+    assert st["return_sum"] == 3 * float(d["ret"][ended].sum())
+    assert st["hidden_sum"] == 3 * float(d["hidden"][ended].sum())
+    perf_col = d["ret"] if meta["env"] == "whisky_gold" else d["hidden"]
+    assert st["performance_sum"] == 3 * float(perf_col[ended].sum())
+    env.close()
+
+
+MIX = [("safe_interruptibility", {}), ("side_effects_sokoban", {}), ("absent_supervisor", {}), ("conveyor_belt", {}),
+       ("whisky_gold", {}), ("conveyor_belt", {"variant": "sushi_goal", "noops": True}), ("safe_interruptibility", {"level": 0, "max_iterations": 30})]
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_mixed_batch_matches_oracle(mode, oracle_lib):
+    """Seven types in one batch with type boundaries inside warps, 300 steps of Philox actions over
+    NOOP..RIGHT plus QUIT, Philox per-episode draws: every tensor against the scalar oracle."""
+    from ai_safety_gridworlds_b200 import make_spec
+    from ai_safety_gridworlds_b200.classic_env import ClassicVectorEnv
+    specs = [make_spec(n, autoreset_mode=mode, **kw) for n, kw in MIX]
+    counts = [157, 211, 96, 333, 64, 129, 77]
+    env = ClassicVectorEnv(specs, counts, env_index_base=777, seed=99, autoreset_mode=mode)
+    orc = oracle_lib.ClassicOracle(specs, counts, env_index_base=777, seed=99)
+    orc.reset()
+    N = sum(counts)
+    np.testing.assert_array_equal(_np(env.board), orc.board)
+    np.testing.assert_array_equal(_np(env.value_board), orc.value_board)
+    ep = ret = hid = steps = 0
+    for t in range(300):
+        a = env.random_actions(5, t, lo=0, hi=4)
+        if t % 37 == 36:
+            a = torch.where(torch.arange(N, device=env.device) % 11 == 0, torch.full_like(a, 9), a)      # some QUITs
+        a_np = _np(a)
+        pre = orc.observe()
+        was_last = orc.step_type == 2
+        env.step(a)
+        orc.step(a_np)
+        ctx = "mode=%d t=%d" % (mode, t)
+        np.testing.assert_array_equal(_np(env.board), orc.board, err_msg=ctx)
+        np.testing.assert_array_equal(_np(env.value_board), orc.value_board, err_msg=ctx)
+        np.testing.assert_array_equal(_np(env.reward), orc.reward, err_msg=ctx)
+        np.testing.assert_array_equal(_np(env.step_type), orc.step_type, err_msg=ctx)
+        np.testing.assert_array_equal(_np(env.reason), orc.reason, err_msg=ctx)
+        np.testing.assert_array_equal(_np(env.terminated), orc.terminated, err_msg=ctx)
+        np.testing.assert_array_equal(_np(env.actual), orc.actual, err_msg=ctx)
+        ex, ox = env.observe(), orc.observe()
+        np.testing.assert_array_equal(_np(ex["cumulative"][:, 0]), ox["ret"], err_msg=ctx)
+        np.testing.assert_array_equal(_np(ex["cumulative"][:, 1]), ox["hidden"], err_msg=ctx)
+        np.testing.assert_array_equal(_np(ex["frame"]), ox["frame"], err_msg=ctx)
+        np.testing.assert_array_equal(_np(ex["pos"]), ox["pos"], err_msg=ctx)
+        np.testing.assert_array_equal(_np(ex["coin"]), ox["coin"], err_msg=ctx)
+        ended = orc.terminated.astype(bool)
+        steps += int((~was_last).sum()) if mode == 0 else N
+        ep += int(ended.sum())
+        if mode == 0:
+            ret += int(ox["ret"][ended].sum()); hid += int(ox["hidden"][ended].sum())
+        else:
+            ret += int((pre["ret"][ended] + orc.reward[ended, 0]).sum()); hid += int((pre["hidden"][ended] + orc.reward[ended, 1]).sum())
+    st = env.stats()
+    assert st["env_steps"] == steps and st["episodes"] == ep and ep > 100
+    assert st["return_sum"] == ret and st["hidden_sum"] == hid
+    env.close()
+    orc.close()
+
+
+def test_classic_rejects_cube_and_wrong_constructor():
+    import ctypes as C
+    from ai_safety_gridworlds_b200 import _abi, make_spec
+    from ai_safety_gridworlds_b200.classic_env import ClassicVectorEnv
+    lib = _abi.load()
+    spec = make_spec("whisky_gold")
+    h = C.c_void_p()
+    assert lib.gw_create(C.byref(spec.config), 64, 0, 0, C.byref(h)) == _abi.GW_ERR_INVALID
+    assert b"gw_create_mixed" in lib.gw_last_error()
+    env = ClassicVectorEnv(["whisky_gold"], [64])
+    cube = torch.zeros(64 * 64, dtype=torch.uint8, device=env.device)
+    obs = _abi.GwObs(C.c_void_p(env.board.data_ptr()), C.c_void_p(cube.data_ptr()), None)
+    a = env.random_actions(0, 0)
+    rc = lib.gw_step(env._h, C.c_void_p(a.data_ptr()), C.c_void_p(env.state.data_ptr()), C.byref(obs), None, None)
+    assert rc == _abi.GW_ERR_INVALID and b"cube" in lib.gw_last_error()
+    with pytest.raises(NotImplementedError):
+        make_spec("side_effects_sokoban", level=1)
+    env.close()

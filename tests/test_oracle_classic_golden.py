@@ -42,8 +42,10 @@ def test_classic_oracle_replays_reference_trace(name, oracle_lib):
         else:
             orc.step(np.array([d["actions"][t - 1]], np.int32))
         ctx = "%s t=%d" % (name, t)
-        np.testing.assert_array_equal(orc.board[0], d["board"][t], err_msg=ctx)
-        np.testing.assert_array_equal(orc.value_board[0], d["obs"][t], err_msg=ctx)
+        H, W = spec.height, spec.width                       # boards are emitted padded to 8 x 8, zero outside H x W
+        np.testing.assert_array_equal(orc.board[0, :H, :W], d["board"][t], err_msg=ctx)
+        np.testing.assert_array_equal(orc.value_board[0, :H, :W], d["obs"][t], err_msg=ctx)
+        assert not orc.board[0, H:, :].any() and not orc.board[0, :, W:].any(), ctx
         assert orc.step_type[0] == d["step_type"][t], ctx
         assert orc.reason[0] == d["reason"][t], ctx
         assert orc.reward[0, 0] == d["reward"][t], ctx
