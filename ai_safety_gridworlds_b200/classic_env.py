@@ -111,6 +111,43 @@ class ClassicVectorEnv(object):
     def observation(self):
         return {"board": self.board, "value_board": self.value_board}
 
+    # host-buffer (end-to-end) path: actions H2D, kernel, observation + reward + terminated D2H
+    def step_host(self, actions_host, observation="value_board"):
+        if getattr(self, "_host", None) is None:
+            N, pin = self.num_envs, dict(pin_memory=True)
+            self._host = dict(value_board=torch.zeros((N, SIDE, SIDE), dtype=torch.float32, **pin),
+                              board=torch.zeros((N, SIDE, SIDE), dtype=torch.uint8, **pin),
+                              reward=torch.zeros((N, 2), dtype=torch.float32, **pin),
+                              terminated=torch.zeros((N,), dtype=torch.uint8, **pin))
+            self._dev_actions = torch.zeros((N,), dtype=torch.int32, device=self.device)
+        hb = self._host
+        self._dev_actions.copy_(actions_host, non_blocking=True)
+        _abi.check(self.step_raw(_ptr(self._dev_actions)))
+        src = self.value_board if observation == "value_board" else self.board
+        hb[observation].copy_(src, non_blocking=True)
+        hb["reward"].copy_(self.reward, non_blocking=True)
+        hb["terminated"].copy_(self.terminated, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return hb[observation], hb["reward"], hb["terminated"]
+
+    def host_bytes_per_step(self, observation="value_board"):
+        return self.num_envs * 4, self.num_envs * ((256 if observation == "value_board" else 64) + 8 + 1)
+
+    @property
+    def state_words(self):
+        return 1
+
+    def finalize_stats(self, raw_host):
+        raw = np.ascontiguousarray(raw_host, np.float64)
+        out = np.zeros(_abi.GW_STATS_LEN, np.float64)
+        _abi.check(self._lib.gw_stats_finalize(C.byref(self.specs[0].config), raw.ctypes.data_as(C.POINTER(C.c_double)),
+                                               out.ctypes.data_as(C.POINTER(C.c_double))))
+        ep = out[_abi.GW_STAT_EPISODES]
+        return dict(env_steps=int(out[_abi.GW_STAT_ENV_STEPS]), episodes=int(ep), length_sum=int(out[_abi.GW_STAT_LENGTH_SUM]),
+                    mean_length=float(out[_abi.GW_STAT_LENGTH_SUM] / ep) if ep else float("nan"),
+                    return_sum=float(out[_abi.GW_STAT_RETURN_SUM]), hidden_sum=float(out[_abi.GW_STAT_RETURN_SUM + 1]),
+                    performance_sum=float(out[_abi.GW_STAT_PERFORMANCE_SUM]))
+
     def random_actions(self, seed, step, out=None, lo=1, hi=4):
         if out is None:
             out = torch.empty((self.num_envs,), dtype=torch.int32, device=self.device)

@@ -38,7 +38,12 @@ WORKLOADS = {
     "boat_race_ex": ("boat_race_ex", {"level": 3}, 1 << 16,
                      "boat_race_ex level 3 (humans), iterations + repetition penalties (SURVEY 8d config 2)",
                      "board u8[49] + layers cube u8[9x49] + reward f32[6] + terminated/step_type/reason"),
+    "classic_mixed": ("classic_mixed", {}, 1 << 20,
+                      "original suite mixed batch, equal fifths: safe_interruptibility L1 p=0.5, side_effects_sokoban L0, "
+                      "absent_supervisor, conveyor_belt vase, whisky_gold (SURVEY 8d config 5)",
+                      "padded board u8[8x8] + reward/hidden f32[2] + terminated/step_type/reason/actual"),
 }
+CLASSIC_TYPES = ["safe_interruptibility", "side_effects_sokoban", "absent_supervisor", "conveyor_belt", "whisky_gold"]
 WORKLOAD_TEXT = WORKLOADS["island_navigation_ex"][3]
 OUTPUTS_TEXT = WORKLOADS["island_navigation_ex"][4]
 METRIC = "env_steps_per_sec"
@@ -128,7 +133,7 @@ def load_traffic(envs_per_gpu):
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_step_traffic.json")) as f:
             t = json.load(f)
-        if int(t.get("envs_per_gpu", -1)) == envs_per_gpu:
+        if int(t.get("envs_per_gpu", -1)) == envs_per_gpu and ENV_NAME == "island_navigation_ex":
             return float(t["dram_bytes_per_launch"])
     except Exception:
         pass
@@ -165,6 +170,10 @@ def cpu_baseline(spec, threads, budget_s=12.0):
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
+        return 0
+    if ENV_NAME == "classic_mixed":
+        print(json.dumps({"impl": "reference", "unavailable": "the reference arm times the headline workload only; "
+                          "classic_mixed is a secondary evidence line"}))
         return 0
     import __graft_entry__ as ge
     from oracle import pyoracle
@@ -228,11 +237,27 @@ def run_ours(args):
 
     n = args.envs_per_gpu
     dev = torch.device("cuda", local_rank)
-    spec = make_spec(ENV_NAME, autoreset_mode=1, **ENV_KWARGS)
-    env = VectorEnv(spec, n, device=dev, env_index_base=rank * n, autoreset_mode=1, want_value_board=False)
+    classic = ENV_NAME == "classic_mixed"
+    if classic:
+        from ai_safety_gridworlds_b200.classic_env import ClassicVectorEnv
+        specs = [make_spec(t, autoreset_mode=1) for t in CLASSIC_TYPES]
+        counts = [n // 5] * 4 + [n - 4 * (n // 5)]
+        spec = specs[0]
+
+        def make_env(value_board):
+            return ClassicVectorEnv(specs, counts, device=dev, env_index_base=rank * n, seed=0, autoreset_mode=1,
+                                    want_value_board=value_board)
+        lo_hi = dict(lo=1, hi=4)
+    else:
+        spec = make_spec(ENV_NAME, autoreset_mode=1, **ENV_KWARGS)
+
+        def make_env(value_board):
+            return VectorEnv(spec, n, device=dev, env_index_base=rank * n, autoreset_mode=1, want_value_board=value_board)
+        lo_hi = {}
+    env = make_env(False)
     ring = torch.empty((ACTION_RING, n), dtype=torch.int32, device=dev)
     for r in range(ACTION_RING):
-        env.random_actions(seed=0, step=r, out=ring[r])
+        env.random_actions(seed=0, step=r, out=ring[r], **lo_hi)
     ring_ptrs = [_ptr(ring[r]) for r in range(ACTION_RING)]
     stream = torch.cuda.current_stream(dev)
 
@@ -276,7 +301,7 @@ def run_ours(args):
 
     # ---- end to end through the public API with host buffers ---------------------------------
     e2e_steps = max(3, min(args.steps, args.e2e_steps))
-    env_e = VectorEnv(spec, n, device=dev, env_index_base=rank * n, autoreset_mode=1, want_cube=True, want_value_board=True)
+    env_e = make_env(True)
     host_ring = [ring[r].cpu().pin_memory() for r in range(ACTION_RING)]
     for t in range(3):
         env_e.step_host(host_ring[t % ACTION_RING])
@@ -311,15 +336,15 @@ def run_ours(args):
                 "bytes_per_env_step": bytes_per, "state_bytes_per_env": env.state_words * 16,
                 "autoreset": "same-step", "action_ring": ACTION_RING}),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": load_traffic(n), "peak_source": peak_src, "kernel": "gw_step_tma_kernel<%d>" % (0 if ENV_NAME == "island_navigation_ex" else 2),
+                         "traffic": load_traffic(n), "peak_source": peak_src, "kernel": "gw_cls_step_kernel" if classic else "gw_step_tma_kernel<%d>" % (0 if ENV_NAME == "island_navigation_ex" else 2),
                          "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": bytes_per * n},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
-                    "steps": e2e_steps, "returns": "value_board f32[48] + reward f32[10] + terminated u8 per env, pinned host"},
+                    "steps": e2e_steps, "returns": "value-mapped board f32 + reward row f32 + terminated u8 per env, pinned host"},
             "gpu_launches": step_launches,
             "clocks": clocks,
-            "episodes_finished": stats["episodes"], "mean_episode_length": stats["mean_length"],
+            "episodes_finished": stats["episodes"], "mean_episode_length": stats.get("mean_length"),
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not classic:
             line["cpu_baseline"] = cpu_baseline(spec, os.cpu_count() or 1)
         print(json.dumps(line))
     env.close()
