@@ -96,6 +96,47 @@ class GwExtras(C.Structure):
                 ("reward_in", C.c_void_p), ("coin", C.c_void_p)]
 
 
+# ---- include/gwsim_fm.h: firemaker_ex_ma (multi-agent) ----
+GW_FM_SIDE, GW_FM_CELLS, GW_FM_AGENTS, GW_FM_LAYERS = 17, 289, 3, 9
+GW_FM_WCROP, GW_FM_SCROP, GW_FM_METRICS, GW_FM_STATE_WORDS, GW_FM_MAX_DRAWS = 5, 33, 16, 8, 1800
+FM_R = dict(AGENT_MOVEMENT=0, WORKSHOP_WORK=1, WORKSHOP_ENERGY=2, SUP_MOVEMENT=3, SUP_EXTERNAL_FIRE=4, SUP_TRESPASSING=5,
+            SUP_STOP_BUTTON=6, SUP_WORKSHOP=7)
+
+
+class GwFmConfig(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("max_iterations", C.c_int32), ("autoreset_mode", C.c_int32), ("randomize_order", C.c_int32),
+        ("stop_button_duration", C.c_int32), ("reserved", C.c_int32 * 3),
+        ("fire_continuation_probability", C.c_double), ("fire_spread_probability_at_distance_one", C.c_double),
+        ("fire_spread_exclusive_max_distance", C.c_double), ("rewards", C.c_double * 8),
+        ("value_map", C.c_float * 128), ("art", C.c_uint8 * (GW_FM_CELLS + 7)),
+    ]
+
+
+class GwFmObs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("board", "cube", "crop_workers", "crop_supervisor", "lcrop_workers", "lcrop_supervisor")]
+
+
+class GwFmOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("reward_workers", "reward_supervisor", "terminated", "step_type")]
+
+
+class GwFmExtras(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("metrics", "cumulative", "frame", "pos", "ext_fires")]
+
+
+FM_SYMBOLS = [
+    ("gw_fm_config_bytes", C.c_int64, []),
+    ("gw_fm_create", C.c_int, [C.POINTER(GwFmConfig), C.c_int64, C.c_int, C.c_int64, C.c_uint64, C.POINTER(C.c_void_p)]),
+    ("gw_fm_destroy", None, [C.c_void_p]),
+    ("gw_fm_state_bytes", C.c_int64, [C.c_int64]),
+    ("gw_fm_reset", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(GwFmObs), C.POINTER(GwFmOut), C.c_void_p]),
+    ("gw_fm_step", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(GwFmObs),
+                             C.POINTER(GwFmOut), C.c_void_p]),
+    ("gw_fm_observe", C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GwFmExtras), C.c_void_p]),
+    ("gw_fm_launch_count", C.c_int64, [C.c_void_p]),
+]
+
 # every symbol include/gwsim.h declares: (name, restype, argtypes)
 SYMBOLS = [
     ("gw_abi_version", C.c_int, []),

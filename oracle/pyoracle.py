@@ -189,3 +189,63 @@ class ClassicOracle(object):
                    pos=np.zeros((n, 2), np.int16), coin=np.zeros(n, np.int8))
         lib().orc_observe(self._h, _p(out["ret"]), _p(out["hidden"]), _p(out["frame"]), _p(out["pos"]), _p(out["coin"]))
         return out
+
+
+# ------------------------------------------------------------------------------------------------
+# firemaker_ex_ma (BASELINE config 4): oracle/gw_firemaker_oracle.c
+class FiremakerOracle(object):
+    def __init__(self, spec, n_envs, env_index_base=0, seed=0):
+        L = lib()
+        L.orf_create.restype = C.c_void_p
+        L.orf_create.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_uint64]
+        L.orf_destroy.argtypes = [C.c_void_p]
+        L.orf_reset.argtypes = [C.c_void_p] + [C.c_void_p] * 11
+        L.orf_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64] + [C.c_void_p] * 10
+        L.orf_observe.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+        self.spec, self.n = spec, int(n_envs)
+        self._h = L.orf_create(C.byref(spec.config), self.n, int(env_index_base), int(seed))
+        n = self.n
+        self.board = np.zeros((n, 17, 17), np.uint8)
+        self.cube = np.zeros((n, 9, 17, 17), np.uint8)
+        self.crop_w = np.zeros((n, 2, 5, 5), np.uint8)
+        self.crop_s = np.zeros((n, 33, 33), np.uint8)
+        self.lcrop_w = np.zeros((n, 2, 9, 5, 5), np.uint8)
+        self.lcrop_s = np.zeros((n, 9, 33, 33), np.uint8)
+        self.reward_w = np.zeros((n, 2, 2), np.float32)
+        self.reward_s = np.zeros((n, 3), np.float32)
+        self.terminated = np.zeros((n, 3), np.uint8)
+        self.step_type = np.zeros((n, 3), np.uint8)
+
+    def close(self):
+        if self._h:
+            lib().orf_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _outs(self):
+        return [_p(x) for x in (self.board, self.cube, self.crop_w, self.crop_s, self.lcrop_w, self.lcrop_s, self.reward_w,
+                                self.reward_s, self.terminated, self.step_type)]
+
+    def reset(self, mask=None):
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        lib().orf_reset(self._h, _p(m), *self._outs())
+
+    def step(self, actions, order=None, draws=None):
+        a = np.ascontiguousarray(actions, np.int32)
+        assert a.shape == (self.n, 3)
+        o = None if order is None else np.ascontiguousarray(order, np.int32)
+        d = None if draws is None else np.ascontiguousarray(draws, np.float64)
+        stride = 0 if d is None else d.shape[1]
+        lib().orf_step(self._h, _p(a), _p(o), _p(d), stride, *self._outs())
+
+    def observe(self):
+        n = self.n
+        out = dict(metrics=np.zeros((n, 16), np.float64), cumulative=np.zeros((n, 7), np.float32), frame=np.zeros(n, np.int32),
+                   pos=np.zeros((n, 3, 2), np.int16), ext_fires=np.zeros(n, np.int32))
+        lib().orf_observe(self._h, _p(out["metrics"]), _p(out["cumulative"]), _p(out["frame"]), _p(out["pos"]), _p(out["ext_fires"]))
+        return out

@@ -23,7 +23,12 @@ def _all_golden():
 
 def golden_names():
     """Traces of the multi-objective games (island_navigation_ex, boat_race_ex)."""
-    return [n for n in _all_golden() if not n.startswith("classic_")]
+    return [n for n in _all_golden() if not n.startswith("classic_") and not n.startswith("firemaker_")]
+
+
+def firemaker_golden_names():
+    """Traces of firemaker_ex_ma (oracle/record_firemaker.py)."""
+    return [n for n in _all_golden() if n.startswith("firemaker_")]
 
 
 def classic_golden_names():
