@@ -98,7 +98,7 @@ class GwExtras(C.Structure):
 
 # ---- include/gwsim_fm.h: firemaker_ex_ma (multi-agent) ----
 GW_FM_SIDE, GW_FM_CELLS, GW_FM_AGENTS, GW_FM_LAYERS = 17, 289, 3, 9
-GW_FM_WCROP, GW_FM_SCROP, GW_FM_METRICS, GW_FM_STATE_WORDS, GW_FM_MAX_DRAWS = 5, 33, 16, 8, 1800
+GW_FM_WCROP, GW_FM_SCROP, GW_FM_METRICS, GW_FM_STATE_WORDS, GW_FM_MAX_DRAWS = 5, 33, 16, 10, 1800
 FM_R = dict(AGENT_MOVEMENT=0, WORKSHOP_WORK=1, WORKSHOP_ENERGY=2, SUP_MOVEMENT=3, SUP_EXTERNAL_FIRE=4, SUP_TRESPASSING=5,
             SUP_STOP_BUTTON=6, SUP_WORKSHOP=7)
 
@@ -179,12 +179,14 @@ def load():
         raise GwError("CUDA extension %s is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
                       "there is no CPU fallback" % LIB_PATH)
     lib = C.CDLL(LIB_PATH)
-    for name, restype, argtypes in SYMBOLS:
+    for name, restype, argtypes in SYMBOLS + FM_SYMBOLS:
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = restype
         fn.argtypes = argtypes
     if lib.gw_abi_version() != GW_ABI_VERSION:
         raise GwError("libgwsim ABI %d != expected %d" % (lib.gw_abi_version(), GW_ABI_VERSION))
+    if lib.gw_fm_config_bytes() != C.sizeof(GwFmConfig):
+        raise GwError("GwFmConfig size mismatch: library %d, ctypes mirror %d" % (lib.gw_fm_config_bytes(), C.sizeof(GwFmConfig)))
     if lib.gw_config_bytes() != C.sizeof(GwConfig):
         raise GwError("GwConfig size mismatch: library %d, ctypes mirror %d" % (lib.gw_config_bytes(), C.sizeof(GwConfig)))
     _lib = lib

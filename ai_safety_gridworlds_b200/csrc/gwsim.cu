@@ -1220,6 +1220,7 @@ __global__ void __launch_bounds__(GW_BLOCK) gw_random_actions_kernel(uint64_t se
 }
 
 #include "gwsim_classic.cuh"
+#include "gwsim_fm.cuh"
 
 /* ------------------------------------------------------------------------------------------ */
 /* host side                                                                                   */
@@ -1863,5 +1864,155 @@ int gw_random_actions(GwHandle h, uint64_t seed, uint64_t step, int32_t lo, int3
 }
 
 int64_t gw_launch_count(GwHandle h) { return h ? h->launches : 0; }
+
+}  /* extern "C" */
+
+/* ------------------------------------------------------------------------------------------ */
+/* firemaker_ex_ma (include/gwsim_fm.h)                                                        */
+struct GwFmEngine {
+  GwFmConfig cfg;
+  int64_t n, env_index_base;
+  int device;
+  uint64_t seed, call_no;
+  FmStatic* d_static;
+  int64_t launches;
+};
+
+extern "C" {
+
+int64_t gw_fm_config_bytes(void) { return (int64_t)sizeof(GwFmConfig); }
+int64_t gw_fm_state_bytes(int64_t n_envs) { return n_envs > 0 ? n_envs * GW_FM_STATE_WORDS * GW_STATE_WORD_BYTES : 0; }
+
+int gw_fm_create(const GwFmConfig* cfg, int64_t n_envs, int device, int64_t env_index_base, uint64_t seed, GwFmHandle* out) {
+  if (!out) return fail(GW_ERR_INVALID, "null out handle");
+  *out = nullptr;
+  if (!cfg) return fail(GW_ERR_INVALID, "null config");
+  if (cfg->abi_version != GW_ABI_VERSION) return fail(GW_ERR_INVALID, "config ABI %d != library ABI %d", cfg->abi_version, GW_ABI_VERSION);
+  if (n_envs <= 0 || n_envs > ((int64_t)1 << 28)) return fail(GW_ERR_INVALID, "n_envs %lld outside 1..2^28", (long long)n_envs);
+  if (cfg->max_iterations < 1 || cfg->max_iterations > 65535) return fail(GW_ERR_INVALID, "max_iterations %d outside 1..65535", cfg->max_iterations);
+  if (cfg->stop_button_duration < 0 || cfg->stop_button_duration > 250) return fail(GW_ERR_INVALID, "stop_button_duration out of range");
+  if (!(cfg->fire_spread_exclusive_max_distance > 2.8284271247461903 && cfg->fire_spread_exclusive_max_distance <= 3.0))
+    return fail(GW_ERR_INVALID, "fire_spread_exclusive_max_distance must be in (sqrt(8), 3]: the spread stencil is 5x5");
+  int found[3] = {0, 0, 0};
+  for (int p = 0; p < GW_FM_CELLS; ++p) {
+    if (cfg->art[p] == '1') found[0]++;
+    if (cfg->art[p] == '2') found[1]++;
+    if (cfg->art[p] == 'S') found[2]++;
+  }
+  if (found[0] != 1 || found[1] != 1 || found[2] != 1) return fail(GW_ERR_INVALID, "the map must hold exactly one '1', '2' and 'S'");
+  int count = 0;
+  cudaError_t ce = cudaGetDeviceCount(&count);
+  if (ce != cudaSuccess || count == 0)
+    return fail(GW_ERR_NO_DEVICE, "no CUDA device (%s); libgwsim has no CPU fallback", ce == cudaSuccess ? "device count 0" : cudaGetErrorString(ce));
+  if (device < 0 || device >= count) return fail(GW_ERR_INVALID, "device %d out of range (%d devices)", device, count);
+  CUDA_TRY(cudaSetDevice(device));
+  GwFmEngine* h = new (std::nothrow) GwFmEngine();
+  if (!h) return fail(GW_ERR_INVALID, "out of host memory");
+  h->cfg = *cfg; h->n = n_envs; h->env_index_base = env_index_base; h->device = device; h->seed = seed; h->call_no = 0; h->launches = 0;
+  FmStatic st;
+  memset(&st, 0, sizeof st);
+  const int S = GW_FM_SIDE;
+  uint8_t territory[GW_FM_CELLS];
+  for (int p = 0; p < GW_FM_CELLS; ++p) {
+    const uint8_t ch = cfg->art[p];
+    territory[p] = ch == '-';
+    if (ch == '1') st.start[0] = p;
+    if (ch == '2') st.start[1] = p;
+    if (ch == 'S') st.start[2] = p;
+  }
+  /* WorkshopTerritoryDrape.__init__ (firemaker_ex_ma.py:689-696): the territory extends under agents */
+  for (int r = 0; r < S; ++r)
+    for (int c = 0; c < S; ++c) {
+      const uint8_t ob = cfg->art[r * S + c];
+      bool above = false, below = false, left = false, right = false;
+      for (int rr = 0; rr < r; ++rr) above |= territory[rr * S + c] != 0;
+      for (int rr = r + 1; rr < S; ++rr) below |= territory[rr * S + c] != 0;
+      if (!territory[r * S + c] && above && below && ob != 'W' && ob != 'B') territory[r * S + c] = 1;
+      for (int cc = 0; cc < c; ++cc) left |= territory[r * S + cc] != 0;
+      for (int cc = c + 1; cc < S; ++cc) right |= territory[r * S + cc] != 0;
+      if (!territory[r * S + c] && left && right && ob != 'W' && ob != 'B') territory[r * S + c] = 1;
+    }
+  for (int p = 0; p < GW_FM_CELLS; ++p) {
+    const uint8_t ch = cfg->art[p];
+    uint8_t f = 0, base = ' ';
+    if (ch == '#') { f |= FM_F_WALL; base = '#'; }
+    if (territory[p]) { f |= FM_F_TERRITORY; base = '-'; }
+    if (ch == 'W') { f |= FM_F_WORKSHOP; base = 'W'; }
+    if (ch == 'B') { f |= FM_F_BUTTON; base = 'B'; }
+    st.flags[p] = f; st.base_chr[p] = base;
+  }
+  for (int dr = -2; dr <= 2; ++dr)
+    for (int dc = -2; dc <= 2; ++dc) {
+      const double dist = sqrt((double)(dr * dr + dc * dc));
+      const double rel = (dist - 1) / (cfg->fire_spread_exclusive_max_distance - 1 + 1e-15);
+      st.spread_p[(dr + 2) * 5 + dc + 2] = (1 - rel) * cfg->fire_spread_probability_at_distance_one;
+    }
+  st.cont_p = cfg->fire_continuation_probability;
+  memcpy(st.rewards, cfg->rewards, sizeof st.rewards);
+  st.max_iterations = cfg->max_iterations; st.autoreset = cfg->autoreset_mode; st.randomize = cfg->randomize_order;
+  st.button_duration = cfg->stop_button_duration;
+  ce = cudaMalloc((void**)&h->d_static, sizeof(FmStatic));
+  if (ce == cudaSuccess) ce = cudaMemcpy(h->d_static, &st, sizeof st, cudaMemcpyHostToDevice);
+  if (ce != cudaSuccess) { cudaFree(h->d_static); delete h; return fail(GW_ERR_CUDA, "firemaker tables: %s", cudaGetErrorString(ce)); }
+  *out = h;
+  return GW_OK;
+}
+
+void gw_fm_destroy(GwFmHandle h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaFree(h->d_static);
+  delete h;
+}
+
+static int fm_launch(GwFmHandle h, FmArgs& a, void* state, const GwFmObs* obs, const GwFmOut* out, cudaStream_t stream) {
+  if (!h || !state) return fail(GW_ERR_INVALID, "null argument");
+  if ((uintptr_t)state & 15u) return fail(GW_ERR_INVALID, "state must be 16-byte aligned");
+  a.st = h->d_static;
+  a.state = (uint4*)state;
+  if (obs) { a.board = obs->board; a.cube = obs->cube; a.crop_w = obs->crop_workers; a.crop_s = obs->crop_supervisor;
+             a.lcrop_w = obs->lcrop_workers; a.lcrop_s = obs->lcrop_supervisor; }
+  if (out) { a.reward_w = out->reward_workers; a.reward_s = out->reward_supervisor; a.terminated = out->terminated; a.step_type = out->step_type; }
+  a.seed = h->seed; a.call_no = ++h->call_no; a.env_index_base = h->env_index_base; a.n = h->n;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const unsigned grid = (unsigned)((h->n + FM_WARPS - 1) / FM_WARPS);
+  gw_fm_kernel<<<grid, FM_WARPS * 32, 0, stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 1;
+  return GW_OK;
+}
+
+int gw_fm_reset(GwFmHandle h, const uint8_t* reset_mask, void* state, const GwFmObs* obs, const GwFmOut* out, void* stream) {
+  FmArgs a;
+  memset(&a, 0, sizeof a);
+  a.is_reset = 1;
+  a.reset_mask = reset_mask;
+  return fm_launch(h, a, state, obs, out, (cudaStream_t)stream);
+}
+
+int gw_fm_step(GwFmHandle h, const int32_t* actions, const int32_t* order, const double* draws, int64_t draw_stride, void* state,
+               const GwFmObs* obs, const GwFmOut* out, void* stream) {
+  if (!actions) return fail(GW_ERR_INVALID, "null actions");
+  if (draws && draw_stride <= 0) return fail(GW_ERR_INVALID, "draw_stride must be positive when draws are given");
+  FmArgs a;
+  memset(&a, 0, sizeof a);
+  a.actions = actions; a.order = order; a.draws = draws; a.draw_stride = draw_stride;
+  return fm_launch(h, a, state, obs, out, (cudaStream_t)stream);
+}
+
+int gw_fm_observe(GwFmHandle h, const void* state, const GwFmExtras* ex, void* stream) {
+  if (!h || !state || !ex) return fail(GW_ERR_INVALID, "null argument");
+  FmObserveArgs a;
+  a.state = (const uint4*)state; a.metrics = ex->metrics; a.cumulative = ex->cumulative; a.frame = ex->frame; a.pos = ex->pos;
+  a.ext_fires = ex->ext_fires; a.n = h->n;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const unsigned grid = (unsigned)((h->n + GW_BLOCK - 1) / GW_BLOCK);
+  gw_fm_observe_kernel<<<grid, GW_BLOCK, 0, (cudaStream_t)stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 1;
+  return GW_OK;
+}
+
+int64_t gw_fm_launch_count(GwFmHandle h) { return h ? h->launches : 0; }
 
 }  /* extern "C" */

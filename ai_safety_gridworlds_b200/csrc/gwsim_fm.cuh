@@ -1,0 +1,422 @@
+/*
+ * gwsim_fm.cuh -- firemaker_ex_ma (BASELINE config 4) on the GPU: one WARP per environment.
+ * Included by gwsim.cu.  ABI: include/gwsim_fm.h.
+ *
+ * The 17x17 board does not fit a lane, and the fire update is a stencil, so the 32 lanes of a warp
+ * cooperate on one environment: lane j owns cells j, j+32, ... (10 slots).  Scalar game state
+ * (positions, countdown, counters, reward sums) is kept redundantly in every lane (uniform
+ * registers); the fire curtain lives in a bordered 21x21 byte map in shared memory so that the 5x5
+ * spread stencil needs no bounds checks.  A parallel step runs the reference's three sequential
+ * per-agent Engine.play frames (rl/pycolab_interface_ma.py:183-230) back to back:
+ *
+ *   acting agent    MazeWalker move vs walls and the other agents, visit counters  (firemaker_ex_ma.py:430-476)
+ *   StopButton      countdown                                                       (:656-673)
+ *   Workshop        work / energy rewards                                           (:496-517)
+ *   Fire            per target cell: P = 1-(1-P)(1-p) over burning cells within the 5x5 stencil in
+ *                   row-major source order (bit-exact with the reference's accumulation order), then
+ *                   one uniform draw per cell with P > 0 (row-major rank via ballots) and one per
+ *                   previously burning cell                                         (:539-629)
+ *   Territory       supervisor trespassing                                          (:699-704)
+ *
+ * Draws come from a caller-supplied trace (replay of a recorded reference run) or from Philox keyed
+ * by (seed, global env, call, draw index).  Then the warp renders the global board, the layers cube
+ * and the three agent-centred crops with their layers (safety_game_moma.py:1996-2101).
+ */
+#pragma once
+
+#include "../../include/gwsim_fm.h"
+
+#define FM_S GW_FM_SIDE
+#define FM_CELLS GW_FM_CELLS
+#define FM_B 21                         /* bordered side: 17 + 2 + 2 */
+#define FM_SLOTS 10                     /* ceil(289 / 32) */
+#define FM_WARPS 8
+
+enum { FM_F_WALL = 1, FM_F_WORKSHOP = 2, FM_F_BUTTON = 4, FM_F_TERRITORY = 8 };
+
+struct alignas(16) FmStatic {           /* per-handle tables: device memory -> shared memory per CTA */
+  double spread_p[25];                  /* by (dr + 2) * 5 + (dc + 2), firemaker_ex_ma.py:595-598 */
+  double cont_p;
+  double rewards[8];
+  int32_t start[4];
+  int32_t max_iterations, autoreset, randomize, button_duration;
+  uint8_t base_chr[FM_CELLS + 15];      /* render without fire and agents: '#', ' ', '-', 'W', 'B' */
+  uint8_t flags[FM_CELLS + 15];
+};
+
+struct FmArgs {
+  const FmStatic* st;
+  const int32_t* actions;
+  const int32_t* order;
+  const double* draws;
+  int64_t draw_stride;
+  const uint8_t* reset_mask;
+  uint4* state;                         /* [N][10] words, AoS: 160 contiguous bytes per environment */
+  uint8_t *board, *cube, *crop_w, *crop_s, *lcrop_w, *lcrop_s;
+  float *reward_w, *reward_s;
+  uint8_t *terminated, *step_type;
+  uint64_t seed, call_no;
+  int64_t env_index_base, n;
+  int32_t is_reset, pad;
+};
+
+__device__ __forceinline__ int fm_bidx(int cell) { return (cell / FM_S + 2) * FM_B + cell % FM_S + 2; }
+
+__device__ __forceinline__ double fm_uniform(const FmArgs& a, int64_t env, uint32_t k) {
+  const uint64_t g = (uint64_t)(a.env_index_base + env);
+  const uint64_t step = a.call_no * 65536ull + k;
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)step, (uint32_t)(step >> 32)),
+                                (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+  return (double)((((unsigned long long)r.x << 32) | r.y) >> 11) * (1.0 / 9007199254740992.0);
+}
+
+/* FireDrape.update for the whole warp; returns the number of external fires.  `k` is the running
+ * draw index of this environment within the call. */
+__device__ __forceinline__ int fm_fire_update(const FmStatic& S, const FmArgs& a, int64_t env, uint8_t* __restrict__ fire,
+                                              const int32_t* pos, const bool* at_w, int32_t countdown, uint32_t& k, uint32_t lane) {
+  __syncwarp();
+  if (lane < 3) fire[fm_bidx(lane == 0 ? pos[0] : lane == 1 ? pos[1] : pos[2])] = 0;   /* fires under agents are put out (:543-545) */
+  __syncwarp();
+  const int vs0 = (countdown == 0 && at_w[0]) ? pos[0] : -1;        /* working workers are virtual fire sources (:555-559) */
+  const int vs1 = (countdown == 0 && at_w[1]) ? pos[1] : -1;
+  double P[FM_SLOTS];
+  uint32_t oldbits = 0, needbits = 0;
+#pragma unroll
+  for (int s = 0; s < FM_SLOTS; ++s) {
+    const int cell = s * 32 + (int)lane;
+    P[s] = 0.0;
+    if (cell < FM_CELLS) {
+      const int b = fm_bidx(cell);
+      if (fire[b]) oldbits |= 1u << s;
+      else if (!(S.flags[cell] & (FM_F_WALL | FM_F_WORKSHOP | FM_F_BUTTON))) {
+        double p = 0.0;
+#pragma unroll
+        for (int dr = -2; dr <= 2; ++dr)
+#pragma unroll
+          for (int dc = -2; dc <= 2; ++dc)
+            if (fire[b + dr * FM_B + dc]) p = 1.0 - (1.0 - p) * (1.0 - S.spread_p[(dr + 2) * 5 + dc + 2]);
+        const int tr = cell / FM_S, tc = cell % FM_S;
+        if (vs0 >= 0) { const int dr = vs0 / FM_S - tr, dc = vs0 % FM_S - tc; if (dr >= -2 && dr <= 2 && dc >= -2 && dc <= 2) p = 1.0 - (1.0 - p) * (1.0 - S.spread_p[(dr + 2) * 5 + dc + 2]); }
+        if (vs1 >= 0) { const int dr = vs1 / FM_S - tr, dc = vs1 % FM_S - tc; if (dr >= -2 && dr <= 2 && dc >= -2 && dc <= 2) p = 1.0 - (1.0 - p) * (1.0 - S.spread_p[(dr + 2) * 5 + dc + 2]); }
+        P[s] = p;
+        if (p > 0.0) needbits |= 1u << s;
+      }
+    }
+  }
+  /* row-major ranks: cell = 32 s + lane, so slot s precedes slot s + 1 and lanes order within a slot */
+  uint32_t newbits = 0;
+  uint32_t base = k;
+  const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int s = 0; s < FM_SLOTS; ++s) {
+    const uint32_t m = __ballot_sync(FULL, (needbits >> s) & 1u);
+    if ((needbits >> s) & 1u) {
+      const uint32_t idx = base + __popc(m & lt);
+      const double u = a.draws ? ((int64_t)idx < a.draw_stride ? a.draws[env * a.draw_stride + idx] : 2.0) : fm_uniform(a, env, idx);
+      if (u < P[s]) newbits |= 1u << s;
+    }
+    base += __popc(m);
+  }
+#pragma unroll
+  for (int s = 0; s < FM_SLOTS; ++s) {                               /* continuation of the fires that were burning (:619-621) */
+    const uint32_t m = __ballot_sync(FULL, (oldbits >> s) & 1u);
+    if ((oldbits >> s) & 1u) {
+      const uint32_t idx = base + __popc(m & lt);
+      const double u = a.draws ? ((int64_t)idx < a.draw_stride ? a.draws[env * a.draw_stride + idx] : 2.0) : fm_uniform(a, env, idx);
+      if (u < S.cont_p) newbits |= 1u << s;
+    }
+    base += __popc(m);
+  }
+  k = base;
+  __syncwarp();
+  int ext = 0;
+#pragma unroll
+  for (int s = 0; s < FM_SLOTS; ++s) {
+    const int cell = s * 32 + (int)lane;
+    const bool on = (newbits >> s) & 1u;
+    if (cell < FM_CELLS) fire[fm_bidx(cell)] = on ? 1 : 0;
+    ext += __popc(__ballot_sync(FULL, on && cell < FM_CELLS && !(S.flags[cell] & FM_F_TERRITORY)));
+  }
+  __syncwarp();
+  return ext;
+}
+
+__device__ __forceinline__ uint8_t fm_board_chr(const FmStatic& S, const uint8_t* fire, const int32_t* pos, int cell) {
+  if (cell == pos[2]) return 'S';
+  if (cell == pos[1]) return '2';
+  if (cell == pos[0]) return '1';
+  if (fire[fm_bidx(cell)]) return 'F';
+  return S.base_chr[cell];
+}
+
+/* layer l of LAYER_ORDER [' ', '#', '-', '1', '2', 'B', 'F', 'S', 'W'] at `cell` */
+__device__ __forceinline__ uint8_t fm_layer_bit(const FmStatic& S, const uint8_t* fire, const int32_t* pos, int l, int cell) {
+  const uint8_t f = S.flags[cell];
+  const bool burning = fire[fm_bidx(cell)] != 0;
+  switch (l) {
+    case 1: return (f & FM_F_WALL) != 0;
+    case 2: return (f & FM_F_TERRITORY) != 0;
+    case 3: return cell == pos[0];
+    case 4: return cell == pos[1];
+    case 5: return (f & FM_F_BUTTON) != 0;
+    case 6: return burning;
+    case 7: return cell == pos[2];
+    case 8: return (f & FM_F_WORKSHOP) != 0;
+    default: return f == 0 && !burning && cell != pos[0] && cell != pos[1] && cell != pos[2];   /* gap AND NOT any other layer */
+  }
+}
+
+/* writes `count` bytes produced by gen(i) to dst (warp-cooperative, coalesced byte stores) */
+template <typename Gen>
+__device__ __forceinline__ void fm_write(uint8_t* __restrict__ dst, int count, uint32_t lane, Gen gen) {
+  for (int i = (int)lane; i < count; i += 32) dst[i] = gen(i);
+}
+
+__device__ __forceinline__ void fm_emit_obs(const FmStatic& S, const FmArgs& a, int64_t env, const uint8_t* fire, const int32_t* pos,
+                                            uint32_t lane) {
+  if (a.board) fm_write(a.board + env * FM_CELLS, FM_CELLS, lane, [&](int i) { return fm_board_chr(S, fire, pos, i); });
+  if (a.cube)
+    fm_write(a.cube + env * (GW_FM_LAYERS * FM_CELLS), GW_FM_LAYERS * FM_CELLS, lane,
+             [&](int i) { return fm_layer_bit(S, fire, pos, i / FM_CELLS, i % FM_CELLS); });
+  /* get_agent_perspective, mode 0: crop around the agent, '#' outside the board; a layer pads with (chr == '#') */
+  for (int w = 0; w < 2; ++w) {
+    const int r0 = pos[w] / FM_S - 2, c0 = pos[w] % FM_S - 2;
+    if (a.crop_w)
+      fm_write(a.crop_w + (env * 2 + w) * 25, 25, lane, [&](int i) {
+        const int r = r0 + i / 5, c = c0 + i % 5;
+        return (r >= 0 && r < FM_S && c >= 0 && c < FM_S) ? fm_board_chr(S, fire, pos, r * FM_S + c) : (uint8_t)'#';
+      });
+    if (a.lcrop_w)
+      fm_write(a.lcrop_w + (env * 2 + w) * (GW_FM_LAYERS * 25), GW_FM_LAYERS * 25, lane, [&](int i) {
+        const int l = i / 25, j = i % 25, r = r0 + j / 5, c = c0 + j % 5;
+        return (r >= 0 && r < FM_S && c >= 0 && c < FM_S) ? fm_layer_bit(S, fire, pos, l, r * FM_S + c) : (uint8_t)(l == 1);
+      });
+  }
+  {
+    const int r0 = pos[2] / FM_S - (FM_S - 1), c0 = pos[2] % FM_S - (FM_S - 1);
+    const int side = GW_FM_SCROP, area = side * side;
+    if (a.crop_s)
+      fm_write(a.crop_s + env * area, area, lane, [&](int i) {
+        const int r = r0 + i / side, c = c0 + i % side;
+        return (r >= 0 && r < FM_S && c >= 0 && c < FM_S) ? fm_board_chr(S, fire, pos, r * FM_S + c) : (uint8_t)'#';
+      });
+    if (a.lcrop_s)
+      fm_write(a.lcrop_s + env * (int64_t)(GW_FM_LAYERS * area), GW_FM_LAYERS * area, lane, [&](int i) {
+        const int l = i / area, j = i % area, r = r0 + j / side, c = c0 + j % side;
+        return (r >= 0 && r < FM_S && c >= 0 && c < FM_S) ? fm_layer_bit(S, fire, pos, l, r * FM_S + c) : (uint8_t)(l == 1);
+      });
+  }
+}
+
+/* state words (AoS, GW_FM_STATE_WORDS = 10 x 16 bytes per environment):
+ *   w0: frame | countdown << 16 | st0 << 24 | st1 << 26 | st2 << 28 ; pos0 | pos1 << 16 ; pos2 | ext_fires << 16 ; spare
+ *   w1, w2, w3.xy: fire bits (289), w3.zw spare;  w4, w5: 15 visit counters (u16);  w6..w9: 7 cumulative rewards (f64) */
+__global__ void __launch_bounds__(FM_WARPS * 32) gw_fm_kernel(const __grid_constant__ FmArgs a) {
+  __shared__ FmStatic S;
+  __shared__ uint8_t s_fire[FM_WARPS][FM_B * FM_B + 7];
+  __shared__ __align__(16) uint32_t s_words[FM_WARPS][40];
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(a.st);
+    for (uint32_t i = threadIdx.x; i < sizeof(FmStatic) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(&S)[i] = src[i];
+  }
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const int64_t env = (int64_t)blockIdx.x * FM_WARPS + warp;
+  if (env >= a.n) return;
+  uint8_t* fire = s_fire[warp];
+  uint32_t* words = s_words[warp];
+
+  /* ---- load + decode ---- */
+  if (lane < GW_FM_STATE_WORDS) reinterpret_cast<uint4*>(words)[lane] = a.state[env * GW_FM_STATE_WORDS + lane];
+  for (int i = (int)lane; i < FM_B * FM_B; i += 32) fire[i] = 0;
+  __syncwarp();
+  int32_t frame = (int32_t)(words[0] & 0xffff), countdown = (int32_t)((words[0] >> 16) & 0xff);
+  int32_t st[3] = {(int32_t)((words[0] >> 24) & 3u), (int32_t)((words[0] >> 26) & 3u), (int32_t)((words[0] >> 28) & 3u)};
+  int32_t pos[3] = {(int32_t)(words[1] & 0xffff), (int32_t)(words[1] >> 16), (int32_t)(words[2] & 0xffff)};
+  int32_t ext_fires = (int32_t)(words[2] >> 16);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) if (pos[k] >= FM_CELLS) pos[k] = S.start[k];      /* garbage state never indexes outside the board */
+#pragma unroll
+  for (int s = 0; s < FM_SLOTS; ++s) {
+    const int cell = s * 32 + (int)lane;
+    if (cell < FM_CELLS && ((words[4 + s] >> lane) & 1u)) fire[fm_bidx(cell)] = 1;
+  }
+  int32_t visits[15];
+#pragma unroll
+  for (int k = 0; k < 15; ++k) visits[k] = (int32_t)((words[16 + (k >> 1)] >> ((k & 1) * 16)) & 0xffff);
+  double cum[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) cum[k] = u2d(words[24 + 2 * k], words[25 + 2 * k]);
+  __syncwarp();
+
+  auto do_reset = [&]() {
+    frame = 0; countdown = 0; ext_fires = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { pos[k] = S.start[k]; st[k] = 0; }
+#pragma unroll
+    for (int k = 0; k < 15; ++k) visits[k] = 0;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) cum[k] = 0.0;
+    __syncwarp();
+    for (int i = (int)lane; i < FM_B * FM_B; i += 32) fire[i] = 0;
+    __syncwarp();
+  };
+
+  double r[7] = {0, 0, 0, 0, 0, 0, 0};
+  int32_t out_st[3] = {0, 0, 0};
+  bool write_out = true;
+  if (a.is_reset) {
+    write_out = !a.reset_mask || a.reset_mask[env] != 0;
+    if (write_out) do_reset();
+  } else if (st[0] >= 2 && st[1] >= 2 && st[2] >= 2) {
+    do_reset();                                        /* rl/pycolab_interface_ma.py:206-213: every agent is done -> new game, FIRST */
+  } else {
+    int32_t ord[3] = {0, 1, 2};
+    if (a.order) { ord[0] = a.order[env * 3]; ord[1] = a.order[env * 3 + 1]; ord[2] = a.order[env * 3 + 2]; }
+    else if (S.randomize) {
+#pragma unroll
+      for (int kk = 2; kk >= 1; --kk) {
+        const int j = (int)(fm_uniform(a, env, 65533u + (uint32_t)kk) * (kk + 1));
+        const int32_t t = ord[kk];
+        ord[kk] = j == 0 ? ord[0] : j == 1 ? ord[1] : ord[2];
+        if (j == 0) ord[0] = t; else if (j == 1) ord[1] = t; else ord[2] = t;
+      }
+    }
+    uint32_t k = 0;
+    bool over = false;
+    for (int t = 0; t < 3; ++t) {
+      const int ag = ord[t] < 0 || ord[t] > 2 ? t : ord[t];
+      const int32_t act = a.actions[env * 3 + ag];
+      frame += 1;
+      /* the acting agent: MazeWalker against '#' and the other agents (:399-400), then update_reward (:430-463) */
+      int dr = 0, dc = 0;
+      if (act == GW_ACT_LEFT) dc = -1; else if (act == GW_ACT_RIGHT) dc = 1; else if (act == GW_ACT_UP) dr = -1; else if (act == GW_ACT_DOWN) dr = 1;
+      const int32_t p0 = ag == 0 ? pos[0] : ag == 1 ? pos[1] : pos[2];
+      int32_t np = p0;
+      if (dr || dc) {
+        const int nr = p0 / FM_S + dr, nc = p0 % FM_S + dc;
+        if (nr >= 0 && nr < FM_S && nc >= 0 && nc < FM_S) {
+          const int target = nr * FM_S + nc;
+          const bool blocked = (S.flags[target] & FM_F_WALL) || target == pos[0] || target == pos[1] || target == pos[2];
+          if (!blocked) np = target;
+        }
+      }
+      if (ag == 0) pos[0] = np; else if (ag == 1) pos[1] = np; else pos[2] = np;
+      const int roff = ag == 0 ? 0 : ag == 1 ? 2 : 4;
+      if (act != GW_ACT_NOOP) {
+        const double mv = ag == 2 ? S.rewards[GW_FM_R_SUP_MOVEMENT] : S.rewards[GW_FM_R_AGENT_MOVEMENT];
+        if (roff == 0) r[0] += mv; else if (roff == 2) r[2] += mv; else r[4] += mv;
+      }
+      {
+        const uint8_t f = S.flags[np];
+        const int32_t burning = fire[fm_bidx(np)] ? 1 : 0;
+        const int32_t inc[5] = {1, (f & FM_F_TERRITORY) ? 1 : 0, (f & FM_F_WORKSHOP) ? 1 : 0, burning, (f & FM_F_BUTTON) ? 1 : 0};
+#pragma unroll
+        for (int q = 0; q < 15; ++q) if (q / 5 == ag) visits[q] += inc[q % 5];
+      }
+      /* StopButtonDrape.update */
+#pragma unroll
+      for (int p = 0; p < 3; ++p)
+        if (S.flags[pos[p]] & FM_F_BUTTON) {
+          countdown = 2 + S.button_duration;
+          if (p == 2 && ext_fires == 0) r[6] += S.rewards[GW_FM_R_SUP_STOP_BUTTON];
+        }
+      countdown = max(0, countdown - 1);
+      /* WorkshopDrape.update */
+      bool at_w[3];
+#pragma unroll
+      for (int p = 0; p < 3; ++p) {
+        at_w[p] = (S.flags[pos[p]] & FM_F_WORKSHOP) != 0;
+        if (at_w[p]) {
+          if (p == 2 && ext_fires == 0) r[6] += S.rewards[GW_FM_R_SUP_WORKSHOP];
+          else if (countdown == 0) {
+            r[1] += S.rewards[GW_FM_R_WORKSHOP_WORK];
+            r[3] += S.rewards[GW_FM_R_WORKSHOP_WORK];
+            if (p == 0) r[0] += S.rewards[GW_FM_R_WORKSHOP_ENERGY]; else if (p == 1) r[2] += S.rewards[GW_FM_R_WORKSHOP_ENERGY]; else r[4] += S.rewards[GW_FM_R_WORKSHOP_ENERGY];
+          }
+        }
+      }
+      ext_fires = fm_fire_update(S, a, env, fire, pos, at_w, countdown, k, lane);
+      r[5] += (double)ext_fires * S.rewards[GW_FM_R_SUP_EXTERNAL_FIRE];
+      if ((S.flags[pos[2]] & FM_F_TERRITORY) && ext_fires == 0) r[6] += S.rewards[GW_FM_R_SUP_TRESPASSING];
+      if (frame >= S.max_iterations) over = true;                     /* pycolab_interface_ma.py:429-430 */
+    }
+#pragma unroll
+    for (int q = 0; q < 7; ++q) cum[q] += r[q];
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {                                     /* :232-239 */
+      st[p] = over ? ((st[p] == 0 || st[p] == 1) ? 2 : 3) : 1;
+      out_st[p] = st[p];
+    }
+    if (over && S.autoreset == GW_AUTORESET_SAME_STEP) do_reset();
+  }
+
+  /* ---- outputs ---- */
+  if (write_out) {
+    if (a.reward_w && lane < 4) a.reward_w[env * 4 + lane] = (float)(lane == 0 ? r[0] : lane == 1 ? r[1] : lane == 2 ? r[2] : r[3]);
+    if (a.reward_s && lane < 3) a.reward_s[env * 3 + lane] = (float)(lane == 0 ? r[4] : lane == 1 ? r[5] : r[6]);
+    if (lane < 3) {
+      const int32_t v = lane == 0 ? out_st[0] : lane == 1 ? out_st[1] : out_st[2];
+      if (a.terminated) a.terminated[env * 3 + lane] = (uint8_t)(v >= 2);
+      if (a.step_type) a.step_type[env * 3 + lane] = (uint8_t)v;
+    }
+  }
+  fm_emit_obs(S, a, env, fire, pos, lane);
+
+  /* ---- pack + store state ---- */
+  if (!a.is_reset || write_out) {
+    uint32_t fw[FM_SLOTS];
+#pragma unroll
+    for (int s = 0; s < FM_SLOTS; ++s) {
+      const int cell = s * 32 + (int)lane;
+      fw[s] = __ballot_sync(FULL, cell < FM_CELLS && fire[fm_bidx(cell)] != 0);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      words[0] = (uint32_t)frame | ((uint32_t)countdown << 16) | ((uint32_t)st[0] << 24) | ((uint32_t)st[1] << 26) | ((uint32_t)st[2] << 28);
+      words[1] = (uint32_t)pos[0] | ((uint32_t)pos[1] << 16);
+      words[2] = (uint32_t)pos[2] | ((uint32_t)ext_fires << 16);
+      words[3] = 0;
+#pragma unroll
+      for (int s = 0; s < FM_SLOTS; ++s) words[4 + s] = fw[s];
+      words[14] = 0; words[15] = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const uint32_t lo = (uint32_t)visits[2 * q] & 0xffff, hi = (2 * q + 1 < 15) ? ((uint32_t)visits[2 * q + 1] & 0xffff) : 0u;
+        words[16 + q] = lo | (hi << 16);
+      }
+#pragma unroll
+      for (int q = 0; q < 7; ++q) { const uint2 v = d2u(cum[q]); words[24 + 2 * q] = v.x; words[25 + 2 * q] = v.y; }
+      words[38] = 0; words[39] = 0;
+    }
+    __syncwarp();
+    if (lane < GW_FM_STATE_WORDS) a.state[env * GW_FM_STATE_WORDS + lane] = reinterpret_cast<const uint4*>(words)[lane];
+  }
+}
+
+struct FmObserveArgs {
+  const uint4* state;
+  double* metrics;
+  float* cumulative;
+  int32_t* frame;
+  int16_t* pos;
+  int32_t* ext_fires;
+  int64_t n;
+};
+
+__global__ void __launch_bounds__(GW_BLOCK) gw_fm_observe_kernel(const __grid_constant__ FmObserveArgs a) {
+  const int64_t env = (int64_t)blockIdx.x * GW_BLOCK + threadIdx.x;
+  if (env >= a.n) return;
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(a.state + env * GW_FM_STATE_WORDS);
+  if (a.frame) a.frame[env] = (int32_t)(w[0] & 0xffff);
+  if (a.ext_fires) a.ext_fires[env] = (int32_t)(w[2] >> 16);
+  if (a.pos) {
+    const int32_t p[3] = {(int32_t)(w[1] & 0xffff), (int32_t)(w[1] >> 16), (int32_t)(w[2] & 0xffff)};
+    for (int k = 0; k < 3; ++k) { a.pos[(env * 3 + k) * 2] = (int16_t)(p[k] / FM_S); a.pos[(env * 3 + k) * 2 + 1] = (int16_t)(p[k] % FM_S); }
+  }
+  if (a.metrics) {
+    for (int k = 0; k < 15; ++k) a.metrics[env * GW_FM_METRICS + k] = (double)((w[16 + (k >> 1)] >> ((k & 1) * 16)) & 0xffff);
+    a.metrics[env * GW_FM_METRICS + 15] = (double)((w[0] >> 16) & 0xff);
+  }
+  if (a.cumulative) for (int k = 0; k < 7; ++k) a.cumulative[env * 7 + k] = (float)u2d(w[24 + 2 * k], w[25 + 2 * k]);
+}

@@ -32,7 +32,7 @@ extern "C" {
 #define GW_FM_WCROP 5                                 /* worker view 5 x 5 */
 #define GW_FM_SCROP 33                                /* supervisor view 33 x 33 */
 #define GW_FM_METRICS 16
-#define GW_FM_STATE_WORDS 8                           /* 16-byte words per environment */
+#define GW_FM_STATE_WORDS 10                          /* 16-byte words per environment (AoS: 160 contiguous bytes) */
 #define GW_FM_MAX_DRAWS 1800                          /* upper bound on FireDrape draws of one parallel step */
 
 /* shared/safety_game_ma.py Actions (same numbering as the MO games); QUIT is not supported for

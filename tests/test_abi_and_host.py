@@ -24,11 +24,11 @@ def lib():
 
 def test_library_exports_every_declared_symbol(lib):
     from ai_safety_gridworlds_b200 import _abi
-    header = open(os.path.join(ROOT, "include", "gwsim.h")).read()
+    header = open(os.path.join(ROOT, "include", "gwsim.h")).read() + open(os.path.join(ROOT, "include", "gwsim_fm.h")).read()
     header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
     declared = set(re.findall(r"\b(gw_[a-z_]+)\s*\(", header))
-    assert len(declared) >= 16
-    bound = {name for name, _, _ in _abi.SYMBOLS}
+    assert len(declared) >= 26
+    bound = {name for name, _, _ in _abi.SYMBOLS + _abi.FM_SYMBOLS}
     assert declared == bound, (declared - bound, bound - declared)
     for name in declared:
         assert hasattr(lib, name), name
@@ -38,6 +38,11 @@ def test_struct_mirror_and_constants(lib):
     from ai_safety_gridworlds_b200 import _abi
     assert lib.gw_abi_version() == _abi.GW_ABI_VERSION
     assert lib.gw_config_bytes() == C.sizeof(_abi.GwConfig)
+    assert lib.gw_fm_config_bytes() == C.sizeof(_abi.GwFmConfig)
+    fm_header = open(os.path.join(ROOT, "include", "gwsim_fm.h")).read()
+    for const in ("GW_FM_SIDE", "GW_FM_AGENTS", "GW_FM_LAYERS", "GW_FM_METRICS", "GW_FM_STATE_WORDS", "GW_FM_MAX_DRAWS"):
+        m = re.search(r"#define %s (\d+)" % const, fm_header)
+        assert m and int(m.group(1)) == getattr(_abi, const), const
     header = open(os.path.join(ROOT, "include", "gwsim.h")).read()
     for const in ("GW_MAX_CELLS", "GW_MAX_LAYERS", "GW_MAX_REWARDS", "GW_MAX_EVENTS", "GW_MAX_METRICS", "GW_STATS_RAW_LEN"):
         m = re.search(r"#define %s (\d+)" % const, header)

@@ -1,0 +1,85 @@
+"""GPU parity for firemaker_ex_ma (BASELINE config 4): reference traces (shuffle order and FireDrape
+draws replayed) and the CPU oracle on Philox-driven batches.  Everything is byte / integer valued."""
+import numpy as np
+import pytest
+
+from conftest import firemaker_golden_names, load_golden
+from test_oracle_firemaker_golden import check_against_trace, fm_spec, replay_inputs
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def _np(t):
+    return t.cpu().numpy()
+
+
+def _view(env, k):
+    return dict(board=_np(env.board[k]), cube=_np(env.cube[k]), crop_w=_np(env.crop_workers[k]), crop_s=_np(env.crop_supervisor[k]),
+                lcrop_w=_np(env.lcrop_workers[k]), lcrop_s=_np(env.lcrop_supervisor[k]), reward_w=_np(env.reward_workers[k]),
+                reward_s=_np(env.reward_supervisor[k]), step_type=_np(env.step_type[k]), terminated=_np(env.terminated[k]))
+
+
+@pytest.mark.parametrize("name", firemaker_golden_names())
+def test_cuda_replays_firemaker_reference_trace(name):
+    from ai_safety_gridworlds_b200.firemaker_env import FiremakerVectorEnv
+    d, meta = load_golden(name)
+    spec = fm_spec(meta)
+    env = FiremakerVectorEnv(2, autoreset_mode=0, spec=spec)
+    T = len(d["actions"])
+    for t in range(T + 1):
+        if t == 0:
+            env.reset()
+        else:
+            a, o, dr = replay_inputs(d, t)
+            dev = env.device
+            env.step(torch.from_numpy(np.repeat(a, 2, 0)).to(dev), torch.from_numpy(np.repeat(o, 2, 0)).to(dev),
+                     torch.from_numpy(np.repeat(dr, 2, 0)).to(dev))
+        ex = env.observe()
+        for k in (0, 1):
+            ox = {key: _np(v[k]) for key, v in ex.items()}
+            check_against_trace(_view(env, k), ox, d, meta, t, "%s t=%d env=%d" % (name, t, k))
+    env.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_firemaker_matches_oracle_with_philox_draws(mode, oracle_lib):
+    """100 environments, 90 parallel steps (frames beyond the 200-frame cut-off, so episodes end and
+    restart), shuffle orders and fire draws from the shared Philox streams."""
+    from ai_safety_gridworlds_b200 import make_spec
+    from ai_safety_gridworlds_b200.firemaker_env import FiremakerVectorEnv
+    spec = make_spec("firemaker_ex_ma", autoreset_mode=mode, max_iterations=200)
+    N = 100
+    env = FiremakerVectorEnv(N, env_index_base=31, seed=5, autoreset_mode=mode, spec=spec)
+    orc = oracle_lib.FiremakerOracle(spec, N, env_index_base=31, seed=5)
+    orc.reset()
+    rng = np.random.default_rng(0)
+    for t in range(90):
+        a = rng.integers(0, 5, size=(N, 3)).astype(np.int32)
+        env.step(torch.from_numpy(a).to(env.device))
+        orc.step(a)
+        ctx = "mode=%d t=%d" % (mode, t)
+        np.testing.assert_array_equal(_np(env.board), orc.board, err_msg=ctx)
+        np.testing.assert_array_equal(_np(env.cube), orc.cube, err_msg=ctx)
+        np.testing.assert_array_equal(_np(env.crop_workers), orc.crop_w, err_msg=ctx)
+        np.testing.assert_array_equal(_np(env.crop_supervisor), orc.crop_s, err_msg=ctx)
+        np.testing.assert_array_equal(_np(env.lcrop_workers), orc.lcrop_w, err_msg=ctx)
+        np.testing.assert_array_equal(_np(env.lcrop_supervisor), orc.lcrop_s, err_msg=ctx)
+        np.testing.assert_array_equal(_np(env.reward_workers), orc.reward_w, err_msg=ctx)
+        np.testing.assert_array_equal(_np(env.reward_supervisor), orc.reward_s, err_msg=ctx)
+        np.testing.assert_array_equal(_np(env.step_type), orc.step_type, err_msg=ctx)
+        np.testing.assert_array_equal(_np(env.terminated), orc.terminated, err_msg=ctx)
+        ex, ox = env.observe(), orc.observe()
+        for key in ("metrics", "cumulative", "frame", "pos", "ext_fires"):
+            np.testing.assert_array_equal(_np(ex[key]), ox[key], err_msg=ctx + " " + key)
+    assert int(_np(env.board == ord("F")).sum()) > 0
+    env.close()
+    orc.close()
+
+
+def test_firemaker_rejects_unsupported_configurations():
+    from ai_safety_gridworlds_b200 import make_spec
+    for kw in ({"amount_agents": 2}, {"observation_direction_mode": 1}, {"agent_observation_radius": [1, 1, 1, 1]},
+               {"FIRE_SPREAD_EXCLUSIVE_MAX_DISTANCE": 4.0}, {"AGENT_MOVEMENT_REWARD": "{'OTHER': -1}"}):
+        with pytest.raises(NotImplementedError):
+            make_spec("firemaker_ex_ma", **kw)
