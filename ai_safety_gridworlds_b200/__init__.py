@@ -8,7 +8,8 @@ API.  There is no CPU fallback.
 from . import _abi  # noqa: F401
 from .envs import make_spec, ENVIRONMENTS  # noqa: F401
 
-__all__ = ["make_spec", "ENVIRONMENTS", "VectorEnv", "GridworldGymEnv"]
+__all__ = ["make_spec", "ENVIRONMENTS", "VectorEnv", "ClassicVectorEnv", "FiremakerVectorEnv", "GridworldGymEnv",
+           "GridworldZooParallelEnv"]
 
 
 def __getattr__(name):
@@ -16,6 +17,15 @@ def __getattr__(name):
     if name == "VectorEnv":
         from .vector_env import VectorEnv
         return VectorEnv
+    if name == "ClassicVectorEnv":
+        from .classic_env import ClassicVectorEnv
+        return ClassicVectorEnv
+    if name == "FiremakerVectorEnv":
+        from .firemaker_env import FiremakerVectorEnv
+        return FiremakerVectorEnv
+    if name == "GridworldZooParallelEnv":
+        from .helpers.gridworld_zoo_parallel_env import GridworldZooParallelEnv
+        return GridworldZooParallelEnv
     if name == "GridworldGymEnv":
         from .helpers.gridworld_gym_env import GridworldGymEnv
         return GridworldGymEnv

@@ -1,0 +1,196 @@
+"""GridworldZooParallelEnv: the reference's PettingZoo parallel signature over the CUDA backend.
+
+Mirrors helpers/gridworld_zoo_parallel_env.py of the reference (constructor :100-135, `reset`
+:618-702, `step` :429-615, `agents` :252-253) for firemaker_ex_ma:
+
+  * `num_envs=None` is the drop-in single environment: dicts keyed 'agent_1', 'agent_2', 'agent_S' of
+    numpy values with the reference's shapes -- observations '<U1' [1,5,5] / [1,33,33] (float32
+    value-mapped with `ascii_observation_format=False`), rewards float64 [2] / [3], terminateds bool,
+    truncateds False, infos -- done agents leave `agents`, stepping a done agent raises ValueError
+    (rl/pycolab_interface_ma.py:217-218) and a finished game needs `reset()`;
+  * `num_envs=N` is the batched form: the same dicts of torch CUDA tensors with a leading batch
+    dimension (observations as uint8 ASCII codes or float32), auto-reset inside the step that ends
+    a game.
+
+pettingzoo itself is not imported (duck-typed).  Every step is one launch of the warp-per-environment
+kernel; there is no CPU fallback.
+"""
+import numpy as np
+import torch
+
+from .. import _abi
+from ..envs import make_spec
+from ..firemaker_env import FiremakerVectorEnv
+from .gridworld_gym_env import (DiscreteActionSpace, INFO_OBSERVATION_LAYERS_CUBE, INFO_OBSERVATION_LAYERS_ORDER)
+
+INFO_AGENT_OBSERVATIONS = "info_agent_observations"
+INFO_AGENT_OBSERVATION_LAYERS_ORDER = "info_agent_observation_layers_order"
+INFO_AGENT_OBSERVATION_LAYERS_CUBE = "info_agent_observation_layers_cube"
+
+_WRAPPER_ONLY = ("use_transitions", "render_animation_delay", "flatten_observations", "object_coordinates_in_observation",
+                 "layers_in_observation", "occlusion_in_layers", "layers_order_in_cube", "layers_order_in_cube_per_agent",
+                 "ascii_attributes_format", "attribute_coordinates_in_observation", "layers_in_attribute_observation",
+                 "occlusion_in_atribute_layers", "observable_attribute_categories", "observable_attribute_value_mapping",
+                 "use_multi_discrete_action_space", "np_random", "test_death", "test_death_probability", "pre_reset_callback",
+                 "post_reset_callback", "pre_step_callback", "post_step_callback", "render_mode")
+
+
+class GridworldZooParallelEnv(object):
+    metadata = {"render.modes": ["ansi"], "name": "gridworld_zoo_parallel_env_b200"}
+
+    def __init__(self, env_name, ascii_observation_format=True, seed=None, num_envs=None, device=None, **kwargs):
+        if kwargs.get("test_death"):
+            raise NotImplementedError("test_death fault injection is a wrapper-side debugging aid and is not built")
+        for k in _WRAPPER_ONLY:
+            kwargs.pop(k, None)
+        if env_name.lower() != "firemaker_ex_ma":
+            raise NotImplementedError("the multi-agent CUDA backend is built for firemaker_ex_ma (BASELINE config 4)")
+        kwargs.setdefault("amount_agents", 3)
+        self._batched = num_envs is not None
+        n = int(num_envs) if self._batched else 1
+        mode = _abi.GW_AUTORESET_SAME_STEP if self._batched else _abi.GW_AUTORESET_NEXT_STEP
+        self._spec = make_spec(env_name, autoreset_mode=mode, **kwargs)
+        self._env = FiremakerVectorEnv(n, device=device, seed=0 if seed is None else seed, autoreset_mode=mode, spec=self._spec)
+        self._ascii = bool(ascii_observation_format)
+        self.possible_agents = ["agent_1", "agent_2", "agent_S"]
+        self.agent_name_mapping = dict(zip(self.possible_agents, ["1", "2", "S"]))
+        self.agent_name_reverse_mapping = {v: k for k, v in self.agent_name_mapping.items()}
+        lo, hi = self._spec.action_range
+        self.action_spaces = {a: DiscreteActionSpace(lo, hi, seed) for a in self.possible_agents}
+        self.num_envs = n
+        self._dones = {a: False for a in self.possible_agents}
+        lut = torch.zeros(256, dtype=torch.float32, device=self._env.device)
+        for ch, v in self._spec.value_mapping.items():
+            lut[ord(ch)] = v
+        self._lut = lut
+
+    # ------------------------------------------------------------------ PettingZoo surface
+    @property
+    def agents(self):
+        return [a for a in self.possible_agents if not self._dones[a]]
+
+    @property
+    def num_agents(self):
+        return len(self.agents)
+
+    @property
+    def max_num_agents(self):
+        return len(self.possible_agents)
+
+    def action_space(self, agent):
+        return self.action_spaces[agent]
+
+    @property
+    def vector_env(self):
+        return self._env
+
+    def close(self):
+        self._env.close()
+
+    def seed(self, seed=None):
+        for sp in self.action_spaces.values():
+            sp._rng = np.random.default_rng(seed)
+
+    def reset(self, seed=None, *args, **kwargs):
+        if seed is not None:
+            self.seed(seed)
+        self._env.reset()
+        self._dones = {a: False for a in self.possible_agents}
+        return self._observations(), self._infos()
+
+    def step(self, actions, *args, replay_order=None, replay_draws=None, **kwargs):
+        """`replay_order` (agent indices in execution order) and `replay_draws` (the FireDrape uniform draws of this
+        step, in call order) replay a recorded reference run -- test hooks of the single-environment form."""
+        env = self._env
+        if self._batched:
+            cols = []
+            for a in self.possible_agents:
+                v = actions[a]
+                v = v if torch.is_tensor(v) else torch.as_tensor(np.asarray(v), device=env.device)
+                cols.append(v.to(device=env.device, dtype=torch.int32).reshape(-1))
+            act = torch.stack(cols, dim=1).contiguous()
+        else:
+            for a in actions:
+                if self._dones.get(a, False):
+                    raise ValueError("Agent %s is done" % self.agent_name_mapping[a])     # pycolab_interface_ma.py:217-218
+            if not self.agents:
+                raise ValueError("all agents are done: call reset()")
+            vals = []
+            for a in self.possible_agents:
+                v = actions.get(a, 0)
+                v = v["step"] if isinstance(v, dict) else v                               # {"step": a} modality (safety_game_ma.py:412-423)
+                vals.append(int(np.asarray(v).item()))
+            if any(v == 9 for v in vals):
+                raise NotImplementedError("QUIT is not supported by the multi-agent CUDA backend")
+            act = torch.tensor([vals], dtype=torch.int32, device=env.device)
+        order = draws = None
+        if replay_order is not None:
+            order = torch.tensor(np.asarray(replay_order, np.int32).reshape(1, 3), device=env.device)
+        if replay_draws is not None:
+            dr = np.full((1, _abi.GW_FM_MAX_DRAWS), 2.0)
+            dr[0, :len(replay_draws)] = replay_draws
+            draws = torch.from_numpy(dr).to(env.device)
+        env.step(act, order, draws)
+        obs, infos = self._observations(), self._infos()
+        rewards, terms, truncs = {}, {}, {}
+        for i, a in enumerate(self.possible_agents):
+            r = env.reward_supervisor if i == 2 else env.reward_workers[:, i]
+            t = env.terminated[:, i].bool()
+            if self._batched:
+                rewards[a], terms[a], truncs[a] = r.double(), t, torch.zeros_like(t)
+            else:
+                rewards[a], terms[a], truncs[a] = r[0].double().cpu().numpy(), bool(t[0].item()), False
+        if not self._batched:
+            self._dones.update(terms)
+        return obs, rewards, terms, truncs, infos
+
+    # ------------------------------------------------------------------ helpers
+    def _crop(self, i):
+        env = self._env
+        return env.crop_supervisor if i == 2 else env.crop_workers[:, i]
+
+    def _lcrop(self, i):
+        env = self._env
+        return env.lcrop_supervisor if i == 2 else env.lcrop_workers[:, i]
+
+    def _observations(self):
+        out = {}
+        for i, a in enumerate(self.possible_agents):
+            codes = self._crop(i)
+            if self._batched:
+                out[a] = (codes.clone() if self._ascii else self._lut[codes.long()]).unsqueeze(1)
+            elif self._ascii:
+                c = codes[0].cpu().numpy()
+                out[a] = np.vectorize(chr)(c)[np.newaxis, :]                                # '<U1' [1, h, w]
+            else:
+                out[a] = self._lut[codes[0].long()].cpu().numpy()[np.newaxis, :]
+        return out
+
+    def _infos(self):
+        env, spec = self._env, self._spec
+        ex = env.observe()
+        infos = {}
+        for i, a in enumerate(self.possible_agents):
+            lo, hi = (4, 7) if i == 2 else (2 * i, 2 * i + 2)
+            info = {
+                "ascii_codes": env.board, INFO_OBSERVATION_LAYERS_ORDER: list(spec.layer_order),
+                INFO_OBSERVATION_LAYERS_CUBE: env.cube.bool(),
+                INFO_AGENT_OBSERVATION_LAYERS_ORDER: list(spec.layer_order),
+                INFO_AGENT_OBSERVATION_LAYERS_CUBE: self._lcrop(i).bool(),
+                INFO_AGENT_OBSERVATIONS: self._crop(i),
+                "cumulative_reward": ex["cumulative"][:, lo:hi].double(),
+                "metrics_dict": {n: ex["metrics"][:, j] for j, n in enumerate(spec.metric_names)},
+                "frame": ex["frame"], "agent_positions": ex["pos"], "external_fires": ex["ext_fires"],
+                "step_type": env.step_type[:, i],
+            }
+            if not self._batched:
+                def host(x):
+                    if torch.is_tensor(x):
+                        return x[0].cpu().numpy()
+                    if isinstance(x, dict):
+                        return {k: host(v) for k, v in x.items()}
+                    return x
+                info = {k: host(v) for k, v in info.items()}
+                info["metrics_dict"] = {k: float(v) for k, v in info["metrics_dict"].items()}
+            infos[a] = info
+        return infos
