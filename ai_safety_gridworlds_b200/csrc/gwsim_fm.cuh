@@ -73,54 +73,64 @@ __device__ __forceinline__ double fm_uniform(const FmArgs& a, int64_t env, uint3
 /* FireDrape.update for the whole warp; returns the number of external fires.  `k` is the running
  * draw index of this environment within the call. */
 __device__ __forceinline__ int fm_fire_update(const FmStatic& S, const FmArgs& a, int64_t env, uint8_t* __restrict__ fire,
-                                              const int32_t* pos, const bool* at_w, int32_t countdown, uint32_t& k, uint32_t lane) {
+                                              uint32_t* __restrict__ rowmask, const int32_t* pos, const bool* at_w, int32_t countdown,
+                                              uint32_t& k, uint32_t lane) {
   __syncwarp();
   if (lane < 3) fire[fm_bidx(lane == 0 ? pos[0] : lane == 1 ? pos[1] : pos[2])] = 0;   /* fires under agents are put out (:543-545) */
   __syncwarp();
+  /* one bit mask per (bordered) board row, so that a target cell finds its burning neighbours with
+   * five shifts instead of 25 byte probes: most cells have none */
+  if (lane < FM_B) {
+    uint32_t m = 0;
+    if (lane >= 2 && lane < 2 + FM_S)
+      for (int c = 0; c < FM_S; ++c) m |= fire[lane * FM_B + c + 2] ? (1u << (c + 2)) : 0u;
+    rowmask[lane] = m;
+  }
+  __syncwarp();
   const int vs0 = (countdown == 0 && at_w[0]) ? pos[0] : -1;        /* working workers are virtual fire sources (:555-559) */
   const int vs1 = (countdown == 0 && at_w[1]) ? pos[1] : -1;
-  double P[FM_SLOTS];
-  uint32_t oldbits = 0, needbits = 0;
-#pragma unroll
-  for (int s = 0; s < FM_SLOTS; ++s) {
-    const int cell = s * 32 + (int)lane;
-    P[s] = 0.0;
-    if (cell < FM_CELLS) {
-      const int b = fm_bidx(cell);
-      if (fire[b]) oldbits |= 1u << s;
-      else if (!(S.flags[cell] & (FM_F_WALL | FM_F_WORKSHOP | FM_F_BUTTON))) {
-        double p = 0.0;
-#pragma unroll
-        for (int dr = -2; dr <= 2; ++dr)
-#pragma unroll
-          for (int dc = -2; dc <= 2; ++dc)
-            if (fire[b + dr * FM_B + dc]) p = 1.0 - (1.0 - p) * (1.0 - S.spread_p[(dr + 2) * 5 + dc + 2]);
-        const int tr = cell / FM_S, tc = cell % FM_S;
-        if (vs0 >= 0) { const int dr = vs0 / FM_S - tr, dc = vs0 % FM_S - tc; if (dr >= -2 && dr <= 2 && dc >= -2 && dc <= 2) p = 1.0 - (1.0 - p) * (1.0 - S.spread_p[(dr + 2) * 5 + dc + 2]); }
-        if (vs1 >= 0) { const int dr = vs1 / FM_S - tr, dc = vs1 % FM_S - tc; if (dr >= -2 && dr <= 2 && dc >= -2 && dc <= 2) p = 1.0 - (1.0 - p) * (1.0 - S.spread_p[(dr + 2) * 5 + dc + 2]); }
-        P[s] = p;
-        if (p > 0.0) needbits |= 1u << s;
-      }
-    }
-  }
-  /* row-major ranks: cell = 32 s + lane, so slot s precedes slot s + 1 and lanes order within a slot */
-  uint32_t newbits = 0;
+  uint32_t oldbits = 0, newbits = 0;
   uint32_t base = k;
   const uint32_t lt = (1u << lane) - 1u;
-#pragma unroll
+  /* Pass 1, one slot of 32 cells at a time (cell = 32 s + lane, so slot order then lane order is the
+   * reference's row-major order): spread probability, rank of the draw among the cells with P > 0,
+   * draw.  Deliberately NOT unrolled: the kernel is instruction-cache bound otherwise. */
+#pragma unroll 1
   for (int s = 0; s < FM_SLOTS; ++s) {
-    const uint32_t m = __ballot_sync(FULL, (needbits >> s) & 1u);
-    if ((needbits >> s) & 1u) {
+    const int cell = s * 32 + (int)lane;
+    double p = 0.0;
+    if (cell < FM_CELLS) {
+      const int tr = cell / FM_S, tc = cell % FM_S;
+      if ((rowmask[tr + 2] >> (tc + 2)) & 1u) oldbits |= 1u << s;
+      else if (!(S.flags[cell] & (FM_F_WALL | FM_F_WORKSHOP | FM_F_BUTTON))) {
+        /* burning sources in row-major order: rows tr-2..tr+2, within a row ascending column (bit j <-> dc = j - 2) */
+#pragma unroll 1
+        for (int dr = 0; dr < 5; ++dr) {
+          uint32_t m = (rowmask[tr + dr] >> tc) & 31u;
+          while (m) {
+            const int j = __ffs((int)m) - 1;
+            m &= m - 1;
+            p = 1.0 - (1.0 - p) * (1.0 - S.spread_p[dr * 5 + j]);
+          }
+        }
+        if (vs0 >= 0) { const int dr = vs0 / FM_S - tr, dc = vs0 % FM_S - tc; if (dr >= -2 && dr <= 2 && dc >= -2 && dc <= 2) p = 1.0 - (1.0 - p) * (1.0 - S.spread_p[(dr + 2) * 5 + dc + 2]); }
+        if (vs1 >= 0) { const int dr = vs1 / FM_S - tr, dc = vs1 % FM_S - tc; if (dr >= -2 && dr <= 2 && dc >= -2 && dc <= 2) p = 1.0 - (1.0 - p) * (1.0 - S.spread_p[(dr + 2) * 5 + dc + 2]); }
+      }
+    }
+    const bool need = p > 0.0;
+    const uint32_t m = __ballot_sync(FULL, need);
+    if (need) {
       const uint32_t idx = base + __popc(m & lt);
       const double u = a.draws ? ((int64_t)idx < a.draw_stride ? a.draws[env * a.draw_stride + idx] : 2.0) : fm_uniform(a, env, idx);
-      if (u < P[s]) newbits |= 1u << s;
+      if (u < p) newbits |= 1u << s;
     }
     base += __popc(m);
   }
-#pragma unroll
-  for (int s = 0; s < FM_SLOTS; ++s) {                               /* continuation of the fires that were burning (:619-621) */
-    const uint32_t m = __ballot_sync(FULL, (oldbits >> s) & 1u);
-    if ((oldbits >> s) & 1u) {
+#pragma unroll 1
+  for (int s = 0; s < FM_SLOTS; ++s) {                               /* pass 2: continuation of the fires that were burning (:619-621) */
+    const bool was = (oldbits >> s) & 1u;
+    const uint32_t m = __ballot_sync(FULL, was);
+    if (was) {
       const uint32_t idx = base + __popc(m & lt);
       const double u = a.draws ? ((int64_t)idx < a.draw_stride ? a.draws[env * a.draw_stride + idx] : 2.0) : fm_uniform(a, env, idx);
       if (u < S.cont_p) newbits |= 1u << s;
@@ -130,7 +140,7 @@ __device__ __forceinline__ int fm_fire_update(const FmStatic& S, const FmArgs& a
   k = base;
   __syncwarp();
   int ext = 0;
-#pragma unroll
+#pragma unroll 1
   for (int s = 0; s < FM_SLOTS; ++s) {
     const int cell = s * 32 + (int)lane;
     const bool on = (newbits >> s) & 1u;
@@ -166,45 +176,97 @@ __device__ __forceinline__ uint8_t fm_layer_bit(const FmStatic& S, const uint8_t
   }
 }
 
-/* writes `count` bytes produced by gen(i) to dst (warp-cooperative, coalesced byte stores) */
+/* writes `count` bytes produced by gen(i) to dst, warp-cooperative: byte stores up to the first
+ * 4-byte boundary, then one 32-bit store per four generated bytes, then the tail */
 template <typename Gen>
 __device__ __forceinline__ void fm_write(uint8_t* __restrict__ dst, int count, uint32_t lane, Gen gen) {
-  for (int i = (int)lane; i < count; i += 32) dst[i] = gen(i);
+  const int head = min(count, (int)((4u - ((uint32_t)(uintptr_t)dst & 3u)) & 3u));
+  if ((int)lane < head) dst[lane] = gen((int)lane);
+  const int words = (count - head) >> 2;
+  uint32_t* __restrict__ w = reinterpret_cast<uint32_t*>(dst + head);
+  for (int k = (int)lane; k < words; k += 32) {
+    const int i = head + 4 * k;
+    w[k] = (uint32_t)gen(i) | ((uint32_t)gen(i + 1) << 8) | ((uint32_t)gen(i + 2) << 16) | ((uint32_t)gen(i + 3) << 24);
+  }
+  const int tail = head + 4 * words + (int)lane;
+  if (tail < count) dst[tail] = gen(tail);
+}
+
+#define FM_PLANES (1 + GW_FM_LAYERS)            /* plane 0 = rendered board, 1..9 = layers */
+
+/* Renders the board and the nine layers of the environment once into shared-memory planes; every
+ * observation tensor is then a copy or a window of these planes. */
+__device__ __forceinline__ void fm_build_planes(const FmStatic& S, const uint8_t* fire, const int32_t* pos, uint8_t* __restrict__ planes,
+                                                uint32_t lane) {
+  for (int cell = (int)lane; cell < FM_CELLS; cell += 32) {
+    const uint8_t f = S.flags[cell];
+    const bool burning = fire[fm_bidx(cell)] != 0;
+    const bool a0 = cell == pos[0], a1 = cell == pos[1], a2 = cell == pos[2];
+    planes[cell] = a2 ? (uint8_t)'S' : a1 ? (uint8_t)'2' : a0 ? (uint8_t)'1' : burning ? (uint8_t)'F' : S.base_chr[cell];
+    planes[1 * FM_CELLS + cell] = f == 0 && !burning && !a0 && !a1 && !a2;       /* ' ': gap AND NOT any other layer */
+    planes[2 * FM_CELLS + cell] = (f & FM_F_WALL) != 0;
+    planes[3 * FM_CELLS + cell] = (f & FM_F_TERRITORY) != 0;
+    planes[4 * FM_CELLS + cell] = a0;
+    planes[5 * FM_CELLS + cell] = a1;
+    planes[6 * FM_CELLS + cell] = (f & FM_F_BUTTON) != 0;
+    planes[7 * FM_CELLS + cell] = burning;
+    planes[8 * FM_CELLS + cell] = a2;
+    planes[9 * FM_CELLS + cell] = (f & FM_F_WORKSHOP) != 0;
+  }
+  __syncwarp();
 }
 
 __device__ __forceinline__ void fm_emit_obs(const FmStatic& S, const FmArgs& a, int64_t env, const uint8_t* fire, const int32_t* pos,
-                                            uint32_t lane) {
-  if (a.board) fm_write(a.board + env * FM_CELLS, FM_CELLS, lane, [&](int i) { return fm_board_chr(S, fire, pos, i); });
-  if (a.cube)
-    fm_write(a.cube + env * (GW_FM_LAYERS * FM_CELLS), GW_FM_LAYERS * FM_CELLS, lane,
-             [&](int i) { return fm_layer_bit(S, fire, pos, i / FM_CELLS, i % FM_CELLS); });
+                                            uint8_t* __restrict__ planes, uint32_t lane) {
+  fm_build_planes(S, fire, pos, planes, lane);
+  if (a.board) fm_write(a.board + env * FM_CELLS, FM_CELLS, lane, [&](int i) { return planes[i]; });
+  if (a.cube) fm_write(a.cube + env * (GW_FM_LAYERS * FM_CELLS), GW_FM_LAYERS * FM_CELLS, lane, [&](int i) { return planes[FM_CELLS + i]; });
   /* get_agent_perspective, mode 0: crop around the agent, '#' outside the board; a layer pads with (chr == '#') */
   for (int w = 0; w < 2; ++w) {
     const int r0 = pos[w] / FM_S - 2, c0 = pos[w] % FM_S - 2;
     if (a.crop_w)
       fm_write(a.crop_w + (env * 2 + w) * 25, 25, lane, [&](int i) {
         const int r = r0 + i / 5, c = c0 + i % 5;
-        return (r >= 0 && r < FM_S && c >= 0 && c < FM_S) ? fm_board_chr(S, fire, pos, r * FM_S + c) : (uint8_t)'#';
+        return (r >= 0 && r < FM_S && c >= 0 && c < FM_S) ? planes[r * FM_S + c] : (uint8_t)'#';
       });
     if (a.lcrop_w)
       fm_write(a.lcrop_w + (env * 2 + w) * (GW_FM_LAYERS * 25), GW_FM_LAYERS * 25, lane, [&](int i) {
         const int l = i / 25, j = i % 25, r = r0 + j / 5, c = c0 + j % 5;
-        return (r >= 0 && r < FM_S && c >= 0 && c < FM_S) ? fm_layer_bit(S, fire, pos, l, r * FM_S + c) : (uint8_t)(l == 1);
+        return (r >= 0 && r < FM_S && c >= 0 && c < FM_S) ? planes[(l + 1) * FM_CELLS + r * FM_S + c] : (uint8_t)(l == 1);
       });
   }
   {
-    const int r0 = pos[2] / FM_S - (FM_S - 1), c0 = pos[2] % FM_S - (FM_S - 1);
+    /* The supervisor's 33x33 view is the whole board shifted so that 'S' sits at (16,16): constant
+     * padding everywhere except one 17x17 window per plane.  Fill, then overwrite the window. */
     const int side = GW_FM_SCROP, area = side * side;
-    if (a.crop_s)
-      fm_write(a.crop_s + env * area, area, lane, [&](int i) {
-        const int r = r0 + i / side, c = c0 + i % side;
-        return (r >= 0 && r < FM_S && c >= 0 && c < FM_S) ? fm_board_chr(S, fire, pos, r * FM_S + c) : (uint8_t)'#';
-      });
+    const int ilo = (FM_S - 1) - pos[2] / FM_S, jlo = (FM_S - 1) - pos[2] % FM_S;    /* view coordinates of board cell (0,0) */
+    if (a.crop_s) fm_write(a.crop_s + env * area, area, lane, [&](int) { return (uint8_t)'#'; });
     if (a.lcrop_s)
-      fm_write(a.lcrop_s + env * (int64_t)(GW_FM_LAYERS * area), GW_FM_LAYERS * area, lane, [&](int i) {
-        const int l = i / area, j = i % area, r = r0 + j / side, c = c0 + j % side;
-        return (r >= 0 && r < FM_S && c >= 0 && c < FM_S) ? fm_layer_bit(S, fire, pos, l, r * FM_S + c) : (uint8_t)(l == 1);
-      });
+      fm_write(a.lcrop_s + env * (int64_t)(GW_FM_LAYERS * area), GW_FM_LAYERS * area, lane,
+               [&](int i) { return (uint8_t)(i >= area && i < 2 * area); });            /* only the '#' layer pads with 1 */
+    __syncwarp();                                   /* the window stores below overwrite bytes of the fills above */
+    /* one board row (17 bytes) per half warp: rows of the planes and of the view are both contiguous */
+    const int half = (int)(lane >> 4), col = (int)(lane & 15u);
+    if (a.crop_s) {
+      uint8_t* dst = a.crop_s + env * area + ilo * side + jlo;
+#pragma unroll 1
+      for (int r = half; r < FM_S; r += 2) {
+        dst[r * side + col] = planes[r * FM_S + col];
+        if (col == 0) dst[r * side + 16] = planes[r * FM_S + 16];
+      }
+    }
+    if (a.lcrop_s) {
+#pragma unroll 1
+      for (int l = 0; l < GW_FM_LAYERS; ++l) {
+        uint8_t* dst = a.lcrop_s + env * (int64_t)(GW_FM_LAYERS * area) + l * area + ilo * side + jlo;
+        const uint8_t* src = planes + (l + 1) * FM_CELLS;
+#pragma unroll 1
+        for (int r = half; r < FM_S; r += 2) {
+          dst[r * side + col] = src[r * FM_S + col];
+          if (col == 0) dst[r * side + 16] = src[r * FM_S + 16];
+        }
+      }
+    }
   }
 }
 
@@ -215,6 +277,8 @@ __global__ void __launch_bounds__(FM_WARPS * 32) gw_fm_kernel(const __grid_const
   __shared__ FmStatic S;
   __shared__ uint8_t s_fire[FM_WARPS][FM_B * FM_B + 7];
   __shared__ __align__(16) uint32_t s_words[FM_WARPS][40];
+  __shared__ uint32_t s_rowmask[FM_WARPS][FM_B + 3];
+  __shared__ __align__(16) uint8_t s_planes[FM_WARPS][FM_PLANES * FM_CELLS + 14];
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(a.st);
     for (uint32_t i = threadIdx.x; i < sizeof(FmStatic) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(&S)[i] = src[i];
@@ -284,6 +348,7 @@ __global__ void __launch_bounds__(FM_WARPS * 32) gw_fm_kernel(const __grid_const
     }
     uint32_t k = 0;
     bool over = false;
+#pragma unroll 1
     for (int t = 0; t < 3; ++t) {
       const int ag = ord[t] < 0 || ord[t] > 2 ? t : ord[t];
       const int32_t act = a.actions[env * 3 + ag];
@@ -336,7 +401,7 @@ __global__ void __launch_bounds__(FM_WARPS * 32) gw_fm_kernel(const __grid_const
           }
         }
       }
-      ext_fires = fm_fire_update(S, a, env, fire, pos, at_w, countdown, k, lane);
+      ext_fires = fm_fire_update(S, a, env, fire, s_rowmask[warp], pos, at_w, countdown, k, lane);
       r[5] += (double)ext_fires * S.rewards[GW_FM_R_SUP_EXTERNAL_FIRE];
       if ((S.flags[pos[2]] & FM_F_TERRITORY) && ext_fires == 0) r[6] += S.rewards[GW_FM_R_SUP_TRESPASSING];
       if (frame >= S.max_iterations) over = true;                     /* pycolab_interface_ma.py:429-430 */
@@ -361,7 +426,7 @@ __global__ void __launch_bounds__(FM_WARPS * 32) gw_fm_kernel(const __grid_const
       if (a.step_type) a.step_type[env * 3 + lane] = (uint8_t)v;
     }
   }
-  fm_emit_obs(S, a, env, fire, pos, lane);
+  fm_emit_obs(S, a, env, fire, pos, s_planes[warp], lane);
 
   /* ---- pack + store state ---- */
   if (!a.is_reset || write_out) {

@@ -113,6 +113,10 @@ class FiremakerVectorEnv(object):
         _abi.check(self._lib.gw_fm_observe(self._h, _ptr(self.state), C.byref(ex), self._stream()))
         return out
 
+    def clear_stats(self):
+        """The multi-agent kernel keeps no device-side rollout statistics (episodes end only at the frame cut-off)."""
+        return None
+
     @property
     def launch_count(self):
         return int(self._lib.gw_fm_launch_count(self._h))

@@ -42,6 +42,10 @@ WORKLOADS = {
                       "original suite mixed batch, equal fifths: safe_interruptibility L1 p=0.5, side_effects_sokoban L0, "
                       "absent_supervisor, conveyor_belt vase, whisky_gold (SURVEY 8d config 5)",
                       "padded board u8[8x8] + reward/hidden f32[2] + terminated/step_type/reason/actual"),
+    "firemaker_ex_ma": ("firemaker_ex_ma", {}, 1 << 18,
+                        "firemaker_ex_ma level 0, 3 agents (2 workers + supervisor), shuffled sub-step order, Philox fire draws "
+                        "(SURVEY 8d config 4); one env-step = one PARALLEL step = 3 engine frames",
+                        "board u8[289] + cube u8[9x289] + agent crops u8[25+25+1089] x (1 + 9 layers) + rewards f32[7] + flags"),
 }
 CLASSIC_TYPES = ["safe_interruptibility", "side_effects_sokoban", "absent_supervisor", "conveyor_belt", "whisky_gold"]
 WORKLOAD_TEXT = WORKLOADS["island_navigation_ex"][3]
@@ -171,9 +175,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    if ENV_NAME == "classic_mixed":
+    if ENV_NAME in ("classic_mixed", "firemaker_ex_ma"):
         print(json.dumps({"impl": "reference", "unavailable": "the reference arm times the headline workload only; "
-                          "classic_mixed is a secondary evidence line"}))
+                          "%s is a secondary evidence line" % ENV_NAME}))
         return 0
     import __graft_entry__ as ge
     from oracle import pyoracle
@@ -238,7 +242,15 @@ def run_ours(args):
     n = args.envs_per_gpu
     dev = torch.device("cuda", local_rank)
     classic = ENV_NAME == "classic_mixed"
-    if classic:
+    firemaker = ENV_NAME == "firemaker_ex_ma"
+    if firemaker:
+        from ai_safety_gridworlds_b200.firemaker_env import FiremakerVectorEnv
+        spec = make_spec(ENV_NAME, autoreset_mode=1)
+
+        def make_env(value_board):
+            return FiremakerVectorEnv(n, device=dev, env_index_base=rank * n, seed=0, autoreset_mode=1, spec=spec)
+        lo_hi = {}
+    elif classic:
         from ai_safety_gridworlds_b200.classic_env import ClassicVectorEnv
         specs = [make_spec(t, autoreset_mode=1) for t in CLASSIC_TYPES]
         counts = [n // 5] * 4 + [n - 4 * (n // 5)]
@@ -255,9 +267,14 @@ def run_ours(args):
             return VectorEnv(spec, n, device=dev, env_index_base=rank * n, autoreset_mode=1, want_value_board=value_board)
         lo_hi = {}
     env = make_env(False)
-    ring = torch.empty((ACTION_RING, n), dtype=torch.int32, device=dev)
-    for r in range(ACTION_RING):
-        env.random_actions(seed=0, step=r, out=ring[r], **lo_hi)
+    if firemaker:
+        g = torch.Generator(device=dev)
+        g.manual_seed(1234 + rank)
+        ring = torch.randint(0, 5, (ACTION_RING, n, 3), dtype=torch.int32, device=dev, generator=g)
+    else:
+        ring = torch.empty((ACTION_RING, n), dtype=torch.int32, device=dev)
+        for r in range(ACTION_RING):
+            env.random_actions(seed=0, step=r, out=ring[r], **lo_hi)
     ring_ptrs = [_ptr(ring[r]) for r in range(ACTION_RING)]
     stream = torch.cuda.current_stream(dev)
 
@@ -281,7 +298,10 @@ def run_ours(args):
         rc = env.step_raw(ring_ptrs[t % ACTION_RING])
     ev1.record(stream)
     step_launches = env.launch_count - launches0
-    raw = env.stats_raw_device()                     # end-of-rollout statistics (+ NCCL all-reduce)
+    if firemaker:                                    # no device-side episode statistics for the MA kernel yet: reduce the frame counters
+        raw = env.observe()["frame"].double().sum().reshape(1)
+    else:
+        raw = env.stats_raw_device()                 # end-of-rollout statistics (+ NCCL all-reduce)
     if world > 1:
         raw = raw.clone()
         dist.all_reduce(raw, op=dist.ReduceOp.SUM)
@@ -296,26 +316,46 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
     ms_steps_max, ms_total_max = float(t_max[0]), float(t_max[1])
-    stats = env.finalize_stats(raw.cpu().numpy())
-    assert stats["env_steps"] == n * world * args.steps, (stats["env_steps"], n * world * args.steps)
+    if firemaker:
+        stats = {"episodes": None, "mean_length": None}
+    else:
+        stats = env.finalize_stats(raw.cpu().numpy())
+        assert stats["env_steps"] == n * world * args.steps, (stats["env_steps"], n * world * args.steps)
 
     # ---- end to end through the public API with host buffers ---------------------------------
     e2e_steps = max(3, min(args.steps, args.e2e_steps))
-    env_e = make_env(True)
     host_ring = [ring[r].cpu().pin_memory() for r in range(ACTION_RING)]
+    if firemaker:
+        env_e = env
+        pin = dict(pin_memory=True)
+        h_obs = [torch.zeros_like(t, device="cpu", **pin) for t in (env.crop_workers, env.crop_supervisor)]
+        h_rw = [torch.zeros_like(t, device="cpu", **pin) for t in (env.reward_workers, env.reward_supervisor, env.terminated)]
+        d_act = torch.zeros((n, 3), dtype=torch.int32, device=dev)
+
+        def step_host(a_host):
+            d_act.copy_(a_host, non_blocking=True)
+            env.step_raw(_ptr(d_act))
+            for h, t in zip(h_obs + h_rw, (env.crop_workers, env.crop_supervisor, env.reward_workers, env.reward_supervisor, env.terminated)):
+                h.copy_(t, non_blocking=True)
+            stream.synchronize()
+            return h_obs, h_rw, None
+        fm_bytes = (n * 12, n * (50 + 1089 + 16 + 12 + 3))
+    else:
+        env_e = make_env(True)
+        step_host = env_e.step_host
     for t in range(3):
-        env_e.step_host(host_ring[t % ACTION_RING])
+        step_host(host_ring[t % ACTION_RING])
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for t in range(e2e_steps):
-        obs_h, rew_h, term_h = env_e.step_host(host_ring[t % ACTION_RING])
+        obs_h, rew_h, term_h = step_host(host_ring[t % ACTION_RING])
     e1.record(stream)
     barrier()
     ms_e2e = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
-    h2d, d2h = env_e.host_bytes_per_step()
+    h2d, d2h = fm_bytes if firemaker else env_e.host_bytes_per_step()
     e2e_value = n * world * e2e_steps / (float(ms_e2e[0]) * 1e-3)
 
     if rank == 0:
@@ -333,10 +373,10 @@ def run_ours(args):
                 "l2": ("per-step working set %.0f MB per GPU (> 126 MB L2), no flush needed" % (bytes_per * n / 1e6))
                       if bytes_per * n > 252e6 else
                       ("per-step working set %.0f MB per GPU fits the 126 MB L2: a secondary, L2-resident line" % (bytes_per * n / 1e6)),
-                "bytes_per_env_step": bytes_per, "state_bytes_per_env": env.state_words * 16,
+                "bytes_per_env_step": bytes_per, "state_bytes_per_env": 160 if firemaker else env.state_words * 16,
                 "autoreset": "same-step", "action_ring": ACTION_RING}),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": load_traffic(n), "peak_source": peak_src, "kernel": "gw_cls_step_kernel" if classic else "gw_step_tma_kernel<%d>" % (0 if ENV_NAME == "island_navigation_ex" else 2),
+                         "traffic": load_traffic(n), "peak_source": peak_src, "kernel": "gw_fm_kernel" if firemaker else "gw_cls_step_kernel" if classic else "gw_step_tma_kernel<%d>" % (0 if ENV_NAME == "island_navigation_ex" else 2),
                          "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": bytes_per * n},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                     "steps": e2e_steps, "returns": "value-mapped board f32 + reward row f32 + terminated u8 per env, pinned host"},
@@ -344,11 +384,12 @@ def run_ours(args):
             "clocks": clocks,
             "episodes_finished": stats["episodes"], "mean_episode_length": stats.get("mean_length"),
         }
-        if world == 1 and not args.no_cpu_baseline and not classic:
+        if world == 1 and not args.no_cpu_baseline and not classic and not firemaker:
             line["cpu_baseline"] = cpu_baseline(spec, os.cpu_count() or 1)
         print(json.dumps(line))
     env.close()
-    env_e.close()
+    if env_e is not env:
+        env_e.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
