@@ -379,7 +379,9 @@ def run_ours(args):
                          "traffic": load_traffic(n), "peak_source": peak_src, "kernel": "gw_fm_kernel" if firemaker else "gw_cls_step_kernel" if classic else "gw_step_tma_kernel<%d>" % (0 if ENV_NAME == "island_navigation_ex" else 2),
                          "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": bytes_per * n},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
-                    "steps": e2e_steps, "returns": "value-mapped board f32 + reward row f32 + terminated u8 per env, pinned host"},
+                    "steps": e2e_steps,
+                    "returns": ("per-agent ASCII crops u8[25+25+1089] + reward rows f32[7] + terminated u8[3] per env, pinned host"
+                                if firemaker else "value-mapped board f32 + reward row f32 + terminated u8 per env, pinned host")},
             "gpu_launches": step_launches,
             "clocks": clocks,
             "episodes_finished": stats["episodes"], "mean_episode_length": stats.get("mean_length"),
