@@ -1,0 +1,49 @@
+#!/usr/bin/env python
+"""Reads the flag overlays of the reference's island_navigation_ex experiments
+(ai_safety_gridworlds/experiments/*.py: `init_experiment_flags()`) by importing them, and prints the
+values that differ from the environment's own defaults as Python literals.  TEST / BUILD
+INFRASTRUCTURE: the output was pasted into ai_safety_gridworlds_b200/envs/experiments.py.
+Run with PYTHONPATH=oracle/stubs:/root/reference, one experiment per fresh interpreter (absl flags
+are process globals)."""
+import importlib
+import json
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+NAMES = ["food_bounded", "food_drink_bounded", "food_drink_bounded_death", "food_drink_bounded_death_gold",
+         "food_drink_bounded_death_gold_silver", "food_drink_bounded_gold", "food_drink_bounded_gold_silver", "food_drink_rolf",
+         "food_drink_rolf_gold_as_gap", "food_drink_rolf_gold_as_resource", "food_drink_rolf_gold_as_resource_scaled",
+         "food_drink_unbounded"]
+
+
+def worker(name):
+    sys.path.insert(0, HERE)
+    import shims  # noqa: F401
+    sys.path.insert(0, os.path.dirname(HERE))
+    from ai_safety_gridworlds_b200.envs.island_navigation_ex import DEFAULT_FLAGS
+    mod = importlib.import_module("ai_safety_gridworlds.experiments." + name)
+    flags = mod.init_experiment_flags()
+    out = {}
+    for key, default in DEFAULT_FLAGS.items():
+        v = getattr(flags, key)
+        if hasattr(v, "_reward_dimensions_dict"):
+            v = dict(v._reward_dimensions_dict)
+        if isinstance(default, bool):
+            v = bool(v)
+        elif isinstance(default, float):
+            v = float(v)
+        if v != default:
+            out[key] = v
+    art = getattr(mod, "GAME_ART", None)
+    print(json.dumps({"name": name, "overlay": out}))
+
+
+if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[1] == "--worker":
+        worker(sys.argv[2])
+    else:
+        env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(HERE, "stubs"), "/root/reference"]))
+        for n in NAMES:
+            subprocess.run([sys.executable, os.path.abspath(__file__), "--worker", n], env=env)

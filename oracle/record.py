@@ -82,6 +82,19 @@ CASES = {
         "DRINK_EXTRACTION_RATE": 3.5, "FOOD_EXTRACTION_RATE": 6.25, "DRINK_REGROWTH_EXPONENT": 1.3,
         "DRINK_AVAILABILITY_INITIAL": 12.5, "FOOD_GROWTH_LIMIT": 15, "FOOD_AVAILABILITY_INITIAL": 15},
         steps=500, seed=19, policy="safe", avoid="W", lo=0, hi=4),
+    # ---- experiment overlays (ai_safety_gridworlds/experiments/*.py), through the reference's factory names ----
+    "island_exp_food_bounded": dict(env="food_bounded", kwargs={}, steps=200, seed=30, policy="uniform", lo=0, hi=4),
+    "island_exp_food_drink_bounded": dict(env="food_drink_bounded", kwargs={}, steps=200, seed=31, policy="uniform", lo=0, hi=4),
+    "island_exp_food_drink_bounded_death": dict(env="food_drink_bounded_death", kwargs={}, steps=200, seed=32, policy="uniform", lo=0, hi=4),
+    "island_exp_food_drink_bounded_death_gold": dict(env="food_drink_bounded_death_gold", kwargs={}, steps=200, seed=33, policy="uniform", lo=0, hi=4),
+    "island_exp_food_drink_bounded_death_gold_silver": dict(env="food_drink_bounded_death_gold_silver", kwargs={}, steps=200, seed=34, policy="uniform", lo=0, hi=4),
+    "island_exp_food_drink_bounded_gold": dict(env="food_drink_bounded_gold", kwargs={}, steps=200, seed=35, policy="uniform", lo=0, hi=4),
+    "island_exp_food_drink_bounded_gold_silver": dict(env="food_drink_bounded_gold_silver", kwargs={}, steps=200, seed=36, policy="uniform", lo=0, hi=4),
+    "island_exp_food_drink_rolf": dict(env="food_drink_rolf", kwargs={}, steps=200, seed=37, policy="uniform", lo=0, hi=4),
+    "island_exp_food_drink_rolf_gold_as_gap": dict(env="food_drink_rolf_gold_as_gap", kwargs={}, steps=200, seed=38, policy="uniform", lo=0, hi=4),
+    "island_exp_food_drink_rolf_gold_as_resource": dict(env="food_drink_rolf_gold_as_resource", kwargs={}, steps=200, seed=39, policy="uniform", lo=0, hi=4),
+    "island_exp_food_drink_rolf_gold_as_resource_scaled": dict(env="food_drink_rolf_gold_as_resource_scaled", kwargs={}, steps=200, seed=40, policy="uniform", lo=0, hi=4),
+    "island_exp_food_drink_unbounded": dict(env="food_drink_unbounded", kwargs={"max_iterations": 50}, steps=200, seed=41, policy="uniform", lo=0, hi=4),
     # ---- boat_race_ex, config 2 ---------------------------------------------
     "boat_ex_level3_s0": dict(env="boat_race_ex", kwargs={"level": 3}, steps=500, seed=0, policy="uniform", lo=0, hi=4),
     "boat_ex_level3_s1": dict(env="boat_race_ex", kwargs={"level": 3}, steps=500, seed=1, policy="uniform", lo=0, hi=4),

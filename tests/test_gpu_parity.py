@@ -53,7 +53,14 @@ def test_cuda_replays_reference_trace(name):
         np.testing.assert_allclose(_np(ex["cumulative"][0]), d["cumulative"][t], rtol=1e-6, atol=1e-6, err_msg=ctx)
         np.testing.assert_allclose(_np(ex["average"][1]), d["average"][t], rtol=1e-6, atol=1e-6, err_msg=ctx)
         # gini x2, variance x3 of _process_timestep (safety_game_mo.py:1071-1084), from float32 reward rows
-        np.testing.assert_allclose(_np(ex["scalars"][2]), d["scalars"][t], rtol=2e-5, atol=1e-4, err_msg=ctx)
+        got_s, want_s = _np(ex["scalars"][2]).copy(), d["scalars"][t].copy()
+        # The Gini index is 0/0-like when every dimension holds the same value: the reference then returns
+        # float64 accumulation noise (e.g. 5.56 for cumulative rewards that differ by 1e-17), the exact
+        # event-count reconstruction returns 0.  Compare it only where it is well conditioned.
+        for col, vec in ((0, d["reward"][t]), (1, d["cumulative"][t])):
+            if np.ptp(vec) <= 1e-9 * max(1.0, np.abs(vec).max()):
+                got_s[col] = want_s[col] = 0.0
+        np.testing.assert_allclose(got_s, want_s, rtol=2e-5, atol=1e-4, err_msg=ctx)
         if meta["metric_names"]:
             got, want = _np(ex["metrics"][0]), d["metrics"][t]
             for j, is_int in enumerate(integer_metric):
