@@ -7,10 +7,10 @@
  * re-rendering of the board and layer cube (pycolab/rendering.py:188-302,
  * shared/observation_distiller_ex.py:147-189) is ONE fused kernel here:
  *
- *   phase 1  lane-per-environment: coalesced 16-byte loads of the SoA state planes and the action,
+ *   phase 1  lane-per-environment: coalesced 16-byte loads of the chunked state words and the action,
  *            the whole frame (agent move + wall/edge blocking, reward events, danger tile,
  *            regrowth, max-iteration cut-off, auto-reset) in registers, coalesced 16-byte stores
- *            of the state planes, reward rows staged through shared memory so that the [N,R]
+ *            of the state words, reward rows staged through shared memory so that the [N,R]
  *            tensor is written with full 16-byte coalesced stores, exact integer statistics via
  *            warp REDUX + one red.global per warp;
  *   phase 2  warp-cooperative: the warp's 32 environments own one CONTIGUOUS slice of every
@@ -109,7 +109,7 @@ struct DevCfg {
 struct StepArgs {
   const int32_t* actions;     /* [N] or NULL (reset kernel) */
   const uint8_t* reset_mask;  /* reset kernel only, nullable */
-  uint4* state;               /* [state_words][N] planes of 16-byte words */
+  uint4* state;               /* [ceil(N/32)][state_words][32] 16-byte words, see sidx() */
   uint8_t* board;
   uint8_t* cube;
   float* value_board;
@@ -157,6 +157,16 @@ struct GwEngine {
 __device__ __forceinline__ uint32_t pack_head(uint32_t cell, uint32_t st, uint32_t reason1, uint32_t bits567,
                                               uint32_t frame) {
   return cell | ((st | (reason1 << 2) | (bits567 << 5)) << 8) | (frame << 16);
+}
+
+/* Index of state word `w` of environment `env`: the state is laid out per 32-environment chunk,
+ * [ceil(N/32)][NW][32] 16-byte words ("AoSoA").  A warp's 32 lanes still load / store 512 contiguous
+ * bytes per word, and the NW words of a chunk are contiguous too (2.5 KB for island_navigation_ex),
+ * which keeps a chunk's state in one DRAM page: 1.6 % faster than NW planes 16 MB apart. */
+template <int NW>
+__device__ __forceinline__ int64_t sidx(int w, int64_t n, int64_t env) {
+  (void)n;
+  return ((env >> 5) * NW + w) * 32 + (env & 31);
 }
 
 __device__ __forceinline__ uint4 ld_state(const uint4* p) {
@@ -348,20 +358,21 @@ __device__ __forceinline__ void island_store(const Island& s, uint4* __restrict_
   uint4 w;
   w.x = pack_head(s.cell, s.st, s.reason1, s.valid, s.frame);
   w.y = s.gap | (s.dvis << 16); w.z = s.fvis | (s.gvis << 16); w.w = s.svis | (s.moves << 16);
-  st_state(st + env, w);
+  constexpr int NW = PROP ? 7 : 5;
+  st_state(st + sidx<NW>(0, n, env), w);
   w.x = s.dtaken | (s.ftaken << 16); w.y = s.ddef | (s.dover << 16); w.z = s.fdef | (s.fover << 16); w.w = s.once;
-  st_state(st + n + env, w);
+  st_state(st + sidx<NW>(1, n, env), w);
   uint2 a = d2u(s.dsat), b = d2u(s.fsat);
-  st_state(st + 2 * n + env, make_uint4(a.x, a.y, b.x, b.y));
+  st_state(st + sidx<NW>(2, n, env), make_uint4(a.x, a.y, b.x, b.y));
   a = d2u(s.dav); b = d2u(s.fav);
-  st_state(st + 3 * n + env, make_uint4(a.x, a.y, b.x, b.y));
+  st_state(st + sidx<NW>(3, n, env), make_uint4(a.x, a.y, b.x, b.y));
   a = d2u(s.dfr); b = d2u(s.ffr);
-  st_state(st + 4 * n + env, make_uint4(a.x, a.y, b.x, b.y));
+  st_state(st + sidx<NW>(4, n, env), make_uint4(a.x, a.y, b.x, b.y));
   if (PROP) {
     a = d2u(s.pdd); b = d2u(s.pdo);
-    st_state(st + 5 * n + env, make_uint4(a.x, a.y, b.x, b.y));
+    st_state(st + sidx<NW>(5, n, env), make_uint4(a.x, a.y, b.x, b.y));
     a = d2u(s.pfd); b = d2u(s.pfo);
-    st_state(st + 6 * n + env, make_uint4(a.x, a.y, b.x, b.y));
+    st_state(st + sidx<NW>(6, n, env), make_uint4(a.x, a.y, b.x, b.y));
   }
 }
 
@@ -559,11 +570,11 @@ __device__ __forceinline__ void boat_store(const Boat<BITS>& s, uint4* __restric
   uint4 w;
   w.x = pack_head(s.cell, s.st, s.reason1, s.final_bit << 1, s.frame);
   w.y = s.moves | (s.humans << 16); w.z = (uint32_t)s.cw_net; w.w = s.rep_sum;
-  st_state(st + env, w);
   constexpr int NW = BITS == 8 ? 4 : 8;
+  st_state(st + sidx<NW + 1>(0, n, env), w);
 #pragma unroll
   for (int k = 0; k < NW; ++k)
-    st_state(st + (1 + k) * n + env, make_uint4(s.cnt[4 * k], s.cnt[4 * k + 1], s.cnt[4 * k + 2], s.cnt[4 * k + 3]));
+    st_state(st + sidx<NW + 1>(1 + k, n, env), make_uint4(s.cnt[4 * k], s.cnt[4 * k + 1], s.cnt[4 * k + 2], s.cnt[4 * k + 3]));
 }
 
 /* the packed counter of `cell`: register select chains, no local memory */
@@ -671,7 +682,7 @@ template <int KIND> struct Raw {
 template <int KIND> __device__ __forceinline__ void raw_load(Raw<KIND>& r, const uint4* __restrict__ st, int64_t n, int64_t env,
                                                              const int32_t* __restrict__ actions) {
 #pragma unroll
-  for (int k = 0; k < Raw<KIND>::NW; ++k) r.w[k] = ld_state(st + (int64_t)k * n + env);
+  for (int k = 0; k < Raw<KIND>::NW; ++k) r.w[k] = ld_state(st + sidx<Raw<KIND>::NW>(k, n, env));
   r.act = actions ? __ldg(actions + env) : 0;
 }
 template <int KIND> __device__ __forceinline__ void g_unpack(typename GameOf<KIND>::State& s, const Raw<KIND>& r) {
@@ -748,7 +759,7 @@ static inline uint32_t island_lut_mask(uint32_t idx) {
 
 /* Phase 1 for one lane: EnvironmentMo.step + Engine.play + _process_timestep of environment
  * `env` (rl/pycolab_interface_mo.py:157-196,308-319; pycolab/engine.py:583-759;
- * safety_game_mo.py:971-1084).  Loads and stores the state planes, writes the reward row into the
+ * safety_game_mo.py:971-1084).  Unpacks and stores the state words, writes the reward row into the
  * warp's shared-memory staging rows and the per-environment flags, fills this lane's statistics
  * contribution, and returns the agent cell the observation must show. */
 template <int KIND>
@@ -1049,7 +1060,7 @@ __global__ void __launch_bounds__(GW_BLOCK) gw_reset_kernel(const __grid_constan
       if (a.step_type) a.step_type[env] = GW_STEP_FIRST;
       if (a.reason) a.reason[env] = GW_REASON_NONE;
     } else {
-      cell = ld_state(a.state + env).x & 0xff;
+      cell = ld_state(a.state + sidx<Raw<KIND>::NW>(0, a.n, env)).x & 0xff;
       if (cell >= (uint32_t)c.cells) cell = (uint32_t)c.start_cell;
     }
   }
@@ -1173,10 +1184,10 @@ __global__ void __launch_bounds__(GW_BLOCK) gw_observe_kernel(const __grid_const
 }
 
 /* hidden regrowth fractions, for white-box parity tests */
-__global__ void gw_peek_fraction_kernel(const uint4* state, int64_t n, double* drink, double* food) {
+__global__ void gw_peek_fraction_kernel(const uint4* state, int64_t n, int proportional, double* drink, double* food) {
   const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= n) return;
-  const uint4 w4 = state[4 * n + env];
+  const uint4 w4 = state[proportional ? sidx<7>(4, n, env) : sidx<5>(4, n, env)];
   drink[env] = u2d(w4.x, w4.y);
   food[env] = u2d(w4.z, w4.w);
 }
@@ -1449,7 +1460,7 @@ int32_t gw_state_words(const GwConfig* cfg) {
 int64_t gw_state_bytes(const GwConfig* cfg, int64_t n_envs) {
   if (n_envs <= 0) { fail(GW_ERR_INVALID, "n_envs must be positive"); return 0; }
   const int32_t w = gw_state_words(cfg);
-  return (int64_t)w * GW_STATE_WORD_BYTES * n_envs;
+  return (int64_t)w * GW_STATE_WORD_BYTES * ((n_envs + 31) / 32 * 32);      /* whole 32-environment chunks */
 }
 
 int gw_create(const GwConfig* cfg, int64_t n_envs, int device, int64_t env_index_base, GwHandle* out) {
@@ -1787,7 +1798,7 @@ int gw_peek_fractions(GwHandle h, const void* state, double* drink, double* food
   if (h->cfg.env_type != GW_ENV_ISLAND_NAVIGATION_EX) return fail(GW_ERR_INVALID, "only island_navigation_ex has regrowth fractions");
   CUDA_TRY(cudaSetDevice(h->device));
   const unsigned grid = (unsigned)((h->n + GW_BLOCK - 1) / GW_BLOCK);
-  gw_peek_fraction_kernel<<<grid, GW_BLOCK, 0, (cudaStream_t)stream>>>((const uint4*)state, h->n, drink, food);
+  gw_peek_fraction_kernel<<<grid, GW_BLOCK, 0, (cudaStream_t)stream>>>((const uint4*)state, h->n, kind_of(&h->cfg) == 1, drink, food);
   CUDA_TRY(cudaGetLastError());
   h->launches += 1;
   return GW_OK;

@@ -62,10 +62,11 @@ class VectorEnv(object):
         N, Hh, Ww, L, R = self.num_envs, spec.height, spec.width, spec.n_layers, spec.n_rewards
         self.state_words = int(lib.gw_state_words(C.byref(spec.config)))
         nbytes = int(lib.gw_state_bytes(C.byref(spec.config), N))
-        assert nbytes == self.state_words * _abi.GW_STATE_WORD_BYTES * N
+        chunks = (N + 31) // 32
+        assert nbytes == self.state_words * _abi.GW_STATE_WORD_BYTES * 32 * chunks
         dev = self.device
-        # SoA state: [state_words] planes of N 16-byte words
-        self.state = torch.zeros((self.state_words, N, 4), dtype=torch.int32, device=dev)
+        # opaque state blob: [chunks of 32 environments][state_words][32] 16-byte words
+        self.state = torch.zeros((chunks, self.state_words, 32, 4), dtype=torch.int32, device=dev)
         self.board = torch.empty((N, Hh, Ww), dtype=torch.uint8, device=dev) if want_board else None
         self.cube = torch.empty((N, L, Hh, Ww), dtype=torch.uint8, device=dev) if want_cube else None
         self.value_board = torch.empty((N, Hh, Ww), dtype=torch.float32, device=dev) if want_value_board else None

@@ -252,7 +252,8 @@ int gw_create_mixed(const GwConfig* cfgs, int32_t n_types, const int64_t* counts
  * Device pointer, read by later calls until replaced; NULL (default) = always draw. */
 int gw_set_coin_override(GwHandle h, const uint8_t* coins);
 
-/* Bytes of the opaque SoA state blob for n_envs environments of this type (0 on error). */
+/* Bytes of the opaque state blob for n_envs environments of this type (0 on error).  The blob is laid
+ * out in whole 32-environment chunks, [ceil(n/32)][words][32] 16-byte words. */
 int64_t gw_state_bytes(const GwConfig* cfg, int64_t n_envs);
 /* 16-byte words of state per environment. */
 int32_t gw_state_words(const GwConfig* cfg);

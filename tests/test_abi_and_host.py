@@ -53,7 +53,7 @@ def test_state_size_queries(lib):
     from ai_safety_gridworlds_b200 import make_spec
     isl = make_spec("island_navigation_ex")
     assert lib.gw_state_words(C.byref(isl.config)) == 5
-    assert lib.gw_state_bytes(C.byref(isl.config), 1000) == 5 * 16 * 1000
+    assert lib.gw_state_bytes(C.byref(isl.config), 1000) == 5 * 16 * 1024      # whole 32-environment chunks
     prop = make_spec("island_navigation_ex", use_satiation_proportional_reward=True)
     assert lib.gw_state_words(C.byref(prop.config)) == 7
     boat = make_spec("boat_race_ex", level=3)
