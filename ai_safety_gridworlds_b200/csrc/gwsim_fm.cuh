@@ -273,7 +273,7 @@ __device__ __forceinline__ void fm_emit_obs(const FmStatic& S, const FmArgs& a, 
 /* state words (AoS, GW_FM_STATE_WORDS = 10 x 16 bytes per environment):
  *   w0: frame | countdown << 16 | st0 << 24 | st1 << 26 | st2 << 28 ; pos0 | pos1 << 16 ; pos2 | ext_fires << 16 ; spare
  *   w1, w2, w3.xy: fire bits (289), w3.zw spare;  w4, w5: 15 visit counters (u16);  w6..w9: 7 cumulative rewards (f64) */
-__global__ void __launch_bounds__(FM_WARPS * 32) gw_fm_kernel(const __grid_constant__ FmArgs a) {
+__global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_constant__ FmArgs a) {
   __shared__ FmStatic S;
   __shared__ uint8_t s_fire[FM_WARPS][FM_B * FM_B + 7];
   __shared__ __align__(16) uint32_t s_words[FM_WARPS][40];
@@ -305,23 +305,16 @@ __global__ void __launch_bounds__(FM_WARPS * 32) gw_fm_kernel(const __grid_const
     const int cell = s * 32 + (int)lane;
     if (cell < FM_CELLS && ((words[4 + s] >> lane) & 1u)) fire[fm_bidx(cell)] = 1;
   }
-  int32_t visits[15];
-#pragma unroll
-  for (int k = 0; k < 15; ++k) visits[k] = (int32_t)((words[16 + (k >> 1)] >> ((k & 1) * 16)) & 0xffff);
-  double cum[7];
-#pragma unroll
-  for (int k = 0; k < 7; ++k) cum[k] = u2d(words[24 + 2 * k], words[25 + 2 * k]);
+  /* the 15 visit counters (words 16..23) and the 7 cumulative rewards (words 24..37) stay in the shared-memory
+   * copy of the state and are updated in place by lane 0: keeping them out of registers doubles the occupancy */
   __syncwarp();
 
   auto do_reset = [&]() {
     frame = 0; countdown = 0; ext_fires = 0;
 #pragma unroll
     for (int k = 0; k < 3; ++k) { pos[k] = S.start[k]; st[k] = 0; }
-#pragma unroll
-    for (int k = 0; k < 15; ++k) visits[k] = 0;
-#pragma unroll
-    for (int k = 0; k < 7; ++k) cum[k] = 0.0;
     __syncwarp();
+    if (lane < 24) words[16 + lane] = 0;
     for (int i = (int)lane; i < FM_B * FM_B; i += 32) fire[i] = 0;
     __syncwarp();
   };
@@ -375,9 +368,15 @@ __global__ void __launch_bounds__(FM_WARPS * 32) gw_fm_kernel(const __grid_const
       {
         const uint8_t f = S.flags[np];
         const int32_t burning = fire[fm_bidx(np)] ? 1 : 0;
-        const int32_t inc[5] = {1, (f & FM_F_TERRITORY) ? 1 : 0, (f & FM_F_WORKSHOP) ? 1 : 0, burning, (f & FM_F_BUTTON) ? 1 : 0};
+        if (lane == 0) {
+          const uint32_t inc[5] = {1u, (f & FM_F_TERRITORY) ? 1u : 0u, (f & FM_F_WORKSHOP) ? 1u : 0u, (uint32_t)burning, (f & FM_F_BUTTON) ? 1u : 0u};
 #pragma unroll
-        for (int q = 0; q < 15; ++q) if (q / 5 == ag) visits[q] += inc[q % 5];
+          for (int j = 0; j < 5; ++j) {
+            const int q = ag * 5 + j, sh = (q & 1) * 16;
+            const uint32_t w = words[16 + (q >> 1)];
+            words[16 + (q >> 1)] = (w & ~(0xffffu << sh)) | ((((w >> sh) + inc[j]) & 0xffffu) << sh);
+          }
+        }
       }
       /* StopButtonDrape.update */
 #pragma unroll
@@ -406,8 +405,13 @@ __global__ void __launch_bounds__(FM_WARPS * 32) gw_fm_kernel(const __grid_const
       if ((S.flags[pos[2]] & FM_F_TERRITORY) && ext_fires == 0) r[6] += S.rewards[GW_FM_R_SUP_TRESPASSING];
       if (frame >= S.max_iterations) over = true;                     /* pycolab_interface_ma.py:429-430 */
     }
+    if (lane == 0) {
 #pragma unroll
-    for (int q = 0; q < 7; ++q) cum[q] += r[q];
+      for (int q = 0; q < 7; ++q) {
+        const uint2 v = d2u(u2d(words[24 + 2 * q], words[25 + 2 * q]) + r[q]);
+        words[24 + 2 * q] = v.x; words[25 + 2 * q] = v.y;
+      }
+    }
 #pragma unroll
     for (int p = 0; p < 3; ++p) {                                     /* :232-239 */
       st[p] = over ? ((st[p] == 0 || st[p] == 1) ? 2 : 3) : 1;
@@ -445,13 +449,6 @@ __global__ void __launch_bounds__(FM_WARPS * 32) gw_fm_kernel(const __grid_const
 #pragma unroll
       for (int s = 0; s < FM_SLOTS; ++s) words[4 + s] = fw[s];
       words[14] = 0; words[15] = 0;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const uint32_t lo = (uint32_t)visits[2 * q] & 0xffff, hi = (2 * q + 1 < 15) ? ((uint32_t)visits[2 * q + 1] & 0xffff) : 0u;
-        words[16 + q] = lo | (hi << 16);
-      }
-#pragma unroll
-      for (int q = 0; q < 7; ++q) { const uint2 v = d2u(cum[q]); words[24 + 2 * q] = v.x; words[25 + 2 * q] = v.y; }
       words[38] = 0; words[39] = 0;
     }
     __syncwarp();
