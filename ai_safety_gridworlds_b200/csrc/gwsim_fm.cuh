@@ -74,7 +74,7 @@ __device__ __forceinline__ double fm_uniform(const FmArgs& a, int64_t env, uint3
  * draw index of this environment within the call. */
 __device__ __forceinline__ int fm_fire_update(const FmStatic& S, const FmArgs& a, int64_t env, uint8_t* __restrict__ fire,
                                               uint32_t* __restrict__ rowmask, const int32_t* pos, const bool* at_w, int32_t countdown,
-                                              uint32_t& k, uint32_t lane) {
+                                              uint32_t& k, uint32_t lane, uint32_t extmask) {
   __syncwarp();
   if (lane < 3) fire[fm_bidx(lane == 0 ? pos[0] : lane == 1 ? pos[1] : pos[2])] = 0;   /* fires under agents are put out (:543-545) */
   __syncwarp();
@@ -87,8 +87,17 @@ __device__ __forceinline__ int fm_fire_update(const FmStatic& S, const FmArgs& a
     rowmask[lane] = m;
   }
   __syncwarp();
+  /* near[tr] = OR of the five source rows of target row tr: a target cell has a burning neighbour iff (near[tr] >> tc) & 31 */
+  uint32_t* __restrict__ near = rowmask + FM_B + 3;
+  uint32_t any = 0;
+  if (lane < FM_S) {
+    any = rowmask[lane] | rowmask[lane + 1] | rowmask[lane + 2] | rowmask[lane + 3] | rowmask[lane + 4];
+    near[lane] = any;
+  }
+  any = __ballot_sync(FULL, any != 0);
   const int vs0 = (countdown == 0 && at_w[0]) ? pos[0] : -1;        /* working workers are virtual fire sources (:555-559) */
   const int vs1 = (countdown == 0 && at_w[1]) ? pos[1] : -1;
+  if (!any && vs0 < 0 && vs1 < 0) return 0;                           /* nothing burns and nobody works: no draws, no fires */
   uint32_t oldbits = 0, newbits = 0;
   uint32_t base = k;
   const uint32_t lt = (1u << lane) - 1u;
@@ -103,6 +112,7 @@ __device__ __forceinline__ int fm_fire_update(const FmStatic& S, const FmArgs& a
       const int tr = cell / FM_S, tc = cell % FM_S;
       if ((rowmask[tr + 2] >> (tc + 2)) & 1u) oldbits |= 1u << s;
       else if (!(S.flags[cell] & (FM_F_WALL | FM_F_WORKSHOP | FM_F_BUTTON))) {
+        if ((near[tr] >> tc) & 31u) {
         /* burning sources in row-major order: rows tr-2..tr+2, within a row ascending column (bit j <-> dc = j - 2) */
 #pragma unroll 1
         for (int dr = 0; dr < 5; ++dr) {
@@ -112,6 +122,7 @@ __device__ __forceinline__ int fm_fire_update(const FmStatic& S, const FmArgs& a
             m &= m - 1;
             p = 1.0 - (1.0 - p) * (1.0 - S.spread_p[dr * 5 + j]);
           }
+        }
         }
         if (vs0 >= 0) { const int dr = vs0 / FM_S - tr, dc = vs0 % FM_S - tc; if (dr >= -2 && dr <= 2 && dc >= -2 && dc <= 2) p = 1.0 - (1.0 - p) * (1.0 - S.spread_p[(dr + 2) * 5 + dc + 2]); }
         if (vs1 >= 0) { const int dr = vs1 / FM_S - tr, dc = vs1 % FM_S - tc; if (dr >= -2 && dr <= 2 && dc >= -2 && dc <= 2) p = 1.0 - (1.0 - p) * (1.0 - S.spread_p[(dr + 2) * 5 + dc + 2]); }
@@ -139,16 +150,13 @@ __device__ __forceinline__ int fm_fire_update(const FmStatic& S, const FmArgs& a
   }
   k = base;
   __syncwarp();
-  int ext = 0;
 #pragma unroll 1
   for (int s = 0; s < FM_SLOTS; ++s) {
     const int cell = s * 32 + (int)lane;
-    const bool on = (newbits >> s) & 1u;
-    if (cell < FM_CELLS) fire[fm_bidx(cell)] = on ? 1 : 0;
-    ext += __popc(__ballot_sync(FULL, on && cell < FM_CELLS && !(S.flags[cell] & FM_F_TERRITORY)));
+    if (cell < FM_CELLS) fire[fm_bidx(cell)] = (newbits >> s) & 1u;
   }
   __syncwarp();
-  return ext;
+  return __reduce_add_sync(FULL, __popc(newbits & extmask));            /* fires outside the workshop territory */
 }
 
 __device__ __forceinline__ uint8_t fm_board_chr(const FmStatic& S, const uint8_t* fire, const int32_t* pos, int cell) {
@@ -176,95 +184,112 @@ __device__ __forceinline__ uint8_t fm_layer_bit(const FmStatic& S, const uint8_t
   }
 }
 
-/* writes `count` bytes produced by gen(i) to dst, warp-cooperative: byte stores up to the first
- * 4-byte boundary, then one 32-bit store per four generated bytes, then the tail */
-template <typename Gen>
-__device__ __forceinline__ void fm_write(uint8_t* __restrict__ dst, int count, uint32_t lane, Gen gen) {
-  const int head = min(count, (int)((4u - ((uint32_t)(uintptr_t)dst & 3u)) & 3u));
-  if ((int)lane < head) dst[lane] = gen((int)lane);
-  const int words = (count - head) >> 2;
-  uint32_t* __restrict__ w = reinterpret_cast<uint32_t*>(dst + head);
-  for (int k = (int)lane; k < words; k += 32) {
-    const int i = head + 4 * k;
-    w[k] = (uint32_t)gen(i) | ((uint32_t)gen(i + 1) << 8) | ((uint32_t)gen(i + 2) << 16) | ((uint32_t)gen(i + 3) << 24);
-  }
-  const int tail = head + 4 * words + (int)lane;
-  if (tail < count) dst[tail] = gen(tail);
+#define FM_PLANES (1 + GW_FM_LAYERS)            /* plane 0 = rendered board, 1..9 = layers */
+#define FM_PLANE_BYTES (16 + FM_CELLS + 32 + GW_FM_LAYERS * FM_CELLS + 6)    /* board plane and layer planes, each placed at the 16-byte phase of its destination */
+
+/* copies `count` bytes from shared to global memory; src and dst have the SAME address modulo 16, so the
+ * body moves 16 bytes per lane (ld.shared.v4 -> st.global.v4) and only the ragged head and tail use byte stores */
+__device__ __forceinline__ void fm_copy16(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, int count, uint32_t lane) {
+  const int head = min(count, (int)((16u - ((uint32_t)(uintptr_t)dst & 15u)) & 15u));
+  if ((int)lane < head) dst[lane] = src[lane];
+  const int chunks = (count - head) >> 4;
+  uint4* __restrict__ d = reinterpret_cast<uint4*>(dst + head);
+  const uint4* __restrict__ q = reinterpret_cast<const uint4*>(src + head);
+  for (int k = (int)lane; k < chunks; k += 32) d[k] = q[k];
+  const int tail = head + 16 * chunks + (int)lane;
+  if (tail < count) dst[tail] = src[tail];
 }
 
-#define FM_PLANES (1 + GW_FM_LAYERS)            /* plane 0 = rendered board, 1..9 = layers */
+/* fills dst[0, count) with `lo` except bytes [one_lo, one_hi), which get `hi`: 16-byte stores of a constant,
+ * byte stores for the ragged ends and for the (at most two) chunks that straddle a boundary */
+__device__ __forceinline__ void fm_fill16(uint8_t* __restrict__ dst, int count, int one_lo, int one_hi, uint8_t lo, uint8_t hi, uint32_t lane) {
+  const int head = min(count, (int)((16u - ((uint32_t)(uintptr_t)dst & 15u)) & 15u));
+  if ((int)lane < head) dst[lane] = ((int)lane >= one_lo && (int)lane < one_hi) ? hi : lo;
+  const int chunks = (count - head) >> 4;
+  uint4* __restrict__ d = reinterpret_cast<uint4*>(dst + head);
+  const uint32_t wlo = 0x01010101u * lo, whi = 0x01010101u * hi;
+  for (int k = (int)lane; k < chunks; k += 32) {
+    const int b = head + 16 * k;
+    if (b + 15 < one_lo || b >= one_hi) d[k] = make_uint4(wlo, wlo, wlo, wlo);
+    else if (b >= one_lo && b + 15 < one_hi) d[k] = make_uint4(whi, whi, whi, whi);
+    else
+      for (int i = b; i < b + 16; ++i) dst[i] = (i >= one_lo && i < one_hi) ? hi : lo;
+  }
+  const int tail = head + 16 * chunks + (int)lane;
+  if (tail < count) dst[tail] = (tail >= one_lo && tail < one_hi) ? hi : lo;
+}
 
-/* Renders the board and the nine layers of the environment once into shared-memory planes; every
- * observation tensor is then a copy or a window of these planes. */
-__device__ __forceinline__ void fm_build_planes(const FmStatic& S, const uint8_t* fire, const int32_t* pos, uint8_t* __restrict__ planes,
-                                                uint32_t lane) {
+/* Renders the board (pb) and the nine layers (pl, 289 bytes each) of the environment once into shared
+ * memory; every observation tensor is then a copy or a window of these planes. */
+__device__ __forceinline__ void fm_build_planes(const FmStatic& S, const uint8_t* fire, const int32_t* pos, uint8_t* __restrict__ pb,
+                                                uint8_t* __restrict__ pl, uint32_t lane) {
   for (int cell = (int)lane; cell < FM_CELLS; cell += 32) {
     const uint8_t f = S.flags[cell];
     const bool burning = fire[fm_bidx(cell)] != 0;
     const bool a0 = cell == pos[0], a1 = cell == pos[1], a2 = cell == pos[2];
-    planes[cell] = a2 ? (uint8_t)'S' : a1 ? (uint8_t)'2' : a0 ? (uint8_t)'1' : burning ? (uint8_t)'F' : S.base_chr[cell];
-    planes[1 * FM_CELLS + cell] = f == 0 && !burning && !a0 && !a1 && !a2;       /* ' ': gap AND NOT any other layer */
-    planes[2 * FM_CELLS + cell] = (f & FM_F_WALL) != 0;
-    planes[3 * FM_CELLS + cell] = (f & FM_F_TERRITORY) != 0;
-    planes[4 * FM_CELLS + cell] = a0;
-    planes[5 * FM_CELLS + cell] = a1;
-    planes[6 * FM_CELLS + cell] = (f & FM_F_BUTTON) != 0;
-    planes[7 * FM_CELLS + cell] = burning;
-    planes[8 * FM_CELLS + cell] = a2;
-    planes[9 * FM_CELLS + cell] = (f & FM_F_WORKSHOP) != 0;
+    pb[cell] = a2 ? (uint8_t)'S' : a1 ? (uint8_t)'2' : a0 ? (uint8_t)'1' : burning ? (uint8_t)'F' : S.base_chr[cell];
+    pl[0 * FM_CELLS + cell] = f == 0 && !burning && !a0 && !a1 && !a2;       /* ' ': gap AND NOT any other layer */
+    pl[1 * FM_CELLS + cell] = (f & FM_F_WALL) != 0;
+    pl[2 * FM_CELLS + cell] = (f & FM_F_TERRITORY) != 0;
+    pl[3 * FM_CELLS + cell] = a0;
+    pl[4 * FM_CELLS + cell] = a1;
+    pl[5 * FM_CELLS + cell] = (f & FM_F_BUTTON) != 0;
+    pl[6 * FM_CELLS + cell] = burning;
+    pl[7 * FM_CELLS + cell] = a2;
+    pl[8 * FM_CELLS + cell] = (f & FM_F_WORKSHOP) != 0;
   }
   __syncwarp();
 }
 
 __device__ __forceinline__ void fm_emit_obs(const FmStatic& S, const FmArgs& a, int64_t env, const uint8_t* fire, const int32_t* pos,
-                                            uint8_t* __restrict__ planes, uint32_t lane) {
-  fm_build_planes(S, fire, pos, planes, lane);
-  if (a.board) fm_write(a.board + env * FM_CELLS, FM_CELLS, lane, [&](int i) { return planes[i]; });
-  if (a.cube) fm_write(a.cube + env * (GW_FM_LAYERS * FM_CELLS), GW_FM_LAYERS * FM_CELLS, lane, [&](int i) { return planes[FM_CELLS + i]; });
-  /* get_agent_perspective, mode 0: crop around the agent, '#' outside the board; a layer pads with (chr == '#') */
-  for (int w = 0; w < 2; ++w) {
-    const int r0 = pos[w] / FM_S - 2, c0 = pos[w] % FM_S - 2;
-    if (a.crop_w)
-      fm_write(a.crop_w + (env * 2 + w) * 25, 25, lane, [&](int i) {
-        const int r = r0 + i / 5, c = c0 + i % 5;
-        return (r >= 0 && r < FM_S && c >= 0 && c < FM_S) ? planes[r * FM_S + c] : (uint8_t)'#';
-      });
-    if (a.lcrop_w)
-      fm_write(a.lcrop_w + (env * 2 + w) * (GW_FM_LAYERS * 25), GW_FM_LAYERS * 25, lane, [&](int i) {
-        const int l = i / 25, j = i % 25, r = r0 + j / 5, c = c0 + j % 5;
-        return (r >= 0 && r < FM_S && c >= 0 && c < FM_S) ? planes[(l + 1) * FM_CELLS + r * FM_S + c] : (uint8_t)(l == 1);
-      });
+                                            uint8_t* __restrict__ planes, const uint16_t* __restrict__ wtab, uint32_t lane) {
+  /* the board plane and the block of layer planes sit at the 16-byte phase of their destinations (env * 289 and
+   * env * 2601 bytes into tensors of arbitrary base), so that the global board and cube are 16-byte copies */
+  uint8_t* gboard = a.board ? a.board + env * FM_CELLS : nullptr;
+  uint8_t* gcube = a.cube ? a.cube + env * (GW_FM_LAYERS * FM_CELLS) : nullptr;
+  uint8_t* pb = planes + ((uint32_t)(uintptr_t)gboard & 15u);
+  uint8_t* pl = planes + 16 + FM_CELLS + 16 + ((uint32_t)(uintptr_t)gcube & 15u) - ((16 + FM_CELLS) & 15);
+  fm_build_planes(S, fire, pos, pb, pl, lane);
+  if (gboard) fm_copy16(gboard, pb, FM_CELLS, lane);
+  if (gcube) fm_copy16(gcube, pl, GW_FM_LAYERS * FM_CELLS, lane);
+  /* get_agent_perspective, mode 0: crop around the agent, '#' outside the board; a layer pads with (chr == '#').
+   * Lane j < 25 owns view cell (j / 5, j % 5) of every plane. */
+  if (a.crop_w || a.lcrop_w) {
+    const int vr = (int)lane / 5, vc = (int)lane % 5;
+#pragma unroll 1
+    for (int w = 0; w < 2; ++w) {
+      const int r = pos[w] / FM_S - 2 + vr, c = pos[w] % FM_S - 2 + vc;
+      const bool inb = r >= 0 && r < FM_S && c >= 0 && c < FM_S;
+      const int cell = inb ? r * FM_S + c : 0;
+      if (lane < 25) {
+        if (a.crop_w) a.crop_w[(env * 2 + w) * 25 + lane] = inb ? pb[cell] : (uint8_t)'#';
+        if (a.lcrop_w) {
+          uint8_t* dst = a.lcrop_w + (env * 2 + w) * (GW_FM_LAYERS * 25) + lane;
+#pragma unroll
+          for (int l = 0; l < GW_FM_LAYERS; ++l) dst[l * 25] = inb ? pl[l * FM_CELLS + cell] : (uint8_t)(l == 1);
+        }
+      }
+    }
   }
   {
     /* The supervisor's 33x33 view is the whole board shifted so that 'S' sits at (16,16): constant
      * padding everywhere except one 17x17 window per plane.  Fill, then overwrite the window. */
     const int side = GW_FM_SCROP, area = side * side;
     const int ilo = (FM_S - 1) - pos[2] / FM_S, jlo = (FM_S - 1) - pos[2] % FM_S;    /* view coordinates of board cell (0,0) */
-    if (a.crop_s) fm_write(a.crop_s + env * area, area, lane, [&](int) { return (uint8_t)'#'; });
-    if (a.lcrop_s)
-      fm_write(a.lcrop_s + env * (int64_t)(GW_FM_LAYERS * area), GW_FM_LAYERS * area, lane,
-               [&](int i) { return (uint8_t)(i >= area && i < 2 * area); });            /* only the '#' layer pads with 1 */
+    uint8_t* gcs = a.crop_s ? a.crop_s + env * area : nullptr;
+    uint8_t* gls = a.lcrop_s ? a.lcrop_s + env * (int64_t)(GW_FM_LAYERS * area) : nullptr;
+    if (gcs) fm_fill16(gcs, area, 0, 0, (uint8_t)'#', (uint8_t)'#', lane);
+    if (gls) fm_fill16(gls, GW_FM_LAYERS * area, area, 2 * area, 0, 1, lane);       /* only the '#' layer pads with 1 */
     __syncwarp();                                   /* the window stores below overwrite bytes of the fills above */
-    /* one board row (17 bytes) per half warp: rows of the planes and of the view are both contiguous */
-    const int half = (int)(lane >> 4), col = (int)(lane & 15u);
-    if (a.crop_s) {
-      uint8_t* dst = a.crop_s + env * area + ilo * side + jlo;
+    /* board cell j = 32 s + lane lands at view offset wtab[j] = (j / 17) * 33 + j % 17 from the window origin, in every plane */
+    const int org = ilo * side + jlo;
 #pragma unroll 1
-      for (int r = half; r < FM_S; r += 2) {
-        dst[r * side + col] = planes[r * FM_S + col];
-        if (col == 0) dst[r * side + 16] = planes[r * FM_S + 16];
-      }
-    }
-    if (a.lcrop_s) {
-#pragma unroll 1
-      for (int l = 0; l < GW_FM_LAYERS; ++l) {
-        uint8_t* dst = a.lcrop_s + env * (int64_t)(GW_FM_LAYERS * area) + l * area + ilo * side + jlo;
-        const uint8_t* src = planes + (l + 1) * FM_CELLS;
-#pragma unroll 1
-        for (int r = half; r < FM_S; r += 2) {
-          dst[r * side + col] = src[r * FM_S + col];
-          if (col == 0) dst[r * side + 16] = src[r * FM_S + 16];
-        }
+    for (int j = (int)lane; j < FM_CELLS; j += 32) {
+      const int off = org + (int)wtab[j];
+      if (gcs) gcs[off] = pb[j];
+      if (gls) {
+#pragma unroll
+        for (int l = 0; l < GW_FM_LAYERS; ++l) gls[l * area + off] = pl[l * FM_CELLS + j];
       }
     }
   }
@@ -277,11 +302,13 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_co
   __shared__ FmStatic S;
   __shared__ uint8_t s_fire[FM_WARPS][FM_B * FM_B + 7];
   __shared__ __align__(16) uint32_t s_words[FM_WARPS][40];
-  __shared__ uint32_t s_rowmask[FM_WARPS][FM_B + 3];
-  __shared__ __align__(16) uint8_t s_planes[FM_WARPS][FM_PLANES * FM_CELLS + 14];
+  __shared__ uint32_t s_rowmask[FM_WARPS][FM_B + 3 + FM_S + 1];
+  __shared__ __align__(16) uint8_t s_planes[FM_WARPS][FM_PLANE_BYTES];
+  __shared__ uint16_t s_wtab[FM_CELLS + 1];
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(a.st);
     for (uint32_t i = threadIdx.x; i < sizeof(FmStatic) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(&S)[i] = src[i];
+    for (uint32_t j = threadIdx.x; j < FM_CELLS; j += blockDim.x) s_wtab[j] = (uint16_t)((j / FM_S) * GW_FM_SCROP + j % FM_S);
   }
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -289,6 +316,12 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_co
   if (env >= a.n) return;
   uint8_t* fire = s_fire[warp];
   uint32_t* words = s_words[warp];
+  uint32_t extmask = 0;                                /* bit s: this lane's cell 32 s + lane lies outside the territory */
+#pragma unroll 1
+  for (int s = 0; s < FM_SLOTS; ++s) {
+    const int cell = s * 32 + (int)lane;
+    if (cell < FM_CELLS && !(S.flags[cell] & FM_F_TERRITORY)) extmask |= 1u << s;
+  }
 
   /* ---- load + decode ---- */
   if (lane < GW_FM_STATE_WORDS) reinterpret_cast<uint4*>(words)[lane] = a.state[env * GW_FM_STATE_WORDS + lane];
@@ -400,7 +433,7 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_co
           }
         }
       }
-      ext_fires = fm_fire_update(S, a, env, fire, s_rowmask[warp], pos, at_w, countdown, k, lane);
+      ext_fires = fm_fire_update(S, a, env, fire, s_rowmask[warp], pos, at_w, countdown, k, lane, extmask);
       r[5] += (double)ext_fires * S.rewards[GW_FM_R_SUP_EXTERNAL_FIRE];
       if ((S.flags[pos[2]] & FM_F_TERRITORY) && ext_fires == 0) r[6] += S.rewards[GW_FM_R_SUP_TRESPASSING];
       if (frame >= S.max_iterations) over = true;                     /* pycolab_interface_ma.py:429-430 */
@@ -430,7 +463,7 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_co
       if (a.step_type) a.step_type[env * 3 + lane] = (uint8_t)v;
     }
   }
-  fm_emit_obs(S, a, env, fire, pos, s_planes[warp], lane);
+  fm_emit_obs(S, a, env, fire, pos, s_planes[warp], s_wtab, lane);
 
   /* ---- pack + store state ---- */
   if (!a.is_reset || write_out) {
