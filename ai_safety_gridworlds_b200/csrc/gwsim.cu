@@ -1886,6 +1886,9 @@ struct GwFmEngine {
   int device;
   uint64_t seed, call_no;
   FmStatic* d_static;
+  unsigned long long* d_claim;        /* environment-queue counter (monotonic) */
+  unsigned long long claim_base;      /* its value once every launch issued so far has finished */
+  int grid;                           /* resident CTAs of the persistent step kernel */
   int64_t launches;
 };
 
@@ -1964,7 +1967,14 @@ int gw_fm_create(const GwFmConfig* cfg, int64_t n_envs, int device, int64_t env_
   st.button_duration = cfg->stop_button_duration;
   ce = cudaMalloc((void**)&h->d_static, sizeof(FmStatic));
   if (ce == cudaSuccess) ce = cudaMemcpy(h->d_static, &st, sizeof st, cudaMemcpyHostToDevice);
-  if (ce != cudaSuccess) { cudaFree(h->d_static); delete h; return fail(GW_ERR_CUDA, "firemaker tables: %s", cudaGetErrorString(ce)); }
+  h->d_claim = nullptr; h->claim_base = 0;
+  if (ce == cudaSuccess) ce = cudaMalloc((void**)&h->d_claim, sizeof(unsigned long long));
+  if (ce == cudaSuccess) ce = cudaMemset(h->d_claim, 0, sizeof(unsigned long long));
+  int per_sm = 0, sms = 0;
+  if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gw_fm_kernel, FM_WARPS * 32, 0);
+  if (ce == cudaSuccess) ce = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  if (ce != cudaSuccess) { cudaFree(h->d_static); cudaFree(h->d_claim); delete h; return fail(GW_ERR_CUDA, "firemaker tables: %s", cudaGetErrorString(ce)); }
+  h->grid = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 1);
   *out = h;
   return GW_OK;
 }
@@ -1973,6 +1983,7 @@ void gw_fm_destroy(GwFmHandle h) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaFree(h->d_static);
+  cudaFree(h->d_claim);
   delete h;
 }
 
@@ -1986,8 +1997,12 @@ static int fm_launch(GwFmHandle h, FmArgs& a, void* state, const GwFmObs* obs, c
   if (out) { a.reward_w = out->reward_workers; a.reward_s = out->reward_supervisor; a.terminated = out->terminated; a.step_type = out->step_type; }
   a.seed = h->seed; a.call_no = ++h->call_no; a.env_index_base = h->env_index_base; a.n = h->n;
   CUDA_TRY(cudaSetDevice(h->device));
-  const unsigned grid = (unsigned)((h->n + FM_WARPS - 1) / FM_WARPS);
-  gw_fm_kernel<<<grid, FM_WARPS * 32, 0, stream>>>(a);
+  int64_t grid = (h->n + FM_WARPS - 1) / FM_WARPS;
+  if (grid > h->grid) grid = h->grid;                           /* persistent: one wave, warps claim environments */
+  a.claim_counter = h->d_claim;
+  a.claim_base = h->claim_base;
+  h->claim_base += (unsigned long long)h->n + (unsigned long long)grid * FM_WARPS;   /* every environment once + one failing claim per warp */
+  gw_fm_kernel<<<(unsigned)grid, FM_WARPS * 32, 0, stream>>>(a);
   CUDA_TRY(cudaGetLastError());
   h->launches += 1;
   return GW_OK;

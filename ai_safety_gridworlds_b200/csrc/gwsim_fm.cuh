@@ -58,6 +58,8 @@ struct FmArgs {
   uint64_t seed, call_no;
   int64_t env_index_base, n;
   int32_t is_reset, pad;
+  unsigned long long* claim_counter;    /* dynamic environment queue of the persistent kernel */
+  unsigned long long claim_base;
 };
 
 __device__ __forceinline__ int fm_bidx(int cell) { return (cell / FM_S + 2) * FM_B + cell % FM_S + 2; }
@@ -312,8 +314,6 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_co
   }
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const int64_t env = (int64_t)blockIdx.x * FM_WARPS + warp;
-  if (env >= a.n) return;
   uint8_t* fire = s_fire[warp];
   uint32_t* words = s_words[warp];
   uint32_t extmask = 0;                                /* bit s: this lane's cell 32 s + lane lies outside the territory */
@@ -322,6 +322,21 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_co
     const int cell = s * 32 + (int)lane;
     if (cell < FM_CELLS && !(S.flags[cell] & FM_F_TERRITORY)) extmask |= 1u << s;
   }
+  /* Persistent warps, dynamic environment queue: a warp claims one environment at a time with one atomicAdd
+   * (environments with many fires take several times longer than quiet ones; with a static assignment the
+   * warps of a CTA idle until its slowest environment is done).  The counter is never reset: the host passes
+   * the value it has after all earlier launches, and every warp makes exactly one failing claim per launch. */
+  auto claim = [&]() -> int64_t {
+    unsigned long long v = 0;
+    if (lane == 0) v = atomicAdd(a.claim_counter, 1ull) - a.claim_base;
+    return (int64_t)__shfl_sync(FULL, v, 0);
+  };
+  int64_t env_next = claim();
+#pragma unroll 1
+  for (;;) {
+  const int64_t env = env_next;
+  if (env >= a.n) break;
+  env_next = claim();                                  /* consumed after this environment: the atomic's latency is hidden */
 
   /* ---- load + decode ---- */
   if (lane < GW_FM_STATE_WORDS) reinterpret_cast<uint4*>(words)[lane] = a.state[env * GW_FM_STATE_WORDS + lane];
@@ -487,6 +502,8 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_co
     __syncwarp();
     if (lane < GW_FM_STATE_WORDS) a.state[env * GW_FM_STATE_WORDS + lane] = reinterpret_cast<const uint4*>(words)[lane];
   }
+  __syncwarp();
+  }  /* environment queue */
 }
 
 struct FmObserveArgs {
