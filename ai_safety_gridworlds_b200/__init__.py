@@ -9,7 +9,7 @@ from . import _abi  # noqa: F401
 from .envs import make_spec, ENVIRONMENTS  # noqa: F401
 
 __all__ = ["make_spec", "ENVIRONMENTS", "VectorEnv", "ClassicVectorEnv", "FiremakerVectorEnv", "GridworldGymEnv",
-           "GridworldZooParallelEnv"]
+           "GridworldZooParallelEnv", "GridworldZooAecEnv"]
 
 
 def __getattr__(name):
@@ -26,6 +26,9 @@ def __getattr__(name):
     if name == "GridworldZooParallelEnv":
         from .helpers.gridworld_zoo_parallel_env import GridworldZooParallelEnv
         return GridworldZooParallelEnv
+    if name == "GridworldZooAecEnv":
+        from .helpers.gridworld_zoo_aec_env import GridworldZooAecEnv
+        return GridworldZooAecEnv
     if name == "GridworldGymEnv":
         from .helpers.gridworld_gym_env import GridworldGymEnv
         return GridworldGymEnv

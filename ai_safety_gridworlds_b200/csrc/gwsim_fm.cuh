@@ -391,7 +391,8 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_co
     bool over = false;
 #pragma unroll 1
     for (int t = 0; t < 3; ++t) {
-      const int ag = ord[t] < 0 || ord[t] > 2 ? t : ord[t];
+      if (ord[t] < 0) continue;                          /* sub-step left out: an AEC step plays ONE agent's frame (order = {agent, -1, -1}) */
+      const int ag = ord[t] > 2 ? t : ord[t];
       const int32_t act = a.actions[env * 3 + ag];
       frame += 1;
       /* the acting agent: MazeWalker against '#' and the other agents (:399-400), then update_reward (:430-463) */

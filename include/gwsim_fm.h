@@ -100,8 +100,10 @@ int gw_fm_reset(GwFmHandle h, const uint8_t* reset_mask, void* state, const GwFm
 
 /* One PARALLEL step.  actions: int32 [N, 3].  order: int32 [N, 3] = the agent indices in execution
  * order (replays the reference's Generator.shuffle), NULL = Philox permutation when
- * cfg.randomize_order, identity otherwise.  draws: float64 [N, draw_stride] = the uniform draws
- * FireDrape consumes for environment i in this call, in call order (replay of a recorded
+ * cfg.randomize_order, identity otherwise.  An order entry of -1 leaves that sub-step out: {agent, -1, -1}
+ * is the single-agent call EnvironmentMa.step({agent: action}) that GridworldZooAecEnv.step makes
+ * (helpers/gridworld_zoo_aec_env.py:651-652): one engine frame, rewards of that frame for all agents.
+ * draws: float64 [N, draw_stride] = the uniform draws FireDrape consumes for environment i in this call, in call order (replay of a recorded
  * reference run), NULL = Philox draws. */
 int gw_fm_step(GwFmHandle h, const int32_t* actions, const int32_t* order, const double* draws, int64_t draw_stride,
                void* state, const GwFmObs* obs, const GwFmOut* out, void* stream);

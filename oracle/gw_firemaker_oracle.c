@@ -303,6 +303,7 @@ void orf_step(void* h, const int32_t* actions, const int32_t* order, const doubl
     DrawSrc d = {o, i, draws ? draws + i * draw_stride : 0, draw_stride, 0};
     int over = 0;
     for (int k = 0; k < NA; ++k) {
+      if (ord[k] < 0) continue;                                               /* AEC: step({agent: action}) plays one agent's frame only */
       play(o, e, 1, ord[k], actions[i * NA + ord[k]], r, &d);
       if (e->frame >= o->cfg.max_iterations) over = 1;                        /* pycolab_interface_ma.py:429-430 */
     }

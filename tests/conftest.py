@@ -28,7 +28,12 @@ def golden_names():
 
 def firemaker_golden_names():
     """Traces of firemaker_ex_ma (oracle/record_firemaker.py)."""
-    return [n for n in _all_golden() if n.startswith("firemaker_")]
+    return [n for n in _all_golden() if n.startswith("firemaker_") and not n.startswith("firemaker_aec_")]
+
+
+def firemaker_aec_golden_names():
+    """Traces of firemaker_ex_ma through the AEC wrapper, one engine frame per step (oracle/record_firemaker_aec.py)."""
+    return [n for n in _all_golden() if n.startswith("firemaker_aec_")]
 
 
 def classic_golden_names():
