@@ -1,5 +1,5 @@
 """Environment registry: name -> spec compiler (the counterpart of helpers/factory.py:100-201)."""
-from . import boat_race_ex, classic, experiments, firemaker_ex_ma, island_navigation_ex
+from . import boat_race_ex, classic, experiments, firemaker_ex_ma, island_navigation_ex, island_navigation_ex_ma
 
 ENVIRONMENTS = {
     island_navigation_ex.NAME: island_navigation_ex.compile_spec,
@@ -7,6 +7,7 @@ ENVIRONMENTS = {
 }
 ENVIRONMENTS.update(classic.COMPILERS)
 ENVIRONMENTS[firemaker_ex_ma.NAME] = firemaker_ex_ma.compile_spec
+ENVIRONMENTS[island_navigation_ex_ma.NAME] = island_navigation_ex_ma.compile_spec
 ENVIRONMENTS.update(experiments.COMPILERS)
 
 

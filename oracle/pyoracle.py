@@ -249,3 +249,59 @@ class FiremakerOracle(object):
                    pos=np.zeros((n, 3, 2), np.int16), ext_fires=np.zeros(n, np.int32))
         lib().orf_observe(self._h, _p(out["metrics"]), _p(out["cumulative"]), _p(out["frame"]), _p(out["pos"]), _p(out["ext_fires"]))
         return out
+
+
+class IslandMaOracle(object):
+    """N independent island_navigation_ex_ma games (2 agents), oracle/gw_island_ma_oracle.c."""
+
+    def __init__(self, spec, n_envs, env_index_base=0, seed=0):
+        L = lib()
+        L.ori_create.restype = C.c_void_p
+        L.ori_create.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_uint64]
+        L.ori_destroy.argtypes = [C.c_void_p]
+        L.ori_reset.argtypes = [C.c_void_p] + [C.c_void_p] * 8
+        L.ori_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_void_p] * 7
+        L.ori_observe.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+        self.spec, self.n = spec, int(n_envs)
+        self._h = L.ori_create(C.byref(spec.config), self.n, int(env_index_base), int(seed))
+        if not self._h:
+            raise ValueError("oracle rejected the configuration")
+        n, H, W, Lr, R = self.n, spec.height, spec.width, spec.n_layers, spec.n_rewards
+        self.board = np.zeros((n, H, W), np.uint8)
+        self.cube = np.zeros((n, Lr, H, W), np.uint8)
+        self.crop = np.zeros((n, 2, 5, 5), np.uint8)
+        self.lcrop = np.zeros((n, 2, Lr, 5, 5), np.uint8)
+        self.reward = np.zeros((n, 2, R), np.float32)
+        self.terminated = np.zeros((n, 2), np.uint8)
+        self.step_type = np.zeros((n, 2), np.uint8)
+
+    def close(self):
+        if self._h:
+            lib().ori_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _outs(self):
+        return [_p(x) for x in (self.board, self.cube, self.crop, self.lcrop, self.reward, self.terminated, self.step_type)]
+
+    def reset(self, mask=None):
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        lib().ori_reset(self._h, _p(m), *self._outs())
+
+    def step(self, actions, order=None):
+        a = np.ascontiguousarray(actions, np.int32)
+        assert a.shape == (self.n, 2)
+        o = None if order is None else np.ascontiguousarray(order, np.int32)
+        lib().ori_step(self._h, _p(a), _p(o), *self._outs())
+
+    def observe(self):
+        n, R = self.n, self.spec.n_rewards
+        out = dict(metrics=np.zeros((n, 16), np.float64), cumulative=np.zeros((n, 2, R), np.float32), frame=np.zeros(n, np.int32),
+                   pos=np.zeros((n, 2, 2), np.int16), directions=np.zeros((n, 2, 2), np.int8))
+        lib().ori_observe(self._h, _p(out["metrics"]), _p(out["cumulative"]), _p(out["frame"]), _p(out["pos"]), _p(out["directions"]))
+        return out

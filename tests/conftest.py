@@ -23,7 +23,7 @@ def _all_golden():
 
 def golden_names():
     """Traces of the multi-objective games (island_navigation_ex, boat_race_ex)."""
-    return [n for n in _all_golden() if not n.startswith("classic_") and not n.startswith("firemaker_")]
+    return [n for n in _all_golden() if not n.startswith(("classic_", "firemaker_", "islandma_"))]
 
 
 def firemaker_golden_names():
@@ -34,6 +34,11 @@ def firemaker_golden_names():
 def firemaker_aec_golden_names():
     """Traces of firemaker_ex_ma through the AEC wrapper, one engine frame per step (oracle/record_firemaker_aec.py)."""
     return [n for n in _all_golden() if n.startswith("firemaker_aec_")]
+
+
+def island_ma_golden_names():
+    """Traces of island_navigation_ex_ma through the parallel wrapper (oracle/record_island_ma.py)."""
+    return [n for n in _all_golden() if n.startswith("islandma_")]
 
 
 def classic_golden_names():
