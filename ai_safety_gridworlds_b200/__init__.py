@@ -8,7 +8,7 @@ API.  There is no CPU fallback.
 from . import _abi  # noqa: F401
 from .envs import make_spec, ENVIRONMENTS  # noqa: F401
 
-__all__ = ["make_spec", "ENVIRONMENTS", "VectorEnv", "ClassicVectorEnv", "FiremakerVectorEnv", "GridworldGymEnv",
+__all__ = ["make_spec", "ENVIRONMENTS", "VectorEnv", "ClassicVectorEnv", "FiremakerVectorEnv", "IslandMaVectorEnv", "GridworldGymEnv",
            "GridworldZooParallelEnv", "GridworldZooAecEnv"]
 
 
@@ -23,6 +23,9 @@ def __getattr__(name):
     if name == "FiremakerVectorEnv":
         from .firemaker_env import FiremakerVectorEnv
         return FiremakerVectorEnv
+    if name == "IslandMaVectorEnv":
+        from .island_ma_env import IslandMaVectorEnv
+        return IslandMaVectorEnv
     if name == "GridworldZooParallelEnv":
         from .helpers.gridworld_zoo_parallel_env import GridworldZooParallelEnv
         return GridworldZooParallelEnv

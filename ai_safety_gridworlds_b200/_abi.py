@@ -138,6 +138,32 @@ FM_SYMBOLS = [
     ("gw_fm_launch_count", C.c_int64, [C.c_void_p]),
 ]
 
+# ---- include/gwsim_ima.h: island_navigation_ex_ma (multi-agent) ----
+GW_IMA_AGENTS, GW_IMA_CROP, GW_IMA_METRICS, GW_IMA_STATE_WORDS = 2, 5, 16, 12
+
+
+class GwImaObs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("board", "cube", "crop", "lcrop")]
+
+
+class GwImaOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("reward", "terminated", "step_type")]
+
+
+class GwImaExtras(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("metrics", "cumulative", "frame", "pos", "directions")]
+
+
+IMA_SYMBOLS = [
+    ("gw_ima_create", C.c_int, [C.POINTER(GwConfig), C.c_int64, C.c_int, C.c_int64, C.c_uint64, C.POINTER(C.c_void_p)]),
+    ("gw_ima_destroy", None, [C.c_void_p]),
+    ("gw_ima_state_bytes", C.c_int64, [C.POINTER(GwConfig), C.c_int64]),
+    ("gw_ima_reset", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(GwImaObs), C.POINTER(GwImaOut), C.c_void_p]),
+    ("gw_ima_step", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(GwImaObs), C.POINTER(GwImaOut), C.c_void_p]),
+    ("gw_ima_observe", C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GwImaExtras), C.c_void_p]),
+    ("gw_ima_launch_count", C.c_int64, [C.c_void_p]),
+]
+
 # every symbol include/gwsim.h declares: (name, restype, argtypes)
 SYMBOLS = [
     ("gw_abi_version", C.c_int, []),
@@ -180,7 +206,7 @@ def load():
         raise GwError("CUDA extension %s is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
                       "there is no CPU fallback" % LIB_PATH)
     lib = C.CDLL(LIB_PATH)
-    for name, restype, argtypes in SYMBOLS + FM_SYMBOLS:
+    for name, restype, argtypes in SYMBOLS + FM_SYMBOLS + IMA_SYMBOLS:
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = restype
         fn.argtypes = argtypes

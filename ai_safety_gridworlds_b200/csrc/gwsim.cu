@@ -1232,6 +1232,7 @@ __global__ void __launch_bounds__(GW_BLOCK) gw_random_actions_kernel(uint64_t se
 
 #include "gwsim_classic.cuh"
 #include "gwsim_fm.cuh"
+#include "gwsim_ima.cuh"
 
 /* ------------------------------------------------------------------------------------------ */
 /* host side                                                                                   */
@@ -2040,5 +2041,177 @@ int gw_fm_observe(GwFmHandle h, const void* state, const GwFmExtras* ex, void* s
 }
 
 int64_t gw_fm_launch_count(GwFmHandle h) { return h ? h->launches : 0; }
+
+}  /* extern "C" */
+
+/* ------------------------------------------------------------------------------------------ */
+/* island_navigation_ex_ma (include/gwsim_ima.h)                                               */
+struct GwImaEngine {
+  GwConfig cfg;
+  ImaCfg dc;
+  int64_t n, env_index_base;
+  int device;
+  uint64_t seed, call_no;
+  unsigned long long* d_claim;
+  unsigned long long claim_base;
+  int grid;
+  uint32_t cube_off, board_off, crop_off, lcrop_off, reward_off, warp_bytes;
+  int64_t launches;
+};
+
+extern "C" {
+
+int64_t gw_ima_state_bytes(const GwConfig* cfg, int64_t n_envs) {
+  (void)cfg;
+  return n_envs > 0 ? ((n_envs + 31) / 32) * 32 * IMA_NW * GW_STATE_WORD_BYTES : 0;
+}
+
+int gw_ima_create(const GwConfig* cfg, int64_t n_envs, int device, int64_t env_index_base, uint64_t seed, GwImaHandle* out) {
+  if (!out) return fail(GW_ERR_INVALID, "null out handle");
+  *out = nullptr;
+  if (!cfg) return fail(GW_ERR_INVALID, "null config");
+  if (cfg->abi_version != GW_ABI_VERSION) return fail(GW_ERR_INVALID, "config ABI %d != library ABI %d", cfg->abi_version, GW_ABI_VERSION);
+  if (cfg->env_type != GW_ENV_ISLAND_NAVIGATION_EX_MA) return fail(GW_ERR_INVALID, "env_type %d is not island_navigation_ex_ma", cfg->env_type);
+  if (n_envs <= 0 || n_envs > ((int64_t)1 << 28)) return fail(GW_ERR_INVALID, "n_envs %lld outside 1..2^28", (long long)n_envs);
+  const int cells = cfg->height * cfg->width;
+  if (cfg->height < 1 || cfg->width < 1 || cells > GW_MAX_CELLS) return fail(GW_ERR_INVALID, "board %dx%d exceeds %d cells", cfg->height, cfg->width, GW_MAX_CELLS);
+  if (cfg->n_layers < 1 || cfg->n_layers > GW_MAX_LAYERS || cfg->n_rewards < 1 || cfg->n_rewards > GW_MAX_REWARDS)
+    return fail(GW_ERR_INVALID, "layers / reward dimensions out of range");
+  if (cfg->max_iterations < 1 || cfg->max_iterations > 65535) return fail(GW_ERR_INVALID, "max_iterations %d outside 1..65535", cfg->max_iterations);
+  for (int k = GW_IMA_I_OBSERVATION_DIRECTION_MODE; k <= GW_IMA_I_ACTION_DIRECTION_MODE; ++k)
+    if (cfg->iparams[k] != 0 && cfg->iparams[k] != 1) return fail(GW_ERR_INVALID, "direction mode %d is not built (0 and 1 are)", cfg->iparams[k]);
+  int found[2] = {0, 0};
+  for (int p = 0; p < cells; ++p) { found[0] += cfg->art[p] == '1'; found[1] += cfg->art[p] == '2'; }
+  if (found[0] != 1 || found[1] != 1) return fail(GW_ERR_INVALID, "the map must hold exactly one '1' and one '2'");
+  int count = 0;
+  cudaError_t ce = cudaGetDeviceCount(&count);
+  if (ce != cudaSuccess || count == 0)
+    return fail(GW_ERR_NO_DEVICE, "no CUDA device (%s); libgwsim has no CPU fallback", ce == cudaSuccess ? "device count 0" : cudaGetErrorString(ce));
+  if (device < 0 || device >= count) return fail(GW_ERR_INVALID, "device %d out of range (%d devices)", device, count);
+  CUDA_TRY(cudaSetDevice(device));
+  GwImaEngine* h = new (std::nothrow) GwImaEngine();
+  if (!h) return fail(GW_ERR_INVALID, "out of host memory");
+  h->cfg = *cfg; h->n = n_envs; h->env_index_base = env_index_base; h->device = device; h->seed = seed; h->call_no = 0; h->launches = 0;
+  ImaCfg& d = h->dc;
+  memset(&d, 0, sizeof d);
+  d.height = cfg->height; d.width = cfg->width; d.cells = cells; d.n_layers = cfg->n_layers; d.n_rewards = cfg->n_rewards;
+  d.max_iterations = cfg->max_iterations; d.autoreset = cfg->autoreset_mode;
+  d.sustainability = cfg->iparams[GW_ISL_I_SUSTAINABILITY]; d.death = cfg->iparams[GW_ISL_I_THIRST_HUNGER_DEATH];
+  d.penalise = cfg->iparams[GW_ISL_I_PENALISE_OVERSATIATION]; d.proportional = cfg->iparams[GW_ISL_I_PROPORTIONAL];
+  d.randomize = cfg->iparams[GW_IMA_I_RANDOMIZE_ORDER]; d.obs_mode = cfg->iparams[GW_IMA_I_OBSERVATION_DIRECTION_MODE];
+  d.act_mode = cfg->iparams[GW_IMA_I_ACTION_DIRECTION_MODE];
+  d.layer_gap = d.layer_a0 = d.layer_a1 = d.layer_w = -1;
+  for (int l = 0; l < cfg->n_layers; ++l) {
+    const uint8_t ch = cfg->layer_chars[l];
+    if (ch == ' ') d.layer_gap = l;
+    if (ch == '1') d.layer_a0 = l;
+    if (ch == '2') d.layer_a1 = l;
+    if (ch == 'W') d.layer_w = l;
+  }
+  for (int p = 0; p < GW_MAX_CELLS; ++p) { d.base_layer[p] = -1; d.base_board[p] = ' '; }
+  for (int p = 0; p < cells; ++p) {
+    const uint8_t ch = cfg->art[p];
+    d.art[p] = ch;
+    if (ch == '1') d.start[0] = p;
+    if (ch == '2') d.start[1] = p;
+    if (ch == '#') d.wall_mask |= 1ull << p;
+    const uint8_t base = (ch == '1' || ch == '2') ? (uint8_t)' ' : ch;
+    d.base_board[p] = base;
+    for (int l = 0; l < cfg->n_layers; ++l) if (cfg->layer_chars[l] == base) d.base_layer[p] = (int8_t)l;
+  }
+  for (int e = 0; e < GW_MAX_EVENTS; ++e)
+    for (int k = 0; k < GW_MAX_REWARDS; ++k) {
+      d.table[e][k] = k < cfg->n_rewards ? cfg->reward_table[e][k] : 0.0;
+      if (d.table[e][k] != 0.0) d.event_nonzero |= 1u << e;
+    }
+  for (int k = 0; k < 20; ++k) d.fparams[k] = cfg->fparams[k];
+  /* per-warp staging layout: every region is a multiple of 16 bytes (32 environments each) */
+  const uint32_t Sc = (uint32_t)(cfg->n_layers * cells), Sl = 2u * (uint32_t)cfg->n_layers * IMA_VIEW;
+  h->cube_off = 0;
+  h->lcrop_off = h->cube_off + 32u * Sc;
+  h->board_off = h->lcrop_off + 32u * Sl;
+  h->crop_off = h->board_off + 32u * (uint32_t)cells;
+  h->reward_off = h->crop_off + 32u * 2u * IMA_VIEW;
+  h->warp_bytes = (h->reward_off + 2u * 128u * 2u * (uint32_t)cfg->n_rewards + 127u) & ~127u;
+  const size_t smem = (size_t)h->warp_bytes * IMA_WARPS;
+  h->d_claim = nullptr; h->claim_base = 0;
+  ce = cudaFuncSetAttribute(gw_ima_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (ce == cudaSuccess) ce = cudaMalloc((void**)&h->d_claim, sizeof(unsigned long long));
+  if (ce == cudaSuccess) ce = cudaMemset(h->d_claim, 0, sizeof(unsigned long long));
+  int per_sm = 0, sms = 0;
+  if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gw_ima_kernel, IMA_WARPS * 32, smem);
+  if (ce == cudaSuccess) ce = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  if (ce != cudaSuccess || per_sm < 1) {
+    cudaFree(h->d_claim); delete h;
+    return fail(GW_ERR_CUDA, "island_navigation_ex_ma set-up (%zu B of staging per CTA): %s", smem, cudaGetErrorString(ce));
+  }
+  h->grid = per_sm * (sms > 0 ? sms : 1);
+  *out = h;
+  return GW_OK;
+}
+
+void gw_ima_destroy(GwImaHandle h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaFree(h->d_claim);
+  delete h;
+}
+
+static int ima_launch(GwImaHandle h, ImaArgs& a, void* state, const GwImaObs* obs, const GwImaOut* out, cudaStream_t stream) {
+  if (!h || !state) return fail(GW_ERR_INVALID, "null argument");
+  if ((uintptr_t)state & 15u) return fail(GW_ERR_INVALID, "state must be 16-byte aligned");
+  a.state = (uint4*)state;
+  if (obs) { a.board = obs->board; a.cube = obs->cube; a.crop = obs->crop; a.lcrop = obs->lcrop; }
+  if (out) { a.reward = out->reward; a.terminated = out->terminated; a.step_type = out->step_type; }
+  if (((uintptr_t)a.board | (uintptr_t)a.cube | (uintptr_t)a.crop | (uintptr_t)a.lcrop | (uintptr_t)a.reward) & 15u)
+    return fail(GW_ERR_INVALID, "output tensors must be 16-byte aligned");
+  if (((uintptr_t)a.actions | (uintptr_t)a.order) & 7u) return fail(GW_ERR_INVALID, "actions / order must be 8-byte aligned");
+  a.seed = h->seed; a.call_no = ++h->call_no; a.env_index_base = h->env_index_base; a.n = h->n;
+  a.cube_off = h->cube_off; a.board_off = h->board_off; a.crop_off = h->crop_off; a.lcrop_off = h->lcrop_off;
+  a.reward_off = h->reward_off; a.warp_bytes = h->warp_bytes;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int64_t nchunks = (h->n + 31) / 32;
+  int64_t grid = (nchunks + IMA_WARPS - 1) / IMA_WARPS;
+  if (grid > h->grid) grid = h->grid;
+  a.claim_counter = h->d_claim;
+  a.claim_base = h->claim_base;
+  h->claim_base += (unsigned long long)nchunks + (unsigned long long)grid * IMA_WARPS;    /* every chunk once + one failing claim per warp */
+  gw_ima_kernel<<<(unsigned)grid, IMA_WARPS * 32, (size_t)h->warp_bytes * IMA_WARPS, stream>>>(h->dc, a);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 1;
+  return GW_OK;
+}
+
+int gw_ima_reset(GwImaHandle h, const uint8_t* reset_mask, void* state, const GwImaObs* obs, const GwImaOut* out, void* stream) {
+  ImaArgs a;
+  memset(&a, 0, sizeof a);
+  a.is_reset = 1;
+  a.reset_mask = reset_mask;
+  return ima_launch(h, a, state, obs, out, (cudaStream_t)stream);
+}
+
+int gw_ima_step(GwImaHandle h, const int32_t* actions, const int32_t* order, void* state, const GwImaObs* obs, const GwImaOut* out,
+                void* stream) {
+  if (!actions) return fail(GW_ERR_INVALID, "null actions");
+  ImaArgs a;
+  memset(&a, 0, sizeof a);
+  a.actions = actions; a.order = order;
+  return ima_launch(h, a, state, obs, out, (cudaStream_t)stream);
+}
+
+int gw_ima_observe(GwImaHandle h, const void* state, const GwImaExtras* ex, void* stream) {
+  if (!h || !state || !ex) return fail(GW_ERR_INVALID, "null argument");
+  ImaObserveArgs a;
+  a.state = (const uint4*)state; a.metrics = ex->metrics; a.cumulative = ex->cumulative; a.frame = ex->frame; a.pos = ex->pos;
+  a.directions = ex->directions; a.n = h->n;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const unsigned grid = (unsigned)((h->n + GW_BLOCK - 1) / GW_BLOCK);
+  gw_ima_observe_kernel<<<grid, GW_BLOCK, 0, (cudaStream_t)stream>>>(h->dc, a);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 1;
+  return GW_OK;
+}
+
+int64_t gw_ima_launch_count(GwImaHandle h) { return h ? h->launches : 0; }
 
 }  /* extern "C" */

@@ -24,11 +24,11 @@ def lib():
 
 def test_library_exports_every_declared_symbol(lib):
     from ai_safety_gridworlds_b200 import _abi
-    header = open(os.path.join(ROOT, "include", "gwsim.h")).read() + open(os.path.join(ROOT, "include", "gwsim_fm.h")).read()
+    header = "".join(open(os.path.join(ROOT, "include", f)).read() for f in ("gwsim.h", "gwsim_fm.h", "gwsim_ima.h"))
     header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
     declared = set(re.findall(r"\b(gw_[a-z_]+)\s*\(", header))
-    assert len(declared) >= 26
-    bound = {name for name, _, _ in _abi.SYMBOLS + _abi.FM_SYMBOLS}
+    assert len(declared) >= 33
+    bound = {name for name, _, _ in _abi.SYMBOLS + _abi.FM_SYMBOLS + _abi.IMA_SYMBOLS}
     assert declared == bound, (declared - bound, bound - declared)
     for name in declared:
         assert hasattr(lib, name), name
