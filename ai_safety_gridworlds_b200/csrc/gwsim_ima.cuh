@@ -310,38 +310,34 @@ __device__ __forceinline__ void ima_step_lane(const ImaCfg& c, const ImaArgs& a,
     if (d < c.n_rewards) { rw[d] = (float)r0[d]; rw[c.n_rewards + d] = (float)r1[d]; }
 }
 
-/* source cell of view cell (i, j) of a 5x5 crop around `pos`, rotated by the observation direction
- * (np.rot90: DOWN k=2, LEFT k=-1, RIGHT k=1); -1 outside the board */
-__device__ __forceinline__ int ima_view_cell(const ImaCfg& c, int pos, int dir, int i, int j) {
-  int si = i, sj = j;
-  if (dir == GW_DIR_DOWN) { si = 4 - i; sj = 4 - j; }
-  else if (dir == GW_DIR_LEFT) { si = 4 - j; sj = i; }
-  else if (dir == GW_DIR_RIGHT) { si = j; sj = 4 - i; }
-  const int r = pos / c.width - 2 + si, cc = pos % c.width - 2 + sj;
-  return (r >= 0 && r < c.height && cc >= 0 && cc < c.width) ? r * c.width + cc : -1;
-}
+#define IMA_BMAP 352                     /* bordered map entries: (H + 4) * (W + 4) <= 352 for H * W <= 64 */
 
-/* The agents' views of one environment into crop[2][25] / lcrop[2][L][25] (lcrop pre-zeroed). */
-__device__ __forceinline__ void ima_views(const ImaCfg& c, const uint8_t* __restrict__ s_base, const int8_t* __restrict__ s_blayer,
+/* The agents' views of one environment into crop[2][25] / lcrop[2][L][25] (lcrop pre-zeroed).
+ * get_agent_perspective (safety_game_moma.py:1996-2101): 5x5 crop around the agent, what_lies_outside ('W') beyond the
+ * board, np.rot90 by the observation direction (DOWN k=2, LEFT k=-1, RIGHT k=1).  The map is held with a 2-cell border
+ * of 'W' (s_bmap: character | layer << 8), and s_voff[dir][v] is the offset of the source of view cell v from the
+ * agent in that bordered map, so a view cell costs one table look-up and no bounds test. */
+__device__ __forceinline__ void ima_views(const ImaCfg& c, const uint16_t* __restrict__ s_bmap, const int16_t* __restrict__ s_voff,
                                           int pos0, int pos1, int odir0, int odir1, uint8_t* __restrict__ crop, uint8_t* __restrict__ lcrop) {
-  const int L = c.n_layers;
+  const int L = c.n_layers, BW = c.width + 4;
+  const int p0b = (pos0 / c.width + 2) * BW + pos0 % c.width + 2, p1b = (pos1 / c.width + 2) * BW + pos1 % c.width + 2;
 #pragma unroll 1
   for (int ag = 0; ag < 2; ++ag) {
-    const int pos = ag ? pos1 : pos0, dir = c.obs_mode ? (ag ? odir1 : odir0) : GW_DIR_UP;
-#pragma unroll 1
+    const int posb = ag ? p1b : p0b;
+    const int16_t* __restrict__ off = s_voff + (c.obs_mode ? (ag ? odir1 : odir0) : GW_DIR_UP) * IMA_VIEW;
+    uint8_t* __restrict__ lc = lcrop ? lcrop + ag * L * IMA_VIEW : nullptr;
+#pragma unroll 5
     for (int v = 0; v < IMA_VIEW; ++v) {
-      const int cell = ima_view_cell(c, pos, dir, v / 5, v % 5);
-      uint8_t ch = 'W';
-      int l0 = c.layer_w, l1 = -1;
-      if (cell >= 0) {
-        ch = s_base[cell]; l0 = s_blayer[cell];
-        if (cell == pos0) { ch = '1'; l1 = c.layer_a0; if (l0 == c.layer_gap) l0 = -1; }
-        if (cell == pos1) { ch = '2'; l1 = c.layer_a1; if (l0 == c.layer_gap) l0 = -1; }
-      }
-      if (crop) crop[ag * IMA_VIEW + v] = ch;
-      if (lcrop) {
-        if (l0 >= 0) lcrop[(ag * L + l0) * IMA_VIEW + v] = 1;
-        if (l1 >= 0) lcrop[(ag * L + l1) * IMA_VIEW + v] = 1;
+      const int cb = posb + off[v];
+      const uint32_t e = s_bmap[cb];
+      uint32_t ch = e & 0xffu;
+      int l0 = (int)(int8_t)(e >> 8), l1 = -1;
+      if (cb == p0b) { ch = '1'; l1 = c.layer_a0; if (l0 == c.layer_gap) l0 = -1; }
+      if (cb == p1b) { ch = '2'; l1 = c.layer_a1; if (l0 == c.layer_gap) l0 = -1; }
+      if (crop) crop[ag * IMA_VIEW + v] = (uint8_t)ch;
+      if (lc) {
+        if (l0 >= 0) lc[l0 * IMA_VIEW + v] = 1;
+        if (l1 >= 0) lc[l1 * IMA_VIEW + v] = 1;
       }
     }
   }
@@ -351,7 +347,27 @@ __global__ void __launch_bounds__(IMA_WARPS * 32, 2) gw_ima_kernel(const __grid_
   extern __shared__ __align__(128) uint8_t ima_stage[];
   __shared__ uint8_t s_art[GW_MAX_CELLS], s_base[GW_MAX_CELLS];
   __shared__ int8_t s_blayer[GW_MAX_CELLS];
+  __shared__ uint16_t s_bmap[IMA_BMAP];
+  __shared__ int16_t s_voff[4 * IMA_VIEW];
   for (uint32_t i = threadIdx.x; i < GW_MAX_CELLS; i += blockDim.x) { s_art[i] = c.art[i]; s_base[i] = c.base_board[i]; s_blayer[i] = c.base_layer[i]; }
+  {
+    const int BW = c.width + 4, BH = c.height + 4;
+    for (int i = (int)threadIdx.x; i < IMA_BMAP; i += (int)blockDim.x) {
+      const int r = i / BW - 2, cc = i % BW - 2;
+      uint32_t e = (uint32_t)'W' | (((uint32_t)c.layer_w & 0xffu) << 8);                  /* what_lies_outside; a layer pads with (chr == 'W') */
+      if (i < BW * BH && r >= 0 && r < c.height && cc >= 0 && cc < c.width)
+        e = (uint32_t)c.base_board[r * c.width + cc] | (((uint32_t)c.base_layer[r * c.width + cc] & 0xffu) << 8);
+      s_bmap[i] = (uint16_t)e;
+    }
+    for (int i = (int)threadIdx.x; i < 4 * IMA_VIEW; i += (int)blockDim.x) {
+      const int dir = i / IMA_VIEW, vi = (i % IMA_VIEW) / 5, vj = i % 5;
+      int si = vi, sj = vj;                                                                /* out[vi][vj] = in[si][sj] */
+      if (dir == GW_DIR_DOWN) { si = 4 - vi; sj = 4 - vj; }
+      else if (dir == GW_DIR_LEFT) { si = 4 - vj; sj = vi; }                               /* rot90 k=-1 (clockwise) */
+      else if (dir == GW_DIR_RIGHT) { si = vj; sj = 4 - vi; }                              /* rot90 k=1 (counterclockwise) */
+      s_voff[i] = (int16_t)((si - 2) * BW + (sj - 2));
+    }
+  }
   __syncthreads();
 
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -442,7 +458,7 @@ __global__ void __launch_bounds__(IMA_WARPS * 32, 2) gw_ima_kernel(const __grid_
       __syncwarp();
     }
     if (a.crop || a.lcrop)
-      ima_views(c, s_base, s_blayer, p0, p1, s.ag[0].odir, s.ag[1].odir, a.crop ? s_crop + lane * Sv : nullptr,
+      ima_views(c, s_bmap, s_voff, p0, p1, s.ag[0].odir, s.ag[1].odir, a.crop ? s_crop + lane * Sv : nullptr,
                 a.lcrop ? s_lcrop + lane * Sl : nullptr);
 
     if (nvalid == 32 && !(a.is_reset && a.reset_mask)) {

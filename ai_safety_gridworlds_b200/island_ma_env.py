@@ -105,6 +105,10 @@ class IslandMaVectorEnv(object):
         out["metrics"] = out["metrics"][:, slots]                  # the columns this level activates, metrics_dict order
         return out
 
+    def clear_stats(self):
+        """The multi-agent kernels keep no device-side rollout statistics."""
+        return None
+
     @property
     def launch_count(self):
         return int(self._lib.gw_ima_launch_count(self._h))

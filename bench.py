@@ -46,6 +46,10 @@ WORKLOADS = {
                         "firemaker_ex_ma level 0, 3 agents (2 workers + supervisor), shuffled sub-step order, Philox fire draws "
                         "(SURVEY 8d config 4); one env-step = one PARALLEL step = 3 engine frames",
                         "board u8[289] + cube u8[9x289] + agent crops u8[25+25+1089] x (1 + 9 layers) + rewards f32[7] + flags"),
+    "island_navigation_ex_ma": ("island_navigation_ex_ma", {}, 1 << 20,
+                                "island_navigation_ex_ma level 9, 2 agents, default flags (relative actions and views, shuffled "
+                                "sub-step order; SURVEY 8f row 1); one env-step = one PARALLEL step = up to 2 engine frames",
+                                "board u8[48] + cube u8[9x48] + agent views u8[2x25] x (1 + 9 layers) + rewards f32[2x8] + flags"),
 }
 CLASSIC_TYPES = ["safe_interruptibility", "side_effects_sokoban", "absent_supervisor", "conveyor_belt", "whisky_gold"]
 WORKLOAD_TEXT = WORKLOADS["island_navigation_ex"][3]
@@ -243,7 +247,17 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     classic = ENV_NAME == "classic_mixed"
     firemaker = ENV_NAME == "firemaker_ex_ma"
-    if firemaker:
+    island_ma = ENV_NAME == "island_navigation_ex_ma"
+    n_agents = 3 if firemaker else 2
+    if island_ma:
+        from ai_safety_gridworlds_b200.island_ma_env import IslandMaVectorEnv
+        spec = make_spec(ENV_NAME, autoreset_mode=1)
+
+        def make_env(value_board):
+            return IslandMaVectorEnv(n, device=dev, env_index_base=rank * n, seed=0, autoreset_mode=1, spec=spec)
+        lo_hi = {}
+        firemaker = True                             # from here on: "the multi-agent path" (per-agent action columns, no device statistics)
+    elif firemaker:
         from ai_safety_gridworlds_b200.firemaker_env import FiremakerVectorEnv
         spec = make_spec(ENV_NAME, autoreset_mode=1)
 
@@ -270,7 +284,7 @@ def run_ours(args):
     if firemaker:
         g = torch.Generator(device=dev)
         g.manual_seed(1234 + rank)
-        ring = torch.randint(0, 5, (ACTION_RING, n, 3), dtype=torch.int32, device=dev, generator=g)
+        ring = torch.randint(0, 5, (ACTION_RING, n, n_agents), dtype=torch.int32, device=dev, generator=g)
     else:
         ring = torch.empty((ACTION_RING, n), dtype=torch.int32, device=dev)
         for r in range(ACTION_RING):
@@ -328,18 +342,19 @@ def run_ours(args):
     if firemaker:
         env_e = env
         pin = dict(pin_memory=True)
-        h_obs = [torch.zeros_like(t, device="cpu", **pin) for t in (env.crop_workers, env.crop_supervisor)]
-        h_rw = [torch.zeros_like(t, device="cpu", **pin) for t in (env.reward_workers, env.reward_supervisor, env.terminated)]
-        d_act = torch.zeros((n, 3), dtype=torch.int32, device=dev)
+        d_tensors = (env.crop, env.reward, env.terminated) if island_ma else \
+            (env.crop_workers, env.crop_supervisor, env.reward_workers, env.reward_supervisor, env.terminated)
+        h_tensors = [torch.zeros_like(t, device="cpu", **pin) for t in d_tensors]
+        d_act = torch.zeros((n, n_agents), dtype=torch.int32, device=dev)
 
         def step_host(a_host):
             d_act.copy_(a_host, non_blocking=True)
             env.step_raw(_ptr(d_act))
-            for h, t in zip(h_obs + h_rw, (env.crop_workers, env.crop_supervisor, env.reward_workers, env.reward_supervisor, env.terminated)):
+            for h, t in zip(h_tensors, d_tensors):
                 h.copy_(t, non_blocking=True)
             stream.synchronize()
-            return h_obs, h_rw, None
-        fm_bytes = (n * 12, n * (50 + 1089 + 16 + 12 + 3))
+            return h_tensors, None, None
+        fm_bytes = (n * 4 * n_agents, sum(t.numel() * t.element_size() for t in d_tensors))
     else:
         env_e = make_env(True)
         step_host = env_e.step_host
@@ -373,14 +388,15 @@ def run_ours(args):
                 "l2": ("per-step working set %.0f MB per GPU (> 126 MB L2), no flush needed" % (bytes_per * n / 1e6))
                       if bytes_per * n > 252e6 else
                       ("per-step working set %.0f MB per GPU fits the 126 MB L2: a secondary, L2-resident line" % (bytes_per * n / 1e6)),
-                "bytes_per_env_step": bytes_per, "state_bytes_per_env": 160 if firemaker else env.state_words * 16,
+                "bytes_per_env_step": bytes_per, "state_bytes_per_env": 192 if island_ma else 160 if firemaker else env.state_words * 16,
                 "autoreset": "same-step", "action_ring": ACTION_RING}),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": load_traffic(n), "peak_source": peak_src, "kernel": "gw_fm_kernel" if firemaker else "gw_cls_step_kernel" if classic else "gw_step_tma_kernel<%d>" % (0 if ENV_NAME == "island_navigation_ex" else 2),
+                         "traffic": load_traffic(n), "peak_source": peak_src, "kernel": "gw_ima_kernel" if island_ma else "gw_fm_kernel" if firemaker else "gw_cls_step_kernel" if classic else "gw_step_tma_kernel<%d>" % (0 if ENV_NAME == "island_navigation_ex" else 2),
                          "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": bytes_per * n},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                     "steps": e2e_steps,
-                    "returns": ("per-agent ASCII crops u8[25+25+1089] + reward rows f32[7] + terminated u8[3] per env, pinned host"
+                    "returns": ("per-agent ASCII views u8[2x25] + reward rows f32[2xR] + terminated u8[2] per env, pinned host" if island_ma else
+                                "per-agent ASCII crops u8[25+25+1089] + reward rows f32[7] + terminated u8[3] per env, pinned host"
                                 if firemaker else "value-mapped board f32 + reward row f32 + terminated u8 per env, pinned host")},
             "gpu_launches": step_launches,
             "clocks": clocks,
