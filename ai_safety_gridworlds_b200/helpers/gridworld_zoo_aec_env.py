@@ -2,9 +2,9 @@
 
 Mirrors helpers/gridworld_zoo_aec_env.py of the reference (constructor :100-262, `agent_iter`
 :327-333, `observe` :380-411, `last` :503-518, `step` :607-806, `reset` :809-905) for
-firemaker_ex_ma.  One AEC step is ONE single-agent `EnvironmentMa.step({agent: action})`
+firemaker_ex_ma and island_navigation_ex_ma.  One AEC step is ONE single-agent `EnvironmentMa.step({agent: action})`
 (rl/pycolab_interface_ma.py:173-246), i.e. one engine frame: the wrapper launches the
-warp-per-environment kernel with the execution order {agent, -1, -1} (include/gwsim_fm.h).
+kernel with the execution order {agent, -1, ...} (include/gwsim_fm.h, include/gwsim_ima.h).
 
   * `num_envs=None` is the drop-in single environment with the reference's bookkeeping: `rewards`
     holds the frame's reward vector of every agent, `_cumulative_rewards[agent]` restarts at the
@@ -57,7 +57,7 @@ class GridworldZooAecEnv(object):
     def _zero_reward(self, i):
         env = self._par._env
         if self._batched:
-            return torch.zeros((self.num_envs, 3 if i == 2 else 2), dtype=torch.float64, device=env.device)
+            return torch.zeros((self.num_envs, self._par._backend.reward(i).shape[-1]), dtype=torch.float64, device=env.device)
         return 0.0                                      # the reference initialises scalars (:899-901)
 
     def _init_bookkeeping(self):
@@ -176,10 +176,11 @@ class GridworldZooAecEnv(object):
             self._rewards = {a: 0.0 for a in self._agents}
             self._move_to_next_agent()
             return
-        order = torch.tensor([[idx, -1, -1]], dtype=torch.int32, device=env.device).expand(self.num_envs, 3).contiguous()
+        A = len(self.possible_agents)
+        order = torch.tensor([[idx] + [-1] * (A - 1)], dtype=torch.int32, device=env.device).expand(self.num_envs, A).contiguous()
         if self._batched:
             v = action if torch.is_tensor(action) else torch.as_tensor(np.asarray(action), device=env.device)
-            act = torch.zeros((self.num_envs, 3), dtype=torch.int32, device=env.device)
+            act = torch.zeros((self.num_envs, A), dtype=torch.int32, device=env.device)
             act[:, idx] = v.to(device=env.device, dtype=torch.int32).reshape(-1)
             draws = None
         else:
@@ -189,7 +190,7 @@ class GridworldZooAecEnv(object):
             v = int(np.asarray(v).item())
             if v == 9:
                 raise NotImplementedError("QUIT is not supported by the multi-agent CUDA backend")
-            row = [0, 0, 0]
+            row = [0] * A
             row[idx] = v
             act = torch.tensor([row], dtype=torch.int32, device=env.device)
             draws = None
@@ -197,11 +198,11 @@ class GridworldZooAecEnv(object):
                 dr = np.full((1, _abi.GW_FM_MAX_DRAWS), 2.0)
                 dr[0, :len(replay_draws)] = replay_draws
                 draws = torch.from_numpy(dr).to(env.device)
-        env.step(act, order, draws)
+        self._par._backend.step(act, order, draws)
         self._infos[sel] = self._par._infos()[sel]
         rewards = {}
         for i, a in enumerate(self.possible_agents):
-            r = (env.reward_supervisor if i == 2 else env.reward_workers[:, i]).double()
+            r = self._par._backend.reward(i).double()
             rewards[a] = r.clone() if self._batched else r[0].cpu().numpy()
         self._cumulative_rewards[sel] = self._zero_reward(idx)                      # :757
         for a, r in rewards.items():

@@ -1,19 +1,20 @@
 """GridworldZooParallelEnv: the reference's PettingZoo parallel signature over the CUDA backend.
 
 Mirrors helpers/gridworld_zoo_parallel_env.py of the reference (constructor :100-135, `reset`
-:618-702, `step` :429-615, `agents` :252-253) for firemaker_ex_ma:
+:618-702, `step` :429-615, `agents` :252-253) for firemaker_ex_ma (agents '1', '2', 'S') and
+island_navigation_ex_ma (agents '1', '2'):
 
-  * `num_envs=None` is the drop-in single environment: dicts keyed 'agent_1', 'agent_2', 'agent_S' of
-    numpy values with the reference's shapes -- observations '<U1' [1,5,5] / [1,33,33] (float32
-    value-mapped with `ascii_observation_format=False`), rewards float64 [2] / [3], terminateds bool,
-    truncateds False, infos -- done agents leave `agents`, stepping a done agent raises ValueError
-    (rl/pycolab_interface_ma.py:217-218) and a finished game needs `reset()`;
+  * `num_envs=None` is the drop-in single environment: dicts keyed 'agent_<chr>' of numpy values
+    with the reference's shapes -- observations '<U1' [1,5,5] (the firemaker supervisor: [1,33,33];
+    float32 value-mapped with `ascii_observation_format=False`), rewards float64 [R], terminateds bool,
+    truncateds False, infos -- done agents leave `agents` and the returned dicts, stepping a done
+    agent raises ValueError (rl/pycolab_interface_ma.py:217-218) and a finished game needs `reset()`;
   * `num_envs=N` is the batched form: the same dicts of torch CUDA tensors with a leading batch
     dimension (observations as uint8 ASCII codes or float32), auto-reset inside the step that ends
-    a game.
+    a game; the action entries of agents that are done in an environment are ignored.
 
-pettingzoo itself is not imported (duck-typed).  Every step is one launch of the warp-per-environment
-kernel; there is no CPU fallback.
+pettingzoo itself is not imported (duck-typed).  Every step is one kernel launch; there is no CPU
+fallback.
 """
 import numpy as np
 import torch
@@ -21,6 +22,7 @@ import torch
 from .. import _abi
 from ..envs import make_spec
 from ..firemaker_env import FiremakerVectorEnv
+from ..island_ma_env import IslandMaVectorEnv
 from .gridworld_gym_env import (DiscreteActionSpace, INFO_OBSERVATION_LAYERS_CUBE, INFO_OBSERVATION_LAYERS_ORDER)
 
 INFO_AGENT_OBSERVATIONS = "info_agent_observations"
@@ -35,6 +37,62 @@ _WRAPPER_ONLY = ("use_transitions", "render_animation_delay", "flatten_observati
                  "post_reset_callback", "pre_step_callback", "post_step_callback", "render_mode")
 
 
+class _FiremakerBackend(object):
+    """Per-agent views of FiremakerVectorEnv's tensors (workers share [N,2,...] tensors, the supervisor has its own)."""
+    agent_chars = ["1", "2", "S"]
+
+    def __init__(self, n, device, seed, mode, spec):
+        self.env = FiremakerVectorEnv(n, device=device, seed=seed, autoreset_mode=mode, spec=spec)
+
+    def crop(self, i):
+        return self.env.crop_supervisor if i == 2 else self.env.crop_workers[:, i]
+
+    def lcrop(self, i):
+        return self.env.lcrop_supervisor if i == 2 else self.env.lcrop_workers[:, i]
+
+    def reward(self, i):
+        return self.env.reward_supervisor if i == 2 else self.env.reward_workers[:, i]
+
+    def step(self, act, order, draws):
+        self.env.step(act, order, draws)
+
+    def extras(self):
+        ex = self.env.observe()
+        cum = ex["cumulative"]
+        ex["cumulative_per_agent"] = [cum[:, 0:2], cum[:, 2:4], cum[:, 4:7]]
+        ex["external_fires"] = ex["ext_fires"]
+        return ex
+
+
+class _IslandMaBackend(object):
+    agent_chars = ["1", "2"]
+
+    def __init__(self, n, device, seed, mode, spec):
+        self.env = IslandMaVectorEnv(n, device=device, seed=seed, autoreset_mode=mode, spec=spec)
+
+    def crop(self, i):
+        return self.env.crop[:, i]
+
+    def lcrop(self, i):
+        return self.env.lcrop[:, i]
+
+    def reward(self, i):
+        return self.env.reward[:, i]
+
+    def step(self, act, order, draws):
+        if draws is not None:
+            raise ValueError("island_navigation_ex_ma draws no random numbers inside a step")
+        self.env.step(act, order)
+
+    def extras(self):
+        ex = self.env.observe()
+        ex["cumulative_per_agent"] = [ex["cumulative"][:, 0], ex["cumulative"][:, 1]]
+        return ex
+
+
+_BACKENDS = {"firemaker_ex_ma": _FiremakerBackend, "island_navigation_ex_ma": _IslandMaBackend}
+
+
 class GridworldZooParallelEnv(object):
     metadata = {"render.modes": ["ansi"], "name": "gridworld_zoo_parallel_env_b200"}
 
@@ -43,17 +101,20 @@ class GridworldZooParallelEnv(object):
             raise NotImplementedError("test_death fault injection is a wrapper-side debugging aid and is not built")
         for k in _WRAPPER_ONLY:
             kwargs.pop(k, None)
-        if env_name.lower() != "firemaker_ex_ma":
-            raise NotImplementedError("the multi-agent CUDA backend is built for firemaker_ex_ma (BASELINE config 4)")
-        kwargs.setdefault("amount_agents", 3)
+        if env_name.lower() not in _BACKENDS:
+            raise NotImplementedError("the multi-agent CUDA backend is built for " + " and ".join(sorted(_BACKENDS)))
+        if env_name.lower() == "firemaker_ex_ma":
+            kwargs.setdefault("amount_agents", 3)
         self._batched = num_envs is not None
         n = int(num_envs) if self._batched else 1
         mode = _abi.GW_AUTORESET_SAME_STEP if self._batched else _abi.GW_AUTORESET_NEXT_STEP
         self._spec = make_spec(env_name, autoreset_mode=mode, **kwargs)
-        self._env = FiremakerVectorEnv(n, device=device, seed=0 if seed is None else seed, autoreset_mode=mode, spec=self._spec)
+        self._backend = _BACKENDS[env_name.lower()](n, device, 0 if seed is None else seed, mode, self._spec)
+        self._env = self._backend.env
         self._ascii = bool(ascii_observation_format)
-        self.possible_agents = ["agent_1", "agent_2", "agent_S"]
-        self.agent_name_mapping = dict(zip(self.possible_agents, ["1", "2", "S"]))
+        chars = self._backend.agent_chars
+        self.possible_agents = ["agent_" + ch for ch in chars]
+        self.agent_name_mapping = dict(zip(self.possible_agents, chars))
         self.agent_name_reverse_mapping = {v: k for k, v in self.agent_name_mapping.items()}
         lo, hi = self._spec.action_range
         self.action_spaces = {a: DiscreteActionSpace(lo, hi, seed) for a in self.possible_agents}
@@ -99,9 +160,9 @@ class GridworldZooParallelEnv(object):
         return self._observations(), self._infos()
 
     def step(self, actions, *args, replay_order=None, replay_draws=None, **kwargs):
-        """`replay_order` (agent indices in execution order) and `replay_draws` (the FireDrape uniform draws of this
-        step, in call order) replay a recorded reference run -- test hooks of the single-environment form."""
-        env = self._env
+        """`replay_order` (agent indices in execution order, -1 = no frame) and `replay_draws` (the FireDrape uniform draws
+        of this step, in call order) replay a recorded reference run -- test hooks of the single-environment form."""
+        env, A = self._env, len(self.possible_agents)
         if self._batched:
             cols = []
             for a in self.possible_agents:
@@ -109,12 +170,14 @@ class GridworldZooParallelEnv(object):
                 v = v if torch.is_tensor(v) else torch.as_tensor(np.asarray(v), device=env.device)
                 cols.append(v.to(device=env.device, dtype=torch.int32).reshape(-1))
             act = torch.stack(cols, dim=1).contiguous()
+            stepped = list(self.possible_agents)
         else:
             for a in actions:
                 if self._dones.get(a, False):
                     raise ValueError("Agent %s is done" % self.agent_name_mapping[a])     # pycolab_interface_ma.py:217-218
             if not self.agents:
                 raise ValueError("all agents are done: call reset()")
+            stepped = [a for a in self.possible_agents if not self._dones[a]]
             vals = []
             for a in self.possible_agents:
                 v = actions.get(a, 0)
@@ -125,16 +188,18 @@ class GridworldZooParallelEnv(object):
             act = torch.tensor([vals], dtype=torch.int32, device=env.device)
         order = draws = None
         if replay_order is not None:
-            order = torch.tensor(np.asarray(replay_order, np.int32).reshape(1, 3), device=env.device)
+            order = torch.tensor(np.asarray(replay_order, np.int32).reshape(1, A), device=env.device)
         if replay_draws is not None:
             dr = np.full((1, _abi.GW_FM_MAX_DRAWS), 2.0)
             dr[0, :len(replay_draws)] = replay_draws
             draws = torch.from_numpy(dr).to(env.device)
-        env.step(act, order, draws)
-        obs, infos = self._observations(), self._infos()
+        self._backend.step(act, order, draws)
+        obs, infos = self._observations(stepped), self._infos(stepped)
         rewards, terms, truncs = {}, {}, {}
         for i, a in enumerate(self.possible_agents):
-            r = env.reward_supervisor if i == 2 else env.reward_workers[:, i]
+            if a not in stepped:
+                continue
+            r = self._backend.reward(i)
             t = env.terminated[:, i].bool()
             if self._batched:
                 rewards[a], terms[a], truncs[a] = r.double(), t, torch.zeros_like(t)
@@ -146,16 +211,16 @@ class GridworldZooParallelEnv(object):
 
     # ------------------------------------------------------------------ helpers
     def _crop(self, i):
-        env = self._env
-        return env.crop_supervisor if i == 2 else env.crop_workers[:, i]
+        return self._backend.crop(i)
 
     def _lcrop(self, i):
-        env = self._env
-        return env.lcrop_supervisor if i == 2 else env.lcrop_workers[:, i]
+        return self._backend.lcrop(i)
 
-    def _observations(self):
+    def _observations(self, agents=None):
         out = {}
         for i, a in enumerate(self.possible_agents):
+            if agents is not None and a not in agents:
+                continue
             codes = self._crop(i)
             if self._batched:
                 out[a] = (codes.clone() if self._ascii else self._lut[codes.long()]).unsqueeze(1)
@@ -166,23 +231,29 @@ class GridworldZooParallelEnv(object):
                 out[a] = self._lut[codes[0].long()].cpu().numpy()[np.newaxis, :]
         return out
 
-    def _infos(self):
+    def _infos(self, agents=None):
         env, spec = self._env, self._spec
-        ex = env.observe()
+        ex = self._backend.extras()
         infos = {}
         for i, a in enumerate(self.possible_agents):
-            lo, hi = (4, 7) if i == 2 else (2 * i, 2 * i + 2)
+            if agents is not None and a not in agents:
+                continue
             info = {
                 "ascii_codes": env.board, INFO_OBSERVATION_LAYERS_ORDER: list(spec.layer_order),
                 INFO_OBSERVATION_LAYERS_CUBE: env.cube.bool(),
                 INFO_AGENT_OBSERVATION_LAYERS_ORDER: list(spec.layer_order),
                 INFO_AGENT_OBSERVATION_LAYERS_CUBE: self._lcrop(i).bool(),
                 INFO_AGENT_OBSERVATIONS: self._crop(i),
-                "cumulative_reward": ex["cumulative"][:, lo:hi].double(),
+                "cumulative_reward": ex["cumulative_per_agent"][i].double(),
                 "metrics_dict": {n: ex["metrics"][:, j] for j, n in enumerate(spec.metric_names)},
-                "frame": ex["frame"], "agent_positions": ex["pos"], "external_fires": ex["ext_fires"],
+                "frame": ex["frame"], "agent_positions": ex["pos"],
                 "step_type": env.step_type[:, i],
             }
+            if "external_fires" in ex:
+                info["external_fires"] = ex["external_fires"]
+            if "directions" in ex:
+                info["action_direction"] = ex["directions"][:, i, 0]
+                info["observation_direction"] = ex["directions"][:, i, 1]
             if not self._batched:
                 def host(x):
                     if torch.is_tensor(x):

@@ -82,3 +82,70 @@ def test_batched_form():
     assert done_seen == N                                        # 60 frames = 20 parallel steps: every game ended once and restarted
     assert len(env.agents) == 3
     env.close()
+
+
+@pytest.mark.parametrize("name", ["islandma_default_s0", "islandma_homeostasis_s2", "islandma_level4_s5"])
+def test_island_ma_single_env_drop_in_replays_reference_trace(name):
+    """island_navigation_ex_ma through the parallel wrapper: agents finish one by one, leave `agents` and the returned
+    dicts, and the recorder's reset() calls are replayed where every agent was done."""
+    from ai_safety_gridworlds_b200 import GridworldZooParallelEnv
+    d, meta = load_golden(name)
+    env = GridworldZooParallelEnv("island_navigation_ex_ma", seed=meta["seed"], **meta["kwargs"])
+    obs, infos = env.reset(seed=meta["seed"])
+    names = ["agent_1", "agent_2"]
+    assert env.agents == names and obs["agent_1"].shape == (1, 5, 5) and obs["agent_1"].dtype.kind == "U"
+    codes = lambda o: np.vectorize(ord)(o[0]).astype(np.uint8)
+    np.testing.assert_array_equal(codes(obs["agent_2"]), d["crop2"][0])
+    assert infos["agent_1"]["info_observation_layers_order"] == meta["layer_order"]
+    for t in range(1, len(d["actions"]) + 1):
+        a = d["actions"][t - 1]
+        if (a < 0).all():                        # the recorder called reset(): every agent was done
+            assert env.agents == []
+            with pytest.raises(ValueError):
+                env.step({})
+            obs, infos = env.reset()
+            np.testing.assert_array_equal(infos["agent_1"]["ascii_codes"], d["board"][t])
+            continue
+        live = [n for i, n in enumerate(names) if a[i] >= 0]
+        assert env.agents == live
+        obs, rewards, terms, truncs, infos = env.step({n: int(a[names.index(n)]) for n in live}, replay_order=d["order"][t - 1])
+        assert sorted(obs) == sorted(live) == sorted(rewards) == sorted(terms)
+        for n in live:
+            k = n[-1]
+            i = names.index(n)
+            np.testing.assert_array_equal(codes(obs[n]), d["crop" + k][t])
+            np.testing.assert_allclose(rewards[n], d["reward" + k][t], rtol=1e-6)
+            assert terms[n] == bool(d["done"][t][i]) and truncs[n] is False
+            np.testing.assert_array_equal(infos[n]["info_agent_observation_layers_cube"], d["lcrop" + k][t].astype(bool))
+            np.testing.assert_allclose(infos[n]["cumulative_reward"], d["cum"][t][i], rtol=1e-6)
+            assert int(infos[n]["observation_direction"]) == d["odir"][t][i]
+        n0 = live[0]
+        np.testing.assert_array_equal(infos[n0]["ascii_codes"], d["board"][t])
+        np.testing.assert_array_equal(infos[n0]["info_observation_layers_cube"], d["cube"][t].astype(bool))
+        np.testing.assert_allclose(list(infos[n0]["metrics_dict"].values()), d["metrics"][t], rtol=1e-9)
+    env.close()
+
+
+def test_island_ma_batched_parallel_and_aec_forms():
+    from ai_safety_gridworlds_b200 import GridworldZooAecEnv, GridworldZooParallelEnv
+    N = 1024
+    env = GridworldZooParallelEnv("island_navigation_ex_ma", num_envs=N, seed=3)
+    obs, infos = env.reset()
+    assert obs["agent_1"].shape == (N, 1, 5, 5) and obs["agent_1"].dtype == torch.uint8 and len(env.agents) == 2
+    ended = 0
+    for t in range(30):
+        acts = {a: torch.randint(0, 5, (N,), device=env.vector_env.device) for a in env.possible_agents}
+        obs, rewards, terms, truncs, infos = env.step(acts)
+        assert rewards["agent_2"].shape == (N, 8) and rewards["agent_2"].dtype == torch.float64
+        ended += int((terms["agent_1"] & terms["agent_2"]).sum())
+    assert ended > 0                                             # games ended and restarted inside the step
+    env.close()
+    aec = GridworldZooAecEnv("island_navigation_ex_ma", num_envs=N, seed=3)
+    aec.reset()
+    for k, a in zip(range(8), aec.agent_iter()):
+        assert a == ["agent_1", "agent_2"][k % 2]
+        obs, cum, term, trunc, info = aec.last()
+        assert obs.shape == (N, 1, 5, 5) and cum.shape == (N, 8)
+        aec.step(torch.randint(0, 5, (N,), device=aec.vector_env.device))
+    assert int(aec.get_step_no().max()) <= 8
+    aec.close()
