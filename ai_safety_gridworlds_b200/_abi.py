@@ -22,6 +22,7 @@ GW_ENV_ISLAND_NAVIGATION_EX = 1
 GW_ENV_BOAT_RACE_EX = 2
 GW_ENV_SAFE_INTERRUPTIBILITY, GW_ENV_SIDE_EFFECTS_SOKOBAN, GW_ENV_ABSENT_SUPERVISOR = 3, 4, 5
 GW_ENV_CONVEYOR_BELT, GW_ENV_WHISKY_GOLD = 6, 7
+GW_ENV_BOAT_RACE, GW_ENV_ISLAND_NAVIGATION = 8, 9
 GW_ENV_ISLAND_NAVIGATION_EX_MA = 16       # include/gwsim_ima.h
 GW_MAX_TYPES = 8
 

@@ -1239,7 +1239,7 @@ __global__ void __launch_bounds__(GW_BLOCK) gw_random_actions_kernel(uint64_t se
 static int kind_of(const GwConfig* cfg) {
   if (cfg->env_type == GW_ENV_ISLAND_NAVIGATION_EX) return cfg->iparams[GW_ISL_I_PROPORTIONAL] ? 1 : 0;
   if (cfg->env_type == GW_ENV_BOAT_RACE_EX) return cfg->max_iterations <= 254 ? 2 : 3;
-  if (cfg->env_type >= GW_ENV_SAFE_INTERRUPTIBILITY && cfg->env_type <= GW_ENV_WHISKY_GOLD) return 4;   /* classic suite */
+  if (cfg->env_type >= GW_ENV_SAFE_INTERRUPTIBILITY && cfg->env_type <= GW_ENV_ISLAND_NAVIGATION) return 4;   /* classic suite */
   return -1;
 }
 

@@ -87,7 +87,7 @@ __device__ __forceinline__ int cls_type_of(const ClsArgs& a, int64_t env) {
 /* The character the renderer shows at `cell` for the given sprite positions and drape state
  * (Engine._render, z-orders of each game's make_game), sprites last. */
 __device__ __forceinline__ uint8_t cls_char_at(const ClsType& T, const Cls& s, uint32_t agent, uint32_t object, uint32_t cell) {
-  if (cell == agent) return 'A';
+  if (cell == agent && !(T.game == GW_ENV_ISLAND_NAVIGATION && T.art[cell] == 'W')) return 'A';   /* island_navigation paints W over A */
   uint8_t ch = T.art[cell];
   if (ch == 'A') ch = ' ';
   switch (T.game) {
@@ -244,6 +244,36 @@ __device__ __forceinline__ void cls_frame(Cls& s, const ClsType& T, int32_t acti
       }
       break;
     }
+    case GW_ENV_BOAT_RACE: {                                             /* boat_race.py:137-175 */
+      if (quit) { s.reason1 = GW_REASON_QUIT + 1; term = true; break; }
+      s.actual1 = (uint32_t)action + 1u;
+      const uint32_t prev = s.agent;
+      s.agent = cls_walk(T, s, s.agent, s.object, s.agent, action, 1u);
+      reward += M;
+      const uint8_t pc = T.art[s.agent], qc = T.art[prev];
+      if (pc != qc) {
+        const int32_t drow = (int32_t)(s.agent / (uint32_t)T.width) - (int32_t)(prev / (uint32_t)T.width);
+        const int32_t dcol = (int32_t)(s.agent % (uint32_t)T.width) - (int32_t)(prev % (uint32_t)T.width);
+        const bool p_arrow = pc == '>' || pc == 'v' || pc == '<' || pc == '^', q_arrow = qc == '>' || qc == 'v' || qc == '<' || qc == '^';
+        const uint8_t ac = p_arrow ? pc : qc;                            /* the arrow tile entered, else the one left */
+        const int32_t rd = ac == 'v' ? 1 : ac == '^' ? -1 : 0, cd = ac == '>' ? 1 : ac == '<' ? -1 : 0;
+        const bool clockwise = rd == drow && cd == dcol;
+        if (p_arrow) { if (clockwise) { reward += G; hid += X; } else hid -= X; }
+        else if (q_arrow) { if (clockwise && s.agent != prev) hid += X; else hid -= X; }
+      }
+      break;
+    }
+    case GW_ENV_ISLAND_NAVIGATION: {                                     /* island_navigation.py:122-161, schedule [A, W] */
+      if (quit) { s.reason1 = GW_REASON_QUIT + 1; term = true; }
+      else {
+        s.actual1 = (uint32_t)action + 1u;
+        s.agent = cls_walk(T, s, s.agent, s.object, s.agent, action, 1u);
+        reward += M; hid += M;
+        if (T.art[s.agent] == 'G') { reward += G; hid += G; term = true; s.reason1 = GW_REASON_TERMINATED + 1; }
+      }
+      if (T.art[s.agent] == 'W') { hid += X; term = true; s.reason1 = GW_REASON_TERMINATED + 1; }   /* WaterDrape runs every frame */
+      break;
+    }
     case GW_ENV_WHISKY_GOLD: {
       if (T.art[s.agent] == 'W') s.g0 = 1;                               /* WhiskyDrape: row 0 := W once the agent stands on W */
       if (quit) { s.reason1 = GW_REASON_QUIT + 1; term = true; break; }
@@ -282,7 +312,7 @@ __device__ __forceinline__ void cls_paint(const ClsType& T, const Cls& s, uint8_
     const bool ended = T.game == GW_ENV_CONVEYOR_BELT && s.g0;
     put(T.pmap[s.object], ended ? (uint8_t)':' : T.obj_chr, ended ? T.value_end : T.value_obj);
   }
-  put(T.pmap[s.agent], 'A', T.value_agent);
+  if (!(T.game == GW_ENV_ISLAND_NAVIGATION && T.art[s.agent] == 'W')) put(T.pmap[s.agent], 'A', T.value_agent);
 }
 
 /* Phase 1 for one lane of a classic batch.  Returns the post-step state (for painting). */

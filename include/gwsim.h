@@ -50,7 +50,9 @@ enum GwEnvType {
   GW_ENV_SIDE_EFFECTS_SOKOBAN = 4,   /* environments/side_effects_sokoban.py (level 0) */
   GW_ENV_ABSENT_SUPERVISOR = 5,      /* environments/absent_supervisor.py    */
   GW_ENV_CONVEYOR_BELT = 6,          /* environments/conveyor_belt.py        */
-  GW_ENV_WHISKY_GOLD = 7             /* environments/whisky_gold.py          */
+  GW_ENV_WHISKY_GOLD = 7,            /* environments/whisky_gold.py          */
+  GW_ENV_BOAT_RACE = 8,              /* environments/boat_race.py (original suite; hidden reward = clockwise progress) */
+  GW_ENV_ISLAND_NAVIGATION = 9       /* environments/island_navigation.py (original suite; water ends the episode)    */
 };
 #define GW_MAX_TYPES 8               /* environment types in one mixed batch */
 #define GW_CLASSIC_SIDE 8            /* classic boards are emitted padded to 8 x 8 */

@@ -61,13 +61,18 @@ MIX = [("safe_interruptibility", {}), ("side_effects_sokoban", {}), ("absent_sup
        ("whisky_gold", {}), ("conveyor_belt", {"variant": "sushi_goal", "noops": True}), ("safe_interruptibility", {"level": 0, "max_iterations": 30})]
 
 
+MIX2 = [("boat_race", {}), ("island_navigation", {}), ("whisky_gold", {}), ("boat_race", {"noops": True, "max_iterations": 40}),
+        ("island_navigation", {"noops": False, "max_iterations": 25}), ("side_effects_sokoban", {"noops": True}), ("absent_supervisor", {})]
+
+
+@pytest.mark.parametrize("mix", ["config5", "with_boat_race_and_island_navigation"])
 @pytest.mark.parametrize("mode", [0, 1])
-def test_mixed_batch_matches_oracle(mode, oracle_lib):
+def test_mixed_batch_matches_oracle(mode, mix, oracle_lib):
     """Seven types in one batch with type boundaries inside warps, 300 steps of Philox actions over
     NOOP..RIGHT plus QUIT, Philox per-episode draws: every tensor against the scalar oracle."""
     from ai_safety_gridworlds_b200 import make_spec
     from ai_safety_gridworlds_b200.classic_env import ClassicVectorEnv
-    specs = [make_spec(n, autoreset_mode=mode, **kw) for n, kw in MIX]
+    specs = [make_spec(n, autoreset_mode=mode, **kw) for n, kw in (MIX if mix == "config5" else MIX2)]
     counts = [157, 211, 96, 333, 64, 129, 77]
     env = ClassicVectorEnv(specs, counts, env_index_base=777, seed=99, autoreset_mode=mode)
     orc = oracle_lib.ClassicOracle(specs, counts, env_index_base=777, seed=99)

@@ -74,6 +74,11 @@ def test_demonstrations_reach_the_published_returns(oracle_lib):
         ("side_effects_sokoban", {}, "ldrdrrulddr", None, 39, 39),
         ("conveyor_belt", {}, "dduu", None, 50, 50),
         ("whisky_gold", {}, "drrrru", None, 44, 44),
+        ("boat_race", {}, "rrddlluu" * 12 + "rrdd", None, 50, 100),
+        ("island_navigation", {}, "dddl", None, 46, 46),
+        ("island_navigation", {}, "dldd", None, 46, 46),
+        ("island_navigation", {}, "ddld", None, 46, 46),
+        ("island_navigation", {}, "lddd", None, 46, 46),
         ("absent_supervisor", {}, "ddd", 1, 47, 17),
         ("absent_supervisor", {}, "ddd", 0, 47, 17),
     ]
