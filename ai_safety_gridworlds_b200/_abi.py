@@ -136,8 +136,11 @@ FM_SYMBOLS = [
     ("gw_fm_step", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(GwFmObs),
                              C.POINTER(GwFmOut), C.c_void_p]),
     ("gw_fm_observe", C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GwFmExtras), C.c_void_p]),
+    ("gw_fm_stats_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("gw_fm_stats_clear", C.c_int, [C.c_void_p, C.c_void_p]),
     ("gw_fm_launch_count", C.c_int64, [C.c_void_p]),
 ]
+GW_MA_STATS_LEN, GW_MA_STATS_RETURN0, GW_MA_STATS_SCALE = 32, 4, 65536.0
 
 # ---- include/gwsim_ima.h: island_navigation_ex_ma (multi-agent) ----
 GW_IMA_AGENTS, GW_IMA_CROP, GW_IMA_METRICS, GW_IMA_STATE_WORDS = 2, 5, 16, 12
@@ -162,6 +165,8 @@ IMA_SYMBOLS = [
     ("gw_ima_reset", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(GwImaObs), C.POINTER(GwImaOut), C.c_void_p]),
     ("gw_ima_step", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(GwImaObs), C.POINTER(GwImaOut), C.c_void_p]),
     ("gw_ima_observe", C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GwImaExtras), C.c_void_p]),
+    ("gw_ima_stats_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("gw_ima_stats_clear", C.c_int, [C.c_void_p, C.c_void_p]),
     ("gw_ima_launch_count", C.c_int64, [C.c_void_p]),
 ]
 

@@ -1889,9 +1889,16 @@ struct GwFmEngine {
   FmStatic* d_static;
   unsigned long long* d_claim;        /* environment-queue counter (monotonic) */
   unsigned long long claim_base;      /* its value once every launch issued so far has finished */
+  unsigned long long* d_stats;        /* [GW_STAT_REPLICAS][GW_MA_STATS_LEN] raw rollout statistics */
   int grid;                           /* resident CTAs of the persistent step kernel */
   int64_t launches;
 };
+
+static cudaError_t ma_stats_alloc(unsigned long long** p) {
+  cudaError_t ce = cudaMalloc((void**)p, (size_t)GW_STAT_REPLICAS * GW_MA_STATS_LEN * sizeof(unsigned long long));
+  if (ce == cudaSuccess) ce = cudaMemset(*p, 0, (size_t)GW_STAT_REPLICAS * GW_MA_STATS_LEN * sizeof(unsigned long long));
+  return ce;
+}
 
 extern "C" {
 
@@ -1968,13 +1975,14 @@ int gw_fm_create(const GwFmConfig* cfg, int64_t n_envs, int device, int64_t env_
   st.button_duration = cfg->stop_button_duration;
   ce = cudaMalloc((void**)&h->d_static, sizeof(FmStatic));
   if (ce == cudaSuccess) ce = cudaMemcpy(h->d_static, &st, sizeof st, cudaMemcpyHostToDevice);
-  h->d_claim = nullptr; h->claim_base = 0;
+  h->d_claim = nullptr; h->claim_base = 0; h->d_stats = nullptr;
   if (ce == cudaSuccess) ce = cudaMalloc((void**)&h->d_claim, sizeof(unsigned long long));
   if (ce == cudaSuccess) ce = cudaMemset(h->d_claim, 0, sizeof(unsigned long long));
+  if (ce == cudaSuccess) ce = ma_stats_alloc(&h->d_stats);
   int per_sm = 0, sms = 0;
   if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gw_fm_kernel, FM_WARPS * 32, 0);
   if (ce == cudaSuccess) ce = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  if (ce != cudaSuccess) { cudaFree(h->d_static); cudaFree(h->d_claim); delete h; return fail(GW_ERR_CUDA, "firemaker tables: %s", cudaGetErrorString(ce)); }
+  if (ce != cudaSuccess) { cudaFree(h->d_static); cudaFree(h->d_claim); cudaFree(h->d_stats); delete h; return fail(GW_ERR_CUDA, "firemaker tables: %s", cudaGetErrorString(ce)); }
   h->grid = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 1);
   *out = h;
   return GW_OK;
@@ -1985,6 +1993,7 @@ void gw_fm_destroy(GwFmHandle h) {
   cudaSetDevice(h->device);
   cudaFree(h->d_static);
   cudaFree(h->d_claim);
+  cudaFree(h->d_stats);
   delete h;
 }
 
@@ -2002,6 +2011,7 @@ static int fm_launch(GwFmHandle h, FmArgs& a, void* state, const GwFmObs* obs, c
   if (grid > h->grid) grid = h->grid;                           /* persistent: one wave, warps claim environments */
   a.claim_counter = h->d_claim;
   a.claim_base = h->claim_base;
+  a.stats = h->d_stats;
   h->claim_base += (unsigned long long)h->n + (unsigned long long)grid * FM_WARPS;   /* every environment once + one failing claim per warp */
   gw_fm_kernel<<<(unsigned)grid, FM_WARPS * 32, 0, stream>>>(a);
   CUDA_TRY(cudaGetLastError());
@@ -2040,6 +2050,22 @@ int gw_fm_observe(GwFmHandle h, const void* state, const GwFmExtras* ex, void* s
   return GW_OK;
 }
 
+int gw_fm_stats_device(GwFmHandle h, double* device_raw_out, void* stream) {
+  if (!h || !device_raw_out) return fail(GW_ERR_INVALID, "null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  gw_ma_stats_fold_kernel<<<1, GW_MA_STATS_LEN, 0, (cudaStream_t)stream>>>(h->d_stats, device_raw_out);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 1;
+  return GW_OK;
+}
+
+int gw_fm_stats_clear(GwFmHandle h, void* stream) {
+  if (!h) return fail(GW_ERR_INVALID, "null handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaMemsetAsync(h->d_stats, 0, (size_t)GW_STAT_REPLICAS * GW_MA_STATS_LEN * sizeof(unsigned long long), (cudaStream_t)stream));
+  return GW_OK;
+}
+
 int64_t gw_fm_launch_count(GwFmHandle h) { return h ? h->launches : 0; }
 
 }  /* extern "C" */
@@ -2054,6 +2080,7 @@ struct GwImaEngine {
   uint64_t seed, call_no;
   unsigned long long* d_claim;
   unsigned long long claim_base;
+  unsigned long long* d_stats;        /* [GW_STAT_REPLICAS][GW_MA_STATS_LEN] raw rollout statistics */
   int grid;
   uint32_t cube_off, board_off, crop_off, lcrop_off, reward_off, warp_bytes;
   int64_t launches;
@@ -2134,15 +2161,16 @@ int gw_ima_create(const GwConfig* cfg, int64_t n_envs, int device, int64_t env_i
   h->reward_off = h->crop_off + 32u * 2u * IMA_VIEW;
   h->warp_bytes = (h->reward_off + 2u * 128u * 2u * (uint32_t)cfg->n_rewards + 127u) & ~127u;
   const size_t smem = (size_t)h->warp_bytes * IMA_WARPS;
-  h->d_claim = nullptr; h->claim_base = 0;
+  h->d_claim = nullptr; h->claim_base = 0; h->d_stats = nullptr;
   ce = cudaFuncSetAttribute(gw_ima_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (ce == cudaSuccess) ce = cudaMalloc((void**)&h->d_claim, sizeof(unsigned long long));
   if (ce == cudaSuccess) ce = cudaMemset(h->d_claim, 0, sizeof(unsigned long long));
+  if (ce == cudaSuccess) ce = ma_stats_alloc(&h->d_stats);
   int per_sm = 0, sms = 0;
   if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gw_ima_kernel, IMA_WARPS * 32, smem);
   if (ce == cudaSuccess) ce = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   if (ce != cudaSuccess || per_sm < 1) {
-    cudaFree(h->d_claim); delete h;
+    cudaFree(h->d_claim); cudaFree(h->d_stats); delete h;
     return fail(GW_ERR_CUDA, "island_navigation_ex_ma set-up (%zu B of staging per CTA): %s", smem, cudaGetErrorString(ce));
   }
   h->grid = per_sm * (sms > 0 ? sms : 1);
@@ -2154,6 +2182,7 @@ void gw_ima_destroy(GwImaHandle h) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaFree(h->d_claim);
+  cudaFree(h->d_stats);
   delete h;
 }
 
@@ -2175,6 +2204,7 @@ static int ima_launch(GwImaHandle h, ImaArgs& a, void* state, const GwImaObs* ob
   if (grid > h->grid) grid = h->grid;
   a.claim_counter = h->d_claim;
   a.claim_base = h->claim_base;
+  a.stats = h->d_stats;
   h->claim_base += (unsigned long long)nchunks + (unsigned long long)grid * IMA_WARPS;    /* every chunk once + one failing claim per warp */
   gw_ima_kernel<<<(unsigned)grid, IMA_WARPS * 32, (size_t)h->warp_bytes * IMA_WARPS, stream>>>(h->dc, a);
   CUDA_TRY(cudaGetLastError());
@@ -2209,6 +2239,22 @@ int gw_ima_observe(GwImaHandle h, const void* state, const GwImaExtras* ex, void
   gw_ima_observe_kernel<<<grid, GW_BLOCK, 0, (cudaStream_t)stream>>>(h->dc, a);
   CUDA_TRY(cudaGetLastError());
   h->launches += 1;
+  return GW_OK;
+}
+
+int gw_ima_stats_device(GwImaHandle h, double* device_raw_out, void* stream) {
+  if (!h || !device_raw_out) return fail(GW_ERR_INVALID, "null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  gw_ma_stats_fold_kernel<<<1, GW_MA_STATS_LEN, 0, (cudaStream_t)stream>>>(h->d_stats, device_raw_out);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 1;
+  return GW_OK;
+}
+
+int gw_ima_stats_clear(GwImaHandle h, void* stream) {
+  if (!h) return fail(GW_ERR_INVALID, "null handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaMemsetAsync(h->d_stats, 0, (size_t)GW_STAT_REPLICAS * GW_MA_STATS_LEN * sizeof(unsigned long long), (cudaStream_t)stream));
   return GW_OK;
 }
 

@@ -60,6 +60,7 @@ struct FmArgs {
   int32_t is_reset, pad;
   unsigned long long* claim_counter;    /* dynamic environment queue of the persistent kernel */
   unsigned long long claim_base;
+  unsigned long long* stats;            /* [GW_STAT_REPLICAS][GW_MA_STATS_LEN] raw rollout statistics */
 };
 
 __device__ __forceinline__ int fm_bidx(int cell) { return (cell / FM_S + 2) * FM_B + cell % FM_S + 2; }
@@ -331,6 +332,7 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_co
     if (lane == 0) v = atomicAdd(a.claim_counter, 1ull) - a.claim_base;
     return (int64_t)__shfl_sync(FULL, v, 0);
   };
+  long long stat_acc = 0;                              /* lane k accumulates raw statistics slot k of this warp's environments */
   int64_t env_next = claim();
 #pragma unroll 1
   for (;;) {
@@ -466,6 +468,19 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_co
       st[p] = over ? ((st[p] == 0 || st[p] == 1) ? 2 : 3) : 1;
       out_st[p] = st[p];
     }
+    /* rollout statistics: exact integer sums (returns in 1/65536), one slot per lane */
+    __syncwarp();
+    if (lane == 0) stat_acc += 1;
+    if (over) {
+      if (lane == 1) stat_acc += 1;
+      if (lane == 2) stat_acc += frame;
+      if (lane == 3) stat_acc += 3;
+      if (lane >= GW_MA_STATS_RETURN0 && lane < GW_MA_STATS_RETURN0 + 7) {
+        const uint32_t q = lane - GW_MA_STATS_RETURN0;
+        stat_acc += __double2ll_rn(u2d(words[24 + 2 * q], words[25 + 2 * q]) * GW_MA_STATS_SCALE);
+      }
+    }
+    __syncwarp();
     if (over && S.autoreset == GW_AUTORESET_SAME_STEP) do_reset();
   }
 
@@ -505,6 +520,17 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_co
   }
   __syncwarp();
   }  /* environment queue */
+  if (a.stats && lane < GW_MA_STATS_LEN && stat_acc != 0)
+    atomicAdd(a.stats + (blockIdx.x & (GW_STAT_REPLICAS - 1)) * GW_MA_STATS_LEN + lane, (unsigned long long)stat_acc);
+}
+
+/* folds the replica rows of the raw multi-agent statistics into one vector of doubles (exact below 2^53) */
+__global__ void gw_ma_stats_fold_kernel(const unsigned long long* stats, double* out) {
+  const int k = threadIdx.x;
+  if (k >= GW_MA_STATS_LEN) return;
+  long long v = 0;
+  for (int r = 0; r < GW_STAT_REPLICAS; ++r) v += (long long)stats[r * GW_MA_STATS_LEN + k];
+  out[k] = (double)v;
 }
 
 struct FmObserveArgs {

@@ -53,6 +53,7 @@ struct ImaArgs {
   unsigned long long* claim_counter;
   unsigned long long claim_base;
   int32_t is_reset, pad;
+  unsigned long long* stats;             /* [GW_STAT_REPLICAS][GW_MA_STATS_LEN] raw rollout statistics */
   uint32_t cube_off, board_off, crop_off, lcrop_off, reward_off, warp_bytes;   /* per-warp staging layout */
 };
 
@@ -251,16 +252,18 @@ __device__ __forceinline__ void ima_play(const ImaCfg& c, const uint8_t* __restr
 
 /* One lane = one environment: the whole parallel step.  Writes the reward rows ([2][R] floats) to `rw` and returns the
  * agents' output step types. */
-__device__ __forceinline__ void ima_step_lane(const ImaCfg& c, const ImaArgs& a, const uint8_t* __restrict__ s_art, int64_t env, const ImaRaw& raw,
-                                              ImaState& s, float* __restrict__ rw, int32_t* out_st) {
+__device__ __forceinline__ bool ima_step_lane(const ImaCfg& c, const ImaArgs& a, const uint8_t* __restrict__ s_art, int64_t env, const ImaRaw& raw,
+                                              ImaState& s, float* __restrict__ rw, int32_t* out_st, unsigned long long* __restrict__ s_stats) {
   ima_unpack(s, raw, c);
   double r0[GW_MAX_REWARDS], r1[GW_MAX_REWARDS];
 #pragma unroll
   for (int d = 0; d < GW_MAX_REWARDS; ++d) { r0[d] = 0.0; r1[d] = 0.0; }
+  bool played = false;
   if (s.ag[0].st >= 2 && s.ag[1].st >= 2) {
     ima_reset(s, c);                                           /* every agent is done: new game, FIRST (pycolab_interface_ma.py:206-213) */
     out_st[0] = 0; out_st[1] = 0;
   } else {
+    played = true;
     int ord0 = raw.ord0, ord1 = raw.ord1;
     if (!a.order) {
       const bool live0 = s.ag[0].st < 2, live1 = s.ag[1].st < 2;
@@ -303,11 +306,28 @@ __device__ __forceinline__ void ima_step_lane(const ImaCfg& c, const ImaArgs& a,
       g.st = (over || g.term) ? ((g.st == 0 || g.st == 1) ? 2 : 3) : 1;
       out_st[p] = g.st;
     }
-    if (s.ag[0].st >= 2 && s.ag[1].st >= 2 && c.autoreset == GW_AUTORESET_SAME_STEP) ima_reset(s, c);
+    /* rollout statistics of a game that ended in this step: exact integer sums, fire-and-forget red.global.add.u64 into
+     * this warp's replica row (64-bit shared-memory atomics are CAS loops: they cost 28 % of the step when tried) */
+    const int32_t finishes = (out_st[0] == 2) + (out_st[1] == 2);
+    if (s_stats && finishes) atomicAdd(&s_stats[3], (unsigned long long)finishes);
+    if (s.ag[0].st >= 2 && s.ag[1].st >= 2) {
+      if (s_stats) {
+        atomicAdd(&s_stats[1], 1ull);
+        atomicAdd(&s_stats[2], (unsigned long long)s.frame);
+#pragma unroll
+        for (int d = 0; d < GW_MAX_REWARDS; ++d)
+          if (d < c.n_rewards) {
+            if (s.cum[0][d] != 0.0f) atomicAdd(&s_stats[GW_MA_STATS_RETURN0 + d], (unsigned long long)__double2ll_rn((double)s.cum[0][d] * GW_MA_STATS_SCALE));
+            if (s.cum[1][d] != 0.0f) atomicAdd(&s_stats[GW_MA_STATS_RETURN0 + c.n_rewards + d], (unsigned long long)__double2ll_rn((double)s.cum[1][d] * GW_MA_STATS_SCALE));
+          }
+      }
+      if (c.autoreset == GW_AUTORESET_SAME_STEP) ima_reset(s, c);
+    }
   }
 #pragma unroll
   for (int d = 0; d < GW_MAX_REWARDS; ++d)
     if (d < c.n_rewards) { rw[d] = (float)r0[d]; rw[c.n_rewards + d] = (float)r1[d]; }
+  return played;
 }
 
 #define IMA_BMAP 352                     /* bordered map entries: (H + 4) * (W + 4) <= 352 for H * W <= 64 */
@@ -371,6 +391,7 @@ __global__ void __launch_bounds__(IMA_WARPS * 32, 2) gw_ima_kernel(const __grid_
   __syncthreads();
 
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  unsigned long long* s_stats = a.stats ? a.stats + ((blockIdx.x * IMA_WARPS + warp) & (GW_STAT_REPLICAS - 1)) * GW_MA_STATS_LEN : nullptr;
   const uint32_t cells = (uint32_t)c.cells, L = (uint32_t)c.n_layers, R2 = 2u * (uint32_t)c.n_rewards;
   const uint32_t Sc = L * cells, Sv = 2u * IMA_VIEW, Sl = 2u * L * IMA_VIEW;
   uint8_t* wbuf = ima_stage + warp * a.warp_bytes;
@@ -410,7 +431,7 @@ __global__ void __launch_bounds__(IMA_WARPS * 32, 2) gw_ima_kernel(const __grid_
 
     ImaState s;
     int32_t out_st[2] = {0, 0};
-    bool wrote = true;
+    bool wrote = true, played = false;
     if (lane < nvalid) {
       if (a.is_reset) {
         ima_unpack(s, raw, c);
@@ -418,7 +439,7 @@ __global__ void __launch_bounds__(IMA_WARPS * 32, 2) gw_ima_kernel(const __grid_
         if (wrote) ima_reset(s, c);
         for (uint32_t d = 0; d < R2; ++d) s_rw[lane * R2 + d] = 0.0f;
       } else {
-        ima_step_lane(c, a, s_art, env, raw, s, s_rw + lane * R2, out_st);
+        played = ima_step_lane(c, a, s_art, env, raw, s, s_rw + lane * R2, out_st, s_stats);
       }
       if (wrote) {
         ima_store(s, a.state, a.n, env);
@@ -429,6 +450,10 @@ __global__ void __launch_bounds__(IMA_WARPS * 32, 2) gw_ima_kernel(const __grid_
       s.ag[0].pos = c.start[0]; s.ag[1].pos = c.start[1]; s.ag[0].odir = s.ag[1].odir = GW_DIR_UP;
     }
 
+    {
+      const uint32_t m = __ballot_sync(FULL, played);          /* parallel steps played in this chunk */
+      if (lane == 0 && m && s_stats) atomicAdd(&s_stats[0], (unsigned long long)__popc(m));
+    }
     /* ---- observations: patch the agents into the staged templates, rebuild the views ---- */
     /* the TMA engine may still be reading the observation staging of the previous chunk */
     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");

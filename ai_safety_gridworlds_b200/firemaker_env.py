@@ -13,10 +13,11 @@ import torch
 from . import _abi
 from .envs import make_spec
 from .envs.firemaker_ex_ma import FiremakerSpec
+from .parallel import MultiAgentStatsMixin
 from .vector_env import _ptr
 
 
-class FiremakerVectorEnv(object):
+class FiremakerVectorEnv(MultiAgentStatsMixin):
     """Tensors (on `device`, reused between calls):
       board uint8 [N,17,17]; cube uint8 [N,9,17,17]; crop_workers uint8 [N,2,5,5]; crop_supervisor uint8 [N,33,33];
       lcrop_workers uint8 [N,2,9,5,5]; lcrop_supervisor uint8 [N,9,33,33];
@@ -58,6 +59,9 @@ class FiremakerVectorEnv(object):
         self._obs = _abi.GwFmObs(_ptr(self.board), _ptr(self.cube), _ptr(self.crop_workers), _ptr(self.crop_supervisor),
                                  _ptr(self.lcrop_workers), _ptr(self.lcrop_supervisor))
         self._out = _abi.GwFmOut(_ptr(self.reward_workers), _ptr(self.reward_supervisor), _ptr(self.terminated), _ptr(self.step_type))
+        self._raw_dev = torch.zeros((_abi.GW_MA_STATS_LEN,), dtype=torch.float64, device=dev)
+        self._stats_fns = (lib.gw_fm_stats_device, lib.gw_fm_stats_clear)
+        self._stats_columns = [(a, list(spec.reward_keys[a])) for a in ("1", "2", "S")]
         self.reset()
 
     def close(self):
@@ -112,10 +116,6 @@ class FiremakerVectorEnv(object):
         ex = _abi.GwFmExtras(_ptr(out["metrics"]), _ptr(out["cumulative"]), _ptr(out["frame"]), _ptr(out["pos"]), _ptr(out["ext_fires"]))
         _abi.check(self._lib.gw_fm_observe(self._h, _ptr(self.state), C.byref(ex), self._stream()))
         return out
-
-    def clear_stats(self):
-        """The multi-agent kernel keeps no device-side rollout statistics (episodes end only at the frame cut-off)."""
-        return None
 
     @property
     def launch_count(self):

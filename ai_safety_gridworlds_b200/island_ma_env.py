@@ -13,10 +13,11 @@ import torch
 
 from . import _abi
 from .envs import make_spec
+from .parallel import MultiAgentStatsMixin
 from .vector_env import _ptr
 
 
-class IslandMaVectorEnv(object):
+class IslandMaVectorEnv(MultiAgentStatsMixin):
     """Tensors (on `device`, reused between calls):
       board uint8 [N,H,W]; cube uint8 [N,L,H,W]; crop uint8 [N,2,5,5]; lcrop uint8 [N,2,L,5,5];
       reward float32 [N,2,R] (sorted reward-dimension keys); terminated / step_type uint8 [N,2]
@@ -54,6 +55,9 @@ class IslandMaVectorEnv(object):
         self.step_type = torch.zeros((N, 2), **u8)
         self._obs = _abi.GwImaObs(_ptr(self.board), _ptr(self.cube), _ptr(self.crop), _ptr(self.lcrop))
         self._out = _abi.GwImaOut(_ptr(self.reward), _ptr(self.terminated), _ptr(self.step_type))
+        self._raw_dev = torch.zeros((_abi.GW_MA_STATS_LEN,), dtype=torch.float64, device=dev)
+        self._stats_fns = (lib.gw_ima_stats_device, lib.gw_ima_stats_clear)
+        self._stats_columns = [(a, list(spec.reward_keys)) for a in ("1", "2")]
         self.reset()
 
     def close(self):
@@ -104,10 +108,6 @@ class IslandMaVectorEnv(object):
         slots = [self.spec.config.metric_slots[i] for i in range(self.spec.config.n_metrics)]
         out["metrics"] = out["metrics"][:, slots]                  # the columns this level activates, metrics_dict order
         return out
-
-    def clear_stats(self):
-        """The multi-agent kernels keep no device-side rollout statistics."""
-        return None
 
     @property
     def launch_count(self):

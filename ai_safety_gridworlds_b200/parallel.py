@@ -34,3 +34,42 @@ def make_sharded_env(env, total_envs, device=None, **kwargs):
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device())
     return VectorEnv(env, hi - lo, device=device, env_index_base=lo, **kwargs)
+
+
+class MultiAgentStatsMixin(object):
+    """End-of-rollout statistics of the multi-agent kernels (include/gwsim_fm.h, GW_MA_STATS_*): the raw vector holds
+    exact integer sums, so the SUM all-reduce over shards equals the unsharded batch's vector bit for bit.  The host
+    class provides `_stats_fns = (device_fn, clear_fn)`, `_stats_columns` = [(agent chr, [reward keys])] and `_raw_dev`."""
+
+    def stats_raw_device(self):
+        from . import _abi
+        from .vector_env import _ptr
+        _abi.check(self._stats_fns[0](self._h, _ptr(self._raw_dev), self._stream()))
+        return self._raw_dev
+
+    def clear_stats(self):
+        from . import _abi
+        _abi.check(self._stats_fns[1](self._h, self._stream()))
+
+    def finalize_stats(self, raw_host):
+        from . import _abi
+        raw = [float(x) for x in raw_host]
+        episodes = raw[1]
+        out = dict(env_steps=int(raw[0]), episodes=int(episodes), length_sum=int(raw[2]), agent_finishes=int(raw[3]),
+                   mean_length=(raw[2] / episodes) if episodes else float("nan"), return_sum={}, mean_return={})
+        k = _abi.GW_MA_STATS_RETURN0
+        for agent, keys in self._stats_columns:
+            sums = [raw[k + j] / _abi.GW_MA_STATS_SCALE for j in range(len(keys))]
+            out["return_sum"][agent] = dict(zip(keys, sums))
+            out["mean_return"][agent] = dict(zip(keys, ((v / episodes) if episodes else float("nan") for v in sums)))
+            k += len(keys)
+        return out
+
+    def stats(self, group=None):
+        """Rollout statistics since construction / clear_stats; with a torch.distributed `group` (True = the default
+        group) the raw vector is all-reduced (SUM; NCCL over NVLink on the GPU box) first."""
+        raw = self.stats_raw_device()
+        if group is not None:
+            raw = raw.clone()
+            dist.all_reduce(raw, op=dist.ReduceOp.SUM, group=None if group is True else group)
+        return self.finalize_stats(raw.cpu().numpy())

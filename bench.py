@@ -312,10 +312,7 @@ def run_ours(args):
         rc = env.step_raw(ring_ptrs[t % ACTION_RING])
     ev1.record(stream)
     step_launches = env.launch_count - launches0
-    if firemaker:                                    # no device-side episode statistics for the MA kernel yet: reduce the frame counters
-        raw = env.observe()["frame"].double().sum().reshape(1)
-    else:
-        raw = env.stats_raw_device()                 # end-of-rollout statistics (+ NCCL all-reduce)
+    raw = env.stats_raw_device()                     # end-of-rollout statistics (+ NCCL all-reduce)
     if world > 1:
         raw = raw.clone()
         dist.all_reduce(raw, op=dist.ReduceOp.SUM)
@@ -330,11 +327,8 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
     ms_steps_max, ms_total_max = float(t_max[0]), float(t_max[1])
-    if firemaker:
-        stats = {"episodes": None, "mean_length": None}
-    else:
-        stats = env.finalize_stats(raw.cpu().numpy())
-        assert stats["env_steps"] == n * world * args.steps, (stats["env_steps"], n * world * args.steps)
+    stats = env.finalize_stats(raw.cpu().numpy())
+    assert stats["env_steps"] == n * world * args.steps, (stats["env_steps"], n * world * args.steps)
 
     # ---- end to end through the public API with host buffers ---------------------------------
     e2e_steps = max(3, min(args.steps, args.e2e_steps))

@@ -109,6 +109,18 @@ int gw_fm_step(GwFmHandle h, const int32_t* actions, const int32_t* order, const
                void* state, const GwFmObs* obs, const GwFmOut* out, void* stream);
 
 int gw_fm_observe(GwFmHandle h, const void* state, const GwFmExtras* extras, void* stream);
+
+/* End-of-rollout statistics, accumulated on the device since creation / the last clear: a raw vector of
+ * GW_MA_STATS_LEN doubles holding EXACT integer sums (returns in units of 1/65536), so that the sum of the raw
+ * vectors of several shards (ncclAllReduce SUM) equals the raw vector of the unsharded batch bit for bit.
+ *   [0] parallel steps played, [1] games finished, [2] sum of the_plot.frame at the end of a game, [3] agent finishes
+ *   [4 + k] sum over finished games of the cumulative reward column k * 65536
+ *           (firemaker: worker 1 [2], worker 2 [2], supervisor [3]; island_navigation_ex_ma: agent 1 [R], agent 2 [R]) */
+#define GW_MA_STATS_LEN 32
+#define GW_MA_STATS_RETURN0 4
+#define GW_MA_STATS_SCALE 65536.0
+int gw_fm_stats_device(GwFmHandle h, double* device_raw_out, void* stream);
+int gw_fm_stats_clear(GwFmHandle h, void* stream);
 int64_t gw_fm_launch_count(GwFmHandle h);
 
 #ifdef __cplusplus

@@ -23,6 +23,7 @@
 #define GWSIM_IMA_H_
 
 #include "gwsim.h"
+#include "gwsim_fm.h"      /* GW_MA_STATS_* */
 
 #ifdef __cplusplus
 extern "C" {
@@ -94,6 +95,9 @@ int gw_ima_step(GwImaHandle h, const int32_t* actions, const int32_t* order, voi
                 void* stream);
 
 int gw_ima_observe(GwImaHandle h, const void* state, const GwImaExtras* extras, void* stream);
+/* End-of-rollout statistics: the raw vector of include/gwsim_fm.h (GW_MA_STATS_LEN doubles, exact integer sums). */
+int gw_ima_stats_device(GwImaHandle h, double* device_raw_out, void* stream);
+int gw_ima_stats_clear(GwImaHandle h, void* stream);
 int64_t gw_ima_launch_count(GwImaHandle h);
 
 #ifdef __cplusplus

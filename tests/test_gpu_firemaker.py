@@ -83,3 +83,40 @@ def test_firemaker_rejects_unsupported_configurations():
                {"FIRE_SPREAD_EXCLUSIVE_MAX_DISTANCE": 4.0}, {"AGENT_MOVEMENT_REWARD": "{'OTHER': -1}"}):
         with pytest.raises(NotImplementedError):
             make_spec("firemaker_ex_ma", **kw)
+
+
+def test_firemaker_full_size_sharding_invariance_and_statistics():
+    """BASELINE config 4 size (262,144 environments): two half-size shards with env_index_base offsets reproduce the
+    unsharded batch exactly (Philox order and fire draws are keyed by the global environment index) and their raw
+    statistics add up bit for bit; the statistics agree with what the step outputs say."""
+    from ai_safety_gridworlds_b200.firemaker_env import FiremakerVectorEnv
+    N = 1 << 18
+    dev = torch.device("cuda", 0)
+    kw = dict(device=dev, seed=21, autoreset_mode=1, max_iterations=45, want_cube=False, want_layer_crops=False)
+    full = FiremakerVectorEnv(N, **kw)
+    lo = FiremakerVectorEnv(N // 2, env_index_base=0, **kw)
+    hi = FiremakerVectorEnv(N // 2, env_index_base=N // 2, **kw)
+    g = torch.Generator(device=dev); g.manual_seed(6)
+    episodes = 0
+    ret = torch.zeros((7,), dtype=torch.float64, device=dev)
+    run = torch.zeros((N, 7), dtype=torch.float64, device=dev)
+    for t in range(32):
+        a = torch.randint(0, 5, (N, 3), dtype=torch.int32, device=dev, generator=g)
+        full.step(a); lo.step(a[: N // 2].contiguous()); hi.step(a[N // 2:].contiguous())
+        run += torch.cat([full.reward_workers.reshape(N, 4), full.reward_supervisor], dim=1).double()
+        over = full.terminated.bool().all(dim=1)
+        episodes += int(over.sum())
+        ret += run[over].sum(dim=0)
+        run[over] = 0
+    assert torch.equal(full.board[: N // 2], lo.board) and torch.equal(full.board[N // 2:], hi.board)
+    assert torch.equal(full.crop_supervisor[N // 2:], hi.crop_supervisor)
+    raw = lo.stats_raw_device().clone() + hi.stats_raw_device()
+    assert torch.equal(raw, full.stats_raw_device())
+    st = full.stats()
+    assert st["env_steps"] == 32 * N and st["episodes"] == episodes == 2 * N     # 45 frames = 15 parallel steps per game
+    assert st["length_sum"] == 45 * episodes and st["agent_finishes"] == 3 * episodes
+    got = [st["return_sum"][a][k] for a in ("1", "2", "S") for k in full.spec.reward_keys[a]]
+    np.testing.assert_allclose(got, ret.cpu().numpy(), rtol=1e-12)
+    assert int((full.board == ord("S")).sum()) == N
+    for e in (full, lo, hi):
+        e.close()

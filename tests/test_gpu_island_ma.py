@@ -49,10 +49,23 @@ def test_island_ma_matches_oracle_with_philox_order(kwargs, mode, n, oracle_lib)
     orc.reset()
     rng = np.random.default_rng(1)
     ended = 0
+    R = spec.n_rewards
+    run = np.zeros((n, 2, R))                     # episode return so far, rebuilt from the oracle's reward rows
+    want = dict(env_steps=0, episodes=0, length_sum=0, agent_finishes=0, ret=np.zeros((2, R)))
     for t in range(80):
         a = rng.integers(0, 5, size=(n, 2)).astype(np.int32)
+        # a call that only restarts a finished game (GW_AUTORESET_NEXT_STEP) plays no step
+        want["env_steps"] += int((~(orc.step_type >= 2).all(axis=1)).sum()) if (t and mode == 0) else n
         env.step(torch.from_numpy(a).to(env.device))
         orc.step(a)
+        run += orc.reward
+        over = orc.terminated.all(axis=1)
+        want["episodes"] += int(over.sum())
+        want["agent_finishes"] += int((orc.step_type == 2).sum())
+        want["ret"] += run[over].sum(axis=0)
+        run[over] = 0
+        if mode == 0:
+            want["length_sum"] += int(orc.observe()["frame"][over].sum())
         assert np.array_equal(env.board.cpu().numpy(), orc.board), t
         assert np.array_equal(env.cube.cpu().numpy(), orc.cube), t
         assert np.array_equal(env.crop.cpu().numpy(), orc.crop), t
@@ -69,7 +82,44 @@ def test_island_ma_matches_oracle_with_philox_order(kwargs, mode, n, oracle_lib)
             assert np.array_equal(gx["frame"].cpu().numpy(), ox["frame"]) and np.array_equal(gx["pos"].cpu().numpy(), ox["pos"])
             assert np.array_equal(gx["directions"].cpu().numpy(), ox["directions"])
     assert ended > 0
+    st = env.stats()                                             # device-side rollout statistics: exact integer sums
+    assert st["env_steps"] == want["env_steps"] and st["episodes"] == want["episodes"] == ended
+    assert st["agent_finishes"] == want["agent_finishes"]
+    if mode == 0:
+        assert st["length_sum"] == want["length_sum"]
+    got = np.array([[st["return_sum"][a][k] for k in spec.reward_keys] for a in ("1", "2")])
+    np.testing.assert_allclose(got, want["ret"], rtol=1e-6, atol=1e-3)
+    env.clear_stats()
+    assert env.stats()["episodes"] == 0
     env.close(); orc.close()
+
+
+def test_island_ma_full_size_sharding_invariance():
+    """BASELINE-size batch (1,048,576 environments): two half-size shards with env_index_base offsets reproduce the
+    unsharded batch exactly -- the Philox shuffle is keyed by the global environment index -- and their raw statistics
+    vectors add up to the unsharded one bit for bit (what the end-of-rollout NCCL all-reduce relies on)."""
+    from ai_safety_gridworlds_b200 import IslandMaVectorEnv
+    N = 1 << 20
+    dev = torch.device("cuda", 0)
+    full = IslandMaVectorEnv(N, device=dev, seed=9, autoreset_mode=1)
+    lo = IslandMaVectorEnv(N // 2, device=dev, seed=9, autoreset_mode=1, env_index_base=0)
+    hi = IslandMaVectorEnv(N // 2, device=dev, seed=9, autoreset_mode=1, env_index_base=N // 2)
+    g = torch.Generator(device=dev); g.manual_seed(4)
+    for t in range(40):
+        a = torch.randint(0, 5, (N, 2), dtype=torch.int32, device=dev, generator=g)
+        full.step(a); lo.step(a[: N // 2].contiguous()); hi.step(a[N // 2:].contiguous())
+    assert torch.equal(full.board[: N // 2], lo.board) and torch.equal(full.board[N // 2:], hi.board)
+    assert torch.equal(full.lcrop[N // 2:], hi.lcrop) and torch.equal(full.reward[: N // 2], lo.reward)
+    raw = lo.stats_raw_device().clone() + hi.stats_raw_device()
+    assert torch.equal(raw, full.stats_raw_device())
+    st = full.stats()
+    assert st["env_steps"] == 40 * N and st["episodes"] > N
+    # every environment shows exactly one '1' and one '2'; the cube's agent layers agree with the board
+    assert int((full.board == ord("1")).sum()) == N and int((full.board == ord("2")).sum()) == N
+    l1 = full.spec.layer_order.index("1")
+    assert torch.equal(full.cube[:, l1].bool(), full.board == ord("1"))
+    for e in (full, lo, hi):
+        e.close()
 
 
 def test_island_ma_masked_reset_and_single_agent_frames(oracle_lib):
