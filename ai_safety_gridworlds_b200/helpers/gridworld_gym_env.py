@@ -10,7 +10,12 @@ Mirrors helpers/gridworld_gym_env.py of the reference (constructor :99-133, `ste
     returns the first observation, rl/pycolab_interface_mo.py:175-178);
   * `num_envs=N` is the batched form: the same quantities as torch CUDA tensors with a leading
     batch dimension and auto-reset inside the terminal step (the observation returned with
-    `terminated` is the new episode's first frame).
+    `terminated` is the new episode's first frame);
+  * the original-suite games (safe_interruptibility, side_effects_sokoban, absent_supervisor,
+    conveyor_belt, whisky_gold, boat_race, island_navigation) run on the classic kernel: obs
+    float32 [1,H,W], SCALAR reward, and `info['hidden_reward']` = this step's hidden reward
+    (gridworld_gym_env.py:497-506), the way the reference's wrapper serves them
+    (tests/gridworld_gym_env_test.py:63-110 replays the demonstrations through it).
 
 gymnasium itself is not imported: the class is duck-typed, and the two space classes below carry
 what the reference's spaces expose.  Every step is one launch of the fused CUDA kernel; there is
@@ -21,9 +26,11 @@ import torch
 
 from .. import _abi
 from ..envs import make_spec
+from ..envs.classic import CLASSIC_ENV_TYPES
 from ..vector_env import VectorEnv
 
 INFO_OBSERVED_REWARD = "observed_reward"
+INFO_HIDDEN_REWARD = "hidden_reward"
 INFO_DISCOUNT = "discount"
 INFO_OBSERVATION_COORDINATES = "info_observation_coordinates"
 INFO_OBSERVATION_LAYERS_DICT = "info_observation_layers_dict"
@@ -31,7 +38,7 @@ INFO_OBSERVATION_LAYERS_ORDER = "info_observation_layers_order"
 INFO_OBSERVATION_LAYERS_CUBE = "info_observation_layers_cube"
 
 # constructor arguments of the reference wrapper that do not change what the kernel computes
-_WRAPPER_ONLY = ("render_animation_delay", "flatten_observations", "ascii_observation_format", "ascii_attributes_format",
+_WRAPPER_ONLY = ("render_animation_delay", "ascii_observation_format", "ascii_attributes_format",
                  "attribute_coordinates_in_observation", "layers_in_attribute_observation", "occlusion_in_atribute_layers",
                  "observable_attribute_categories", "observable_attribute_value_mapping", "use_multi_discrete_action_space",
                  "agent_character", "np_random", "pre_reset_callback", "post_reset_callback", "pre_step_callback",
@@ -76,8 +83,9 @@ class GridworldGymEnv(object):
     metadata = {"render.modes": ["ansi", "rgb_array"]}
     reward_range = (-float("inf"), float("inf"))
 
-    def __init__(self, env_name, use_transitions=False, object_coordinates_in_observation=True, layers_in_observation=True,
-                 occlusion_in_layers=False, layers_order_in_cube=[], seed=None, num_envs=None, device=None, **kwargs):
+    def __init__(self, env_name, use_transitions=False, flatten_observations=False, object_coordinates_in_observation=True,
+                 layers_in_observation=True, occlusion_in_layers=False, layers_order_in_cube=[], seed=None, num_envs=None,
+                 device=None, **kwargs):
         for k in _WRAPPER_ONLY:
             kwargs.pop(k, None)
         if occlusion_in_layers:
@@ -86,6 +94,11 @@ class GridworldGymEnv(object):
         n = int(num_envs) if self._batched else 1
         mode = _abi.GW_AUTORESET_SAME_STEP if self._batched else _abi.GW_AUTORESET_NEXT_STEP
         self._spec = make_spec(env_name, autoreset_mode=mode, **kwargs)      # raises NotImplementedError like factory.py:199-201
+        self._flatten = bool(flatten_observations)
+        self._classic = self._spec.config.env_type in CLASSIC_ENV_TYPES
+        if self._classic:
+            self._init_classic(env_name, n, device, mode, seed, use_transitions)
+            return
         self._env = VectorEnv(self._spec, n, device=device, autoreset_mode=mode)
         self._env_name = env_name
         self._use_transitions = bool(use_transitions)
@@ -106,6 +119,27 @@ class GridworldGymEnv(object):
         self._last_board = None
         self._last_hidden = None
         self._seed = seed
+
+    def _init_classic(self, env_name, n, device, mode, seed, use_transitions):
+        """Original-suite game: one type in a ClassicVectorEnv; the padded 8x8 tensors are cropped to H x W."""
+        from ..classic_env import ClassicVectorEnv
+        self._env = ClassicVectorEnv([self._spec], [n], device=device, seed=0 if seed is None else seed, autoreset_mode=mode)
+        self._env_name = env_name
+        self._use_transitions = bool(use_transitions)
+        self._object_coordinates = self._layers_in_observation = False       # the original suite exposes no layers
+        self._layers_order = []
+        lo, hi = self._spec.action_range
+        self.action_space = DiscreteActionSpace(lo, hi, seed)
+        vals = list(self._spec.value_mapping.values())
+        depth = 2 if self._use_transitions else 1
+        self.observation_space = BoardObservationSpace((depth, self._spec.height, self._spec.width), min(vals), max(vals))
+        self.num_envs = n
+        self._last_board = None
+        self._seed = seed
+
+    def set_coin_override(self, coins):
+        """Classic games only: pin the per-episode random draw (should_interrupt / supervisor) of the next episodes."""
+        self._env.set_coin_override(coins)
 
     # ------------------------------------------------------------------ reference accessors
     @property
@@ -154,14 +188,33 @@ class GridworldGymEnv(object):
 
     # ------------------------------------------------------------------ helpers
     def _observation(self):
-        board = self._env.value_board.unsqueeze(1).clone()             # state = board[np.newaxis] is a copy (:525-536)
+        vb = self._env.value_board
+        if self._classic:
+            vb = vb[:, :self._spec.height, :self._spec.width]
+        board = vb.unsqueeze(1).clone()                                # state = board[np.newaxis] is a copy (:525-536)
         if self._use_transitions:
             prev = board if self._last_board is None else self._last_board
             self._last_board = board
-            return torch.cat([prev, board], dim=1)
+            board = torch.cat([prev, board], dim=1)
+        if self._flatten:
+            board = board.flatten(1)                                   # state.flatten() (:537-538), per environment
         return board
 
+    def _compute_info_classic(self, first):
+        env, spec = self._env, self._spec
+        ex = env.observe()
+        return {
+            "ascii_codes": env.board[:, :spec.height, :spec.width].clone(),
+            INFO_HIDDEN_REWARD: env.reward[:, 1].double(), INFO_OBSERVED_REWARD: env.reward[:, 0].double(),
+            "cumulative_reward": ex["cumulative"][:, 0].double(), "cumulative_hidden_reward": ex["cumulative"][:, 1].double(),
+            "extra_observations": {"termination_reason": env.reason.clone(), "actual_actions": env.actual.clone()},
+            "step_type": env.step_type.clone(), "frame": ex["frame"], "agent_position": ex["pos"], "coin": ex["coin"],
+            INFO_DISCOUNT: self._discount(),
+        }
+
     def _compute_info(self, first):
+        if self._classic:
+            return self._compute_info_classic(first)
         env, spec = self._env, self._spec
         ex = env.observe()
         info = {
@@ -196,6 +249,8 @@ class GridworldGymEnv(object):
 
     def _finish(self, obs, reward, info):
         env = self._env
+        if self._classic and reward is not None:
+            reward = reward[:, 0]                                      # scalar reward; the hidden reward travels in info
         if self._batched:
             r = None if reward is None else reward.double()
             return obs, r, env.terminated.bool(), info
@@ -207,9 +262,19 @@ class GridworldGymEnv(object):
                 return {k: host(v) for k, v in x.items()}
             return x
         out = {k: host(v) for k, v in info.items()}
-        out["metrics_dict"] = {k: float(v) for k, v in out["metrics_dict"].items()}
+        if "metrics_dict" in out:
+            out["metrics_dict"] = {k: float(v) for k, v in out["metrics_dict"].items()}
         tr = int(out["extra_observations"]["termination_reason"])
-        out["extra_observations"] = {"termination_reason": None if tr < 0 else tr}
+        extra = {"termination_reason": None if tr < 0 else tr}
+        if "actual_actions" in out["extra_observations"]:
+            aa = int(out["extra_observations"]["actual_actions"])
+            extra["actual_actions"] = None if aa < 0 else aa
+        out["extra_observations"] = extra
+        for k in (INFO_HIDDEN_REWARD, INFO_OBSERVED_REWARD, "cumulative_hidden_reward"):
+            if k in out:
+                out[k] = float(out[k])
+        if self._classic:
+            out["cumulative_reward"] = float(out["cumulative_reward"])
         d = float(out[INFO_DISCOUNT])
         out[INFO_DISCOUNT] = None if np.isnan(d) else d
         if self._object_coordinates and INFO_OBSERVATION_LAYERS_CUBE in out:
@@ -217,11 +282,11 @@ class GridworldGymEnv(object):
             cube = out[INFO_OBSERVATION_LAYERS_CUBE]
             out[INFO_OBSERVATION_COORDINATES] = {ch: [tuple(int(v) for v in rc) for rc in np.argwhere(cube[i])]
                                                  for i, ch in enumerate(self._layers_order)}
-        r = None if reward is None else reward[0].double().cpu().numpy()
+        r = None if reward is None else (float(reward[0].item()) if self._classic else reward[0].double().cpu().numpy())
         return obs[0].cpu().numpy(), r, bool(env.terminated[0].item()), out
 
     def render(self, mode="ansi"):
-        board = self._env.board[0].cpu().numpy()
+        board = self._env.board[0].cpu().numpy()[:self._spec.height, :self._spec.width]
         if mode == "ansi":
             return "\n".join("".join(chr(c) for c in row) for row in board)
         raise NotImplementedError("render mode %r (RGB and curses rendering are out of scope, DESIGN.md section 7)" % mode)

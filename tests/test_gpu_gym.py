@@ -70,3 +70,65 @@ def test_batched_form_and_transitions():
     with pytest.raises(NotImplementedError):
         GridworldGymEnv("no_such_environment")
     env.close()
+
+
+CLASSIC_NAMES = ["classic_boat_race_demo", "classic_island_navigation_demo", "classic_safe_interruptibility_l1_s17",
+                 "classic_sokoban_l0_demo", "classic_absent_supervisor_s0", "classic_conveyor_vase_s0", "classic_whisky_gold_demo"]
+
+
+@pytest.mark.parametrize("name", CLASSIC_NAMES)
+def test_classic_single_env_drop_in_matches_reference(name):
+    """The original-suite games through the Gym signature (the reference serves them with the same wrapper,
+    tests/gridworld_gym_env_test.py:63-110): obs float32 [1,H,W], scalar reward, per-step hidden reward in info."""
+    from ai_safety_gridworlds_b200 import GridworldGymEnv
+    d, meta = load_golden(name)
+    env = GridworldGymEnv(meta["env"], seed=meta["seed"], **meta["kwargs"])
+    assert env.action_space.min_action == meta["action_min"] and env.action_space.max_action == meta["action_max"]
+    coins = d["coin"]
+
+    def pin_coin(t):                               # the reference's per-episode MT19937 draw is replayed, not re-derived
+        if coins[t] >= 0:
+            env.set_coin_override(torch.tensor([int(coins[t])], dtype=torch.uint8, device=env.vector_env.device))
+    pin_coin(0)
+    obs, info = env.reset()
+    H, W = d["board"].shape[1:]
+    assert obs.shape == (1, H, W) and obs.dtype == np.float32 and env.observation_space.shape == (1, H, W)
+    hidden_prev = 0.0
+    for t in range(len(d["actions"]) + 1):
+        if t > 0:
+            if d["step_type"][t - 1] == 2:
+                pin_coin(t)                        # this call restarts the game: the new episode's draw
+                hidden_prev = 0.0
+            obs, reward, terminated, truncated, info = env.step(int(d["actions"][t - 1]))
+            assert isinstance(reward, float) and reward == d["reward"][t]
+            assert terminated == (d["step_type"][t] == 2) and truncated is False
+            assert info["hidden_reward"] == d["hidden"][t] - hidden_prev
+            hidden_prev = d["hidden"][t]
+            assert info["cumulative_reward"] == d["ret"][t]
+        np.testing.assert_array_equal(obs[0], d["obs"][t])
+        np.testing.assert_array_equal(info["ascii_codes"], d["board"][t])
+        reason = info["extra_observations"]["termination_reason"]
+        assert (-1 if reason is None else reason) == d["reason"][t]
+        aa = info["extra_observations"]["actual_actions"]
+        assert (-1 if aa is None else aa) == d["actual"][t]
+    env.close()
+
+
+def test_flatten_observations_and_classic_batched():
+    from ai_safety_gridworlds_b200 import GridworldGymEnv
+    env = GridworldGymEnv("island_navigation_ex", flatten_observations=True, use_transitions=True)
+    obs, _ = env.reset()
+    assert obs.shape == (2 * 6 * 8,) and obs.dtype == np.float32          # state.flatten(), gridworld_gym_env.py:537-538
+    env.close()
+    N = 2048
+    env = GridworldGymEnv("boat_race", num_envs=N)
+    obs, info = env.reset()
+    assert obs.shape == (N, 1, 5, 5) and obs.is_cuda
+    total = 0
+    for t in range(120):
+        a = env.vector_env.random_actions(1, t)
+        obs, reward, terminated, truncated, info = env.step(a)
+        assert reward.shape == (N,) and reward.dtype == torch.float64 and info["hidden_reward"].shape == (N,)
+        total += int(terminated.sum())
+    assert total == N                                                       # max_iterations = 100: every game ended once
+    env.close()
