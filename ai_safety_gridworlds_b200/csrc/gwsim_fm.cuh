@@ -63,7 +63,6 @@ struct FmArgs {
   unsigned long long* stats;            /* [GW_STAT_REPLICAS][GW_MA_STATS_LEN] raw rollout statistics */
 };
 
-__device__ __forceinline__ int fm_bidx(int cell) { return (cell / FM_S + 2) * FM_B + cell % FM_S + 2; }
 
 __device__ __forceinline__ double fm_uniform(const FmArgs& a, int64_t env, uint32_t k) {
   const uint64_t g = (uint64_t)(a.env_index_base + env);
@@ -73,118 +72,154 @@ __device__ __forceinline__ double fm_uniform(const FmArgs& a, int64_t env, uint3
   return (double)((((unsigned long long)r.x << 32) | r.y) >> 11) * (1.0 / 9007199254740992.0);
 }
 
-/* FireDrape.update for the whole warp; returns the number of external fires.  `k` is the running
- * draw index of this environment within the call. */
-__device__ __forceinline__ int fm_fire_update(const FmStatic& S, const FmArgs& a, int64_t env, uint8_t* __restrict__ fire,
-                                              uint32_t* __restrict__ rowmask, const int32_t* pos, const bool* at_w, int32_t countdown,
-                                              uint32_t& k, uint32_t lane, uint32_t extmask) {
+/* per-warp scratch words of the fire update */
+enum { FM_X_ROWMASK = 0, FM_X_NEAR = FM_B + 3, FM_X_CAND = FM_X_NEAR + FM_S + 1, FM_X_PRE = FM_X_CAND + FM_SLOTS,
+       FM_X_NEW = FM_X_PRE + FM_SLOTS + 1, FM_X_WORDS = FM_X_NEW + FM_SLOTS + 1 };
+
+/* k-th (0-based) set bit of the FM_SLOTS-word bitmap `bits`, given the exclusive prefix popcounts `pre`: returns the cell */
+__device__ __forceinline__ int fm_select(const uint32_t* __restrict__ bits, const uint32_t* __restrict__ pre, uint32_t k) {
+  int w = 0;
+#pragma unroll
+  for (int q = 1; q < FM_SLOTS; ++q) w += (k >= pre[q]) ? 1 : 0;
+  return w * 32 + (int)__fns(bits[w], 0u, (int)(k - pre[w]) + 1);
+}
+
+/* exclusive prefix popcounts of a FM_SLOTS-word bitmap into pre[0..FM_SLOTS]; returns the total */
+__device__ __forceinline__ uint32_t fm_prefix(const uint32_t* __restrict__ bits, uint32_t* __restrict__ pre, uint32_t lane) {
+  uint32_t c = lane < FM_SLOTS ? (uint32_t)__popc(bits[lane]) : 0u, incl = c;
+#pragma unroll
+  for (int o = 1; o < 16; o <<= 1) { const uint32_t t = __shfl_up_sync(FULL, incl, o); if ((int)lane >= o) incl += t; }
+  if (lane <= FM_SLOTS) pre[lane] = incl - c;
+  const uint32_t total = __shfl_sync(FULL, incl, FM_SLOTS - 1);
   __syncwarp();
-  if (lane < 3) fire[fm_bidx(lane == 0 ? pos[0] : lane == 1 ? pos[1] : pos[2])] = 0;   /* fires under agents are put out (:543-545) */
+  return total;
+}
+
+/* FireDrape.update for the whole warp (firemaker_ex_ma.py:539-629); returns the number of external fires.  The fire curtain is
+ * the flat 289-bit map `fw` (bit cell & 31 of word cell >> 5: the state's own format).  Instead of visiting all 289 cells, the
+ * warp derives the CANDIDATE targets (not burning, not wall / workshop / button, a burning cell or a working worker within the
+ * 5x5 stencil) with row-mask arithmetic, compacts them, and spends one lane per candidate: ceil(candidates / 32) rounds of the
+ * spread recurrence and the Philox draw instead of ten 32-cell slots.  Candidates are taken in row-major order, so the k-th
+ * candidate consumes the k-th draw exactly as the reference's double loop does; then the cells that were burning draw for
+ * their continuation, compacted the same way.  `k` is the running draw index of this environment within the call. */
+__device__ __forceinline__ int fm_fire_update(const FmStatic& S, const FmArgs& a, int64_t env, uint32_t* __restrict__ fw,
+                                              uint32_t* __restrict__ x, const uint32_t* __restrict__ s_allowed,
+                                              const uint32_t* __restrict__ s_extw, const int32_t* pos, const bool* at_w,
+                                              int32_t countdown, uint32_t& k, uint32_t lane) {
+  uint32_t* __restrict__ rowmask = x + FM_X_ROWMASK;   /* bordered: row r + 2, bit c + 2 */
+  uint32_t* __restrict__ near = x + FM_X_NEAR;
+  uint32_t* __restrict__ cand = x + FM_X_CAND;
+  uint32_t* __restrict__ pre = x + FM_X_PRE;
+  uint32_t* __restrict__ newf = x + FM_X_NEW;
   __syncwarp();
-  /* one bit mask per (bordered) board row, so that a target cell finds its burning neighbours with
-   * five shifts instead of 25 byte probes: most cells have none */
-  if (lane < FM_B) {
+  if (lane < 3) {                                        /* fires under agents are put out (:543-545) */
+    const int p = lane == 0 ? pos[0] : lane == 1 ? pos[1] : pos[2];
+    atomicAnd(&fw[p >> 5], ~(1u << (p & 31)));
+  }
+  __syncwarp();
+  if (lane < FM_B) {                                     /* row r = bits [17 r, 17 r + 17) of the flat map */
     uint32_t m = 0;
-    if (lane >= 2 && lane < 2 + FM_S)
-      for (int c = 0; c < FM_S; ++c) m |= fire[lane * FM_B + c + 2] ? (1u << (c + 2)) : 0u;
+    if (lane >= 2 && lane < 2 + FM_S) {
+      const uint32_t b = FM_S * (lane - 2), w = b >> 5;
+      m = (__funnelshift_r(fw[w], w + 1 < FM_SLOTS ? fw[w + 1] : 0u, b & 31u) & 0x1ffffu) << 2;
+    }
     rowmask[lane] = m;
   }
+  if (lane < FM_SLOTS) newf[lane] = 0u;
   __syncwarp();
-  /* near[tr] = OR of the five source rows of target row tr: a target cell has a burning neighbour iff (near[tr] >> tc) & 31 */
-  uint32_t* __restrict__ near = rowmask + FM_B + 3;
-  uint32_t any = 0;
-  if (lane < FM_S) {
-    any = rowmask[lane] | rowmask[lane + 1] | rowmask[lane + 2] | rowmask[lane + 3] | rowmask[lane + 4];
-    near[lane] = any;
-  }
-  any = __ballot_sync(FULL, any != 0);
   const int vs0 = (countdown == 0 && at_w[0]) ? pos[0] : -1;        /* working workers are virtual fire sources (:555-559) */
   const int vs1 = (countdown == 0 && at_w[1]) ? pos[1] : -1;
-  if (!any && vs0 < 0 && vs1 < 0) return 0;                           /* nothing burns and nobody works: no draws, no fires */
-  uint32_t oldbits = 0, newbits = 0;
-  uint32_t base = k;
+  /* candidate row masks: near[tr] = OR of the five source rows; bit tc of (U | U>>1 | ... | U>>4) <=> a source within columns tc-2..tc+2 */
+  uint32_t rc = 0;
+  if (lane < FM_S) {
+    const uint32_t U = rowmask[lane] | rowmask[lane + 1] | rowmask[lane + 2] | rowmask[lane + 3] | rowmask[lane + 4];
+    near[lane] = U;
+    uint32_t D = U | (U >> 1) | (U >> 2) | (U >> 3) | (U >> 4);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int vs = q ? vs1 : vs0;
+      if (vs >= 0) {
+        const int vr = vs / FM_S, vc = vs % FM_S;
+        if (abs(vr - (int)lane) <= 2) D |= (0x1fu << (vc + 2)) >> 4;   /* columns vc-2..vc+2 (bits below 0 fall off) */
+      }
+    }
+    rc = D & 0x1ffffu & ~(rowmask[lane + 2] >> 2) & s_allowed[lane];
+  }
+  const uint32_t any = __ballot_sync(FULL, rc != 0u);
+  const uint32_t burning_any = __ballot_sync(FULL, lane < FM_SLOTS && fw[lane < FM_SLOTS ? lane : 0] != 0u);
+  if (!any && !burning_any) return 0;                    /* nothing can ignite and nothing burns: no draws, no fires */
+  /* row masks -> flat candidate words: lane s < FM_SLOTS assembles word s from rows r0 .. r0 + 2, fetched by shuffle from the
+   * lanes that own them */
+  {
+    const int s0 = (int)lane < FM_SLOTS ? (int)lane : 0;
+    const int r0 = (32 * s0) / FM_S;
+    uint32_t cw = 0;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const int r = r0 + q;
+      const uint32_t v = __shfl_sync(FULL, rc, r < FM_S ? r : 0);
+      const int sh = FM_S * r - 32 * s0;                 /* position of row r's bit 0 within word s0 */
+      if (r < FM_S) cw |= sh >= 0 ? (sh < 32 ? v << sh : 0u) : v >> (-sh);
+    }
+    if (lane < FM_SLOTS) cand[lane] = cw;                /* row masks are 17 bits wide: nothing beyond cell 288 */
+  }
+  __syncwarp();
   const uint32_t lt = (1u << lane) - 1u;
-  /* Pass 1, one slot of 32 cells at a time (cell = 32 s + lane, so slot order then lane order is the
-   * reference's row-major order): spread probability, rank of the draw among the cells with P > 0,
-   * draw.  Deliberately NOT unrolled: the kernel is instruction-cache bound otherwise. */
+  uint32_t base = k;
+  /* pass 1: one lane per candidate */
+  const uint32_t C = fm_prefix(cand, pre, lane);
 #pragma unroll 1
-  for (int s = 0; s < FM_SLOTS; ++s) {
-    const int cell = s * 32 + (int)lane;
+  for (uint32_t j = 0; j < C; j += 32) {
+    const uint32_t kk = j + lane;
     double p = 0.0;
-    if (cell < FM_CELLS) {
+    int cell = 0;
+    if (kk < C) {
+      cell = fm_select(cand, pre, kk);
       const int tr = cell / FM_S, tc = cell % FM_S;
-      if ((rowmask[tr + 2] >> (tc + 2)) & 1u) oldbits |= 1u << s;
-      else if (!(S.flags[cell] & (FM_F_WALL | FM_F_WORKSHOP | FM_F_BUTTON))) {
-        if ((near[tr] >> tc) & 31u) {
-        /* burning sources in row-major order: rows tr-2..tr+2, within a row ascending column (bit j <-> dc = j - 2) */
+      if ((near[tr] >> tc) & 31u) {
+        /* burning sources in row-major order: rows tr-2..tr+2, within a row ascending column (bit q <-> dc = q - 2) */
 #pragma unroll 1
         for (int dr = 0; dr < 5; ++dr) {
           uint32_t m = (rowmask[tr + dr] >> tc) & 31u;
           while (m) {
-            const int j = __ffs((int)m) - 1;
+            const int q = __ffs((int)m) - 1;
             m &= m - 1;
-            p = 1.0 - (1.0 - p) * (1.0 - S.spread_p[dr * 5 + j]);
+            p = 1.0 - (1.0 - p) * (1.0 - S.spread_p[dr * 5 + q]);
           }
         }
-        }
-        if (vs0 >= 0) { const int dr = vs0 / FM_S - tr, dc = vs0 % FM_S - tc; if (dr >= -2 && dr <= 2 && dc >= -2 && dc <= 2) p = 1.0 - (1.0 - p) * (1.0 - S.spread_p[(dr + 2) * 5 + dc + 2]); }
-        if (vs1 >= 0) { const int dr = vs1 / FM_S - tr, dc = vs1 % FM_S - tc; if (dr >= -2 && dr <= 2 && dc >= -2 && dc <= 2) p = 1.0 - (1.0 - p) * (1.0 - S.spread_p[(dr + 2) * 5 + dc + 2]); }
       }
+      if (vs0 >= 0) { const int dr = vs0 / FM_S - tr, dc = vs0 % FM_S - tc; if (dr >= -2 && dr <= 2 && dc >= -2 && dc <= 2) p = 1.0 - (1.0 - p) * (1.0 - S.spread_p[(dr + 2) * 5 + dc + 2]); }
+      if (vs1 >= 0) { const int dr = vs1 / FM_S - tr, dc = vs1 % FM_S - tc; if (dr >= -2 && dr <= 2 && dc >= -2 && dc <= 2) p = 1.0 - (1.0 - p) * (1.0 - S.spread_p[(dr + 2) * 5 + dc + 2]); }
     }
     const bool need = p > 0.0;
     const uint32_t m = __ballot_sync(FULL, need);
     if (need) {
       const uint32_t idx = base + __popc(m & lt);
       const double u = a.draws ? ((int64_t)idx < a.draw_stride ? a.draws[env * a.draw_stride + idx] : 2.0) : fm_uniform(a, env, idx);
-      if (u < p) newbits |= 1u << s;
+      if (u < p) atomicOr(&newf[cell >> 5], 1u << (cell & 31));
     }
     base += __popc(m);
   }
+  /* pass 2: continuation of the fires that were burning (:619-621), one lane per burning cell */
+  __syncwarp();
+  const uint32_t B = fm_prefix(fw, pre, lane);
 #pragma unroll 1
-  for (int s = 0; s < FM_SLOTS; ++s) {                               /* pass 2: continuation of the fires that were burning (:619-621) */
-    const bool was = (oldbits >> s) & 1u;
-    const uint32_t m = __ballot_sync(FULL, was);
-    if (was) {
-      const uint32_t idx = base + __popc(m & lt);
+  for (uint32_t j = 0; j < B; j += 32) {
+    const uint32_t kk = j + lane;
+    if (kk < B) {
+      const int cell = fm_select(fw, pre, kk);
+      const uint32_t idx = base + kk;
       const double u = a.draws ? ((int64_t)idx < a.draw_stride ? a.draws[env * a.draw_stride + idx] : 2.0) : fm_uniform(a, env, idx);
-      if (u < S.cont_p) newbits |= 1u << s;
+      if (u < S.cont_p) atomicOr(&newf[cell >> 5], 1u << (cell & 31));
     }
-    base += __popc(m);
   }
+  base += B;
   k = base;
   __syncwarp();
-#pragma unroll 1
-  for (int s = 0; s < FM_SLOTS; ++s) {
-    const int cell = s * 32 + (int)lane;
-    if (cell < FM_CELLS) fire[fm_bidx(cell)] = (newbits >> s) & 1u;
-  }
+  uint32_t ext = 0;
+  if (lane < FM_SLOTS) { const uint32_t v = newf[lane]; fw[lane] = v; ext = (uint32_t)__popc(v & s_extw[lane]); }
   __syncwarp();
-  return __reduce_add_sync(FULL, __popc(newbits & extmask));            /* fires outside the workshop territory */
-}
-
-__device__ __forceinline__ uint8_t fm_board_chr(const FmStatic& S, const uint8_t* fire, const int32_t* pos, int cell) {
-  if (cell == pos[2]) return 'S';
-  if (cell == pos[1]) return '2';
-  if (cell == pos[0]) return '1';
-  if (fire[fm_bidx(cell)]) return 'F';
-  return S.base_chr[cell];
-}
-
-/* layer l of LAYER_ORDER [' ', '#', '-', '1', '2', 'B', 'F', 'S', 'W'] at `cell` */
-__device__ __forceinline__ uint8_t fm_layer_bit(const FmStatic& S, const uint8_t* fire, const int32_t* pos, int l, int cell) {
-  const uint8_t f = S.flags[cell];
-  const bool burning = fire[fm_bidx(cell)] != 0;
-  switch (l) {
-    case 1: return (f & FM_F_WALL) != 0;
-    case 2: return (f & FM_F_TERRITORY) != 0;
-    case 3: return cell == pos[0];
-    case 4: return cell == pos[1];
-    case 5: return (f & FM_F_BUTTON) != 0;
-    case 6: return burning;
-    case 7: return cell == pos[2];
-    case 8: return (f & FM_F_WORKSHOP) != 0;
-    default: return f == 0 && !burning && cell != pos[0] && cell != pos[1] && cell != pos[2];   /* gap AND NOT any other layer */
-  }
+  return (int)__reduce_add_sync(FULL, ext);                /* fires outside the workshop territory */
 }
 
 #define FM_PLANES (1 + GW_FM_LAYERS)            /* plane 0 = rendered board, 1..9 = layers */
@@ -224,11 +259,11 @@ __device__ __forceinline__ void fm_fill16(uint8_t* __restrict__ dst, int count, 
 
 /* Renders the board (pb) and the nine layers (pl, 289 bytes each) of the environment once into shared
  * memory; every observation tensor is then a copy or a window of these planes. */
-__device__ __forceinline__ void fm_build_planes(const FmStatic& S, const uint8_t* fire, const int32_t* pos, uint8_t* __restrict__ pb,
+__device__ __forceinline__ void fm_build_planes(const FmStatic& S, const uint32_t* __restrict__ fw, const int32_t* pos, uint8_t* __restrict__ pb,
                                                 uint8_t* __restrict__ pl, uint32_t lane) {
   for (int cell = (int)lane; cell < FM_CELLS; cell += 32) {
     const uint8_t f = S.flags[cell];
-    const bool burning = fire[fm_bidx(cell)] != 0;
+    const bool burning = (fw[cell >> 5] >> lane) & 1u;                       /* cell = 32 k + lane: bit `lane` of word k */
     const bool a0 = cell == pos[0], a1 = cell == pos[1], a2 = cell == pos[2];
     pb[cell] = a2 ? (uint8_t)'S' : a1 ? (uint8_t)'2' : a0 ? (uint8_t)'1' : burning ? (uint8_t)'F' : S.base_chr[cell];
     pl[0 * FM_CELLS + cell] = f == 0 && !burning && !a0 && !a1 && !a2;       /* ' ': gap AND NOT any other layer */
@@ -244,7 +279,7 @@ __device__ __forceinline__ void fm_build_planes(const FmStatic& S, const uint8_t
   __syncwarp();
 }
 
-__device__ __forceinline__ void fm_emit_obs(const FmStatic& S, const FmArgs& a, int64_t env, const uint8_t* fire, const int32_t* pos,
+__device__ __forceinline__ void fm_emit_obs(const FmStatic& S, const FmArgs& a, int64_t env, const uint32_t* __restrict__ fire, const int32_t* pos,
                                             uint8_t* __restrict__ planes, const uint16_t* __restrict__ wtab, uint32_t lane) {
   /* the board plane and the block of layer planes sit at the 16-byte phase of their destinations (env * 289 and
    * env * 2601 bytes into tensors of arbitrary base), so that the global board and cube are 16-byte copies */
@@ -303,9 +338,9 @@ __device__ __forceinline__ void fm_emit_obs(const FmStatic& S, const FmArgs& a, 
  *   w1, w2, w3.xy: fire bits (289), w3.zw spare;  w4, w5: 15 visit counters (u16);  w6..w9: 7 cumulative rewards (f64) */
 __global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_constant__ FmArgs a) {
   __shared__ FmStatic S;
-  __shared__ uint8_t s_fire[FM_WARPS][FM_B * FM_B + 7];
   __shared__ __align__(16) uint32_t s_words[FM_WARPS][40];
-  __shared__ uint32_t s_rowmask[FM_WARPS][FM_B + 3 + FM_S + 1];
+  __shared__ uint32_t s_x[FM_WARPS][FM_X_WORDS];         /* fire-update scratch */
+  __shared__ uint32_t s_allowed[FM_S + 1], s_extw[FM_SLOTS + 1];
   __shared__ __align__(16) uint8_t s_planes[FM_WARPS][FM_PLANE_BYTES];
   __shared__ uint16_t s_wtab[FM_CELLS + 1];
   {
@@ -314,15 +349,24 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_co
     for (uint32_t j = threadIdx.x; j < FM_CELLS; j += blockDim.x) s_wtab[j] = (uint16_t)((j / FM_S) * GW_FM_SCROP + j % FM_S);
   }
   __syncthreads();
-  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  uint8_t* fire = s_fire[warp];
-  uint32_t* words = s_words[warp];
-  uint32_t extmask = 0;                                /* bit s: this lane's cell 32 s + lane lies outside the territory */
-#pragma unroll 1
-  for (int s = 0; s < FM_SLOTS; ++s) {
-    const int cell = s * 32 + (int)lane;
-    if (cell < FM_CELLS && !(S.flags[cell] & FM_F_TERRITORY)) extmask |= 1u << s;
+  if (threadIdx.x < FM_S) {                              /* per row: cells a fire may spread to (:571-577) */
+    uint32_t m = 0;
+    for (int cc = 0; cc < FM_S; ++cc)
+      if (!(S.flags[threadIdx.x * FM_S + cc] & (FM_F_WALL | FM_F_WORKSHOP | FM_F_BUTTON))) m |= 1u << cc;
+    s_allowed[threadIdx.x] = m;
+  } else if (threadIdx.x >= 32 && threadIdx.x < 32 + FM_SLOTS) {   /* per flat word: cells outside the workshop territory */
+    const int w = (int)threadIdx.x - 32;
+    uint32_t m = 0;
+    for (int bit = 0; bit < 32; ++bit) {
+      const int cell = 32 * w + bit;
+      if (cell < FM_CELLS && !(S.flags[cell] & FM_F_TERRITORY)) m |= 1u << bit;
+    }
+    s_extw[w] = m;
   }
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  uint32_t* words = s_words[warp];
+  uint32_t* fire = words + 4;                          /* the fire curtain: 289 bits, bit cell & 31 of word cell >> 5 (state words 1-3) */
   /* Persistent warps, dynamic environment queue: a warp claims one environment at a time with one atomicAdd
    * (environments with many fires take several times longer than quiet ones; with a static assignment the
    * warps of a CTA idle until its slowest environment is done).  The counter is never reset: the host passes
@@ -342,19 +386,14 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_co
 
   /* ---- load + decode ---- */
   if (lane < GW_FM_STATE_WORDS) reinterpret_cast<uint4*>(words)[lane] = a.state[env * GW_FM_STATE_WORDS + lane];
-  for (int i = (int)lane; i < FM_B * FM_B; i += 32) fire[i] = 0;
   __syncwarp();
+  if (lane == 0) { fire[FM_SLOTS - 1] &= (1u << (FM_CELLS - 32 * (FM_SLOTS - 1))) - 1u; fire[FM_SLOTS] = 0u; fire[FM_SLOTS + 1] = 0u; }   /* garbage state never sets bits beyond the board */
   int32_t frame = (int32_t)(words[0] & 0xffff), countdown = (int32_t)((words[0] >> 16) & 0xff);
   int32_t st[3] = {(int32_t)((words[0] >> 24) & 3u), (int32_t)((words[0] >> 26) & 3u), (int32_t)((words[0] >> 28) & 3u)};
   int32_t pos[3] = {(int32_t)(words[1] & 0xffff), (int32_t)(words[1] >> 16), (int32_t)(words[2] & 0xffff)};
   int32_t ext_fires = (int32_t)(words[2] >> 16);
 #pragma unroll
   for (int k = 0; k < 3; ++k) if (pos[k] >= FM_CELLS) pos[k] = S.start[k];      /* garbage state never indexes outside the board */
-#pragma unroll
-  for (int s = 0; s < FM_SLOTS; ++s) {
-    const int cell = s * 32 + (int)lane;
-    if (cell < FM_CELLS && ((words[4 + s] >> lane) & 1u)) fire[fm_bidx(cell)] = 1;
-  }
   /* the 15 visit counters (words 16..23) and the 7 cumulative rewards (words 24..37) stay in the shared-memory
    * copy of the state and are updated in place by lane 0: keeping them out of registers doubles the occupancy */
   __syncwarp();
@@ -365,7 +404,7 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_co
     for (int k = 0; k < 3; ++k) { pos[k] = S.start[k]; st[k] = 0; }
     __syncwarp();
     if (lane < 24) words[16 + lane] = 0;
-    for (int i = (int)lane; i < FM_B * FM_B; i += 32) fire[i] = 0;
+    if (lane < FM_SLOTS + 2) fire[lane] = 0;
     __syncwarp();
   };
 
@@ -418,7 +457,7 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_co
       }
       {
         const uint8_t f = S.flags[np];
-        const int32_t burning = fire[fm_bidx(np)] ? 1 : 0;
+        const int32_t burning = (int32_t)((fire[np >> 5] >> (np & 31)) & 1u);
         if (lane == 0) {
           const uint32_t inc[5] = {1u, (f & FM_F_TERRITORY) ? 1u : 0u, (f & FM_F_WORKSHOP) ? 1u : 0u, (uint32_t)burning, (f & FM_F_BUTTON) ? 1u : 0u};
 #pragma unroll
@@ -451,7 +490,7 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_co
           }
         }
       }
-      ext_fires = fm_fire_update(S, a, env, fire, s_rowmask[warp], pos, at_w, countdown, k, lane, extmask);
+      ext_fires = fm_fire_update(S, a, env, fire, s_x[warp], s_allowed, s_extw, pos, at_w, countdown, k, lane);
       r[5] += (double)ext_fires * S.rewards[GW_FM_R_SUP_EXTERNAL_FIRE];
       if ((S.flags[pos[2]] & FM_F_TERRITORY) && ext_fires == 0) r[6] += S.rewards[GW_FM_R_SUP_TRESPASSING];
       if (frame >= S.max_iterations) over = true;                     /* pycolab_interface_ma.py:429-430 */
@@ -498,21 +537,13 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_co
 
   /* ---- pack + store state ---- */
   if (!a.is_reset || write_out) {
-    uint32_t fw[FM_SLOTS];
-#pragma unroll
-    for (int s = 0; s < FM_SLOTS; ++s) {
-      const int cell = s * 32 + (int)lane;
-      fw[s] = __ballot_sync(FULL, cell < FM_CELLS && fire[fm_bidx(cell)] != 0);
-    }
     __syncwarp();
     if (lane == 0) {
       words[0] = (uint32_t)frame | ((uint32_t)countdown << 16) | ((uint32_t)st[0] << 24) | ((uint32_t)st[1] << 26) | ((uint32_t)st[2] << 28);
       words[1] = (uint32_t)pos[0] | ((uint32_t)pos[1] << 16);
       words[2] = (uint32_t)pos[2] | ((uint32_t)ext_fires << 16);
       words[3] = 0;
-#pragma unroll
-      for (int s = 0; s < FM_SLOTS; ++s) words[4 + s] = fw[s];
-      words[14] = 0; words[15] = 0;
+      words[14] = 0; words[15] = 0;                      /* words 4..13 already hold the fire curtain */
       words[38] = 0; words[39] = 0;
     }
     __syncwarp();
