@@ -144,6 +144,7 @@ GW_MA_STATS_LEN, GW_MA_STATS_RETURN0, GW_MA_STATS_SCALE = 32, 4, 65536.0
 
 # ---- include/gwsim_ima.h: island_navigation_ex_ma (multi-agent) ----
 GW_IMA_AGENTS, GW_IMA_CROP, GW_IMA_METRICS, GW_IMA_STATE_WORDS = 2, 5, 16, 12
+GW_IMA_MAPS_STATIC, GW_IMA_MAPS_SHUFFLE_EVERY_GAME, GW_IMA_MAPS_SHUFFLE_ON_RESET = 0, 1, 2
 
 
 class GwImaObs(C.Structure):
@@ -162,6 +163,7 @@ IMA_SYMBOLS = [
     ("gw_ima_create", C.c_int, [C.POINTER(GwConfig), C.c_int64, C.c_int, C.c_int64, C.c_uint64, C.POINTER(C.c_void_p)]),
     ("gw_ima_destroy", None, [C.c_void_p]),
     ("gw_ima_state_bytes", C.c_int64, [C.POINTER(GwConfig), C.c_int64]),
+    ("gw_ima_set_maps", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
     ("gw_ima_reset", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(GwImaObs), C.POINTER(GwImaOut), C.c_void_p]),
     ("gw_ima_step", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(GwImaObs), C.POINTER(GwImaOut), C.c_void_p]),
     ("gw_ima_observe", C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GwImaExtras), C.c_void_p]),

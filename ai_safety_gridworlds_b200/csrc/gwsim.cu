@@ -2083,6 +2083,10 @@ struct GwImaEngine {
   unsigned long long* d_stats;        /* [GW_STAT_REPLICAS][GW_MA_STATS_LEN] raw rollout statistics */
   int grid;
   uint32_t cube_off, board_off, crop_off, lcrop_off, reward_off, warp_bytes;
+  uint32_t map_off, warp_bytes_pm;     /* per-environment-map variant: + 32 maps of staging per warp */
+  uint8_t* maps;                        /* caller-owned [N, cells] tensor or NULL */
+  int32_t map_mode;                     /* GwImaMapMode */
+  int grid_pm;
   int64_t launches;
 };
 
@@ -2135,6 +2139,7 @@ int gw_ima_create(const GwConfig* cfg, int64_t n_envs, int device, int64_t env_i
     if (ch == '2') d.layer_a1 = l;
     if (ch == 'W') d.layer_w = l;
   }
+  for (int l = 0; l < GW_MAX_LAYERS; ++l) d.layer_chars[l] = l < cfg->n_layers ? cfg->layer_chars[l] : 0;
   for (int p = 0; p < GW_MAX_CELLS; ++p) { d.base_layer[p] = -1; d.base_board[p] = ' '; }
   for (int p = 0; p < cells; ++p) {
     const uint8_t ch = cfg->art[p];
@@ -2160,21 +2165,37 @@ int gw_ima_create(const GwConfig* cfg, int64_t n_envs, int device, int64_t env_i
   h->crop_off = h->board_off + 32u * (uint32_t)cells;
   h->reward_off = h->crop_off + 32u * 2u * IMA_VIEW;
   h->warp_bytes = (h->reward_off + 2u * 128u * 2u * (uint32_t)cfg->n_rewards + 127u) & ~127u;
-  const size_t smem = (size_t)h->warp_bytes * IMA_WARPS;
+  h->map_off = h->warp_bytes;
+  h->warp_bytes_pm = (h->map_off + 32u * (uint32_t)cells + 127u) & ~127u;
+  h->maps = nullptr; h->map_mode = GW_IMA_MAPS_STATIC;
+  const size_t smem = (size_t)h->warp_bytes * IMA_WARPS, smem_pm = (size_t)h->warp_bytes_pm * IMA_WARPS;
   h->d_claim = nullptr; h->claim_base = 0; h->d_stats = nullptr;
-  ce = cudaFuncSetAttribute(gw_ima_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  ce = cudaFuncSetAttribute(gw_ima_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (ce == cudaSuccess) ce = cudaFuncSetAttribute(gw_ima_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pm);
   if (ce == cudaSuccess) ce = cudaMalloc((void**)&h->d_claim, sizeof(unsigned long long));
   if (ce == cudaSuccess) ce = cudaMemset(h->d_claim, 0, sizeof(unsigned long long));
   if (ce == cudaSuccess) ce = ma_stats_alloc(&h->d_stats);
   int per_sm = 0, sms = 0;
-  if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gw_ima_kernel, IMA_WARPS * 32, smem);
+  int per_sm_pm = 0;
+  if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gw_ima_kernel<false>, IMA_WARPS * 32, smem);
+  if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_pm, gw_ima_kernel<true>, IMA_WARPS * 32, smem_pm);
   if (ce == cudaSuccess) ce = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  if (ce != cudaSuccess || per_sm < 1) {
+  if (ce != cudaSuccess || per_sm < 1 || per_sm_pm < 1) {
     cudaFree(h->d_claim); cudaFree(h->d_stats); delete h;
     return fail(GW_ERR_CUDA, "island_navigation_ex_ma set-up (%zu B of staging per CTA): %s", smem, cudaGetErrorString(ce));
   }
   h->grid = per_sm * (sms > 0 ? sms : 1);
+  h->grid_pm = per_sm_pm * (sms > 0 ? sms : 1);
   *out = h;
+  return GW_OK;
+}
+
+int gw_ima_set_maps(GwImaHandle h, uint8_t* maps, int32_t mode) {
+  if (!h) return fail(GW_ERR_INVALID, "null handle");
+  if (mode < GW_IMA_MAPS_STATIC || mode > GW_IMA_MAPS_SHUFFLE_ON_RESET) return fail(GW_ERR_INVALID, "bad map mode %d", mode);
+  if ((uintptr_t)maps & 15u) return fail(GW_ERR_INVALID, "maps must be 16-byte aligned");
+  h->maps = maps;
+  h->map_mode = maps ? mode : GW_IMA_MAPS_STATIC;
   return GW_OK;
 }
 
@@ -2201,12 +2222,17 @@ static int ima_launch(GwImaHandle h, ImaArgs& a, void* state, const GwImaObs* ob
   CUDA_TRY(cudaSetDevice(h->device));
   const int64_t nchunks = (h->n + 31) / 32;
   int64_t grid = (nchunks + IMA_WARPS - 1) / IMA_WARPS;
-  if (grid > h->grid) grid = h->grid;
+  const bool pm = h->maps != nullptr;
+  if (grid > (pm ? h->grid_pm : h->grid)) grid = pm ? h->grid_pm : h->grid;
+  a.maps = h->maps; a.map_off = (int32_t)h->map_off;
+  a.map_shuffle = pm && (h->map_mode == GW_IMA_MAPS_SHUFFLE_EVERY_GAME || (h->map_mode == GW_IMA_MAPS_SHUFFLE_ON_RESET && a.is_reset)) ? 1 : 0;
+  if (pm) a.warp_bytes = h->warp_bytes_pm;
   a.claim_counter = h->d_claim;
   a.claim_base = h->claim_base;
   a.stats = h->d_stats;
   h->claim_base += (unsigned long long)nchunks + (unsigned long long)grid * IMA_WARPS;    /* every chunk once + one failing claim per warp */
-  gw_ima_kernel<<<(unsigned)grid, IMA_WARPS * 32, (size_t)h->warp_bytes * IMA_WARPS, stream>>>(h->dc, a);
+  if (pm) gw_ima_kernel<true><<<(unsigned)grid, IMA_WARPS * 32, (size_t)h->warp_bytes_pm * IMA_WARPS, stream>>>(h->dc, a);
+  else gw_ima_kernel<false><<<(unsigned)grid, IMA_WARPS * 32, (size_t)h->warp_bytes * IMA_WARPS, stream>>>(h->dc, a);
   CUDA_TRY(cudaGetLastError());
   h->launches += 1;
   return GW_OK;

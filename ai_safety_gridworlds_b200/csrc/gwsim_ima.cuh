@@ -36,6 +36,7 @@ struct ImaCfg {
   uint8_t art[GW_MAX_CELLS];                           /* as configured ('1' / '2' on the start tiles) */
   uint8_t base_board[GW_MAX_CELLS];                    /* rendered board without the agents */
   int8_t base_layer[GW_MAX_CELLS];                     /* the one layer set at a cell with no agent on it */
+  uint8_t layer_chars[GW_MAX_LAYERS];                  /* sorted layer keys */
   double fparams[20];
   double table[GW_MAX_EVENTS][GW_MAX_REWARDS];
 };
@@ -54,6 +55,8 @@ struct ImaArgs {
   unsigned long long claim_base;
   int32_t is_reset, pad;
   unsigned long long* stats;             /* [GW_STAT_REPLICAS][GW_MA_STATS_LEN] raw rollout statistics */
+  uint8_t* maps;                         /* [N, cells] per-environment ascii art (map randomisation), NULL = cfg art for all */
+  int32_t map_shuffle, map_off;          /* regenerate an environment's map at every new game of this call; staging offset of the maps */
   uint32_t cube_off, board_off, crop_off, lcrop_off, reward_off, warp_bytes;   /* per-warp staging layout */
 };
 
@@ -135,12 +138,12 @@ __device__ __forceinline__ void ima_store(const ImaState& s, uint4* st, int64_t 
                         __float_as_uint(s.cum[k / 3][(k % 3) * 4 + 2]), __float_as_uint(s.cum[k / 3][(k % 3) * 4 + 3])));
 }
 
-__device__ __forceinline__ void ima_reset(ImaState& s, const ImaCfg& c) {
+__device__ __forceinline__ void ima_reset(ImaState& s, const ImaCfg& c, int32_t start0, int32_t start1) {
   s.frame = 0;
 #pragma unroll
   for (int p = 0; p < 2; ++p) {
     ImaAgent& g = s.ag[p];
-    g.pos = c.start[p]; g.adir = g.odir = GW_DIR_UP; g.term = 0; g.st = 0;
+    g.pos = p ? start1 : start0; g.adir = g.odir = GW_DIR_UP; g.term = 0; g.st = 0;
 #pragma unroll
     for (int k = 0; k < 5; ++k) g.visits[k] = 0;
     g.dsat = c.fparams[GW_ISL_F_DRINK_DEFICIENCY_INITIAL];
@@ -151,6 +154,44 @@ __device__ __forceinline__ void ima_reset(ImaState& s, const ImaCfg& c) {
   s.dav = c.fparams[GW_ISL_F_DRINK_AVAILABILITY_INITIAL];
   s.fav = c.fparams[GW_ISL_F_FOOD_AVAILABILITY_INITIAL];
   s.dfr = 0.0; s.ffr = 0.0;
+}
+
+/* This lane's map: the type's art (shared by every environment) or the environment's own (map randomisation,
+ * safety_game_mo_base.py:943-1134 through island_navigation_ex_ma.py:497-511). */
+struct ImaMap {
+  const uint8_t* art;                    /* cells bytes in shared memory */
+  uint8_t* own;                          /* the same bytes, writable, in per-environment mode; else nullptr */
+  bool shuffle, changed;
+};
+
+/* A fresh layout: the interior of the type's art (preserve_map_edges_when_randomizing) in Fisher-Yates order, 32-bit Philox
+ * draws keyed (seed, global environment, call): draw t of a call is word t & 3 of block t >> 2, j = floor(word * (i + 1) / 2^32). */
+__device__ __forceinline__ void ima_shuffle(const ImaCfg& c, const ImaArgs& a, const uint8_t* __restrict__ s_art, int64_t env, uint8_t* __restrict__ own) {
+  for (int p = 0; p < c.cells; ++p) own[p] = s_art[p];
+  const int iw = c.width - 2, n = (c.height - 2) * iw;
+  if (iw < 1 || n < 2) return;
+  const uint64_t g = (uint64_t)(a.env_index_base + env);
+  uint4 q = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = n - 1, t = 0; i >= 1; --i, ++t) {
+    if ((t & 3) == 0) {
+      const uint64_t step = a.call_no * 65536ull + 65000ull + (uint64_t)(t >> 2);
+      q = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)step, (uint32_t)(step >> 32)), (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+    }
+    const uint32_t word = (t & 3) == 0 ? q.x : (t & 3) == 1 ? q.y : (t & 3) == 2 ? q.z : q.w;
+    const int j = (int)__umulhi(word, (uint32_t)(i + 1));
+    const int pi = (1 + i / iw) * c.width + 1 + i % iw, pj = (1 + j / iw) * c.width + 1 + j % iw;
+    const uint8_t tmp = own[pi]; own[pi] = own[pj]; own[pj] = tmp;
+  }
+}
+
+/* make_game + its_showtime: (a fresh layout,) the agents on their start tiles, nothing collected */
+__device__ __forceinline__ void ima_new_game(const ImaCfg& c, const ImaArgs& a, const uint8_t* __restrict__ s_art, int64_t env, ImaMap& M, ImaState& s) {
+  int32_t st0 = c.start[0], st1 = c.start[1];
+  if (M.own) {
+    if (M.shuffle) { ima_shuffle(c, a, s_art, env, M.own); M.changed = true; }
+    for (int p = 0; p < c.cells; ++p) { if (M.own[p] == '1') st0 = p; if (M.own[p] == '2') st1 = p; }
+  }
+  ima_reset(s, c, st0, st1);
 }
 
 /* get_absolute_action / get_new_action_or_observation_direction, mode 1 (safety_game_ma.py:505-587): UP = forwards,
@@ -198,7 +239,7 @@ __device__ __forceinline__ void ima_play(const ImaCfg& c, const uint8_t* __restr
     const int nr = me.pos / c.width + dr, nc = me.pos % c.width + dc;
     if (nr >= 0 && nr < c.height && nc >= 0 && nc < c.width) {                                 /* confined to the board */
       const int target = nr * c.width + nc;
-      if (!((c.wall_mask >> target) & 1ull) && target != other_pos) me.pos = target;           /* impassable: '#', the other agent */
+      if (s_art[target] != '#' && target != other_pos) me.pos = target;                        /* impassable: '#', the other agent */
     }
     if (c.act_mode == 1) me.adir = dir;
     IMA_ADD(fr, GW_ISL_E_MOVEMENT, 1.0);                                                       /* :568-572 */
@@ -252,15 +293,17 @@ __device__ __forceinline__ void ima_play(const ImaCfg& c, const uint8_t* __restr
 
 /* One lane = one environment: the whole parallel step.  Writes the reward rows ([2][R] floats) to `rw` and returns the
  * agents' output step types. */
-__device__ __forceinline__ bool ima_step_lane(const ImaCfg& c, const ImaArgs& a, const uint8_t* __restrict__ s_art, int64_t env, const ImaRaw& raw,
-                                              ImaState& s, float* __restrict__ rw, int32_t* out_st, unsigned long long* __restrict__ s_stats) {
+__device__ __forceinline__ bool ima_step_lane(const ImaCfg& c, const ImaArgs& a, const uint8_t* __restrict__ s_type_art, ImaMap& M, int64_t env,
+                                              const ImaRaw& raw, ImaState& s, float* __restrict__ rw, int32_t* out_st,
+                                              unsigned long long* __restrict__ s_stats) {
+  const uint8_t* __restrict__ s_art = M.art;
   ima_unpack(s, raw, c);
   double r0[GW_MAX_REWARDS], r1[GW_MAX_REWARDS];
 #pragma unroll
   for (int d = 0; d < GW_MAX_REWARDS; ++d) { r0[d] = 0.0; r1[d] = 0.0; }
   bool played = false;
   if (s.ag[0].st >= 2 && s.ag[1].st >= 2) {
-    ima_reset(s, c);                                           /* every agent is done: new game, FIRST (pycolab_interface_ma.py:206-213) */
+    ima_new_game(c, a, s_type_art, env, M, s);                 /* every agent is done: new game, FIRST (pycolab_interface_ma.py:206-213) */
     out_st[0] = 0; out_st[1] = 0;
   } else {
     played = true;
@@ -321,7 +364,7 @@ __device__ __forceinline__ bool ima_step_lane(const ImaCfg& c, const ImaArgs& a,
             if (s.cum[1][d] != 0.0f) atomicAdd(&s_stats[GW_MA_STATS_RETURN0 + c.n_rewards + d], (unsigned long long)__double2ll_rn((double)s.cum[1][d] * GW_MA_STATS_SCALE));
           }
       }
-      if (c.autoreset == GW_AUTORESET_SAME_STEP) ima_reset(s, c);
+      if (c.autoreset == GW_AUTORESET_SAME_STEP) ima_new_game(c, a, s_type_art, env, M, s);
     }
   }
 #pragma unroll
@@ -363,12 +406,50 @@ __device__ __forceinline__ void ima_views(const ImaCfg& c, const uint16_t* __res
   }
 }
 
+/* The same views from an environment's OWN map (map randomisation): no shared bordered map, so each view cell is bounds-tested;
+ * s_vdij[dir][v] = (si - 2) & 0xff | (sj - 2) << 8 is the source offset of view cell v, s_lchar[chr] the layer of a character. */
+__device__ __forceinline__ void ima_views_own(const ImaCfg& c, const uint8_t* __restrict__ art, const int16_t* __restrict__ s_vdij,
+                                              const int8_t* __restrict__ s_lchar, int pos0, int pos1, int odir0, int odir1,
+                                              uint8_t* __restrict__ crop, uint8_t* __restrict__ lcrop) {
+  const int L = c.n_layers;
+#pragma unroll 1
+  for (int ag = 0; ag < 2; ++ag) {
+    const int pos = ag ? pos1 : pos0, pr = pos / c.width, pc = pos % c.width;
+    const int16_t* __restrict__ dij = s_vdij + (c.obs_mode ? (ag ? odir1 : odir0) : GW_DIR_UP) * IMA_VIEW;
+    uint8_t* __restrict__ lc = lcrop ? lcrop + ag * L * IMA_VIEW : nullptr;
+#pragma unroll 5
+    for (int v = 0; v < IMA_VIEW; ++v) {
+      const int e = dij[v], r = pr + (int)(int8_t)(e & 0xff), cc = pc + (int)(int8_t)(e >> 8);
+      uint32_t ch = 'W';
+      int l0 = c.layer_w, l1 = -1;
+      if (r >= 0 && r < c.height && cc >= 0 && cc < c.width) {
+        const int cell = r * c.width + cc;
+        ch = art[cell];
+        if (ch == '1' || ch == '2') ch = ' ';
+        l0 = s_lchar[ch & 127u];
+        if (cell == pos0) { ch = '1'; l1 = c.layer_a0; if (l0 == c.layer_gap) l0 = -1; }
+        if (cell == pos1) { ch = '2'; l1 = c.layer_a1; if (l0 == c.layer_gap) l0 = -1; }
+      }
+      if (crop) crop[ag * IMA_VIEW + v] = (uint8_t)ch;
+      if (lc) {
+        if (l0 >= 0) lc[l0 * IMA_VIEW + v] = 1;
+        if (l1 >= 0) lc[l1 * IMA_VIEW + v] = 1;
+      }
+    }
+  }
+}
+
+/* PM = per-environment maps (map randomisation): the art is read from (and, after a shuffle, written back to) a.maps, and board
+ * and cube are rendered from it for every chunk instead of being a patched template. */
+template <bool PM>
 __global__ void __launch_bounds__(IMA_WARPS * 32, 2) gw_ima_kernel(const __grid_constant__ ImaCfg c, const ImaArgs a) {
   extern __shared__ __align__(128) uint8_t ima_stage[];
   __shared__ uint8_t s_art[GW_MAX_CELLS], s_base[GW_MAX_CELLS];
   __shared__ int8_t s_blayer[GW_MAX_CELLS];
   __shared__ uint16_t s_bmap[IMA_BMAP];
   __shared__ int16_t s_voff[4 * IMA_VIEW];
+  __shared__ int16_t s_vdij[4 * IMA_VIEW];
+  __shared__ int8_t s_lchar[128];
   for (uint32_t i = threadIdx.x; i < GW_MAX_CELLS; i += blockDim.x) { s_art[i] = c.art[i]; s_base[i] = c.base_board[i]; s_blayer[i] = c.base_layer[i]; }
   {
     const int BW = c.width + 4, BH = c.height + 4;
@@ -386,6 +467,12 @@ __global__ void __launch_bounds__(IMA_WARPS * 32, 2) gw_ima_kernel(const __grid_
       else if (dir == GW_DIR_LEFT) { si = 4 - vj; sj = vi; }                               /* rot90 k=-1 (clockwise) */
       else if (dir == GW_DIR_RIGHT) { si = vj; sj = 4 - vi; }                              /* rot90 k=1 (counterclockwise) */
       s_voff[i] = (int16_t)((si - 2) * BW + (sj - 2));
+      s_vdij[i] = (int16_t)(((si - 2) & 0xff) | ((sj - 2) << 8));
+    }
+    for (int i = (int)threadIdx.x; i < 128; i += (int)blockDim.x) {
+      int8_t l = -1;
+      for (int k = 0; k < c.n_layers; ++k) if (c.layer_chars[k] == (uint8_t)i) l = (int8_t)k;
+      s_lchar[i] = l;
     }
   }
   __syncthreads();
@@ -399,11 +486,14 @@ __global__ void __launch_bounds__(IMA_WARPS * 32, 2) gw_ima_kernel(const __grid_
   uint8_t* s_board = wbuf + a.board_off;
   uint8_t* s_crop = wbuf + a.crop_off;
   uint8_t* s_lcrop = wbuf + a.lcrop_off;
+  uint8_t* s_map = wbuf + a.map_off;             /* PM: the chunk's 32 maps, [32][cells] as in a.maps */
   uint32_t parity = 0;                           /* reward rows are double-buffered: the previous chunk's may still be in flight */
-  /* agent-free templates of this lane's staged environment */
-  for (uint32_t p = 0; p < cells; ++p) {
-    s_board[lane * cells + p] = s_base[p];
-    for (uint32_t l = 0; l < L; ++l) s_cube[lane * Sc + l * cells + p] = (uint8_t)(s_blayer[p] == (int8_t)l);
+  if constexpr (!PM) {
+    /* agent-free templates of this lane's staged environment */
+    for (uint32_t p = 0; p < cells; ++p) {
+      s_board[lane * cells + p] = s_base[p];
+      for (uint32_t l = 0; l < L; ++l) s_cube[lane * Sc + l * cells + p] = (uint8_t)(s_blayer[p] == (int8_t)l);
+    }
   }
   __syncwarp();
   int32_t staged0 = -1, staged1 = -1;            /* the cells this lane's staged environment shows the agents on */
@@ -429,6 +519,18 @@ __global__ void __launch_bounds__(IMA_WARPS * 32, 2) gw_ima_kernel(const __grid_
     float* s_rw = reinterpret_cast<float*>(wbuf + a.reward_off + parity * (128u * R2));
     parity ^= 1u;
 
+    ImaMap M;
+    M.art = s_art; M.own = nullptr; M.shuffle = false; M.changed = false;
+    if constexpr (PM) {
+      /* this chunk's maps: one coalesced copy (the TMA engine has finished reading the previous chunk's staging before the
+       * observation phase; the map staging is only touched by generic loads and stores) */
+      const uint4* src = reinterpret_cast<const uint4*>(a.maps + env0 * (int64_t)cells);
+      const uint32_t nb = nvalid * cells;
+      for (uint32_t q = lane; q < (nb >> 4); q += 32) reinterpret_cast<uint4*>(s_map)[q] = src[q];
+      for (uint32_t i = (nb & ~15u) + lane; i < nb; i += 32) s_map[i] = a.maps[env0 * (int64_t)cells + i];
+      __syncwarp();
+      M.art = s_map + lane * cells; M.own = s_map + lane * cells; M.shuffle = a.map_shuffle != 0;
+    }
     ImaState s;
     int32_t out_st[2] = {0, 0};
     bool wrote = true, played = false;
@@ -436,10 +538,10 @@ __global__ void __launch_bounds__(IMA_WARPS * 32, 2) gw_ima_kernel(const __grid_
       if (a.is_reset) {
         ima_unpack(s, raw, c);
         wrote = !a.reset_mask || a.reset_mask[env] != 0;
-        if (wrote) ima_reset(s, c);
+        if (wrote) ima_new_game(c, a, s_art, env, M, s);
         for (uint32_t d = 0; d < R2; ++d) s_rw[lane * R2 + d] = 0.0f;
       } else {
-        played = ima_step_lane(c, a, s_art, env, raw, s, s_rw + lane * R2, out_st, s_stats);
+        played = ima_step_lane(c, a, s_art, M, env, raw, s, s_rw + lane * R2, out_st, s_stats);
       }
       if (wrote) {
         ima_store(s, a.state, a.n, env);
@@ -459,6 +561,32 @@ __global__ void __launch_bounds__(IMA_WARPS * 32, 2) gw_ima_kernel(const __grid_
     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     __syncwarp();
     const int32_t p0 = s.ag[0].pos, p1 = s.ag[1].pos;
+    if constexpr (PM) {
+      if (__any_sync(FULL, M.changed)) {                       /* fresh layouts go back to the caller's tensor, whole chunk coalesced */
+        uint8_t* dst = a.maps + env0 * (int64_t)cells;
+        const uint32_t nb = nvalid * cells;
+        for (uint32_t q = lane; q < (nb >> 4); q += 32) reinterpret_cast<uint4*>(dst)[q] = reinterpret_cast<const uint4*>(s_map)[q];
+        for (uint32_t i = (nb & ~15u) + lane; i < nb; i += 32) dst[i] = s_map[i];
+      }
+      /* render board and cube of this lane's environment from its own map */
+      if (a.cube) {
+        uint4* z = reinterpret_cast<uint4*>(s_cube);
+        for (uint32_t q = lane; q < (32u * Sc) >> 4; q += 32) z[q] = make_uint4(0u, 0u, 0u, 0u);
+        __syncwarp();
+      }
+      if (lane < nvalid) {
+        const uint8_t* art = M.art;
+        for (uint32_t p = 0; p < cells; ++p) {
+          uint32_t ch = art[p];
+          if (ch == '1' || ch == '2') ch = ' ';
+          int l = s_lchar[ch & 127u];
+          if ((int32_t)p == p0) { ch = '1'; if (l == c.layer_gap) l = -1; if (c.layer_a0 >= 0) s_cube[lane * Sc + c.layer_a0 * cells + p] = 1; }
+          if ((int32_t)p == p1) { ch = '2'; if (l == c.layer_gap) l = -1; if (c.layer_a1 >= 0) s_cube[lane * Sc + c.layer_a1 * cells + p] = 1; }
+          s_board[lane * cells + p] = (uint8_t)ch;
+          if (l >= 0) s_cube[lane * Sc + l * cells + p] = 1;
+        }
+      }
+    } else
     if (p0 != staged0 || p1 != staged1) {
       if (staged0 >= 0) {
 #pragma unroll
@@ -482,9 +610,16 @@ __global__ void __launch_bounds__(IMA_WARPS * 32, 2) gw_ima_kernel(const __grid_
       for (uint32_t q = lane; q < (32u * Sl) >> 4; q += 32) z[q] = make_uint4(0u, 0u, 0u, 0u);
       __syncwarp();
     }
-    if (a.crop || a.lcrop)
-      ima_views(c, s_bmap, s_voff, p0, p1, s.ag[0].odir, s.ag[1].odir, a.crop ? s_crop + lane * Sv : nullptr,
-                a.lcrop ? s_lcrop + lane * Sl : nullptr);
+    if (a.crop || a.lcrop) {
+      if constexpr (PM) {
+        if (lane < nvalid)
+          ima_views_own(c, M.art, s_vdij, s_lchar, p0, p1, s.ag[0].odir, s.ag[1].odir, a.crop ? s_crop + lane * Sv : nullptr,
+                        a.lcrop ? s_lcrop + lane * Sl : nullptr);
+      } else {
+        ima_views(c, s_bmap, s_voff, p0, p1, s.ag[0].odir, s.ag[1].odir, a.crop ? s_crop + lane * Sv : nullptr,
+                  a.lcrop ? s_lcrop + lane * Sl : nullptr);
+      }
+    }
 
     if (nvalid == 32 && !(a.is_reset && a.reset_mask)) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   /* generic-proxy writes -> visible to the TMA */

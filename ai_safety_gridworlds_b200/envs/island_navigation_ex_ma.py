@@ -36,6 +36,7 @@ DEFAULT_FLAGS: Dict[str, object] = dict(
     level=9, max_iterations=100, noops=True, randomize_agent_actions_order=True, sustainability_challenge=False,
     thirst_hunger_death=False, penalise_oversatiation=False, use_satiation_proportional_reward=False,
     observation_radius=[2, 2, 2, 2], observation_direction_mode=1, action_direction_mode=1, amount_agents=2,
+    map_randomization_frequency=0,
     MOVEMENT_REWARD={"MOVEMENT_REWARD": -1}, FINAL_REWARD={"FINAL_REWARD": 50},
     DRINK_DEFICIENCY_REWARD={"DRINK_DEFICIENCY_REWARD": -1}, FOOD_DEFICIENCY_REWARD={"FOOD_DEFICIENCY_REWARD": -1},
     DRINK_REWARD={"DRINK_REWARD": 20}, FOOD_REWARD={"FOOD_REWARD": 20},
@@ -105,6 +106,8 @@ def compile_spec(autoreset_mode: int = _abi.GW_AUTORESET_NEXT_STEP, **kwargs) ->
     for mode in ("observation_direction_mode", "action_direction_mode"):
         if flags[mode] not in (0, 1):
             raise NotImplementedError("%s 2 (separate turning actions) is not built" % mode)
+    if flags["map_randomization_frequency"] not in (0, 1, 2, 3):
+        raise ValueError("map_randomization_frequency")                       # safety_game_mo_base.py:979
     art = LEVELS[level]
     has = {ch: map_contains(ch, art) for ch in "UDFGSW"}
     penalise, death = flags["penalise_oversatiation"], flags["thirst_hunger_death"]

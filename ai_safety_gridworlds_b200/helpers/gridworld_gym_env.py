@@ -85,9 +85,12 @@ class GridworldGymEnv(object):
 
     def __init__(self, env_name, use_transitions=False, flatten_observations=False, object_coordinates_in_observation=True,
                  layers_in_observation=True, occlusion_in_layers=False, layers_order_in_cube=[], seed=None, num_envs=None,
-                 device=None, **kwargs):
+                 device=None, scalarise=False, **kwargs):
         for k in _WRAPPER_ONLY:
             kwargs.pop(k, None)
+        # SafetyEnvironmentMo(scalarise=True): reward, cumulative_reward and average_reward are the SUM over the reward
+        # dimensions, as np.float64 (safety_game_mo.py:1028-1064)
+        self._scalarise = bool(scalarise)
         if occlusion_in_layers:
             raise NotImplementedError("occlusion_in_layers=True: the MO environments force it off (safety_game_mo_base.py)")
         self._batched = num_envs is not None
@@ -217,10 +220,13 @@ class GridworldGymEnv(object):
             return self._compute_info_classic(first)
         env, spec = self._env, self._spec
         ex = env.observe()
+        cum, avg = ex["cumulative"].double(), ex["average"].double()
+        if self._scalarise:
+            cum, avg = cum.sum(dim=1), avg.sum(dim=1)
         info = {
             "ascii_codes": env.board.clone(),
-            "cumulative_reward": ex["cumulative"].double(),
-            "average_reward": ex["average"].double(),
+            "cumulative_reward": cum,
+            "average_reward": avg,
             "gini_index": ex["scalars"][:, 0], "cumulative_gini_index": ex["scalars"][:, 1],
             "mo_variance": ex["scalars"][:, 2], "cumulative_mo_variance": ex["scalars"][:, 3],
             "average_mo_variance": ex["scalars"][:, 4],
@@ -251,6 +257,8 @@ class GridworldGymEnv(object):
         env = self._env
         if self._classic and reward is not None:
             reward = reward[:, 0]                                      # scalar reward; the hidden reward travels in info
+        elif self._scalarise and reward is not None:
+            reward = reward.double().sum(dim=1)
         if self._batched:
             r = None if reward is None else reward.double()
             return obs, r, env.terminated.bool(), info
@@ -282,7 +290,14 @@ class GridworldGymEnv(object):
             cube = out[INFO_OBSERVATION_LAYERS_CUBE]
             out[INFO_OBSERVATION_COORDINATES] = {ch: [tuple(int(v) for v in rc) for rc in np.argwhere(cube[i])]
                                                  for i, ch in enumerate(self._layers_order)}
-        r = None if reward is None else (float(reward[0].item()) if self._classic else reward[0].double().cpu().numpy())
+        if reward is None:
+            r = None
+        elif self._classic:
+            r = float(reward[0].item())
+        elif self._scalarise:
+            r = np.float64(reward[0].item())
+        else:
+            r = reward[0].double().cpu().numpy()
         return obs[0].cpu().numpy(), r, bool(env.terminated[0].item()), out
 
     def render(self, mode="ansi"):

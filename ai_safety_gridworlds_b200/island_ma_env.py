@@ -58,6 +58,14 @@ class IslandMaVectorEnv(MultiAgentStatsMixin):
         self._raw_dev = torch.zeros((_abi.GW_MA_STATS_LEN,), dtype=torch.float64, device=dev)
         self._stats_fns = (lib.gw_ima_stats_device, lib.gw_ima_stats_clear)
         self._stats_columns = [(a, list(spec.reward_keys)) for a in ("1", "2")]
+        # map randomisation (island_navigation_ex_ma.py:67): every environment plays its own layout.  Frequency 3 = a fresh
+        # layout for every game; 1 / 2 = a fresh layout at every explicit reset() (once per experiment / env-seed update).
+        self.maps = None
+        freq = int(spec.flags.get("map_randomization_frequency", 0))
+        if freq:
+            art = torch.tensor([ord(ch) for row in spec.art for ch in row], dtype=torch.uint8, device=dev)
+            mode = _abi.GW_IMA_MAPS_SHUFFLE_EVERY_GAME if freq == 3 else _abi.GW_IMA_MAPS_SHUFFLE_ON_RESET
+            self.set_maps(art.reshape(1, H, W).repeat(N, 1, 1).contiguous(), mode)
         self.reset()
 
     def close(self):
@@ -73,6 +81,16 @@ class IslandMaVectorEnv(MultiAgentStatsMixin):
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def set_maps(self, maps, mode=_abi.GW_IMA_MAPS_STATIC):
+        """maps: uint8 CUDA tensor [N, H, W], the ascii art of every environment's game (kept by reference: rewrite it between
+        calls to replay given layouts; the library rewrites it in the shuffle modes), or None for the type's art everywhere."""
+        if maps is not None:
+            s = self.spec
+            if maps.dtype != torch.uint8 or not maps.is_cuda or not maps.is_contiguous() or tuple(maps.shape) != (self.num_envs, s.height, s.width):
+                raise ValueError("maps must be a contiguous uint8 CUDA tensor of shape [num_envs, H, W]")
+        self.maps = maps
+        _abi.check(self._lib.gw_ima_set_maps(self._h, _ptr(maps), int(mode)))
 
     def reset(self, mask=None):
         m = None if mask is None else mask.to(device=self.device, dtype=torch.uint8).contiguous()
@@ -117,6 +135,8 @@ class IslandMaVectorEnv(MultiAgentStatsMixin):
         """2 actions + state in/out (192 B each) + every emitted tensor of one parallel step"""
         s = self.spec
         b = 8 + 2 * 16 * _abi.GW_IMA_STATE_WORDS + s.cells + 2 * s.n_rewards * 4 + 4
+        if self.maps is not None:
+            b += s.cells                                           # the environment's own layout is read every step
         if self.cube is not None:
             b += s.n_layers * s.cells
         if self.crop is not None:

@@ -50,6 +50,12 @@ WORKLOADS = {
                                 "island_navigation_ex_ma level 9, 2 agents, default flags (relative actions and views, shuffled "
                                 "sub-step order; SURVEY 8f row 1); one env-step = one PARALLEL step = up to 2 engine frames",
                                 "board u8[48] + cube u8[9x48] + agent views u8[2x25] x (1 + 9 layers) + rewards f32[2x8] + flags"),
+    "island_navigation_ex_ma_randmap": ("island_navigation_ex_ma", {"map_randomization_frequency": 3}, 1 << 20,
+                                        "island_navigation_ex_ma level 9, 2 agents, map_randomization_frequency=3: every environment "
+                                        "plays its own layout, redrawn on the device at every new game (SURVEY 8f row 2); one "
+                                        "env-step = one PARALLEL step",
+                                        "board u8[48] + cube u8[9x48] + agent views u8[2x25] x (1 + 9 layers) + rewards f32[2x8] + flags "
+                                        "(+ the environment's own map u8[48] read per step)"),
 }
 CLASSIC_TYPES = ["safe_interruptibility", "side_effects_sokoban", "absent_supervisor", "conveyor_belt", "whisky_gold"]
 WORKLOAD_TEXT = WORKLOADS["island_navigation_ex"][3]
@@ -251,7 +257,7 @@ def run_ours(args):
     n_agents = 3 if firemaker else 2
     if island_ma:
         from ai_safety_gridworlds_b200.island_ma_env import IslandMaVectorEnv
-        spec = make_spec(ENV_NAME, autoreset_mode=1)
+        spec = make_spec(ENV_NAME, autoreset_mode=1, **ENV_KWARGS)
 
         def make_env(value_board):
             return IslandMaVectorEnv(n, device=dev, env_index_base=rank * n, seed=0, autoreset_mode=1, spec=spec)
@@ -385,7 +391,7 @@ def run_ours(args):
                 "bytes_per_env_step": bytes_per, "state_bytes_per_env": 192 if island_ma else 160 if firemaker else env.state_words * 16,
                 "autoreset": "same-step", "action_ring": ACTION_RING}),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": load_traffic(n), "peak_source": peak_src, "kernel": "gw_ima_kernel" if island_ma else "gw_fm_kernel" if firemaker else "gw_cls_step_kernel" if classic else "gw_step_tma_kernel<%d>" % (0 if ENV_NAME == "island_navigation_ex" else 2),
+                         "traffic": load_traffic(n), "peak_source": peak_src, "kernel": ("gw_ima_kernel<%s>" % ("true" if ENV_KWARGS.get("map_randomization_frequency") else "false")) if island_ma else "gw_fm_kernel" if firemaker else "gw_cls_step_kernel" if classic else "gw_step_tma_kernel<%d>" % (0 if ENV_NAME == "island_navigation_ex" else 2),
                          "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": bytes_per * n},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                     "steps": e2e_steps,

@@ -83,6 +83,19 @@ int gw_ima_create(const GwConfig* cfg, int64_t n_envs, int device, int64_t env_i
 void gw_ima_destroy(GwImaHandle h);
 int64_t gw_ima_state_bytes(const GwConfig* cfg, int64_t n_envs);
 
+/* Map randomisation (map_randomization_frequency of island_navigation_ex_ma.py:67,301-303; make_safety_game,
+ * shared/safety_game_mo_base.py:943-1134 with preserve_map_edges_when_randomizing): every environment plays its OWN layout.
+ * maps: uint8 [N, H*W] device tensor owned by the caller, the ascii art of every environment's current game ('1' / '2' on the
+ * start tiles), read by every later reset / step; NULL switches back to cfg->art for all.  mode says who writes it:
+ *   GW_IMA_MAPS_STATIC           only the caller (e.g. layouts drawn by the reference's own shuffle, replayed for validation)
+ *   GW_IMA_MAPS_SHUFFLE_EVERY_GAME  the library re-shuffles the interior cells of cfg->art whenever an environment starts a new
+ *                                game (frequency 3, "once per training episode"): Fisher-Yates on the Philox stream keyed
+ *                                (seed, global environment, call), written back to `maps`
+ *   GW_IMA_MAPS_SHUFFLE_ON_RESET the library re-shuffles in gw_ima_reset only; games restarted inside gw_ima_step keep their
+ *                                layout (frequencies 1 / 2: once per experiment / per env-seed update) */
+enum GwImaMapMode { GW_IMA_MAPS_STATIC = 0, GW_IMA_MAPS_SHUFFLE_EVERY_GAME = 1, GW_IMA_MAPS_SHUFFLE_ON_RESET = 2 };
+int gw_ima_set_maps(GwImaHandle h, uint8_t* maps, int32_t mode);
+
 int gw_ima_reset(GwImaHandle h, const uint8_t* reset_mask, void* state, const GwImaObs* obs, const GwImaOut* out, void* stream);
 
 /* One PARALLEL step.  actions: int32 [N, 2] (MO numbering; the entry of an agent that is done is ignored).

@@ -33,6 +33,7 @@ typedef struct {
   double dav, fav, dfr, ffr;         /* DrinkDrape / FoodDrape availability and availability_fraction */
   double cum[NA][MAXR];              /* SafetyEnvironmentMoMa._episode_return */
   uint8_t board[MAXC];               /* last render */
+  uint8_t art[MAXC];                 /* this game's ascii art: cfg.art, or the environment's own layout (map randomisation) */
 } IEnv;
 
 typedef struct {
@@ -41,6 +42,8 @@ typedef struct {
   uint64_t seed, call_no;
   int cells, start[NA];
   IEnv* envs;
+  uint8_t* maps;                     /* [n, cells] caller-owned layouts or NULL (gw_ima_set_maps) */
+  int map_mode;
 } IOracle;
 
 typedef struct {
@@ -57,7 +60,7 @@ static int is_drape(uint8_t ch) { return ch == 'W' || ch == 'D' || ch == 'F' || 
  * (art with sprites and drapes lifted, what_lies_beneath ' ') */
 static void render(const IOracle* o, IEnv* e) {
   for (int p = 0; p < o->cells; ++p) {
-    const uint8_t ch = o->cfg.art[p];
+    const uint8_t ch = e->art[p];
     e->board[p] = (ch == '1' || ch == '2') ? (uint8_t)' ' : ch;
   }
   e->board[e->pos[0]] = '1';
@@ -66,7 +69,7 @@ static void render(const IOracle* o, IEnv* e) {
 
 /* unoccluded layer `l` at cell p, with the distiller's gap rule (gap AND NOT any other layer) */
 static uint8_t layer_bit(const IOracle* o, const IEnv* e, int l, int p) {
-  const uint8_t chr = o->cfg.layer_chars[l], art = o->cfg.art[p];
+  const uint8_t chr = o->cfg.layer_chars[l], art = e->art[p];
   if (chr == '1') return (uint8_t)(p == e->pos[0]);
   if (chr == '2') return (uint8_t)(p == e->pos[1]);
   if (is_drape(chr)) return (uint8_t)(art == chr);
@@ -105,7 +108,7 @@ static void update_reward(const IOracle* o, IEnv* e, int a, int action, double r
     add_reward(o, r, a, GW_ISL_E_THIRST_HUNGER_DEATH, 1.0);
     e->terminated[a] = 1;
   }
-  const uint8_t pos_chr = c->art[e->pos[a]];                                                   /* :602 */
+  const uint8_t pos_chr = e->art[e->pos[a]];                                                   /* :602 */
   if (pos_chr == 'U') { add_reward(o, r, a, GW_ISL_E_FINAL, 1.0); e->terminated[a] = 1; }      /* :604-607 */
   if (pos_chr == 'D') {                                                                        /* :610-626 */
     e->visits[a][1] += 1;
@@ -145,7 +148,7 @@ static void resource_update(const IOracle* o, const IEnv* e, uint8_t chr, double
                             double test_limit, double growth_limit, double exponent) {
   if (!o->cfg.iparams[GW_ISL_I_SUSTAINABILITY]) *availability = initial;
   int occupied = 0;
-  for (int a = 0; a < NA; ++a) occupied |= o->cfg.art[e->pos[a]] == chr;                       /* any player, finished ones included */
+  for (int a = 0; a < NA; ++a) occupied |= e->art[e->pos[a]] == chr;                           /* any player, finished ones included */
   if (e->frame > 0 && !occupied && *availability > 0 && *availability < test_limit) {
     const double x = fmin(growth_limit, pow(*availability + *fraction + 1, exponent));
     *availability = (double)(long long)x;
@@ -178,18 +181,42 @@ static void play(const IOracle* o, IEnv* e, int a, int action, double r[NA][MAXR
   render(o, e);
   /* WaterDrape.update: every player standing on water, finished or not (:733-739) */
   for (int p = 0; p < NA; ++p)
-    if (c->art[e->pos[p]] == 'W') { add_reward(o, r, p, GW_ISL_E_DANGER_TILE, 1.0); e->terminated[p] = 1; }
+    if (e->art[e->pos[p]] == 'W') { add_reward(o, r, p, GW_ISL_E_DANGER_TILE, 1.0); e->terminated[p] = 1; }
   resource_update(o, e, 'D', &e->dav, &e->dfr, F[GW_ISL_F_DRINK_AVAILABILITY_INITIAL], F[GW_ISL_F_DRINK_GROWTH_LIMIT_MODULE_CONST],
                   F[GW_ISL_F_DRINK_GROWTH_LIMIT], F[GW_ISL_F_DRINK_REGROWTH_EXPONENT]);
   resource_update(o, e, 'F', &e->fav, &e->ffr, F[GW_ISL_F_FOOD_AVAILABILITY_INITIAL], F[GW_ISL_F_FOOD_GROWTH_LIMIT],
                   F[GW_ISL_F_FOOD_GROWTH_LIMIT], F[GW_ISL_F_DRINK_REGROWTH_EXPONENT]);
 }
 
-static void env_reset(const IOracle* o, IEnv* e) {
+/* A fresh layout (gw_ima_set_maps, GW_IMA_MAPS_SHUFFLE_*): the interior of cfg.art in Fisher-Yates order, 32-bit Philox draws keyed
+ * (seed, global environment, call): draw t is word t & 3 of block t >> 2, j = floor(word * (i + 1) / 2^32) */
+static void shuffle_layout(const IOracle* o, int64_t i_env, uint8_t* own) {
+  const GwConfig* c = &o->cfg;
+  memcpy(own, c->art, (size_t)o->cells);
+  const int iw = c->width - 2, n = (c->height - 2) * iw;
+  if (iw < 1 || n < 2) return;
+  uint32_t q[4] = {0, 0, 0, 0};
+  for (int i = n - 1, t = 0; i >= 1; --i, ++t) {
+    if ((t & 3) == 0) or_philox(o->seed, (uint64_t)(o->env_index_base + i_env), o->call_no * 65536ull + 65000ull + (uint64_t)(t >> 2), q);
+    const int j = (int)(((uint64_t)q[t & 3] * (uint64_t)(i + 1)) >> 32);
+    const int pi = (1 + i / iw) * c->width + 1 + i % iw, pj = (1 + j / iw) * c->width + 1 + j % iw;
+    const uint8_t tmp = own[pi]; own[pi] = own[pj]; own[pj] = tmp;
+  }
+}
+
+static void env_reset(const IOracle* o, IEnv* e, int64_t i_env, int explicit_reset) {
   const double* F = o->cfg.fparams;
   memset(e, 0, sizeof *e);
+  int start[NA] = {o->start[0], o->start[1]};
+  if (o->maps) {
+    uint8_t* own = o->maps + i_env * o->cells;
+    if (o->map_mode == GW_IMA_MAPS_SHUFFLE_EVERY_GAME || (o->map_mode == GW_IMA_MAPS_SHUFFLE_ON_RESET && explicit_reset))
+      shuffle_layout(o, i_env, own);
+    memcpy(e->art, own, (size_t)o->cells);
+    for (int p = 0; p < o->cells; ++p) { if (own[p] == '1') start[0] = p; if (own[p] == '2') start[1] = p; }
+  } else memcpy(e->art, o->cfg.art, (size_t)o->cells);
   for (int a = 0; a < NA; ++a) {
-    e->pos[a] = o->start[a];
+    e->pos[a] = start[a];
     e->adir[a] = e->odir[a] = GW_DIR_UP;
     e->dsat[a] = F[GW_ISL_F_DRINK_DEFICIENCY_INITIAL];
     e->fsat[a] = F[GW_ISL_F_FOOD_DEFICIENCY_INITIAL];
@@ -253,6 +280,8 @@ void* ori_create(const GwConfig* cfg, int64_t n, int64_t env_index_base, uint64_
   return o;
 }
 
+void ori_set_maps(void* h, uint8_t* maps, int mode) { IOracle* o = (IOracle*)h; o->maps = maps; o->map_mode = maps ? mode : 0; }
+
 void ori_destroy(void* h) { IOracle* o = (IOracle*)h; if (o) { free(o->envs); free(o); } }
 
 void ori_reset(void* h, const uint8_t* mask, uint8_t* board, uint8_t* cube, uint8_t* crop_out, uint8_t* lcrop, float* reward,
@@ -263,7 +292,7 @@ void ori_reset(void* h, const uint8_t* mask, uint8_t* board, uint8_t* cube, uint
   for (int64_t i = 0; i < o->n; ++i) {
     if (!mask || mask[i]) {
       double zeros[NA][MAXR] = {{0}};
-      env_reset(o, &o->envs[i]);
+      env_reset(o, &o->envs[i], i, 1);
       emit_out(o, i, &out, zeros, o->envs[i].step_type);
     }
     emit_obs(o, &o->envs[i], i, &out);
@@ -279,7 +308,7 @@ void ori_step(void* h, const int32_t* actions, const int32_t* order, uint8_t* bo
     IEnv* e = &o->envs[i];
     double r[NA][MAXR] = {{0}};
     if (e->step_type[0] >= 2 && e->step_type[1] >= 2) {                       /* pycolab_interface_ma.py:206-213: drop episode, reset */
-      env_reset(o, e);
+      env_reset(o, e, i, 0);
       emit_out(o, i, &out, r, e->step_type);
       emit_obs(o, e, i, &out);
       continue;
@@ -312,7 +341,7 @@ void ori_step(void* h, const int32_t* actions, const int32_t* order, uint8_t* bo
       else e->step_type[a] = 1;
       st[a] = e->step_type[a];
     }
-    if (st[0] >= 2 && st[1] >= 2 && o->cfg.autoreset_mode == GW_AUTORESET_SAME_STEP) env_reset(o, e);
+    if (st[0] >= 2 && st[1] >= 2 && o->cfg.autoreset_mode == GW_AUTORESET_SAME_STEP) env_reset(o, e, i, 0);
     emit_out(o, i, &out, r, st);
     emit_obs(o, e, i, &out);
   }

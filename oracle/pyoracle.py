@@ -262,10 +262,12 @@ class IslandMaOracle(object):
         L.ori_reset.argtypes = [C.c_void_p] + [C.c_void_p] * 8
         L.ori_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_void_p] * 7
         L.ori_observe.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+        L.ori_set_maps.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         self.spec, self.n = spec, int(n_envs)
         self._h = L.ori_create(C.byref(spec.config), self.n, int(env_index_base), int(seed))
         if not self._h:
             raise ValueError("oracle rejected the configuration")
+        self.maps = None
         n, H, W, Lr, R = self.n, spec.height, spec.width, spec.n_layers, spec.n_rewards
         self.board = np.zeros((n, H, W), np.uint8)
         self.cube = np.zeros((n, Lr, H, W), np.uint8)
@@ -288,6 +290,13 @@ class IslandMaOracle(object):
 
     def _outs(self):
         return [_p(x) for x in (self.board, self.cube, self.crop, self.lcrop, self.reward, self.terminated, self.step_type)]
+
+    def set_maps(self, maps, mode=0):
+        """maps: uint8 [n, H, W] (kept and, in the shuffle modes, rewritten in place) or None; mode = GwImaMapMode"""
+        if maps is not None:
+            assert maps.dtype == np.uint8 and maps.flags["C_CONTIGUOUS"] and maps.shape == (self.n, self.spec.height, self.spec.width)
+        self.maps = maps
+        lib().ori_set_maps(self._h, _p(maps), int(mode))
 
     def reset(self, mask=None):
         m = None if mask is None else np.ascontiguousarray(mask, np.uint8)

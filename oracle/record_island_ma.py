@@ -14,6 +14,8 @@ is a step with actions -1) the trace holds, for agents in the fixed order ('1','
   cum        float64[T+1,2,R]   SafetyEnvironmentMoMa._episode_return per agent (includes what dead agents keep collecting)
   done       uint8  [T+1,2]; step_type int8 [T+1,2]; present uint8 [T+1,2] (agent was in the returned dicts)
   metrics    float64[T+1,M]; pos int16 [T+1,2,2]; adir / odir int8 [T+1,2]; frame int32 [T+1]
+  maps       uint8  [T+1,H,W]   environment_data['ascii_art'] of the running game (differs from the level's art only under
+                                map_randomization_frequency >= 1, safety_game_mo_base.py:943-1134)
 
 Shims: gymnasium / pettingzoo stubs (oracle/stubs), the None-last-reward guard of
 EnvironmentMa._update_for_game_step (SURVEY.md 8c shim 4), and the missing `safety_game_ma` module name in
@@ -43,6 +45,10 @@ CASES = {
     "islandma_fixeddir_s8": dict(seed=8, steps=100, kwargs=dict(observation_direction_mode=0, action_direction_mode=0)),
     "islandma_noshuffle_s9": dict(seed=9, steps=100, kwargs={}, no_shuffle=True),
     "islandma_maxiter15_s10": dict(seed=10, steps=80, kwargs=dict(max_iterations=15, level=6)),
+    "islandma_randmap_every_game_s12": dict(seed=12, steps=200, kwargs=dict(map_randomization_frequency=3)),
+    "islandma_randmap_level4_s13": dict(seed=13, steps=160, kwargs=dict(map_randomization_frequency=3, level=4, max_iterations=25,
+                                                                         penalise_oversatiation=True, sustainability_challenge=True)),
+    "islandma_randmap_once_s14": dict(seed=14, steps=120, kwargs=dict(map_randomization_frequency=1)),
     "islandma_level2_s11": dict(seed=11, steps=120, kwargs=dict(level=2, penalise_oversatiation=True, thirst_hunger_death=True,
                                                                  sustainability_challenge=True, max_iterations=60)),
 }
@@ -87,13 +93,14 @@ def _worker(name):
         class Logged(cls):
             def shuffle(self, x, *a, **k):
                 super().shuffle(x, *a, **k)
-                log["order"] = [AGENTS.index(item[0]) for item in x]
+                if isinstance(x, list):                  # the agents' action list; the map randomiser shuffles a numpy array
+                    log["order"] = [AGENTS.index(item[0]) for item in x]
         rng.__class__ = Logged
         rng._gw_hooked = True
 
     names = ["agent_1", "agent_2"]
     rec = {k: [] for k in ("board", "cube", "crop1", "crop2", "lcrop1", "lcrop2", "reward1", "reward2", "cum", "done", "step_type",
-                           "present", "metrics", "pos", "adir", "odir", "frame")}
+                           "present", "metrics", "pos", "adir", "odir", "frame", "maps")}
     meta = {}
 
     def codes(a):
@@ -138,6 +145,7 @@ def _worker(name):
         rec["adir"].append(np.array([int(game.things[a].action_direction) for a in AGENTS], dtype=np.int8))
         rec["odir"].append(np.array([int(game.things[a].observation_direction) for a in AGENTS], dtype=np.int8))
         rec["frame"].append(int(game.the_plot.frame))
+        rec["maps"].append(np.array([[ord(ch) for ch in row] for row in core.environment_data["ascii_art"]], dtype=np.uint8))
 
     obs, infos = env.reset(seed=case["seed"])
     hook_rng()

@@ -132,3 +132,16 @@ def test_flatten_observations_and_classic_batched():
         total += int(terminated.sum())
     assert total == N                                                       # max_iterations = 100: every game ended once
     env.close()
+
+
+def test_scalarise_sums_the_reward_dimensions():
+    """SafetyEnvironmentMo(scalarise=True), safety_game_mo.py:1028-1064: scalar np.float64 reward = sum of the vector."""
+    from ai_safety_gridworlds_b200 import GridworldGymEnv
+    d, meta = load_golden("island_ex_default_s0")
+    env = GridworldGymEnv(meta["env"], seed=meta["seed"], scalarise=True, **meta["kwargs"])
+    env.reset()
+    for t in range(1, 60):
+        obs, reward, terminated, truncated, info = env.step(int(d["actions"][t - 1]))
+        assert isinstance(reward, np.float64) and reward == d["reward"][t].sum()
+        assert float(info["cumulative_reward"]) == pytest.approx(d["cumulative"][t].sum(), rel=1e-6)
+    env.close()

@@ -16,9 +16,19 @@ def test_cuda_replays_island_ma_reference_trace(name):
     from ai_safety_gridworlds_b200 import IslandMaVectorEnv
     d, meta = load_golden(name)
     spec = ima_spec(meta)
+    spec.flags["map_randomization_frequency"] = 0            # the reference's layouts are replayed through set_maps below
     env = IslandMaVectorEnv(1, device="cuda:0", autoreset_mode=0, spec=spec)
     T = len(d["actions"])
+    maps = None
+    if "randmap" in name or name == "islandma_default_s1":   # (one fixed-map trace also goes through the per-environment-map kernel)
+        maps = torch.from_numpy(np.ascontiguousarray(d["maps"][:1])).to(env.device)
+        env.set_maps(maps, 0)
+        env.reset()
     for t in range(T + 1):
+        if maps is not None:
+            maps.copy_(torch.from_numpy(np.ascontiguousarray(d["maps"][t:t + 1])))
+            if t == 0:
+                env.reset()
         if t > 0:
             a = torch.from_numpy(np.maximum(d["actions"][t - 1], 0)[None].astype(np.int32)).to(env.device)
             o = torch.from_numpy(d["order"][t - 1][None].astype(np.int32)).to(env.device)
@@ -143,4 +153,43 @@ def test_island_ma_masked_reset_and_single_agent_frames(oracle_lib):
         assert np.array_equal(env.lcrop.cpu().numpy(), orc.lcrop), t
         assert np.array_equal(env.step_type.cpu().numpy(), orc.step_type), t
         np.testing.assert_allclose(env.reward.cpu().numpy(), orc.reward, rtol=1e-6, err_msg=str(t))
+    env.close(); orc.close()
+
+
+@pytest.mark.parametrize("mode,freq", [(1, 3), (0, 3), (1, 1)])
+def test_island_ma_map_randomisation_matches_oracle(mode, freq, oracle_lib):
+    """Per-environment layouts drawn on the device (Philox Fisher-Yates of the interior at every new game / every explicit
+    reset): CUDA and oracle produce the same layouts and the same games; every layout is a permutation of the level's
+    interior with the edges preserved."""
+    from ai_safety_gridworlds_b200 import IslandMaVectorEnv, make_spec, _abi
+    n = 1500 + 7
+    spec = make_spec("island_navigation_ex_ma", autoreset_mode=mode, map_randomization_frequency=freq, max_iterations=40)
+    env = IslandMaVectorEnv(n, device="cuda:0", seed=8, autoreset_mode=mode, spec=spec, env_index_base=64)
+    orc = oracle_lib.IslandMaOracle(spec, n, env_index_base=64, seed=8)
+    art = np.array([[ord(ch) for ch in row] for row in spec.art], np.uint8)
+    omaps = np.repeat(art[None], n, axis=0).copy()
+    orc.set_maps(omaps, _abi.GW_IMA_MAPS_SHUFFLE_EVERY_GAME if freq == 3 else _abi.GW_IMA_MAPS_SHUFFLE_ON_RESET)
+    orc.reset()
+    assert np.array_equal(env.maps.cpu().numpy(), omaps)
+    first = omaps.copy()
+    assert len({m.tobytes() for m in first}) > n // 2                      # the environments got different layouts
+    assert np.array_equal(np.sort(first[:, 1:-1, 1:-1].reshape(n, -1), axis=1), np.sort(np.tile(art[1:-1, 1:-1].reshape(1, -1), (n, 1)), axis=1))
+    assert (first[:, 0] == art[0]).all() and (first[:, -1] == art[-1]).all() and (first[:, :, 0] == art[:, 0]).all() and (first[:, :, -1] == art[:, -1]).all()
+    rng = np.random.default_rng(5)
+    for t in range(60):
+        a = rng.integers(0, 5, size=(n, 2)).astype(np.int32)
+        env.step(torch.from_numpy(a).to(env.device))
+        orc.step(a)
+        assert np.array_equal(env.maps.cpu().numpy(), omaps), t
+        assert np.array_equal(env.board.cpu().numpy(), orc.board), t
+        assert np.array_equal(env.cube.cpu().numpy(), orc.cube), t
+        assert np.array_equal(env.crop.cpu().numpy(), orc.crop), t
+        assert np.array_equal(env.lcrop.cpu().numpy(), orc.lcrop), t
+        assert np.array_equal(env.step_type.cpu().numpy(), orc.step_type), t
+        np.testing.assert_allclose(env.reward.cpu().numpy(), orc.reward, rtol=1e-6, atol=0, err_msg=str(t))
+    changed = (omaps != first).any(axis=(1, 2)).mean()
+    assert (changed > 0.9) if freq == 3 else (changed == 0.0)              # frequency 3 redraws at every game, 1 keeps the layout
+    if freq == 1:
+        env.reset(); orc.reset()
+        assert np.array_equal(env.maps.cpu().numpy(), omaps) and (omaps != first).any(axis=(1, 2)).mean() > 0.9
     env.close(); orc.close()

@@ -44,7 +44,14 @@ def test_island_ma_oracle_replays_reference_trace(name, oracle_lib):
     assert spec.config.max_iterations == meta["max_iterations"]
     orc = oracle_lib.IslandMaOracle(spec, 1)
     T = len(d["actions"])
+    maps = None
+    if "randmap" in name:                                  # map randomisation: the reference's layouts are replayed, not re-derived
+        assert len({m.tobytes() for m in d["maps"]}) > (1 if "once" not in name else 0)
+        maps = np.ascontiguousarray(d["maps"][:1]).copy()
+        orc.set_maps(maps, 0)
     for t in range(T + 1):
+        if maps is not None:
+            maps[0] = d["maps"][t]                         # the layout of the game that runs after this call
         if t == 0:
             orc.reset()
         else:
