@@ -109,6 +109,52 @@ CASES = {
 }
 
 
+def _fuzz_cases():
+    """Randomised flag combinations (fixed seed): levels, switches, fractional rates / limits / thresholds, multi-dimensional and
+    zero reward flags, short cut-offs.  They widen the pin of the oracle beyond the hand-picked variants above."""
+    import random
+    rnd = random.Random(20261018)
+    out = {}
+    for k in range(16):
+        kw = {"level": rnd.randrange(0, 10), "sustainability_challenge": rnd.random() < 0.5, "thirst_hunger_death": rnd.random() < 0.4,
+              "penalise_oversatiation": rnd.random() < 0.6, "use_satiation_proportional_reward": rnd.random() < 0.4,
+              "max_iterations": rnd.choice([12, 40, 100, 100])}
+        for prefix in ("DRINK", "FOOD"):
+            if rnd.random() < 0.6:
+                kw[prefix + "_DEFICIENCY_RATE"] = rnd.choice([-1, -0.5, -2, -0.25])
+            if rnd.random() < 0.6:
+                kw[prefix + "_EXTRACTION_RATE"] = rnd.choice([10, 4, 7, 2.5, 20])
+            if rnd.random() < 0.5:
+                kw[prefix + "_OVERSATIATION_LIMIT"] = rnd.choice([4, 0, 8, 2.5])
+            if rnd.random() < 0.4:
+                kw[prefix + "_DEFICIENCY_LIMIT"] = rnd.choice([-20, -6, -10])
+            if rnd.random() < 0.4:
+                kw[prefix + "_DEFICIENCY_INITIAL"] = rnd.choice([0, -2, 3])
+            if rnd.random() < 0.4:
+                kw[prefix + "_AVAILABILITY_INITIAL"] = rnd.choice([20, 8, 12.5])
+            if rnd.random() < 0.3:
+                kw[prefix + "_GROWTH_LIMIT"] = rnd.choice([20, 15, 30])
+        if rnd.random() < 0.4:
+            kw["DRINK_REGROWTH_EXPONENT"] = rnd.choice([1.1, 1.3, 1.05])
+        if rnd.random() < 0.3:
+            kw["MOVEMENT_REWARD"] = rnd.choice(["{'MOVEMENT_REWARD': 0}", "{'MOVEMENT_REWARD': -2.5}", "{'MOVEMENT_REWARD': -1, 'DRINK_REWARD': 0.5}"])
+        if rnd.random() < 0.3:
+            kw["GOLD_REWARD"] = rnd.choice(["{'GOLD_REWARD': 15}", "{'GOLD_REWARD': 40, 'SILVER_REWARD': 1}"])
+        if rnd.random() < 0.3:
+            kw["DRINK_REWARD"] = rnd.choice(["{'DRINK_REWARD': 0}", "{'DRINK_REWARD': 7.5}"])
+        if k == 14:
+            # level 0 (no drink tile) with DRINK_DEFICIENCY_INITIAL = -2: the reference itself raises "Reward DRINK_DEFICIENCY_REWARD is
+            # not enabled but is still included in mo_reward with nonzero value" at the first step (mo_reward.py:198); the spec compiler
+            # raises the same error eagerly (tests/test_abi_and_host.py::test_reference_rejected_flags_are_rejected)
+            continue
+        out["island_fuzz_%02d" % k] = dict(env="island_navigation_ex", kwargs=kw, steps=160, seed=500 + k,
+                                           policy=rnd.choice(["uniform", "mixed", "safe"]), avoid="W", lo=0, hi=4)
+    return out
+
+
+CASES.update(_fuzz_cases())
+
+
 def _worker(name):
     """Runs inside the fresh interpreter (PYTHONPATH = stubs + reference)."""
     import numpy as np

@@ -170,3 +170,16 @@ def test_two_rank_host_logic_over_gloo(lib, tmp_path):
     p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout + p.stderr
     assert "rank 0 ok" in p.stdout and "rank 1 ok" in p.stdout
+
+
+def test_reference_rejected_flags_are_rejected():
+    """A randomised flag combination (oracle/record.py fuzz case 14) that the reference itself fails on -- level 0 has no drink
+    tile, so DRINK_DEFICIENCY_REWARD is not an enabled dimension, yet DRINK_DEFICIENCY_INITIAL = -2 posts it at the first step
+    (mo_reward.py:184-203) -- raises the same ValueError from the spec compiler, eagerly."""
+    from ai_safety_gridworlds_b200 import make_spec
+    msg = "Reward DRINK_DEFICIENCY_REWARD is not enabled but is still included in mo_reward with nonzero value"
+    with pytest.raises(ValueError, match=msg):
+        make_spec("island_navigation_ex", level=0, penalise_oversatiation=False, DRINK_DEFICIENCY_INITIAL=-2)
+    with pytest.raises(ValueError, match=msg):
+        make_spec("island_navigation_ex", level=0)       # verified against the reference: default flags fail on level 0 at the first step
+    make_spec("island_navigation_ex", level=0, penalise_oversatiation=False)      # satiation stays at 0: nothing is posted
