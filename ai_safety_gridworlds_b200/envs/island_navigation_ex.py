@@ -117,6 +117,9 @@ def compile_spec(autoreset_mode: int = _abi.GW_AUTORESET_NEXT_STEP, game_art: Li
     def can_go_negative(prefix):
         return flags[prefix + "_DEFICIENCY_INITIAL"] < 0 or (penalise and flags[prefix + "_DEFICIENCY_RATE"] < 0)
 
+    def can_starve(prefix):       # can the satiation reach the death limit? (it only falls under penalise_oversatiation)
+        return flags[prefix + "_DEFICIENCY_INITIAL"] <= flags[prefix + "_DEFICIENCY_LIMIT"] or (penalise and flags[prefix + "_DEFICIENCY_RATE"] < 0)
+
     def can_go_positive(prefix, tile):
         return penalise and (flags[prefix + "_DEFICIENCY_INITIAL"] > 0 or flags[prefix + "_DEFICIENCY_RATE"] > 0
                              or has[tile])
@@ -124,7 +127,7 @@ def compile_spec(autoreset_mode: int = _abi.GW_AUTORESET_NEXT_STEP, game_art: Li
     reachable = dict(
         MOVEMENT=True, FINAL=has["U"], DRINK_DEFICIENCY=can_go_negative("DRINK"), FOOD_DEFICIENCY=can_go_negative("FOOD"),
         DRINK=has["D"], FOOD=has["F"], NON_DRINK=True, NON_FOOD=True, GAP=True, GOLD=has["G"], SILVER=has["S"],
-        DANGER_TILE=has["W"], THIRST_HUNGER_DEATH=bool(death),
+        DANGER_TILE=has["W"], THIRST_HUNGER_DEATH=bool(death) and (can_starve("DRINK") or can_starve("FOOD")),
         DRINK_OVERSATIATION=can_go_positive("DRINK", "D"), FOOD_OVERSATIATION=can_go_positive("FOOD", "F"))
 
     # layers: backdrop palette (art characters that are neither sprite nor drape, plus the gap

@@ -136,13 +136,16 @@ def compile_spec(autoreset_mode: int = _abi.GW_AUTORESET_NEXT_STEP, **kwargs) ->
     def below(prefix):            # can the satiation fall under the deficiency threshold?
         return flags[prefix + "_DEFICIENCY_INITIAL"] < flags[prefix + "_DEFICIENCY_THRESHOLD"] or (penalise and flags[prefix + "_DEFICIENCY_RATE"] < 0)
 
+    def can_starve(prefix):       # can the satiation reach the death limit? (it only falls under penalise_oversatiation)
+        return flags[prefix + "_DEFICIENCY_INITIAL"] <= flags[prefix + "_DEFICIENCY_LIMIT"] or (penalise and flags[prefix + "_DEFICIENCY_RATE"] < 0)
+
     def above(prefix, tile):
         return penalise and (flags[prefix + "_DEFICIENCY_INITIAL"] > flags[prefix + "_OVERSATIATION_THRESHOLD"]
                              or flags[prefix + "_DEFICIENCY_RATE"] > 0 or has[tile])
 
     reachable = dict(
         MOVEMENT=True, FINAL=has["U"], DRINK_DEFICIENCY=below("DRINK"), FOOD_DEFICIENCY=below("FOOD"), DRINK=has["D"], FOOD=has["F"],
-        NON_DRINK=True, NON_FOOD=True, GAP=True, GOLD=has["G"], SILVER=has["S"], DANGER_TILE=has["W"], THIRST_HUNGER_DEATH=bool(death),
+        NON_DRINK=True, NON_FOOD=True, GAP=True, GOLD=has["G"], SILVER=has["S"], DANGER_TILE=has["W"], THIRST_HUNGER_DEATH=bool(death) and (can_starve("DRINK") or can_starve("FOOD")),
         DRINK_OVERSATIATION=above("DRINK", "D"), FOOD_OVERSATIATION=above("FOOD", "F"))
 
     backdrop_chars = {ch for row in art for ch in row if ch not in AGENTS and ch not in DRAPE_CHARS} | {GAP_CHR}

@@ -52,6 +52,39 @@ CASES = {
     "islandma_level2_s11": dict(seed=11, steps=120, kwargs=dict(level=2, penalise_oversatiation=True, thirst_hunger_death=True,
                                                                  sustainability_challenge=True, max_iterations=60)),
 }
+
+
+def _fuzz_cases():
+    """Randomised flag combinations (fixed seed) to widen the pin of the oracle beyond the hand-picked variants."""
+    import random
+    rnd = random.Random(7120261018)
+    out = {}
+    for k in range(10):
+        kw = {"level": rnd.choice([1, 2, 3, 4, 5, 6, 7, 8, 9, 10]), "sustainability_challenge": rnd.random() < 0.5,
+              "thirst_hunger_death": rnd.random() < 0.4, "penalise_oversatiation": rnd.random() < 0.6,
+              "use_satiation_proportional_reward": rnd.random() < 0.4, "max_iterations": rnd.choice([14, 40, 100]),
+              "observation_direction_mode": rnd.choice([0, 1, 1]), "action_direction_mode": rnd.choice([0, 1, 1]),
+              "map_randomization_frequency": rnd.choice([0, 0, 3])}
+        for prefix in ("DRINK", "FOOD"):
+            if rnd.random() < 0.5:
+                kw[prefix + "_DEFICIENCY_RATE"] = rnd.choice([-1, -0.5, -2])
+            if rnd.random() < 0.5:
+                kw[prefix + "_EXTRACTION_RATE"] = rnd.choice([10, 4, 2.5])
+            if rnd.random() < 0.4:
+                kw[prefix + "_OVERSATIATION_LIMIT"] = rnd.choice([4, 0, 8])
+            if rnd.random() < 0.4:
+                kw[prefix + "_DEFICIENCY_THRESHOLD"] = rnd.choice([-3, -1, -5.5])
+            if rnd.random() < 0.4:
+                kw[prefix + "_OVERSATIATION_THRESHOLD"] = rnd.choice([2, 0, 3])
+            if rnd.random() < 0.3:
+                kw[prefix + "_DEFICIENCY_LIMIT"] = rnd.choice([-20, -6])
+        if rnd.random() < 0.3:
+            kw["MOVEMENT_REWARD"] = rnd.choice(["{'MOVEMENT_REWARD': 0}", "{'MOVEMENT_REWARD': -2.5}"])
+        out["islandma_fuzz_%02d" % k] = dict(seed=700 + k, steps=120, kwargs=kw, no_shuffle=rnd.random() < 0.25)
+    return out
+
+
+CASES.update(_fuzz_cases())
 AGENTS = ["1", "2"]
 
 

@@ -20,7 +20,7 @@ def test_cuda_replays_island_ma_reference_trace(name):
     env = IslandMaVectorEnv(1, device="cuda:0", autoreset_mode=0, spec=spec)
     T = len(d["actions"])
     maps = None
-    if "randmap" in name or name == "islandma_default_s1":   # (one fixed-map trace also goes through the per-environment-map kernel)
+    if meta["kwargs"].get("map_randomization_frequency") or name == "islandma_default_s1":   # (one fixed-map trace also goes through the per-environment-map kernel)
         maps = torch.from_numpy(np.ascontiguousarray(d["maps"][:1])).to(env.device)
         env.set_maps(maps, 0)
         env.reset()

@@ -45,8 +45,8 @@ def test_island_ma_oracle_replays_reference_trace(name, oracle_lib):
     orc = oracle_lib.IslandMaOracle(spec, 1)
     T = len(d["actions"])
     maps = None
-    if "randmap" in name:                                  # map randomisation: the reference's layouts are replayed, not re-derived
-        assert len({m.tobytes() for m in d["maps"]}) > (1 if "once" not in name else 0)
+    if meta["kwargs"].get("map_randomization_frequency"):  # map randomisation: the reference's layouts are replayed, not re-derived
+        assert len({m.tobytes() for m in d["maps"]}) > (1 if meta["kwargs"]["map_randomization_frequency"] == 3 else 0)
         maps = np.ascontiguousarray(d["maps"][:1]).copy()
         orc.set_maps(maps, 0)
     for t in range(T + 1):
