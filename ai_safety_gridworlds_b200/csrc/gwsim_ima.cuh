@@ -381,27 +381,38 @@ __device__ __forceinline__ bool ima_step_lane(const ImaCfg& c, const ImaArgs& a,
  * of 'W' (s_bmap: character | layer << 8), and s_voff[dir][v] is the offset of the source of view cell v from the
  * agent in that bordered map, so a view cell costs one table look-up and no bounds test. */
 __device__ __forceinline__ void ima_views(const ImaCfg& c, const uint16_t* __restrict__ s_bmap, const int16_t* __restrict__ s_voff,
-                                          int pos0, int pos1, int odir0, int odir1, uint8_t* __restrict__ crop, uint8_t* __restrict__ lcrop) {
+                                          const uint8_t* __restrict__ s_vinv, int pos0, int pos1, int odir0, int odir1,
+                                          uint8_t* __restrict__ crop, uint8_t* __restrict__ lcrop) {
   const int L = c.n_layers, BW = c.width + 4;
-  const int p0b = (pos0 / c.width + 2) * BW + pos0 % c.width + 2, p1b = (pos1 / c.width + 2) * BW + pos1 % c.width + 2;
+  const int r0 = pos0 / c.width, c0 = pos0 % c.width, r1 = pos1 / c.width, c1 = pos1 % c.width;
+  const int p0b = (r0 + 2) * BW + c0 + 2, p1b = (r1 + 2) * BW + c1 + 2;
+  const int g0 = (int)(int8_t)(s_bmap[p0b] >> 8) == c.layer_gap, g1 = (int)(int8_t)(s_bmap[p1b] >> 8) == c.layer_gap;   /* on a gap tile? */
 #pragma unroll 1
   for (int ag = 0; ag < 2; ++ag) {
-    const int posb = ag ? p1b : p0b;
-    const int16_t* __restrict__ off = s_voff + (c.obs_mode ? (ag ? odir1 : odir0) : GW_DIR_UP) * IMA_VIEW;
+    const int posb = ag ? p1b : p0b, dir = c.obs_mode ? (ag ? odir1 : odir0) : GW_DIR_UP;
+    const int16_t* __restrict__ off = s_voff + dir * IMA_VIEW;
+    uint8_t* __restrict__ cr = crop ? crop + ag * IMA_VIEW : nullptr;
     uint8_t* __restrict__ lc = lcrop ? lcrop + ag * L * IMA_VIEW : nullptr;
+    /* the agent-free view: one table look-up, one character byte and one layer byte per cell */
 #pragma unroll 5
     for (int v = 0; v < IMA_VIEW; ++v) {
-      const int cb = posb + off[v];
-      const uint32_t e = s_bmap[cb];
-      uint32_t ch = e & 0xffu;
-      int l0 = (int)(int8_t)(e >> 8), l1 = -1;
-      if (cb == p0b) { ch = '1'; l1 = c.layer_a0; if (l0 == c.layer_gap) l0 = -1; }
-      if (cb == p1b) { ch = '2'; l1 = c.layer_a1; if (l0 == c.layer_gap) l0 = -1; }
-      if (crop) crop[ag * IMA_VIEW + v] = (uint8_t)ch;
-      if (lc) {
-        if (l0 >= 0) lc[l0 * IMA_VIEW + v] = 1;
-        if (l1 >= 0) lc[l1 * IMA_VIEW + v] = 1;
-      }
+      const uint32_t e = s_bmap[posb + off[v]];
+      if (cr) cr[v] = (uint8_t)e;
+      const int l0 = (int)(int8_t)(e >> 8);
+      if (lc && l0 >= 0) lc[l0 * IMA_VIEW + v] = 1;
+    }
+    /* the agents on top: the viewer at the centre, the other one where it falls inside the window (s_vinv maps a
+     * source offset to the rotated view cell); an agent's layer is set and the gap layer under it cleared */
+    const int dr = (ag ? r0 - r1 : r1 - r0) + 2, dc = (ag ? c0 - c1 : c1 - c0) + 2;
+    const int vo = (dr >= 0 && dr <= 4 && dc >= 0 && dc <= 4) ? (int)s_vinv[dir * IMA_VIEW + dr * 5 + dc] : -1;
+    const int v0 = ag ? vo : 12, v1 = ag ? 12 : vo;            /* view cells of agent '1' and agent '2' */
+    if (v0 >= 0) {
+      if (cr) cr[v0] = '1';
+      if (lc) { if (g0 && c.layer_gap >= 0) lc[c.layer_gap * IMA_VIEW + v0] = 0; if (c.layer_a0 >= 0) lc[c.layer_a0 * IMA_VIEW + v0] = 1; }
+    }
+    if (v1 >= 0) {
+      if (cr) cr[v1] = '2';
+      if (lc) { if (g1 && c.layer_gap >= 0) lc[c.layer_gap * IMA_VIEW + v1] = 0; if (c.layer_a1 >= 0) lc[c.layer_a1 * IMA_VIEW + v1] = 1; }
     }
   }
 }
@@ -449,6 +460,7 @@ __global__ void __launch_bounds__(IMA_WARPS * 32, 2) gw_ima_kernel(const __grid_
   __shared__ uint16_t s_bmap[IMA_BMAP];
   __shared__ int16_t s_voff[4 * IMA_VIEW];
   __shared__ int16_t s_vdij[4 * IMA_VIEW];
+  __shared__ uint8_t s_vinv[4 * IMA_VIEW];
   __shared__ int8_t s_lchar[128];
   for (uint32_t i = threadIdx.x; i < GW_MAX_CELLS; i += blockDim.x) { s_art[i] = c.art[i]; s_base[i] = c.base_board[i]; s_blayer[i] = c.base_layer[i]; }
   {
@@ -468,6 +480,7 @@ __global__ void __launch_bounds__(IMA_WARPS * 32, 2) gw_ima_kernel(const __grid_
       else if (dir == GW_DIR_RIGHT) { si = vj; sj = 4 - vi; }                              /* rot90 k=1 (counterclockwise) */
       s_voff[i] = (int16_t)((si - 2) * BW + (sj - 2));
       s_vdij[i] = (int16_t)(((si - 2) & 0xff) | ((sj - 2) << 8));
+      s_vinv[dir * IMA_VIEW + si * 5 + sj] = (uint8_t)(vi * 5 + vj);
     }
     for (int i = (int)threadIdx.x; i < 128; i += (int)blockDim.x) {
       int8_t l = -1;
@@ -616,7 +629,7 @@ __global__ void __launch_bounds__(IMA_WARPS * 32, 2) gw_ima_kernel(const __grid_
           ima_views_own(c, M.art, s_vdij, s_lchar, p0, p1, s.ag[0].odir, s.ag[1].odir, a.crop ? s_crop + lane * Sv : nullptr,
                         a.lcrop ? s_lcrop + lane * Sl : nullptr);
       } else {
-        ima_views(c, s_bmap, s_voff, p0, p1, s.ag[0].odir, s.ag[1].odir, a.crop ? s_crop + lane * Sv : nullptr,
+        ima_views(c, s_bmap, s_voff, s_vinv, p0, p1, s.ag[0].odir, s.ag[1].odir, a.crop ? s_crop + lane * Sv : nullptr,
                   a.lcrop ? s_lcrop + lane * Sl : nullptr);
       }
     }
