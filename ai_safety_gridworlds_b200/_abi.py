@@ -108,7 +108,7 @@ FM_R = dict(AGENT_MOVEMENT=0, WORKSHOP_WORK=1, WORKSHOP_ENERGY=2, SUP_MOVEMENT=3
 class GwFmConfig(C.Structure):
     _fields_ = [
         ("abi_version", C.c_int32), ("max_iterations", C.c_int32), ("autoreset_mode", C.c_int32), ("randomize_order", C.c_int32),
-        ("stop_button_duration", C.c_int32), ("reserved", C.c_int32 * 3),
+        ("stop_button_duration", C.c_int32), ("amount_agents", C.c_int32), ("reserved", C.c_int32 * 2),
         ("fire_continuation_probability", C.c_double), ("fire_spread_probability_at_distance_one", C.c_double),
         ("fire_spread_exclusive_max_distance", C.c_double), ("rewards", C.c_double * 8),
         ("value_map", C.c_float * 128), ("art", C.c_uint8 * (GW_FM_CELLS + 7)),

@@ -1921,6 +1921,7 @@ int gw_fm_create(const GwFmConfig* cfg, int64_t n_envs, int device, int64_t env_
     if (cfg->art[p] == '2') found[1]++;
     if (cfg->art[p] == 'S') found[2]++;
   }
+  if (cfg->amount_agents != 2 && cfg->amount_agents != 3) return fail(GW_ERR_INVALID, "amount_agents %d: 2 and 3 are built", cfg->amount_agents);
   if (found[0] != 1 || found[1] != 1 || found[2] != 1) return fail(GW_ERR_INVALID, "the map must hold exactly one '1', '2' and 'S'");
   int count = 0;
   cudaError_t ce = cudaGetDeviceCount(&count);
@@ -1973,6 +1974,9 @@ int gw_fm_create(const GwFmConfig* cfg, int64_t n_envs, int device, int64_t env_
   memcpy(st.rewards, cfg->rewards, sizeof st.rewards);
   st.max_iterations = cfg->max_iterations; st.autoreset = cfg->autoreset_mode; st.randomize = cfg->randomize_order;
   st.button_duration = cfg->stop_button_duration;
+  st.two_workers = cfg->amount_agents == 3;
+  st.static2 = -1;
+  if (!st.two_workers) { st.static2 = st.start[1]; st.start[1] = 0xffff; }
   ce = cudaMalloc((void**)&h->d_static, sizeof(FmStatic));
   if (ce == cudaSuccess) ce = cudaMemcpy(h->d_static, &st, sizeof st, cudaMemcpyHostToDevice);
   h->d_claim = nullptr; h->claim_base = 0; h->d_stats = nullptr;

@@ -40,6 +40,8 @@ struct alignas(16) FmStatic {           /* per-handle tables: device memory -> s
   double rewards[8];
   int32_t start[4];
   int32_t max_iterations, autoreset, randomize, button_duration;
+  int32_t two_workers, static2, pad1, pad2;  /* amount_agents == 3; with 2 there is no worker '2': start[1] = 0xffff, never on the board,
+                                                and static2 = the art's '2' tile, a backdrop character whose layer reads 1 */
   uint8_t base_chr[FM_CELLS + 15];      /* render without fire and agents: '#', ' ', '-', 'W', 'B' */
   uint8_t flags[FM_CELLS + 15];
 };
@@ -114,7 +116,7 @@ __device__ __forceinline__ int fm_fire_update(const FmStatic& S, const FmArgs& a
   __syncwarp();
   if (lane < 3) {                                        /* fires under agents are put out (:543-545) */
     const int p = lane == 0 ? pos[0] : lane == 1 ? pos[1] : pos[2];
-    atomicAnd(&fw[p >> 5], ~(1u << (p & 31)));
+    if (p < FM_CELLS) atomicAnd(&fw[p >> 5], ~(1u << (p & 31)));
   }
   __syncwarp();
   if (lane < FM_B) {                                     /* row r = bits [17 r, 17 r + 17) of the flat map */
@@ -270,7 +272,7 @@ __device__ __forceinline__ void fm_build_planes(const FmStatic& S, const uint32_
     pl[1 * FM_CELLS + cell] = (f & FM_F_WALL) != 0;
     pl[2 * FM_CELLS + cell] = (f & FM_F_TERRITORY) != 0;
     pl[3 * FM_CELLS + cell] = a0;
-    pl[4 * FM_CELLS + cell] = a1;
+    pl[4 * FM_CELLS + cell] = a1 || cell == S.static2;
     pl[5 * FM_CELLS + cell] = (f & FM_F_BUTTON) != 0;
     pl[6 * FM_CELLS + cell] = burning;
     pl[7 * FM_CELLS + cell] = a2;
@@ -296,6 +298,7 @@ __device__ __forceinline__ void fm_emit_obs(const FmStatic& S, const FmArgs& a, 
     const int vr = (int)lane / 5, vc = (int)lane % 5;
 #pragma unroll 1
     for (int w = 0; w < 2; ++w) {
+      if (pos[w] >= FM_CELLS) continue;                    /* no worker '2': its view stays zero */
       const int r = pos[w] / FM_S - 2 + vr, c = pos[w] % FM_S - 2 + vc;
       const bool inb = r >= 0 && r < FM_S && c >= 0 && c < FM_S;
       const int cell = inb ? r * FM_S + c : 0;
@@ -394,6 +397,7 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_co
   int32_t ext_fires = (int32_t)(words[2] >> 16);
 #pragma unroll
   for (int k = 0; k < 3; ++k) if (pos[k] >= FM_CELLS) pos[k] = S.start[k];      /* garbage state never indexes outside the board */
+  if (!S.two_workers) pos[1] = 0xffff;                                           /* no worker '2': matches no cell */
   /* the 15 visit counters (words 16..23) and the 7 cumulative rewards (words 24..37) stay in the shared-memory
    * copy of the state and are updated in place by lane 0: keeping them out of registers doubles the occupancy */
   __syncwarp();
@@ -414,14 +418,16 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_co
   if (a.is_reset) {
     write_out = !a.reset_mask || a.reset_mask[env] != 0;
     if (write_out) do_reset();
-  } else if (st[0] >= 2 && st[1] >= 2 && st[2] >= 2) {
+  } else if (st[0] >= 2 && (st[1] >= 2 || !S.two_workers) && st[2] >= 2) {
     do_reset();                                        /* rl/pycolab_interface_ma.py:206-213: every agent is done -> new game, FIRST */
   } else {
     int32_t ord[3] = {0, 1, 2};
+    if (!S.two_workers) { ord[1] = 2; ord[2] = -1; }
     if (a.order) { ord[0] = a.order[env * 3]; ord[1] = a.order[env * 3 + 1]; ord[2] = a.order[env * 3 + 2]; }
     else if (S.randomize) {
 #pragma unroll
       for (int kk = 2; kk >= 1; --kk) {
+        if (kk == 2 && !S.two_workers) continue;
         const int j = (int)(fm_uniform(a, env, 65533u + (uint32_t)kk) * (kk + 1));
         const int32_t t = ord[kk];
         ord[kk] = j == 0 ? ord[0] : j == 1 ? ord[1] : ord[2];
@@ -434,6 +440,7 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_co
     for (int t = 0; t < 3; ++t) {
       if (ord[t] < 0) continue;                          /* sub-step left out: an AEC step plays ONE agent's frame (order = {agent, -1, -1}) */
       const int ag = ord[t] > 2 ? t : ord[t];
+      if (ag == 1 && !S.two_workers) continue;           /* no worker '2' in this game */
       const int32_t act = a.actions[env * 3 + ag];
       frame += 1;
       /* the acting agent: MazeWalker against '#' and the other agents (:399-400), then update_reward (:430-463) */
@@ -459,7 +466,7 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_co
         const uint8_t f = S.flags[np];
         const int32_t burning = (int32_t)((fire[np >> 5] >> (np & 31)) & 1u);
         if (lane == 0) {
-          const uint32_t inc[5] = {1u, (f & FM_F_TERRITORY) ? 1u : 0u, (f & FM_F_WORKSHOP) ? 1u : 0u, (uint32_t)burning, (f & FM_F_BUTTON) ? 1u : 0u};
+          const uint32_t inc[5] = {np != S.static2 ? 1u : 0u, (f & FM_F_TERRITORY) ? 1u : 0u, (f & FM_F_WORKSHOP) ? 1u : 0u, (uint32_t)burning, (f & FM_F_BUTTON) ? 1u : 0u};
 #pragma unroll
           for (int j = 0; j < 5; ++j) {
             const int q = ag * 5 + j, sh = (q & 1) * 16;
@@ -471,7 +478,7 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_co
       /* StopButtonDrape.update */
 #pragma unroll
       for (int p = 0; p < 3; ++p)
-        if (S.flags[pos[p]] & FM_F_BUTTON) {
+        if (pos[p] < FM_CELLS && (S.flags[pos[p]] & FM_F_BUTTON)) {
           countdown = 2 + S.button_duration;
           if (p == 2 && ext_fires == 0) r[6] += S.rewards[GW_FM_R_SUP_STOP_BUTTON];
         }
@@ -480,12 +487,12 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_co
       bool at_w[3];
 #pragma unroll
       for (int p = 0; p < 3; ++p) {
-        at_w[p] = (S.flags[pos[p]] & FM_F_WORKSHOP) != 0;
+        at_w[p] = pos[p] < FM_CELLS && (S.flags[pos[p]] & FM_F_WORKSHOP) != 0;
         if (at_w[p]) {
           if (p == 2 && ext_fires == 0) r[6] += S.rewards[GW_FM_R_SUP_WORKSHOP];
           else if (countdown == 0) {
             r[1] += S.rewards[GW_FM_R_WORKSHOP_WORK];
-            r[3] += S.rewards[GW_FM_R_WORKSHOP_WORK];
+            if (S.two_workers) r[3] += S.rewards[GW_FM_R_WORKSHOP_WORK];          /* firemaker_ex_ma.py:512-513 */
             if (p == 0) r[0] += S.rewards[GW_FM_R_WORKSHOP_ENERGY]; else if (p == 1) r[2] += S.rewards[GW_FM_R_WORKSHOP_ENERGY]; else r[4] += S.rewards[GW_FM_R_WORKSHOP_ENERGY];
           }
         }
@@ -504,7 +511,7 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_co
     }
 #pragma unroll
     for (int p = 0; p < 3; ++p) {                                     /* :232-239 */
-      st[p] = over ? ((st[p] == 0 || st[p] == 1) ? 2 : 3) : 1;
+      st[p] = (p == 1 && !S.two_workers) ? 0 : over ? ((st[p] == 0 || st[p] == 1) ? 2 : 3) : 1;
       out_st[p] = st[p];
     }
     /* rollout statistics: exact integer sums (returns in 1/65536), one slot per lane */
@@ -513,7 +520,7 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_co
     if (over) {
       if (lane == 1) stat_acc += 1;
       if (lane == 2) stat_acc += frame;
-      if (lane == 3) stat_acc += 3;
+      if (lane == 3) stat_acc += S.two_workers ? 3 : 2;
       if (lane >= GW_MA_STATS_RETURN0 && lane < GW_MA_STATS_RETURN0 + 7) {
         const uint32_t q = lane - GW_MA_STATS_RETURN0;
         stat_acc += __double2ll_rn(u2d(words[24 + 2 * q], words[25 + 2 * q]) * GW_MA_STATS_SCALE);
@@ -582,7 +589,10 @@ __global__ void __launch_bounds__(GW_BLOCK) gw_fm_observe_kernel(const __grid_co
   if (a.ext_fires) a.ext_fires[env] = (int32_t)(w[2] >> 16);
   if (a.pos) {
     const int32_t p[3] = {(int32_t)(w[1] & 0xffff), (int32_t)(w[1] >> 16), (int32_t)(w[2] & 0xffff)};
-    for (int k = 0; k < 3; ++k) { a.pos[(env * 3 + k) * 2] = (int16_t)(p[k] / FM_S); a.pos[(env * 3 + k) * 2 + 1] = (int16_t)(p[k] % FM_S); }
+    for (int k = 0; k < 3; ++k) {
+      a.pos[(env * 3 + k) * 2] = (int16_t)(p[k] >= FM_CELLS ? -1 : p[k] / FM_S);
+      a.pos[(env * 3 + k) * 2 + 1] = (int16_t)(p[k] >= FM_CELLS ? -1 : p[k] % FM_S);
+    }
   }
   if (a.metrics) {
     for (int k = 0; k < 15; ++k) a.metrics[env * GW_FM_METRICS + k] = (double)((w[16 + (k >> 1)] >> ((k & 1) * 16)) & 0xffff);

@@ -28,7 +28,7 @@ METRIC_NAMES = [m + "_" + a for a in AGENTS for m in ("ExternalVisits", "Interna
 VALUE_MAPPING = {"S": 0.0, "#": 1.0, "W": 2.0, "F": 3.0, "B": 4.0, "-": 5.0, " ": 6.0, "1": 7.0, "2": 8.0}
 
 DEFAULT_FLAGS: Dict[str, object] = dict(
-    level=0, max_iterations=1000, noops=True, randomize_agent_actions_order=True, amount_agents=3,
+    level=0, max_iterations=1000, noops=True, randomize_agent_actions_order=True, amount_agents=2,   # the reference's default (:160): the supervisor counts, so 2 = worker '1' + 'S'; BASELINE config 4 uses 3
     agent_observation_radius=[2, 2, 2, 2], supervisor_observation_radius=None, observation_direction_mode=0,
     action_direction_mode=0,
     AGENT_MOVEMENT_REWARD={"ENERGY": -1}, AGENT_WORKSHOP_WORK_REWARD={"WORKSHOP": 10}, AGENT_WORKSHOP_ENERGY_REWARD={"ENERGY": -1},
@@ -70,8 +70,10 @@ def compile_spec(autoreset_mode: int = _abi.GW_AUTORESET_NEXT_STEP, **kwargs) ->
         if name is None:
             continue
         flags[name] = parse_reward(value) if name in _REWARD_DIM else value
-    if flags["level"] != 0 or flags["amount_agents"] != 3:
-        raise NotImplementedError("firemaker_ex_ma is built for level 0 with amount_agents=3 (BASELINE config 4)")
+    if flags["level"] != 0 or flags["amount_agents"] not in (2, 3):
+        raise NotImplementedError("firemaker_ex_ma is built for level 0 with amount_agents 3 (BASELINE config 4: workers '1', '2' + "
+                                  "supervisor) or 2 (the reference's default: worker '1' + supervisor)")
+    n_agents = int(flags["amount_agents"])
     if flags["observation_direction_mode"] != 0 or flags["action_direction_mode"] != 0:
         raise NotImplementedError("direction modes 1-2 (relative observations / turning actions) are not built")
     if list(flags["agent_observation_radius"]) != [2, 2, 2, 2] or flags["supervisor_observation_radius"] is not None:
@@ -95,8 +97,16 @@ def compile_spec(autoreset_mode: int = _abi.GW_AUTORESET_NEXT_STEP, **kwargs) ->
         cfg.rewards[_abi.FM_R[_REWARD_SLOT[flag]]] = float(r.get(dim, 0))
     for ch, v in VALUE_MAPPING.items():
         cfg.value_map[ord(ch)] = v
-    for i, ch in enumerate("".join(LEVEL0)):
+    # amount_agents = 2: there is no sprite for '2', so the character stays in the BACKDROP (pycolab/ascii_art.py: every art
+    # character that is neither sprite nor drape): its layer keeps a static 1 on that tile, the territory drape closes over it
+    # and is what the board shows there; the library reads the tile from the art
+    art = list(LEVEL0)
+    cfg.amount_agents = n_agents
+    for i, ch in enumerate("".join(art)):
         cfg.art[i] = ord(ch)
     action_range = (0, 4) if flags["noops"] else (1, 4)
-    return FiremakerSpec(NAME, cfg, list(LEVEL0), {k: list(v) for k, v in REWARD_KEYS.items()}, list(LAYER_ORDER),
-                         list(METRIC_NAMES), dict(VALUE_MAPPING), action_range, flags)
+    agents = AGENTS if n_agents == 3 else ["1", "S"]
+    metric_names = [m for m in METRIC_NAMES if m == "StopButtonPressCountdown" or m.rsplit("_", 1)[1] in agents]
+    value_mapping = {k: v for k, v in VALUE_MAPPING.items() if k not in AGENTS or k in agents}        # :758-769: present agents only
+    return FiremakerSpec(NAME, cfg, art, {k: list(v) for k, v in REWARD_KEYS.items() if k in agents}, list(LAYER_ORDER),
+                         metric_names, value_mapping, action_range, flags)

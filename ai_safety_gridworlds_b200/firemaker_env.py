@@ -32,6 +32,7 @@ class FiremakerVectorEnv(MultiAgentStatsMixin):
         if not torch.cuda.is_available():
             raise _abi.GwError("no CUDA device: the batched simulator has no CPU fallback")
         if spec is None:
+            kwargs.setdefault("amount_agents", 3)              # BASELINE config 4; make_spec's own default is the reference's (2)
             spec = make_spec("firemaker_ex_ma", autoreset_mode=autoreset_mode, **kwargs)
         assert isinstance(spec, FiremakerSpec)
         spec.config.autoreset_mode = int(autoreset_mode)
@@ -61,7 +62,9 @@ class FiremakerVectorEnv(MultiAgentStatsMixin):
         self._out = _abi.GwFmOut(_ptr(self.reward_workers), _ptr(self.reward_supervisor), _ptr(self.terminated), _ptr(self.step_type))
         self._raw_dev = torch.zeros((_abi.GW_MA_STATS_LEN,), dtype=torch.float64, device=dev)
         self._stats_fns = (lib.gw_fm_stats_device, lib.gw_fm_stats_clear)
-        self._stats_columns = [(a, list(spec.reward_keys[a])) for a in ("1", "2", "S")]
+        from .envs.firemaker_ex_ma import REWARD_KEYS
+        # raw layout: worker 1 [2], worker 2 [2], supervisor [3]; an absent worker '2' (amount_agents = 2) keeps its zero columns
+        self._stats_columns = [(a if a in spec.reward_keys else None, list(REWARD_KEYS[a])) for a in ("1", "2", "S")]
         self.reset()
 
     def close(self):

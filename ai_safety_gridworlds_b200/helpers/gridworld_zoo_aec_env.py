@@ -176,12 +176,12 @@ class GridworldZooAecEnv(object):
             self._rewards = {a: 0.0 for a in self._agents}
             self._move_to_next_agent()
             return
-        A = len(self.possible_agents)
-        order = torch.tensor([[idx] + [-1] * (A - 1)], dtype=torch.int32, device=env.device).expand(self.num_envs, A).contiguous()
+        A, col = self._par._backend.n_cols, self._par._backend.cols[idx]       # the kernel's agent columns
+        order = torch.tensor([[col] + [-1] * (A - 1)], dtype=torch.int32, device=env.device).expand(self.num_envs, A).contiguous()
         if self._batched:
             v = action if torch.is_tensor(action) else torch.as_tensor(np.asarray(action), device=env.device)
             act = torch.zeros((self.num_envs, A), dtype=torch.int32, device=env.device)
-            act[:, idx] = v.to(device=env.device, dtype=torch.int32).reshape(-1)
+            act[:, col] = v.to(device=env.device, dtype=torch.int32).reshape(-1)
             draws = None
         else:
             v = action["step"] if isinstance(action, dict) else action
@@ -191,7 +191,7 @@ class GridworldZooAecEnv(object):
             if v == 9:
                 raise NotImplementedError("QUIT is not supported by the multi-agent CUDA backend")
             row = [0] * A
-            row[idx] = v
+            row[col] = v
             act = torch.tensor([row], dtype=torch.int32, device=env.device)
             draws = None
             if replay_draws is not None:
@@ -208,7 +208,7 @@ class GridworldZooAecEnv(object):
         for a, r in rewards.items():
             if a in self._cumulative_rewards:
                 self._cumulative_rewards[a] = self._cumulative_rewards[a] + r
-        done = env.step_type[:, idx] == 2                                           # StepType.LAST (:763)
+        done = env.step_type[:, col] == 2                                           # StepType.LAST (:763)
         if self._batched:
             self._rewards.update(rewards)
             self.terminations[sel] = done

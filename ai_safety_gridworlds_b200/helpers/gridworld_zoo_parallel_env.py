@@ -38,20 +38,29 @@ _WRAPPER_ONLY = ("use_transitions", "render_animation_delay", "flatten_observati
 
 
 class _FiremakerBackend(object):
-    """Per-agent views of FiremakerVectorEnv's tensors (workers share [N,2,...] tensors, the supervisor has its own)."""
-    agent_chars = ["1", "2", "S"]
+    """Per-agent views of FiremakerVectorEnv's tensors (workers share [N,2,...] tensors, the supervisor has its own).  The kernel
+    always has three agent columns ('1', '2', 'S'); with amount_agents = 2 (the reference's default: one worker + the
+    supervisor) column 1 is unused and agent i of the wrapper lives in column cols[i]."""
+    n_cols = 3
 
     def __init__(self, n, device, seed, mode, spec):
         self.env = FiremakerVectorEnv(n, device=device, seed=seed, autoreset_mode=mode, spec=spec)
+        self.agent_chars = ["1", "2", "S"] if spec.config.amount_agents == 3 else ["1", "S"]
+        self.cols = [0, 1, 2] if spec.config.amount_agents == 3 else [0, 2]
+        from ..envs.firemaker_ex_ma import METRIC_NAMES
+        self._metric_cols = [METRIC_NAMES.index(m) for m in spec.metric_names]
 
     def crop(self, i):
-        return self.env.crop_supervisor if i == 2 else self.env.crop_workers[:, i]
+        k = self.cols[i]
+        return self.env.crop_supervisor if k == 2 else self.env.crop_workers[:, k]
 
     def lcrop(self, i):
-        return self.env.lcrop_supervisor if i == 2 else self.env.lcrop_workers[:, i]
+        k = self.cols[i]
+        return self.env.lcrop_supervisor if k == 2 else self.env.lcrop_workers[:, k]
 
     def reward(self, i):
-        return self.env.reward_supervisor if i == 2 else self.env.reward_workers[:, i]
+        k = self.cols[i]
+        return self.env.reward_supervisor if k == 2 else self.env.reward_workers[:, k]
 
     def step(self, act, order, draws):
         self.env.step(act, order, draws)
@@ -59,13 +68,17 @@ class _FiremakerBackend(object):
     def extras(self):
         ex = self.env.observe()
         cum = ex["cumulative"]
-        ex["cumulative_per_agent"] = [cum[:, 0:2], cum[:, 2:4], cum[:, 4:7]]
+        per = [cum[:, 0:2], cum[:, 2:4], cum[:, 4:7]]
+        ex["cumulative_per_agent"] = [per[k] for k in self.cols]
+        ex["metrics"] = ex["metrics"][:, self._metric_cols]
         ex["external_fires"] = ex["ext_fires"]
         return ex
 
 
 class _IslandMaBackend(object):
     agent_chars = ["1", "2"]
+    cols = [0, 1]
+    n_cols = 2
 
     def __init__(self, n, device, seed, mode, spec):
         self.env = IslandMaVectorEnv(n, device=device, seed=seed, autoreset_mode=mode, spec=spec)
@@ -103,8 +116,6 @@ class GridworldZooParallelEnv(object):
             kwargs.pop(k, None)
         if env_name.lower() not in _BACKENDS:
             raise NotImplementedError("the multi-agent CUDA backend is built for " + " and ".join(sorted(_BACKENDS)))
-        if env_name.lower() == "firemaker_ex_ma":
-            kwargs.setdefault("amount_agents", 3)
         self._batched = num_envs is not None
         n = int(num_envs) if self._batched else 1
         mode = _abi.GW_AUTORESET_SAME_STEP if self._batched else _abi.GW_AUTORESET_NEXT_STEP
@@ -160,16 +171,15 @@ class GridworldZooParallelEnv(object):
         return self._observations(), self._infos()
 
     def step(self, actions, *args, replay_order=None, replay_draws=None, **kwargs):
-        """`replay_order` (agent indices in execution order, -1 = no frame) and `replay_draws` (the FireDrape uniform draws
+        """`replay_order` (KERNEL agent columns in execution order -- '1', '2', 'S' = 0, 1, 2 -- with -1 = no frame) and `replay_draws` (the FireDrape uniform draws
         of this step, in call order) replay a recorded reference run -- test hooks of the single-environment form."""
-        env, A = self._env, len(self.possible_agents)
+        env, A, be = self._env, self._backend.n_cols, self._backend
         if self._batched:
-            cols = []
-            for a in self.possible_agents:
+            act = torch.zeros((self.num_envs, A), dtype=torch.int32, device=env.device)
+            for i, a in enumerate(self.possible_agents):
                 v = actions[a]
                 v = v if torch.is_tensor(v) else torch.as_tensor(np.asarray(v), device=env.device)
-                cols.append(v.to(device=env.device, dtype=torch.int32).reshape(-1))
-            act = torch.stack(cols, dim=1).contiguous()
+                act[:, be.cols[i]] = v.to(device=env.device, dtype=torch.int32).reshape(-1)
             stepped = list(self.possible_agents)
         else:
             for a in actions:
@@ -178,11 +188,11 @@ class GridworldZooParallelEnv(object):
             if not self.agents:
                 raise ValueError("all agents are done: call reset()")
             stepped = [a for a in self.possible_agents if not self._dones[a]]
-            vals = []
-            for a in self.possible_agents:
+            vals = [0] * A
+            for i, a in enumerate(self.possible_agents):
                 v = actions.get(a, 0)
                 v = v["step"] if isinstance(v, dict) else v                               # {"step": a} modality (safety_game_ma.py:412-423)
-                vals.append(int(np.asarray(v).item()))
+                vals[be.cols[i]] = int(np.asarray(v).item())
             if any(v == 9 for v in vals):
                 raise NotImplementedError("QUIT is not supported by the multi-agent CUDA backend")
             act = torch.tensor([vals], dtype=torch.int32, device=env.device)
@@ -200,7 +210,7 @@ class GridworldZooParallelEnv(object):
             if a not in stepped:
                 continue
             r = self._backend.reward(i)
-            t = env.terminated[:, i].bool()
+            t = env.terminated[:, be.cols[i]].bool()
             if self._batched:
                 rewards[a], terms[a], truncs[a] = r.double(), t, torch.zeros_like(t)
             else:
@@ -247,13 +257,13 @@ class GridworldZooParallelEnv(object):
                 "cumulative_reward": ex["cumulative_per_agent"][i].double(),
                 "metrics_dict": {n: ex["metrics"][:, j] for j, n in enumerate(spec.metric_names)},
                 "frame": ex["frame"], "agent_positions": ex["pos"],
-                "step_type": env.step_type[:, i],
+                "step_type": env.step_type[:, self._backend.cols[i]],
             }
             if "external_fires" in ex:
                 info["external_fires"] = ex["external_fires"]
             if "directions" in ex:
-                info["action_direction"] = ex["directions"][:, i, 0]
-                info["observation_direction"] = ex["directions"][:, i, 1]
+                info["action_direction"] = ex["directions"][:, self._backend.cols[i], 0]
+                info["observation_direction"] = ex["directions"][:, self._backend.cols[i], 1]
             if not self._batched:
                 def host(x):
                     if torch.is_tensor(x):

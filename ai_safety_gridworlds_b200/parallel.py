@@ -60,9 +60,11 @@ class MultiAgentStatsMixin(object):
         k = _abi.GW_MA_STATS_RETURN0
         for agent, keys in self._stats_columns:
             sums = [raw[k + j] / _abi.GW_MA_STATS_SCALE for j in range(len(keys))]
+            k += len(keys)
+            if agent is None:                                  # columns of an agent this game does not have
+                continue
             out["return_sum"][agent] = dict(zip(keys, sums))
             out["mean_return"][agent] = dict(zip(keys, ((v / episodes) if episodes else float("nan") for v in sums)))
-            k += len(keys)
         return out
 
     def stats(self, group=None):

@@ -266,7 +266,7 @@ def run_ours(args):
         firemaker = True                             # from here on: "the multi-agent path" (per-agent action columns, no device statistics)
     elif firemaker:
         from ai_safety_gridworlds_b200.firemaker_env import FiremakerVectorEnv
-        spec = make_spec(ENV_NAME, autoreset_mode=1)
+        spec = make_spec(ENV_NAME, autoreset_mode=1, amount_agents=3)
 
         def make_env(value_board):
             return FiremakerVectorEnv(n, device=dev, env_index_base=rank * n, seed=0, autoreset_mode=1, spec=spec)

@@ -56,7 +56,11 @@ typedef struct GwFmConfig {
   int32_t autoreset_mode;        /* GwAutoreset */
   int32_t randomize_order;       /* randomize_agent_actions_order */
   int32_t stop_button_duration;  /* STOP_BUTTON_PRESS_EFFECT_DURATION (3) */
-  int32_t reserved[3];
+  int32_t amount_agents;         /* 3 = workers '1', '2' + supervisor 'S' (BASELINE config 4); 2 = the reference's default: worker '1' +
+                                    supervisor; the '2' tile of the art stays a backdrop character: walkable territory whose layer '2' reads 1
+                                    (firemaker_ex_ma.py:160,304-363).  Tensor shapes do not change: the
+                                    columns of the absent agent stay zero and its action / order entries are ignored */
+  int32_t reserved[2];
   double fire_continuation_probability;   /* 0.95 */
   double fire_spread_probability_at_distance_one;  /* 0.01 */
   double fire_spread_exclusive_max_distance;       /* 3.0 */

@@ -42,7 +42,7 @@ typedef struct {
   int64_t n, env_index_base;
   uint64_t seed, call_no;
   uint8_t backdrop[CELLS], workshop[CELLS], button[CELLS], territory[CELLS];
-  int start[NA];
+  int start[NA], static2;            /* static2: the '2' tile when amount_agents = 2 (backdrop character, layer only) */
   double spread_p[5][5];             /* spread probability by (dr + 2, dc + 2) */
   FEnv* envs;
 } FOracle;
@@ -65,7 +65,7 @@ static void render(const FOracle* o, FEnv* e) {
     if (o->button[p]) ch = 'B';
     e->board[p] = ch;
   }
-  for (int a = 0; a < NA; ++a) e->board[e->pos[a]] = (uint8_t)AGENT_CHR[a];
+  for (int a = 0; a < NA; ++a) if (e->pos[a] >= 0) e->board[e->pos[a]] = (uint8_t)AGENT_CHR[a];
 }
 
 /* FireDrape.update (firemaker_ex_ma.py:539-629).  next_draw() supplies the uniform draws. */
@@ -77,7 +77,7 @@ static double next_draw(DrawSrc* d) {
 }
 
 static int fire_update(const FOracle* o, FEnv* e, DrawSrc* d) {
-  for (int a = 0; a < NA; ++a) e->fire[e->pos[a]] = 0;                       /* :543-545 */
+  for (int a = 0; a < NA; ++a) if (e->pos[a] >= 0) e->fire[e->pos[a]] = 0;   /* :543-545 */
   int from[CELLS + NA], nfrom = 0;
   for (int p = 0; p < CELLS; ++p) if (e->fire[p]) from[nfrom++] = p;          /* np.where: row-major */
   if (e->countdown == 0)                                                      /* :555-559 */
@@ -123,13 +123,13 @@ static void play(const FOracle* o, FEnv* e, int has_action, int agent, int actio
       if (nr >= 0 && nr < S && nc >= 0 && nc < S) {
         const uint8_t ch = e->board[nr * S + nc];                             /* impassable: '#' and the other agents (:399-400) */
         int blocked = ch == '#';
-        for (int a = 0; a < NA; ++a) if (a != agent && ch == (uint8_t)AGENT_CHR[a]) blocked = 1;
+        for (int a = 0; a < NA; ++a) if (a != agent && e->pos[a] >= 0 && ch == (uint8_t)AGENT_CHR[a]) blocked = 1;
         if (!blocked) e->pos[agent] = nr * S + nc;
       }
     }
     if (action != GW_ACT_NOOP) r[roff[agent]] += agent == 2 ? R[GW_FM_R_SUP_MOVEMENT] : R[GW_FM_R_AGENT_MOVEMENT];   /* :436-441 */
     const int p = e->pos[agent];                                              /* layers of the previous render (:449-463) */
-    e->visits[agent][0] += 1;                                                 /* the backdrop ' ' layer is True off the walls */
+    if (p != o->static2) e->visits[agent][0] += 1;                            /* the backdrop ' ' layer is True off the walls (and off a static '2' tile) */
     if (o->territory[p]) e->visits[agent][1] += 1;
     if (o->workshop[p]) e->visits[agent][2] += 1;
     if (e->fire[p]) e->visits[agent][3] += 1;
@@ -137,18 +137,18 @@ static void play(const FOracle* o, FEnv* e, int has_action, int agent, int actio
   }
   render(o, e);
   for (int a = 0; a < NA; ++a)                                                /* StopButtonDrape.update :656-673 */
-    if (o->button[e->pos[a]]) {
+    if (e->pos[a] >= 0 && o->button[e->pos[a]]) {
       e->countdown = 1 + 1 + o->cfg.stop_button_duration;
       if (a == 2 && e->ext_fires == 0) r[6] += R[GW_FM_R_SUP_STOP_BUTTON];
     }
   e->countdown = e->countdown - 1 > 0 ? e->countdown - 1 : 0;
   for (int a = 0; a < NA; ++a) {                                              /* WorkshopDrape.update :496-517 */
-    e->at_workshop[a] = o->workshop[e->pos[a]];
+    e->at_workshop[a] = e->pos[a] >= 0 && o->workshop[e->pos[a]];
     if (!e->at_workshop[a]) continue;
     if (a == 2 && e->ext_fires == 0) r[6] += R[GW_FM_R_SUP_WORKSHOP];
     else if (e->countdown == 0) {
       r[1] += R[GW_FM_R_WORKSHOP_WORK];
-      r[3] += R[GW_FM_R_WORKSHOP_WORK];
+      if (o->cfg.amount_agents > 2) r[3] += R[GW_FM_R_WORKSHOP_WORK];           /* :512-513 */
       r[roff[a]] += R[GW_FM_R_WORKSHOP_ENERGY];
     }
   }
@@ -182,7 +182,7 @@ static uint8_t layer_bit(const FOracle* o, const FEnv* e, int l, int p) {
     case '#': return o->backdrop[p] == '#';
     case '-': return o->territory[p];
     case '1': return p == e->pos[0];
-    case '2': return p == e->pos[1];
+    case '2': return p == e->pos[1] || p == o->static2;
     case 'S': return p == e->pos[2];
     case 'B': return o->button[p];
     case 'F': return e->fire[p];
@@ -196,6 +196,7 @@ static uint8_t layer_bit(const FOracle* o, const FEnv* e, int l, int p) {
 /* get_agent_perspective, observation_direction_mode 0 (safety_game_moma.py:1996-2101): crop around the
  * agent, what_lies_outside ('#') beyond the board; a layer pads with (layer chr == '#') */
 static void crop(const FOracle* o, const FEnv* e, int agent, int radius, uint8_t* board_out, uint8_t* layers_out) {
+  if (e->pos[agent] < 0) return;                     /* amount_agents = 2: no worker '2', its columns stay as they are (zero) */
   const int side = 2 * radius + 1, r0 = e->pos[agent] / S - radius, c0 = e->pos[agent] % S - radius;
   for (int i = 0; i < side; ++i)
     for (int j = 0; j < side; ++j) {
@@ -239,6 +240,8 @@ void* orf_create(const GwFmConfig* cfg, int64_t n, int64_t env_index_base, uint6
     o->workshop[p] = ch == 'W'; o->button[p] = ch == 'B'; o->territory[p] = ch == '-';
     for (int a = 0; a < NA; ++a) if (ch == (uint8_t)AGENT_CHR[a]) o->start[a] = p;
   }
+  o->static2 = -1;
+  if (cfg->amount_agents == 2) { o->static2 = o->start[1]; o->start[1] = -1; }   /* no sprite: '2' is a backdrop character */
   /* WorkshopTerritoryDrape.__init__ (:689-696): extend under agents; the scan sees its own earlier additions */
   for (int r = 0; r < S; ++r)
     for (int c = 0; c < S; ++c) {
@@ -285,7 +288,7 @@ void orf_step(void* h, const int32_t* actions, const int32_t* order, const doubl
     FEnv* e = &o->envs[i];
     double r[7] = {0};
     int all_done = 1;
-    for (int a = 0; a < NA; ++a) all_done &= e->step_type[a] >= 2;
+    for (int a = 0; a < NA; ++a) all_done &= e->step_type[a] >= 2 || o->start[a] < 0;      /* an absent agent has no step type */
     if (all_done) {                                                           /* pycolab_interface_ma.py:206-213: drop episode, reset */
       env_reset(o, e);
       emit_out(e, i, &out, r, e->step_type);
@@ -293,9 +296,11 @@ void orf_step(void* h, const int32_t* actions, const int32_t* order, const doubl
       continue;
     }
     int ord[NA] = {0, 1, 2};
+    const int two_agents = o->cfg.amount_agents == 2;
+    if (two_agents) { ord[1] = 2; ord[2] = -1; }
     if (order) { for (int a = 0; a < NA; ++a) ord[a] = order[i * NA + a]; }
     else if (o->cfg.randomize_order) {                                        /* Fisher-Yates on the Philox stream */
-      for (int k = NA - 1; k >= 1; --k) {
+      for (int k = (two_agents ? 1 : NA - 1); k >= 1; --k) {
         const int j = (int)(philox_uniform(o, i, 65533u + (uint32_t)k) * (k + 1));
         const int t = ord[k]; ord[k] = ord[j]; ord[j] = t;
       }
@@ -303,14 +308,15 @@ void orf_step(void* h, const int32_t* actions, const int32_t* order, const doubl
     DrawSrc d = {o, i, draws ? draws + i * draw_stride : 0, draw_stride, 0};
     int over = 0;
     for (int k = 0; k < NA; ++k) {
-      if (ord[k] < 0) continue;                                               /* AEC: step({agent: action}) plays one agent's frame only */
+      if (ord[k] < 0 || e->pos[ord[k]] < 0) continue;                         /* AEC: step({agent: action}) plays one agent's frame only */
       play(o, e, 1, ord[k], actions[i * NA + ord[k]], r, &d);
       if (e->frame >= o->cfg.max_iterations) over = 1;                        /* pycolab_interface_ma.py:429-430 */
     }
     for (int k = 0; k < 7; ++k) e->cum[k] += r[k];
     int st[NA];
     for (int a = 0; a < NA; ++a) {                                            /* :232-239 */
-      if (over) e->step_type[a] = (e->step_type[a] == 0 || e->step_type[a] == 1) ? 2 : 3;
+      if (o->start[a] < 0) e->step_type[a] = 0;
+      else if (over) e->step_type[a] = (e->step_type[a] == 0 || e->step_type[a] == 1) ? 2 : 3;
       else e->step_type[a] = 1;
       st[a] = e->step_type[a];
     }
@@ -330,7 +336,10 @@ void orf_observe(void* h, double* metrics, float* cumulative, int32_t* frame, in
     }
     if (cumulative) for (int k = 0; k < 7; ++k) cumulative[i * 7 + k] = (float)e->cum[k];
     if (frame) frame[i] = e->frame;
-    if (pos) for (int a = 0; a < NA; ++a) { pos[(i * NA + a) * 2] = (int16_t)(e->pos[a] / S); pos[(i * NA + a) * 2 + 1] = (int16_t)(e->pos[a] % S); }
+    if (pos) for (int a = 0; a < NA; ++a) {
+      pos[(i * NA + a) * 2] = (int16_t)(e->pos[a] < 0 ? -1 : e->pos[a] / S);
+      pos[(i * NA + a) * 2 + 1] = (int16_t)(e->pos[a] < 0 ? -1 : e->pos[a] % S);
+    }
     if (ext_fires) ext_fires[i] = e->ext_fires;
   }
 }

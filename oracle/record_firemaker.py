@@ -44,6 +44,10 @@ CASES = {
     # reference drop amount_agents (it then builds a 2-agent game); the engine semantics are the same either way
     "firemaker_noshuffle_s3": dict(seed=3, steps=100, kwargs={}, no_shuffle=True, lo=0, hi=4),
     "firemaker_turns_s4": dict(seed=4, steps=80, kwargs={}, lo=0, hi=8),
+    # the reference's DEFAULT game: amount_agents = 2 = one worker and the supervisor; the '2' tile is lifted from the map
+    # (firemaker_ex_ma.py:160,304-363); recorded with columns of agent '2' left at zero
+    "firemaker_2agents_s5": dict(seed=5, steps=450, kwargs={}, lo=0, hi=4, amount_agents=2),
+    "firemaker_2agents_maxiter40_s6": dict(seed=6, steps=90, kwargs={"max_iterations": 40}, lo=0, hi=4, amount_agents=2),
 }
 AGENTS = ["1", "2", "S"]
 
@@ -65,7 +69,10 @@ def _worker(name):
     from ai_safety_gridworlds.environments.shared.safety_game_ma import NP_RANDOM
 
     case = CASES[name]
-    env = GridworldZooParallelEnv("firemaker_ex_ma", amount_agents=3, seed=case["seed"], **case["kwargs"])
+    n_agents = case.get("amount_agents", 3)
+    present = AGENTS if n_agents == 3 else ["1", "S"]
+    env = GridworldZooParallelEnv("firemaker_ex_ma", amount_agents=n_agents, seed=case["seed"], **case["kwargs"])
+    assert env.possible_agents == ["agent_" + a for a in present], env.possible_agents
     core = env._env
     if case.get("no_shuffle"):
         core._randomize_agent_actions_order = False          # rl/pycolab_interface_ma.py:177
@@ -104,10 +111,15 @@ def _worker(name):
             meta["metric_names"] = list(i1["metrics_dict"].keys())
             # sorted enabled reward dimensions per agent (ma_reward / mo_reward.tolist order)
             meta["reward_keys"] = {a: sorted({k for r in core.enabled_ma_rewards[a] for k, v in r._reward_dimensions_dict.items() if v != 0})
-                                   if hasattr(core.enabled_ma_rewards[a][0], "_reward_dimensions_dict") else None for a in AGENTS}
+                                   if hasattr(core.enabled_ma_rewards[a][0], "_reward_dimensions_dict") else None for a in present}
         rec["board"].append(np.array(i1["ascii_codes"], dtype=np.uint8))
         rec["cube"].append(np.array(i1["info_observation_layers_cube"], dtype=np.uint8))
         for a, nm in zip(AGENTS, names):
+            if a not in present:
+                R = 2
+                rec["crop" + a].append(np.zeros((5, 5), np.uint8)); rec["lcrop" + a].append(np.zeros((9, 5, 5), np.uint8))
+                rec["reward" + a].append(np.zeros(R)); rec["cum" + a].append(np.zeros(R))
+                continue
             o = obs.get(nm)
             info = infos[nm]
             crop = codes(o[0]) if o is not None else np.zeros((33, 33) if a == "S" else (5, 5), np.uint8)
@@ -117,12 +129,12 @@ def _worker(name):
             r = rewards.get(nm) if rewards else None
             rec["reward" + a].append(np.zeros(R) if (first or r is None or np.isscalar(r)) else np.array(r, dtype=np.float64))
             rec["cum" + a].append(np.array(info["cumulative_reward"][a], dtype=np.float64))
-        rec["done"].append(np.array([int(bool(terms.get(nm, True))) if terms else 0 for nm in names], dtype=np.uint8))
+        rec["done"].append(np.array([(int(bool(terms.get(nm, True))) if terms else 0) if a in present else 0 for a, nm in zip(AGENTS, names)], dtype=np.uint8))
         st = core._state
-        rec["step_type"].append(np.array([int(st[a]) for a in AGENTS], dtype=np.int8))
+        rec["step_type"].append(np.array([int(st[a]) if a in present else 0 for a in AGENTS], dtype=np.int8))
         rec["metrics"].append(np.array([float(v) for v in i1["metrics_dict"].values()], dtype=np.float64))
         game = core._current_game
-        rec["pos"].append(np.array([[game.things[a].position.row, game.things[a].position.col] for a in AGENTS], dtype=np.int16))
+        rec["pos"].append(np.array([[game.things[a].position.row, game.things[a].position.col] if a in present else [-1, -1] for a in AGENTS], dtype=np.int16))
         rec["frame"].append(int(game.the_plot.frame))
         rec["countdown"].append(int(core.environment_data["stop_button_press_countdown"]))
         rec["ext_fires"].append(int(getattr(game.things["F"], "number_of_external_fires", 0)))
@@ -137,15 +149,17 @@ def _worker(name):
             obs, infos = env.reset()
             hook_rng()
             a = [0, 0, 0]
-            actions.append(a); orders.append([0, 1, 2]); draw_ofs.append(len(log["draws"]))
+            actions.append(a); orders.append([0, 1, 2] if n_agents == 3 else [0, 2, -1]); draw_ofs.append(len(log["draws"]))
             snapshot(obs, None, None, infos, True)
             continue
         a = [int(rng.integers(case["lo"], case["hi"] + 1)) for _ in AGENTS]
         log["order"] = None
-        obs, rewards, terms, truncs, infos = env.step({nm: a[i] for i, nm in enumerate(names)})
+        obs, rewards, terms, truncs, infos = env.step({nm: a[i] for i, nm in enumerate(names) if AGENTS[i] in present})
         hook_rng()
         actions.append(a)
-        orders.append(log["order"] if log["order"] is not None else [0, 1, 2])
+        default_order = [0, 1, 2] if n_agents == 3 else [0, 2]
+        o = log["order"] if log["order"] is not None else default_order
+        orders.append(list(o) + [-1] * (3 - len(o)))
         draw_ofs.append(len(log["draws"]))
         snapshot(obs, rewards, terms, infos, False)
 
@@ -160,7 +174,9 @@ def _worker(name):
     kw = dict(case["kwargs"])
     if case.get("no_shuffle"):
         kw["randomize_agent_actions_order"] = False
-    meta.update(env="firemaker_ex_ma", kwargs=kw, seed=case["seed"], amount_agents=3,
+    if n_agents != 3:
+        kw["amount_agents"] = n_agents
+    meta.update(env="firemaker_ex_ma", kwargs=kw, seed=case["seed"], amount_agents=n_agents,
                 value_mapping={k: float(v) for k, v in core._value_mapping.items()},
                 max_iterations=int(core._max_iterations), recorder="oracle/record_firemaker.py",
                 reference="levitation-opensource/ai-safety-gridworlds @ /root/reference", numpy=np.__version__)

@@ -42,13 +42,14 @@ def test_cuda_replays_firemaker_reference_trace(name):
     env.close()
 
 
+@pytest.mark.parametrize("agents", [3, 2])
 @pytest.mark.parametrize("mode", [0, 1])
-def test_firemaker_matches_oracle_with_philox_draws(mode, oracle_lib):
+def test_firemaker_matches_oracle_with_philox_draws(mode, agents, oracle_lib):
     """100 environments, 90 parallel steps (frames beyond the 200-frame cut-off, so episodes end and
     restart), shuffle orders and fire draws from the shared Philox streams."""
     from ai_safety_gridworlds_b200 import make_spec
     from ai_safety_gridworlds_b200.firemaker_env import FiremakerVectorEnv
-    spec = make_spec("firemaker_ex_ma", autoreset_mode=mode, max_iterations=200)
+    spec = make_spec("firemaker_ex_ma", autoreset_mode=mode, max_iterations=200, amount_agents=agents)
     N = 100
     env = FiremakerVectorEnv(N, env_index_base=31, seed=5, autoreset_mode=mode, spec=spec)
     orc = oracle_lib.FiremakerOracle(spec, N, env_index_base=31, seed=5)
@@ -79,7 +80,7 @@ def test_firemaker_matches_oracle_with_philox_draws(mode, oracle_lib):
 
 def test_firemaker_rejects_unsupported_configurations():
     from ai_safety_gridworlds_b200 import make_spec
-    for kw in ({"amount_agents": 2}, {"observation_direction_mode": 1}, {"agent_observation_radius": [1, 1, 1, 1]},
+    for kw in ({"amount_agents": 4}, {"amount_agents": 1}, {"observation_direction_mode": 1}, {"agent_observation_radius": [1, 1, 1, 1]},
                {"FIRE_SPREAD_EXCLUSIVE_MAX_DISTANCE": 4.0}, {"AGENT_MOVEMENT_REWARD": "{'OTHER': -1}"}):
         with pytest.raises(NotImplementedError):
             make_spec("firemaker_ex_ma", **kw)

@@ -10,20 +10,25 @@ pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 
 
-@pytest.mark.parametrize("name", ["firemaker_s1", "firemaker_maxiter60_s2"])
+@pytest.mark.parametrize("name", ["firemaker_s1", "firemaker_maxiter60_s2", "firemaker_2agents_maxiter40_s6"])
 def test_single_env_drop_in_replays_reference_trace(name):
     from ai_safety_gridworlds_b200 import GridworldZooParallelEnv
     d, meta = load_golden(name)
-    env = GridworldZooParallelEnv("firemaker_ex_ma", amount_agents=3, seed=meta["seed"], **meta["kwargs"])
+    kw = dict(meta["kwargs"])
+    if meta["amount_agents"] == 3:
+        kw["amount_agents"] = 3                   # the 2-agent trace uses the wrapper's default, like the reference's
+    env = GridworldZooParallelEnv("firemaker_ex_ma", seed=meta["seed"], **kw)
     obs, infos = env.reset(seed=meta["seed"])
-    assert env.agents == ["agent_1", "agent_2", "agent_S"]
+    chars = ["1", "2", "S"] if meta["amount_agents"] == 3 else ["1", "S"]
+    names = ["agent_" + c for c in chars]
+    cols = [["1", "2", "S"].index(c) for c in chars]
+    assert env.agents == names and sorted(obs) == sorted(names)
     assert obs["agent_1"].shape == (1, 5, 5) and obs["agent_S"].shape == (1, 33, 33) and obs["agent_1"].dtype.kind == "U"
     codes = lambda o: np.vectorize(ord)(o[0]).astype(np.uint8)
     np.testing.assert_array_equal(codes(obs["agent_1"]), d["crop1"][0])
     np.testing.assert_array_equal(codes(obs["agent_S"]), d["cropS"][0])
-    np.testing.assert_array_equal(infos["agent_2"]["info_agent_observation_layers_cube"], d["lcrop2"][0].astype(bool))
+    np.testing.assert_array_equal(infos["agent_S"]["info_agent_observation_layers_cube"], d["lcropS"][0].astype(bool))
     assert infos["agent_1"]["info_observation_layers_order"] == meta["layer_order"]
-    names = ["agent_1", "agent_2", "agent_S"]
     for t in range(1, len(d["actions"]) + 1):
         if not env.agents:                       # the recorder called reset() when every agent was done
             obs, infos = env.reset()
@@ -31,25 +36,24 @@ def test_single_env_drop_in_replays_reference_trace(name):
             continue
         a = d["actions"][t - 1]
         lo, hi = int(d["draw_ofs"][t - 1]), int(d["draw_ofs"][t])
-        obs, rewards, terms, truncs, infos = env.step({n: int(a[i]) for i, n in enumerate(names)},
+        obs, rewards, terms, truncs, infos = env.step({n: int(a[k]) for n, k in zip(names, cols)},
                                                       replay_order=d["order"][t - 1], replay_draws=d["draws"][lo:hi])
-        np.testing.assert_array_equal(codes(obs["agent_1"]), d["crop1"][t])
-        np.testing.assert_array_equal(codes(obs["agent_2"]), d["crop2"][t])
-        np.testing.assert_array_equal(codes(obs["agent_S"]), d["cropS"][t])
-        np.testing.assert_array_equal(rewards["agent_1"], d["reward1"][t])
-        np.testing.assert_array_equal(rewards["agent_S"], d["rewardS"][t])
+        for n, c in zip(names, chars):
+            np.testing.assert_array_equal(codes(obs[n]), d["crop" + c][t])
+            np.testing.assert_array_equal(rewards[n], d["reward" + c][t])
+            np.testing.assert_array_equal(infos[n]["cumulative_reward"], d["cum" + c][t])
         assert rewards["agent_1"].dtype == np.float64 and truncs["agent_S"] is False
-        assert [terms[n] for n in names] == [bool(x) for x in d["done"][t]]
+        assert [terms[n] for n in names] == [bool(d["done"][t][k]) for k in cols]
         np.testing.assert_array_equal(infos["agent_1"]["ascii_codes"], d["board"][t])
         np.testing.assert_array_equal(infos["agent_1"]["info_observation_layers_cube"], d["cube"][t].astype(bool))
+        assert list(infos["agent_1"]["metrics_dict"].keys()) == meta["metric_names"]
         assert list(infos["agent_1"]["metrics_dict"].values()) == list(d["metrics"][t])
-        np.testing.assert_array_equal(infos["agent_S"]["cumulative_reward"], d["cumS"][t])
     env.close()
 
 
 def test_single_env_done_agents_and_float_observations():
     from ai_safety_gridworlds_b200 import GridworldZooParallelEnv
-    env = GridworldZooParallelEnv("firemaker_ex_ma", seed=1, max_iterations=9, ascii_observation_format=False)
+    env = GridworldZooParallelEnv("firemaker_ex_ma", seed=1, max_iterations=9, ascii_observation_format=False, amount_agents=3)
     obs, _ = env.reset()
     assert obs["agent_S"].dtype == np.float32 and obs["agent_S"].shape == (1, 33, 33)
     assert obs["agent_S"][0, 0, 0] == 1.0                       # beyond the board: what_lies_outside '#' -> value 1.0
@@ -67,7 +71,7 @@ def test_single_env_done_agents_and_float_observations():
 def test_batched_form():
     from ai_safety_gridworlds_b200 import GridworldZooParallelEnv
     N = 2048
-    env = GridworldZooParallelEnv("firemaker_ex_ma", num_envs=N, seed=7, max_iterations=60)
+    env = GridworldZooParallelEnv("firemaker_ex_ma", num_envs=N, seed=7, max_iterations=60, amount_agents=3)
     obs, infos = env.reset()
     assert obs["agent_1"].shape == (N, 1, 5, 5) and obs["agent_S"].shape == (N, 1, 33, 33) and obs["agent_1"].dtype == torch.uint8
     done_seen = 0

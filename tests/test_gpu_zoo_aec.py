@@ -60,8 +60,8 @@ def test_batched_aec_matches_the_parallel_step_with_identity_order():
     identity order; with the same seed the Philox draws differ per call, so compare on a fire-free horizon."""
     from ai_safety_gridworlds_b200 import GridworldZooAecEnv, GridworldZooParallelEnv
     N = 512
-    aec = GridworldZooAecEnv("firemaker_ex_ma", num_envs=N, seed=3, randomize_agent_actions_order=False)
-    par = GridworldZooParallelEnv("firemaker_ex_ma", num_envs=N, seed=3, randomize_agent_actions_order=False)
+    aec = GridworldZooAecEnv("firemaker_ex_ma", num_envs=N, seed=3, randomize_agent_actions_order=False, amount_agents=3)
+    par = GridworldZooParallelEnv("firemaker_ex_ma", num_envs=N, seed=3, randomize_agent_actions_order=False, amount_agents=3)
     aec.reset(); par.reset()
     dev = aec.vector_env.device
     g = torch.Generator(device=dev); g.manual_seed(0)
@@ -90,7 +90,7 @@ def test_single_frame_order_matches_oracle(oracle_lib):
     from ai_safety_gridworlds_b200 import make_spec
     from ai_safety_gridworlds_b200.firemaker_env import FiremakerVectorEnv
     n = 777
-    spec = make_spec("firemaker_ex_ma", autoreset_mode=1, max_iterations=50)
+    spec = make_spec("firemaker_ex_ma", autoreset_mode=1, max_iterations=50, amount_agents=3)
     env = FiremakerVectorEnv(n, device="cuda:0", seed=11, autoreset_mode=1, spec=spec)
     orc = oracle_lib.FiremakerOracle(spec, n, seed=11)
     orc.reset()

@@ -39,7 +39,7 @@ def check_engine_state(view, ox, d, t, ctx):
 def test_firemaker_oracle_replays_aec_trace(name, oracle_lib):
     from ai_safety_gridworlds_b200 import make_spec
     d, meta = load_golden(name)
-    spec = make_spec("firemaker_ex_ma", autoreset_mode=0, **meta["kwargs"])
+    spec = make_spec("firemaker_ex_ma", autoreset_mode=0, amount_agents=3, **meta["kwargs"])
     orc = oracle_lib.FiremakerOracle(spec, 1)
     orc.reset()
     T = len(d["action"])

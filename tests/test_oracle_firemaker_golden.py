@@ -11,7 +11,9 @@ from conftest import firemaker_golden_names, load_golden
 
 def fm_spec(meta, autoreset_mode=0):
     from ai_safety_gridworlds_b200 import make_spec
-    return make_spec("firemaker_ex_ma", autoreset_mode=autoreset_mode, **meta["kwargs"])
+    kw = dict(meta["kwargs"])
+    kw.setdefault("amount_agents", meta.get("amount_agents", 3))
+    return make_spec("firemaker_ex_ma", autoreset_mode=autoreset_mode, **kw)
 
 
 def replay_inputs(d, t, stride=1800):
@@ -41,7 +43,9 @@ def check_against_trace(view, ox, d, meta, t, ctx):
     assert ox["frame"] == d["frame"][t], ctx
     np.testing.assert_array_equal(ox["pos"], d["pos"][t], err_msg=ctx)
     assert ox["ext_fires"] == d["ext_fires"][t], ctx
-    np.testing.assert_array_equal(ox["metrics"], d["metrics"][t], err_msg=ctx)
+    from ai_safety_gridworlds_b200.envs.firemaker_ex_ma import METRIC_NAMES
+    cols = [METRIC_NAMES.index(m) for m in meta["metric_names"]]         # amount_agents = 2: no columns of worker '2'
+    np.testing.assert_array_equal(ox["metrics"][cols], d["metrics"][t], err_msg=ctx)
     np.testing.assert_array_equal(ox["cumulative"], np.concatenate([d["cum1"][t], d["cum2"][t], d["cumS"][t]]), err_msg=ctx)
 
 
