@@ -23,6 +23,7 @@ GW_ENV_BOAT_RACE_EX = 2
 GW_ENV_SAFE_INTERRUPTIBILITY, GW_ENV_SIDE_EFFECTS_SOKOBAN, GW_ENV_ABSENT_SUPERVISOR = 3, 4, 5
 GW_ENV_CONVEYOR_BELT, GW_ENV_WHISKY_GOLD = 6, 7
 GW_ENV_BOAT_RACE, GW_ENV_ISLAND_NAVIGATION = 8, 9
+GW_ENV_DISTRIBUTIONAL_SHIFT, GW_ENV_ROCKS_DIAMONDS, GW_ENV_TOMATO_WATERING, GW_ENV_TOMATO_CRMDP = 10, 11, 12, 13
 GW_ENV_ISLAND_NAVIGATION_EX_MA = 16       # include/gwsim_ima.h
 GW_MAX_TYPES = 8
 
@@ -56,8 +57,8 @@ BOAT_E = dict(MOVEMENT=0, CLOCKWISE=1, FINAL=2, ITERATIONS=3, REPETITION=4, HUMA
 
 # classic-suite slots
 CLS_I = dict(MOVEMENT_REWARD=0, GOAL_REWARD=1, AUX_REWARD=2, WALL_REWARD=3, CORNER_REWARD=4, VARIANT=5)
-CLS_F = dict(PROBABILITY=0)
-CLS_E = dict(RETURN=0, HIDDEN=1, PERFORMANCE=2)
+CLS_F = dict(PROBABILITY=0, REWARD_FACTOR=1)
+CLS_E = dict(RETURN=0, HIDDEN=1, PERFORMANCE=2, RETURN_UNITS=3, HIDDEN_UNITS=4)
 CACT = dict(NOOP=0, UP=1, DOWN=2, LEFT=3, RIGHT=4, QUIT=9)
 
 
@@ -181,6 +182,8 @@ SYMBOLS = [
     ("gw_create_mixed", C.c_int, [C.POINTER(GwConfig), C.c_int32, C.POINTER(C.c_int64), C.c_int, C.c_int64, C.c_uint64,
                                   C.POINTER(C.c_void_p)]),
     ("gw_set_coin_override", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("gw_set_dried_override", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("gw_classic_pitch", C.c_int32, [C.c_void_p]),
     ("gw_destroy", None, [C.c_void_p]),
     ("gw_state_bytes", C.c_int64, [C.POINTER(GwConfig), C.c_int64]),
     ("gw_state_words", C.c_int32, [C.POINTER(GwConfig)]),

@@ -1,8 +1,9 @@
 """ClassicVectorEnv: a MIXED batch of original-DeepMind-suite environments on one B200.
 
 The batched counterpart of `safety_game.SafetyEnvironment.step` (environments/shared/safety_game.py:314)
-for safe_interruptibility, side_effects_sokoban (level 0), absent_supervisor, conveyor_belt and
-whisky_gold: environments [sum(counts[:t]), sum(counts[:t+1])) are of type specs[t], all stepped by
+for safe_interruptibility, side_effects_sokoban (level 0), absent_supervisor, conveyor_belt,
+whisky_gold, boat_race, island_navigation, distributional_shift, rocks_diamonds, tomato_watering and
+tomato_crmdp: environments [sum(counts[:t]), sum(counts[:t+1])) are of type specs[t], all stepped by
 ONE launch of the fused kernel in csrc/gwsim_classic.cuh (BASELINE config 5).  Actions use the
 original numbering (NOOP 0, UP 1, DOWN 2, LEFT 3, RIGHT 4, QUIT 9).  No CPU fallback.
 """
@@ -16,12 +17,21 @@ from .envs import make_spec
 from .envs.common import EnvSpec
 from .vector_env import _ptr
 
-SIDE = 8          # GW_CLASSIC_SIDE: boards are emitted padded to 8 x 8
+SIDE = 8          # GW_CLASSIC_SIDE: one 64-entry board row per environment, [8, 8] with a pitch of 8 (maps wider than 8: dense)
+
+
+def crop_board(rows, spec):
+    """[..., 8, 8] board rows of environments of type `spec` -> their [..., H, W] boards (a view)."""
+    H, W = spec.height, spec.width
+    if W > SIDE:                                   # the 7 x 9 maps are laid out densely in the 64 entries
+        return rows.reshape(rows.shape[:-2] + (SIDE * SIDE,))[..., :H * W].reshape(rows.shape[:-2] + (H, W))
+    return rows[..., :H, :W]
 
 
 class ClassicVectorEnv(object):
     """Tensors (on `device`, reused between calls):
-      board        uint8  [N, 8, 8]  rendered board, ASCII codes, zero outside each type's H x W
+      board        uint8  [N, 8, 8]  rendered board, ASCII codes, zero outside each type's H x W (crop_board / boards_of
+                                     give the H x W view; maps wider than 8 fill their 64 entries densely)
       value_board  float32[N, 8, 8]  value-mapped board (the Gym observation of the original suite)
       reward       float32[N, 2]     (reward, hidden-reward delta of this step)
       terminated / step_type uint8 [N]; reason / actual int8 [N]
@@ -91,6 +101,19 @@ class ClassicVectorEnv(object):
             raise ValueError("coins must be a uint8 CUDA tensor of shape [num_envs]")
         self._coins = coins
         _abi.check(self._lib.gw_set_coin_override(self._h, _ptr(coins)))
+
+    def set_dried_override(self, dried):
+        """dried: uint16 CUDA tensor [N], the tomato games' per-frame draws of the NEXT calls as a bit mask over each
+        environment's tomato cells in row-major order (0xFFFF = draw from Philox), or None."""
+        if dried is not None and (dried.dtype != torch.uint16 or not dried.is_cuda or dried.shape != (self.num_envs,)):
+            raise ValueError("dried must be a uint16 CUDA tensor of shape [num_envs]")
+        self._dried = dried
+        _abi.check(self._lib.gw_set_dried_override(self._h, _ptr(dried)))
+
+    def boards_of(self, t, which="board"):
+        """The [counts[t], H, W] boards of type t (a view of `board` or `value_board`)."""
+        lo, hi = int(self.type_start[t]), int(self.type_start[t + 1])
+        return crop_board(getattr(self, which)[lo:hi], self.specs[t])
 
     def reset(self, mask=None):
         m = None

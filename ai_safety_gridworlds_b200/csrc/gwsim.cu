@@ -145,6 +145,7 @@ struct GwEngine {
   ClsType* d_types;
   uint64_t seed, call_no;
   const uint8_t* coin_override;
+  const uint16_t* dried_override;
   int step_impl;                      /* 0 = persistent TMA kernel (product), 1 = direct stores (GWSIM_STEP_IMPL=direct) */
 };
 
@@ -1239,7 +1240,7 @@ __global__ void __launch_bounds__(GW_BLOCK) gw_random_actions_kernel(uint64_t se
 static int kind_of(const GwConfig* cfg) {
   if (cfg->env_type == GW_ENV_ISLAND_NAVIGATION_EX) return cfg->iparams[GW_ISL_I_PROPORTIONAL] ? 1 : 0;
   if (cfg->env_type == GW_ENV_BOAT_RACE_EX) return cfg->max_iterations <= 254 ? 2 : 3;
-  if (cfg->env_type >= GW_ENV_SAFE_INTERRUPTIBILITY && cfg->env_type <= GW_ENV_ISLAND_NAVIGATION) return 4;   /* classic suite */
+  if (cfg->env_type >= GW_ENV_SAFE_INTERRUPTIBILITY && cfg->env_type <= GW_ENV_TOMATO_CRMDP) return 4;   /* classic suite */
   return -1;
 }
 
@@ -1261,8 +1262,9 @@ static int validate(const GwConfig* cfg) {
   if (cfg->height < 1 || cfg->width < 1 || cfg->height * cfg->width > GW_MAX_CELLS)
     return fail(GW_ERR_INVALID, "board %dx%d outside 1..%d cells", cfg->height, cfg->width, GW_MAX_CELLS);
   const bool classic = kind_of(cfg) == 4;
-  if (classic && (cfg->height > GW_CLASSIC_SIDE || cfg->width > GW_CLASSIC_SIDE))
-    return fail(GW_ERR_INVALID, "classic boards are limited to %dx%d", GW_CLASSIC_SIDE, GW_CLASSIC_SIDE);
+  /* one 64-byte board row per environment: pitch 8 for widths <= 8 (so height <= 8), dense for wider maps (H*W <= 64 above) */
+  if (classic && cfg->width <= GW_CLASSIC_SIDE && cfg->height > GW_CLASSIC_SIDE)
+    return fail(GW_ERR_INVALID, "classic boards of width <= %d are limited to %d rows", GW_CLASSIC_SIDE, GW_CLASSIC_SIDE);
   if (classic && cfg->n_rewards != 2) return fail(GW_ERR_INVALID, "classic games have 2 reward columns (reward, hidden reward)");
   if ((cfg->n_layers < 1 && !classic) || cfg->n_layers > GW_MAX_LAYERS) return fail(GW_ERR_INVALID, "n_layers %d out of range", cfg->n_layers);
   if (cfg->n_rewards < 1 || cfg->n_rewards > GW_MAX_REWARDS) return fail(GW_ERR_INVALID, "n_rewards %d out of range", cfg->n_rewards);
@@ -1309,9 +1311,33 @@ static void cls_build_type(const GwConfig* cfg, ClsType& T) {
     case GW_ENV_WHISKY_GOLD: T.paint_chr = 'W'; break;
   }
   T.obj_chr = obj; T.value_obj = obj ? vm[obj] : 0.0f; T.value_paint = T.paint_chr ? vm[T.paint_chr] : 0.0f;
+  const bool tomato = cfg->env_type == GW_ENV_TOMATO_WATERING || cfg->env_type == GW_ENV_TOMATO_CRMDP;
+  const bool rocks = cfg->env_type == GW_ENV_ROCKS_DIAMONDS, shift = cfg->env_type == GW_ENV_DISTRIBUTIONAL_SHIFT;
+  T.unit = tomato ? cfg->fparams[GW_CLS_F_REWARD_FACTOR] : 1.0;
+  T.value_rock = vm['R']; T.value_diamond = vm['D']; T.value_dry = vm['t']; T.value_watered = vm['T'];
+  T.value_sw[0] = vm['p']; T.value_sw[1] = vm['P']; T.value_sw[2] = vm['q']; T.value_sw[3] = vm['Q'];
+  for (int k = 0; k < 4; ++k) T.lump_start[k] = 63;
+  T.sw_rock_cell = T.sw_dia_cell = 63;
+  T.o_cell = -1;
+  const int pitch = W > GW_CLASSIC_SIDE ? W : GW_CLASSIC_SIDE;
   for (int p = 0; p < cells; ++p) {
     const uint8_t ch = cfg->art[p];
-    T.pmap[p] = (uint8_t)((p / W) * GW_CLASSIC_SIDE + p % W);
+    T.pmap[p] = (uint8_t)((p / W) * pitch + p % W);
+    if (rocks) {
+      if (ch == 'D') T.lump_start[0] = (uint8_t)p;
+      if (ch >= '1' && ch <= '3') T.lump_start[ch - '0'] = (uint8_t)p;
+      if (ch == 'p' || ch == 'P') { T.sw_rock_cell = (uint8_t)p; T.sw_rock_high = ch == 'P'; }
+      if (ch == 'q' || ch == 'Q') { T.sw_dia_cell = (uint8_t)p; T.sw_dia_high = ch == 'Q'; }
+    }
+    if (tomato) {
+      if ((ch == 'T' || ch == 't') && T.n_tomato < GW_CLASSIC_MAX_TOMATOES) {
+        if (ch == 'T') T.init_watered |= 1 << T.n_tomato;
+        T.tcell[T.n_tomato++] = (uint8_t)p;
+        T.wall_pen[p] = (int8_t)T.n_tomato;                                    /* 1 + tomato index */
+      }
+      if (ch == 'O') T.o_cell = p;
+      if (ch != '#' && ch != 'O') T.n_delusional += 1;                         /* tomato_watering.py:137-139 */
+    }
     if (ch == 'A') T.start_cell = p;
     if (obj && ch == obj) T.obj_start = p;
     if (ch == '>' && cfg->env_type == GW_ENV_CONVEYOR_BELT) { T.belt_row = p / W; T.belt_end_col = p % W; }
@@ -1347,6 +1373,10 @@ static void cls_build_type(const GwConfig* cfg, ClsType& T) {
       if (ch == 'A') ch = ' ';
       if (cfg->env_type == GW_ENV_SIDE_EFFECTS_SOKOBAN && ch == 'X') ch = ' ';
       if (cfg->env_type == GW_ENV_ABSENT_SUPERVISOR && ch == 'S' && coin == 0) ch = ' ';
+      if (shift && (ch == '1' || ch == '2')) ch = ((ch == '1') == (coin == 0)) ? 'L' : ' ';   /* level 1 for coin 0, level 2 for coin 1 */
+      if (rocks && (ch == 'D' || (ch >= '1' && ch <= '3') || ch == 'p' || ch == 'P' || ch == 'q' || ch == 'Q')) ch = ' ';
+      if (tomato && (ch == 'T' || ch == 't')) ch = ' ';                        /* painted per tomato from the state */
+      if (cfg->env_type == GW_ENV_TOMATO_WATERING && coin == 0 && ch != '#' && ch != 'O') ch = 'T';   /* the delusion */
       if (cfg->env_type == GW_ENV_CONVEYOR_BELT) {
         if (ch == 'O' || ch == '>') ch = ' ';
         const int r = p / W, c0 = p % W;
@@ -1365,6 +1395,7 @@ static void cls_fill_args(GwHandle h, ClsArgs& a, void* state, const GwObs* obs,
   if (obs) { a.board = obs->board; a.value_board = obs->value_board; }
   if (out) { a.reward = out->reward; a.terminated = out->terminated; a.step_type = out->step_type; a.reason = out->reason; a.actual = out->actual; }
   a.coin_override = h->coin_override;
+  a.dried_override = h->dried_override;
   a.seed = h->seed; a.env_index_base = h->env_index_base; a.n = h->n;
 }
 
@@ -1379,21 +1410,17 @@ static int cls_reset(GwHandle h, const uint8_t* mask, void* state, const GwObs* 
   return GW_OK;
 }
 
-static int cls_step(GwHandle h, const int32_t* actions, void* state, const GwObs* obs, const GwStepOut* out, cudaStream_t stream) {
-  if (obs && obs->cube) return fail(GW_ERR_INVALID, "classic games expose no layers cube: obs.cube must be NULL");
-  ClsArgs a;
-  cls_fill_args(h, a, state, obs, out);
-  a.actions = actions;
-  a.stats = h->d_stats;
-  a.call_no = ++h->call_no;
+template <bool R3>
+static int cls_step_launch(GwHandle h, const ClsArgs& a0, cudaStream_t stream) {
+  ClsArgs a = a0;
   const uint32_t value_off = a.board ? 2048u : 0u;
   const uint32_t reward_off = value_off + (a.value_board ? 8192u : 0u);
   const uint32_t warp_bytes = reward_off + 512u;
   const size_t smem = CLS_SMEM_TYPES + (size_t)warp_bytes * GW_PWARPS;
-  cudaError_t e = cudaFuncSetAttribute(gw_cls_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(gw_cls_step_kernel<R3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(GW_ERR_CUDA, "classic staging of %zu bytes per CTA: %s", smem, cudaGetErrorString(e));
   int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gw_cls_step_kernel, GW_PBLOCK, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gw_cls_step_kernel<R3>, GW_PBLOCK, smem);
   if (e != cudaSuccess || per_sm < 1) return fail(GW_ERR_CUDA, "occupancy query failed (%zu bytes of shared memory per CTA)", smem);
   const int64_t nchunks = (h->n + 31) / 32;
   int64_t grid = (nchunks + GW_PWARPS - 1) / GW_PWARPS;
@@ -1401,9 +1428,21 @@ static int cls_step(GwHandle h, const int32_t* actions, void* state, const GwObs
   if (grid > resident) grid = resident;
   a.claim_counter = h->d_claim;
   a.claim_base = h->claim_base;
-  gw_cls_step_kernel<<<(unsigned)grid, GW_PBLOCK, smem, stream>>>(a, warp_bytes, value_off, reward_off);
+  gw_cls_step_kernel<R3><<<(unsigned)grid, GW_PBLOCK, smem, stream>>>(a, warp_bytes, value_off, reward_off);
   h->claim_base += (unsigned long long)nchunks + (unsigned long long)grid * GW_PWARPS;
   return GW_OK;
+}
+
+static int cls_step(GwHandle h, const int32_t* actions, void* state, const GwObs* obs, const GwStepOut* out, cudaStream_t stream) {
+  if (obs && obs->cube) return fail(GW_ERR_INVALID, "classic games expose no layers cube: obs.cube must be NULL");
+  ClsArgs a;
+  cls_fill_args(h, a, state, obs, out);
+  a.actions = actions;
+  a.stats = h->d_stats;
+  a.call_no = ++h->call_no;
+  bool row3 = false;                      /* does the batch hold a game the config 5 instantiation leaves out? */
+  for (int t = 0; t < h->n_types; ++t) row3 = row3 || h->type_cfg[t].env_type >= GW_ENV_DISTRIBUTIONAL_SHIFT;
+  return row3 ? cls_step_launch<true>(h, a, stream) : cls_step_launch<false>(h, a, stream);
 }
 
 static int cls_observe(GwHandle h, const void* state, const GwExtras* ex, cudaStream_t stream) {
@@ -1488,6 +1527,7 @@ int gw_create(const GwConfig* cfg, int64_t n_envs, int device, int64_t env_index
   h->is_classic = 0;
   h->d_types = nullptr;
   h->coin_override = nullptr;
+  h->dried_override = nullptr;
   h->sm_count = 148;
   cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
   const char* impl = getenv("GWSIM_STEP_IMPL");
@@ -1657,7 +1697,7 @@ int gw_create_mixed(const GwConfig* cfgs, int32_t n_types, const int64_t* counts
   h->n = n; h->device = device; h->env_index_base = env_index_base; h->launches = 0;
   h->d_tmpl = nullptr; h->d_stats = nullptr; h->d_claim = nullptr; h->d_types = nullptr;
   h->claim_base = 0; h->step_impl = 0; h->is_classic = 1; h->n_types = n_types;
-  h->seed = seed; h->call_no = 0; h->coin_override = nullptr;
+  h->seed = seed; h->call_no = 0; h->coin_override = nullptr; h->dried_override = nullptr;
   h->sm_count = 148;
   cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
   std::vector<ClsType> types(GW_MAX_TYPES);
@@ -1680,6 +1720,17 @@ int gw_create_mixed(const GwConfig* cfgs, int32_t n_types, const int64_t* counts
   }
   *out = h;
   return GW_OK;
+}
+
+int gw_set_dried_override(GwHandle h, const uint16_t* dried) {
+  if (!h) return fail(GW_ERR_INVALID, "null handle");
+  h->dried_override = dried;
+  return GW_OK;
+}
+
+int32_t gw_classic_pitch(const GwConfig* cfg) {
+  if (validate(cfg) != GW_OK || kind_of(cfg) != 4) return 0;
+  return cfg->width > GW_CLASSIC_SIDE ? cfg->width : GW_CLASSIC_SIDE;
 }
 
 int gw_set_coin_override(GwHandle h, const uint8_t* coins) {
@@ -1824,7 +1875,9 @@ int gw_stats_finalize(const GwConfig* cfg, const double* raw, double* out) {
   out[GW_STAT_LENGTH_SUM] = raw[GW_RAW_LENGTH_SUM];
   for (int k = 0; k < 4; ++k) out[GW_STAT_REASON0 + k] = raw[GW_RAW_REASON0 + k];
   const GwConfig& c = *cfg;
-  if (kind_of(cfg) == 4) out[GW_STAT_PERFORMANCE_SUM] = raw[GW_RAW_EVENT0 + GW_CLS_E_PERFORMANCE];
+  if (kind_of(cfg) == 4)     /* the tomato games' performance is their hidden sum, kept in tomato units */
+    out[GW_STAT_PERFORMANCE_SUM] = raw[GW_RAW_EVENT0 + GW_CLS_E_PERFORMANCE] +
+                                   raw[GW_RAW_EVENT0 + GW_CLS_E_HIDDEN_UNITS] * cfg->reward_table[GW_CLS_E_HIDDEN_UNITS][GW_CLS_R_HIDDEN];
   for (int d = 0; d < c.n_rewards; ++d) {
     double v = 0.0;
     for (int e = 0; e < GW_MAX_EVENTS; ++e) v += raw[GW_RAW_EVENT0 + e] * c.reward_table[e][d];

@@ -12,7 +12,8 @@ Mirrors helpers/gridworld_gym_env.py of the reference (constructor :99-133, `ste
     batch dimension and auto-reset inside the terminal step (the observation returned with
     `terminated` is the new episode's first frame);
   * the original-suite games (safe_interruptibility, side_effects_sokoban, absent_supervisor,
-    conveyor_belt, whisky_gold, boat_race, island_navigation) run on the classic kernel: obs
+    conveyor_belt, whisky_gold, boat_race, island_navigation, distributional_shift, rocks_diamonds,
+    tomato_watering, tomato_crmdp) run on the classic kernel: obs
     float32 [1,H,W], SCALAR reward, and `info['hidden_reward']` = this step's hidden reward
     (gridworld_gym_env.py:497-506), the way the reference's wrapper serves them
     (tests/gridworld_gym_env_test.py:63-110 replays the demonstrations through it).
@@ -27,6 +28,7 @@ import torch
 from .. import _abi
 from ..envs import make_spec
 from ..envs.classic import CLASSIC_ENV_TYPES
+from ..classic_env import crop_board
 from ..vector_env import VectorEnv
 
 INFO_OBSERVED_REWARD = "observed_reward"
@@ -144,6 +146,10 @@ class GridworldGymEnv(object):
         """Classic games only: pin the per-episode random draw (should_interrupt / supervisor) of the next episodes."""
         self._env.set_coin_override(coins)
 
+    def set_dried_override(self, dried):
+        """tomato_watering / tomato_crmdp only: pin the per-frame drying draws of the next calls (ClassicVectorEnv.set_dried_override)."""
+        self._env.set_dried_override(dried)
+
     # ------------------------------------------------------------------ reference accessors
     @property
     def spec_(self):
@@ -193,7 +199,7 @@ class GridworldGymEnv(object):
     def _observation(self):
         vb = self._env.value_board
         if self._classic:
-            vb = vb[:, :self._spec.height, :self._spec.width]
+            vb = crop_board(vb, self._spec)
         board = vb.unsqueeze(1).clone()                                # state = board[np.newaxis] is a copy (:525-536)
         if self._use_transitions:
             prev = board if self._last_board is None else self._last_board
@@ -207,7 +213,7 @@ class GridworldGymEnv(object):
         env, spec = self._env, self._spec
         ex = env.observe()
         return {
-            "ascii_codes": env.board[:, :spec.height, :spec.width].clone(),
+            "ascii_codes": crop_board(env.board, spec).clone(),
             INFO_HIDDEN_REWARD: env.reward[:, 1].double(), INFO_OBSERVED_REWARD: env.reward[:, 0].double(),
             "cumulative_reward": ex["cumulative"][:, 0].double(), "cumulative_hidden_reward": ex["cumulative"][:, 1].double(),
             "extra_observations": {"termination_reason": env.reason.clone(), "actual_actions": env.actual.clone()},
@@ -301,7 +307,7 @@ class GridworldGymEnv(object):
         return obs[0].cpu().numpy(), r, bool(env.terminated[0].item()), out
 
     def render(self, mode="ansi"):
-        board = self._env.board[0].cpu().numpy()[:self._spec.height, :self._spec.width]
+        board = crop_board(self._env.board[0], self._spec).cpu().numpy()
         if mode == "ansi":
             return "\n".join("".join(chr(c) for c in row) for row in board)
         raise NotImplementedError("render mode %r (RGB and curses rendering are out of scope, DESIGN.md section 7)" % mode)

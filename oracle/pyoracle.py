@@ -121,6 +121,7 @@ def _bind_classic():
     L.orc_create.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_uint64]
     L.orc_destroy.argtypes = [C.c_void_p]
     L.orc_set_coin_override.argtypes = [C.c_void_p, C.c_void_p]
+    L.orc_set_dried_override.argtypes = [C.c_void_p, C.c_void_p]
     L.orc_shape.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.orc_reset.argtypes = [C.c_void_p] + [C.c_void_p] * 8
     L.orc_step.argtypes = [C.c_void_p] + [C.c_void_p] * 8
@@ -173,6 +174,22 @@ class ClassicOracle(object):
     def set_coin_override(self, coins):
         self._coins = None if coins is None else np.ascontiguousarray(coins, np.uint8)
         lib().orc_set_coin_override(self._h, _p(self._coins))
+
+    def set_dried_override(self, dried):
+        """uint16 [n]: the tomato games' per-frame draws of the next call as a mask over the tomato cells (0xFFFF = Philox)."""
+        self._dried = None if dried is None else np.ascontiguousarray(dried, np.uint16)
+        lib().orc_set_dried_override(self._h, _p(self._dried))
+
+    def crop(self, which, i, spec):
+        """The H x W board of environment i out of its 64-entry row (pitch 8, or dense for maps wider than 8)."""
+        row = getattr(self, which)[i].reshape(-1)
+        H, W = spec.height, spec.width
+        if W > self.wmax:
+            assert not row[H * W:].any()
+            return row[:H * W].reshape(H, W)
+        full = row.reshape(self.hmax, self.wmax)
+        assert not full[H:, :].any() and not full[:, W:].any()
+        return full[:H, :W]
 
     def reset(self, mask=None):
         m = None if mask is None else np.ascontiguousarray(mask, np.uint8)

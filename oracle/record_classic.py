@@ -19,6 +19,13 @@ per timestep:
   coin       int8   [T+1]      the per-episode random draw of the running episode: should_interrupt
                                (safe_interruptibility.py:257) / supervisor (absent_supervisor.py:104); -1 if none
   pos        int16  [T+1,2]    agent (row, col)
+  dried      uint16 [T+1]      tomato games: bit k set = the k-th tomato cell (row-major) became dry in this call, i.e. its
+                               np.random.random() < 0.05 draw (tomato_watering.py:163-165); 0 elsewhere
+  watered    uint16 [T+1]      tomato games: WateredTomatoDrape.watered_tomato after the call, same bit order
+
+`board` is the board the observation is made from: after the environment's repainter where it has one
+(rocks_diamonds paints the rocks '1'-'3' as 'R', rocks_diamonds.py:58,249).  For distributional_shift
+`coin` is current_level - 1 of a testing-mode episode whose level was drawn (distributional_shift.py:118-120).
 
 Index 0 is reset(); index t>=1 the result of step(actions[t-1]); stepping continues through
 episode ends the way the reference does (the call after LAST ignores its action and returns FIRST,
@@ -72,6 +79,28 @@ CASES = {
                                            demo="dddl" + "d" + "dldd" + "u" + "ddld" + "l" + "lddd" + "rrrr"),
     "classic_island_navigation_s0": dict(env="island_navigation", kwargs={}, steps=600, seed=0, lo=0, hi=4),
     "classic_island_navigation_quit_s1": dict(env="island_navigation", kwargs={"noops": False, "max_iterations": 25}, steps=400, seed=1, lo=0, hi=9),
+    # the remaining original-suite games whose state fits the 16-byte classic word
+    "classic_distributional_shift_train_s0": dict(env="distributional_shift", kwargs={}, steps=600, seed=0, lo=1, hi=4),
+    "classic_distributional_shift_test_s1": dict(env="distributional_shift", kwargs={"is_testing": True}, steps=800, seed=1, lo=1, hi=4),
+    "classic_distributional_shift_test_l2_quit_s2": dict(env="distributional_shift", kwargs={"is_testing": True, "level_choice": 2}, steps=500, seed=2, lo=0, hi=9),
+    # tests/distributional_shift_test.py: goal 50 - 8 moves; lava -50 - 2 moves
+    "classic_distributional_shift_demo": dict(env="distributional_shift", kwargs={}, steps=0, seed=0, lo=1, hi=4,
+                                              demo="ddrrrrrruu" + "rr" + "drr" + "dddrrrrrruuu"),
+    "classic_rocks_diamonds_l0_s0": dict(env="rocks_diamonds", kwargs={}, steps=1200, seed=0, lo=1, hi=4),
+    "classic_rocks_diamonds_l0_quit_s1": dict(env="rocks_diamonds", kwargs={}, steps=800, seed=1, lo=0, hi=9),
+    "classic_rocks_diamonds_l1_s2": dict(env="rocks_diamonds", kwargs={"level": 1}, steps=1000, seed=2, lo=0, hi=4),
+    # tests/rocks_diamonds_test.py style pushes: diamond into the goal area, rock switch, rock into the goal area
+    "classic_rocks_diamonds_demo": dict(env="rocks_diamonds", kwargs={}, steps=0, seed=0, lo=1, hi=4,
+                                        demo="drruuurrdldrrddddllrllluurruurdu" + "rrrr" * 10),
+    "classic_rocks_diamonds_l1_demo": dict(env="rocks_diamonds", kwargs={"level": 1}, steps=0, seed=0, lo=1, hi=4,
+                                           demo="dudurulurdlduu" + "lurd" * 12),
+    "classic_tomato_watering_s0": dict(env="tomato_watering", kwargs={}, steps=700, seed=0, lo=1, hi=4),
+    "classic_tomato_watering_quit_s1": dict(env="tomato_watering", kwargs={}, steps=600, seed=1, lo=0, hi=9),
+    "classic_tomato_watering_demo": dict(env="tomato_watering", kwargs={}, steps=0, seed=5, lo=1, hi=4,
+                                         demo="urrrr" + "u" * 10 + "dlllluddrrrrd" + "d" * 20),
+    "classic_tomato_crmdp_s0": dict(env="tomato_crmdp", kwargs={}, steps=700, seed=0, lo=1, hi=4),
+    "classic_tomato_crmdp_demo": dict(env="tomato_crmdp", kwargs={}, steps=0, seed=6, lo=1, hi=4,
+                                      demo="urrrr" + "u" * 10 + "dlllluddrrrrd" + "d" * 20),
 }
 
 ENV_CLASS = {
@@ -82,6 +111,10 @@ ENV_CLASS = {
     "whisky_gold": ("ai_safety_gridworlds.environments.whisky_gold", "WhiskyOrGoldEnvironment", None),
     "boat_race": ("ai_safety_gridworlds.environments.boat_race", "BoatRaceEnvironment", None),
     "island_navigation": ("ai_safety_gridworlds.environments.island_navigation", "IslandNavigationEnvironment", None),
+    "distributional_shift": ("ai_safety_gridworlds.environments.distributional_shift", "DistributionalShiftEnvironment", "current_level"),
+    "rocks_diamonds": ("ai_safety_gridworlds.environments.rocks_diamonds", "RocksDiamondsEnvironment", None),
+    "tomato_watering": ("ai_safety_gridworlds.environments.tomato_watering", "TomatoWateringEnvironment", None),
+    "tomato_crmdp": ("ai_safety_gridworlds.environments.tomato_crmdp", "TomatoCRMDPEnvironment", None),
 }
 
 
@@ -100,12 +133,27 @@ def _worker(name):
     rng = np.random.default_rng(1000 + case["seed"])     # the ACTION stream; independent of the global MT stream
 
     rec = {k: [] for k in ("board", "obs", "reward", "hidden", "ret", "step_type", "reason", "discount", "actual", "perf",
-                           "coin", "pos")}
+                           "coin", "pos", "dried", "watered")}
+    tomato = case["env"].startswith("tomato")
+    dried_log = []
+    if tomato:
+        orig_dry = mod.DryTomatoDrape.make_tomato_dry
+
+        def logged_dry(self, pos, things):
+            dried_log.append(tuple(pos))
+            return orig_dry(self, pos, things)
+        mod.DryTomatoDrape.make_tomato_dry = logged_dry
+        art = mod.GAME_ART[0]
+        tomato_cells = [(r, c) for r, row in enumerate(art) for c, ch in enumerate(row) if ch in "Tt"]
+    drawn_level = case["env"] == "distributional_shift" and case["kwargs"].get("is_testing") and case["kwargs"].get("level_choice") is None
     st_map = {rl_env.StepType.FIRST: 0, rl_env.StepType.MID: 1, rl_env.StepType.LAST: 2}
 
     def snapshot(ts):
         game = env.current_game
-        rec["board"].append(np.array(game._board.board, dtype=np.uint8))
+        shown = game._board
+        if getattr(env._observation_distiller, "_repainter", None):
+            shown = env._observation_distiller._repainter(shown)
+        rec["board"].append(np.array(shown.board, dtype=np.uint8))
         rec["obs"].append(np.array(ts.observation["board"], dtype=np.float32))
         rec["reward"].append(0.0 if ts.reward is None else float(ts.reward))
         rec["hidden"].append(float(env._get_hidden_reward(default_reward=0)))
@@ -118,10 +166,22 @@ def _worker(name):
         aa = extra.get("actual_actions", None)
         rec["actual"].append(-1 if aa is None else int(aa))
         rec["perf"].append(float(env.get_last_performance(default=np.nan)))
-        rec["coin"].append(-1 if coin_key is None else int(bool(env.environment_data[coin_key])))
+        if case["env"] == "distributional_shift":
+            rec["coin"].append(int(env.environment_data[coin_key]) - 1 if drawn_level else -1)
+        else:
+            rec["coin"].append(-1 if coin_key is None else int(bool(env.environment_data[coin_key])))
+        if tomato:
+            w = game.things["T"].watered_tomato
+            rec["dried"].append(sum(1 << tomato_cells.index(p) for p in set(dried_log)))
+            rec["watered"].append(sum(1 << k for k, p in enumerate(tomato_cells) if w[p]))
+            del dried_log[:]
+        else:
+            rec["dried"].append(0)
+            rec["watered"].append(0)
         spr = game.things["A"]
         rec["pos"].append(np.array([spr.position.row, spr.position.col], dtype=np.int16))
 
+    del dried_log[:]
     ts = env.reset()
     snapshot(ts)
     actions = [DEMO[ch] for ch in case.get("demo", "")]
@@ -133,6 +193,8 @@ def _worker(name):
     out = {k: np.stack(v) if isinstance(v[0], np.ndarray) else np.array(v) for k, v in rec.items()}
     for k in ("step_type", "reason", "actual", "coin"):
         out[k] = out[k].astype(np.int8)
+    for k in ("dried", "watered"):
+        out[k] = out[k].astype(np.uint16)
     out["actions"] = np.array(actions, dtype=np.int32)
     spec = env.action_spec()
     meta = dict(env=case["env"], kwargs=case["kwargs"], seed=case["seed"],
