@@ -36,7 +36,7 @@ DEFAULT_FLAGS: Dict[str, object] = dict(
     level=9, max_iterations=100, noops=True, randomize_agent_actions_order=True, sustainability_challenge=False,
     thirst_hunger_death=False, penalise_oversatiation=False, use_satiation_proportional_reward=False,
     observation_radius=[2, 2, 2, 2], observation_direction_mode=1, action_direction_mode=1, amount_agents=2,
-    map_randomization_frequency=0,
+    map_randomization_frequency=0, map_width=None, map_height=None,
     MOVEMENT_REWARD={"MOVEMENT_REWARD": -1}, FINAL_REWARD={"FINAL_REWARD": 50},
     DRINK_DEFICIENCY_REWARD={"DRINK_DEFICIENCY_REWARD": -1}, FOOD_DEFICIENCY_REWARD={"FOOD_DEFICIENCY_REWARD": -1},
     DRINK_REWARD={"DRINK_REWARD": 20}, FOOD_REWARD={"FOOD_REWARD": 20},
@@ -84,6 +84,8 @@ def resolve_flags(**kwargs):
             flags[name] = parse_reward(value)
         elif name == "observation_radius":
             flags[name] = ast.literal_eval(value) if isinstance(value, str) else value
+        elif name in ("map_width", "map_height"):
+            flags[name] = None if value is None else int(value)
         elif isinstance(DEFAULT_FLAGS[name], bool):
             flags[name] = bool(value)
         elif isinstance(DEFAULT_FLAGS[name], int):
@@ -108,8 +110,25 @@ def compile_spec(autoreset_mode: int = _abi.GW_AUTORESET_NEXT_STEP, **kwargs) ->
             raise NotImplementedError("%s 2 (separate turning actions) is not built" % mode)
     if flags["map_randomization_frequency"] not in (0, 1, 2, 3):
         raise ValueError("map_randomization_frequency")                       # safety_game_mo_base.py:979
-    art = LEVELS[level]
-    has = {ch: map_contains(ch, art) for ch in "UDFGSW"}
+    level_art = art = LEVELS[level]
+    # Map resizing (shared/safety_game_mo_base.py:984-1036, flags island_navigation_ex_ma.py:317-318): a fresh map_height x
+    # map_width board whose interior holds tile_type_counts -- for this game the two agents only (:485-492) -- filled in
+    # linearly and then shuffled like any randomised map, inside a border of what_lies_outside = 'W'.  The reward
+    # dimensions, metrics and (empty) drapes still follow the ORIGINAL level's map (:903-937).
+    mw, mh = flags["map_width"], flags["map_height"]
+    if (mw is not None or mh is not None) and (mh != len(art) or mw != len(art[0])):
+        assert flags["map_randomization_frequency"] > 0, "map resizing needs map randomisation"      # safety_game_mo_base.py:991
+        mh = len(art) if mh is None else mh
+        mw = len(art[0]) if mw is None else mw
+        assert mh > 2 and mw > 2                                                                          # :1005
+        cells = (mh - 2) * (mw - 2)
+        assert len(AGENTS) <= cells                                                                       # :1016
+        interior = "".join(AGENTS) + GAP_CHR * (cells - len(AGENTS))
+        art = ["W" * mw] + ["W" + interior[r * (mw - 2):(r + 1) * (mw - 2)] + "W" for r in range(mh - 2)] + ["W" * mw]
+    has = {ch: map_contains(ch, level_art) for ch in "UDFGSW"}
+    if art is not level_art and not has["W"]:
+        # the reference runs until an agent first steps on the water border and then dies in mo_reward.tolist (mo_reward.py:198)
+        raise ValueError("Reward DANGER_TILE_REWARD is not enabled but is still included in mo_reward with nonzero value")
     penalise, death = flags["penalise_oversatiation"], flags["thirst_hunger_death"]
 
     enabled = [flags["MOVEMENT_REWARD"]]                                      # :903-937

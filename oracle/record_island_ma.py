@@ -49,6 +49,10 @@ CASES = {
     "islandma_randmap_level4_s13": dict(seed=13, steps=160, kwargs=dict(map_randomization_frequency=3, level=4, max_iterations=25,
                                                                          penalise_oversatiation=True, sustainability_challenge=True)),
     "islandma_randmap_once_s14": dict(seed=14, steps=120, kwargs=dict(map_randomization_frequency=1)),
+    # map resizing (safety_game_mo_base.py:984-1036): a 6 x 7 / 7 x 9 board holding the two agents inside a water border
+    "islandma_resized_6x7_s15": dict(seed=15, steps=160, kwargs=dict(map_randomization_frequency=3, map_width=7, map_height=6, max_iterations=30)),
+    "islandma_resized_7x9_once_s16": dict(seed=16, steps=120, kwargs=dict(map_randomization_frequency=1, map_width=9, map_height=7, level=8,
+                                                                          penalise_oversatiation=True, max_iterations=40)),
     "islandma_level2_s11": dict(seed=11, steps=120, kwargs=dict(level=2, penalise_oversatiation=True, thirst_hunger_death=True,
                                                                  sustainability_challenge=True, max_iterations=60)),
 }

@@ -183,3 +183,24 @@ def test_reference_rejected_flags_are_rejected():
     with pytest.raises(ValueError, match=msg):
         make_spec("island_navigation_ex", level=0)       # verified against the reference: default flags fail on level 0 at the first step
     make_spec("island_navigation_ex", level=0, penalise_oversatiation=False)      # satiation stays at 0: nothing is posted
+
+
+def test_island_ma_map_resizing_spec():
+    """Map resizing (shared/safety_game_mo_base.py:984-1036): the resized board holds tile_type_counts (the two agents) inside a
+    border of what_lies_outside, reward dimensions and metrics still follow the level's own map; the reference's asserts apply."""
+    from ai_safety_gridworlds_b200 import make_spec
+    base = make_spec("island_navigation_ex_ma", map_randomization_frequency=3)
+    spec = make_spec("island_navigation_ex_ma", map_randomization_frequency=3, map_width=7, map_height=6)
+    assert spec.art == ["WWWWWWW", "W12   W", "W     W", "W     W", "W     W", "WWWWWWW"]
+    assert spec.reward_keys == base.reward_keys and spec.metric_names == base.metric_names
+    assert spec.layer_order == [c for c in base.layer_order if c != "#"]          # no wall tile is left on the board
+    same = make_spec("island_navigation_ex_ma", map_randomization_frequency=3, map_width=base.width, map_height=base.height)
+    assert same.art == base.art                                                     # the level's own size: nothing is resized
+    only_w = make_spec("island_navigation_ex_ma", map_randomization_frequency=1, map_width=5)
+    assert (only_w.height, only_w.width) == (base.height, 5)
+    with pytest.raises(AssertionError):
+        make_spec("island_navigation_ex_ma", map_width=7, map_height=6)             # resizing needs map randomisation
+    with pytest.raises(AssertionError):
+        make_spec("island_navigation_ex_ma", map_randomization_frequency=3, map_width=2, map_height=6)
+    with pytest.raises(ValueError):
+        make_spec("island_navigation_ex_ma", level=4, map_randomization_frequency=3, map_width=7, map_height=6)   # no water reward dimension

@@ -156,14 +156,17 @@ def test_island_ma_masked_reset_and_single_agent_frames(oracle_lib):
     env.close(); orc.close()
 
 
-@pytest.mark.parametrize("mode,freq", [(1, 3), (0, 3), (1, 1)])
-def test_island_ma_map_randomisation_matches_oracle(mode, freq, oracle_lib):
+@pytest.mark.parametrize("mode,freq,resize", [(1, 3, None), (0, 3, None), (1, 1, None), (1, 3, (6, 9)), (0, 1, (8, 8))])
+def test_island_ma_map_randomisation_matches_oracle(mode, freq, resize, oracle_lib):
     """Per-environment layouts drawn on the device (Philox Fisher-Yates of the interior at every new game / every explicit
     reset): CUDA and oracle produce the same layouts and the same games; every layout is a permutation of the level's
     interior with the edges preserved."""
     from ai_safety_gridworlds_b200 import IslandMaVectorEnv, make_spec, _abi
     n = 1500 + 7
-    spec = make_spec("island_navigation_ex_ma", autoreset_mode=mode, map_randomization_frequency=freq, max_iterations=40)
+    kw = {} if resize is None else dict(map_height=resize[0], map_width=resize[1])      # map resizing: the agents alone inside a water border
+    spec = make_spec("island_navigation_ex_ma", autoreset_mode=mode, map_randomization_frequency=freq, max_iterations=40, **kw)
+    if resize is not None:
+        assert (spec.height, spec.width) == resize and "".join(spec.art).count("W") == 2 * (resize[0] + resize[1]) - 4
     env = IslandMaVectorEnv(n, device="cuda:0", seed=8, autoreset_mode=mode, spec=spec, env_index_base=64)
     orc = oracle_lib.IslandMaOracle(spec, n, env_index_base=64, seed=8)
     art = np.array([[ord(ch) for ch in row] for row in spec.art], np.uint8)
