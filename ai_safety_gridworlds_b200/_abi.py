@@ -24,6 +24,7 @@ GW_ENV_SAFE_INTERRUPTIBILITY, GW_ENV_SIDE_EFFECTS_SOKOBAN, GW_ENV_ABSENT_SUPERVI
 GW_ENV_CONVEYOR_BELT, GW_ENV_WHISKY_GOLD = 6, 7
 GW_ENV_BOAT_RACE, GW_ENV_ISLAND_NAVIGATION = 8, 9
 GW_ENV_DISTRIBUTIONAL_SHIFT, GW_ENV_ROCKS_DIAMONDS, GW_ENV_TOMATO_WATERING, GW_ENV_TOMATO_CRMDP = 10, 11, 12, 13
+GW_ENV_FRIEND_FOE = 14
 GW_ENV_ISLAND_NAVIGATION_EX_MA = 16       # include/gwsim_ima.h
 GW_MAX_TYPES = 8
 
@@ -56,8 +57,8 @@ BOAT_E = dict(MOVEMENT=0, CLOCKWISE=1, FINAL=2, ITERATIONS=3, REPETITION=4, HUMA
 
 
 # classic-suite slots
-CLS_I = dict(MOVEMENT_REWARD=0, GOAL_REWARD=1, AUX_REWARD=2, WALL_REWARD=3, CORNER_REWARD=4, VARIANT=5)
-CLS_F = dict(PROBABILITY=0, REWARD_FACTOR=1)
+CLS_I = dict(MOVEMENT_REWARD=0, GOAL_REWARD=1, AUX_REWARD=2, WALL_REWARD=3, CORNER_REWARD=4, VARIANT=5, EXTRA_STEP=6)
+CLS_F = dict(PROBABILITY=0, REWARD_FACTOR=1, LEARNING_RATE=2)
 CLS_E = dict(RETURN=0, HIDDEN=1, PERFORMANCE=2, RETURN_UNITS=3, HIDDEN_UNITS=4)
 CACT = dict(NOOP=0, UP=1, DOWN=2, LEFT=3, RIGHT=4, QUIT=9)
 

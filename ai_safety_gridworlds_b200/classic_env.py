@@ -3,7 +3,7 @@
 The batched counterpart of `safety_game.SafetyEnvironment.step` (environments/shared/safety_game.py:314)
 for safe_interruptibility, side_effects_sokoban (level 0), absent_supervisor, conveyor_belt,
 whisky_gold, boat_race, island_navigation, distributional_shift, rocks_diamonds, tomato_watering and
-tomato_crmdp: environments [sum(counts[:t]), sum(counts[:t+1])) are of type specs[t], all stepped by
+tomato_crmdp, friend_foe: environments [sum(counts[:t]), sum(counts[:t+1])) are of type specs[t], all stepped by
 ONE launch of the fused kernel in csrc/gwsim_classic.cuh (BASELINE config 5).  Actions use the
 original numbering (NOOP 0, UP 1, DOWN 2, LEFT 3, RIGHT 4, QUIT 9).  No CPU fallback.
 """
@@ -67,7 +67,10 @@ class ClassicVectorEnv(object):
         _abi.check(lib.gw_create_mixed(cfgs, len(specs), cnt, dev_index, int(env_index_base), int(seed), C.byref(handle)))
         self._h = handle
         N, dev = self.num_envs, self.device
-        self.state = torch.zeros((1, N, 4), dtype=torch.int32, device=dev)
+        # opaque state: one 16-byte word per environment, plane-major [words, ceil32(N)]; only friend_foe (its three
+        # PolicyEstimators) needs more than one plane
+        self._state_words = max(int(lib.gw_state_words(C.byref(s.config))) for s in specs)
+        self.state = torch.zeros((self._state_words, (N + 31) // 32 * 32, 4), dtype=torch.int32, device=dev)
         self.board = torch.zeros((N, SIDE, SIDE), dtype=torch.uint8, device=dev) if want_board else None
         self.value_board = torch.zeros((N, SIDE, SIDE), dtype=torch.float32, device=dev) if want_value_board else None
         self.reward = torch.zeros((N, 2), dtype=torch.float32, device=dev)
@@ -158,7 +161,14 @@ class ClassicVectorEnv(object):
 
     @property
     def state_words(self):
-        return 1
+        return self._state_words
+
+    def policies(self):
+        """friend_foe: float64 [N, 3, 2] view of the PolicyEstimator.policy vectors (friend, neutral, adversary); a vector that
+        was never updated reads (0, 0) and stands for the initial (0.5, 0.5)."""
+        if self._state_words < 4:
+            raise ValueError("no friend_foe type in this batch")
+        return self.state[1:4, :self.num_envs].contiguous().view(torch.float64).reshape(3, self.num_envs, 2).permute(1, 0, 2)
 
     def finalize_stats(self, raw_host):
         raw = np.ascontiguousarray(raw_host, np.float64)

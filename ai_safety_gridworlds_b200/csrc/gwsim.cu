@@ -1240,7 +1240,7 @@ __global__ void __launch_bounds__(GW_BLOCK) gw_random_actions_kernel(uint64_t se
 static int kind_of(const GwConfig* cfg) {
   if (cfg->env_type == GW_ENV_ISLAND_NAVIGATION_EX) return cfg->iparams[GW_ISL_I_PROPORTIONAL] ? 1 : 0;
   if (cfg->env_type == GW_ENV_BOAT_RACE_EX) return cfg->max_iterations <= 254 ? 2 : 3;
-  if (cfg->env_type >= GW_ENV_SAFE_INTERRUPTIBILITY && cfg->env_type <= GW_ENV_TOMATO_CRMDP) return 4;   /* classic suite */
+  if (cfg->env_type >= GW_ENV_SAFE_INTERRUPTIBILITY && cfg->env_type <= GW_ENV_FRIEND_FOE) return 4;   /* classic suite */
   return -1;
 }
 
@@ -1314,6 +1314,11 @@ static void cls_build_type(const GwConfig* cfg, ClsType& T) {
   const bool tomato = cfg->env_type == GW_ENV_TOMATO_WATERING || cfg->env_type == GW_ENV_TOMATO_CRMDP;
   const bool rocks = cfg->env_type == GW_ENV_ROCKS_DIAMONDS, shift = cfg->env_type == GW_ENV_DISTRIBUTIONAL_SHIFT;
   T.unit = tomato ? cfg->fparams[GW_CLS_F_REWARD_FACTOR] : 1.0;
+  const bool ff = cfg->env_type == GW_ENV_FRIEND_FOE;
+  T.lr = cfg->fparams[GW_CLS_F_LEARNING_RATE];
+  T.ff_extra_step = (uint8_t)(cfg->iparams[GW_CLS_I_EXTRA_STEP] != 0);
+  T.value_tile[0] = vm['F']; T.value_tile[1] = vm['N']; T.value_tile[2] = vm['B'];
+  T.value_star = vm['*']; T.value_one = vm['1']; T.value_zero = vm['0'];
   T.value_rock = vm['R']; T.value_diamond = vm['D']; T.value_dry = vm['t']; T.value_watered = vm['T'];
   T.value_sw[0] = vm['p']; T.value_sw[1] = vm['P']; T.value_sw[2] = vm['q']; T.value_sw[3] = vm['Q'];
   for (int k = 0; k < 4; ++k) T.lump_start[k] = 63;
@@ -1328,6 +1333,11 @@ static void cls_build_type(const GwConfig* cfg, ClsType& T) {
       if (ch >= '1' && ch <= '3') T.lump_start[ch - '0'] = (uint8_t)p;
       if (ch == 'p' || ch == 'P') { T.sw_rock_cell = (uint8_t)p; T.sw_rock_high = ch == 'P'; }
       if (ch == 'q' || ch == 'Q') { T.sw_dia_cell = (uint8_t)p; T.sw_dia_high = ch == 'Q'; }
+    }
+    if (ff) {
+      if (ch == '1') T.ff_left = (uint8_t)p;
+      if (ch == '0') T.ff_right = (uint8_t)p;
+      if ((ch == ' ' || ch == 'A') && T.n_tomato < GW_CLASSIC_MAX_TOMATOES) T.tcell[T.n_tomato++] = (uint8_t)p;   /* FloorDrape cells */
     }
     if (tomato) {
       if ((ch == 'T' || ch == 't') && T.n_tomato < GW_CLASSIC_MAX_TOMATOES) {
@@ -1376,6 +1386,7 @@ static void cls_build_type(const GwConfig* cfg, ClsType& T) {
       if (shift && (ch == '1' || ch == '2')) ch = ((ch == '1') == (coin == 0)) ? 'L' : ' ';   /* level 1 for coin 0, level 2 for coin 1 */
       if (rocks && (ch == 'D' || (ch >= '1' && ch <= '3') || ch == 'p' || ch == 'P' || ch == 'q' || ch == 'Q')) ch = ' ';
       if (tomato && (ch == 'T' || ch == 't')) ch = ' ';                        /* painted per tomato from the state */
+      if (ff && (ch == '1' || ch == '0')) ch = '*';                            /* HideGoalDrape covers both boxes */
       if (cfg->env_type == GW_ENV_TOMATO_WATERING && coin == 0 && ch != '#' && ch != 'O') ch = 'T';   /* the delusion */
       if (cfg->env_type == GW_ENV_CONVEYOR_BELT) {
         if (ch == 'O' || ch == '>') ch = ' ';
@@ -1396,6 +1407,7 @@ static void cls_fill_args(GwHandle h, ClsArgs& a, void* state, const GwObs* obs,
   if (out) { a.reward = out->reward; a.terminated = out->terminated; a.step_type = out->step_type; a.reason = out->reason; a.actual = out->actual; }
   a.coin_override = h->coin_override;
   a.dried_override = h->dried_override;
+  a.plane_stride = (h->n + 31) / 32 * 32;
   a.seed = h->seed; a.env_index_base = h->env_index_base; a.n = h->n;
 }
 
@@ -1494,6 +1506,7 @@ int64_t gw_config_bytes(void) { return (int64_t)sizeof(GwConfig); }
 
 int32_t gw_state_words(const GwConfig* cfg) {
   if (validate(cfg) != GW_OK) return 0;
+  if (cfg->env_type == GW_ENV_FRIEND_FOE) return 4;       /* the game word + three PolicyEstimator planes */
   return words_of_kind(kind_of(cfg));
 }
 

@@ -122,6 +122,7 @@ def _bind_classic():
     L.orc_destroy.argtypes = [C.c_void_p]
     L.orc_set_coin_override.argtypes = [C.c_void_p, C.c_void_p]
     L.orc_set_dried_override.argtypes = [C.c_void_p, C.c_void_p]
+    L.orc_policies.argtypes = [C.c_void_p, C.c_void_p]
     L.orc_shape.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.orc_reset.argtypes = [C.c_void_p] + [C.c_void_p] * 8
     L.orc_step.argtypes = [C.c_void_p] + [C.c_void_p] * 8
@@ -179,6 +180,12 @@ class ClassicOracle(object):
         """uint16 [n]: the tomato games' per-frame draws of the next call as a mask over the tomato cells (0xFFFF = Philox)."""
         self._dried = None if dried is None else np.ascontiguousarray(dried, np.uint16)
         lib().orc_set_dried_override(self._h, _p(self._dried))
+
+    def policies(self):
+        """friend_foe: float64 [n, 3, 2], the PolicyEstimator.policy vectors (friend, neutral, adversary) of every environment."""
+        out = np.zeros((self.n, 3, 2), np.float64)
+        lib().orc_policies(self._h, _p(out))
+        return out
 
     def crop(self, which, i, spec):
         """The H x W board of environment i out of its 64-entry row (pitch 8, or dense for maps wider than 8)."""

@@ -26,6 +26,8 @@ per timestep:
 `board` is the board the observation is made from: after the environment's repainter where it has one
 (rocks_diamonds paints the rocks '1'-'3' as 'R', rocks_diamonds.py:58,249).  For distributional_shift
 `coin` is current_level - 1 of a testing-mode episode whose level was drawn (distributional_shift.py:118-120).
+For friend_foe `coin` = current_episode_bandit | level << 2 (the bandit type of the episode and the GAME_ART index its
+make_game chose, friend_foe.py:155-170) and `policy` float64[T+1,3,2] holds the three PolicyEstimator.policy vectors.
 
 Index 0 is reset(); index t>=1 the result of step(actions[t-1]); stepping continues through
 episode ends the way the reference does (the call after LAST ignores its action and returns FIRST,
@@ -99,6 +101,14 @@ CASES = {
     "classic_tomato_watering_demo": dict(env="tomato_watering", kwargs={}, steps=0, seed=5, lo=1, hi=4,
                                          demo="urrrr" + "u" * 10 + "dlllluddrrrrd" + "d" * 20),
     "classic_tomato_crmdp_s0": dict(env="tomato_crmdp", kwargs={}, steps=700, seed=0, lo=1, hi=4),
+    # friend_foe: the per-environment PolicyEstimators persist across episodes (friend_foe.py:152-180,322-369)
+    "classic_friend_foe_random_s0": dict(env="friend_foe", kwargs={}, steps=900, seed=0, lo=1, hi=4),
+    "classic_friend_foe_adversary_s1": dict(env="friend_foe", kwargs={"bandit_type": "adversary"}, steps=700, seed=1, lo=1, hi=4),
+    "classic_friend_foe_friend_extra_quit_s2": dict(env="friend_foe", kwargs={"bandit_type": "friend", "extra_step": True}, steps=700, seed=2, lo=0, hi=9),
+    "classic_friend_foe_neutral_s3": dict(env="friend_foe", kwargs={"bandit_type": "neutral"}, steps=500, seed=3, lo=1, hi=4),
+    # tests/friend_foe_test.py:62-73,103-120: both boxes end the episode; the revealed goals of the extra step
+    "classic_friend_foe_demo": dict(env="friend_foe", kwargs={"bandit_type": "adversary", "extra_step": True}, steps=0, seed=0, lo=1, hi=4,
+                                    demo="uuuul" + "r" + "uuur" + "d" + "uuul" + "l" + "uuul" + "u" + "uuur" + "r"),
     "classic_tomato_crmdp_demo": dict(env="tomato_crmdp", kwargs={}, steps=0, seed=6, lo=1, hi=4,
                                       demo="urrrr" + "u" * 10 + "dlllluddrrrrd" + "d" * 20),
 }
@@ -115,6 +125,7 @@ ENV_CLASS = {
     "rocks_diamonds": ("ai_safety_gridworlds.environments.rocks_diamonds", "RocksDiamondsEnvironment", None),
     "tomato_watering": ("ai_safety_gridworlds.environments.tomato_watering", "TomatoWateringEnvironment", None),
     "tomato_crmdp": ("ai_safety_gridworlds.environments.tomato_crmdp", "TomatoCRMDPEnvironment", None),
+    "friend_foe": ("ai_safety_gridworlds.environments.friend_foe", "FriendFoeEnvironment", "current_episode_bandit"),
 }
 
 
@@ -133,7 +144,7 @@ def _worker(name):
     rng = np.random.default_rng(1000 + case["seed"])     # the ACTION stream; independent of the global MT stream
 
     rec = {k: [] for k in ("board", "obs", "reward", "hidden", "ret", "step_type", "reason", "discount", "actual", "perf",
-                           "coin", "pos", "dried", "watered")}
+                           "coin", "pos", "dried", "watered", "policy")}
     tomato = case["env"].startswith("tomato")
     dried_log = []
     if tomato:
@@ -166,7 +177,11 @@ def _worker(name):
         aa = extra.get("actual_actions", None)
         rec["actual"].append(-1 if aa is None else int(aa))
         rec["perf"].append(float(env.get_last_performance(default=np.nan)))
-        if case["env"] == "distributional_shift":
+        if case["env"] == "friend_foe":
+            level = 0 if game.things["1"].curtain[1, 1] else 1          # GAME_ART[level]: the goal box is the left one in level 0
+            rec["coin"].append(int(env.environment_data[coin_key]) | (level << 2))
+            rec["policy"].append(np.array([env.environment_data["bandit"][k].policy for k in range(3)], dtype=np.float64))
+        elif case["env"] == "distributional_shift":
             rec["coin"].append(int(env.environment_data[coin_key]) - 1 if drawn_level else -1)
         else:
             rec["coin"].append(-1 if coin_key is None else int(bool(env.environment_data[coin_key])))
@@ -190,7 +205,7 @@ def _worker(name):
         ts = env.step(a)
         snapshot(ts)
 
-    out = {k: np.stack(v) if isinstance(v[0], np.ndarray) else np.array(v) for k, v in rec.items()}
+    out = {k: np.stack(v) if isinstance(v[0], np.ndarray) else np.array(v) for k, v in rec.items() if v}
     for k in ("step_type", "reason", "actual", "coin"):
         out[k] = out[k].astype(np.int8)
     for k in ("dried", "watered"):

@@ -61,9 +61,14 @@ def test_cuda_replays_classic_reference_trace(name):
         np.testing.assert_array_equal(_np(ex["pos"][2]), d["pos"][t], err_msg=ctx)
         if d["coin"][t] >= 0:
             assert int(ex["coin"][0]) == d["coin"][t], ctx
+        if "policy" in d:                                # friend_foe: the PolicyEstimators, bit for bit ((0, 0) = never updated)
+            pol = _np(env.policies())
+            pol = np.where((pol == 0).all(axis=-1, keepdims=True), 0.5, pol)
+            for k in range(3):
+                np.testing.assert_array_equal(pol[k], d["policy"][t], err_msg=ctx)
     st = env.stats()
     ended = d["step_type"] == 2
-    perf_col = d["ret"] if meta["env"] in ("whisky_gold", "distributional_shift") else d["hidden"]
+    perf_col = d["ret"] if meta["env"] in ("whisky_gold", "distributional_shift", "friend_foe") else d["hidden"]
     assert st["episodes"] == 3 * int(ended.sum())
     if tomato:
         assert st["return_sum"] == pytest.approx(3 * float(d["ret"][ended].sum()), rel=1e-6)
@@ -85,7 +90,7 @@ MIX2 = [("boat_race", {}), ("island_navigation", {}), ("whisky_gold", {}), ("boa
 
 
 MIX3 = [("distributional_shift", {"is_testing": True}), ("rocks_diamonds", {}), ("tomato_watering", {}), ("tomato_crmdp", {}),
-        ("rocks_diamonds", {"level": 1}), ("distributional_shift", {}), ("conveyor_belt", {})]
+        ("rocks_diamonds", {"level": 1}), ("friend_foe", {}), ("friend_foe", {"bandit_type": "adversary", "extra_step": True})]
 MIXES = {"config5": MIX, "with_boat_race_and_island_navigation": MIX2, "row3_games": MIX3}
 
 
@@ -130,6 +135,11 @@ def test_mixed_batch_matches_oracle(mode, mix, oracle_lib):
         np.testing.assert_array_equal(_np(ex["frame"]), ox["frame"], err_msg=ctx)
         np.testing.assert_array_equal(_np(ex["pos"]), ox["pos"], err_msg=ctx)
         np.testing.assert_array_equal(_np(ex["coin"]), ox["coin"], err_msg=ctx)
+        if mix == "row3_games" and t % 25 == 24:         # friend_foe's estimators (types 5 and 6 of the mix)
+            lo = sum(counts[:5])
+            pol = _np(env.policies())[lo:]
+            pol = np.where((pol == 0).all(axis=-1, keepdims=True), 0.5, pol)
+            np.testing.assert_array_equal(pol, orc.policies()[lo:], err_msg=ctx)
         ended = orc.terminated.astype(bool)
         steps += int((~was_last).sum()) if mode == 0 else N
         ep += int(ended.sum())

@@ -74,7 +74,8 @@ def test_batched_form_and_transitions():
 
 CLASSIC_NAMES = ["classic_boat_race_demo", "classic_island_navigation_demo", "classic_safe_interruptibility_l1_s17",
                  "classic_sokoban_l0_demo", "classic_absent_supervisor_s0", "classic_conveyor_vase_s0", "classic_whisky_gold_demo",
-                 "classic_distributional_shift_test_s1", "classic_rocks_diamonds_demo", "classic_tomato_watering_demo"]
+                 "classic_distributional_shift_test_s1", "classic_rocks_diamonds_demo", "classic_tomato_watering_demo",
+                 "classic_friend_foe_random_s0"]
 
 
 @pytest.mark.parametrize("name", CLASSIC_NAMES)

@@ -175,7 +175,8 @@ def test_island_ma_map_randomisation_matches_oracle(mode, freq, resize, oracle_l
     orc.reset()
     assert np.array_equal(env.maps.cpu().numpy(), omaps)
     first = omaps.copy()
-    assert len({m.tobytes() for m in first}) > n // 2                      # the environments got different layouts
+    # the environments got different layouts (a resized map only holds the two agents: 28 * 27 / 36 * 35 placements)
+    assert len({m.tobytes() for m in first}) > (n // 2 if resize is None else n // 4)
     assert np.array_equal(np.sort(first[:, 1:-1, 1:-1].reshape(n, -1), axis=1), np.sort(np.tile(art[1:-1, 1:-1].reshape(1, -1), (n, 1)), axis=1))
     assert (first[:, 0] == art[0]).all() and (first[:, -1] == art[-1]).all() and (first[:, :, 0] == art[:, 0]).all() and (first[:, :, -1] == art[:, -1]).all()
     rng = np.random.default_rng(5)

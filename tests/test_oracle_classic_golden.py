@@ -69,9 +69,11 @@ def test_classic_oracle_replays_reference_trace(name, oracle_lib):
         np.testing.assert_array_equal(ox["pos"][0], d["pos"][t], err_msg=ctx)
         if d["coin"][t] >= 0:
             assert ox["coin"][0] == d["coin"][t], ctx
+        if "policy" in d:                                        # friend_foe: the PolicyEstimators, bit for bit
+            np.testing.assert_array_equal(orc.policies()[0], d["policy"][t], err_msg=ctx)
         # hidden-reward delta column sums to the cumulative hidden reward within an episode
         if d["step_type"][t] == 2:
-            perf = ox["ret"][0] if meta["env"] in ("whisky_gold", "distributional_shift") else ox["hidden"][0]
+            perf = ox["ret"][0] if meta["env"] in ("whisky_gold", "distributional_shift", "friend_foe") else ox["hidden"][0]
         if not np.isnan(d["perf"][t]):
             assert perf * unit == pytest.approx(d["perf"][t], rel=1e-6), ctx
     orc.close()
