@@ -42,6 +42,10 @@ WORKLOADS = {
                       "original suite mixed batch, equal fifths: safe_interruptibility L1 p=0.5, side_effects_sokoban L0, "
                       "absent_supervisor, conveyor_belt vase, whisky_gold (SURVEY 8d config 5)",
                       "padded board u8[8x8] + reward/hidden f32[2] + terminated/step_type/reason/actual"),
+    "classic_row3": ("classic_mixed", {"row3": True}, 1 << 20,
+                     "original suite, SURVEY 8f row 3 games in one mixed batch, equal sevenths: distributional_shift (testing mode), "
+                     "rocks_diamonds L0, tomato_watering, tomato_crmdp, rocks_diamonds L1, friend_foe, friend_foe adversary + extra step",
+                     "64-byte board row u8 + reward/hidden f32[2] + terminated/step_type/reason/actual"),
     "firemaker_ex_ma": ("firemaker_ex_ma", {}, 1 << 18,
                         "firemaker_ex_ma level 0, 3 agents (2 workers + supervisor), shuffled sub-step order, Philox fire draws "
                         "(SURVEY 8d config 4); one env-step = one PARALLEL step = 3 engine frames",
@@ -58,6 +62,8 @@ WORKLOADS = {
                                         "(+ the environment's own map u8[48] read per step)"),
 }
 CLASSIC_TYPES = ["safe_interruptibility", "side_effects_sokoban", "absent_supervisor", "conveyor_belt", "whisky_gold"]
+ROW3_TYPES = [("distributional_shift", {"is_testing": True}), ("rocks_diamonds", {}), ("tomato_watering", {}), ("tomato_crmdp", {}),
+              ("rocks_diamonds", {"level": 1}), ("friend_foe", {}), ("friend_foe", {"bandit_type": "adversary", "extra_step": True})]
 WORKLOAD_TEXT = WORKLOADS["island_navigation_ex"][3]
 OUTPUTS_TEXT = WORKLOADS["island_navigation_ex"][4]
 METRIC = "env_steps_per_sec"
@@ -273,8 +279,12 @@ def run_ours(args):
         lo_hi = {}
     elif classic:
         from ai_safety_gridworlds_b200.classic_env import ClassicVectorEnv
-        specs = [make_spec(t, autoreset_mode=1) for t in CLASSIC_TYPES]
-        counts = [n // 5] * 4 + [n - 4 * (n // 5)]
+        if ENV_KWARGS.get("row3"):
+            specs = [make_spec(t, autoreset_mode=1, **kw) for t, kw in ROW3_TYPES]
+        else:
+            specs = [make_spec(t, autoreset_mode=1) for t in CLASSIC_TYPES]
+        k = len(specs)
+        counts = [n // k] * (k - 1) + [n - (k - 1) * (n // k)]
         spec = specs[0]
 
         def make_env(value_board):
@@ -392,7 +402,7 @@ def run_ours(args):
                 "bytes_per_env_step": bytes_per, "state_bytes_per_env": 192 if island_ma else 160 if firemaker else env.state_words * 16,
                 "autoreset": "same-step", "action_ring": ACTION_RING}),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": load_traffic(n), "peak_source": peak_src, "kernel": ("gw_ima_kernel<%s>" % ("true" if ENV_KWARGS.get("map_randomization_frequency") else "false")) if island_ma else "gw_fm_kernel" if firemaker else "gw_cls_step_kernel" if classic else "gw_step_tma_kernel<%d>" % (0 if ENV_NAME == "island_navigation_ex" else 2),
+                         "traffic": load_traffic(n), "peak_source": peak_src, "kernel": ("gw_ima_kernel<%s>" % ("true" if ENV_KWARGS.get("map_randomization_frequency") else "false")) if island_ma else "gw_fm_kernel" if firemaker else ("gw_cls_step_kernel<%s>" % ("true" if ENV_KWARGS.get("row3") else "false")) if classic else "gw_step_tma_kernel<%d>" % (0 if ENV_NAME == "island_navigation_ex" else 2),
                          "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": bytes_per * n},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                     "steps": e2e_steps,
