@@ -265,7 +265,12 @@ void gw_destroy(GwHandle h);
 /* A MIXED batch of classic-suite environments (BASELINE config 5): environments
  * [sum(counts[:t]), sum(counts[:t+1])) are of type cfgs[t].  n_types may be 1.  Observation tensors
  * use the fixed padded shape 8 x 8 (GW_CLASSIC_SIDE; 64 bytes per board, each board sits top-left,
- * padding bytes are 0); obs.cube must be NULL; reward rows have 2 columns (GwClassicRewardColumn);
+ * padding bytes are 0; maps wider than 8 fill their row densely, see GW_CLASSIC_SIDE); obs.cube must
+ * be NULL; reward rows have 2 columns (GwClassicRewardColumn);
+ * The state blob of a mixed batch is plane-major: W planes of ceil32(N) 16-byte words, W = the largest
+ * gw_state_words() of its types (1, or 4 when a friend_foe type is present: planes 1-3 hold that game's three
+ * policy estimators as two doubles each and are left untouched by every other type and by gw_reset, so
+ * that they persist across episodes; a zeroed plane reads as the initial estimate (0.5, 0.5)).
  * actions use GwClassicAction.  `seed` keys the Philox stream of the per-episode draws
  * (should_interrupt, supervisor): counter = (global env index, number of the gw_reset/gw_step call
  * that starts the episode, counted per handle from 1).
