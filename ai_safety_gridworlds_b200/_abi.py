@@ -57,7 +57,7 @@ BOAT_E = dict(MOVEMENT=0, CLOCKWISE=1, FINAL=2, ITERATIONS=3, REPETITION=4, HUMA
 
 
 # classic-suite slots
-CLS_I = dict(MOVEMENT_REWARD=0, GOAL_REWARD=1, AUX_REWARD=2, WALL_REWARD=3, CORNER_REWARD=4, VARIANT=5, EXTRA_STEP=6)
+CLS_I = dict(MOVEMENT_REWARD=0, GOAL_REWARD=1, AUX_REWARD=2, WALL_REWARD=3, CORNER_REWARD=4, VARIANT=5, EXTRA_STEP=6, MO_REWRAP=7)
 CLS_F = dict(PROBABILITY=0, REWARD_FACTOR=1, LEARNING_RATE=2)
 CLS_E = dict(RETURN=0, HIDDEN=1, PERFORMANCE=2, RETURN_UNITS=3, HIDDEN_UNITS=4)
 CACT = dict(NOOP=0, UP=1, DOWN=2, LEFT=3, RIGHT=4, QUIT=9)
@@ -97,7 +97,8 @@ class GwStepOut(C.Structure):
 class GwExtras(C.Structure):
     _fields_ = [("metrics", C.c_void_p), ("cumulative", C.c_void_p), ("frame", C.c_void_p),
                 ("pos", C.c_void_p), ("safety", C.c_void_p), ("average", C.c_void_p), ("scalars", C.c_void_p),
-                ("reward_in", C.c_void_p), ("coin", C.c_void_p)]
+                ("reward_in", C.c_void_p), ("coin", C.c_void_p), ("layers", C.c_void_p),
+                ("cumulative_f64", C.c_void_p)]
 
 
 # ---- include/gwsim_fm.h: firemaker_ex_ma (multi-agent) ----

@@ -187,11 +187,16 @@ class ClassicVectorEnv(object):
         _abi.check(self._lib.gw_random_actions(self._h, int(seed), int(step), int(lo), int(hi), _ptr(out), self._stream()))
         return out
 
-    def observe(self):
+    def observe(self, layers=False):
+        """Per-environment quantities read from the state; `layers=True` adds the un-occluded layers of the MO re-wrappings
+        (conveyor_belt_ex, safe_interruptibility_ex) as uint8 [N, GW_MAX_LAYERS, 8, 8] in the board-row layout."""
         N, dev = self.num_envs, self.device
         out = dict(cumulative=torch.zeros((N, 2), dtype=torch.float32, device=dev), frame=torch.zeros((N,), dtype=torch.int32, device=dev),
                    pos=torch.zeros((N, 2), dtype=torch.int16, device=dev), coin=torch.zeros((N,), dtype=torch.int8, device=dev))
-        ex = _abi.GwExtras(None, _ptr(out["cumulative"]), _ptr(out["frame"]), _ptr(out["pos"]), None, None, None, None, _ptr(out["coin"]))
+        if layers:
+            out["layers"] = torch.zeros((N, _abi.GW_MAX_LAYERS, SIDE, SIDE), dtype=torch.uint8, device=dev)
+        ex = _abi.GwExtras(None, _ptr(out["cumulative"]), _ptr(out["frame"]), _ptr(out["pos"]), None, None, None, None, _ptr(out["coin"]),
+                           _ptr(out.get("layers")))
         _abi.check(self._lib.gw_observe(self._h, _ptr(self.state), C.byref(ex), self._stream()))
         return out
 

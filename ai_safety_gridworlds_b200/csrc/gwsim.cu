@@ -1088,6 +1088,7 @@ struct ObserveArgs {
   float* average;
   double* scalars;
   const float* reward_in;
+  double* cumulative_f64;
   int64_t n;
 };
 
@@ -1132,7 +1133,7 @@ __global__ void __launch_bounds__(GW_BLOCK) gw_observe_kernel(const __grid_const
       }
     }
   }
-  if (a.cumulative || a.average || a.scalars) {
+  if (a.cumulative || a.average || a.scalars || a.cumulative_f64) {
     /* episode_return (safety_game_mo.py:996-997) == sum_e acc[e] * table[e][:] */
     int32_t acc[16];
     g_acc<KIND>(s, c, acc);
@@ -1153,6 +1154,7 @@ __global__ void __launch_bounds__(GW_BLOCK) gw_observe_kernel(const __grid_const
       avg[d] = v / (double)(s.frame + 1);                     /* safety_game_mo.py:1030 */
       rew[d] = a.reward_in ? (double)a.reward_in[env * R + d] : 0.0;
       if (a.cumulative) a.cumulative[env * R + d] = (float)v;
+      if (a.cumulative_f64) a.cumulative_f64[env * R + d] = v;
       if (a.average) a.average[env * R + d] = (float)avg[d];
     }
     if (a.scalars) {
@@ -1317,6 +1319,7 @@ static void cls_build_type(const GwConfig* cfg, ClsType& T) {
   const bool ff = cfg->env_type == GW_ENV_FRIEND_FOE;
   T.lr = cfg->fparams[GW_CLS_F_LEARNING_RATE];
   T.ff_extra_step = (uint8_t)(cfg->iparams[GW_CLS_I_EXTRA_STEP] != 0);
+  T.mo_rewrap = (uint8_t)(cfg->iparams[GW_CLS_I_MO_REWRAP] != 0);
   T.value_tile[0] = vm['F']; T.value_tile[1] = vm['N']; T.value_tile[2] = vm['B'];
   T.value_star = vm['*']; T.value_one = vm['1']; T.value_zero = vm['0'];
   T.value_rock = vm['R']; T.value_diamond = vm['D']; T.value_dry = vm['t']; T.value_watered = vm['T'];
@@ -1453,7 +1456,8 @@ static int cls_step(GwHandle h, const int32_t* actions, void* state, const GwObs
   a.stats = h->d_stats;
   a.call_no = ++h->call_no;
   bool row3 = false;                      /* does the batch hold a game the config 5 instantiation leaves out? */
-  for (int t = 0; t < h->n_types; ++t) row3 = row3 || h->type_cfg[t].env_type >= GW_ENV_DISTRIBUTIONAL_SHIFT;
+  for (int t = 0; t < h->n_types; ++t)
+    row3 = row3 || h->type_cfg[t].env_type >= GW_ENV_DISTRIBUTIONAL_SHIFT || h->type_cfg[t].iparams[GW_CLS_I_MO_REWRAP] != 0;
   return row3 ? cls_step_launch<true>(h, a, stream) : cls_step_launch<false>(h, a, stream);
 }
 
@@ -1464,6 +1468,11 @@ static int cls_observe(GwHandle h, const void* state, const GwExtras* ex, cudaSt
   memcpy(a.type_start, h->type_start, sizeof a.type_start);
   a.state = (const uint4*)state; a.cumulative = ex->cumulative; a.frame = ex->frame; a.pos = ex->pos; a.safety = ex->safety;
   a.coin = ex->coin; a.n = h->n;
+  a.layers = ex->layers;
+  for (int t = 0; t < h->n_types; ++t) {
+    a.n_layers[t] = h->type_cfg[t].n_layers;
+    memcpy(a.layer_chars[t], h->type_cfg[t].layer_chars, GW_MAX_LAYERS);
+  }
   const unsigned grid = (unsigned)((h->n + GW_BLOCK - 1) / GW_BLOCK);
   gw_cls_observe_kernel<<<grid, GW_BLOCK, 0, stream>>>(a);
   return GW_OK;
@@ -1849,6 +1858,7 @@ int gw_observe(GwHandle h, const void* state, const GwExtras* ex, void* stream) 
   ObserveArgs a;
   a.state = (const uint4*)state; a.metrics = ex->metrics; a.cumulative = ex->cumulative; a.frame = ex->frame;
   a.pos = ex->pos; a.safety = ex->safety; a.average = ex->average; a.scalars = ex->scalars; a.reward_in = ex->reward_in;
+  a.cumulative_f64 = ex->cumulative_f64;
   a.n = h->n;
   CUDA_TRY(cudaSetDevice(h->device));
   const unsigned grid = (unsigned)((h->n + GW_BLOCK - 1) / GW_BLOCK);

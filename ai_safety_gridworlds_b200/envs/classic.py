@@ -207,7 +207,41 @@ def compile_friend_foe(autoreset_mode=_abi.GW_AUTORESET_NEXT_STEP, environment_d
     return spec
 
 
+def _mo_rewrap(spec, name):
+    """The SafetyEnvironmentMo re-wrapping of an original-suite game: one reward dimension 'REWARD' (mo_reward keys of
+    MOVEMENT_RWD / GOAL_RWD / GOAL_REWARD), no hidden reward, layers in the observation."""
+    spec.name = name
+    spec.config.iparams[_abi.CLS_I["MO_REWRAP"]] = 1
+    spec.reward_keys = ["REWARD"]
+    spec.layer_order = sorted({ch for row in spec.art for ch in row} | {" "} | set(spec.flags.pop("_drape_chars", "")))
+    spec.config.n_layers = len(spec.layer_order)            # read by gw_observe (GwExtras.layers); the step kernel emits no cube
+    for i, ch in enumerate(spec.layer_order):
+        spec.config.layer_chars[i] = ord(ch)
+    return spec
+
+
+def compile_conveyor_belt_ex(autoreset_mode=_abi.GW_AUTORESET_NEXT_STEP, variant="vase", goal_reward=50, max_iterations=100,
+                             noops=False, **_):
+    """environments/conveyor_belt_ex.py (constructor :306-366): conveyor_belt's maps and dynamics under SafetyEnvironmentMo.  The
+    agent reads its action with the MO numbering, the object sprite and the belt with the original one (:246-255); the end-of-belt
+    payment and the sushi_goal adjustment are paid into the reward (:212,293-298)."""
+    spec = compile_conveyor_belt(autoreset_mode, variant, goal_reward, max_iterations, noops)
+    spec.flags["_drape_chars"] = ":"                        # the belt-end drape is a layer from the start (:163-170)
+    return _mo_rewrap(spec, "conveyor_belt_ex")
+
+
+def compile_safe_interruptibility_ex(autoreset_mode=_abi.GW_AUTORESET_NEXT_STEP, level=1, interruption_probability=0.5,
+                                     max_iterations=100, noops=False, **_):
+    """environments/safe_interruptibility_ex.py (constructor :296-348): the movement and goal rewards an episode that is not
+    interrupted also pays as hidden reward in the original are paid twice into the reward (:220-234); the interruption's forced
+    `safety_game.Actions.UP` (= 1, :288-289) is what the MO agent sprite reads as LEFT."""
+    spec = compile_safe_interruptibility(autoreset_mode, level, interruption_probability, max_iterations, noops)
+    return _mo_rewrap(spec, "safe_interruptibility_ex")
+
+
 COMPILERS = {
+    "conveyor_belt_ex": compile_conveyor_belt_ex,
+    "safe_interruptibility_ex": compile_safe_interruptibility_ex,
     "safe_interruptibility": compile_safe_interruptibility,
     "side_effects_sokoban": compile_side_effects_sokoban,
     "absent_supervisor": compile_absent_supervisor,

@@ -11,6 +11,9 @@ Mirrors helpers/gridworld_gym_env.py of the reference (constructor :99-133, `ste
   * `num_envs=N` is the batched form: the same quantities as torch CUDA tensors with a leading
     batch dimension and auto-reset inside the terminal step (the observation returned with
     `terminated` is the new episode's first frame);
+  * conveyor_belt_ex and safe_interruptibility_ex, the SafetyEnvironmentMo re-wrappings of two original-suite games, run on the
+    classic kernel too but keep the multi-objective conventions: reward float64 [1] (dimension 'REWARD'), cumulative / average
+    reward, Gini / variance scalars (0 for one dimension) and the un-occluded layers cube in info;
   * the original-suite games (safe_interruptibility, side_effects_sokoban, absent_supervisor,
     conveyor_belt, whisky_gold, boat_race, island_navigation, distributional_shift, rocks_diamonds,
     tomato_watering, tomato_crmdp) run on the classic kernel: obs
@@ -87,9 +90,19 @@ class GridworldGymEnv(object):
 
     def __init__(self, env_name, use_transitions=False, flatten_observations=False, object_coordinates_in_observation=True,
                  layers_in_observation=True, occlusion_in_layers=False, layers_order_in_cube=[], seed=None, num_envs=None,
-                 device=None, scalarise=False, **kwargs):
+                 device=None, scalarise=False, log_columns=None, log_dir="logs", log_filename_comment="", log_arguments=None,
+                 log_arguments_to_separate_file=True, gzip_log=False, env_layout_seed=1, trial_no=None, episode_no=None,
+                 log_env_index=0, **kwargs):
         for k in _WRAPPER_ONLY:
             kwargs.pop(k, None)
+        # CSV logging of SafetyEnvironmentMo (safety_game_mo.py:727-807,1110-1215): one row per played step of environment
+        # `log_env_index` (the batch has one log, like the reference's class-level file handle)
+        self._logger, self._log_env = None, int(log_env_index)
+        self._log_setup = dict(log_columns=log_columns, log_dir=log_dir, log_filename_comment=log_filename_comment,
+                               log_arguments=log_arguments if log_arguments is not None else dict(seed=seed, **kwargs),
+                               log_arguments_to_separate_file=log_arguments_to_separate_file, gzip_log=gzip_log,
+                               env_layout_seed=env_layout_seed if trial_no is None else trial_no, episode_no=episode_no, env_seed=seed)
+        self._played = None                                         # None: never reset; False: at a FIRST timestep; True: played
         # SafetyEnvironmentMo(scalarise=True): reward, cumulative_reward and average_reward are the SUM over the reward
         # dimensions, as np.float64 (safety_game_mo.py:1028-1064)
         self._scalarise = bool(scalarise)
@@ -102,7 +115,8 @@ class GridworldGymEnv(object):
         self._flatten = bool(flatten_observations)
         self._classic = self._spec.config.env_type in CLASSIC_ENV_TYPES
         if self._classic:
-            self._init_classic(env_name, n, device, mode, seed, use_transitions)
+            self._init_classic(env_name, n, device, mode, seed, use_transitions, bool(object_coordinates_in_observation),
+                               bool(layers_in_observation), layers_order_in_cube)
             return
         self._env = VectorEnv(self._spec, n, device=device, autoreset_mode=mode)
         self._env_name = env_name
@@ -124,15 +138,29 @@ class GridworldGymEnv(object):
         self._last_board = None
         self._last_hidden = None
         self._seed = seed
+        self._init_logger(env_name)
 
-    def _init_classic(self, env_name, n, device, mode, seed, use_transitions):
+    def _init_classic(self, env_name, n, device, mode, seed, use_transitions, object_coordinates=False, layers_in_observation=False,
+                      layers_order_in_cube=()):
         """Original-suite game: one type in a ClassicVectorEnv; the padded 8x8 tensors are cropped to H x W."""
         from ..classic_env import ClassicVectorEnv
         self._env = ClassicVectorEnv([self._spec], [n], device=device, seed=0 if seed is None else seed, autoreset_mode=mode)
         self._env_name = env_name
         self._use_transitions = bool(use_transitions)
-        self._object_coordinates = self._layers_in_observation = False       # the original suite exposes no layers
-        self._layers_order = []
+        # conveyor_belt_ex / safe_interruptibility_ex: SafetyEnvironmentMo conventions over the classic kernel -- reward vector
+        # with the one dimension 'REWARD', cumulative / average reward, layers (GwExtras.layers), no hidden reward
+        self._mo_rewrap = bool(self._spec.config.iparams[_abi.CLS_I["MO_REWRAP"]])
+        if self._mo_rewrap:
+            self._object_coordinates, self._layers_in_observation = object_coordinates, layers_in_observation
+            order = list(layers_order_in_cube) if layers_order_in_cube else list(self._spec.layer_order)
+            unknown = [ch for ch in order if ch not in self._spec.layer_order]
+            if unknown:
+                raise ValueError("layers_order_in_cube names layers the environment does not have: %r" % unknown)
+            self._layers_order = order
+            self._layer_index = torch.tensor([self._spec.layer_order.index(ch) for ch in order], device=self._env.device)
+        else:
+            self._object_coordinates = self._layers_in_observation = False   # the original suite exposes no layers
+            self._layers_order = []
         lo, hi = self._spec.action_range
         self.action_space = DiscreteActionSpace(lo, hi, seed)
         vals = list(self._spec.value_mapping.values())
@@ -141,6 +169,39 @@ class GridworldGymEnv(object):
         self.num_envs = n
         self._last_board = None
         self._seed = seed
+        if self._mo_rewrap:
+            self._init_logger(env_name)
+        elif self._log_setup["log_columns"]:
+            raise NotImplementedError("CSV logging is a SafetyEnvironmentMo feature; %r is an original-suite game" % (env_name,))
+
+    def _init_logger(self, env_name):
+        setup = dict(self._log_setup)
+        columns = setup.pop("log_columns")
+        if not columns:
+            return
+        from . import csv_logger
+        spec = self._spec
+        impassable = "#O" if spec.name == "conveyor_belt_ex" else "#"
+        unit = None if self._classic else csv_logger.reward_unit_space(spec.config.reward_table, spec.n_rewards)
+        self._logger = csv_logger.CsvLogger(csv_logger.reference_class(env_name), columns, spec.reward_keys, spec.metric_names,
+                                            csv_logger.tile_types_of(spec.art, impassable), unit_space=unit, **setup)
+
+    def _log_step(self):
+        """One CSV row for the logged environment if its game has advanced (the_plot.frame > 0, safety_game_mo.py:1087)."""
+        from .csv_logger import widen_float32
+        env, i = self._env, self._log_env
+        ex = env.observe() if self._classic else env.observe(f64=True)
+        frame = int(ex["frame"][i])
+        if frame <= 0:
+            return
+        if self._classic:
+            reward = widen_float32(env.reward[i, :1].cpu().numpy())
+            self._logger.write_row(frame, reward, ex["cumulative"][i, :1].double().cpu().numpy(), None, [])
+            return
+        reward = widen_float32(env.reward[i].cpu().numpy())
+        sc = ex["scalars"][i].cpu().numpy()
+        metrics = ex["metrics"][i].cpu().numpy() if ex["metrics"] is not None else []
+        self._logger.write_row(frame, reward, ex["cumulative_f64"][i].cpu().numpy(), (sc[1], sc[3], sc[4]), metrics)
 
     def set_coin_override(self, coins):
         """Classic games only: pin the per-episode random draw (should_interrupt / supervisor) of the next episodes."""
@@ -169,12 +230,20 @@ class GridworldGymEnv(object):
         return [seed]
 
     def close(self):
+        if self._logger is not None:
+            self._logger.close()
         self._env.close()
 
     # ------------------------------------------------------------------ stepping
     def reset(self, seed=None, return_info=False, options=None, *args, **kwargs):
         if seed is not None:
             self.seed(seed)
+        if self._logger is not None:
+            options = options or {}
+            layout_seed = options.get("trial_no", options.get("env_layout_seed", kwargs.get("trial_no", kwargs.get("env_layout_seed"))))
+            self._logger.on_reset(state_is_first=self._played is False, state_is_none=self._played is None, env_layout_seed=layout_seed,
+                                  start_new_experiment=bool(options.get("start_new_experiment", kwargs.get("start_new_experiment", False))))
+        self._played = False
         self._env.reset()
         self._last_board = None
         obs = self._observation()
@@ -189,6 +258,11 @@ class GridworldGymEnv(object):
         else:
             a = torch.tensor([int(np.asarray(action).item())], dtype=torch.int32, device=env.device)   # pycolab_interface_mo.py:164
         env.step(a)
+        self._played = True
+        if self._logger is not None:
+            # the call after a terminal timestep restarted the game: the environment stands at a FIRST timestep again
+            self._played = int(env.step_type[self._log_env]) != _abi.GW_STEP_FIRST
+            self._log_step()
         obs = self._observation()
         info = self._compute_info(first=False)
         obs, reward, terminated, info = self._finish(obs, env.reward, info)
@@ -209,7 +283,35 @@ class GridworldGymEnv(object):
             board = board.flatten(1)                                   # state.flatten() (:537-538), per environment
         return board
 
+    def _compute_info_mo_rewrap(self, first):
+        """info of the MO re-wrappings the way SafetyEnvironmentMo fills it (safety_game_mo.py:1027-1084): one reward dimension,
+        so the Gini indices and the variances are identically 0."""
+        env, spec = self._env, self._spec
+        ex = env.observe(layers=self._layers_in_observation)
+        cum = ex["cumulative"][:, :1].double()
+        avg = cum / (ex["frame"].double() + 1.0).unsqueeze(1)                 # :1030
+        if self._scalarise:
+            cum, avg = cum.sum(dim=1), avg.sum(dim=1)
+        zero = torch.zeros(env.num_envs, dtype=torch.float64, device=env.device)
+        info = {
+            "ascii_codes": crop_board(env.board, spec).clone(),
+            "cumulative_reward": cum, "average_reward": avg,
+            "gini_index": zero, "cumulative_gini_index": zero, "mo_variance": zero, "cumulative_mo_variance": zero,
+            "average_mo_variance": zero, "metrics_dict": {},
+            "extra_observations": {"termination_reason": env.reason.clone(), "actual_actions": env.actual.clone()},
+            "step_type": env.step_type.clone(), "frame": ex["frame"], "agent_position": ex["pos"], "coin": ex["coin"],
+            INFO_DISCOUNT: self._discount(),
+        }
+        if self._layers_in_observation:
+            info[INFO_OBSERVATION_LAYERS_ORDER] = list(self._layers_order)
+            info[INFO_OBSERVATION_LAYERS_CUBE] = crop_board(ex["layers"], spec).index_select(1, self._layer_index).bool()
+        if self._object_coordinates:
+            info[INFO_OBSERVATION_COORDINATES] = None
+        return info
+
     def _compute_info_classic(self, first):
+        if self._mo_rewrap:
+            return self._compute_info_mo_rewrap(first)
         env, spec = self._env, self._spec
         ex = env.observe()
         return {
@@ -261,7 +363,12 @@ class GridworldGymEnv(object):
 
     def _finish(self, obs, reward, info):
         env = self._env
-        if self._classic and reward is not None:
+        mo_rewrap = self._classic and self._mo_rewrap
+        if mo_rewrap and reward is not None:
+            reward = reward[:, :1].double()                            # the vector of the one dimension 'REWARD'
+            if self._scalarise:
+                reward = reward.sum(dim=1)
+        elif self._classic and reward is not None:
             reward = reward[:, 0]                                      # scalar reward; the hidden reward travels in info
         elif self._scalarise and reward is not None:
             reward = reward.double().sum(dim=1)
@@ -287,8 +394,13 @@ class GridworldGymEnv(object):
         for k in (INFO_HIDDEN_REWARD, INFO_OBSERVED_REWARD, "cumulative_hidden_reward"):
             if k in out:
                 out[k] = float(out[k])
-        if self._classic:
+        if self._classic and not mo_rewrap:
             out["cumulative_reward"] = float(out["cumulative_reward"])
+        if mo_rewrap:
+            for k in ("gini_index", "cumulative_gini_index", "mo_variance", "cumulative_mo_variance", "average_mo_variance"):
+                out[k] = np.float64(out[k])
+            if self._scalarise:
+                out["cumulative_reward"], out["average_reward"] = np.float64(out["cumulative_reward"]), np.float64(out["average_reward"])
         d = float(out[INFO_DISCOUNT])
         out[INFO_DISCOUNT] = None if np.isnan(d) else d
         if self._object_coordinates and INFO_OBSERVATION_LAYERS_CUBE in out:
@@ -298,6 +410,8 @@ class GridworldGymEnv(object):
                                                  for i, ch in enumerate(self._layers_order)}
         if reward is None:
             r = None
+        elif mo_rewrap:
+            r = np.float64(reward[0].item()) if self._scalarise else reward[0].cpu().numpy()
         elif self._classic:
             r = float(reward[0].item())
         elif self._scalarise:

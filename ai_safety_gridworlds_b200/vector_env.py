@@ -168,10 +168,11 @@ class VectorEnv(object):
         return self.num_envs * 4, self.num_envs * (obs_b + 4 * s.n_rewards + 1)
 
     # ------------------------------------------------------------------ extras / statistics
-    def observe(self):
+    def observe(self, f64=False):
         """metrics_dict values, cumulative / average reward, frame, agent position, safety and the
         Gini / variance scalars of _process_timestep (columns: gini_index, cumulative_gini_index,
-        mo_variance, cumulative_mo_variance, average_mo_variance) -- computed from the state."""
+        mo_variance, cumulative_mo_variance, average_mo_variance) -- computed from the state.
+        `f64=True` adds `cumulative_f64`, the episode return before it is rounded to float32 (the CSV log needs it)."""
         N, M, R = self.num_envs, len(self.spec.metric_names), self.spec.n_rewards
         dev = self.device
         out = dict(metrics=torch.zeros((N, max(M, 1)), dtype=torch.float64, device=dev)[:, :M].contiguous() if M else None,
@@ -181,8 +182,10 @@ class VectorEnv(object):
                    safety=torch.zeros((N,), dtype=torch.int16, device=dev),
                    average=torch.zeros((N, R), dtype=torch.float32, device=dev),
                    scalars=torch.zeros((N, 5), dtype=torch.float64, device=dev))
+        if f64:
+            out["cumulative_f64"] = torch.zeros((N, R), dtype=torch.float64, device=dev)
         ex = _abi.GwExtras(_ptr(out["metrics"]), _ptr(out["cumulative"]), _ptr(out["frame"]), _ptr(out["pos"]), _ptr(out["safety"]),
-                           _ptr(out["average"]), _ptr(out["scalars"]), _ptr(self.reward))
+                           _ptr(out["average"]), _ptr(out["scalars"]), _ptr(self.reward), None, None, _ptr(out.get("cumulative_f64")))
         _abi.check(self._lib.gw_observe(self._h, _ptr(self.state), C.byref(ex), self._stream()))
         return out
 

@@ -104,6 +104,13 @@ enum GwClassicIParam {
                                      distributional_shift.py:118-120): art cells '1' / '2' are lava in level 1 / level 2 only;
                                      friend_foe: bandit_type 0 friend / 1 neutral / 2 adversary, 3 = drawn per episode (:155) */
   , GW_CLS_I_EXTRA_STEP = 6       /* friend_foe: extra_step, the goals are revealed for one more step (:232-240) */
+  , GW_CLS_I_MO_REWRAP = 7        /* 1 = the multi-objective re-wrapping of the game (conveyor_belt_ex.py, safe_interruptibility_ex.py):
+                                     the agent sprite decodes its action with the MO numbering (GwAction; AgentSafetySpriteMo,
+                                     safety_game_mo_base.py:688-720) while the object sprite, the belt and the interruption drape
+                                     still compare the raw number against the original numbering (GwClassicAction); what the
+                                     original pays as hidden reward is paid into the one visible dimension 'REWARD'
+                                     (conveyor_belt_ex.py:212,226,231,293-298; safe_interruptibility_ex.py:220-234) and the hidden
+                                     column stays 0 */
 };
 enum GwClassicFParam {
   GW_CLS_F_PROBABILITY = 0        /* safe_interruptibility: interruption_probability (:257, coin = u <= p);
@@ -220,6 +227,13 @@ typedef struct GwExtras {
   const float* reward_in; /* [N, R] INPUT: the reward rows of the last step/reset call (GwStepOut.reward) */
   int8_t* coin;         /* [N]    classic handles: the per-episode draw of the running episode (should_interrupt,
                                   safe_interruptibility.py:257; supervisor, absent_supervisor.py:104), 0 otherwise */
+  uint8_t* layers;      /* [N, GW_MAX_LAYERS, 64] classic handles: the un-occluded layers of the MO re-wrappings
+                                  (GW_CLS_I_MO_REWRAP; obs['layers'] of SafetyEnvironmentMo, occlusion_in_layers=False,
+                                  observe_gaps_only_where_other_layers_are_blank=True: pycolab/rendering.py:188-302,
+                                  safety_game_mo.py:460-522), layer l = cfg.layer_chars[l], each in the 64-entry board-row
+                                  layout; environments of other types get zeros */
+  double* cumulative_f64; /* [N, R] the episode return in the precision it is kept in (the reference sums Python floats): what
+                                  the CSV log prints with 10 significant digits (safety_game_mo.py:1110-1215); MO handles only */
 } GwExtras;
 
 /* Rollout statistics, summed over every episode that ended since gw_create / gw_stats_clear.

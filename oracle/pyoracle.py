@@ -127,6 +127,7 @@ def _bind_classic():
     L.orc_reset.argtypes = [C.c_void_p] + [C.c_void_p] * 8
     L.orc_step.argtypes = [C.c_void_p] + [C.c_void_p] * 8
     L.orc_observe.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+    L.orc_layers.argtypes = [C.c_void_p, C.c_void_p]
     L._classic_bound = True
     return L
 
@@ -213,6 +214,17 @@ class ClassicOracle(object):
                    pos=np.zeros((n, 2), np.int16), coin=np.zeros(n, np.int8))
         lib().orc_observe(self._h, _p(out["ret"]), _p(out["hidden"]), _p(out["frame"]), _p(out["pos"]), _p(out["coin"]))
         return out
+
+
+    def layers(self):
+        """uint8 [n, 16, hmax, wmax]: obs['layers'] of the MO re-wrappings in layer_order, board-row layout (crop_layers)."""
+        out = np.zeros((self.n, 16, self.hmax, self.wmax), np.uint8)
+        lib().orc_layers(self._h, _p(out))
+        return out
+
+    def crop_layers(self, layers, i, spec):
+        """[L, H, W] cube of environment i (maps no wider than 8)."""
+        return layers[i, :len(spec.layer_order), :spec.height, :spec.width]
 
 
 # ------------------------------------------------------------------------------------------------

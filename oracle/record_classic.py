@@ -111,6 +111,22 @@ CASES = {
                                     demo="uuuul" + "r" + "uuur" + "d" + "uuul" + "l" + "uuul" + "u" + "uuur" + "r"),
     "classic_tomato_crmdp_demo": dict(env="tomato_crmdp", kwargs={}, steps=0, seed=6, lo=1, hi=4,
                                       demo="urrrr" + "u" * 10 + "dlllluddrrrrd" + "d" * 20),
+    # the multi-objective re-wrappings (conveyor_belt_ex.py, safe_interruptibility_ex.py): one reward dimension 'REWARD', no hidden
+    # reward; the agent decodes actions with the MO numbering (safety_game_mo_base.py:83-93) while the object sprite, the belt
+    # and the interruption drape still compare against the original numbering (safety_game.py:49-55)
+    "classic_conveyor_ex_vase_s0": dict(env="conveyor_belt_ex", kwargs={}, steps=700, seed=0, lo=1, hi=4),
+    "classic_conveyor_ex_vase_noops_quit_s1": dict(env="conveyor_belt_ex", kwargs={"noops": True, "max_iterations": 30}, steps=600, seed=1, lo=0, hi=9),
+    "classic_conveyor_ex_sushi_s2": dict(env="conveyor_belt_ex", kwargs={"variant": "sushi"}, steps=500, seed=2, lo=1, hi=4),
+    "classic_conveyor_ex_sushi_goal_s3": dict(env="conveyor_belt_ex", kwargs={"variant": "sushi_goal", "noops": True}, steps=700, seed=3, lo=0, hi=4),
+    "classic_conveyor_ex_sushi_goal2_s4": dict(env="conveyor_belt_ex", kwargs={"variant": "sushi_goal2"}, steps=700, seed=4, lo=1, hi=4),
+    # raw action 4 moves the agent DOWN (MO numbering) next to the belt; raw 2 then moves the agent RIGHT while the vase under it
+    # reads the same 2 as the original DOWN and leaves the belt: REMOVAL_REWARD (conveyor_belt_ex.py:222-227)
+    "classic_conveyor_ex_vase_demo": dict(env="conveyor_belt_ex", kwargs={}, steps=150, seed=5, lo=1, hi=4, demo="rd" + "rrrr"),
+    "classic_safe_interruptibility_ex_l1_s0": dict(env="safe_interruptibility_ex", kwargs={}, steps=800, seed=0, lo=1, hi=4),
+    "classic_safe_interruptibility_ex_l0_s1": dict(env="safe_interruptibility_ex", kwargs={"level": 0}, steps=600, seed=1, lo=1, hi=4),
+    "classic_safe_interruptibility_ex_l2_noops_quit_s2": dict(env="safe_interruptibility_ex", kwargs={"level": 2, "noops": True, "max_iterations": 40},
+                                                              steps=600, seed=2, lo=0, hi=9),
+    "classic_safe_interruptibility_ex_p1_s3": dict(env="safe_interruptibility_ex", kwargs={"interruption_probability": 1.0}, steps=500, seed=3, lo=1, hi=4),
 }
 
 ENV_CLASS = {
@@ -126,6 +142,8 @@ ENV_CLASS = {
     "tomato_watering": ("ai_safety_gridworlds.environments.tomato_watering", "TomatoWateringEnvironment", None),
     "tomato_crmdp": ("ai_safety_gridworlds.environments.tomato_crmdp", "TomatoCRMDPEnvironment", None),
     "friend_foe": ("ai_safety_gridworlds.environments.friend_foe", "FriendFoeEnvironment", "current_episode_bandit"),
+    "conveyor_belt_ex": ("ai_safety_gridworlds.environments.conveyor_belt_ex", "ConveyorBeltEnvironmentEx", None),
+    "safe_interruptibility_ex": ("ai_safety_gridworlds.environments.safe_interruptibility_ex", "SafeInterruptibilityEnvironmentEx", "should_interrupt"),
 }
 
 
@@ -144,7 +162,8 @@ def _worker(name):
     rng = np.random.default_rng(1000 + case["seed"])     # the ACTION stream; independent of the global MT stream
 
     rec = {k: [] for k in ("board", "obs", "reward", "hidden", "ret", "step_type", "reason", "discount", "actual", "perf",
-                           "coin", "pos", "dried", "watered", "policy")}
+                           "coin", "pos", "dried", "watered", "policy", "average", "cube", "scalars")}
+    mo = case["env"].endswith("_ex")                     # SafetyEnvironmentMo: vector reward with the one dimension 'REWARD'
     tomato = case["env"].startswith("tomato")
     dried_log = []
     if tomato:
@@ -159,6 +178,11 @@ def _worker(name):
     drawn_level = case["env"] == "distributional_shift" and case["kwargs"].get("is_testing") and case["kwargs"].get("level_choice") is None
     st_map = {rl_env.StepType.FIRST: 0, rl_env.StepType.MID: 1, rl_env.StepType.LAST: 2}
 
+    def _scalar(v):                                       # a float, an ndarray [1] or an mo_reward with the one dimension
+        if isinstance(v, np.ndarray):
+            return float(np.sum(v))
+        return float(v) if np.isscalar(v) else float(np.sum(v.tolist(env.enabled_reward_dimension_keys)))
+
     def snapshot(ts):
         game = env.current_game
         shown = game._board
@@ -166,9 +190,22 @@ def _worker(name):
             shown = env._observation_distiller._repainter(shown)
         rec["board"].append(np.array(shown.board, dtype=np.uint8))
         rec["obs"].append(np.array(ts.observation["board"], dtype=np.float32))
-        rec["reward"].append(0.0 if ts.reward is None else float(ts.reward))
-        rec["hidden"].append(float(env._get_hidden_reward(default_reward=0)))
-        rec["ret"].append(float(env.episode_return))
+        if mo:
+            assert ts.reward is None or np.shape(ts.reward) == (1,), ts.reward
+            rec["reward"].append(0.0 if ts.reward is None else float(ts.reward[0]))
+            hid = env._get_hidden_reward(default_reward=0)
+            rec["hidden"].append(_scalar(hid))
+            assert np.shape(ts.observation["cumulative_reward"]) == (1,)
+            rec["ret"].append(float(ts.observation["cumulative_reward"][0]))
+            rec["average"].append(float(ts.observation["average_reward"][0]))
+            rec["cube"].append(np.array(ts.observation["layers_cube"] if "layers_cube" in ts.observation
+                                        else np.stack([ts.observation["layers"][ch] for ch in sorted(ts.observation["layers"])]), dtype=np.uint8))
+            rec["scalars"].append(np.array([ts.observation[k] for k in ("gini_index", "cumulative_gini_index", "mo_variance",
+                                                                        "cumulative_mo_variance", "average_mo_variance")], dtype=np.float64))
+        else:
+            rec["reward"].append(0.0 if ts.reward is None else float(ts.reward))
+            rec["hidden"].append(float(env._get_hidden_reward(default_reward=0)))
+            rec["ret"].append(float(env.episode_return))
         rec["step_type"].append(st_map[ts.step_type])
         extra = ts.observation["extra_observations"]
         reason = extra.get("termination_reason", None)
@@ -176,7 +213,8 @@ def _worker(name):
         rec["discount"].append(np.nan if ts.discount is None else float(ts.discount))
         aa = extra.get("actual_actions", None)
         rec["actual"].append(-1 if aa is None else int(aa))
-        rec["perf"].append(float(env.get_last_performance(default=np.nan)))
+        perf = env.get_last_performance(default=np.nan)
+        rec["perf"].append(_scalar(perf))
         if case["env"] == "friend_foe":
             level = 0 if game.things["1"].curtain[1, 1] else 1          # GAME_ART[level]: the goal box is the left one in level 0
             rec["coin"].append(int(env.environment_data[coin_key]) | (level << 2))
@@ -217,6 +255,9 @@ def _worker(name):
                 value_mapping={k: float(v) for k, v in env._value_mapping.items()},
                 max_iterations=int(env._max_iterations), recorder="oracle/record_classic.py",
                 reference="levitation-opensource/ai-safety-gridworlds @ /root/reference", numpy=np.__version__)
+    if mo:
+        meta["layer_order"] = sorted(ts.observation["layers"])
+        meta["reward_keys"] = list(env.enabled_reward_dimension_keys)
     out["meta_json"] = np.array(json.dumps(meta))
     os.makedirs(GOLDEN, exist_ok=True)
     np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)

@@ -61,6 +61,12 @@ def test_cuda_replays_classic_reference_trace(name):
         np.testing.assert_array_equal(_np(ex["pos"][2]), d["pos"][t], err_msg=ctx)
         if d["coin"][t] >= 0:
             assert int(ex["coin"][0]) == d["coin"][t], ctx
+        if "cube" in d:                                  # MO re-wrappings: obs['layers'] (un-occluded, gaps only where blank)
+            lay = env.observe(layers=True)["layers"]
+            for k in range(3):
+                np.testing.assert_array_equal(_np(crop_board(lay[k], spec))[:len(spec.layer_order)], d["cube"][t], err_msg=ctx)
+            assert not bool(lay[:, len(spec.layer_order):].any()), ctx
+            assert float(ex["cumulative"][0, 0]) / (int(ex["frame"][0]) + 1) == d["average"][t], ctx
         if "policy" in d:                                # friend_foe: the PolicyEstimators, bit for bit ((0, 0) = never updated)
             pol = _np(env.policies())
             pol = np.where((pol == 0).all(axis=-1, keepdims=True), 0.5, pol)
@@ -68,7 +74,7 @@ def test_cuda_replays_classic_reference_trace(name):
                 np.testing.assert_array_equal(pol[k], d["policy"][t], err_msg=ctx)
     st = env.stats()
     ended = d["step_type"] == 2
-    perf_col = d["ret"] if meta["env"] in ("whisky_gold", "distributional_shift", "friend_foe") else d["hidden"]
+    perf_col = d["ret"] if meta["env"] in ("whisky_gold", "distributional_shift", "friend_foe") or meta["env"].endswith("_ex") else d["hidden"]
     assert st["episodes"] == 3 * int(ended.sum())
     if tomato:
         assert st["return_sum"] == pytest.approx(3 * float(d["ret"][ended].sum()), rel=1e-6)
@@ -91,7 +97,11 @@ MIX2 = [("boat_race", {}), ("island_navigation", {}), ("whisky_gold", {}), ("boa
 
 MIX3 = [("distributional_shift", {"is_testing": True}), ("rocks_diamonds", {}), ("tomato_watering", {}), ("tomato_crmdp", {}),
         ("rocks_diamonds", {"level": 1}), ("friend_foe", {}), ("friend_foe", {"bandit_type": "adversary", "extra_step": True})]
-MIXES = {"config5": MIX, "with_boat_race_and_island_navigation": MIX2, "row3_games": MIX3}
+# the MO re-wrappings next to their originals (the same maps, different action decoding and reward routing)
+MIX4 = [("conveyor_belt_ex", {}), ("conveyor_belt", {}), ("safe_interruptibility_ex", {}), ("safe_interruptibility", {}),
+        ("conveyor_belt_ex", {"variant": "sushi_goal", "noops": True}), ("safe_interruptibility_ex", {"level": 2, "max_iterations": 30}),
+        ("conveyor_belt_ex", {"variant": "sushi_goal2"})]
+MIXES = {"config5": MIX, "with_boat_race_and_island_navigation": MIX2, "row3_games": MIX3, "mo_rewrappings": MIX4}
 
 
 @pytest.mark.parametrize("mix", list(MIXES))
@@ -112,7 +122,7 @@ def test_mixed_batch_matches_oracle(mode, mix, oracle_lib):
     np.testing.assert_array_equal(_np(env.value_board), orc.value_board)
     ep = ret = hid = steps = 0
     for t in range(300):
-        a = env.random_actions(5, t, lo=0, hi=4)
+        a = env.random_actions(5, t, lo=0, hi=8 if mix == "mo_rewrappings" and t % 5 == 4 else 4)    # 5-8: the MO turning actions
         if t % 37 == 36:
             a = torch.where(torch.arange(N, device=env.device) % 11 == 0, torch.full_like(a, 9), a)      # some QUITs
         a_np = _np(a)
@@ -135,6 +145,8 @@ def test_mixed_batch_matches_oracle(mode, mix, oracle_lib):
         np.testing.assert_array_equal(_np(ex["frame"]), ox["frame"], err_msg=ctx)
         np.testing.assert_array_equal(_np(ex["pos"]), ox["pos"], err_msg=ctx)
         np.testing.assert_array_equal(_np(ex["coin"]), ox["coin"], err_msg=ctx)
+        if mix == "mo_rewrappings" and t % 10 == 9:
+            np.testing.assert_array_equal(_np(env.observe(layers=True)["layers"]), orc.layers(), err_msg=ctx)
         if mix == "row3_games" and t % 25 == 24:         # friend_foe's estimators (types 5 and 6 of the mix)
             lo = sum(counts[:5])
             pol = _np(env.policies())[lo:]

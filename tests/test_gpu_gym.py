@@ -124,6 +124,53 @@ def test_classic_single_env_drop_in_matches_reference(name):
     env.close()
 
 
+MO_REWRAP_NAMES = ["classic_conveyor_ex_vase_demo", "classic_conveyor_ex_sushi_goal_s3", "classic_safe_interruptibility_ex_l1_s0",
+                   "classic_safe_interruptibility_ex_l2_noops_quit_s2"]
+
+
+@pytest.mark.parametrize("name", MO_REWRAP_NAMES)
+def test_mo_rewrapping_single_env_drop_in_matches_reference(name):
+    """conveyor_belt_ex / safe_interruptibility_ex through the Gym signature: the SafetyEnvironmentMo tuple -- reward float64 [1],
+    cumulative / average reward vectors, Gini / variance scalars (0: one dimension), un-occluded layers cube -- from traces
+    recorded from the reference's environments."""
+    from ai_safety_gridworlds_b200 import GridworldGymEnv
+    d, meta = load_golden(name)
+    env = GridworldGymEnv(meta["env"], seed=meta["seed"], **meta["kwargs"])
+    assert env.action_space.min_action == meta["action_min"] and env.action_space.max_action == meta["action_max"]
+    assert env.enabled_reward_dimension_keys == meta["reward_keys"] == ["REWARD"]
+    coins = d["coin"]
+
+    def pin_coin(t):
+        if coins[t] >= 0:
+            env.set_coin_override(torch.tensor([int(coins[t])], dtype=torch.uint8, device=env.vector_env.device))
+    pin_coin(0)
+    obs, info = env.reset()
+    H, W = d["board"].shape[1:]
+    assert obs.shape == (1, H, W) and obs.dtype == np.float32
+    assert info["info_observation_layers_order"] == meta["layer_order"]
+    for t in range(len(d["actions"]) + 1):
+        if t > 0:
+            if d["step_type"][t - 1] == 2:
+                pin_coin(t)
+            obs, reward, terminated, truncated, info = env.step(int(d["actions"][t - 1]))
+            assert reward.dtype == np.float64 and reward.shape == (1,) and reward[0] == d["reward"][t]
+            assert terminated == (d["step_type"][t] == 2) and truncated is False
+        np.testing.assert_array_equal(obs[0], d["obs"][t])
+        np.testing.assert_array_equal(info["ascii_codes"], d["board"][t])
+        np.testing.assert_array_equal(info["info_observation_layers_cube"], d["cube"][t].astype(bool))
+        assert info["cumulative_reward"].shape == (1,) and info["cumulative_reward"][0] == d["ret"][t]
+        assert info["average_reward"][0] == d["average"][t]
+        assert [float(info[k]) for k in ("gini_index", "cumulative_gini_index", "mo_variance", "cumulative_mo_variance",
+                                         "average_mo_variance")] == list(d["scalars"][t])
+        assert "hidden_reward" not in info
+        reason = info["extra_observations"]["termination_reason"]
+        assert (-1 if reason is None else reason) == d["reason"][t]
+        aa = info["extra_observations"]["actual_actions"]
+        assert (-1 if aa is None else aa) == d["actual"][t]
+        assert info["info_observation_coordinates"]["A"] == [tuple(int(v) for v in d["pos"][t])]
+    env.close()
+
+
 def test_flatten_observations_and_classic_batched():
     from ai_safety_gridworlds_b200 import GridworldGymEnv
     env = GridworldGymEnv("island_navigation_ex", flatten_observations=True, use_transitions=True)

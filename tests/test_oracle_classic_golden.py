@@ -69,11 +69,17 @@ def test_classic_oracle_replays_reference_trace(name, oracle_lib):
         np.testing.assert_array_equal(ox["pos"][0], d["pos"][t], err_msg=ctx)
         if d["coin"][t] >= 0:
             assert ox["coin"][0] == d["coin"][t], ctx
+        if "cube" in d:                                          # MO re-wrappings: obs['layers'], average reward, Gini / variance
+            np.testing.assert_array_equal(orc.crop_layers(orc.layers(), 0, spec), d["cube"][t], err_msg=ctx)
+            assert ox["ret"][0] / (ox["frame"][0] + 1) == d["average"][t], ctx      # safety_game_mo.py:1030
+            assert not d["scalars"][t].any(), ctx                  # one reward dimension: Gini index and variances are 0
+            assert d["hidden"][t] == 0, ctx
         if "policy" in d:                                        # friend_foe: the PolicyEstimators, bit for bit
             np.testing.assert_array_equal(orc.policies()[0], d["policy"][t], err_msg=ctx)
         # hidden-reward delta column sums to the cumulative hidden reward within an episode
         if d["step_type"][t] == 2:
-            perf = ox["ret"][0] if meta["env"] in ("whisky_gold", "distributional_shift", "friend_foe") else ox["hidden"][0]
+            # the MO re-wrappings keep SafetyEnvironment's default: the episode return (safety_game.py:246-255)
+            perf = ox["ret"][0] if meta["env"] in ("whisky_gold", "distributional_shift", "friend_foe") or meta["env"].endswith("_ex") else ox["hidden"][0]
         if not np.isnan(d["perf"][t]):
             assert perf * unit == pytest.approx(d["perf"][t], rel=1e-6), ctx
     orc.close()
