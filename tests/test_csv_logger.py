@@ -80,6 +80,6 @@ def test_gym_wrapper_writes_the_reference_csv(name, tmp_path):
         env.step(int(a))
     env.close()
     files = sorted(os.listdir(str(tmp_path)))
-    assert len(files) == 2 and files[0].endswith(".txt") and files[1].endswith(".csv")
-    with open(os.path.join(str(tmp_path), files[1]), newline="") as f:
+    assert len(files) == 2 and sorted(os.path.splitext(f)[1] for f in files) == [".csv", ".txt"]
+    with open(os.path.join(str(tmp_path), [f for f in files if f.endswith(".csv")][0]), newline="") as f:
         assert f.read() == _golden_text(name)
