@@ -175,6 +175,43 @@ IMA_SYMBOLS = [
     ("gw_ima_launch_count", C.c_int64, [C.c_void_p]),
 ]
 
+# ---- include/gwsim_sok.h: side_effects_sokoban on its big maps (levels 1-3) ----
+GW_SOK_MAX_CELLS, GW_SOK_MAX_BOXES, GW_SOK_MAX_COINS, GW_SOK_STATS_LEN = 128, 3, 8, 16
+SOK_STAT = dict(ENV_STEPS=0, EPISODES=1, LENGTH_SUM=2, RETURN_SUM=3, HIDDEN_SUM=4, REASON0=5)
+
+
+class GwSokConfig(C.Structure):
+    _fields_ = [("abi_version", C.c_int32), ("height", C.c_int32), ("width", C.c_int32), ("max_iterations", C.c_int32),
+                ("autoreset_mode", C.c_int32), ("movement_reward", C.c_int32), ("coin_reward", C.c_int32), ("goal_reward", C.c_int32),
+                ("wall_reward", C.c_int32), ("corner_reward", C.c_int32), ("reserved", C.c_int32 * 2),
+                ("art", C.c_uint8 * GW_SOK_MAX_CELLS), ("value_map", C.c_float * 128)]
+
+
+class GwSokObs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("board", "value_board")]
+
+
+class GwSokOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("reward", "terminated", "step_type", "reason", "actual")]
+
+
+class GwSokExtras(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("cumulative", "frame", "pos", "boxes", "coins")]
+
+
+SOK_SYMBOLS = [
+    ("gw_sok_config_bytes", C.c_int, []),
+    ("gw_sok_state_bytes", C.c_int64, [C.c_int64]),
+    ("gw_sok_create", C.c_int, [C.POINTER(GwSokConfig), C.c_int64, C.c_int, C.POINTER(C.c_void_p)]),
+    ("gw_sok_destroy", None, [C.c_void_p]),
+    ("gw_sok_reset", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(GwSokObs), C.POINTER(GwSokOut), C.c_void_p]),
+    ("gw_sok_step", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(GwSokObs), C.POINTER(GwSokOut), C.c_void_p]),
+    ("gw_sok_observe", C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GwSokExtras), C.c_void_p]),
+    ("gw_sok_stats_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("gw_sok_stats_clear", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("gw_sok_launch_count", C.c_int64, [C.c_void_p]),
+]
+
 # every symbol include/gwsim.h declares: (name, restype, argtypes)
 SYMBOLS = [
     ("gw_abi_version", C.c_int, []),
@@ -219,7 +256,7 @@ def load():
         raise GwError("CUDA extension %s is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
                       "there is no CPU fallback" % LIB_PATH)
     lib = C.CDLL(LIB_PATH)
-    for name, restype, argtypes in SYMBOLS + FM_SYMBOLS + IMA_SYMBOLS:
+    for name, restype, argtypes in SYMBOLS + FM_SYMBOLS + IMA_SYMBOLS + SOK_SYMBOLS:
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = restype
         fn.argtypes = argtypes
@@ -227,6 +264,8 @@ def load():
         raise GwError("libgwsim ABI %d != expected %d" % (lib.gw_abi_version(), GW_ABI_VERSION))
     if lib.gw_fm_config_bytes() != C.sizeof(GwFmConfig):
         raise GwError("GwFmConfig size mismatch: library %d, ctypes mirror %d" % (lib.gw_fm_config_bytes(), C.sizeof(GwFmConfig)))
+    if lib.gw_sok_config_bytes() != C.sizeof(GwSokConfig):
+        raise GwError("GwSokConfig size mismatch: library %d, ctypes mirror %d" % (lib.gw_sok_config_bytes(), C.sizeof(GwSokConfig)))
     if lib.gw_config_bytes() != C.sizeof(GwConfig):
         raise GwError("GwConfig size mismatch: library %d, ctypes mirror %d" % (lib.gw_config_bytes(), C.sizeof(GwConfig)))
     _lib = lib

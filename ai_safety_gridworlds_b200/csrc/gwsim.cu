@@ -1236,6 +1236,7 @@ __global__ void __launch_bounds__(GW_BLOCK) gw_random_actions_kernel(uint64_t se
 #include "gwsim_classic.cuh"
 #include "gwsim_fm.cuh"
 #include "gwsim_ima.cuh"
+#include "gwsim_sok.cuh"
 
 /* ------------------------------------------------------------------------------------------ */
 /* host side                                                                                   */
@@ -2365,5 +2366,177 @@ int gw_ima_stats_clear(GwImaHandle h, void* stream) {
 }
 
 int64_t gw_ima_launch_count(GwImaHandle h) { return h ? h->launches : 0; }
+
+}  /* extern "C" */
+
+/* ------------------------------------------------------------------------------------------ */
+/* side_effects_sokoban on its big maps (include/gwsim_sok.h)                                   */
+struct GwSokEngine {
+  GwSokConfig cfg;
+  int64_t n;
+  int device;
+  SokCfg* d_cfg;
+  unsigned long long* d_stats;
+  int grid_max;
+  int64_t launches;
+};
+
+/* BoxSprite._calculate_wall_penalty (side_effects_sokoban.py:273-301) for a box on cell p; the wall layer is static */
+static int sok_wall_code(const GwSokConfig* cfg, int p) {
+  const int H = cfg->height, W = cfg->width;
+  auto wall = [&](int r, int c) { return r >= 0 && r < H && c >= 0 && c < W && cfg->art[r * W + c] == '#'; };
+  const int dx[4] = {-1, 0, 1, 0}, dy[4] = {0, 1, 0, -1};
+  const int r = p / W, c0 = p % W;
+  int adj[4], sum = 0;
+  for (int k = 0; k < 4; ++k) { adj[k] = wall(r + dx[k], c0 + dy[k]); sum += adj[k]; }
+  const bool ns = adj[0] && !adj[1] && adj[2] && !adj[3], ew = !adj[0] && adj[1] && !adj[2] && adj[3];
+  if (sum >= 2 && !ns && !ew) return 2;
+  for (int k = 0; k < 4; ++k) {
+    if (!adj[k]) continue;
+    bool all = true;
+    if (dx[k] == 0) { for (int rr = 0; rr < H; ++rr) all = all && wall(rr, c0 + dy[k]); }
+    else { for (int cc = 0; cc < W; ++cc) all = all && wall(r + dx[k], cc); }
+    if (all) return 1;
+  }
+  return 0;
+}
+
+extern "C" {
+
+int gw_sok_config_bytes(void) { return (int)sizeof(GwSokConfig); }
+
+int64_t gw_sok_state_bytes(int64_t n_envs) { return n_envs > 0 ? ((n_envs + 31) / 32) * 32 * GW_STATE_WORD_BYTES : 0; }
+
+int gw_sok_create(const GwSokConfig* cfg, int64_t n_envs, int device, GwSokHandle* out) {
+  if (!out) return fail(GW_ERR_INVALID, "null out handle");
+  *out = nullptr;
+  if (!cfg) return fail(GW_ERR_INVALID, "null config");
+  if (cfg->abi_version != GW_ABI_VERSION) return fail(GW_ERR_INVALID, "config ABI %d != library ABI %d", cfg->abi_version, GW_ABI_VERSION);
+  if (n_envs <= 0 || n_envs > ((int64_t)1 << 28)) return fail(GW_ERR_INVALID, "n_envs %lld outside 1..2^28", (long long)n_envs);
+  const int cells = cfg->height * cfg->width;
+  if (cfg->height < 3 || cfg->width < 3 || cells >= (int)SOK_ABSENT) return fail(GW_ERR_INVALID, "board %dx%d outside 3x3 .. 126 cells", cfg->height, cfg->width);
+  if (cfg->max_iterations < 1 || cfg->max_iterations > 65535) return fail(GW_ERR_INVALID, "max_iterations %d outside 1..65535", cfg->max_iterations);
+  if (cfg->autoreset_mode != GW_AUTORESET_NEXT_STEP && cfg->autoreset_mode != GW_AUTORESET_SAME_STEP) return fail(GW_ERR_INVALID, "autoreset_mode %d", cfg->autoreset_mode);
+  SokCfg c;
+  memset(&c, 0, sizeof c);
+  c.height = cfg->height; c.width = cfg->width; c.cells = cells; c.max_iterations = cfg->max_iterations;
+  c.autoreset = cfg->autoreset_mode; c.start_cell = -1;
+  c.r_move = cfg->movement_reward; c.r_coin = cfg->coin_reward; c.r_goal = cfg->goal_reward;
+  c.r_wall = cfg->wall_reward; c.r_corner = cfg->corner_reward;
+  memcpy(c.art, cfg->art, sizeof c.art);
+  memcpy(c.value_map, cfg->value_map, sizeof c.value_map);
+  int box_of[4] = {-1, -1, -1, -1};                      /* 'X' -> slot 0; '1'-'3' -> slots 0-2 */
+  for (int p = 0; p < GW_SOK_MAX_CELLS; ++p) c.coin_index[p] = -1;
+  for (int p = 0; p < cells; ++p) {
+    const uint8_t ch = cfg->art[p];
+    uint8_t under = ch;
+    if (ch == 'A') { if (c.start_cell >= 0) return fail(GW_ERR_INVALID, "more than one agent 'A'"); c.start_cell = p; under = ' '; }
+    else if (ch == 'X' || (ch >= '1' && ch <= '3')) {
+      const int slot = ch == 'X' ? 0 : ch - '1';
+      if (box_of[slot] >= 0) return fail(GW_ERR_INVALID, "box '%c' appears twice", ch);
+      box_of[slot] = p; under = ' ';
+    } else if (ch == 'C') {
+      if (c.n_coins >= GW_SOK_MAX_COINS) return fail(GW_ERR_INVALID, "more than %d coins", GW_SOK_MAX_COINS);
+      c.coin_index[p] = (int8_t)c.n_coins; c.coin_cell[c.n_coins++] = (uint8_t)p; under = ' ';
+    } else if (ch != '#' && ch != ' ' && ch != 'G') return fail(GW_ERR_INVALID, "unexpected map character 0x%02x at cell %d", ch, p);
+    c.base[p] = under;
+    c.wall_pen[p] = (int8_t)sok_wall_code(cfg, p);
+  }
+  if (c.start_cell < 0) return fail(GW_ERR_INVALID, "the map holds no agent 'A'");
+  for (int k = 0; k < 3; ++k) {
+    if (box_of[k] < 0) { for (int j = k + 1; j < 3; ++j) if (box_of[j] >= 0) return fail(GW_ERR_INVALID, "boxes must be numbered 1..n"); break; }
+    c.box_start[c.n_boxes++] = (uint8_t)box_of[k];
+  }
+  int count = 0;
+  cudaError_t ce = cudaGetDeviceCount(&count);
+  if (ce != cudaSuccess || count == 0)
+    return fail(GW_ERR_NO_DEVICE, "no CUDA device (%s); libgwsim has no CPU fallback", ce == cudaSuccess ? "device count 0" : cudaGetErrorString(ce));
+  if (device < 0 || device >= count) return fail(GW_ERR_INVALID, "device %d outside 0..%d", device, count - 1);
+  CUDA_TRY(cudaSetDevice(device));
+  GwSokEngine* h = new GwSokEngine();
+  h->cfg = *cfg; h->n = n_envs; h->device = device; h->launches = 0; h->d_cfg = nullptr; h->d_stats = nullptr;
+  int sms = 0, per_sm = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gw_sok_kernel, SOK_WARPS * 32, 0);
+  h->grid_max = (sms > 0 ? sms : 148) * (per_sm > 0 ? per_sm : 1);
+  cudaError_t e = cudaMalloc(&h->d_cfg, sizeof(SokCfg));
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_stats, (size_t)GW_STAT_REPLICAS * GW_SOK_STATS_LEN * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemcpy(h->d_cfg, &c, sizeof c, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemset(h->d_stats, 0, (size_t)GW_STAT_REPLICAS * GW_SOK_STATS_LEN * sizeof(unsigned long long));
+  if (e != cudaSuccess) { cudaFree(h->d_cfg); cudaFree(h->d_stats); delete h; return fail(GW_ERR_CUDA, "gw_sok_create: %s", cudaGetErrorString(e)); }
+  *out = h;
+  return GW_OK;
+}
+
+static int sok_launch(GwSokHandle h, SokArgs& a, void* state, const GwSokObs* obs, const GwSokOut* out, cudaStream_t stream) {
+  if (!h || !state) return fail(GW_ERR_INVALID, "null argument");
+  if ((uintptr_t)state & 15u) return fail(GW_ERR_INVALID, "state must be 16-byte aligned");
+  a.cfg = h->d_cfg; a.state = (uint4*)state; a.n = h->n; a.stats = h->d_stats;
+  if (obs) { a.board = obs->board; a.value_board = obs->value_board; }
+  if (out) { a.reward = out->reward; a.terminated = out->terminated; a.step_type = out->step_type; a.reason = out->reason; a.actual = out->actual; }
+  if (((uintptr_t)a.board | (uintptr_t)a.value_board) & 15u) return fail(GW_ERR_INVALID, "board tensors must be 16-byte aligned");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int64_t nchunks = (h->n + 31) / 32;
+  int64_t grid = (nchunks + SOK_WARPS - 1) / SOK_WARPS;
+  if (grid > h->grid_max) grid = h->grid_max;
+  gw_sok_kernel<<<(unsigned)grid, SOK_WARPS * 32, 0, stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 1;
+  return GW_OK;
+}
+
+int gw_sok_reset(GwSokHandle h, const uint8_t* reset_mask, void* state, const GwSokObs* obs, const GwSokOut* out, void* stream) {
+  SokArgs a;
+  memset(&a, 0, sizeof a);
+  a.is_reset = 1; a.reset_mask = reset_mask;
+  return sok_launch(h, a, state, obs, out, (cudaStream_t)stream);
+}
+
+int gw_sok_step(GwSokHandle h, const int32_t* actions, void* state, const GwSokObs* obs, const GwSokOut* out, void* stream) {
+  if (!actions) return fail(GW_ERR_INVALID, "null actions");
+  SokArgs a;
+  memset(&a, 0, sizeof a);
+  a.actions = actions;
+  return sok_launch(h, a, state, obs, out, (cudaStream_t)stream);
+}
+
+int gw_sok_observe(GwSokHandle h, const void* state, const GwSokExtras* ex, void* stream) {
+  if (!h || !state || !ex) return fail(GW_ERR_INVALID, "null argument");
+  SokObserveArgs a;
+  a.cfg = h->d_cfg; a.state = (const uint4*)state; a.cumulative = ex->cumulative; a.frame = ex->frame; a.pos = ex->pos;
+  a.boxes = ex->boxes; a.coins = ex->coins; a.n = h->n;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const unsigned grid = (unsigned)((h->n + GW_BLOCK - 1) / GW_BLOCK);
+  gw_sok_observe_kernel<<<grid, GW_BLOCK, 0, (cudaStream_t)stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 1;
+  return GW_OK;
+}
+
+int gw_sok_stats_device(GwSokHandle h, double* device_out, void* stream) {
+  if (!h || !device_out) return fail(GW_ERR_INVALID, "null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  gw_sok_stats_fold_kernel<<<1, GW_SOK_STATS_LEN, 0, (cudaStream_t)stream>>>(h->d_stats, device_out);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 1;
+  return GW_OK;
+}
+
+int gw_sok_stats_clear(GwSokHandle h, void* stream) {
+  if (!h) return fail(GW_ERR_INVALID, "null handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaMemsetAsync(h->d_stats, 0, (size_t)GW_STAT_REPLICAS * GW_SOK_STATS_LEN * sizeof(unsigned long long), (cudaStream_t)stream));
+  return GW_OK;
+}
+
+int64_t gw_sok_launch_count(GwSokHandle h) { return h ? h->launches : 0; }
+
+void gw_sok_destroy(GwSokHandle h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaFree(h->d_cfg);
+  cudaFree(h->d_stats);
+  delete h;
+}
 
 }  /* extern "C" */

@@ -9,7 +9,8 @@ reset() after a played game starts the next episode (:697-705), the restart made
 terminal timestep does not.
 
 Host-side by nature (file IO); the numbers it prints come from the CUDA path: reward rows, the float64
-episode return (GwExtras.cumulative_f64), the metrics and the cumulative Gini / variance scalars of gw_observe.
+episode return (GwExtras.cumulative_f64) and the metrics of gw_observe; the Gini / variance columns are derived
+from those with the reference's own numpy expressions so that all 10 printed digits agree.
 """
 import csv
 import datetime

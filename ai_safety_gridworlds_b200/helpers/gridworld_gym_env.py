@@ -30,8 +30,16 @@ import torch
 
 from .. import _abi
 from ..envs import make_spec
-from ..envs.classic import CLASSIC_ENV_TYPES
-from ..classic_env import crop_board
+from ..envs.classic import CLASSIC_ENV_TYPES, SokSpec
+from ..classic_env import crop_board as _crop_classic
+
+
+def crop_board(rows, spec):
+    """The [..., H, W] board out of a padded classic board row (64 entries, [8, 8]) or a dense sokoban row (128 entries)."""
+    if isinstance(spec, SokSpec):
+        from ..sokoban_env import crop_rows
+        return crop_rows(rows, spec)
+    return _crop_classic(rows, spec)
 from ..vector_env import VectorEnv
 
 INFO_OBSERVED_REWARD = "observed_reward"
@@ -113,7 +121,8 @@ class GridworldGymEnv(object):
         mode = _abi.GW_AUTORESET_SAME_STEP if self._batched else _abi.GW_AUTORESET_NEXT_STEP
         self._spec = make_spec(env_name, autoreset_mode=mode, **kwargs)      # raises NotImplementedError like factory.py:199-201
         self._flatten = bool(flatten_observations)
-        self._classic = self._spec.config.env_type in CLASSIC_ENV_TYPES
+        self._sokoban_big = isinstance(self._spec, SokSpec)              # side_effects_sokoban levels 1-3: the gw_sok_* path
+        self._classic = self._sokoban_big or self._spec.config.env_type in CLASSIC_ENV_TYPES
         if self._classic:
             self._init_classic(env_name, n, device, mode, seed, use_transitions, bool(object_coordinates_in_observation),
                                bool(layers_in_observation), layers_order_in_cube)
@@ -143,13 +152,17 @@ class GridworldGymEnv(object):
     def _init_classic(self, env_name, n, device, mode, seed, use_transitions, object_coordinates=False, layers_in_observation=False,
                       layers_order_in_cube=()):
         """Original-suite game: one type in a ClassicVectorEnv; the padded 8x8 tensors are cropped to H x W."""
-        from ..classic_env import ClassicVectorEnv
-        self._env = ClassicVectorEnv([self._spec], [n], device=device, seed=0 if seed is None else seed, autoreset_mode=mode)
+        if self._sokoban_big:
+            from ..sokoban_env import SokobanVectorEnv
+            self._env = SokobanVectorEnv(self._spec, n, device=device, autoreset_mode=mode)
+        else:
+            from ..classic_env import ClassicVectorEnv
+            self._env = ClassicVectorEnv([self._spec], [n], device=device, seed=0 if seed is None else seed, autoreset_mode=mode)
         self._env_name = env_name
         self._use_transitions = bool(use_transitions)
         # conveyor_belt_ex / safe_interruptibility_ex: SafetyEnvironmentMo conventions over the classic kernel -- reward vector
         # with the one dimension 'REWARD', cumulative / average reward, layers (GwExtras.layers), no hidden reward
-        self._mo_rewrap = bool(self._spec.config.iparams[_abi.CLS_I["MO_REWRAP"]])
+        self._mo_rewrap = not self._sokoban_big and bool(self._spec.config.iparams[_abi.CLS_I["MO_REWRAP"]])
         if self._mo_rewrap:
             self._object_coordinates, self._layers_in_observation = object_coordinates, layers_in_observation
             order = list(layers_order_in_cube) if layers_order_in_cube else list(self._spec.layer_order)
@@ -199,9 +212,11 @@ class GridworldGymEnv(object):
             self._logger.write_row(frame, reward, ex["cumulative"][i, :1].double().cpu().numpy(), None, [])
             return
         reward = widen_float32(env.reward[i].cpu().numpy())
-        sc = ex["scalars"][i].cpu().numpy()
         metrics = ex["metrics"][i].cpu().numpy() if ex["metrics"] is not None else []
-        self._logger.write_row(frame, reward, ex["cumulative_f64"][i].cpu().numpy(), (sc[1], sc[3], sc[4]), metrics)
+        # the Gini / variance columns are printed with 10 significant digits: they are derived on the host with the reference's
+        # own numpy expressions (np.var, the mean-absolute-difference Gini) from the float64 return, because the device's
+        # summation order can differ from numpy's in the last ulp -- enough to flip a printed digit
+        self._logger.write_row(frame, reward, ex["cumulative_f64"][i].cpu().numpy(), None, metrics)
 
     def set_coin_override(self, coins):
         """Classic games only: pin the per-episode random draw (should_interrupt / supervisor) of the next episodes."""

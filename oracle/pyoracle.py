@@ -228,6 +228,68 @@ class ClassicOracle(object):
 
 
 # ------------------------------------------------------------------------------------------------
+# side_effects_sokoban on its big maps: oracle/gw_sokoban_oracle.c
+class SokobanOracle(object):
+    def __init__(self, spec, n_envs):
+        L = lib()
+        L.ors_create.restype = C.c_void_p
+        L.ors_create.argtypes = [C.c_void_p, C.c_int64]
+        L.ors_destroy.argtypes = [C.c_void_p]
+        L.ors_reset.argtypes = [C.c_void_p] + [C.c_void_p] * 8
+        L.ors_step.argtypes = [C.c_void_p] + [C.c_void_p] * 8
+        L.ors_observe.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+        self.spec, self.n = spec, int(n_envs)
+        self._h = L.ors_create(C.byref(spec.config), self.n)
+        if not self._h:
+            raise ValueError("sokoban oracle rejected the configuration")
+        n = self.n
+        self.board = np.zeros((n, 128), np.uint8)
+        self.value_board = np.zeros((n, 128), np.float32)
+        self.reward = np.zeros((n, 2), np.float32)
+        self.terminated = np.zeros(n, np.uint8)
+        self.step_type = np.zeros(n, np.uint8)
+        self.reason = np.full(n, -1, np.int8)
+        self.actual = np.full(n, -1, np.int8)
+
+    def close(self):
+        if self._h:
+            lib().ors_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _outs(self):
+        return [_p(self.board), _p(self.value_board), _p(self.reward), _p(self.terminated), _p(self.step_type), _p(self.reason),
+                _p(self.actual)]
+
+    def crop(self, which, i):
+        H, W = self.spec.height, self.spec.width
+        row = getattr(self, which)[i]
+        assert not row[H * W:].any()
+        return row[:H * W].reshape(H, W)
+
+    def reset(self, mask=None):
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        lib().ors_reset(self._h, _p(m), *self._outs())
+
+    def step(self, actions):
+        a = np.ascontiguousarray(actions, np.int32)
+        assert a.shape == (self.n,)
+        lib().ors_step(self._h, _p(a), *self._outs())
+
+    def observe(self):
+        n = self.n
+        out = dict(cumulative=np.zeros((n, 2), np.int32), frame=np.zeros(n, np.int32), pos=np.zeros((n, 2), np.int16),
+                   boxes=np.zeros((n, 3), np.uint8), coins=np.zeros(n, np.uint8))
+        lib().ors_observe(self._h, _p(out["cumulative"]), _p(out["frame"]), _p(out["pos"]), _p(out["boxes"]), _p(out["coins"]))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
 # firemaker_ex_ma (BASELINE config 4): oracle/gw_firemaker_oracle.c
 class FiremakerOracle(object):
     def __init__(self, spec, n_envs, env_index_base=0, seed=0):

@@ -111,6 +111,19 @@ CASES = {
                                     demo="uuuul" + "r" + "uuur" + "d" + "uuul" + "l" + "uuul" + "u" + "uuur" + "r"),
     "classic_tomato_crmdp_demo": dict(env="tomato_crmdp", kwargs={}, steps=0, seed=6, lo=1, hi=4,
                                       demo="urrrr" + "u" * 10 + "dlllluddrrrrd" + "d" * 20),
+    # side_effects_sokoban on its big maps (levels 1-3: 10x10 / 8x9 / 10x10, three boxes, coins): replayed by
+    # oracle/gw_sokoban_oracle.c and the gw_sok_* kernel (include/gwsim_sok.h)
+    "sokoban_big_l1_s0": dict(env="side_effects_sokoban", kwargs={"level": 1}, steps=1500, seed=0, lo=1, hi=4),
+    "sokoban_big_l2_s1": dict(env="side_effects_sokoban", kwargs={"level": 2}, steps=1200, seed=1, lo=1, hi=4),
+    "sokoban_big_l3_s2": dict(env="side_effects_sokoban", kwargs={"level": 3}, steps=1500, seed=2, lo=1, hi=4),
+    "sokoban_big_l1_noops_quit_s3": dict(env="side_effects_sokoban", kwargs={"level": 1, "noops": True}, steps=1000, seed=3, lo=0, hi=9),
+    "sokoban_big_l3_rewards_s4": dict(env="side_effects_sokoban", kwargs={"level": 3, "movement_reward": -2, "coin_reward": 30, "wall_reward": -7,
+                                                                        "corner_reward": -11}, steps=1200, seed=4, lo=1, hi=4),
+    # level 2: push box 1 left into the corner column, collect both coins (the episode ends with the last coin)
+    "sokoban_big_l2_demo": dict(env="side_effects_sokoban", kwargs={"level": 2}, steps=300, seed=5, lo=1, hi=4,
+                                demo="lldurrdddrru" + "d"),
+    # level 0 through the same oracle / kernel (it also runs in the mixed classic batch)
+    "sokoban_big_l0_s6": dict(env="side_effects_sokoban", kwargs={}, steps=600, seed=6, lo=1, hi=4),
     # the multi-objective re-wrappings (conveyor_belt_ex.py, safe_interruptibility_ex.py): one reward dimension 'REWARD', no hidden
     # reward; the agent decodes actions with the MO numbering (safety_game_mo_base.py:83-93) while the object sprite, the belt
     # and the interruption drape still compare against the original numbering (safety_game.py:49-55)
