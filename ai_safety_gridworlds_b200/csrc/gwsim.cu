@@ -2442,6 +2442,13 @@ int gw_sok_create(const GwSokConfig* cfg, int64_t n_envs, int device, GwSokHandl
     c.base[p] = under;
     c.wall_pen[p] = (int8_t)sok_wall_code(cfg, p);
   }
+  for (int p = 0; p < GW_SOK_MAX_CELLS; ++p) {
+    const int r = p / cfg->width, col = p % cfg->width;
+    c.nbr[0][p] = (uint8_t)(p < cells && r > 0 ? p - cfg->width : 255);
+    c.nbr[1][p] = (uint8_t)(p < cells && r + 1 < cfg->height ? p + cfg->width : 255);
+    c.nbr[2][p] = (uint8_t)(p < cells && col > 0 ? p - 1 : 255);
+    c.nbr[3][p] = (uint8_t)(p < cells && col + 1 < cfg->width ? p + 1 : 255);
+  }
   if (c.start_cell < 0) return fail(GW_ERR_INVALID, "the map holds no agent 'A'");
   for (int k = 0; k < 3; ++k) {
     if (box_of[k] < 0) { for (int j = k + 1; j < 3; ++j) if (box_of[j] >= 0) return fail(GW_ERR_INVALID, "boxes must be numbered 1..n"); break; }

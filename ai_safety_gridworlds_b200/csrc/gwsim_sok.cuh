@@ -30,6 +30,7 @@ struct SokCfg {                       /* constant per handle; device memory -> s
   alignas(16) uint8_t base[GW_SOK_MAX_CELLS];    /* the render without agent, boxes and coins; zero past H*W */
   alignas(16) int8_t wall_pen[GW_SOK_MAX_CELLS]; /* BoxSprite._calculate_wall_penalty per cell: 0 none, 1 wall, 2 corner */
   alignas(16) int8_t coin_index[GW_SOK_MAX_CELLS]; /* index of the coin on this cell, -1 = none */
+  alignas(16) uint8_t nbr[4][GW_SOK_MAX_CELLS];  /* the cell above / below / left of / right of a cell, 255 = off the board */
   alignas(16) float value_map[128];
 };
 static_assert(sizeof(SokCfg) % 16 == 0, "SokCfg is copied in 16-byte pieces");
@@ -89,24 +90,19 @@ __device__ __forceinline__ uint8_t sok_char_at(const SokCfg& c, const Sok& s, ui
 
 /* MazeWalker cardinal move (pycolab/prefab_parts/sprites.py:356-411,479-550); `mask`: 1 = '#', 2 = boxes, 4 = coins */
 __device__ __forceinline__ uint32_t sok_walk(const SokCfg& c, const Sok& s, uint32_t pos, int32_t action, uint32_t mask) {
-  int32_t dr = 0, dc = 0;
-  if (action == GW_CACT_UP) dr = -1; else if (action == GW_CACT_DOWN) dr = 1;
-  else if (action == GW_CACT_LEFT) dc = -1; else if (action == GW_CACT_RIGHT) dc = 1; else return pos;
-  const int32_t r = (int32_t)pos / c.width + dr, col = (int32_t)pos % c.width + dc;
-  if (r < 0 || r >= c.height || col < 0 || col >= c.width) return pos;
-  const uint32_t target = (uint32_t)(r * c.width + col);
+  if (action < GW_CACT_UP || action > GW_CACT_RIGHT) return pos;
+  const uint32_t target = c.nbr[action - GW_CACT_UP][pos];            /* GwClassicAction: UP 1, DOWN 2, LEFT 3, RIGHT 4 */
+  if (target == 255u) return pos;
   const uint8_t ch = sok_char_at(c, s, target);
   const bool blocked = (ch == '#' && (mask & 1u)) || (ch == 'X' && (mask & 2u)) || (ch == 'C' && (mask & 4u));
   return blocked ? pos : target;
 }
 
 __device__ __forceinline__ bool sok_agent_behind(const SokCfg& c, uint32_t agent, uint32_t pos, int32_t action) {
-  int32_t dr = 0, dc = 0;                                   /* layers[AGENT_CHR][rows + 1, cols] etc. (:259-267) */
-  if (action == GW_CACT_UP) dr = 1; else if (action == GW_CACT_DOWN) dr = -1;
-  else if (action == GW_CACT_LEFT) dc = 1; else if (action == GW_CACT_RIGHT) dc = -1; else return false;
-  const int32_t r = (int32_t)pos / c.width + dr, col = (int32_t)pos % c.width + dc;
-  if (r < 0 || r >= c.height || col < 0 || col >= c.width) return false;
-  return (uint32_t)(r * c.width + col) == agent;
+  /* layers[AGENT_CHR][rows + 1, cols] for UP etc. (:259-267): the agent stands on the neighbour OPPOSITE to the push
+   * direction; UP <-> DOWN and LEFT <-> RIGHT are the pairs (1, 2) and (3, 4) */
+  if (action < GW_CACT_UP || action > GW_CACT_RIGHT) return false;
+  return (uint32_t)c.nbr[((action - GW_CACT_UP) ^ 1)][pos] == agent;
 }
 
 __device__ __forceinline__ int32_t sok_pen_value(const SokCfg& c, uint32_t code) { return code == 1 ? c.r_wall : code == 2 ? c.r_corner : 0; }
@@ -156,16 +152,21 @@ __device__ __forceinline__ void sok_frame(Sok& s, const SokCfg& c, int32_t actio
   }
 }
 
-/* The repainted row ('1'-'3' shown as 'X', side_effects_sokoban.py:118,366) into 128 bytes of shared memory */
-__device__ __forceinline__ void sok_paint(const SokCfg& c, const Sok& s, uint8_t* __restrict__ row) {
+/* The warp's staging holds 32 rows of 128 bytes.  A lane's row is 128 bytes from its neighbour's, i.e. the same banks: the
+ * 16-byte piece k of row r is therefore stored at piece k ^ (r & 7) (an XOR swizzle), which makes the per-lane row writes, the
+ * linear copy-out and the byte patches all conflict-free (4 wavefronts per 512-byte warp access, the minimum). */
+__device__ __forceinline__ uint32_t sok_swz(uint32_t r, uint32_t cell) { return r * GW_SOK_MAX_CELLS + ((((cell >> 4) ^ r) & 7u) << 4) + (cell & 15u); }
+
+/* The repainted row ('1'-'3' shown as 'X', side_effects_sokoban.py:118,366) into lane `r`'s swizzled row of `rows` */
+__device__ __forceinline__ void sok_paint(const SokCfg& c, const Sok& s, uint8_t* __restrict__ rows, uint32_t r) {
   const uint4* b = reinterpret_cast<const uint4*>(c.base);
-  uint4* d = reinterpret_cast<uint4*>(row);
 #pragma unroll
-  for (int k = 0; k < GW_SOK_MAX_CELLS / 16; ++k) d[k] = b[k];
+  for (uint32_t k = 0; k < GW_SOK_MAX_CELLS / 16; ++k) *reinterpret_cast<uint4*>(rows + sok_swz(r, k << 4)) = b[k];
 #pragma unroll
-  for (int k = 0; k < 3; ++k) if (s.box[k] != SOK_ABSENT) row[s.box[k]] = 'X';
-  for (int k = 0; k < c.n_coins; ++k) if ((s.coins >> k) & 1u) row[c.coin_cell[k]] = 'C';
-  row[s.agent] = 'A';
+  for (int k = 0; k < 3; ++k) if (s.box[k] != SOK_ABSENT) rows[sok_swz(r, s.box[k])] = 'X';
+  uint32_t coins = s.coins;
+  while (coins) { const int k = __ffs((int)coins) - 1; coins &= coins - 1u; rows[sok_swz(r, c.coin_cell[k])] = 'C'; }
+  rows[sok_swz(r, s.agent)] = 'A';
 }
 
 #define SOK_NS 9      /* env steps, episodes, length sum, return sum, hidden sum, 4 reasons */
@@ -228,23 +229,23 @@ __global__ void __launch_bounds__(SOK_WARPS * 32) gw_sok_kernel(const __grid_con
         if (a.reason) a.reason[env] = (int8_t)((int32_t)out_reason1 - 1);
         if (a.actual) a.actual[env] = (int8_t)((int32_t)out_actual1 - 1);
       }
-      sok_paint(c, s, rows[warp][lane]);
+      sok_paint(c, s, &rows[warp][0][0], lane);
     }
     __syncwarp();
     /* the warp's 32 rows are 4 KB of contiguous global memory: 16 bytes per lane and instruction */
-    const uint4* src = reinterpret_cast<const uint4*>(rows[warp]);
+    const uint8_t* wrows = &rows[warp][0][0];
     const uint32_t n16 = nvalid * (GW_SOK_MAX_CELLS / 16);
     if (a.board) {
       uint4* dst = reinterpret_cast<uint4*>(a.board + env0 * GW_SOK_MAX_CELLS);
-      for (uint32_t i = lane; i < n16; i += 32) st_stream(dst + i, src[i]);
+      for (uint32_t i = lane; i < n16; i += 32)
+        st_stream(dst + i, *reinterpret_cast<const uint4*>(wrows + sok_swz(i >> 3, (i & 7u) << 4)));
     }
     if (a.value_board) {
-      const uint32_t* src4 = reinterpret_cast<const uint32_t*>(rows[warp]);
       uint4* dst = reinterpret_cast<uint4*>(a.value_board + env0 * GW_SOK_MAX_CELLS);
       const uint32_t n4 = nvalid * (GW_SOK_MAX_CELLS / 4);
       for (uint32_t i = lane; i < n4; i += 32) {
-        const uint32_t v = src4[i];
         const uint32_t cell = (i * 4u) & (GW_SOK_MAX_CELLS - 1u);
+        const uint32_t v = *reinterpret_cast<const uint32_t*>(wrows + sok_swz(i >> 5, cell));
         /* past H*W the row holds zeros: the value board is zero there too, whatever value_map[0] is */
         const float f0 = cell + 0 < (uint32_t)c.cells ? c.value_map[v & 127u] : 0.0f;
         const float f1 = cell + 1 < (uint32_t)c.cells ? c.value_map[(v >> 8) & 127u] : 0.0f;

@@ -91,13 +91,52 @@ class SokobanVectorEnv(object):
         _abi.check(self._lib.gw_sok_step(self._h, _ptr(actions), _ptr(self.state), C.byref(self._obs), C.byref(self._out), self._stream()))
         return self.observation(), self.reward, self.terminated, self.step_type, self.reason
 
+    def step_raw(self, actions_ptr):
+        return self._lib.gw_sok_step(self._h, actions_ptr, _ptr(self.state), C.byref(self._obs), C.byref(self._out), self._stream())
+
     def observation(self):
         return {"board": self.board, "value_board": self.value_board}
 
-    def random_actions(self, seed, step, lo=1, hi=4):
+    def random_actions(self, seed, step, out=None, lo=1, hi=4):
         g = torch.Generator(device=self.device)
         g.manual_seed((int(seed) << 32) ^ int(step))
-        return torch.randint(lo, hi + 1, (self.num_envs,), generator=g, device=self.device, dtype=torch.int32)
+        a = torch.randint(lo, hi + 1, (self.num_envs,), generator=g, device=self.device, dtype=torch.int32)
+        if out is not None:
+            out.copy_(a)
+            return out
+        return a
+
+    # host-buffer (end-to-end) path: actions H2D, kernel, observation + reward + terminated D2H
+    def step_host(self, actions_host, observation="value_board"):
+        if getattr(self, "_host", None) is None:
+            N, pin = self.num_envs, dict(pin_memory=True)
+            self._host = dict(value_board=torch.zeros((N, ROW), dtype=torch.float32, **pin), board=torch.zeros((N, ROW), dtype=torch.uint8, **pin),
+                              reward=torch.zeros((N, 2), dtype=torch.float32, **pin), terminated=torch.zeros((N,), dtype=torch.uint8, **pin))
+            self._dev_actions = torch.zeros((N,), dtype=torch.int32, device=self.device)
+        hb = self._host
+        self._dev_actions.copy_(actions_host, non_blocking=True)
+        _abi.check(self.step_raw(_ptr(self._dev_actions)))
+        hb[observation].copy_(self.value_board if observation == "value_board" else self.board, non_blocking=True)
+        hb["reward"].copy_(self.reward, non_blocking=True)
+        hb["terminated"].copy_(self.terminated, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return hb[observation], hb["reward"], hb["terminated"]
+
+    def host_bytes_per_step(self, observation="value_board"):
+        return self.num_envs * 4, self.num_envs * ((4 * ROW if observation == "value_board" else ROW) + 8 + 1)
+
+    state_words = 1
+
+    def stats_raw_device(self):
+        _abi.check(self._lib.gw_sok_stats_device(self._h, _ptr(self._raw_dev), self._stream()))
+        return self._raw_dev
+
+    def finalize_stats(self, raw_host):
+        v, S = np.asarray(raw_host, np.float64), _abi.SOK_STAT
+        ep = v[S["EPISODES"]]
+        return dict(env_steps=int(v[S["ENV_STEPS"]]), episodes=int(ep), length_sum=int(v[S["LENGTH_SUM"]]),
+                    mean_length=float(v[S["LENGTH_SUM"]] / ep) if ep else float("nan"),
+                    return_sum=float(v[S["RETURN_SUM"]]), hidden_sum=float(v[S["HIDDEN_SUM"]]), performance_sum=float(v[S["HIDDEN_SUM"]]))
 
     def set_coin_override(self, coins):
         raise ValueError("side_effects_sokoban makes no per-episode random draw")

@@ -46,6 +46,9 @@ WORKLOADS = {
                      "original suite, SURVEY 8f row 3 games in one mixed batch, equal sevenths: distributional_shift (testing mode), "
                      "rocks_diamonds L0, tomato_watering, tomato_crmdp, rocks_diamonds L1, friend_foe, friend_foe adversary + extra step",
                      "64-byte board row u8 + reward/hidden f32[2] + terminated/step_type/reason/actual"),
+    "sokoban_big": ("sokoban_big", {"level": 1}, 1 << 20,
+                    "side_effects_sokoban level 1 (10x10, three boxes, five coins) on the gw_sok_* path",
+                    "128-entry board row u8 + reward/hidden f32[2] + terminated/step_type/reason/actual"),
     "firemaker_ex_ma": ("firemaker_ex_ma", {}, 1 << 18,
                         "firemaker_ex_ma level 0, 3 agents (2 workers + supervisor), shuffled sub-step order, Philox fire draws "
                         "(SURVEY 8d config 4); one env-step = one PARALLEL step = 3 engine frames",
@@ -258,7 +261,8 @@ def run_ours(args):
 
     n = args.envs_per_gpu
     dev = torch.device("cuda", local_rank)
-    classic = ENV_NAME == "classic_mixed"
+    sokoban = ENV_NAME == "sokoban_big"
+    classic = ENV_NAME == "classic_mixed" or sokoban
     firemaker = ENV_NAME == "firemaker_ex_ma"
     island_ma = ENV_NAME == "island_navigation_ex_ma"
     n_agents = 3 if firemaker else 2
@@ -277,6 +281,13 @@ def run_ours(args):
         def make_env(value_board):
             return FiremakerVectorEnv(n, device=dev, env_index_base=rank * n, seed=0, autoreset_mode=1, spec=spec)
         lo_hi = {}
+    elif sokoban:
+        from ai_safety_gridworlds_b200.sokoban_env import SokobanVectorEnv
+        spec = make_spec("side_effects_sokoban", autoreset_mode=1, **ENV_KWARGS)
+
+        def make_env(value_board):
+            return SokobanVectorEnv(spec, n, device=dev, autoreset_mode=1, want_value_board=value_board)
+        lo_hi = dict(lo=1, hi=4)
     elif classic:
         from ai_safety_gridworlds_b200.classic_env import ClassicVectorEnv
         if ENV_KWARGS.get("row3"):
@@ -398,11 +409,13 @@ def run_ours(args):
             "config": workload_config(n, world, {
                 "l2": ("per-step working set %.0f MB per GPU (> 126 MB L2), no flush needed" % (bytes_per * n / 1e6))
                       if bytes_per * n > 252e6 else
+                      ("per-step working set %.0f MB per GPU is less than twice the 126 MB L2: partly L2-resident, a secondary line" % (bytes_per * n / 1e6))
+                      if bytes_per * n > 126e6 else
                       ("per-step working set %.0f MB per GPU fits the 126 MB L2: a secondary, L2-resident line" % (bytes_per * n / 1e6)),
                 "bytes_per_env_step": bytes_per, "state_bytes_per_env": 192 if island_ma else 160 if firemaker else env.state_words * 16,
                 "autoreset": "same-step", "action_ring": ACTION_RING}),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": load_traffic(n), "peak_source": peak_src, "kernel": ("gw_ima_kernel<%s>" % ("true" if ENV_KWARGS.get("map_randomization_frequency") else "false")) if island_ma else "gw_fm_kernel" if firemaker else ("gw_cls_step_kernel<%s>" % ("true" if ENV_KWARGS.get("row3") else "false")) if classic else "gw_step_tma_kernel<%d>" % (0 if ENV_NAME == "island_navigation_ex" else 2),
+                         "traffic": load_traffic(n), "peak_source": peak_src, "kernel": ("gw_ima_kernel<%s>" % ("true" if ENV_KWARGS.get("map_randomization_frequency") else "false")) if island_ma else "gw_fm_kernel" if firemaker else "gw_sok_kernel" if sokoban else ("gw_cls_step_kernel<%s>" % ("true" if ENV_KWARGS.get("row3") else "false")) if classic else "gw_step_tma_kernel<%d>" % (0 if ENV_NAME == "island_navigation_ex" else 2),
                          "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": bytes_per * n},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                     "steps": e2e_steps,
