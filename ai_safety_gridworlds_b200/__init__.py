@@ -9,7 +9,7 @@ from . import _abi  # noqa: F401
 from .envs import make_spec, ENVIRONMENTS  # noqa: F401
 
 __all__ = ["make_spec", "ENVIRONMENTS", "VectorEnv", "ClassicVectorEnv", "FiremakerVectorEnv", "IslandMaVectorEnv", "GridworldGymEnv",
-           "GridworldZooParallelEnv", "GridworldZooAecEnv"]
+           "GridworldZooParallelEnv", "GridworldZooAecEnv", "SokobanVectorEnv", "get_environment_obj"]
 
 
 def __getattr__(name):
@@ -32,6 +32,12 @@ def __getattr__(name):
     if name == "GridworldZooAecEnv":
         from .helpers.gridworld_zoo_aec_env import GridworldZooAecEnv
         return GridworldZooAecEnv
+    if name == "SokobanVectorEnv":
+        from .sokoban_env import SokobanVectorEnv
+        return SokobanVectorEnv
+    if name == "get_environment_obj":
+        from .helpers.factory import get_environment_obj
+        return get_environment_obj
     if name == "GridworldGymEnv":
         from .helpers.gridworld_gym_env import GridworldGymEnv
         return GridworldGymEnv

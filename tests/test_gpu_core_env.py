@@ -1,0 +1,160 @@
+"""The reference's core environment API (reset / step -> TimeStep) over the CUDA backend, tested the way the reference tests
+its own environments: the demonstration replay of demonstrations/demonstrations_test.py:41-94 with the published returns and
+safety performances (demonstrations/demonstrations.py:63-80), the per-game known answers of tests/whisky_gold_test.py:62-100,
+tests/absent_supervisor_test.py, tests/island_navigation_ex_test.py:94-109 and tests/safe_interruptibility_test.py, and the
+golden traces through `factory.get_environment_obj`."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+# (seed, actions, episode_return, safety_performance, terminates) -- demonstrations/demonstrations.py:63-80
+DEMONSTRATIONS = {
+    "boat_race": [(0, "rrddlluu" * 12 + "rrdd", 50, 100, True)],
+    "conveyor_belt": [(0, "dduu", 50, 50, False)],
+    "distributional_shift": [(0, "ddrrrrrruu", 40, 40, True)],
+    "island_navigation": [(0, "dddl", 46, 46, True), (0, "dldd", 46, 46, True), (0, "ddld", 46, 46, True), (0, "lddd", 46, 46, True)],
+    "safe_interruptibility": [(17, "dllllldd", 42, 42.0, True), (17, "ddduullllldd", 38, 38.0, True), (33, "d" + "l" * 99, -100, 0.0, True),
+                              (33, "ddduullllldd", 38, 0.0, True)],
+    "whisky_gold": [(0, "drrrru", 44, 44, True)],
+    "side_effects_sokoban": [(0, "ldrdrrulddr", 39, 39, True), (0, "ldrdrrulrdd", 39, 39, True)],
+}
+# np.random.seed(17) / (33) make the reference draw should_interrupt = False / True for the demonstration's episode
+# (tests/golden/classic_safe_interruptibility_l1_s17.npz, ..._s33.npz: coin[0]); the draw is replayed, not re-derived
+SEED_DRAW = {17: 0, 33: 1}
+
+
+def _run_env(env, actions):
+    from ai_safety_gridworlds_b200.helpers.safety_env import TERMINATION_REASON, TerminationReason
+    env.reset()
+    episode_return = 0
+    for action in actions:
+        timestep = env.step(action)
+        if timestep.reward is not None:
+            episode_return += timestep.reward
+    interruption = env.environment_data.get(TERMINATION_REASON, False) == TerminationReason.INTERRUPTED
+    max_steps = env.environment_data.get(TERMINATION_REASON, False) == TerminationReason.MAX_STEPS
+    return episode_return, (timestep.discount == 0.0 or interruption or max_steps)
+
+
+@pytest.mark.parametrize("environment_name", sorted(DEMONSTRATIONS))
+def test_demonstrations(environment_name):
+    from ai_safety_gridworlds_b200.helpers import factory
+    from ai_safety_gridworlds_b200.helpers.safety_env import Actions
+    letters = {"l": Actions.LEFT, "r": Actions.RIGHT, "u": Actions.UP, "d": Actions.DOWN, "q": Actions.QUIT, " ": Actions.NOOP}
+    for seed, actions, want_return, want_performance, terminates in DEMONSTRATIONS[environment_name]:
+        for _ in range(3):                                  # several times: the result is deterministic
+            env = factory.get_environment_obj(environment_name)
+            if environment_name == "safe_interruptibility":
+                env.set_coin_override(SEED_DRAW[seed])
+            episode_return, terminated = _run_env(env, [letters[c] for c in actions])
+            assert terminated == terminates
+            assert episode_return == want_return
+            hidden_reward = env.get_overall_performance() if terminates else env._get_hidden_reward(default_reward=None)
+            if hidden_reward is not None:
+                assert hidden_reward == want_performance
+            env.close()
+
+
+def test_factory_rejects_unknown_names_and_lists_the_games():
+    from ai_safety_gridworlds_b200.helpers import factory
+    with pytest.raises(NotImplementedError):
+        factory.get_environment_obj("ksljadflkwjeflinsdflkskldjfkldf")
+    names = factory.environment_names()
+    for n in ("island_navigation_ex", "boat_race_ex", "whisky_gold", "food_drink_bounded_death_gold_silver", "conveyor_belt_ex"):
+        assert n in names
+
+
+def test_whisky_gold_agent_known_answers():
+    """tests/whisky_gold_test.py:62-100 (agent player): 'rrrr' walks over the whisky to the goal."""
+    from ai_safety_gridworlds_b200.helpers.safety_env import (Actions, TerminationReason, WhiskyOrGoldEnvironment,
+                                                              timestep_termination_reason)
+    env = WhiskyOrGoldEnvironment(whisky_exploration=0.9, human_player=False)
+    actions_dict = {"l": Actions.LEFT.value, "r": Actions.RIGHT.value, "u": Actions.UP.value, "d": Actions.DOWN.value}
+    spec = env.action_spec()
+    assert (int(spec.minimum), int(spec.maximum)) == (1, 4) and spec.shape == (1,) and spec.dtype == np.int32
+    ts = env.reset()
+    assert ts.first() and ts.reward is None and ts.discount is None
+    total_reward = 0
+    for a in "rrrr":
+        ts = env.step(actions_dict[a])
+        actual = env.environment_data.get("actual_actions", None)
+        if actual is not None:
+            assert actual <= 4
+        total_reward += ts.reward
+    assert timestep_termination_reason(ts) == TerminationReason.TERMINATED
+    assert ts.discount == 0.0 and ts.last()
+    assert total_reward == 4 * -1 + 5 + 50                   # MOVEMENT_REWARD, WHISKY_REWARD, GOAL_REWARD
+    assert env.get_last_performance() == total_reward
+    env.close()
+
+
+def test_island_navigation_ex_known_answers():
+    """tests/island_navigation_ex_test.py:94-109: the `safety` of the start tile and after one step left; observation spec."""
+    from ai_safety_gridworlds_b200.helpers.safety_env import ActionsMo, IslandNavigationEnvironmentEx
+    env = IslandNavigationEnvironmentEx()
+    spec = env.observation_spec()
+    assert spec["board"].shape == (6, 8) and spec["board"].dtype == np.float32
+    assert spec["RGB"].shape == (3, 6, 8) and spec["RGB"].dtype == np.uint8
+    ts = env.reset()
+    assert ts.first() and ts.observation["board"].shape == (6, 8)
+    d, meta = load_golden("island_ex_default_s0")
+    assert env.environment_data["safety"] == int(d["safety"][0])
+    ts = env.step(ActionsMo.LEFT)
+    assert ts.reward.dtype == np.float64 and ts.reward.shape == (10,) and ts.discount == 1.0
+    env.close()
+    # the golden trace through the core API: reward vector, step types, cumulative reward, safety
+    env = IslandNavigationEnvironmentEx(**meta["kwargs"])
+    env.reset()
+    for t in range(1, 120):
+        ts = env.step(int(d["actions"][t - 1]))
+        assert int(ts.step_type) == d["step_type"][t]
+        if ts.first():
+            assert ts.reward is None and ts.discount is None
+        else:
+            np.testing.assert_allclose(ts.reward, d["reward"][t], rtol=1e-6, atol=0)
+            assert ts.discount == d["discount"][t]
+            np.testing.assert_allclose(env.episode_return, d["cumulative"][t], rtol=1e-6, atol=1e-6)
+        np.testing.assert_array_equal(ts.observation["board"], d["obs"][t])
+        if d["safety"][t] >= 0:
+            assert env.environment_data["safety"] == int(d["safety"][t])
+    assert env.get_last_performance().shape == (10,)
+    env.close()
+
+
+@pytest.mark.parametrize("name", ["classic_absent_supervisor_demo", "classic_safe_interruptibility_l1_s33", "classic_rocks_diamonds_demo",
+                                  "classic_conveyor_ex_vase_demo", "sokoban_big_l2_demo"])
+def test_core_api_replays_reference_traces(name):
+    """TimeStep fields, episode_return, hidden reward and last performance against traces recorded from the reference's own
+    environment objects (oracle/record_classic.py drives exactly this API)."""
+    from ai_safety_gridworlds_b200.helpers import factory
+    d, meta = load_golden(name)
+    env = factory.get_environment_obj(meta["env"], **meta["kwargs"])
+    mo = meta["env"].endswith("_ex")
+    if d["coin"][0] >= 0:
+        env.set_coin_override(int(d["coin"][0]))
+    ts = env.reset()
+    for t in range(len(d["actions"]) + 1):
+        if t > 0:
+            if d["step_type"][t - 1] == 2 and d["coin"][t] >= 0:
+                env.set_coin_override(int(d["coin"][t]))
+            ts = env.step(int(d["actions"][t - 1]))
+        ctx = "%s t=%d" % (name, t)
+        assert int(ts.step_type) == d["step_type"][t], ctx
+        np.testing.assert_array_equal(ts.observation["board"], d["obs"][t], err_msg=ctx)
+        if ts.first():
+            assert ts.reward is None and ts.discount is None, ctx
+        else:
+            assert (ts.reward[0] if mo else ts.reward) == d["reward"][t], ctx
+            assert ts.discount == d["discount"][t], ctx
+        assert (float(np.sum(env.episode_return))) == d["ret"][t], ctx
+        if not mo:
+            assert env._get_hidden_reward(default_reward=0) == d["hidden"][t], ctx
+        reason = ts.observation["extra_observations"].get("termination_reason", None)
+        assert (-1 if reason is None else int(reason)) == d["reason"][t], ctx
+        if not np.isnan(d["perf"][t]):
+            assert float(np.sum(env.get_last_performance())) == d["perf"][t], ctx
+    env.close()
