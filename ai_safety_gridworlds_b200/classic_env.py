@@ -49,9 +49,15 @@ class ClassicVectorEnv(object):
                 specs.append(e.with_autoreset(autoreset_mode))
             elif isinstance(e, str):
                 specs.append(make_spec(e, autoreset_mode=autoreset_mode))
-            else:
+            elif isinstance(e, (tuple, list)) and len(e) == 2:
                 name, kwargs = e
                 specs.append(make_spec(name, autoreset_mode=autoreset_mode, **kwargs))
+            else:
+                specs.append(e)
+        for s in specs:
+            if not isinstance(s, EnvSpec):
+                raise ValueError("%s is not a mixed-batch type (side_effects_sokoban levels 1-3 run in SokobanVectorEnv)"
+                                 % getattr(s, "name", type(s).__name__))
         self.specs, self.counts = specs, [int(c) for c in counts]
         if len(self.specs) != len(self.counts) or not self.specs:
             raise ValueError("one count per environment type")

@@ -185,6 +185,9 @@ def test_classic_rejects_cube_and_wrong_constructor():
     a = env.random_actions(0, 0)
     rc = lib.gw_step(env._h, C.c_void_p(a.data_ptr()), C.c_void_p(env.state.data_ptr()), C.byref(obs), None, None)
     assert rc == _abi.GW_ERR_INVALID and b"cube" in lib.gw_last_error()
-    with pytest.raises(NotImplementedError):
-        make_spec("side_effects_sokoban", level=1)
+    assert type(make_spec("side_effects_sokoban", level=1)).__name__ == "SokSpec"       # levels 1-3: the gw_sok_* path
+    with pytest.raises(IndexError):
+        make_spec("side_effects_sokoban", level=4)                                         # GAME_ART[level]
+    with pytest.raises(ValueError):
+        ClassicVectorEnv([make_spec("side_effects_sokoban", level=1)], [8])                # not a mixed-batch type
     env.close()
