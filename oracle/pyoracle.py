@@ -228,6 +228,71 @@ class ClassicOracle(object):
 
 
 # ------------------------------------------------------------------------------------------------
+# aintelope_savanna: oracle/gw_savanna_oracle.c
+class SavannaOracle(object):
+    def __init__(self, spec, n_envs, env_index_base=0, seed=0):
+        L = lib()
+        L.orv_create.restype = C.c_void_p
+        L.orv_create.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_uint64]
+        L.orv_destroy.argtypes = [C.c_void_p]
+        L.orv_set_maps.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.orv_reset.argtypes = [C.c_void_p] + [C.c_void_p] * 8
+        L.orv_step.argtypes = [C.c_void_p] + [C.c_void_p] * 9
+        L.orv_observe.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+        self.spec, self.n = spec, int(n_envs)
+        self._h = L.orv_create(C.byref(spec.config), self.n, int(env_index_base), int(seed))
+        if not self._h:
+            raise ValueError("savanna oracle rejected the configuration")
+        n, cells, Lr, R, V = self.n, spec.cells, spec.n_layers, spec.n_rewards, spec.view
+        self.board = np.zeros((n, spec.height, spec.width), np.uint8)
+        self.cube = np.zeros((n, Lr, spec.height, spec.width), np.uint8)
+        self.crop = np.zeros((n, 2, V, V), np.uint8)
+        self.lcrop = np.zeros((n, 2, Lr, V, V), np.uint8)
+        self.reward = np.zeros((n, 2, R), np.float32)
+        self.terminated = np.zeros((n, 2), np.uint8)
+        self.step_type = np.zeros((n, 2), np.uint8)
+        # every environment plays its own layout; default: the canonical art, static
+        self.maps = np.tile(np.frombuffer("".join(spec.art).encode(), np.uint8), (n, 1)).copy()
+        self.set_maps(self.maps, 0)
+
+    def set_maps(self, maps, mode):
+        self.maps = np.ascontiguousarray(maps, np.uint8)
+        assert self.maps.shape == (self.n, self.spec.cells)
+        lib().orv_set_maps(self._h, _p(self.maps), int(mode))
+
+    def close(self):
+        if self._h:
+            lib().orv_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _outs(self):
+        return [_p(self.board), _p(self.cube), _p(self.crop), _p(self.lcrop), _p(self.reward), _p(self.terminated), _p(self.step_type)]
+
+    def reset(self, mask=None):
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        lib().orv_reset(self._h, _p(m), *self._outs())
+
+    def step(self, actions, order=None):
+        a = np.ascontiguousarray(actions, np.int32)
+        assert a.shape == (self.n, 2)
+        o = None if order is None else np.ascontiguousarray(order, np.int32)
+        lib().orv_step(self._h, _p(a), _p(o), *self._outs())
+
+    def observe(self):
+        n, R = self.n, self.spec.n_rewards
+        out = dict(metrics=np.zeros((n, 24), np.float64), cumulative=np.zeros((n, 2, R), np.float32), frame=np.zeros(n, np.int32),
+                   pos=np.zeros((n, 2, 2), np.int16), directions=np.zeros((n, 2, 2), np.int8))
+        lib().orv_observe(self._h, _p(out["metrics"]), _p(out["cumulative"]), _p(out["frame"]), _p(out["pos"]), _p(out["directions"]))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
 # side_effects_sokoban on its big maps: oracle/gw_sokoban_oracle.c
 class SokobanOracle(object):
     def __init__(self, spec, n_envs):

@@ -23,7 +23,7 @@ def _all_golden():
 
 def golden_names():
     """Traces of the multi-objective games (island_navigation_ex, boat_race_ex)."""
-    return [n for n in _all_golden() if not n.startswith(("classic_", "firemaker_", "islandma_", "sokoban_big_"))]
+    return [n for n in _all_golden() if not n.startswith(("classic_", "firemaker_", "islandma_", "sokoban_big_", "savanna_"))]
 
 
 def firemaker_golden_names():
@@ -49,6 +49,11 @@ def classic_golden_names():
 def sokoban_golden_names():
     """Traces of side_effects_sokoban for the gw_sok_* path (levels 0-3; oracle/record_classic.py)."""
     return [n for n in _all_golden() if n.startswith("sokoban_big_")]
+
+
+def savanna_golden_names():
+    """Traces of aintelope_savanna through the parallel wrapper (oracle/record_savanna.py)."""
+    return [n for n in _all_golden() if n.startswith("savanna_")]
 
 
 def load_golden(name):
