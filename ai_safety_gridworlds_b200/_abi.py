@@ -214,7 +214,7 @@ SOK_SYMBOLS = [
 
 # ---- include/gwsim_sav.h: aintelope_savanna ----
 GW_SAV_MAX_CELLS, GW_SAV_AGENTS, GW_SAV_MAX_LAYERS, GW_SAV_MAX_REWARDS, GW_SAV_MAX_RADIUS, GW_SAV_METRICS, GW_SAV_EVENTS = 256, 2, 16, 16, 10, 24, 20
-GW_SAV_STATE_BYTES = 128
+GW_SAV_STATE_BYTES = 192
 SAV_E = dict(MOVEMENT=0, FINAL=1, DRINK_DEFICIENCY=2, FOOD_DEFICIENCY=3, DRINK=4, FOOD=5, SMALL_DRINK=6, SMALL_FOOD=7, NON_DRINK=8, NON_FOOD=9,
              GAP=10, GOLD=11, SILVER=12, DANGER_TILE=13, PREDATOR=14, THIRST_HUNGER_DEATH=15, COOPERATION=16, SMALL_COOPERATION=17,
              DRINK_OVERSATIATION=18, FOOD_OVERSATIATION=19)
@@ -304,7 +304,7 @@ def load():
         raise GwError("CUDA extension %s is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
                       "there is no CPU fallback" % LIB_PATH)
     lib = C.CDLL(LIB_PATH)
-    for name, restype, argtypes in SYMBOLS + FM_SYMBOLS + IMA_SYMBOLS + SOK_SYMBOLS:
+    for name, restype, argtypes in SYMBOLS + FM_SYMBOLS + IMA_SYMBOLS + SOK_SYMBOLS + SAV_SYMBOLS:
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = restype
         fn.argtypes = argtypes
@@ -312,6 +312,8 @@ def load():
         raise GwError("libgwsim ABI %d != expected %d" % (lib.gw_abi_version(), GW_ABI_VERSION))
     if lib.gw_fm_config_bytes() != C.sizeof(GwFmConfig):
         raise GwError("GwFmConfig size mismatch: library %d, ctypes mirror %d" % (lib.gw_fm_config_bytes(), C.sizeof(GwFmConfig)))
+    if lib.gw_sav_config_bytes() != C.sizeof(GwSavConfig):
+        raise GwError("GwSavConfig size mismatch: library %d, ctypes mirror %d" % (lib.gw_sav_config_bytes(), C.sizeof(GwSavConfig)))
     if lib.gw_sok_config_bytes() != C.sizeof(GwSokConfig):
         raise GwError("GwSokConfig size mismatch: library %d, ctypes mirror %d" % (lib.gw_sok_config_bytes(), C.sizeof(GwSokConfig)))
     if lib.gw_config_bytes() != C.sizeof(GwConfig):

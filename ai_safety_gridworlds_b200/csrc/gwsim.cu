@@ -1237,6 +1237,7 @@ __global__ void __launch_bounds__(GW_BLOCK) gw_random_actions_kernel(uint64_t se
 #include "gwsim_fm.cuh"
 #include "gwsim_ima.cuh"
 #include "gwsim_sok.cuh"
+#include "gwsim_sav.cuh"
 
 /* ------------------------------------------------------------------------------------------ */
 /* host side                                                                                   */
@@ -2545,5 +2546,172 @@ void gw_sok_destroy(GwSokHandle h) {
   cudaFree(h->d_stats);
   delete h;
 }
+
+}  /* extern "C" */
+
+/* ------------------------------------------------------------------------------------------ */
+/* aintelope_savanna (include/gwsim_sav.h)                                                      */
+struct GwSavEngine {
+  GwSavConfig cfg;
+  int64_t n, env_index_base;
+  int device;
+  uint64_t seed, call_no;
+  SavCfg* d_cfg;
+  unsigned long long* d_stats;
+  uint8_t* maps;
+  int32_t map_mode;
+  int grid_max;
+  int64_t launches;
+};
+
+extern "C" {
+
+int gw_sav_config_bytes(void) { return (int)sizeof(GwSavConfig); }
+
+int64_t gw_sav_state_bytes(int64_t n_envs) { return n_envs > 0 ? ((n_envs + 31) / 32) * 32 * GW_SAV_STATE_BYTES : 0; }
+
+int gw_sav_create(const GwSavConfig* cfg, int64_t n_envs, int device, int64_t env_index_base, uint64_t seed, GwSavHandle* out) {
+  if (!out) return fail(GW_ERR_INVALID, "null out handle");
+  *out = nullptr;
+  if (!cfg) return fail(GW_ERR_INVALID, "null config");
+  if (cfg->abi_version != GW_ABI_VERSION) return fail(GW_ERR_INVALID, "config ABI %d != library ABI %d", cfg->abi_version, GW_ABI_VERSION);
+  if (n_envs <= 0 || n_envs > ((int64_t)1 << 26)) return fail(GW_ERR_INVALID, "n_envs %lld outside 1..2^26", (long long)n_envs);
+  const int cells = cfg->height * cfg->width;
+  if (cfg->height < 3 || cfg->width < 3 || cells > GW_SAV_MAX_CELLS) return fail(GW_ERR_INVALID, "board %dx%d outside 3x3 .. %d cells", cfg->height, cfg->width, GW_SAV_MAX_CELLS);
+  if (cfg->n_agents < 1 || cfg->n_agents > GW_SAV_AGENTS) return fail(GW_ERR_INVALID, "n_agents %d outside 1..2", cfg->n_agents);
+  if (cfg->n_layers < 1 || cfg->n_layers > GW_SAV_MAX_LAYERS || cfg->n_rewards < 1 || cfg->n_rewards > SAV_MAXR)
+    return fail(GW_ERR_INVALID, "layers / reward dimensions out of range (at most %d layers, %d dimensions)", GW_SAV_MAX_LAYERS, SAV_MAXR);
+  if (cfg->radius < 0 || cfg->radius > GW_SAV_MAX_RADIUS) return fail(GW_ERR_INVALID, "observation radius %d outside 0..%d", cfg->radius, GW_SAV_MAX_RADIUS);
+  if (cfg->max_iterations < 1 || cfg->max_iterations > 65535) return fail(GW_ERR_INVALID, "max_iterations %d outside 1..65535", cfg->max_iterations);
+  if ((cfg->observation_direction_mode | cfg->action_direction_mode) & ~1) return fail(GW_ERR_INVALID, "direction mode 2 is not built (0 and 1 are)");
+  if (cfg->observation_direction_mode != cfg->action_direction_mode) return fail(GW_ERR_INVALID, "the two direction modes must agree");
+  if (cfg->amount[GW_SAV_T_PREDATOR] != 0) return fail(GW_ERR_INVALID, "amount_predators > 0 is not built (PredatorDrape draws random numbers during play)");
+  if (cfg->autoreset_mode != GW_AUTORESET_NEXT_STEP && cfg->autoreset_mode != GW_AUTORESET_SAME_STEP) return fail(GW_ERR_INVALID, "autoreset_mode %d", cfg->autoreset_mode);
+  int found[2] = {0, 0};
+  for (int p = 0; p < cells; ++p) { found[0] += cfg->art[p] == '0'; found[1] += cfg->art[p] == '1'; }
+  if (found[0] != 1 || found[1] != (cfg->n_agents > 1 ? 1 : 0)) return fail(GW_ERR_INVALID, "the map must hold exactly one start tile per agent");
+  SavCfg c;
+  memset(&c, 0, sizeof c);
+  c.height = cfg->height; c.width = cfg->width; c.cells = cells; c.max_iterations = cfg->max_iterations;
+  c.autoreset = cfg->autoreset_mode; c.n_agents = cfg->n_agents; c.n_layers = cfg->n_layers; c.n_rewards = cfg->n_rewards;
+  c.radius = cfg->radius; c.view = 2 * cfg->radius + 1; c.obs_mode = cfg->observation_direction_mode; c.act_mode = cfg->action_direction_mode;
+  c.randomize = cfg->randomize_order; c.death = cfg->thirst_hunger_death; c.penalise = cfg->penalise_oversatiation; c.proportional = cfg->proportional;
+  memcpy(c.amount, cfg->amount, sizeof c.amount);
+  memcpy(c.fparams, cfg->fparams, sizeof c.fparams);
+  memcpy(c.table, cfg->reward_table, sizeof c.table);
+  memcpy(c.layer_chars, cfg->layer_chars, sizeof c.layer_chars);
+  memcpy(c.art, cfg->art, sizeof c.art);
+  c.gap_layer = c.wall_layer = c.agent_layer[0] = c.agent_layer[1] = -1;
+  for (int k = 0; k < 128; ++k) c.layer_of[k] = -1;
+  for (int l = 0; l < cfg->n_layers; ++l) {
+    const uint8_t ch = cfg->layer_chars[l];
+    if (ch == ' ') c.gap_layer = l; else if (ch == '#') c.wall_layer = l;
+    else if (ch == '0') c.agent_layer[0] = l; else if (ch == '1') c.agent_layer[1] = l;
+    if (ch < 128 && ch != '0' && ch != '1') c.layer_of[ch] = (int8_t)l;
+  }
+  if (c.gap_layer < 0 || c.wall_layer < 0) return fail(GW_ERR_INVALID, "the layers must include ' ' and '#'");
+  c.layer_of['0'] = c.layer_of['1'] = (int8_t)c.gap_layer;       /* a start tile is a gap once the sprite is lifted off the map */
+  int count = 0;
+  cudaError_t ce = cudaGetDeviceCount(&count);
+  if (ce != cudaSuccess || count == 0)
+    return fail(GW_ERR_NO_DEVICE, "no CUDA device (%s); libgwsim has no CPU fallback", ce == cudaSuccess ? "device count 0" : cudaGetErrorString(ce));
+  if (device < 0 || device >= count) return fail(GW_ERR_INVALID, "device %d outside 0..%d", device, count - 1);
+  CUDA_TRY(cudaSetDevice(device));
+  GwSavEngine* h = new GwSavEngine();
+  h->cfg = *cfg; h->n = n_envs; h->env_index_base = env_index_base; h->device = device; h->seed = seed; h->call_no = 0;
+  h->d_cfg = nullptr; h->d_stats = nullptr; h->maps = nullptr; h->map_mode = GW_IMA_MAPS_STATIC; h->launches = 0;
+  int sms = 0, per_sm = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gw_sav_kernel, SAV_WARPS * 32, 0);
+  h->grid_max = (sms > 0 ? sms : 148) * (per_sm > 0 ? per_sm : 1);
+  cudaError_t e = cudaMalloc(&h->d_cfg, sizeof(SavCfg));
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_stats, (size_t)GW_STAT_REPLICAS * GW_MA_STATS_LEN * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemcpy(h->d_cfg, &c, sizeof c, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemset(h->d_stats, 0, (size_t)GW_STAT_REPLICAS * GW_MA_STATS_LEN * sizeof(unsigned long long));
+  if (e != cudaSuccess) { cudaFree(h->d_cfg); cudaFree(h->d_stats); delete h; return fail(GW_ERR_CUDA, "gw_sav_create: %s", cudaGetErrorString(e)); }
+  *out = h;
+  return GW_OK;
+}
+
+void gw_sav_destroy(GwSavHandle h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaFree(h->d_cfg);
+  cudaFree(h->d_stats);
+  delete h;
+}
+
+int gw_sav_set_maps(GwSavHandle h, uint8_t* maps, int32_t mode) {
+  if (!h) return fail(GW_ERR_INVALID, "null handle");
+  if (!maps) return fail(GW_ERR_INVALID, "aintelope_savanna needs the per-environment maps tensor");
+  if (mode < GW_IMA_MAPS_STATIC || mode > GW_IMA_MAPS_SHUFFLE_ON_RESET) return fail(GW_ERR_INVALID, "map mode %d", mode);
+  h->maps = maps; h->map_mode = mode;
+  return GW_OK;
+}
+
+static int sav_launch(GwSavHandle h, SavArgs& a, void* state, const GwSavObs* obs, const GwSavOut* out, cudaStream_t stream) {
+  if (!h || !state) return fail(GW_ERR_INVALID, "null argument");
+  if (!h->maps) return fail(GW_ERR_INVALID, "gw_sav_set_maps has not been called");
+  if ((uintptr_t)state & 15u) return fail(GW_ERR_INVALID, "state must be 16-byte aligned");
+  a.cfg = h->d_cfg; a.state = (uint4*)state; a.maps = h->maps; a.n = h->n; a.stats = h->d_stats;
+  if (obs) { a.board = obs->board; a.cube = obs->cube; a.crop = obs->crop; a.lcrop = obs->lcrop; }
+  if (out) { a.reward = out->reward; a.terminated = out->terminated; a.step_type = out->step_type; }
+  a.seed = h->seed; a.call_no = ++h->call_no; a.env_index_base = h->env_index_base;
+  a.map_shuffle = h->map_mode;
+  CUDA_TRY(cudaSetDevice(h->device));
+  int64_t grid = (h->n + SAV_WARPS - 1) / SAV_WARPS;
+  if (grid > h->grid_max) grid = h->grid_max;
+  gw_sav_kernel<<<(unsigned)grid, SAV_WARPS * 32, 0, stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 1;
+  return GW_OK;
+}
+
+int gw_sav_reset(GwSavHandle h, const uint8_t* reset_mask, void* state, const GwSavObs* obs, const GwSavOut* out, void* stream) {
+  SavArgs a;
+  memset(&a, 0, sizeof a);
+  a.is_reset = 1; a.reset_mask = reset_mask;
+  return sav_launch(h, a, state, obs, out, (cudaStream_t)stream);
+}
+
+int gw_sav_step(GwSavHandle h, const int32_t* actions, const int32_t* order, void* state, const GwSavObs* obs, const GwSavOut* out,
+                void* stream) {
+  if (!actions) return fail(GW_ERR_INVALID, "null actions");
+  SavArgs a;
+  memset(&a, 0, sizeof a);
+  a.actions = actions; a.order = order;
+  return sav_launch(h, a, state, obs, out, (cudaStream_t)stream);
+}
+
+int gw_sav_observe(GwSavHandle h, const void* state, const GwSavExtras* ex, void* stream) {
+  if (!h || !state || !ex) return fail(GW_ERR_INVALID, "null argument");
+  SavObserveArgs a;
+  a.cfg = h->d_cfg; a.state = (const uint4*)state; a.metrics = ex->metrics; a.cumulative = ex->cumulative; a.frame = ex->frame;
+  a.pos = ex->pos; a.directions = ex->directions; a.n = h->n;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const unsigned grid = (unsigned)((h->n + GW_BLOCK - 1) / GW_BLOCK);
+  gw_sav_observe_kernel<<<grid, GW_BLOCK, 0, (cudaStream_t)stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 1;
+  return GW_OK;
+}
+
+int gw_sav_stats_device(GwSavHandle h, double* device_raw_out, void* stream) {
+  if (!h || !device_raw_out) return fail(GW_ERR_INVALID, "null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  gw_ma_stats_fold_kernel<<<1, GW_MA_STATS_LEN, 0, (cudaStream_t)stream>>>(h->d_stats, device_raw_out);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 1;
+  return GW_OK;
+}
+
+int gw_sav_stats_clear(GwSavHandle h, void* stream) {
+  if (!h) return fail(GW_ERR_INVALID, "null handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaMemsetAsync(h->d_stats, 0, (size_t)GW_STAT_REPLICAS * GW_MA_STATS_LEN * sizeof(unsigned long long), (cudaStream_t)stream));
+  return GW_OK;
+}
+
+int64_t gw_sav_launch_count(GwSavHandle h) { return h ? h->launches : 0; }
 
 }  /* extern "C" */

@@ -1,0 +1,390 @@
+/*
+ * gwsim_sav.cuh -- aintelope_savanna (include/gwsim_sav.h).  Included by gwsim.cu (shares its helpers).
+ *
+ * One WARP per environment (persistent warps, grid-stride): the output of a parallel step is ~8 KB per agent (a 21 x 21 rotated
+ * view in 12 layers next to the 13 x 13 board and its cube), so the kernel is a renderer with a little game logic in front of it:
+ *   1. the lanes bring the environment's 192-byte state and its own map (<= 256 bytes, caller-owned `maps` tensor) into shared
+ *      memory;
+ *   2. lane 0 plays the frames of the step -- one Engine.play per live agent in (shuffled) order: relative action -> move ->
+ *      AgentSprite.update_reward -> WaterDrape; or starts a new game (Philox Fisher-Yates shuffle of the layout when the library
+ *      draws the maps);
+ *   3. all lanes render board, cube, and per agent the rotated view and its layers from a per-cell "which layer is this" byte.
+ * State (GW_SAV_STATE_BYTES = 192): frame, per agent position / directions / flags, satiations (fp64), visit counters, the
+ * per-agent episode returns (fp32).  The resources' shared availability is not state: without the sustainability challenge the
+ * drapes reset it to the amount_* flag at the end of every frame (aintelope_savanna.py:1232-1236).
+ */
+#pragma once
+
+#include "../../include/gwsim_sav.h"
+
+#define SAV_WARPS 4
+#define SAV_MAXR 14                      /* 2 * R must fit the raw statistics vector (GW_MA_STATS_LEN - 4) */
+
+struct SavCfg {
+  int32_t height, width, cells, max_iterations;
+  int32_t autoreset, n_agents, n_layers, n_rewards;
+  int32_t radius, view, obs_mode, act_mode;
+  int32_t randomize, death, penalise, proportional;
+  int32_t amount[8];
+  int32_t gap_layer, wall_layer, agent_layer[2], pad[4];
+  double fparams[32];
+  double table[GW_SAV_EVENTS][GW_SAV_MAX_REWARDS];
+  uint8_t layer_chars[GW_SAV_MAX_LAYERS];
+  int8_t layer_of[128];                  /* ASCII code -> layer index (agents' start tiles and ' ' -> the gap layer), -1 = none */
+  uint8_t art[GW_SAV_MAX_CELLS];         /* canonical layout: what the library shuffles */
+};
+static_assert(sizeof(SavCfg) % 16 == 0, "SavCfg is copied in 16-byte pieces");
+
+struct SavArgs {
+  const SavCfg* cfg;
+  const int32_t* actions;                /* [N, 2] */
+  const int32_t* order;                  /* [N, 2] or NULL */
+  const uint8_t* reset_mask;
+  uint4* state;                          /* [N] x 12 words */
+  uint8_t* maps;                         /* [N, cells] */
+  uint8_t *board, *cube, *crop, *lcrop;
+  float* reward;
+  uint8_t *terminated, *step_type;
+  unsigned long long* stats;
+  uint64_t seed, call_no;
+  int64_t env_index_base, n;
+  int32_t is_reset, map_shuffle;         /* map_shuffle: the library draws a fresh layout for every game that starts in this call */
+};
+
+struct SavState {                        /* 192 bytes, the layout of one environment's state in global memory */
+  uint32_t frame;
+  uint8_t pos[2];
+  uint8_t flags[2];                      /* adir | odir << 2 | terminated << 4 | step_type << 5 */
+  double dsat[2], fsat[2];
+  uint16_t visits[2][7];
+  uint8_t pad[4];
+  float cum[2][SAV_MAXR];
+  uint8_t pad2[8];
+};
+static_assert(sizeof(SavState) == GW_SAV_STATE_BYTES, "state layout");
+
+__device__ __forceinline__ bool sav_is_drape(uint8_t ch) {
+  return ch == 'W' || ch == 'P' || ch == 'D' || ch == 'F' || ch == 'd' || ch == 'f' || ch == 'G' || ch == 'S';
+}
+
+__device__ __forceinline__ int sav_relative_to_absolute(int action, int dir) {        /* safety_game_ma.py:505-587, mode 1 */
+  const int opposite[4] = {GW_DIR_RIGHT, GW_DIR_LEFT, GW_DIR_DOWN, GW_DIR_UP};
+  const int turn_left[4] = {GW_DIR_DOWN, GW_DIR_UP, GW_DIR_LEFT, GW_DIR_RIGHT};
+  const int turn_right[4] = {GW_DIR_UP, GW_DIR_DOWN, GW_DIR_RIGHT, GW_DIR_LEFT};
+  if (action == GW_ACT_UP) return dir;
+  if (action == GW_ACT_DOWN) return opposite[dir];
+  if (action == GW_ACT_LEFT) return turn_left[dir];
+  return turn_right[dir];
+}
+
+struct SavRun {                          /* lane 0's working copy */
+  int pos[2], adir[2], odir[2], term[2], st[2];
+  double r[2][SAV_MAXR];
+};
+
+__device__ __forceinline__ void sav_add(const SavCfg& c, SavRun& w, int agent, int event, double scale) {
+  for (int d = 0; d < c.n_rewards; ++d) w.r[agent][d] += c.table[event][d] * scale;
+}
+
+__device__ __forceinline__ void sav_consume(const SavCfg& c, SavState& s, SavRun& w, int a, uint8_t pos_chr, uint8_t big, uint8_t small,
+                                            int visit_slot, int tile_big, int tile_small, double* satiation, int e_big, int e_small,
+                                            int e_none, double rate_big, double rate_small, double limit, double* avail /*[2]*/) {
+  if (pos_chr == big || pos_chr == small) {
+    const int is_small = pos_chr == small;
+    double& av = avail[is_small];
+    const double rate = is_small ? rate_small : rate_big;
+    s.visits[a][visit_slot + is_small] += 1;
+    if (av > 0) {
+      sav_add(c, w, a, is_small ? e_small : e_big, 1.0);
+      if (c.penalise) *satiation += fmin(av, rate);
+      if (limit >= 0 && *satiation > 0) *satiation = fmin(limit, *satiation);
+      av = fmax(0.0, av - rate);
+    }
+    if (c.n_agents > 1) sav_add(c, w, 1 - a, is_small ? GW_SAV_E_SMALL_COOPERATION : GW_SAV_E_COOPERATION, 1.0);
+  } else sav_add(c, w, a, e_none, 1.0);
+  (void)tile_big; (void)tile_small;
+}
+
+/* One Engine.play({agent: {"step": action}}) -- aintelope_savanna.py:1030-1046, 810-1028, 1065-1079; the board reads it makes
+ * (the cell the agent walks into) are answered from the map and the positions */
+__device__ __forceinline__ void sav_play(const SavCfg& c, SavState& s, SavRun& w, const uint8_t* __restrict__ art, int a, int action) {
+  const double* F = c.fparams;
+  s.frame += 1;
+  if (action != GW_ACT_NOOP && c.obs_mode == 1) w.odir[a] = sav_relative_to_absolute(action, w.odir[a]);
+  if (action != GW_ACT_NOOP) {
+    int dir;
+    if (c.act_mode == 1) dir = sav_relative_to_absolute(action, w.adir[a]);
+    else dir = action == GW_ACT_LEFT ? GW_DIR_LEFT : action == GW_ACT_RIGHT ? GW_DIR_RIGHT : action == GW_ACT_UP ? GW_DIR_UP : GW_DIR_DOWN;
+    const int dr = dir == GW_DIR_UP ? -1 : dir == GW_DIR_DOWN ? 1 : 0, dc = dir == GW_DIR_LEFT ? -1 : dir == GW_DIR_RIGHT ? 1 : 0;
+    const int nr = w.pos[a] / c.width + dr, nc = w.pos[a] % c.width + dc;
+    if (nr >= 0 && nr < c.height && nc >= 0 && nc < c.width) {
+      const int q = nr * c.width + nc;
+      const bool other = c.n_agents > 1 && q == w.pos[1 - a];
+      if (art[q] != '#' && !other) w.pos[a] = q;                                  /* impassable: '#' and the other agent */
+    }
+    if (c.act_mode == 1) w.adir[a] = dir;
+  }
+  /* update_reward */
+  const bool drink_on = c.amount[GW_SAV_T_DRINK] > 0 || c.amount[GW_SAV_T_SMALL_DRINK] > 0;
+  const bool food_on = c.amount[GW_SAV_T_FOOD] > 0 || c.amount[GW_SAV_T_SMALL_FOOD] > 0;
+  if (action != GW_ACT_NOOP) sav_add(c, w, a, GW_SAV_E_MOVEMENT, 1.0);
+  if (drink_on && c.penalise) s.dsat[a] += F[GW_SAV_F_DRINK_DEFICIENCY_RATE];
+  if (food_on && c.penalise) s.fsat[a] += F[GW_SAV_F_FOOD_DEFICIENCY_RATE];
+  if (c.death && (s.dsat[a] <= F[GW_SAV_F_DRINK_DEFICIENCY_LIMIT] || s.fsat[a] <= F[GW_SAV_F_FOOD_DEFICIENCY_LIMIT])) {
+    sav_add(c, w, a, GW_SAV_E_THIRST_HUNGER_DEATH, 1.0);
+    w.term[a] = 1;
+  }
+  const uint8_t pos_chr = art[w.pos[a]];
+  if (pos_chr == 'U') { sav_add(c, w, a, GW_SAV_E_FINAL, 1.0); w.term[a] = 1; }
+  /* the shared availabilities start every frame at the amount_* flags (reset at the end of the previous frame) */
+  double dav[2] = {(double)c.amount[GW_SAV_T_DRINK], (double)c.amount[GW_SAV_T_SMALL_DRINK]};
+  double fav[2] = {(double)c.amount[GW_SAV_T_FOOD], (double)c.amount[GW_SAV_T_SMALL_FOOD]};
+  sav_consume(c, s, w, a, pos_chr, 'D', 'd', 1, 0, 0, &s.dsat[a], GW_SAV_E_DRINK, GW_SAV_E_SMALL_DRINK, GW_SAV_E_NON_DRINK,
+              F[GW_SAV_F_DRINK_EXTRACTION_RATE], F[GW_SAV_F_SMALL_DRINK_EXTRACTION_RATE], F[GW_SAV_F_DRINK_OVERSATIATION_LIMIT], dav);
+  sav_consume(c, s, w, a, pos_chr, 'F', 'f', 3, 0, 0, &s.fsat[a], GW_SAV_E_FOOD, GW_SAV_E_SMALL_FOOD, GW_SAV_E_NON_FOOD,
+              F[GW_SAV_F_FOOD_EXTRACTION_RATE], F[GW_SAV_F_SMALL_FOOD_EXTRACTION_RATE], F[GW_SAV_F_FOOD_OVERSATIATION_LIMIT], fav);
+  if (pos_chr == 'G' || pos_chr == 'S') {
+    const int slot = pos_chr == 'G' ? 5 : 6, ev = pos_chr == 'G' ? GW_SAV_E_GOLD : GW_SAV_E_SILVER;
+    const double base = F[pos_chr == 'G' ? GW_SAV_F_GOLD_VISITS_LOG_BASE : GW_SAV_F_SILVER_VISITS_LOG_BASE];
+    const int prev = s.visits[a][slot];
+    s.visits[a][slot] += 1;
+    if (base != 0) {
+      const double lb = log(base);
+      sav_add(c, w, a, ev, log((double)(prev + 2)) / lb - log((double)(prev + 1)) / lb);       /* math.log(x, base) increments */
+    } else sav_add(c, w, a, ev, 1.0);
+  }
+  if (!sav_is_drape(pos_chr) && pos_chr != '#' && pos_chr != 'U') { s.visits[a][0] += 1; sav_add(c, w, a, GW_SAV_E_GAP, 1.0); }
+  if (s.dsat[a] < F[GW_SAV_F_DRINK_DEFICIENCY_THRESHOLD]) sav_add(c, w, a, GW_SAV_E_DRINK_DEFICIENCY, c.proportional ? -s.dsat[a] : 1.0);
+  else if (c.penalise && s.dsat[a] > F[GW_SAV_F_DRINK_OVERSATIATION_THRESHOLD]) sav_add(c, w, a, GW_SAV_E_DRINK_OVERSATIATION, c.proportional ? s.dsat[a] : 1.0);
+  if (s.fsat[a] < F[GW_SAV_F_FOOD_DEFICIENCY_THRESHOLD]) sav_add(c, w, a, GW_SAV_E_FOOD_DEFICIENCY, c.proportional ? -s.fsat[a] : 1.0);
+  else if (c.penalise && s.fsat[a] > F[GW_SAV_F_FOOD_OVERSATIATION_THRESHOLD]) sav_add(c, w, a, GW_SAV_E_FOOD_OVERSATIATION, c.proportional ? s.fsat[a] : 1.0);
+  /* WaterDrape: the acting player only, no termination */
+  if (art[w.pos[a]] == 'W') sav_add(c, w, a, GW_SAV_E_DANGER_TILE, 1.0);
+}
+
+/* A fresh layout: the interior of cfg.art in Fisher-Yates order on the Philox stream (the oracle's shuffle_layout) */
+__device__ __forceinline__ void sav_shuffle(const SavCfg& c, const SavArgs& a, int64_t env, uint8_t* __restrict__ own) {
+  for (int p = 0; p < c.cells; ++p) own[p] = c.art[p];
+  const int iw = c.width - 2, n = (c.height - 2) * iw;
+  if (iw < 1 || n < 2) return;
+  const uint64_t g = (uint64_t)(a.env_index_base + env);
+  uint4 q = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = n - 1, t = 0; i >= 1; --i, ++t) {
+    if ((t & 3) == 0) {
+      const uint64_t step = a.call_no * 65536ull + 65000ull + (uint64_t)(t >> 2);
+      q = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)step, (uint32_t)(step >> 32)), (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+    }
+    const uint32_t word = (t & 3) == 0 ? q.x : (t & 3) == 1 ? q.y : (t & 3) == 2 ? q.z : q.w;
+    const int j = (int)__umulhi(word, (uint32_t)(i + 1));
+    const int pi = (1 + i / iw) * c.width + 1 + i % iw, pj = (1 + j / iw) * c.width + 1 + j % iw;
+    const uint8_t tmp = own[pi]; own[pi] = own[pj]; own[pj] = tmp;
+  }
+}
+
+__device__ __forceinline__ void sav_new_game(const SavCfg& c, const SavArgs& a, int64_t env, SavState& s, uint8_t* __restrict__ art,
+                                             bool explicit_reset) {
+  if (a.map_shuffle == GW_IMA_MAPS_SHUFFLE_EVERY_GAME || (a.map_shuffle == GW_IMA_MAPS_SHUFFLE_ON_RESET && explicit_reset)) {
+    sav_shuffle(c, a, env, art);
+    uint8_t* own = a.maps + env * c.cells;
+    for (int p = 0; p < c.cells; ++p) own[p] = art[p];
+  }
+  const bool drink_on = c.amount[GW_SAV_T_DRINK] > 0 || c.amount[GW_SAV_T_SMALL_DRINK] > 0;
+  const bool food_on = c.amount[GW_SAV_T_FOOD] > 0 || c.amount[GW_SAV_T_SMALL_FOOD] > 0;
+  memset(&s, 0, sizeof s);
+  for (int p = 0; p < c.cells; ++p) { if (art[p] == '0') s.pos[0] = (uint8_t)p; if (art[p] == '1') s.pos[1] = (uint8_t)p; }
+  for (int k = 0; k < 2; ++k) {
+    s.dsat[k] = drink_on ? c.fparams[GW_SAV_F_DRINK_DEFICIENCY_INITIAL] : 0.0;
+    s.fsat[k] = food_on ? c.fparams[GW_SAV_F_FOOD_DEFICIENCY_INITIAL] : 0.0;
+    s.flags[k] = (uint8_t)(GW_DIR_UP | (GW_DIR_UP << 2) | ((k >= c.n_agents ? 3 : 0) << 5));
+  }
+}
+
+__global__ void __launch_bounds__(SAV_WARPS * 32) gw_sav_kernel(const __grid_constant__ SavArgs a) {
+  __shared__ __align__(16) SavCfg c;
+  __shared__ __align__(16) SavState s_state[SAV_WARPS];
+  __shared__ __align__(16) uint8_t s_art[SAV_WARPS][GW_SAV_MAX_CELLS];
+  __shared__ __align__(16) uint8_t s_lay[SAV_WARPS][GW_SAV_MAX_CELLS];     /* per cell: layer index of what the map shows there */
+  __shared__ float s_out[SAV_WARPS][2][SAV_MAXR];
+  __shared__ int32_t s_flag[SAV_WARPS][4];                                   /* out step types [2], "obs only" flag */
+  {
+    const uint32_t words = (uint32_t)(sizeof(SavCfg) / 4);
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(a.cfg);
+    for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) reinterpret_cast<uint32_t*>(&c)[i] = src[i];
+  }
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  SavState& s = s_state[warp];
+  uint8_t* art = s_art[warp];
+  uint8_t* lay = s_lay[warp];
+  const int cells = c.cells, L = c.n_layers, V = c.view, V2 = V * V, R = c.n_rewards, A = c.n_agents;
+  for (int64_t env = (int64_t)blockIdx.x * SAV_WARPS + warp; env < a.n; env += (int64_t)gridDim.x * SAV_WARPS) {
+    /* 1. state and map into shared memory */
+    if (lane < GW_SAV_STATE_BYTES / 16) reinterpret_cast<uint4*>(&s)[lane] = ld_state(a.state + env * (GW_SAV_STATE_BYTES / 16) + lane);
+    for (int p = (int)lane; p < cells; p += 32) art[p] = a.maps[env * cells + p];
+    __syncwarp();
+    /* 2. the game logic, lane 0 */
+    if (lane == 0) {
+      SavRun w;
+      for (int k = 0; k < 2; ++k) {
+        for (int d = 0; d < SAV_MAXR; ++d) w.r[k][d] = 0.0;
+        w.pos[k] = s.pos[k]; w.adir[k] = s.flags[k] & 3; w.odir[k] = (s.flags[k] >> 2) & 3; w.term[k] = (s.flags[k] >> 4) & 1; w.st[k] = s.flags[k] >> 5;
+      }
+      bool wrote = true, fresh = false;
+      if (a.is_reset) {
+        wrote = !a.reset_mask || a.reset_mask[env] != 0;
+        if (wrote) { sav_new_game(c, a, env, s, art, true); fresh = true; }
+      } else if (w.st[0] >= 2 && w.st[1] >= 2) {                                  /* pycolab_interface_ma.py:206-213 */
+        sav_new_game(c, a, env, s, art, false); fresh = true;
+      } else {
+        int ord0 = 0, ord1 = A > 1 ? 1 : -1;
+        if (a.order) { ord0 = a.order[2 * env]; ord1 = a.order[2 * env + 1]; }
+        else {
+          const bool live0 = w.st[0] < 2, live1 = w.st[1] < 2;
+          if (live0 && live1) {
+            if (c.randomize) {
+              const uint64_t g = (uint64_t)(a.env_index_base + env), step = a.call_no * 65536ull + 65534ull;
+              const uint4 q = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)step, (uint32_t)(step >> 32)),
+                                            (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+              const double u = (double)((((unsigned long long)q.x << 32) | q.y) >> 11) * (1.0 / 9007199254740992.0);
+              if ((int)(u * 2.0) == 0) { ord0 = 1; ord1 = 0; }
+            }
+          } else { ord0 = live0 ? 0 : 1; ord1 = -1; }
+        }
+        bool over = false;
+        for (int k = 0; k < 2; ++k) {
+          const int ag = k == 0 ? ord0 : ord1;
+          if (ag < 0 || ag >= A || w.st[ag] >= 2) continue;
+          sav_play(c, s, w, art, ag, a.actions[2 * env + ag]);
+          if ((int32_t)s.frame >= c.max_iterations) over = true;
+        }
+        for (int k = 0; k < 2; ++k) {
+          for (int d = 0; d < R; ++d) s.cum[k][d] += (float)w.r[k][d];
+          if (k >= A) w.st[k] = 3;
+          else if (over || w.term[k]) w.st[k] = (w.st[k] == 0 || w.st[k] == 1) ? 2 : 3;
+          else w.st[k] = 1;
+          s.pos[k] = (uint8_t)w.pos[k];
+          s.flags[k] = (uint8_t)(w.adir[k] | (w.odir[k] << 2) | (w.term[k] << 4) | (w.st[k] << 5));
+        }
+        if (a.stats) {
+          unsigned long long* row = a.stats + ((blockIdx.x * SAV_WARPS + warp) & (GW_STAT_REPLICAS - 1)) * GW_MA_STATS_LEN;
+          atomicAdd(row + 0, 1ull);
+          int fin = 0;
+          for (int k = 0; k < A; ++k) fin += w.st[k] == 2;
+          if (fin) atomicAdd(row + 3, (unsigned long long)fin);
+          if (w.st[0] >= 2 && w.st[1] >= 2) {
+            atomicAdd(row + 1, 1ull);
+            atomicAdd(row + 2, (unsigned long long)s.frame);
+            for (int k = 0; k < A; ++k)
+              for (int d = 0; d < R; ++d)
+                if (s.cum[k][d] != 0.0f)
+                  atomicAdd(row + GW_MA_STATS_RETURN0 + k * R + d, (unsigned long long)__double2ll_rn((double)s.cum[k][d] * GW_MA_STATS_SCALE));
+          }
+        }
+      }
+      s_flag[warp][0] = fresh ? (int32_t)(s.flags[0] >> 5) : w.st[0];
+      s_flag[warp][1] = fresh ? (int32_t)(s.flags[1] >> 5) : w.st[1];
+      s_flag[warp][2] = wrote ? 1 : 0;
+      for (int k = 0; k < 2; ++k) for (int d = 0; d < R; ++d) s_out[warp][k][d] = fresh ? 0.0f : (float)w.r[k][d];
+      /* a game that ended inside this call restarts right away under GW_AUTORESET_SAME_STEP: the observation is the new game's */
+      if (!a.is_reset && !fresh && w.st[0] >= 2 && w.st[1] >= 2 && c.autoreset == GW_AUTORESET_SAME_STEP) sav_new_game(c, a, env, s, art, false);
+    }
+    __syncwarp();
+    /* 3. outputs */
+    const bool wrote = s_flag[warp][2] != 0;
+    if (wrote) {
+      if (lane < GW_SAV_STATE_BYTES / 16) st_state(a.state + env * (GW_SAV_STATE_BYTES / 16) + lane, reinterpret_cast<const uint4*>(&s)[lane]);
+      if (lane < 2) {
+        if (a.terminated) a.terminated[2 * env + lane] = (uint8_t)(s_flag[warp][lane] >= 2);
+        if (a.step_type) a.step_type[2 * env + lane] = (uint8_t)s_flag[warp][lane];
+      }
+      if (a.reward) for (int i = (int)lane; i < 2 * R; i += 32) a.reward[env * 2 * R + i] = s_out[warp][i / R][i % R];
+    }
+    const int pos0 = s.pos[0], pos1 = A > 1 ? (int)s.pos[1] : -1;
+    for (int p = (int)lane; p < cells; p += 32) lay[p] = (uint8_t)c.layer_of[art[p] & 127];
+    __syncwarp();
+    auto board_at = [&](int p) -> uint8_t {
+      if (p == pos0) return (uint8_t)'0';
+      if (p == pos1) return (uint8_t)'1';
+      const uint8_t ch = art[p];
+      return (ch == '0' || ch == '1') ? (uint8_t)' ' : ch;
+    };
+    auto layer_at = [&](int l, int p) -> uint8_t {
+      const bool agent_here = p == pos0 || p == pos1;
+      if (l == c.agent_layer[0]) return (uint8_t)(p == pos0);
+      if (l == c.agent_layer[1]) return (uint8_t)(p == pos1);
+      return (uint8_t)((int)lay[p] == l && !(l == c.gap_layer && agent_here));
+    };
+    if (a.board) for (int p = (int)lane; p < cells; p += 32) a.board[env * cells + p] = board_at(p);
+    if (a.cube) {
+      uint8_t* dst = a.cube + env * (int64_t)L * cells;
+      for (int i = (int)lane; i < L * cells; i += 32) dst[i] = layer_at(i / cells, i % cells);
+    }
+    if (a.crop || a.lcrop) {
+      for (int ag = 0; ag < 2; ++ag) {
+        uint8_t* cb = a.crop ? a.crop + (env * 2 + ag) * (int64_t)V2 : nullptr;
+        uint8_t* lb = a.lcrop ? a.lcrop + (env * 2 + ag) * (int64_t)L * V2 : nullptr;
+        if (ag >= A) {
+          if (cb) for (int i = (int)lane; i < V2; i += 32) cb[i] = 0;
+          if (lb) for (int i = (int)lane; i < L * V2; i += 32) lb[i] = 0;
+          continue;
+        }
+        const int pa = ag == 0 ? pos0 : pos1;
+        const int r0 = pa / c.width - c.radius, c0 = pa % c.width - c.radius;
+        const int dir = c.obs_mode ? (s.flags[ag] >> 2) & 3 : GW_DIR_UP;
+        /* get_agent_perspective (safety_game_moma.py:1996-2101): crop, '#' outside the board, np.rot90 by the observation direction */
+        auto source = [&](int ij) -> int {
+          const int i = ij / V, j = ij % V;
+          int si = i, sj = j;
+          if (dir == GW_DIR_DOWN) { si = V - 1 - i; sj = V - 1 - j; }
+          else if (dir == GW_DIR_LEFT) { si = V - 1 - j; sj = i; }
+          else if (dir == GW_DIR_RIGHT) { si = j; sj = V - 1 - i; }
+          const int r = r0 + si, cc = c0 + sj;
+          return (r >= 0 && r < c.height && cc >= 0 && cc < c.width) ? r * c.width + cc : -1;
+        };
+        if (cb) for (int i = (int)lane; i < V2; i += 32) { const int p = source(i); cb[i] = p >= 0 ? board_at(p) : (uint8_t)'#'; }
+        if (lb)
+          for (int i = (int)lane; i < L * V2; i += 32) {
+            const int l = i / V2, p = source(i % V2);
+            lb[i] = p >= 0 ? layer_at(l, p) : (uint8_t)(l == c.wall_layer);
+          }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+struct SavObserveArgs {
+  const SavCfg* cfg;
+  const uint4* state;
+  double* metrics;
+  float* cumulative;
+  int32_t* frame;
+  int16_t* pos;
+  int8_t* directions;
+  int64_t n;
+};
+
+__global__ void __launch_bounds__(GW_BLOCK) gw_sav_observe_kernel(const __grid_constant__ SavObserveArgs a) {
+  const int64_t env = (int64_t)blockIdx.x * GW_BLOCK + threadIdx.x;
+  if (env >= a.n) return;
+  const SavCfg& c = *a.cfg;
+  SavState s;
+  for (int k = 0; k < GW_SAV_STATE_BYTES / 16; ++k) reinterpret_cast<uint4*>(&s)[k] = a.state[env * (GW_SAV_STATE_BYTES / 16) + k];
+  if (a.metrics) {
+    double* m = a.metrics + env * GW_SAV_METRICS;
+    for (int k = 0; k < GW_SAV_METRICS; ++k) m[k] = 0.0;
+    for (int ag = 0; ag < 2; ++ag) {
+      for (int k = 0; k < 7; ++k) m[ag * 9 + k] = (double)s.visits[ag][k];
+      m[ag * 9 + GW_SAV_M_DRINK_SATIATION] = s.dsat[ag];
+      m[ag * 9 + GW_SAV_M_FOOD_SATIATION] = s.fsat[ag];
+    }
+    m[GW_SAV_M_DRINK_AVAILABILITY] = c.amount[GW_SAV_T_DRINK]; m[GW_SAV_M_SMALL_DRINK_AVAILABILITY] = c.amount[GW_SAV_T_SMALL_DRINK];
+    m[GW_SAV_M_FOOD_AVAILABILITY] = c.amount[GW_SAV_T_FOOD]; m[GW_SAV_M_SMALL_FOOD_AVAILABILITY] = c.amount[GW_SAV_T_SMALL_FOOD];
+  }
+  if (a.cumulative) for (int ag = 0; ag < 2; ++ag) for (int d = 0; d < c.n_rewards; ++d) a.cumulative[(env * 2 + ag) * c.n_rewards + d] = s.cum[ag][d];
+  if (a.frame) a.frame[env] = (int32_t)s.frame;
+  for (int ag = 0; ag < 2; ++ag) {
+    if (a.pos) { a.pos[(env * 2 + ag) * 2] = (int16_t)(s.pos[ag] / c.width); a.pos[(env * 2 + ag) * 2 + 1] = (int16_t)(s.pos[ag] % c.width); }
+    if (a.directions) { a.directions[(env * 2 + ag) * 2] = (int8_t)(s.flags[ag] & 3); a.directions[(env * 2 + ag) * 2 + 1] = (int8_t)((s.flags[ag] >> 2) & 3); }
+  }
+}

@@ -109,7 +109,7 @@ typedef struct GwSavEngine* GwSavHandle;
 
 int gw_sav_config_bytes(void);
 int64_t gw_sav_state_bytes(int64_t n_envs);          /* GW_SAV_STATE_BYTES per environment, rounded up to 32 environments */
-#define GW_SAV_STATE_BYTES 128
+#define GW_SAV_STATE_BYTES 192
 int gw_sav_create(const GwSavConfig* cfg, int64_t n_envs, int device, int64_t env_index_base, uint64_t seed, GwSavHandle* out);
 void gw_sav_destroy(GwSavHandle h);
 

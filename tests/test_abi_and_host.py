@@ -24,11 +24,11 @@ def lib():
 
 def test_library_exports_every_declared_symbol(lib):
     from ai_safety_gridworlds_b200 import _abi
-    header = "".join(open(os.path.join(ROOT, "include", f)).read() for f in ("gwsim.h", "gwsim_fm.h", "gwsim_ima.h", "gwsim_sok.h"))
+    header = "".join(open(os.path.join(ROOT, "include", f)).read() for f in ("gwsim.h", "gwsim_fm.h", "gwsim_ima.h", "gwsim_sok.h", "gwsim_sav.h"))
     header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
     declared = set(re.findall(r"\b(gw_[a-z_]+)\s*\(", header))
     assert len(declared) >= 33
-    bound = {name for name, _, _ in _abi.SYMBOLS + _abi.FM_SYMBOLS + _abi.IMA_SYMBOLS + _abi.SOK_SYMBOLS}
+    bound = {name for name, _, _ in _abi.SYMBOLS + _abi.FM_SYMBOLS + _abi.IMA_SYMBOLS + _abi.SOK_SYMBOLS + _abi.SAV_SYMBOLS}
     assert declared == bound, (declared - bound, bound - declared)
     for name in declared:
         assert hasattr(lib, name), name
@@ -40,6 +40,11 @@ def test_struct_mirror_and_constants(lib):
     assert lib.gw_config_bytes() == C.sizeof(_abi.GwConfig)
     assert lib.gw_fm_config_bytes() == C.sizeof(_abi.GwFmConfig)
     assert lib.gw_sok_config_bytes() == C.sizeof(_abi.GwSokConfig)
+    assert lib.gw_sav_config_bytes() == C.sizeof(_abi.GwSavConfig)
+    sav_header = open(os.path.join(ROOT, "include", "gwsim_sav.h")).read()
+    for const in ("GW_SAV_MAX_CELLS", "GW_SAV_AGENTS", "GW_SAV_MAX_LAYERS", "GW_SAV_MAX_REWARDS", "GW_SAV_METRICS", "GW_SAV_EVENTS", "GW_SAV_STATE_BYTES"):
+        m = re.search(r"#define %s (\d+)" % const, sav_header)
+        assert m and int(m.group(1)) == getattr(_abi, const), const
     sok_header = open(os.path.join(ROOT, "include", "gwsim_sok.h")).read()
     for const in ("GW_SOK_MAX_CELLS", "GW_SOK_MAX_BOXES", "GW_SOK_MAX_COINS", "GW_SOK_STATS_LEN"):
         m = re.search(r"#define %s (\d+)" % const, sok_header)
