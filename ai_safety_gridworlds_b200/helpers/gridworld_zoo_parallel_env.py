@@ -103,7 +103,49 @@ class _IslandMaBackend(object):
         return ex
 
 
-_BACKENDS = {"firemaker_ex_ma": _FiremakerBackend, "island_navigation_ex_ma": _IslandMaBackend}
+class _SavannaBackend(object):
+    """aintelope_savanna and its experiment overlays: agents '0' (and '1' with amount_agents = 2); the kernel always has two agent
+    columns."""
+    n_cols = 2
+
+    def __init__(self, n, device, seed, mode, spec):
+        from ..savanna_env import SavannaVectorEnv
+        self.env = SavannaVectorEnv(n, device=device, seed=seed, autoreset_mode=mode, spec=spec)
+        self.agent_chars = ["0", "1"][:spec.n_agents]
+        self.cols = [0, 1][:spec.n_agents]
+
+    def crop(self, i):
+        return self.env.crop[:, i]
+
+    def lcrop(self, i):
+        return self.env.lcrop[:, i]
+
+    def reward(self, i):
+        return self.env.reward[:, i]
+
+    def step(self, act, order, draws):
+        if draws is not None:
+            raise ValueError("the built aintelope_savanna flags draw no random numbers inside a step")
+        self.env.step(act, order)
+
+    def extras(self):
+        ex = self.env.observe()
+        ex["cumulative_per_agent"] = [ex["cumulative"][:, k] for k in self.cols]
+        return ex
+
+
+_BACKENDS = {"firemaker_ex_ma": _FiremakerBackend, "island_navigation_ex_ma": _IslandMaBackend, "aintelope_savanna": _SavannaBackend}
+
+
+def _backend_for(env_name):
+    """The backend class of a factory name; the aintelope experiment overlays are aintelope_savanna games."""
+    name = env_name.lower()
+    if name in _BACKENDS:
+        return _BACKENDS[name]
+    from ..envs import savanna_experiments
+    if name in savanna_experiments.OVERLAYS:
+        return _SavannaBackend
+    return None
 
 
 class GridworldZooParallelEnv(object):
@@ -114,13 +156,14 @@ class GridworldZooParallelEnv(object):
             raise NotImplementedError("test_death fault injection is a wrapper-side debugging aid and is not built")
         for k in _WRAPPER_ONLY:
             kwargs.pop(k, None)
-        if env_name.lower() not in _BACKENDS:
-            raise NotImplementedError("the multi-agent CUDA backend is built for " + " and ".join(sorted(_BACKENDS)))
+        if _backend_for(env_name) is None:
+            raise NotImplementedError("the multi-agent CUDA backend is built for " + ", ".join(sorted(_BACKENDS)) + " and the "
+                                      "aintelope experiment overlays")
         self._batched = num_envs is not None
         n = int(num_envs) if self._batched else 1
         mode = _abi.GW_AUTORESET_SAME_STEP if self._batched else _abi.GW_AUTORESET_NEXT_STEP
         self._spec = make_spec(env_name, autoreset_mode=mode, **kwargs)
-        self._backend = _BACKENDS[env_name.lower()](n, device, 0 if seed is None else seed, mode, self._spec)
+        self._backend = _backend_for(env_name)(n, device, 0 if seed is None else seed, mode, self._spec)
         self._env = self._backend.env
         self._ascii = bool(ascii_observation_format)
         chars = self._backend.agent_chars

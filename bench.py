@@ -57,6 +57,11 @@ WORKLOADS = {
                                 "island_navigation_ex_ma level 9, 2 agents, default flags (relative actions and views, shuffled "
                                 "sub-step order; SURVEY 8f row 1); one env-step = one PARALLEL step = up to 2 engine frames",
                                 "board u8[48] + cube u8[9x48] + agent views u8[2x25] x (1 + 9 layers) + rewards f32[2x8] + flags"),
+    "aintelope_savanna": ("aintelope_savanna", {}, 1 << 17,
+                          "aintelope_savanna level 0 (13x13), default flags: 1 agent, 2 food patches, relative actions, 21x21 rotated view, "
+                          "every environment its own layout redrawn on the device per game (SURVEY 8f row 4); one env-step = one PARALLEL step",
+                          "board u8[169] + cube u8[12x169] + agent views u8[2x441] x (1 + 12 layers) + rewards f32[2x3] + flags (+ the "
+                          "environment's own map u8[169] read per step)"),
     "island_navigation_ex_ma_randmap": ("island_navigation_ex_ma", {"map_randomization_frequency": 3}, 1 << 20,
                                         "island_navigation_ex_ma level 9, 2 agents, map_randomization_frequency=3: every environment "
                                         "plays its own layout, redrawn on the device at every new game (SURVEY 8f row 2); one "
@@ -264,14 +269,17 @@ def run_ours(args):
     sokoban = ENV_NAME == "sokoban_big"
     classic = ENV_NAME == "classic_mixed" or sokoban
     firemaker = ENV_NAME == "firemaker_ex_ma"
-    island_ma = ENV_NAME == "island_navigation_ex_ma"
+    savanna = ENV_NAME == "aintelope_savanna"
+    island_ma = ENV_NAME == "island_navigation_ex_ma" or savanna
     n_agents = 3 if firemaker else 2
     if island_ma:
         from ai_safety_gridworlds_b200.island_ma_env import IslandMaVectorEnv
+        from ai_safety_gridworlds_b200.savanna_env import SavannaVectorEnv
         spec = make_spec(ENV_NAME, autoreset_mode=1, **ENV_KWARGS)
 
         def make_env(value_board):
-            return IslandMaVectorEnv(n, device=dev, env_index_base=rank * n, seed=0, autoreset_mode=1, spec=spec)
+            cls = SavannaVectorEnv if savanna else IslandMaVectorEnv
+            return cls(n, device=dev, env_index_base=rank * n, seed=0, autoreset_mode=1, spec=spec)
         lo_hi = {}
         firemaker = True                             # from here on: "the multi-agent path" (per-agent action columns, no device statistics)
     elif firemaker:
@@ -415,11 +423,12 @@ def run_ours(args):
                 "bytes_per_env_step": bytes_per, "state_bytes_per_env": 192 if island_ma else 160 if firemaker else env.state_words * 16,
                 "autoreset": "same-step", "action_ring": ACTION_RING}),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": load_traffic(n), "peak_source": peak_src, "kernel": ("gw_ima_kernel<%s>" % ("true" if ENV_KWARGS.get("map_randomization_frequency") else "false")) if island_ma else "gw_fm_kernel" if firemaker else "gw_sok_kernel" if sokoban else ("gw_cls_step_kernel<%s>" % ("true" if ENV_KWARGS.get("row3") else "false")) if classic else "gw_step_tma_kernel<%d>" % (0 if ENV_NAME == "island_navigation_ex" else 2),
+                         "traffic": load_traffic(n), "peak_source": peak_src, "kernel": "gw_sav_kernel" if savanna else ("gw_ima_kernel<%s>" % ("true" if ENV_KWARGS.get("map_randomization_frequency") else "false")) if island_ma else "gw_fm_kernel" if firemaker else "gw_sok_kernel" if sokoban else ("gw_cls_step_kernel<%s>" % ("true" if ENV_KWARGS.get("row3") else "false")) if classic else "gw_step_tma_kernel<%d>" % (0 if ENV_NAME == "island_navigation_ex" else 2),
                          "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": bytes_per * n},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                     "steps": e2e_steps,
-                    "returns": ("per-agent ASCII views u8[2x25] + reward rows f32[2xR] + terminated u8[2] per env, pinned host" if island_ma else
+                    "returns": ("per-agent ASCII views u8[2x441] + reward rows f32[2xR] + terminated u8[2] per env, pinned host" if savanna else
+                                "per-agent ASCII views u8[2x25] + reward rows f32[2xR] + terminated u8[2] per env, pinned host" if island_ma else
                                 "per-agent ASCII crops u8[25+25+1089] + reward rows f32[7] + terminated u8[3] per env, pinned host"
                                 if firemaker else "value-mapped board f32 + reward row f32 + terminated u8 per env, pinned host")},
             "gpu_launches": step_launches,

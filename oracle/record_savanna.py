@@ -51,6 +51,11 @@ CASES = {
     "savanna_resized_9x11_s12": dict(seed=12, steps=250, kwargs=dict(map_width=11, map_height=9, max_iterations=50, amount_food_patches=3)),
     "savanna_randmap_once_s13": dict(seed=13, steps=200, kwargs=dict(map_randomization_frequency=1, max_iterations=40)),
 }
+# the experiment overlays (experiments/aintelope/*.py) that draw no random numbers during play, through the reference's factory names
+for _k, _name in enumerate(["danger_tiles", "food_drink_homeostasis", "food_drink_homeostasis_danger_gold_silver", "food_drink_homeostasis_gold",
+                            "food_drink_homeostasis_gold_silver", "food_homeostasis", "food_sharing", "food_unbounded"]):
+    CASES["savanna_exp_" + _name] = dict(seed=40 + _k, steps=150, env=_name, kwargs=dict(max_iterations=60),
+                                         agents=2 if _name == "food_sharing" else 1)
 AGENTS = ["0", "1"]
 
 
@@ -75,10 +80,10 @@ def _worker(name):
     from ai_safety_gridworlds.environments.shared.safety_game_ma import NP_RANDOM
 
     case = CASES[name]
-    A = int(case["kwargs"].get("amount_agents", 1))
+    A = int(case["kwargs"].get("amount_agents", case.get("agents", 1)))
     agents = AGENTS[:A]
     names = ["agent_" + a for a in agents]
-    env = GridworldZooParallelEnv("aintelope_savanna", seed=case["seed"], **case["kwargs"])
+    env = GridworldZooParallelEnv(case.get("env", "aintelope_savanna"), seed=case["seed"], **case["kwargs"])
     core = env._env
     log = {"order": None}
 
@@ -175,7 +180,7 @@ def _worker(name):
     out["actions"] = np.array(actions, dtype=np.int32)
     out["order"] = np.array(orders, dtype=np.int8)
     out["frame"] = out["frame"].astype(np.int32)
-    meta.update(env="aintelope_savanna", kwargs=dict(case["kwargs"]), seed=case["seed"], amount_agents=A,
+    meta.update(env=case.get("env", "aintelope_savanna"), kwargs=dict(case["kwargs"]), seed=case["seed"], amount_agents=A,
                 value_mapping={k: float(v) for k, v in core._value_mapping.items()},
                 max_iterations=int(core._max_iterations), recorder="oracle/record_savanna.py",
                 reference="levitation-opensource/ai-safety-gridworlds @ /root/reference", numpy=np.__version__)

@@ -153,3 +153,84 @@ def test_island_ma_batched_parallel_and_aec_forms():
         aec.step(torch.randint(0, 5, (N,), device=aec.vector_env.device))
     assert int(aec.get_step_no().max()) <= 8
     aec.close()
+
+
+@pytest.mark.parametrize("name", ["savanna_maxiter40_s2", "savanna_two_agents_s7", "savanna_exp_food_sharing",
+                                  "savanna_exp_food_drink_homeostasis_danger_gold_silver"])
+def test_savanna_single_env_drop_in_replays_reference_trace(name):
+    """aintelope_savanna (and its experiment overlays, by their factory names) through the parallel wrapper.  The reference draws
+    a new layout for every game from its Generator; the recorded layouts are replayed through the per-environment maps tensor."""
+    from ai_safety_gridworlds_b200 import GridworldZooParallelEnv
+    d, meta = load_golden(name)
+    A = meta["amount_agents"]
+    env = GridworldZooParallelEnv(meta["env"], seed=meta["seed"], **meta["kwargs"])
+    ve = env.vector_env
+    maps = torch.zeros((1,) + d["maps"].shape[1:], dtype=torch.uint8, device=ve.device)
+    ve.set_maps(maps, 0)                                         # GW_IMA_MAPS_STATIC: the caller writes the layouts
+    maps.copy_(torch.from_numpy(d["maps"][0]).to(ve.device))
+    obs, infos = env.reset(seed=meta["seed"])
+    names = ["agent_0", "agent_1"][:A]
+    V = meta["view"]
+    assert env.agents == names and obs["agent_0"].shape == (1, V, V) and obs["agent_0"].dtype.kind == "U"
+    codes = lambda o: np.vectorize(ord)(o[0]).astype(np.uint8)
+    np.testing.assert_array_equal(codes(obs["agent_0"]), d["crop"][0, 0])
+    assert infos["agent_0"]["info_observation_layers_order"] == meta["layer_order"]
+    assert list(infos["agent_0"]["metrics_dict"].keys()) == list(dict.fromkeys(meta["metric_names"]))
+    for t in range(1, len(d["actions"]) + 1):
+        a = d["actions"][t - 1]
+        if (a < 0).all():                        # the recorder called reset(): every agent was done
+            assert env.agents == []
+            maps.copy_(torch.from_numpy(d["maps"][t]).to(ve.device))
+            obs, infos = env.reset()
+            np.testing.assert_array_equal(infos["agent_0"]["ascii_codes"], d["board"][t])
+            continue
+        live = [n for i, n in enumerate(names) if a[i] >= 0]
+        assert env.agents == live
+        order = list(d["order"][t - 1]) + [-1] * (2 - A)
+        obs, rewards, terms, truncs, infos = env.step({n: int(a[names.index(n)]) for n in live}, replay_order=order)
+        assert sorted(obs) == sorted(live) == sorted(rewards) == sorted(terms)
+        for n in live:
+            i = names.index(n)
+            np.testing.assert_array_equal(codes(obs[n]), d["crop"][t, i])
+            np.testing.assert_allclose(rewards[n], d["reward"][t, i], rtol=1e-6, atol=1e-6)
+            assert terms[n] == bool(d["done"][t][i]) and truncs[n] is False
+            np.testing.assert_array_equal(infos[n]["info_agent_observation_layers_cube"], d["lcrop"][t, i].astype(bool))
+            np.testing.assert_allclose(infos[n]["cumulative_reward"], d["cum"][t][i], rtol=1e-6, atol=1e-5)
+            assert int(infos[n]["observation_direction"]) == d["odir"][t][i]
+        n0 = live[0]
+        np.testing.assert_array_equal(infos[n0]["ascii_codes"], d["board"][t])
+        np.testing.assert_array_equal(infos[n0]["info_observation_layers_cube"], d["cube"][t].astype(bool))
+        got = infos[n0]["metrics_dict"]
+        for label, want in zip(meta["metric_names"], d["metrics"][t]):
+            if not np.isnan(want):
+                assert got[label] == pytest.approx(want, rel=1e-12, abs=1e-12), (t, label)
+    env.close()
+
+
+def test_savanna_batched_parallel_and_aec_forms():
+    from ai_safety_gridworlds_b200 import GridworldZooAecEnv, GridworldZooParallelEnv
+    N = 512
+    env = GridworldZooParallelEnv("aintelope_savanna", num_envs=N, seed=3, amount_agents=2, max_iterations=12)
+    obs, infos = env.reset()
+    assert obs["agent_0"].shape == (N, 1, 21, 21) and obs["agent_0"].dtype == torch.uint8 and len(env.agents) == 2
+    first_maps = env.vector_env.maps.clone()
+    assert int((first_maps != first_maps[0]).any(dim=(1, 2)).sum()) > N // 2          # every environment drew its own layout
+    ended = 0
+    for t in range(14):
+        acts = {a: torch.randint(0, 5, (N,), device=env.vector_env.device) for a in env.possible_agents}
+        obs, rewards, terms, truncs, infos = env.step(acts)
+        assert rewards["agent_1"].shape == (N, 4) and rewards["agent_1"].dtype == torch.float64
+        ended += int((terms["agent_0"] & terms["agent_1"]).sum())
+    assert ended == 2 * N                                        # max_iterations = 12 frames = 6 parallel steps of two agents
+    assert bool((env.vector_env.maps != first_maps).any())       # frequency 3: a new layout for every game
+    env.close()
+    aec = GridworldZooAecEnv("food_unbounded", num_envs=N, seed=3)
+    aec.reset()
+    for k, a in zip(range(6), aec.agent_iter()):
+        assert a == "agent_0"
+        obs, cum, term, trunc, info = aec.last()
+        assert obs.shape == (N, 1, 21, 21) and cum.shape == (N, 1)
+        aec.step(torch.randint(0, 5, (N,), device=aec.vector_env.device))
+    aec.close()
+    with pytest.raises(NotImplementedError):
+        GridworldZooParallelEnv("predators")
