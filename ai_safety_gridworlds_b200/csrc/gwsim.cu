@@ -2656,6 +2656,8 @@ static int sav_launch(GwSavHandle h, SavArgs& a, void* state, const GwSavObs* ob
   a.cfg = h->d_cfg; a.state = (uint4*)state; a.maps = h->maps; a.n = h->n; a.stats = h->d_stats;
   if (obs) { a.board = obs->board; a.cube = obs->cube; a.crop = obs->crop; a.lcrop = obs->lcrop; }
   if (out) { a.reward = out->reward; a.terminated = out->terminated; a.step_type = out->step_type; }
+  if (((uintptr_t)a.board | (uintptr_t)a.cube | (uintptr_t)a.crop | (uintptr_t)a.lcrop) & 15u)
+    return fail(GW_ERR_INVALID, "observation tensors must be 16-byte aligned (rows are padded to 16 bytes, GW_SAV_PITCH)");
   a.seed = h->seed; a.call_no = ++h->call_no; a.env_index_base = h->env_index_base;
   a.map_shuffle = h->map_mode;
   CUDA_TRY(cudaSetDevice(h->device));

@@ -18,6 +18,7 @@
 #include "../../include/gwsim_sav.h"
 
 #define SAV_WARPS 4
+#define SAV_VPITCH 448                   /* (2 * GW_SAV_MAX_RADIUS + 1)^2 = 441 rounded up to 16 */
 #define SAV_MAXR 14                      /* 2 * R must fit the raw statistics vector (GW_MA_STATS_LEN - 4) */
 
 struct SavCfg {
@@ -203,7 +204,12 @@ __global__ void __launch_bounds__(SAV_WARPS * 32) gw_sav_kernel(const __grid_con
   __shared__ __align__(16) SavCfg c;
   __shared__ __align__(16) SavState s_state[SAV_WARPS];
   __shared__ __align__(16) uint8_t s_art[SAV_WARPS][GW_SAV_MAX_CELLS];
-  __shared__ __align__(16) uint8_t s_lay[SAV_WARPS][GW_SAV_MAX_CELLS];     /* per cell: layer index of what the map shows there */
+  __shared__ __align__(16) uint8_t s_prim[SAV_WARPS][GW_SAV_MAX_CELLS];    /* per cell: layer of what the map shows there, 255 = none */
+  __shared__ __align__(16) uint8_t s_sec[SAV_WARPS][GW_SAV_MAX_CELLS];     /* per cell: layer of the agent standing there, 255 = none */
+  __shared__ __align__(16) uint8_t s_bchr[SAV_WARPS][GW_SAV_MAX_CELLS];    /* per cell: the rendered character */
+  __shared__ __align__(16) uint8_t s_vprim[SAV_WARPS][SAV_VPITCH];         /* the same three for the cells of the current agent's view */
+  __shared__ __align__(16) uint8_t s_vsec[SAV_WARPS][SAV_VPITCH];
+  __shared__ __align__(16) uint8_t s_vchr[SAV_WARPS][SAV_VPITCH];
   __shared__ float s_out[SAV_WARPS][2][SAV_MAXR];
   __shared__ int32_t s_flag[SAV_WARPS][4];                                   /* out step types [2], "obs only" flag */
   {
@@ -215,7 +221,6 @@ __global__ void __launch_bounds__(SAV_WARPS * 32) gw_sav_kernel(const __grid_con
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   SavState& s = s_state[warp];
   uint8_t* art = s_art[warp];
-  uint8_t* lay = s_lay[warp];
   const int cells = c.cells, L = c.n_layers, V = c.view, V2 = V * V, R = c.n_rewards, A = c.n_agents;
   for (int64_t env = (int64_t)blockIdx.x * SAV_WARPS + warp; env < a.n; env += (int64_t)gridDim.x * SAV_WARPS) {
     /* 1. state and map into shared memory */
@@ -299,54 +304,80 @@ __global__ void __launch_bounds__(SAV_WARPS * 32) gw_sav_kernel(const __grid_con
       }
       if (a.reward) for (int i = (int)lane; i < 2 * R; i += 32) a.reward[env * 2 * R + i] = s_out[warp][i / R][i % R];
     }
+    /* Every row of the output tensors is padded to a multiple of 16 bytes (GW_SAV_PITCH), so that a lane produces and stores 16
+     * bytes at a time: a cell's layers are described by two bytes -- the layer of what the map shows there (none if it is a gap
+     * an agent stands on) and the layer of the agent standing there (none otherwise) -- and 16 cells of a layer plane are
+     * two byte-wise compares of 16 such codes against the layer index. */
     const int pos0 = s.pos[0], pos1 = A > 1 ? (int)s.pos[1] : -1;
-    for (int p = (int)lane; p < cells; p += 32) lay[p] = (uint8_t)c.layer_of[art[p] & 127];
+    const int cpitch = (cells + 15) & ~15, vpitch = (V2 + 15) & ~15;
+    uint8_t* prim = s_prim[warp];
+    uint8_t* sec = s_sec[warp];
+    uint8_t* bchr = s_bchr[warp];
+    for (int p = (int)lane; p < cpitch; p += 32) {
+      uint8_t pr = 255, se = 255, ch = 0;
+      if (p < cells) {
+        const uint8_t m = art[p];
+        const int ly = c.layer_of[m & 127];
+        const bool a0 = p == pos0, a1 = p == pos1;
+        pr = (uint8_t)((ly == c.gap_layer && (a0 || a1)) ? 255 : ly);
+        se = a0 ? (uint8_t)c.agent_layer[0] : a1 ? (uint8_t)c.agent_layer[1] : (uint8_t)255;
+        ch = a0 ? (uint8_t)'0' : a1 ? (uint8_t)'1' : (m == '0' || m == '1') ? (uint8_t)' ' : m;
+      }
+      prim[p] = pr; sec[p] = se; bchr[p] = ch;
+    }
     __syncwarp();
-    auto board_at = [&](int p) -> uint8_t {
-      if (p == pos0) return (uint8_t)'0';
-      if (p == pos1) return (uint8_t)'1';
-      const uint8_t ch = art[p];
-      return (ch == '0' || ch == '1') ? (uint8_t)' ' : ch;
+    auto plane16 = [&](const uint8_t* pr, const uint8_t* se, int l, int chunk) -> uint4 {
+      const uint4 a4 = *reinterpret_cast<const uint4*>(pr + 16 * chunk), b4 = *reinterpret_cast<const uint4*>(se + 16 * chunk);
+      const uint32_t lv = (uint32_t)l * 0x01010101u;
+      uint4 o;
+      o.x = (__vcmpeq4(a4.x, lv) | __vcmpeq4(b4.x, lv)) & 0x01010101u;
+      o.y = (__vcmpeq4(a4.y, lv) | __vcmpeq4(b4.y, lv)) & 0x01010101u;
+      o.z = (__vcmpeq4(a4.z, lv) | __vcmpeq4(b4.z, lv)) & 0x01010101u;
+      o.w = (__vcmpeq4(a4.w, lv) | __vcmpeq4(b4.w, lv)) & 0x01010101u;
+      return o;
     };
-    auto layer_at = [&](int l, int p) -> uint8_t {
-      const bool agent_here = p == pos0 || p == pos1;
-      if (l == c.agent_layer[0]) return (uint8_t)(p == pos0);
-      if (l == c.agent_layer[1]) return (uint8_t)(p == pos1);
-      return (uint8_t)((int)lay[p] == l && !(l == c.gap_layer && agent_here));
-    };
-    if (a.board) for (int p = (int)lane; p < cells; p += 32) a.board[env * cells + p] = board_at(p);
+    const int cch = cpitch >> 4, vch = vpitch >> 4;
+    if (a.board) {
+      uint4* dst = reinterpret_cast<uint4*>(a.board + env * (int64_t)cpitch);
+      for (int i = (int)lane; i < cch; i += 32) st_stream(dst + i, *reinterpret_cast<const uint4*>(bchr + 16 * i));
+    }
     if (a.cube) {
-      uint8_t* dst = a.cube + env * (int64_t)L * cells;
-      for (int i = (int)lane; i < L * cells; i += 32) dst[i] = layer_at(i / cells, i % cells);
+      uint4* dst = reinterpret_cast<uint4*>(a.cube + env * (int64_t)L * cpitch);
+      for (int i = (int)lane; i < L * cch; i += 32) st_stream(dst + i, plane16(prim, sec, i / cch, i % cch));
     }
     if (a.crop || a.lcrop) {
-      for (int ag = 0; ag < 2; ++ag) {
-        uint8_t* cb = a.crop ? a.crop + (env * 2 + ag) * (int64_t)V2 : nullptr;
-        uint8_t* lb = a.lcrop ? a.lcrop + (env * 2 + ag) * (int64_t)L * V2 : nullptr;
-        if (ag >= A) {
-          if (cb) for (int i = (int)lane; i < V2; i += 32) cb[i] = 0;
-          if (lb) for (int i = (int)lane; i < L * V2; i += 32) lb[i] = 0;
-          continue;
-        }
+      uint8_t* vprim = s_vprim[warp];
+      uint8_t* vsec = s_vsec[warp];
+      uint8_t* vchr = s_vchr[warp];
+      for (int ag = 0; ag < A; ++ag) {                       /* the columns of an agent the game does not have are never written */
         const int pa = ag == 0 ? pos0 : pos1;
         const int r0 = pa / c.width - c.radius, c0 = pa % c.width - c.radius;
         const int dir = c.obs_mode ? (s.flags[ag] >> 2) & 3 : GW_DIR_UP;
         /* get_agent_perspective (safety_game_moma.py:1996-2101): crop, '#' outside the board, np.rot90 by the observation direction */
-        auto source = [&](int ij) -> int {
-          const int i = ij / V, j = ij % V;
-          int si = i, sj = j;
-          if (dir == GW_DIR_DOWN) { si = V - 1 - i; sj = V - 1 - j; }
-          else if (dir == GW_DIR_LEFT) { si = V - 1 - j; sj = i; }
-          else if (dir == GW_DIR_RIGHT) { si = j; sj = V - 1 - i; }
-          const int r = r0 + si, cc = c0 + sj;
-          return (r >= 0 && r < c.height && cc >= 0 && cc < c.width) ? r * c.width + cc : -1;
-        };
-        if (cb) for (int i = (int)lane; i < V2; i += 32) { const int p = source(i); cb[i] = p >= 0 ? board_at(p) : (uint8_t)'#'; }
-        if (lb)
-          for (int i = (int)lane; i < L * V2; i += 32) {
-            const int l = i / V2, p = source(i % V2);
-            lb[i] = p >= 0 ? layer_at(l, p) : (uint8_t)(l == c.wall_layer);
+        for (int ij = (int)lane; ij < vpitch; ij += 32) {
+          uint8_t pr = 255, se = 255, ch = 0;
+          if (ij < V2) {
+            const int i = ij / V, j = ij - i * V;
+            int si = i, sj = j;
+            if (dir == GW_DIR_DOWN) { si = V - 1 - i; sj = V - 1 - j; }
+            else if (dir == GW_DIR_LEFT) { si = V - 1 - j; sj = i; }
+            else if (dir == GW_DIR_RIGHT) { si = j; sj = V - 1 - i; }
+            const int r = r0 + si, cc = c0 + sj;
+            if (r >= 0 && r < c.height && cc >= 0 && cc < c.width) { const int p = r * c.width + cc; pr = prim[p]; se = sec[p]; ch = bchr[p]; }
+            else { pr = (uint8_t)c.wall_layer; ch = (uint8_t)'#'; }
           }
+          vprim[ij] = pr; vsec[ij] = se; vchr[ij] = ch;
+        }
+        __syncwarp();
+        if (a.crop) {
+          uint4* dst = reinterpret_cast<uint4*>(a.crop + (env * 2 + ag) * (int64_t)vpitch);
+          for (int i = (int)lane; i < vch; i += 32) st_stream(dst + i, *reinterpret_cast<const uint4*>(vchr + 16 * i));
+        }
+        if (a.lcrop) {
+          uint4* dst = reinterpret_cast<uint4*>(a.lcrop + (env * 2 + ag) * (int64_t)L * vpitch);
+          for (int i = (int)lane; i < L * vch; i += 32) st_stream(dst + i, plane16(vprim, vsec, i / vch, i % vch));
+        }
+        __syncwarp();
       }
     }
     __syncwarp();

@@ -19,7 +19,7 @@ from .vector_env import _ptr
 
 class SavannaVectorEnv(MultiAgentStatsMixin):
     """Tensors (on `device`, reused between calls), V = 2 * observation radius + 1:
-      board uint8 [N,H,W]; cube uint8 [N,L,H,W]; crop uint8 [N,2,V,V]; lcrop uint8 [N,2,L,V,V];
+      board uint8 [N,H,W]; cube uint8 [N,L,H,W]; crop uint8 [N,2,V,V]; lcrop uint8 [N,2,L,V,V] (views of row-padded buffers);
       reward float32 [N,2,R] (sorted reward-dimension keys); terminated / step_type uint8 [N,2];
       maps uint8 [N,H,W]: every environment's own layout (rewritten by the library when it draws the layouts)."""
 
@@ -45,14 +45,21 @@ class SavannaVectorEnv(MultiAgentStatsMixin):
         H, W, L, R, V = spec.height, spec.width, spec.n_layers, spec.n_rewards, spec.view
         u8 = dict(dtype=torch.uint8, device=dev)
         self.state = torch.zeros((int(lib.gw_sav_state_bytes(N)) // 4,), dtype=torch.int32, device=dev)
-        self.board = torch.zeros((N, H, W), **u8)
-        self.cube = torch.zeros((N, L, H, W), **u8) if want_cube else None
-        self.crop = torch.zeros((N, 2, V, V), **u8) if want_crops else None
-        self.lcrop = torch.zeros((N, 2, L, V, V), **u8) if want_layer_crops else None
+        # the kernel stores 16 bytes per lane: every row of the output tensors is padded to a multiple of 16 bytes (GW_SAV_PITCH);
+        # the public tensors are views of the padded buffers with the reference's shapes
+        cp, vp = (H * W + 15) // 16 * 16, (V * V + 15) // 16 * 16
+        self._board_buf = torch.zeros((N, cp), **u8)
+        self._cube_buf = torch.zeros((N, L, cp), **u8) if want_cube else None
+        self._crop_buf = torch.zeros((N, 2, vp), **u8) if want_crops else None
+        self._lcrop_buf = torch.zeros((N, 2, L, vp), **u8) if want_layer_crops else None
+        self.board = self._board_buf[:, :H * W].unflatten(-1, (H, W))
+        self.cube = self._cube_buf[..., :H * W].unflatten(-1, (H, W)) if want_cube else None
+        self.crop = self._crop_buf[..., :V * V].unflatten(-1, (V, V)) if want_crops else None
+        self.lcrop = self._lcrop_buf[..., :V * V].unflatten(-1, (V, V)) if want_layer_crops else None
         self.reward = torch.zeros((N, 2, R), dtype=torch.float32, device=dev)
         self.terminated = torch.zeros((N, 2), **u8)
         self.step_type = torch.zeros((N, 2), **u8)
-        self._obs = _abi.GwSavObs(_ptr(self.board), _ptr(self.cube), _ptr(self.crop), _ptr(self.lcrop))
+        self._obs = _abi.GwSavObs(_ptr(self._board_buf), _ptr(self._cube_buf), _ptr(self._crop_buf), _ptr(self._lcrop_buf))
         self._out = _abi.GwSavOut(_ptr(self.reward), _ptr(self.terminated), _ptr(self.step_type))
         self._raw_dev = torch.zeros((_abi.GW_MA_STATS_LEN,), dtype=torch.float64, device=dev)
         self._stats_fns = (lib.gw_sav_stats_device, lib.gw_sav_stats_clear)
@@ -129,11 +136,12 @@ class SavannaVectorEnv(MultiAgentStatsMixin):
     def bytes_per_env_step(self):
         """2 actions + state in/out (192 B each) + the environment's map + every emitted tensor of one parallel step"""
         s = self.spec
-        b = 8 + 2 * _abi.GW_SAV_STATE_BYTES + 2 * s.cells + 2 * s.n_rewards * 4 + 4
+        cp, vp = (s.cells + 15) // 16 * 16, (s.view * s.view + 15) // 16 * 16
+        b = 8 + 2 * _abi.GW_SAV_STATE_BYTES + s.cells + cp + 2 * s.n_rewards * 4 + 4
         if self.cube is not None:
-            b += s.n_layers * s.cells
+            b += s.n_layers * cp
         if self.crop is not None:
-            b += 2 * s.view * s.view
+            b += s.n_agents * vp                              # the columns of an absent agent are never written
         if self.lcrop is not None:
-            b += 2 * s.n_layers * s.view * s.view
+            b += s.n_agents * s.n_layers * vp
         return b

@@ -84,11 +84,15 @@ enum GwSavMetric {
   GW_SAV_M_DRINK_AVAILABILITY = 18, GW_SAV_M_SMALL_DRINK_AVAILABILITY = 19, GW_SAV_M_FOOD_AVAILABILITY = 20, GW_SAV_M_SMALL_FOOD_AVAILABILITY = 21
 };
 
-typedef struct GwSavObs {          /* any pointer may be NULL = not wanted; all uint8; V = 2 * radius + 1 */
-  uint8_t* board;                 /* [N, H*W]            global rendered board, ASCII codes                       */
-  uint8_t* cube;                  /* [N, L, H*W]         global layers cube (info_observation_layers_cube)        */
-  uint8_t* crop;                  /* [N, 2, V*V]         the agents' rotated observations (ASCII codes)           */
-  uint8_t* lcrop;                 /* [N, 2, L, V*V]      info_agent_observation_layers_cube per agent             */
+/* Every row of the observation tensors is padded to a multiple of 16 bytes so that the kernel stores 16 bytes per lane:
+ * CP = GW_SAV_PITCH(H * W), VP = GW_SAV_PITCH(V * V) with V = 2 * radius + 1; the padding bytes are zero.  The columns of an
+ * agent the game does not have (n_agents = 1) are never written: allocate the tensors zeroed. */
+#define GW_SAV_PITCH(n) (((n) + 15) & ~15)
+typedef struct GwSavObs {          /* any pointer may be NULL = not wanted; all uint8, 16-byte aligned */
+  uint8_t* board;                 /* [N, CP]             global rendered board, ASCII codes                       */
+  uint8_t* cube;                  /* [N, L, CP]          global layers cube (info_observation_layers_cube)        */
+  uint8_t* crop;                  /* [N, 2, VP]          the agents' rotated observations (ASCII codes)           */
+  uint8_t* lcrop;                 /* [N, 2, L, VP]       info_agent_observation_layers_cube per agent             */
 } GwSavObs;
 
 typedef struct GwSavOut {
