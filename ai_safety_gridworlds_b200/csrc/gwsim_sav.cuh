@@ -200,7 +200,7 @@ __device__ __forceinline__ void sav_new_game(const SavCfg& c, const SavArgs& a, 
   }
 }
 
-__global__ void __launch_bounds__(SAV_WARPS * 32) gw_sav_kernel(const __grid_constant__ SavArgs a) {
+__global__ void __launch_bounds__(SAV_WARPS * 32, 8) gw_sav_kernel(const __grid_constant__ SavArgs a) {
   __shared__ __align__(16) SavCfg c;
   __shared__ __align__(16) SavState s_state[SAV_WARPS];
   __shared__ __align__(16) uint8_t s_art[SAV_WARPS][GW_SAV_MAX_CELLS];
@@ -212,10 +212,15 @@ __global__ void __launch_bounds__(SAV_WARPS * 32) gw_sav_kernel(const __grid_con
   __shared__ __align__(16) uint8_t s_vchr[SAV_WARPS][SAV_VPITCH];
   __shared__ float s_out[SAV_WARPS][2][SAV_MAXR];
   __shared__ int32_t s_flag[SAV_WARPS][4];                                   /* out step types [2], "obs only" flag */
+  __shared__ uint8_t s_vi[SAV_VPITCH], s_vj[SAV_VPITCH];                     /* view cell -> (row, column): no division per cell */
   {
     const uint32_t words = (uint32_t)(sizeof(SavCfg) / 4);
     const uint32_t* src = reinterpret_cast<const uint32_t*>(a.cfg);
     for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) reinterpret_cast<uint32_t*>(&c)[i] = src[i];
+  }
+  for (int ij = (int)threadIdx.x; ij < SAV_VPITCH; ij += (int)blockDim.x) {
+    const int v = 2 * a.cfg->radius + 1;
+    s_vi[ij] = (uint8_t)(ij / v); s_vj[ij] = (uint8_t)(ij % v);
   }
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -357,7 +362,7 @@ __global__ void __launch_bounds__(SAV_WARPS * 32) gw_sav_kernel(const __grid_con
         for (int ij = (int)lane; ij < vpitch; ij += 32) {
           uint8_t pr = 255, se = 255, ch = 0;
           if (ij < V2) {
-            const int i = ij / V, j = ij - i * V;
+            const int i = s_vi[ij], j = s_vj[ij];
             int si = i, sj = j;
             if (dir == GW_DIR_DOWN) { si = V - 1 - i; sj = V - 1 - j; }
             else if (dir == GW_DIR_LEFT) { si = V - 1 - j; sj = i; }
@@ -375,7 +380,9 @@ __global__ void __launch_bounds__(SAV_WARPS * 32) gw_sav_kernel(const __grid_con
         }
         if (a.lcrop) {
           uint4* dst = reinterpret_cast<uint4*>(a.lcrop + (env * 2 + ag) * (int64_t)L * vpitch);
-          for (int i = (int)lane; i < L * vch; i += 32) st_stream(dst + i, plane16(vprim, vsec, i / vch, i % vch));
+          if (vch <= 32) {                                 /* one 16-byte piece per lane and layer: no index arithmetic */
+            if ((int)lane < vch) for (int l = 0; l < L; ++l) st_stream(dst + l * vch + lane, plane16(vprim, vsec, l, (int)lane));
+          } else for (int i = (int)lane; i < L * vch; i += 32) st_stream(dst + i, plane16(vprim, vsec, i / vch, i % vch));
         }
         __syncwarp();
       }
