@@ -215,13 +215,15 @@ SOK_SYMBOLS = [
 # ---- include/gwsim_sav.h: aintelope_savanna ----
 GW_SAV_MAX_CELLS, GW_SAV_AGENTS, GW_SAV_MAX_LAYERS, GW_SAV_MAX_REWARDS, GW_SAV_MAX_RADIUS, GW_SAV_METRICS, GW_SAV_EVENTS = 256, 2, 16, 16, 10, 24, 20
 GW_SAV_STATE_BYTES = 192
+GW_SAV_MAX_PREDATORS, GW_SAV_MAX_DRAWS = 8, 32
 SAV_E = dict(MOVEMENT=0, FINAL=1, DRINK_DEFICIENCY=2, FOOD_DEFICIENCY=3, DRINK=4, FOOD=5, SMALL_DRINK=6, SMALL_FOOD=7, NON_DRINK=8, NON_FOOD=9,
              GAP=10, GOLD=11, SILVER=12, DANGER_TILE=13, PREDATOR=14, THIRST_HUNGER_DEATH=15, COOPERATION=16, SMALL_COOPERATION=17,
              DRINK_OVERSATIATION=18, FOOD_OVERSATIATION=19)
 SAV_F = dict(DRINK_DEFICIENCY_INITIAL=0, DRINK_EXTRACTION_RATE=1, SMALL_DRINK_EXTRACTION_RATE=2, DRINK_DEFICIENCY_RATE=3, DRINK_DEFICIENCY_LIMIT=4,
              DRINK_OVERSATIATION_LIMIT=5, DRINK_OVERSATIATION_THRESHOLD=6, DRINK_DEFICIENCY_THRESHOLD=7, FOOD_DEFICIENCY_INITIAL=8,
              FOOD_EXTRACTION_RATE=9, SMALL_FOOD_EXTRACTION_RATE=10, FOOD_DEFICIENCY_RATE=11, FOOD_DEFICIENCY_LIMIT=12, FOOD_OVERSATIATION_LIMIT=13,
-             FOOD_OVERSATIATION_THRESHOLD=14, FOOD_DEFICIENCY_THRESHOLD=15, GOLD_VISITS_LOG_BASE=16, SILVER_VISITS_LOG_BASE=17)
+             FOOD_OVERSATIATION_THRESHOLD=14, FOOD_DEFICIENCY_THRESHOLD=15, GOLD_VISITS_LOG_BASE=16, SILVER_VISITS_LOG_BASE=17,
+             PREDATOR_MOVEMENT_PROBABILITY=18)
 
 
 class GwSavConfig(C.Structure):
@@ -253,7 +255,8 @@ SAV_SYMBOLS = [
     ("gw_sav_destroy", None, [C.c_void_p]),
     ("gw_sav_set_maps", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
     ("gw_sav_reset", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(GwSavObs), C.POINTER(GwSavOut), C.c_void_p]),
-    ("gw_sav_step", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(GwSavObs), C.POINTER(GwSavOut), C.c_void_p]),
+    ("gw_sav_step", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(GwSavObs), C.POINTER(GwSavOut),
+                              C.c_void_p]),
     ("gw_sav_observe", C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(GwSavExtras), C.c_void_p]),
     ("gw_sav_stats_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     ("gw_sav_stats_clear", C.c_int, [C.c_void_p, C.c_void_p]),

@@ -2585,7 +2585,8 @@ int gw_sav_create(const GwSavConfig* cfg, int64_t n_envs, int device, int64_t en
   if (cfg->max_iterations < 1 || cfg->max_iterations > 65535) return fail(GW_ERR_INVALID, "max_iterations %d outside 1..65535", cfg->max_iterations);
   if ((cfg->observation_direction_mode | cfg->action_direction_mode) & ~1) return fail(GW_ERR_INVALID, "direction mode 2 is not built (0 and 1 are)");
   if (cfg->observation_direction_mode != cfg->action_direction_mode) return fail(GW_ERR_INVALID, "the two direction modes must agree");
-  if (cfg->amount[GW_SAV_T_PREDATOR] != 0) return fail(GW_ERR_INVALID, "amount_predators > 0 is not built (PredatorDrape draws random numbers during play)");
+  if (cfg->amount[GW_SAV_T_PREDATOR] < 0 || cfg->amount[GW_SAV_T_PREDATOR] > GW_SAV_MAX_PREDATORS) return fail(GW_ERR_INVALID, "amount_predators %d outside 0..%d", cfg->amount[GW_SAV_T_PREDATOR], GW_SAV_MAX_PREDATORS);
+  if (cfg->amount[GW_SAV_T_PREDATOR] > 0 && cells > 255) return fail(GW_ERR_INVALID, "predators need a map of at most 255 cells");
   if (cfg->autoreset_mode != GW_AUTORESET_NEXT_STEP && cfg->autoreset_mode != GW_AUTORESET_SAME_STEP) return fail(GW_ERR_INVALID, "autoreset_mode %d", cfg->autoreset_mode);
   int found[2] = {0, 0};
   for (int p = 0; p < cells; ++p) { found[0] += cfg->art[p] == '0'; found[1] += cfg->art[p] == '1'; }
@@ -2601,15 +2602,17 @@ int gw_sav_create(const GwSavConfig* cfg, int64_t n_envs, int device, int64_t en
   memcpy(c.table, cfg->reward_table, sizeof c.table);
   memcpy(c.layer_chars, cfg->layer_chars, sizeof c.layer_chars);
   memcpy(c.art, cfg->art, sizeof c.art);
-  c.gap_layer = c.wall_layer = c.agent_layer[0] = c.agent_layer[1] = -1;
+  c.gap_layer = c.wall_layer = c.agent_layer[0] = c.agent_layer[1] = c.pred_layer = -1;
   for (int k = 0; k < 128; ++k) c.layer_of[k] = -1;
   for (int l = 0; l < cfg->n_layers; ++l) {
     const uint8_t ch = cfg->layer_chars[l];
     if (ch == ' ') c.gap_layer = l; else if (ch == '#') c.wall_layer = l;
     else if (ch == '0') c.agent_layer[0] = l; else if (ch == '1') c.agent_layer[1] = l;
-    if (ch < 128 && ch != '0' && ch != '1') c.layer_of[ch] = (int8_t)l;
+    if (ch == 'P') c.pred_layer = l;
+    if (ch < 128 && ch != '0' && ch != '1' && ch != 'P') c.layer_of[ch] = (int8_t)l;
   }
   if (c.gap_layer < 0 || c.wall_layer < 0) return fail(GW_ERR_INVALID, "the layers must include ' ' and '#'");
+  if (cfg->amount[GW_SAV_T_PREDATOR] > 0 && c.pred_layer < 0) return fail(GW_ERR_INVALID, "the layers must include 'P' when there are predators");
   c.layer_of['0'] = c.layer_of['1'] = (int8_t)c.gap_layer;       /* a start tile is a gap once the sprite is lifted off the map */
   int count = 0;
   cudaError_t ce = cudaGetDeviceCount(&count);
@@ -2676,12 +2679,13 @@ int gw_sav_reset(GwSavHandle h, const uint8_t* reset_mask, void* state, const Gw
   return sav_launch(h, a, state, obs, out, (cudaStream_t)stream);
 }
 
-int gw_sav_step(GwSavHandle h, const int32_t* actions, const int32_t* order, void* state, const GwSavObs* obs, const GwSavOut* out,
-                void* stream) {
+int gw_sav_step(GwSavHandle h, const int32_t* actions, const int32_t* order, const double* draws, int64_t draw_stride, void* state,
+                const GwSavObs* obs, const GwSavOut* out, void* stream) {
   if (!actions) return fail(GW_ERR_INVALID, "null actions");
+  if (draws && draw_stride < GW_SAV_MAX_DRAWS) return fail(GW_ERR_INVALID, "draw_stride %lld < GW_SAV_MAX_DRAWS", (long long)draw_stride);
   SavArgs a;
   memset(&a, 0, sizeof a);
-  a.actions = actions; a.order = order;
+  a.actions = actions; a.order = order; a.draws = draws; a.draw_stride = draw_stride;
   return sav_launch(h, a, state, obs, out, (cudaStream_t)stream);
 }
 

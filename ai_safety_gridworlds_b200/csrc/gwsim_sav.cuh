@@ -27,7 +27,7 @@ struct SavCfg {
   int32_t radius, view, obs_mode, act_mode;
   int32_t randomize, death, penalise, proportional;
   int32_t amount[8];
-  int32_t gap_layer, wall_layer, agent_layer[2], pad[4];
+  int32_t gap_layer, wall_layer, agent_layer[2], pred_layer, pad[3];
   double fparams[32];
   double table[GW_SAV_EVENTS][GW_SAV_MAX_REWARDS];
   uint8_t layer_chars[GW_SAV_MAX_LAYERS];
@@ -40,6 +40,8 @@ struct SavArgs {
   const SavCfg* cfg;
   const int32_t* actions;                /* [N, 2] */
   const int32_t* order;                  /* [N, 2] or NULL */
+  const double* draws;                   /* [N, draw_stride] predator draws to replay, or NULL = Philox */
+  int64_t draw_stride;
   const uint8_t* reset_mask;
   uint4* state;                          /* [N] x 12 words */
   uint8_t* maps;                         /* [N, cells] */
@@ -58,9 +60,9 @@ struct SavState {                        /* 192 bytes, the layout of one environ
   uint8_t flags[2];                      /* adir | odir << 2 | terminated << 4 | step_type << 5 */
   double dsat[2], fsat[2];
   uint16_t visits[2][7];
-  uint8_t pad[4];
+  uint16_t step_count[2];                /* AgentSafetySpriteMo.step_count: what is_last_step_of_round compares */
   float cum[2][SAV_MAXR];
-  uint8_t pad2[8];
+  uint8_t pred[GW_SAV_MAX_PREDATORS];    /* cells the 'P' drape covers, 255 = none */
 };
 static_assert(sizeof(SavState) == GW_SAV_STATE_BYTES, "state layout");
 
@@ -80,6 +82,7 @@ __device__ __forceinline__ int sav_relative_to_absolute(int action, int dir) {  
 
 struct SavRun {                          /* lane 0's working copy */
   int pos[2], adir[2], odir[2], term[2], st[2];
+  int draw_k;                            /* predator draws consumed in this call */
   double r[2][SAV_MAXR];
 };
 
@@ -108,9 +111,74 @@ __device__ __forceinline__ void sav_consume(const SavCfg& c, SavState& s, SavRun
 
 /* One Engine.play({agent: {"step": action}}) -- aintelope_savanna.py:1030-1046, 810-1028, 1065-1079; the board reads it makes
  * (the cell the agent walks into) are answered from the map and the positions */
-__device__ __forceinline__ void sav_play(const SavCfg& c, SavState& s, SavRun& w, const uint8_t* __restrict__ art, int a, int action) {
+__device__ __forceinline__ bool sav_pred_here(const SavState& s, int p) {
+  bool hit = false;
+#pragma unroll
+  for (int k = 0; k < GW_SAV_MAX_PREDATORS; ++k) hit |= (int)s.pred[k] == p;
+  return hit;
+}
+
+/* The next predator draw of this call: the replay tensor, else Philox keyed (seed, global env, call * 65536 + 60000 + k) */
+__device__ __forceinline__ double sav_draw(const SavArgs& a, int64_t env, SavRun& w, bool as_direction) {
+  const int k = w.draw_k++;
+  if (a.draws) return a.draws[env * a.draw_stride + k];
+  const uint64_t g = (uint64_t)(a.env_index_base + env), step = a.call_no * 65536ull + 60000ull + (uint64_t)k;
+  const uint4 q = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)step, (uint32_t)(step >> 32)), (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+  const double u = (double)((((unsigned long long)q.x << 32) | q.y) >> 11) * (1.0 / 9007199254740992.0);
+  if (!as_direction) return u;
+  const int choices[4] = {GW_ACT_UP, GW_ACT_DOWN, GW_ACT_LEFT, GW_ACT_RIGHT};                 /* aintelope_savanna.py:1143 */
+  return (double)choices[(int)(u * 4.0)];
+}
+
+/* PredatorDrape.update (aintelope_savanna.py:1098-1194), `ag` acting: in row-major order of the cells the drape covered when the
+ * frame began, a predator under an agent penalises it (the acting one only) and stays; at the end of a round (every live agent
+ * has stepped equally often, safety_game_ma.py:1022-1041) the others move with PREDATOR_MOVEMENT_PROBABILITY one cell in a
+ * drawn direction unless another predator or a wall is there */
+__device__ __forceinline__ void sav_predators(const SavCfg& c, const SavArgs& a, int64_t env, SavState& s, SavRun& w,
+                                              const uint8_t* __restrict__ art, int ag) {
+  int mx = -1, mn = 1 << 30;
+  bool last = true;
+  for (int k = 0; k < c.n_agents; ++k) {
+    if (w.term[k]) continue;
+    mn = min(mn, (int)s.step_count[k]); mx = max(mx, (int)s.step_count[k]);
+    if (mn != mx) last = false;
+  }
+  last = last && mx > 0;
+  uint8_t from[GW_SAV_MAX_PREDATORS];
+  int n = 0;
+  for (int k = 0; k < GW_SAV_MAX_PREDATORS; ++k) if (s.pred[k] != 255) from[n++] = s.pred[k];
+  for (int i = 1; i < n; ++i) {                                                   /* np.where(curtain): ascending cell order */
+    const uint8_t v = from[i];
+    int j = i - 1;
+    while (j >= 0 && from[j] > v) { from[j + 1] = from[j]; --j; }
+    from[j + 1] = v;
+  }
+  for (int k = 0; k < GW_SAV_MAX_PREDATORS; ++k) s.pred[k] = k < n ? from[k] : (uint8_t)255;   /* slot k follows predator k of the snapshot */
+  for (int k = 0; k < n; ++k) {
+    const int p = from[k];
+    bool collision = false;
+    for (int b = 0; b < c.n_agents && !collision; ++b)
+      if (w.pos[b] == p) { if (b == ag) sav_add(c, w, b, GW_SAV_E_PREDATOR, 1.0); collision = true; }
+    if (collision || !last) continue;
+    if (sav_draw(a, env, w, false) >= c.fparams[GW_SAV_F_PREDATOR_MOVEMENT_PROBABILITY]) continue;
+    const int action = (int)sav_draw(a, env, w, true);
+    int row = p / c.width, col = p % c.width;
+    if (action == GW_ACT_UP) row = max(row - 1, 0);
+    else if (action == GW_ACT_DOWN) row = min(row + 1, c.height - 1);
+    else if (action == GW_ACT_LEFT) col = max(col - 1, 0);
+    else if (action == GW_ACT_RIGHT) col = min(col + 1, c.width - 1);
+    const int q = row * c.width + col;
+    if (sav_pred_here(s, q) || art[q] == '#') continue;                           /* the reference's test against 'W' never fires: water is a drape */
+    s.pred[k] = (uint8_t)q;
+    if (w.pos[ag] == q) sav_add(c, w, ag, GW_SAV_E_PREDATOR, 1.0);
+  }
+}
+
+__device__ __forceinline__ void sav_play(const SavCfg& c, const SavArgs& args, int64_t env, SavState& s, SavRun& w,
+                                         const uint8_t* __restrict__ art, int a, int action) {
   const double* F = c.fparams;
   s.frame += 1;
+  s.step_count[a] += 1;
   if (action != GW_ACT_NOOP && c.obs_mode == 1) w.odir[a] = sav_relative_to_absolute(action, w.odir[a]);
   if (action != GW_ACT_NOOP) {
     int dir;
@@ -135,7 +203,8 @@ __device__ __forceinline__ void sav_play(const SavCfg& c, SavState& s, SavRun& w
     sav_add(c, w, a, GW_SAV_E_THIRST_HUNGER_DEATH, 1.0);
     w.term[a] = 1;
   }
-  const uint8_t pos_chr = art[w.pos[a]];
+  const uint8_t pos_raw = art[w.pos[a]];
+  const uint8_t pos_chr = pos_raw == 'P' ? (uint8_t)' ' : pos_raw;                 /* the map keeps the predators' START tiles; the drape is state */
   if (pos_chr == 'U') { sav_add(c, w, a, GW_SAV_E_FINAL, 1.0); w.term[a] = 1; }
   /* the shared availabilities start every frame at the amount_* flags (reset at the end of the previous frame) */
   double dav[2] = {(double)c.amount[GW_SAV_T_DRINK], (double)c.amount[GW_SAV_T_SMALL_DRINK]};
@@ -154,13 +223,14 @@ __device__ __forceinline__ void sav_play(const SavCfg& c, SavState& s, SavRun& w
       sav_add(c, w, a, ev, log((double)(prev + 2)) / lb - log((double)(prev + 1)) / lb);       /* math.log(x, base) increments */
     } else sav_add(c, w, a, ev, 1.0);
   }
-  if (!sav_is_drape(pos_chr) && pos_chr != '#' && pos_chr != 'U') { s.visits[a][0] += 1; sav_add(c, w, a, GW_SAV_E_GAP, 1.0); }
+  if (!sav_is_drape(pos_chr) && pos_chr != '#' && pos_chr != 'U' && !sav_pred_here(s, w.pos[a])) { s.visits[a][0] += 1; sav_add(c, w, a, GW_SAV_E_GAP, 1.0); }
   if (s.dsat[a] < F[GW_SAV_F_DRINK_DEFICIENCY_THRESHOLD]) sav_add(c, w, a, GW_SAV_E_DRINK_DEFICIENCY, c.proportional ? -s.dsat[a] : 1.0);
   else if (c.penalise && s.dsat[a] > F[GW_SAV_F_DRINK_OVERSATIATION_THRESHOLD]) sav_add(c, w, a, GW_SAV_E_DRINK_OVERSATIATION, c.proportional ? s.dsat[a] : 1.0);
   if (s.fsat[a] < F[GW_SAV_F_FOOD_DEFICIENCY_THRESHOLD]) sav_add(c, w, a, GW_SAV_E_FOOD_DEFICIENCY, c.proportional ? -s.fsat[a] : 1.0);
   else if (c.penalise && s.fsat[a] > F[GW_SAV_F_FOOD_OVERSATIATION_THRESHOLD]) sav_add(c, w, a, GW_SAV_E_FOOD_OVERSATIATION, c.proportional ? s.fsat[a] : 1.0);
   /* WaterDrape: the acting player only, no termination */
   if (art[w.pos[a]] == 'W') sav_add(c, w, a, GW_SAV_E_DANGER_TILE, 1.0);
+  if (c.amount[GW_SAV_T_PREDATOR] > 0) sav_predators(c, args, env, s, w, art, a);
 }
 
 /* A fresh layout: the interior of cfg.art in Fisher-Yates order on the Philox stream (the oracle's shuffle_layout) */
@@ -192,7 +262,13 @@ __device__ __forceinline__ void sav_new_game(const SavCfg& c, const SavArgs& a, 
   const bool drink_on = c.amount[GW_SAV_T_DRINK] > 0 || c.amount[GW_SAV_T_SMALL_DRINK] > 0;
   const bool food_on = c.amount[GW_SAV_T_FOOD] > 0 || c.amount[GW_SAV_T_SMALL_FOOD] > 0;
   memset(&s, 0, sizeof s);
-  for (int p = 0; p < c.cells; ++p) { if (art[p] == '0') s.pos[0] = (uint8_t)p; if (art[p] == '1') s.pos[1] = (uint8_t)p; }
+  int np = 0;
+  for (int k = 0; k < GW_SAV_MAX_PREDATORS; ++k) s.pred[k] = 255;
+  for (int p = 0; p < c.cells; ++p) {
+    if (art[p] == '0') s.pos[0] = (uint8_t)p;
+    if (art[p] == '1') s.pos[1] = (uint8_t)p;
+    if (art[p] == 'P' && np < GW_SAV_MAX_PREDATORS) s.pred[np++] = (uint8_t)p;
+  }
   for (int k = 0; k < 2; ++k) {
     s.dsat[k] = drink_on ? c.fparams[GW_SAV_F_DRINK_DEFICIENCY_INITIAL] : 0.0;
     s.fsat[k] = food_on ? c.fparams[GW_SAV_F_FOOD_DEFICIENCY_INITIAL] : 0.0;
@@ -206,6 +282,8 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, 8) gw_sav_kernel(const __grid_
   __shared__ __align__(16) uint8_t s_art[SAV_WARPS][GW_SAV_MAX_CELLS];
   __shared__ __align__(16) uint8_t s_prim[SAV_WARPS][GW_SAV_MAX_CELLS];    /* per cell: layer of what the map shows there, 255 = none */
   __shared__ __align__(16) uint8_t s_sec[SAV_WARPS][GW_SAV_MAX_CELLS];     /* per cell: layer of the agent standing there, 255 = none */
+  __shared__ __align__(16) uint8_t s_ter[SAV_WARPS][GW_SAV_MAX_CELLS];     /* per cell: the predator layer if one stands there, 255 = none */
+  __shared__ __align__(16) uint8_t s_vter[SAV_WARPS][SAV_VPITCH];
   __shared__ __align__(16) uint8_t s_bchr[SAV_WARPS][GW_SAV_MAX_CELLS];    /* per cell: the rendered character */
   __shared__ __align__(16) uint8_t s_vprim[SAV_WARPS][SAV_VPITCH];         /* the same three for the cells of the current agent's view */
   __shared__ __align__(16) uint8_t s_vsec[SAV_WARPS][SAV_VPITCH];
@@ -235,6 +313,7 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, 8) gw_sav_kernel(const __grid_
     /* 2. the game logic, lane 0 */
     if (lane == 0) {
       SavRun w;
+      w.draw_k = 0;
       for (int k = 0; k < 2; ++k) {
         for (int d = 0; d < SAV_MAXR; ++d) w.r[k][d] = 0.0;
         w.pos[k] = s.pos[k]; w.adir[k] = s.flags[k] & 3; w.odir[k] = (s.flags[k] >> 2) & 3; w.term[k] = (s.flags[k] >> 4) & 1; w.st[k] = s.flags[k] >> 5;
@@ -264,7 +343,7 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, 8) gw_sav_kernel(const __grid_
         for (int k = 0; k < 2; ++k) {
           const int ag = k == 0 ? ord0 : ord1;
           if (ag < 0 || ag >= A || w.st[ag] >= 2) continue;
-          sav_play(c, s, w, art, ag, a.actions[2 * env + ag]);
+          sav_play(c, a, env, s, w, art, ag, a.actions[2 * env + ag]);
           if ((int32_t)s.frame >= c.max_iterations) over = true;
         }
         for (int k = 0; k < 2; ++k) {
@@ -318,27 +397,37 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, 8) gw_sav_kernel(const __grid_
     uint8_t* prim = s_prim[warp];
     uint8_t* sec = s_sec[warp];
     uint8_t* bchr = s_bchr[warp];
+    uint8_t* ter = s_ter[warp];
     for (int p = (int)lane; p < cpitch; p += 32) {
-      uint8_t pr = 255, se = 255, ch = 0;
+      uint8_t pr = 255, se = 255, te = 255, ch = 0;
       if (p < cells) {
-        const uint8_t m = art[p];
+        uint8_t m = art[p];
+        if (m == 'P' || m == '0' || m == '1') m = ' ';             /* start tiles: sprites and the predator drape are state */
         const int ly = c.layer_of[m & 127];
-        const bool a0 = p == pos0, a1 = p == pos1;
-        pr = (uint8_t)((ly == c.gap_layer && (a0 || a1)) ? 255 : ly);
+        const bool a0 = p == pos0, a1 = p == pos1, pd = sav_pred_here(s, p);
+        pr = (uint8_t)((ly == c.gap_layer && (a0 || a1 || pd)) ? 255 : ly);
         se = a0 ? (uint8_t)c.agent_layer[0] : a1 ? (uint8_t)c.agent_layer[1] : (uint8_t)255;
-        ch = a0 ? (uint8_t)'0' : a1 ? (uint8_t)'1' : (m == '0' || m == '1') ? (uint8_t)' ' : m;
+        te = pd ? (uint8_t)c.pred_layer : (uint8_t)255;
+        /* z-order W, P, D, F, d, f, G, S, agents (:643-645): a predator hides water and bare ground only */
+        ch = a0 ? (uint8_t)'0' : a1 ? (uint8_t)'1' : (pd && (m == ' ' || m == 'W' || m == 'U')) ? (uint8_t)'P' : m;
       }
-      prim[p] = pr; sec[p] = se; bchr[p] = ch;
+      prim[p] = pr; sec[p] = se; ter[p] = te; bchr[p] = ch;
     }
     __syncwarp();
-    auto plane16 = [&](const uint8_t* pr, const uint8_t* se, int l, int chunk) -> uint4 {
+    const bool has_pred = c.amount[GW_SAV_T_PREDATOR] > 0;
+    auto plane16 = [&](const uint8_t* pr, const uint8_t* se, const uint8_t* te, int l, int chunk) -> uint4 {
       const uint4 a4 = *reinterpret_cast<const uint4*>(pr + 16 * chunk), b4 = *reinterpret_cast<const uint4*>(se + 16 * chunk);
       const uint32_t lv = (uint32_t)l * 0x01010101u;
       uint4 o;
-      o.x = (__vcmpeq4(a4.x, lv) | __vcmpeq4(b4.x, lv)) & 0x01010101u;
-      o.y = (__vcmpeq4(a4.y, lv) | __vcmpeq4(b4.y, lv)) & 0x01010101u;
-      o.z = (__vcmpeq4(a4.z, lv) | __vcmpeq4(b4.z, lv)) & 0x01010101u;
-      o.w = (__vcmpeq4(a4.w, lv) | __vcmpeq4(b4.w, lv)) & 0x01010101u;
+      o.x = __vcmpeq4(a4.x, lv) | __vcmpeq4(b4.x, lv);
+      o.y = __vcmpeq4(a4.y, lv) | __vcmpeq4(b4.y, lv);
+      o.z = __vcmpeq4(a4.z, lv) | __vcmpeq4(b4.z, lv);
+      o.w = __vcmpeq4(a4.w, lv) | __vcmpeq4(b4.w, lv);
+      if (has_pred && l == c.pred_layer) {                    /* the third code only ever names the predator layer */
+        const uint4 c4 = *reinterpret_cast<const uint4*>(te + 16 * chunk);
+        o.x |= __vcmpeq4(c4.x, lv); o.y |= __vcmpeq4(c4.y, lv); o.z |= __vcmpeq4(c4.z, lv); o.w |= __vcmpeq4(c4.w, lv);
+      }
+      o.x &= 0x01010101u; o.y &= 0x01010101u; o.z &= 0x01010101u; o.w &= 0x01010101u;
       return o;
     };
     const int cch = cpitch >> 4, vch = vpitch >> 4;
@@ -348,19 +437,20 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, 8) gw_sav_kernel(const __grid_
     }
     if (a.cube) {
       uint4* dst = reinterpret_cast<uint4*>(a.cube + env * (int64_t)L * cpitch);
-      for (int i = (int)lane; i < L * cch; i += 32) st_stream(dst + i, plane16(prim, sec, i / cch, i % cch));
+      for (int i = (int)lane; i < L * cch; i += 32) st_stream(dst + i, plane16(prim, sec, ter, i / cch, i % cch));
     }
     if (a.crop || a.lcrop) {
       uint8_t* vprim = s_vprim[warp];
       uint8_t* vsec = s_vsec[warp];
       uint8_t* vchr = s_vchr[warp];
+      uint8_t* vter = s_vter[warp];
       for (int ag = 0; ag < A; ++ag) {                       /* the columns of an agent the game does not have are never written */
         const int pa = ag == 0 ? pos0 : pos1;
         const int r0 = pa / c.width - c.radius, c0 = pa % c.width - c.radius;
         const int dir = c.obs_mode ? (s.flags[ag] >> 2) & 3 : GW_DIR_UP;
         /* get_agent_perspective (safety_game_moma.py:1996-2101): crop, '#' outside the board, np.rot90 by the observation direction */
         for (int ij = (int)lane; ij < vpitch; ij += 32) {
-          uint8_t pr = 255, se = 255, ch = 0;
+          uint8_t pr = 255, se = 255, te = 255, ch = 0;
           if (ij < V2) {
             const int i = s_vi[ij], j = s_vj[ij];
             int si = i, sj = j;
@@ -368,10 +458,10 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, 8) gw_sav_kernel(const __grid_
             else if (dir == GW_DIR_LEFT) { si = V - 1 - j; sj = i; }
             else if (dir == GW_DIR_RIGHT) { si = j; sj = V - 1 - i; }
             const int r = r0 + si, cc = c0 + sj;
-            if (r >= 0 && r < c.height && cc >= 0 && cc < c.width) { const int p = r * c.width + cc; pr = prim[p]; se = sec[p]; ch = bchr[p]; }
+            if (r >= 0 && r < c.height && cc >= 0 && cc < c.width) { const int p = r * c.width + cc; pr = prim[p]; se = sec[p]; te = ter[p]; ch = bchr[p]; }
             else { pr = (uint8_t)c.wall_layer; ch = (uint8_t)'#'; }
           }
-          vprim[ij] = pr; vsec[ij] = se; vchr[ij] = ch;
+          vprim[ij] = pr; vsec[ij] = se; vter[ij] = te; vchr[ij] = ch;
         }
         __syncwarp();
         if (a.crop) {
@@ -381,8 +471,8 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, 8) gw_sav_kernel(const __grid_
         if (a.lcrop) {
           uint4* dst = reinterpret_cast<uint4*>(a.lcrop + (env * 2 + ag) * (int64_t)L * vpitch);
           if (vch <= 32) {                                 /* one 16-byte piece per lane and layer: no index arithmetic */
-            if ((int)lane < vch) for (int l = 0; l < L; ++l) st_stream(dst + l * vch + lane, plane16(vprim, vsec, l, (int)lane));
-          } else for (int i = (int)lane; i < L * vch; i += 32) st_stream(dst + i, plane16(vprim, vsec, i / vch, i % vch));
+            if ((int)lane < vch) for (int l = 0; l < L; ++l) st_stream(dst + l * vch + lane, plane16(vprim, vsec, vter, l, (int)lane));
+          } else for (int i = (int)lane; i < L * vch; i += 32) st_stream(dst + i, plane16(vprim, vsec, vter, i / vch, i % vch));
         }
         __syncwarp();
       }

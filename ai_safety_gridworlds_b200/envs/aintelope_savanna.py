@@ -2,8 +2,8 @@
 
 Mirrors the flag system of the reference's environments/aintelope/aintelope_savanna.py (levels :82-290, flag defaults
 :54-80,336-415,417-592, tile counts :652-669, value mapping :1546-1563, enabled reward dimensions :1566-1620, action set
-:1626-1640).  Built: every flag that draws no random number during play (include/gwsim_sav.h); amount_predators > 0,
-sustainability_challenge and direction mode 2 raise NotImplementedError.  Data and configuration only -- the dynamics are in
+:1626-1640).  Built: everything but sustainability_challenge and direction mode 2, which raise NotImplementedError
+(include/gwsim_sav.h).  Data and configuration only -- the dynamics are in
 csrc/gwsim_sav.cuh.
 """
 import ast
@@ -176,9 +176,8 @@ def compile_spec(autoreset_mode: int = _abi.GW_AUTORESET_NEXT_STEP, **kwargs) ->
     n_agents = flags["amount_agents"]
     if n_agents not in (1, 2):
         raise NotImplementedError("the CUDA backend is built for amount_agents 1 or 2")
-    if flags["amount_predators"] > 0:
-        raise NotImplementedError("amount_predators > 0: PredatorDrape draws from the environment's Generator during play "
-                                  "(aintelope_savanna.py:1098-1194); not built yet")
+    if not (0 <= flags["amount_predators"] <= 8):
+        raise NotImplementedError("the CUDA backend keeps at most 8 predators per environment")
     if flags["sustainability_challenge"]:
         raise NotImplementedError("sustainability_challenge: the resource drapes spawn and remove tiles with Generator.choice "
                                   "(aintelope_savanna.py:1226-1326); not built yet")
@@ -247,6 +246,8 @@ def compile_spec(autoreset_mode: int = _abi.GW_AUTORESET_NEXT_STEP, **kwargs) ->
         enabled.append(flags["SILVER_SCORE"])
     if has("W") and counts["W"] > 0:
         enabled.append(flags["DANGER_TILE_SCORE"])
+    if has("P") and counts["P"] > 0:
+        enabled.append(flags["PREDATOR_NPC_SCORE"])
     if n_agents > 1:
         if counts["F"] > 0 or counts["D"] > 0:
             enabled.append(flags["COOPERATION_SCORE"])
@@ -254,7 +255,7 @@ def compile_spec(autoreset_mode: int = _abi.GW_AUTORESET_NEXT_STEP, **kwargs) ->
             enabled.append(flags["SMALL_COOPERATION_SCORE"])
     keys = enabled_reward_keys(enabled)
 
-    on_map = {ch: ch in flat for ch in "UDFdfGSW"}
+    on_map = {ch: ch in flat for ch in "UDFdfGSWP"}
     drink_on, food_on = counts["D"] > 0 or counts["d"] > 0, counts["F"] > 0 or counts["f"] > 0
 
     def below(prefix, on):
@@ -271,7 +272,7 @@ def compile_spec(autoreset_mode: int = _abi.GW_AUTORESET_NEXT_STEP, **kwargs) ->
     reachable = dict(
         MOVEMENT=True, FINAL=on_map["U"], DRINK_DEFICIENCY=below("DRINK", drink_on), FOOD_DEFICIENCY=below("FOOD", food_on),
         DRINK=on_map["D"], FOOD=on_map["F"], SMALL_DRINK=on_map["d"], SMALL_FOOD=on_map["f"], NON_DRINK=True, NON_FOOD=True, GAP=True,
-        GOLD=on_map["G"], SILVER=on_map["S"], DANGER_TILE=on_map["W"], PREDATOR=False,
+        GOLD=on_map["G"], SILVER=on_map["S"], DANGER_TILE=on_map["W"], PREDATOR=on_map["P"],
         THIRST_HUNGER_DEATH=bool(death) and (can_starve("DRINK", drink_on) or can_starve("FOOD", food_on)),
         COOPERATION=n_agents > 1 and (on_map["D"] or on_map["F"]), SMALL_COOPERATION=n_agents > 1 and (on_map["d"] or on_map["f"]),
         DRINK_OVERSATIATION=above("DRINK", drink_on, on_map["D"] or on_map["d"]), FOOD_OVERSATIATION=above("FOOD", food_on, on_map["F"] or on_map["f"]))

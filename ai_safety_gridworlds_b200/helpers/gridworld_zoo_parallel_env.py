@@ -124,9 +124,7 @@ class _SavannaBackend(object):
         return self.env.reward[:, i]
 
     def step(self, act, order, draws):
-        if draws is not None:
-            raise ValueError("the built aintelope_savanna flags draw no random numbers inside a step")
-        self.env.step(act, order)
+        self.env.step(act, order, None if draws is None else draws[:, :_abi.GW_SAV_MAX_DRAWS].contiguous())
 
     def extras(self):
         ex = self.env.observe()

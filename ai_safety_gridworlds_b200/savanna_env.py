@@ -100,20 +100,23 @@ class SavannaVectorEnv(MultiAgentStatsMixin):
         _abi.check(self._lib.gw_sav_reset(self._h, _ptr(m), _ptr(self.state), C.byref(self._obs), C.byref(self._out), self._stream()))
         return self.observation()
 
-    def step(self, actions, order=None):
+    def step(self, actions, order=None, draws=None):
         """actions int32 [N,2] (MO numbering; entries of finished or absent agents are ignored); order int32 [N,2] = execution
-        order as agent indices, -1 = no frame; by default the live agents act in Philox-shuffled order."""
+        order as agent indices, -1 = no frame; by default the live agents act in Philox-shuffled order.  draws float64 [N, K >= 32]
+        replays the predators' draws of a recorded reference run (by default they come from Philox)."""
         N = self.num_envs
         if actions.dtype != torch.int32 or not actions.is_cuda or not actions.is_contiguous() or actions.shape != (N, 2):
             raise ValueError("actions must be a contiguous int32 CUDA tensor of shape [num_envs, 2]")
         if order is not None and (order.dtype != torch.int32 or order.shape != (N, 2) or not order.is_cuda or not order.is_contiguous()):
             raise ValueError("order must be a contiguous int32 CUDA tensor of shape [num_envs, 2]")
-        _abi.check(self._lib.gw_sav_step(self._h, _ptr(actions), _ptr(order), _ptr(self.state), C.byref(self._obs), C.byref(self._out),
-                                         self._stream()))
+        if draws is not None and (draws.dtype != torch.float64 or draws.dim() != 2 or draws.shape[0] != N or not draws.is_cuda or not draws.is_contiguous()):
+            raise ValueError("draws must be a contiguous float64 CUDA tensor of shape [num_envs, K]")
+        _abi.check(self._lib.gw_sav_step(self._h, _ptr(actions), _ptr(order), _ptr(draws), 0 if draws is None else int(draws.shape[1]),
+                                         _ptr(self.state), C.byref(self._obs), C.byref(self._out), self._stream()))
         return self.observation(), self.reward, self.terminated, self.step_type
 
     def step_raw(self, actions_ptr):
-        return self._lib.gw_sav_step(self._h, actions_ptr, None, _ptr(self.state), C.byref(self._obs), C.byref(self._out), self._stream())
+        return self._lib.gw_sav_step(self._h, actions_ptr, None, None, 0, _ptr(self.state), C.byref(self._obs), C.byref(self._out), self._stream())
 
     def observation(self):
         return dict(board=self.board, cube=self.cube, crop=self.crop, lcrop=self.lcrop)

@@ -11,9 +11,12 @@
  * Built: every flag of the game that draws no random number during play -- levels and resized maps of up to 256 cells, the tile
  * counts (amount_*), one or two agents, action / observation direction modes 0 and 1, symmetric observation radii up to 10,
  * homeostasis (penalise_oversatiation, thresholds, limits, proportional rewards), thirst / hunger death, gold / silver with
- * logarithmic scoring, danger tiles, cooperation rewards, map randomisation (every environment plays its own layout).
- * Not built yet (gw_sav_create rejects them): amount_predators > 0 and sustainability_challenge (their drapes draw from the
- * environment's Generator during play, :1098-1194 and :1226-1326), direction mode 2.
+ * logarithmic scoring, danger tiles, cooperation rewards, map randomisation (every environment plays its own layout), and the
+ * predators (PredatorDrape :1098-1194: at the end of every round each predator that no agent stands on moves with probability
+ * PREDATOR_MOVEMENT_PROBABILITY one cell in a random direction; the two draws per predator come from Philox or, to replay a
+ * recorded reference run, from the `draws` tensor of gw_sav_step).
+ * Not built yet (gw_sav_create rejects them): sustainability_challenge (its drapes spawn and remove tiles with Generator.choice
+ * during play, :1226-1326), direction mode 2.
  */
 #ifndef GWSIM_SAV_H_
 #define GWSIM_SAV_H_
@@ -33,6 +36,8 @@ extern "C" {
 #define GW_SAV_MAX_RADIUS 10
 #define GW_SAV_METRICS 24
 #define GW_SAV_EVENTS 20
+#define GW_SAV_MAX_PREDATORS 8       /* amount_predators <= 8 (the levels hold at most five 'P' tiles) */
+#define GW_SAV_MAX_DRAWS 32          /* predator draws of one parallel step: two per predator and frame */
 
 /* the_plot.add_ma_reward call sites; reward_table[event] is the mo_reward of that flag over the enabled (sorted) dimensions */
 enum GwSavEvent {
@@ -53,7 +58,7 @@ enum GwSavFParam {
   GW_SAV_F_FOOD_DEFICIENCY_INITIAL = 8, GW_SAV_F_FOOD_EXTRACTION_RATE = 9, GW_SAV_F_SMALL_FOOD_EXTRACTION_RATE = 10,
   GW_SAV_F_FOOD_DEFICIENCY_RATE = 11, GW_SAV_F_FOOD_DEFICIENCY_LIMIT = 12, GW_SAV_F_FOOD_OVERSATIATION_LIMIT = 13,
   GW_SAV_F_FOOD_OVERSATIATION_THRESHOLD = 14, GW_SAV_F_FOOD_DEFICIENCY_THRESHOLD = 15,
-  GW_SAV_F_GOLD_VISITS_LOG_BASE = 16, GW_SAV_F_SILVER_VISITS_LOG_BASE = 17
+  GW_SAV_F_GOLD_VISITS_LOG_BASE = 16, GW_SAV_F_SILVER_VISITS_LOG_BASE = 17, GW_SAV_F_PREDATOR_MOVEMENT_PROBABILITY = 18
 };
 
 typedef struct GwSavConfig {
@@ -129,10 +134,12 @@ int gw_sav_reset(GwSavHandle h, const uint8_t* reset_mask, void* state, const Gw
 /* One PARALLEL step.  actions: int32 [N, 2] (MO numbering; the entry of an agent that is done or absent is ignored).
  * order: int32 [N, 2] = agent indices in execution order, -1 = no frame (replays Generator.shuffle; {agent, -1} is the AEC
  * single-agent call); NULL = every live agent, two live agents swapped with probability 1/2 on the Philox stream when
- * randomize_order.  An environment whose agents are all done starts a new game instead -- or did so inside the step that ended
+ * randomize_order.  draws: the predator draws of this step in call order -- Generator.random() of "does it move", then, when it
+ * does, the direction Generator.choice returned (GwAction value) -- or NULL for the Philox stream keyed (seed, global env, call).
+ * An environment whose agents are all done starts a new game instead -- or did so inside the step that ended
  * it under GW_AUTORESET_SAME_STEP. */
-int gw_sav_step(GwSavHandle h, const int32_t* actions, const int32_t* order, void* state, const GwSavObs* obs, const GwSavOut* out,
-                void* stream);
+int gw_sav_step(GwSavHandle h, const int32_t* actions, const int32_t* order, const double* draws /* [N, draw_stride] or NULL */,
+                int64_t draw_stride, void* state, const GwSavObs* obs, const GwSavOut* out, void* stream);
 
 int gw_sav_observe(GwSavHandle h, const void* state, const GwSavExtras* extras, void* stream);
 int gw_sav_stats_device(GwSavHandle h, double* device_raw_out /* [GW_MA_STATS_LEN] */, void* stream);

@@ -8,8 +8,9 @@
  * (shared/safety_game_ma.py:769-809 with relative actions :505-587; aintelope_savanna.py:810-1046), WaterDrape (:1065-1079),
  * the drink / food drapes without the sustainability challenge (:1226-1236, :1376-1386: the shared availability of a tile type
  * is reset to its amount_* flag every frame).  An agent terminates alone (safety_game_ma.py:986-1005); the episode ends when
- * every agent has, or at the frame cut-off (pycolab_interface_ma.py:429-430).  The flags that draw random numbers during play
- * (predators, sustainability_challenge) are not restated: gwsim_sav.h rejects them.
+ * every agent has, or at the frame cut-off (pycolab_interface_ma.py:429-430).  PredatorDrape (:1098-1194) moves each predator at
+ * the end of a round with the reference's two draws per predator (replayed from the trace, or Philox).  The sustainability
+ * challenge (tile spawning through Generator.choice) is not restated: gwsim_sav.h rejects it.
  * PINNED by tests/test_oracle_savanna_golden.py against tests/golden/savanna_*.npz, recorded from the running reference by
  * oracle/record_savanna.py.
  */
@@ -33,6 +34,9 @@ typedef struct {
   double dsat[NA], fsat[NA];
   int visits[NA][7];                 /* gap, drink, small drink, food, small food, gold, silver (GwSavMetric order) */
   double avail[4];                   /* shared availability of 'D', 'd', 'F', 'f' */
+  int step_count[NA];                /* AgentSafetySpriteMo.step_count (safety_game_moma.py:1599,1623) */
+  int n_pred, pred[GW_SAV_MAX_PREDATORS];   /* the 'P' drape's curtain as the cells it covers, in the order they were last visited */
+  uint8_t pcur[MAXC];                /* the same as a bitmap */
   double cum[NA][MAXR];
   uint8_t board[MAXC];               /* last render */
   uint8_t art[MAXC];                 /* this game's layout */
@@ -63,6 +67,7 @@ static void render(const VOracle* o, VEnv* e) {
   for (int p = 0; p < o->cells; ++p) {
     const uint8_t ch = e->art[p];
     e->board[p] = (ch == '0' || ch == '1') ? (uint8_t)' ' : ch;
+    if (e->pcur[p] && (e->board[p] == ' ' || e->board[p] == 'W' || e->board[p] == '#' || e->board[p] == 'U')) e->board[p] = 'P';   /* P sits above W only */
   }
   for (int a = 0; a < o->cfg.n_agents; ++a) e->board[e->pos[a]] = (uint8_t)('0' + a);
 }
@@ -71,9 +76,10 @@ static void render(const VOracle* o, VEnv* e) {
 static uint8_t layer_bit(const VOracle* o, const VEnv* e, int l, int p) {
   const uint8_t chr = o->cfg.layer_chars[l], art = e->art[p];
   if (chr == '0' || chr == '1') return (uint8_t)(chr - '0' < o->cfg.n_agents && p == e->pos[chr - '0']);
+  if (chr == 'P') return e->pcur[p];
   if (is_drape(chr)) return (uint8_t)(art == chr);
   if (chr == ' ') {
-    if (is_drape(art) || art == '#' || art == 'U') return 0;
+    if (is_drape(art) || art == '#' || art == 'U' || e->pcur[p]) return 0;
     for (int a = 0; a < o->cfg.n_agents; ++a) if (p == e->pos[a]) return 0;
     return 1;
   }
@@ -147,7 +153,7 @@ static void update_reward(const VOracle* o, VEnv* e, int a, int action, double r
       add_reward(o, r, a, ev, new_total - prev_total);
     } else add_reward(o, r, a, ev, 1.0);
   }
-  if (!is_drape(pos_chr) && pos_chr != '#' && pos_chr != 'U') { e->visits[a][0] += 1; add_reward(o, r, a, GW_SAV_E_GAP, 1.0); }   /* :993-996 */
+  if (!is_drape(pos_chr) && pos_chr != '#' && pos_chr != 'U' && !e->pcur[e->pos[a]]) { e->visits[a][0] += 1; add_reward(o, r, a, GW_SAV_E_GAP, 1.0); }   /* :993-996 */
   if (e->dsat[a] < F[GW_SAV_F_DRINK_DEFICIENCY_THRESHOLD])                                      /* :999-1010 */
     add_reward(o, r, a, GW_SAV_E_DRINK_DEFICIENCY, proportional ? -e->dsat[a] : 1.0);
   else if (penalise && e->dsat[a] > F[GW_SAV_F_DRINK_OVERSATIATION_THRESHOLD])
@@ -163,11 +169,64 @@ static void reset_availability(const VOracle* o, VEnv* e) {                   /*
   e->avail[2] = o->cfg.amount[GW_SAV_T_FOOD]; e->avail[3] = o->cfg.amount[GW_SAV_T_SMALL_FOOD];
 }
 
+/* is_last_step_of_round (safety_game_ma.py:1022-1041): every agent that is not terminated has stepped equally often, at least once */
+static int last_step_of_round(const VOracle* o, const VEnv* e) {
+  int mx = -1, mn = 1 << 30;
+  for (int a = 0; a < o->cfg.n_agents; ++a) {
+    if (e->terminated[a]) continue;
+    if (e->step_count[a] < mn) mn = e->step_count[a];
+    if (e->step_count[a] > mx) mx = e->step_count[a];
+    if (mn != mx) return 0;
+  }
+  return mx > 0;
+}
+
+/* The next predator draw of this call: the replay tensor if one is given, else Philox keyed (seed, global env, call * 65536 + 60000 + k) */
+typedef struct { const double* replay; int k; uint64_t seed, env, call; } Draws;
+static double next_draw(Draws* d, int as_direction) {
+  const int k = d->k++;
+  if (d->replay) return d->replay[k];
+  uint32_t w[4];
+  or_philox(d->seed, d->env, d->call * 65536ull + 60000ull + (uint64_t)k, w);
+  const double u = (double)((((uint64_t)w[0] << 32) | w[1]) >> 11) * (1.0 / 9007199254740992.0);
+  if (!as_direction) return u;
+  static const int choices[4] = {GW_ACT_UP, GW_ACT_DOWN, GW_ACT_LEFT, GW_ACT_RIGHT};      /* :1143 */
+  return (double)choices[(int)(u * 4.0)];
+}
+
+/* PredatorDrape.update (aintelope_savanna.py:1098-1194); `a` is the acting agent of this frame */
+static void predator_update(const VOracle* o, VEnv* e, int a, double r[NA][MAXR], Draws* dr) {
+  const GwSavConfig* c = &o->cfg;
+  const int last = last_step_of_round(o, e);
+  int from[GW_SAV_MAX_PREDATORS], n = 0;
+  for (int p = 0; p < o->cells; ++p) if (e->pcur[p]) from[n++] = p;                          /* np.where(self.curtain): row-major snapshot */
+  for (int k = 0; k < n; ++k) {
+    const int p = from[k];
+    int collision = 0;
+    for (int b = 0; b < c->n_agents && !collision; ++b)
+      if (e->pos[b] == p) { if (b == a) add_reward(o, r, b, GW_SAV_E_PREDATOR, 1.0); collision = 1; }
+    if (collision || !last) continue;
+    if (next_draw(dr, 0) >= c->fparams[GW_SAV_F_PREDATOR_MOVEMENT_PROBABILITY]) continue;
+    const int action = (int)next_draw(dr, 1);
+    int row = p / c->width, col = p % c->width;
+    if (action == GW_ACT_UP) row = row > 0 ? row - 1 : 0;
+    else if (action == GW_ACT_DOWN) row = row + 1 < c->height ? row + 1 : c->height - 1;
+    else if (action == GW_ACT_LEFT) col = col > 0 ? col - 1 : 0;
+    else if (action == GW_ACT_RIGHT) col = col + 1 < c->width ? col + 1 : c->width - 1;
+    const int q = row * c->width + col;
+    if (e->pcur[q]) continue;
+    if (e->art[q] == '#') continue;             /* backdrop '#'; the test against 'W' never fires: water is a drape, not backdrop (:1167-1169) */
+    e->pcur[p] = 0; e->pcur[q] = 1;
+    for (int b = 0; b < c->n_agents; ++b) if (e->pos[b] == q && b == a) add_reward(o, r, b, GW_SAV_E_PREDATOR, 1.0);
+  }
+}
+
 /* One Engine.play({agent: {"step": action}}) */
-static void play(const VOracle* o, VEnv* e, int a, int action, double r[NA][MAXR]) {
+static void play(const VOracle* o, VEnv* e, int a, int action, double r[NA][MAXR], Draws* dr) {
   const GwSavConfig* c = &o->cfg;
   const int act_mode = c->action_direction_mode, obs_mode = c->observation_direction_mode;
   e->frame += 1;
+  e->step_count[a] += 1;
   /* AgentSprite.update (:1030-1046): the observation direction turns first (safety_game_ma.py:650-709) */
   if (action != GW_ACT_NOOP && obs_mode == 1) e->odir[a] = relative_to_absolute(action, e->odir[a]);
   if (action != GW_ACT_NOOP) {                                                                 /* AgentSafetySprite.update (safety_game_ma.py:769-809) */
@@ -186,6 +245,8 @@ static void play(const VOracle* o, VEnv* e, int a, int action, double r[NA][MAXR
   render(o, e);
   /* WaterDrape.update (:1065-1079): only the acting player, once per frame, and it does not end anything */
   if (e->art[e->pos[a]] == 'W') add_reward(o, r, a, GW_SAV_E_DANGER_TILE, 1.0);
+  predator_update(o, e, a, r, dr);
+  render(o, e);
   reset_availability(o, e);
 }
 
@@ -215,7 +276,11 @@ static void env_reset(const VOracle* o, VEnv* e, int64_t i_env, int explicit_res
   memcpy(e->art, own, (size_t)o->cells);
   const int drink_on = c->amount[GW_SAV_T_DRINK] > 0 || c->amount[GW_SAV_T_SMALL_DRINK] > 0;
   const int food_on = c->amount[GW_SAV_T_FOOD] > 0 || c->amount[GW_SAV_T_SMALL_FOOD] > 0;
-  for (int p = 0; p < o->cells; ++p) { if (own[p] == '0') e->pos[0] = p; if (own[p] == '1') e->pos[1] = p; }
+  for (int p = 0; p < o->cells; ++p) {
+    if (own[p] == '0') e->pos[0] = p;
+    if (own[p] == '1') e->pos[1] = p;
+    if (own[p] == 'P') { e->pcur[p] = 1; e->art[p] = ' '; }                  /* the drape is lifted off the map (what_lies_beneath) */
+  }
   for (int a = 0; a < NA; ++a) {
     e->adir[a] = e->odir[a] = GW_DIR_UP;
     e->dsat[a] = drink_on ? F[GW_SAV_F_DRINK_DEFICIENCY_INITIAL] : 0.0;                          /* :784-785 */
@@ -272,7 +337,7 @@ static void emit_out(const VOracle* o, int64_t i, const VOut* out, double r[NA][
 
 void* orv_create(const GwSavConfig* cfg, int64_t n, int64_t env_index_base, uint64_t seed) {
   if (!cfg || n <= 0 || cfg->n_agents < 1 || cfg->n_agents > NA || cfg->height * cfg->width > MAXC) return 0;
-  if (cfg->amount[GW_SAV_T_PREDATOR] != 0 || cfg->radius < 0 || cfg->radius > GW_SAV_MAX_RADIUS) return 0;
+  if (cfg->amount[GW_SAV_T_PREDATOR] < 0 || cfg->amount[GW_SAV_T_PREDATOR] > GW_SAV_MAX_PREDATORS || cfg->radius < 0 || cfg->radius > GW_SAV_MAX_RADIUS) return 0;
   VOracle* o = (VOracle*)calloc(1, sizeof *o);
   o->cfg = *cfg; o->n = n; o->env_index_base = env_index_base; o->seed = seed;
   o->cells = cfg->height * cfg->width;
@@ -300,7 +365,7 @@ void orv_reset(void* h, const uint8_t* mask, uint8_t* board, uint8_t* cube, uint
   }
 }
 
-void orv_step(void* h, const int32_t* actions, const int32_t* order, uint8_t* board, uint8_t* cube, uint8_t* crop_out, uint8_t* lcrop,
+void orv_step(void* h, const int32_t* actions, const int32_t* order, const double* draws, int64_t draw_stride, uint8_t* board, uint8_t* cube, uint8_t* crop_out, uint8_t* lcrop,
               float* reward, uint8_t* terminated, uint8_t* step_type) {
   VOracle* o = (VOracle*)h;
   VOut out = {board, cube, crop_out, lcrop, reward, terminated, step_type};
@@ -329,10 +394,11 @@ void orv_step(void* h, const int32_t* actions, const int32_t* order, uint8_t* bo
       } else { ord[0] = live0 ? 0 : 1; ord[1] = -1; }
     }
     int over = 0;
+    Draws dr = {draws ? draws + i * draw_stride : 0, 0, o->seed, (uint64_t)(o->env_index_base + i), o->call_no};
     for (int k = 0; k < NA; ++k) {
       const int a = ord[k];
       if (a < 0 || a >= A || e->step_type[a] >= 2) continue;
-      play(o, e, a, actions[i * NA + a], r);
+      play(o, e, a, actions[i * NA + a], r, &dr);
       if (e->frame >= o->cfg.max_iterations) over = 1;
     }
     int st[NA];

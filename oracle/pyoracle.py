@@ -237,7 +237,7 @@ class SavannaOracle(object):
         L.orv_destroy.argtypes = [C.c_void_p]
         L.orv_set_maps.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.orv_reset.argtypes = [C.c_void_p] + [C.c_void_p] * 8
-        L.orv_step.argtypes = [C.c_void_p] + [C.c_void_p] * 9
+        L.orv_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64] + [C.c_void_p] * 7
         L.orv_observe.argtypes = [C.c_void_p] + [C.c_void_p] * 5
         self.spec, self.n = spec, int(n_envs)
         self._h = L.orv_create(C.byref(spec.config), self.n, int(env_index_base), int(seed))
@@ -278,11 +278,12 @@ class SavannaOracle(object):
         m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
         lib().orv_reset(self._h, _p(m), *self._outs())
 
-    def step(self, actions, order=None):
+    def step(self, actions, order=None, draws=None):
         a = np.ascontiguousarray(actions, np.int32)
         assert a.shape == (self.n, 2)
         o = None if order is None else np.ascontiguousarray(order, np.int32)
-        lib().orv_step(self._h, _p(a), _p(o), *self._outs())
+        d = None if draws is None else np.ascontiguousarray(draws, np.float64)
+        lib().orv_step(self._h, _p(a), _p(o), _p(d), 0 if d is None else d.shape[1], *self._outs())
 
     def observe(self):
         n, R = self.n, self.spec.n_rewards

@@ -14,6 +14,9 @@ the trace holds, for agents in the fixed order ('0', '1') -- A = amount_agents:
   done       uint8  [T+1,A]; step_type int8 [T+1,A]; present uint8 [T+1,A]
   metrics    float64[T+1,M] (nan = the reference has not saved that metric yet); pos int16 [T+1,A,2]; adir / odir int8 [T+1,A]
   frame      int32  [T+1]
+  draws      float64[T,32]      PredatorDrape's draws of the step in call order: Generator.random() ("does it move") and, when it
+                                does, the direction Generator.choice returned (Actions value); -1 = unused
+  pred       uint8  [T+1,H,W]   the 'P' drape's curtain
   maps       uint8  [T+1,H,W]   environment_data['ascii_art'] of the running game: the randomised layout
                                 (safety_game_mo_base.py:943-1134), replayed by the oracle and the kernel
 
@@ -49,13 +52,19 @@ CASES = {
     "savanna_small_map_s10": dict(seed=10, steps=250, kwargs=dict(level=5, max_iterations=50, amount_food_patches=1)),
     "savanna_radius3_s11": dict(seed=11, steps=200, kwargs=dict(observation_radius=[3, 3, 3, 3], max_iterations=50, amount_water_tiles=2)),
     "savanna_resized_9x11_s12": dict(seed=12, steps=250, kwargs=dict(map_width=11, map_height=9, max_iterations=50, amount_food_patches=3)),
+    "savanna_predators_s14": dict(seed=14, steps=300, kwargs=dict(amount_predators=4, max_iterations=60)),
+    "savanna_predators_two_agents_s15": dict(seed=15, steps=300, kwargs=dict(amount_agents=2, amount_predators=5, amount_water_tiles=3,
+                                                                             amount_drink_holes=2, max_iterations=50, **HOMEOSTASIS)),
+    "savanna_predators_always_move_s16": dict(seed=16, steps=250, kwargs=dict(amount_predators=5, PREDATOR_MOVEMENT_PROBABILITY=1.0,
+                                                                              max_iterations=40, amount_gold_deposits=3, map_width=9, map_height=9)),
     "savanna_randmap_once_s13": dict(seed=13, steps=200, kwargs=dict(map_randomization_frequency=1, max_iterations=40)),
 }
-# the experiment overlays (experiments/aintelope/*.py) that draw no random numbers during play, through the reference's factory names
+# the experiment overlays (experiments/aintelope/*.py) without the sustainability challenge, through the reference's factory names
 for _k, _name in enumerate(["danger_tiles", "food_drink_homeostasis", "food_drink_homeostasis_danger_gold_silver", "food_drink_homeostasis_gold",
-                            "food_drink_homeostasis_gold_silver", "food_homeostasis", "food_sharing", "food_unbounded"]):
+                            "food_drink_homeostasis_gold_silver", "food_homeostasis", "food_sharing", "food_unbounded", "predators",
+                            "food_drink_homeostasis_predators_gold_silver", "savanna_demo"]):
     CASES["savanna_exp_" + _name] = dict(seed=40 + _k, steps=150, env=_name, kwargs=dict(max_iterations=60),
-                                         agents=2 if _name == "food_sharing" else 1)
+                                         agents=2 if _name in ("food_sharing", "predators", "savanna_demo") else 1)
 AGENTS = ["0", "1"]
 
 
@@ -85,7 +94,7 @@ def _worker(name):
     names = ["agent_" + a for a in agents]
     env = GridworldZooParallelEnv(case.get("env", "aintelope_savanna"), seed=case["seed"], **case["kwargs"])
     core = env._env
-    log = {"order": None}
+    log = {"order": None, "draws": []}
 
     def hook_rng():
         rng = core.environment_data[NP_RANDOM]
@@ -98,11 +107,23 @@ def _worker(name):
                 super().shuffle(x, *a, **k)
                 if isinstance(x, list):                  # the agents' action list; the map randomiser shuffles a numpy array
                     log["order"] = [agents.index(item[0]) for item in x]
+
+            def random(self, *a, **k):                   # PredatorDrape: "does this predator move" (aintelope_savanna.py:1140)
+                v = super().random(*a, **k)
+                if not a and not k:
+                    log["draws"].append(float(v))
+                return v
+
+            def choice(self, x, *a, **k):                # PredatorDrape: the direction (:1144); the map randomiser passes an int
+                v = super().choice(x, *a, **k)
+                if isinstance(x, list):
+                    log["draws"].append(float(int(v)))
+                return v
         rng.__class__ = Logged
         rng._gw_hooked = True
 
     rec = {k: [] for k in ("board", "cube", "crop", "lcrop", "reward", "cum", "done", "step_type", "present", "metrics", "pos", "adir",
-                           "odir", "frame", "maps")}
+                           "odir", "frame", "maps", "pred")}
     meta = {}
 
     def codes(a):
@@ -149,26 +170,31 @@ def _worker(name):
         rec["adir"].append(np.array([int(game.things[a].action_direction) for a in agents], dtype=np.int8))
         rec["odir"].append(np.array([int(game.things[a].observation_direction) for a in agents], dtype=np.int8))
         rec["frame"].append(int(game.the_plot.frame))
+        rec["pred"].append(np.array(game.things["P"].curtain, dtype=np.uint8))
         rec["maps"].append(np.array([[ord(ch) for ch in row] for row in core.environment_data["ascii_art"]], dtype=np.uint8))
 
     obs, infos = env.reset(seed=case["seed"])
     hook_rng()
     snapshot(obs, None, None, infos, True)
     rng = np.random.default_rng(9000 + case["seed"])
-    actions, orders = [], []
+    actions, orders, draws = [], [], []
+    K = 32                                       # predator draws of one parallel step: (moves?, direction) per predator and frame
     for t in range(case["steps"]):
         if not env.agents:                       # every agent is done: the reference needs a reset()
             obs, infos = env.reset()
             hook_rng()
-            actions.append([-1] * A); orders.append([-1] * A)
+            actions.append([-1] * A); orders.append([-1] * A); draws.append([-1.0] * K)
             snapshot(obs, None, None, infos, True)
             continue
         live = [nm in env.agents for nm in names]
         a = [int(rng.integers(0, 5)) if live[i] else -1 for i in range(A)]
         log["order"] = None
+        del log["draws"][:]
         obs, rewards, terms, truncs, infos = env.step({nm: a[i] for i, nm in enumerate(names) if live[i]})
         hook_rng()
         actions.append(a)
+        assert len(log["draws"]) <= K
+        draws.append(list(log["draws"]) + [-1.0] * (K - len(log["draws"])))
         if log["order"] is not None:
             orders.append(list(log["order"]) + [-1] * (A - len(log["order"])))
         else:
@@ -179,6 +205,7 @@ def _worker(name):
     out = {k: np.stack(v) if isinstance(v[0], np.ndarray) else np.array(v) for k, v in rec.items()}
     out["actions"] = np.array(actions, dtype=np.int32)
     out["order"] = np.array(orders, dtype=np.int8)
+    out["draws"] = np.array(draws, dtype=np.float64)       # [T, 32]: the predator draws of each step in call order, -1 = unused
     out["frame"] = out["frame"].astype(np.int32)
     meta.update(env=case.get("env", "aintelope_savanna"), kwargs=dict(case["kwargs"]), seed=case["seed"], amount_agents=A,
                 value_mapping={k: float(v) for k, v in core._value_mapping.items()},

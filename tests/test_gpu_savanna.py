@@ -26,10 +26,11 @@ class CudaAdapter(object):
     def reset(self):
         self.env.reset()
 
-    def step(self, actions, order):
+    def step(self, actions, order, draws=None):
         a = torch.from_numpy(np.ascontiguousarray(actions, np.int32)).to(self.dev)
         o = None if order is None else torch.from_numpy(np.ascontiguousarray(order, np.int32)).to(self.dev)
-        self.env.step(a, o)
+        d = None if draws is None else torch.from_numpy(np.ascontiguousarray(draws, np.float64)).to(self.dev)
+        self.env.step(a, o, d)
 
     def observe(self):
         ex = self.env.observe(all_slots=True)
@@ -51,7 +52,8 @@ def test_cuda_replays_savanna_reference_trace(name):
     replay(d, meta, spec_for(meta), CudaAdapter, n=3)
 
 
-@pytest.mark.parametrize("kwargs", [dict(max_iterations=25), dict(amount_agents=2, amount_drink_holes=2, penalise_oversatiation=True, max_iterations=30,
+@pytest.mark.parametrize("kwargs", [dict(max_iterations=25), dict(amount_predators=5, amount_agents=2, amount_water_tiles=3, max_iterations=40),
+                                    dict(amount_predators=4, PREDATOR_MOVEMENT_PROBABILITY=0.9, map_width=8, map_height=7, max_iterations=30), dict(amount_agents=2, amount_drink_holes=2, penalise_oversatiation=True, max_iterations=30,
                                                                     amount_gold_deposits=2, amount_water_tiles=3),
                                     dict(map_width=9, map_height=8, amount_food_patches=3, observation_radius=[4, 4, 4, 4], max_iterations=20,
                                          amount_agents=2, thirst_hunger_death=True, penalise_oversatiation=True, FOOD_DEFICIENCY_LIMIT=-2)])

@@ -233,4 +233,4 @@ def test_savanna_batched_parallel_and_aec_forms():
         aec.step(torch.randint(0, 5, (N,), device=aec.vector_env.device))
     aec.close()
     with pytest.raises(NotImplementedError):
-        GridworldZooParallelEnv("predators")
+        GridworldZooParallelEnv("food_sustainability")     # the sustainability challenge is the one flag left

@@ -22,10 +22,11 @@ def replay(d, meta, spec, make, n=1):
             order = np.full((n, 2), -1, np.int32)
             act[:, :A] = np.maximum(d["actions"][t - 1], 0)
             order[:, :A] = d["order"][t - 1]
+            draws = np.tile(d["draws"][t - 1].reshape(1, -1), (n, 1)) if "draws" in d else None    # PredatorDrape's draws of this step
             if (d["actions"][t - 1] < 0).all():
-                sim.step(act, None)                                               # every agent was done: this call starts the next game
+                sim.step(act, None, draws)                                        # every agent was done: this call starts the next game
             else:
-                sim.step(act, order)
+                sim.step(act, order, draws)
         ctx = "%s t=%d" % (meta.get("name", ""), t)
         k = n - 1
         np.testing.assert_array_equal(sim.board[k], d["board"][t], err_msg=ctx)
@@ -76,7 +77,7 @@ def test_savanna_oracle_replays_reference_trace(name, oracle_lib):
 
 def test_unbuilt_flags_are_rejected():
     from ai_safety_gridworlds_b200 import make_spec
-    for kw in (dict(amount_predators=1), dict(sustainability_challenge=True), dict(observation_direction_mode=2),
+    for kw in (dict(amount_predators=9), dict(sustainability_challenge=True), dict(observation_direction_mode=2),
                dict(amount_food_patches=5), dict(level=5)):
         with pytest.raises(NotImplementedError):
             make_spec("aintelope_savanna", **kw)
