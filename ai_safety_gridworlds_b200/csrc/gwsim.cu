@@ -2625,7 +2625,8 @@ int gw_sav_create(const GwSavConfig* cfg, int64_t n_envs, int device, int64_t en
   h->d_cfg = nullptr; h->d_stats = nullptr; h->maps = nullptr; h->map_mode = GW_IMA_MAPS_STATIC; h->launches = 0;
   int sms = 0, per_sm = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gw_sav_kernel, SAV_WARPS * 32, 0);
+  if (cfg->amount[GW_SAV_T_PREDATOR] > 0) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gw_sav_kernel<true>, SAV_WARPS * 32, 0);
+  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gw_sav_kernel<false>, SAV_WARPS * 32, 0);
   h->grid_max = (sms > 0 ? sms : 148) * (per_sm > 0 ? per_sm : 1);
   cudaError_t e = cudaMalloc(&h->d_cfg, sizeof(SavCfg));
   if (e == cudaSuccess) e = cudaMalloc(&h->d_stats, (size_t)GW_STAT_REPLICAS * GW_MA_STATS_LEN * sizeof(unsigned long long));
@@ -2666,7 +2667,8 @@ static int sav_launch(GwSavHandle h, SavArgs& a, void* state, const GwSavObs* ob
   CUDA_TRY(cudaSetDevice(h->device));
   int64_t grid = (h->n + SAV_WARPS - 1) / SAV_WARPS;
   if (grid > h->grid_max) grid = h->grid_max;
-  gw_sav_kernel<<<(unsigned)grid, SAV_WARPS * 32, 0, stream>>>(a);
+  if (h->cfg.amount[GW_SAV_T_PREDATOR] > 0) gw_sav_kernel<true><<<(unsigned)grid, SAV_WARPS * 32, 0, stream>>>(a);
+  else gw_sav_kernel<false><<<(unsigned)grid, SAV_WARPS * 32, 0, stream>>>(a);
   CUDA_TRY(cudaGetLastError());
   h->launches += 1;
   return GW_OK;

@@ -174,6 +174,7 @@ __device__ __forceinline__ void sav_predators(const SavCfg& c, const SavArgs& a,
   }
 }
 
+template <bool PRED>
 __device__ __forceinline__ void sav_play(const SavCfg& c, const SavArgs& args, int64_t env, SavState& s, SavRun& w,
                                          const uint8_t* __restrict__ art, int a, int action) {
   const double* F = c.fparams;
@@ -223,14 +224,14 @@ __device__ __forceinline__ void sav_play(const SavCfg& c, const SavArgs& args, i
       sav_add(c, w, a, ev, log((double)(prev + 2)) / lb - log((double)(prev + 1)) / lb);       /* math.log(x, base) increments */
     } else sav_add(c, w, a, ev, 1.0);
   }
-  if (!sav_is_drape(pos_chr) && pos_chr != '#' && pos_chr != 'U' && !sav_pred_here(s, w.pos[a])) { s.visits[a][0] += 1; sav_add(c, w, a, GW_SAV_E_GAP, 1.0); }
+  if (!sav_is_drape(pos_chr) && pos_chr != '#' && pos_chr != 'U' && !(PRED && sav_pred_here(s, w.pos[a]))) { s.visits[a][0] += 1; sav_add(c, w, a, GW_SAV_E_GAP, 1.0); }
   if (s.dsat[a] < F[GW_SAV_F_DRINK_DEFICIENCY_THRESHOLD]) sav_add(c, w, a, GW_SAV_E_DRINK_DEFICIENCY, c.proportional ? -s.dsat[a] : 1.0);
   else if (c.penalise && s.dsat[a] > F[GW_SAV_F_DRINK_OVERSATIATION_THRESHOLD]) sav_add(c, w, a, GW_SAV_E_DRINK_OVERSATIATION, c.proportional ? s.dsat[a] : 1.0);
   if (s.fsat[a] < F[GW_SAV_F_FOOD_DEFICIENCY_THRESHOLD]) sav_add(c, w, a, GW_SAV_E_FOOD_DEFICIENCY, c.proportional ? -s.fsat[a] : 1.0);
   else if (c.penalise && s.fsat[a] > F[GW_SAV_F_FOOD_OVERSATIATION_THRESHOLD]) sav_add(c, w, a, GW_SAV_E_FOOD_OVERSATIATION, c.proportional ? s.fsat[a] : 1.0);
   /* WaterDrape: the acting player only, no termination */
   if (art[w.pos[a]] == 'W') sav_add(c, w, a, GW_SAV_E_DANGER_TILE, 1.0);
-  if (c.amount[GW_SAV_T_PREDATOR] > 0) sav_predators(c, args, env, s, w, art, a);
+  if (PRED) sav_predators(c, args, env, s, w, art, a);
 }
 
 /* A fresh layout: the interior of cfg.art in Fisher-Yates order on the Philox stream (the oracle's shuffle_layout) */
@@ -276,6 +277,9 @@ __device__ __forceinline__ void sav_new_game(const SavCfg& c, const SavArgs& a, 
   }
 }
 
+/* PRED = the game has predators: the instantiation without them carries neither PredatorDrape nor the third layer code (the
+ * kernel is sensitive to its instruction footprint: the predator code cost the default flags 10 % before the split) */
+template <bool PRED>
 __global__ void __launch_bounds__(SAV_WARPS * 32, 8) gw_sav_kernel(const __grid_constant__ SavArgs a) {
   __shared__ __align__(16) SavCfg c;
   __shared__ __align__(16) SavState s_state[SAV_WARPS];
@@ -306,7 +310,7 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, 8) gw_sav_kernel(const __grid_
   uint8_t* art = s_art[warp];
   const int cells = c.cells, L = c.n_layers, V = c.view, V2 = V * V, R = c.n_rewards, A = c.n_agents;
   for (int64_t env = (int64_t)blockIdx.x * SAV_WARPS + warp; env < a.n; env += (int64_t)gridDim.x * SAV_WARPS) {
-    /* 1. state and map into shared memory */
+    /* 1. state and map into shared memory (a register prefetch of the next environment was tried: it spilled the renderer) */
     if (lane < GW_SAV_STATE_BYTES / 16) reinterpret_cast<uint4*>(&s)[lane] = ld_state(a.state + env * (GW_SAV_STATE_BYTES / 16) + lane);
     for (int p = (int)lane; p < cells; p += 32) art[p] = a.maps[env * cells + p];
     __syncwarp();
@@ -343,7 +347,7 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, 8) gw_sav_kernel(const __grid_
         for (int k = 0; k < 2; ++k) {
           const int ag = k == 0 ? ord0 : ord1;
           if (ag < 0 || ag >= A || w.st[ag] >= 2) continue;
-          sav_play(c, a, env, s, w, art, ag, a.actions[2 * env + ag]);
+          sav_play<PRED>(c, a, env, s, w, art, ag, a.actions[2 * env + ag]);
           if ((int32_t)s.frame >= c.max_iterations) over = true;
         }
         for (int k = 0; k < 2; ++k) {
@@ -398,13 +402,14 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, 8) gw_sav_kernel(const __grid_
     uint8_t* sec = s_sec[warp];
     uint8_t* bchr = s_bchr[warp];
     uint8_t* ter = s_ter[warp];
+    constexpr bool has_pred = PRED;
     for (int p = (int)lane; p < cpitch; p += 32) {
       uint8_t pr = 255, se = 255, te = 255, ch = 0;
       if (p < cells) {
         uint8_t m = art[p];
         if (m == 'P' || m == '0' || m == '1') m = ' ';             /* start tiles: sprites and the predator drape are state */
         const int ly = c.layer_of[m & 127];
-        const bool a0 = p == pos0, a1 = p == pos1, pd = sav_pred_here(s, p);
+        const bool a0 = p == pos0, a1 = p == pos1, pd = has_pred && sav_pred_here(s, p);
         pr = (uint8_t)((ly == c.gap_layer && (a0 || a1 || pd)) ? 255 : ly);
         se = a0 ? (uint8_t)c.agent_layer[0] : a1 ? (uint8_t)c.agent_layer[1] : (uint8_t)255;
         te = pd ? (uint8_t)c.pred_layer : (uint8_t)255;
@@ -414,7 +419,6 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, 8) gw_sav_kernel(const __grid_
       prim[p] = pr; sec[p] = se; ter[p] = te; bchr[p] = ch;
     }
     __syncwarp();
-    const bool has_pred = c.amount[GW_SAV_T_PREDATOR] > 0;
     auto plane16 = [&](const uint8_t* pr, const uint8_t* se, const uint8_t* te, int l, int chunk) -> uint4 {
       const uint4 a4 = *reinterpret_cast<const uint4*>(pr + 16 * chunk), b4 = *reinterpret_cast<const uint4*>(se + 16 * chunk);
       const uint32_t lv = (uint32_t)l * 0x01010101u;
@@ -458,10 +462,11 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, 8) gw_sav_kernel(const __grid_
             else if (dir == GW_DIR_LEFT) { si = V - 1 - j; sj = i; }
             else if (dir == GW_DIR_RIGHT) { si = j; sj = V - 1 - i; }
             const int r = r0 + si, cc = c0 + sj;
-            if (r >= 0 && r < c.height && cc >= 0 && cc < c.width) { const int p = r * c.width + cc; pr = prim[p]; se = sec[p]; te = ter[p]; ch = bchr[p]; }
+            if (r >= 0 && r < c.height && cc >= 0 && cc < c.width) { const int p = r * c.width + cc; pr = prim[p]; se = sec[p]; ch = bchr[p]; if (has_pred) te = ter[p]; }
             else { pr = (uint8_t)c.wall_layer; ch = (uint8_t)'#'; }
           }
-          vprim[ij] = pr; vsec[ij] = se; vter[ij] = te; vchr[ij] = ch;
+          vprim[ij] = pr; vsec[ij] = se; vchr[ij] = ch;
+          if (has_pred) vter[ij] = te;
         }
         __syncwarp();
         if (a.crop) {
