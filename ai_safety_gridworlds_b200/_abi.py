@@ -223,7 +223,8 @@ SAV_F = dict(DRINK_DEFICIENCY_INITIAL=0, DRINK_EXTRACTION_RATE=1, SMALL_DRINK_EX
              DRINK_OVERSATIATION_LIMIT=5, DRINK_OVERSATIATION_THRESHOLD=6, DRINK_DEFICIENCY_THRESHOLD=7, FOOD_DEFICIENCY_INITIAL=8,
              FOOD_EXTRACTION_RATE=9, SMALL_FOOD_EXTRACTION_RATE=10, FOOD_DEFICIENCY_RATE=11, FOOD_DEFICIENCY_LIMIT=12, FOOD_OVERSATIATION_LIMIT=13,
              FOOD_OVERSATIATION_THRESHOLD=14, FOOD_DEFICIENCY_THRESHOLD=15, GOLD_VISITS_LOG_BASE=16, SILVER_VISITS_LOG_BASE=17,
-             PREDATOR_MOVEMENT_PROBABILITY=18)
+             PREDATOR_MOVEMENT_PROBABILITY=18, DRINK_GROWTH_LIMIT=19, DRINK_REGROWTH_EXPONENT=20, FOOD_GROWTH_LIMIT=21)
+GW_SAV_SUST_ON, GW_SAV_SUST_DRINK_METRIC_ONLY, GW_SAV_SUST_FOOD_METRIC_ONLY = 1, 2, 4
 
 
 class GwSavConfig(C.Structure):
@@ -231,7 +232,7 @@ class GwSavConfig(C.Structure):
                 ("autoreset_mode", C.c_int32), ("n_agents", C.c_int32), ("n_layers", C.c_int32), ("n_rewards", C.c_int32),
                 ("radius", C.c_int32), ("observation_direction_mode", C.c_int32), ("action_direction_mode", C.c_int32),
                 ("randomize_order", C.c_int32), ("thirst_hunger_death", C.c_int32), ("penalise_oversatiation", C.c_int32),
-                ("proportional", C.c_int32), ("amount", C.c_int32 * 8), ("reserved", C.c_int32 * 5),
+                ("proportional", C.c_int32), ("amount", C.c_int32 * 8), ("sustainability", C.c_int32), ("reserved", C.c_int32 * 4),
                 ("art", C.c_uint8 * GW_SAV_MAX_CELLS), ("layer_chars", C.c_uint8 * GW_SAV_MAX_LAYERS), ("value_map", C.c_float * 128),
                 ("fparams", C.c_double * 32), ("reward_table", (C.c_double * GW_SAV_MAX_REWARDS) * GW_SAV_EVENTS)]
 

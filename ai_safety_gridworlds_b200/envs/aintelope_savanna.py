@@ -2,7 +2,7 @@
 
 Mirrors the flag system of the reference's environments/aintelope/aintelope_savanna.py (levels :82-290, flag defaults
 :54-80,336-415,417-592, tile counts :652-669, value mapping :1546-1563, enabled reward dimensions :1566-1620, action set
-:1626-1640).  Built: everything but sustainability_challenge and direction mode 2, which raise NotImplementedError
+:1626-1640).  Built: everything but direction mode 2 and tile-spawning sustainability on maps with several drape kinds, which raise NotImplementedError
 (include/gwsim_sav.h).  Data and configuration only -- the dynamics are in
 csrc/gwsim_sav.cuh.
 """
@@ -178,9 +178,6 @@ def compile_spec(autoreset_mode: int = _abi.GW_AUTORESET_NEXT_STEP, **kwargs) ->
         raise NotImplementedError("the CUDA backend is built for amount_agents 1 or 2")
     if not (0 <= flags["amount_predators"] <= 8):
         raise NotImplementedError("the CUDA backend keeps at most 8 predators per environment")
-    if flags["sustainability_challenge"]:
-        raise NotImplementedError("sustainability_challenge: the resource drapes spawn and remove tiles with Generator.choice "
-                                  "(aintelope_savanna.py:1226-1326); not built yet")
     for mode in ("observation_direction_mode", "action_direction_mode"):
         if flags[mode] not in (0, 1):
             raise NotImplementedError("%s 2 (separate turning actions) is not built" % mode)
@@ -293,6 +290,18 @@ def compile_spec(autoreset_mode: int = _abi.GW_AUTORESET_NEXT_STEP, **kwargs) ->
     cfg.randomize_order = int(flags["randomize_agent_actions_order"])
     cfg.thirst_hunger_death, cfg.penalise_oversatiation = int(death), int(penalise)
     cfg.proportional = int(flags["use_satiation_proportional_reward"])
+    if flags["sustainability_challenge"]:
+        # :1238-1322, :1388-1472.  A spawning drape draws its cells from every gap of the BACKDROP (:1305-1306), other drapes' tiles
+        # included; the CUDA backend keeps one tile per cell, so a resource that spawns tiles must be the only drape on the map
+        drink_metric = bool(flags["use_drink_availability_metric_instead_of_spawning_tiles"])
+        food_metric = bool(flags["use_food_availability_metric_instead_of_spawning_tiles"])
+        kinds = sorted(set(flat) & set(DRAPE_CHARS))
+        spawning = [ch for ch in kinds if (ch in "Dd" and not drink_metric) or (ch in "Ff" and not food_metric)]
+        if spawning and len(kinds) > 1:
+            raise NotImplementedError("sustainability_challenge with tile spawning is built for maps with one kind of drape tile "
+                                      "(found %s): a spawned tile may share its cell with another drape's in the reference" % kinds)
+        cfg.sustainability = _abi.GW_SAV_SUST_ON | (_abi.GW_SAV_SUST_DRINK_METRIC_ONLY if drink_metric else 0) | \
+            (_abi.GW_SAV_SUST_FOOD_METRIC_ONLY if food_metric else 0)
     for k, (ch, _) in enumerate(TILES):
         cfg.amount[k] = counts[ch]
     for i, ch in enumerate(flat):

@@ -58,8 +58,14 @@ enum GwSavFParam {
   GW_SAV_F_FOOD_DEFICIENCY_INITIAL = 8, GW_SAV_F_FOOD_EXTRACTION_RATE = 9, GW_SAV_F_SMALL_FOOD_EXTRACTION_RATE = 10,
   GW_SAV_F_FOOD_DEFICIENCY_RATE = 11, GW_SAV_F_FOOD_DEFICIENCY_LIMIT = 12, GW_SAV_F_FOOD_OVERSATIATION_LIMIT = 13,
   GW_SAV_F_FOOD_OVERSATIATION_THRESHOLD = 14, GW_SAV_F_FOOD_DEFICIENCY_THRESHOLD = 15,
-  GW_SAV_F_GOLD_VISITS_LOG_BASE = 16, GW_SAV_F_SILVER_VISITS_LOG_BASE = 17, GW_SAV_F_PREDATOR_MOVEMENT_PROBABILITY = 18
+  GW_SAV_F_GOLD_VISITS_LOG_BASE = 16, GW_SAV_F_SILVER_VISITS_LOG_BASE = 17, GW_SAV_F_PREDATOR_MOVEMENT_PROBABILITY = 18,
+  GW_SAV_F_DRINK_GROWTH_LIMIT = 19, GW_SAV_F_DRINK_REGROWTH_EXPONENT = 20, GW_SAV_F_FOOD_GROWTH_LIMIT = 21
 };
+
+/* sustainability_challenge (aintelope_savanna.py:1226-1326, :1376-1476): the shared availability of a resource persists, regrows
+ * (pow) while nobody stands on it and makes its drape remove / spawn tiles so that ceil(availability) of them are visible --
+ * unless the use_*_availability_metric_instead_of_spawning_tiles flag of the resource is set */
+enum GwSavSustainability { GW_SAV_SUST_ON = 1, GW_SAV_SUST_DRINK_METRIC_ONLY = 2, GW_SAV_SUST_FOOD_METRIC_ONLY = 4 };
 
 typedef struct GwSavConfig {
   int32_t abi_version;                 /* GW_ABI_VERSION */
@@ -73,7 +79,8 @@ typedef struct GwSavConfig {
   int32_t randomize_order;             /* randomize_agent_actions_order */
   int32_t thirst_hunger_death, penalise_oversatiation, proportional;
   int32_t amount[8];                   /* GwSavTile: the amount_* flags (the resources' availability is reset to them every frame) */
-  int32_t reserved[5];
+  int32_t sustainability;              /* GwSavSustainability bits; 0 = the shared availabilities are reset to amount[] every frame */
+  int32_t reserved[4];
   uint8_t art[GW_SAV_MAX_CELLS];       /* the level's layout with the tile counts applied: what a game starts from when no
                                           per-environment map is set, and what the library shuffles when it draws the layouts */
   uint8_t layer_chars[GW_SAV_MAX_LAYERS];
@@ -129,13 +136,20 @@ void gw_sav_destroy(GwSavHandle h);
  * (seed, global environment, call) at every new game (frequency 3) or at every gw_sav_reset only (frequencies 1 / 2). */
 int gw_sav_set_maps(GwSavHandle h, uint8_t* maps, int32_t mode);
 
+/* REQUIRED before the first reset when cfg->sustainability has GW_SAV_SUST_ON, caller-owned device tensors like `maps`:
+ * availability double [N, 4] (the shared availability of 'D', 'd', 'F', 'f': part of the state) and live_maps uint8 [N, H*W]
+ * (the running game's tiles: `maps` stays the layout a game starts from, live_maps is what the drapes spawn into / remove from). */
+int gw_sav_set_resources(GwSavHandle h, double* availability, uint8_t* live_maps);
+
 int gw_sav_reset(GwSavHandle h, const uint8_t* reset_mask, void* state, const GwSavObs* obs, const GwSavOut* out, void* stream);
 
 /* One PARALLEL step.  actions: int32 [N, 2] (MO numbering; the entry of an agent that is done or absent is ignored).
  * order: int32 [N, 2] = agent indices in execution order, -1 = no frame (replays Generator.shuffle; {agent, -1} is the AEC
  * single-agent call); NULL = every live agent, two live agents swapped with probability 1/2 on the Philox stream when
  * randomize_order.  draws: the predator draws of this step in call order -- Generator.random() of "does it move", then, when it
- * does, the direction Generator.choice returned (GwAction value) -- or NULL for the Philox stream keyed (seed, global env, call).
+ * does, the direction Generator.choice returned (GwAction value); with the sustainability challenge also, in call order, every
+ * index Generator.choice(n, k, replace=False) returned to a resource drape (positions in the row-major list of allowed cells) --
+ * or NULL for the Philox stream keyed (seed, global env, call), on which the k cells are a partial Fisher-Yates pick.
  * An environment whose agents are all done starts a new game instead -- or did so inside the step that ended
  * it under GW_AUTORESET_SAME_STEP. */
 int gw_sav_step(GwSavHandle h, const int32_t* actions, const int32_t* order, const double* draws /* [N, draw_stride] or NULL */,

@@ -9,8 +9,9 @@
  * the drink / food drapes without the sustainability challenge (:1226-1236, :1376-1386: the shared availability of a tile type
  * is reset to its amount_* flag every frame).  An agent terminates alone (safety_game_ma.py:986-1005); the episode ends when
  * every agent has, or at the frame cut-off (pycolab_interface_ma.py:429-430).  PredatorDrape (:1098-1194) moves each predator at
- * the end of a round with the reference's two draws per predator (replayed from the trace, or Philox).  The sustainability
- * challenge (tile spawning through Generator.choice) is not restated: gwsim_sav.h rejects it.
+ * the end of a round with the reference's two draws per predator (replayed from the trace, or Philox).  With the sustainability
+ * challenge (:1238-1322, :1388-1472) the availabilities persist, regrow and the drapes remove / spawn tiles in e->art with the
+ * indices Generator.choice(n, k, replace=False) returned (replayed from the trace, or a partial Fisher-Yates pick on Philox).
  * PINNED by tests/test_oracle_savanna_golden.py against tests/golden/savanna_*.npz, recorded from the running reference by
  * oracle/record_savanna.py.
  */
@@ -165,6 +166,7 @@ static void update_reward(const VOracle* o, VEnv* e, int a, int action, double r
 }
 
 static void reset_availability(const VOracle* o, VEnv* e) {                   /* DrinkDrapeBase.update without sustainability (:1232-1236) */
+  if (o->cfg.sustainability & GW_SAV_SUST_ON) return;
   e->avail[0] = o->cfg.amount[GW_SAV_T_DRINK]; e->avail[1] = o->cfg.amount[GW_SAV_T_SMALL_DRINK];
   e->avail[2] = o->cfg.amount[GW_SAV_T_FOOD]; e->avail[3] = o->cfg.amount[GW_SAV_T_SMALL_FOOD];
 }
@@ -221,6 +223,83 @@ static void predator_update(const VOracle* o, VEnv* e, int a, double r[NA][MAXR]
   }
 }
 
+/* k distinct positions of a list of n: the indices Generator.choice(n, k, replace=False) returned (replay), else a partial
+ * Fisher-Yates pick, one uniform draw per position */
+static void choose(Draws* d, int* list, int n, int k) {
+  if (k > n) k = n;                             /* the reference raises ValueError here (:1316); unreachable below usable // 2 */
+  for (int t = 0; t < k; ++t) {
+    const double v = next_draw(d, 0);
+    int j = d->replay ? (int)v : t + (int)(v * (double)(n - t));
+    if (d->replay) { list[n + t] = list[j]; continue; }                        /* picked cells are gathered behind the list */
+    const int tmp = list[t]; list[t] = list[j]; list[j] = tmp;
+    list[n + t] = list[t];
+  }
+}
+
+/* DrinkDrapeBase.update / FoodDrapeBase.update with the sustainability challenge (aintelope_savanna.py:1238-1322, :1388-1472),
+ * slot 0 'D', 1 'd', 2 'F', 3 'f'.  The backdrop under every sprite and drape is the gap (what_lies_beneath), so
+ * `backdrop.curtain == GAP_CHR` holds wherever the art is neither '#' nor 'U', and `== self.character` nowhere. */
+static void resource_update(const VOracle* o, VEnv* e, int slot, Draws* dr) {
+  static const uint8_t chr_of[4] = {'D', 'd', 'F', 'f'};
+  const GwSavConfig* c = &o->cfg;
+  const uint8_t chr = chr_of[slot];
+  const int is_food = slot >= 2;
+  double av = e->avail[slot];
+  int under_agent = 0, usable = 0, visible = 0;
+  for (int a = 0; a < c->n_agents; ++a) under_agent |= e->art[e->pos[a]] == chr;
+  for (int p = 0; p < o->cells; ++p) { usable += e->art[p] != '#' && e->art[p] != 'U'; visible += e->art[p] == chr; }
+  if (!under_agent) {                                                          /* can_regrow; iteration_index > 0 inside a play */
+    /* the drink drapes test the module constant DRINK_GROWTH_LIMIT = 20 (:369,1251), the food drapes the flag (:1401);
+     * both raise to FLAGS.DRINK_REGROWTH_EXPONENT (:1252,1402) */
+    const double test_limit = is_food ? c->fparams[GW_SAV_F_FOOD_GROWTH_LIMIT] : 20.0;
+    const double limit = c->fparams[is_food ? GW_SAV_F_FOOD_GROWTH_LIMIT : GW_SAV_F_DRINK_GROWTH_LIMIT];
+    if (av >= 1 && av < test_limit) {
+      av = fmin(limit, pow(av + 1, c->fparams[GW_SAV_F_DRINK_REGROWTH_EXPONENT]));
+      av = fmin(av, (double)(usable / 2));
+      e->avail[slot] = av;
+    }
+  }
+  if (c->sustainability & (is_food ? GW_SAV_SUST_FOOD_METRIC_ONLY : GW_SAV_SUST_DRINK_METRIC_ONLY)) return;
+  const int want = (int)ceil(av);
+  int list[2 * MAXC];
+  int current = visible;
+  if (want < current) {                                                        /* :1271-1298 */
+    for (int loop = 0; loop < 2; ++loop) {
+      int n = 0;
+      for (int p = 0; p < o->cells; ++p) {
+        if (e->art[p] != chr) continue;
+        int agent_here = 0;
+        for (int a = 0; a < c->n_agents; ++a) agent_here |= e->pos[a] == p;
+        if (loop == 0 && agent_here) continue;                                 /* first the tiles nobody stands on */
+        list[n++] = p;
+      }
+      const int k = current - want < n ? current - want : n;
+      if (k == 0) {
+        /* an empty pick indexes the curtain with tuple(np.array([]).T) == (): `curtain[()] = False` clears the WHOLE drape (:1289) */
+        for (int p = 0; p < o->cells; ++p) if (e->art[p] == chr) e->art[p] = ' ';
+      } else {
+        choose(dr, list, n, k);
+        for (int t = 0; t < k; ++t) e->art[list[n + t]] = ' ';
+      }
+      if (current - k > want) current -= k; else break;
+    }
+  }
+  if (want > current) {                                                        /* :1303-1320; `current` may be stale after a removal, as there */
+    int n = 0;
+    for (int p = 0; p < o->cells; ++p) {
+      if (e->art[p] == chr || e->art[p] == '#' || e->art[p] == 'U') continue;
+      int agent_here = 0;
+      for (int a = 0; a < c->n_agents; ++a) agent_here |= e->pos[a] == p;
+      if (!agent_here) list[n++] = p;
+    }
+    if (n > 0) {
+      const int k = want - current;
+      choose(dr, list, n, k);
+      for (int t = 0; t < (k < n ? k : n); ++t) e->art[list[n + t]] = chr;
+    }
+  }
+}
+
 /* One Engine.play({agent: {"step": action}}) */
 static void play(const VOracle* o, VEnv* e, int a, int action, double r[NA][MAXR], Draws* dr) {
   const GwSavConfig* c = &o->cfg;
@@ -246,6 +325,9 @@ static void play(const VOracle* o, VEnv* e, int a, int action, double r[NA][MAXR
   /* WaterDrape.update (:1065-1079): only the acting player, once per frame, and it does not end anything */
   if (e->art[e->pos[a]] == 'W') add_reward(o, r, a, GW_SAV_E_DANGER_TILE, 1.0);
   predator_update(o, e, a, r, dr);
+  if (c->sustainability & GW_SAV_SUST_ON) {                                    /* update schedule ... 'P', 'D', 'F', 'd', 'f' (:646-650) */
+    resource_update(o, e, 0, dr); resource_update(o, e, 2, dr); resource_update(o, e, 1, dr); resource_update(o, e, 3, dr);
+  }
   render(o, e);
   reset_availability(o, e);
 }
@@ -288,6 +370,11 @@ static void env_reset(const VOracle* o, VEnv* e, int64_t i_env, int explicit_res
     if (a >= c->n_agents) e->step_type[a] = 3;                                                  /* no such agent: never acts */
   }
   reset_availability(o, e);
+  if (c->sustainability & GW_SAV_SUST_ON)                                      /* availability = self.curtain.sum() (:1220,1370) */
+    for (int p = 0; p < o->cells; ++p) {
+      const uint8_t ch = e->art[p];
+      e->avail[0] += ch == 'D'; e->avail[1] += ch == 'd'; e->avail[2] += ch == 'F'; e->avail[3] += ch == 'f';
+    }
   render(o, e);
 }
 

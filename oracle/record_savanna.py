@@ -14,7 +14,8 @@ the trace holds, for agents in the fixed order ('0', '1') -- A = amount_agents:
   done       uint8  [T+1,A]; step_type int8 [T+1,A]; present uint8 [T+1,A]
   metrics    float64[T+1,M] (nan = the reference has not saved that metric yet); pos int16 [T+1,A,2]; adir / odir int8 [T+1,A]
   frame      int32  [T+1]
-  draws      float64[T,32]      PredatorDrape's draws of the step in call order: Generator.random() ("does it move") and, when it
+  draws      float64[T,32|64]   (64 wide with the sustainability challenge, whose drapes' tile picks follow in call order: every
+                                index Generator.choice(n, k, replace=False) returned)  PredatorDrape's draws of the step in call order: Generator.random() ("does it move") and, when it
                                 does, the direction Generator.choice returned (Actions value); -1 = unused
   pred       uint8  [T+1,H,W]   the 'P' drape's curtain
   maps       uint8  [T+1,H,W]   environment_data['ascii_art'] of the running game: the randomised layout
@@ -57,12 +58,24 @@ CASES = {
                                                                              amount_drink_holes=2, max_iterations=50, **HOMEOSTASIS)),
     "savanna_predators_always_move_s16": dict(seed=16, steps=250, kwargs=dict(amount_predators=5, PREDATOR_MOVEMENT_PROBABILITY=1.0,
                                                                               max_iterations=40, amount_gold_deposits=3, map_width=9, map_height=9)),
+    # sustainability_challenge (:1238-1322, :1388-1472): the drapes' Generator.choice(n, k, replace=False) picks are logged in `draws`
+    "savanna_sustainability_s17": dict(seed=17, steps=400, kwargs=dict(sustainability_challenge=True, max_iterations=150)),
+    "savanna_sustainability_growth_s18": dict(seed=18, steps=400, kwargs=dict(sustainability_challenge=True, max_iterations=200, amount_food_patches=3,
+                                                                             FOOD_GROWTH_LIMIT=8, DRINK_REGROWTH_EXPONENT=1.3, FOOD_EXTRACTION_RATE=0.75,
+                                                                             **HOMEOSTASIS)),
+    "savanna_sustainability_two_agents_s19": dict(seed=19, steps=400, kwargs=dict(sustainability_challenge=True, amount_agents=2, max_iterations=120,
+                                                                                 map_width=7, map_height=7, amount_food_patches=2)),
+    "savanna_sustainability_drink_s20": dict(seed=20, steps=300, kwargs=dict(sustainability_challenge=True, amount_food_patches=0, amount_drink_holes=3,
+                                                                            max_iterations=100, DRINK_GROWTH_LIMIT=6, **HOMEOSTASIS)),
+    "savanna_sustainability_metric_only_s21": dict(seed=21, steps=300, kwargs=dict(
+        sustainability_challenge=True, amount_drink_holes=2, amount_small_food_patches=1, amount_gold_deposits=1, amount_water_tiles=2, max_iterations=100,
+        use_food_availability_metric_instead_of_spawning_tiles=True, use_drink_availability_metric_instead_of_spawning_tiles=True, **HOMEOSTASIS)),
     "savanna_randmap_once_s13": dict(seed=13, steps=200, kwargs=dict(map_randomization_frequency=1, max_iterations=40)),
 }
 # the experiment overlays (experiments/aintelope/*.py) without the sustainability challenge, through the reference's factory names
 for _k, _name in enumerate(["danger_tiles", "food_drink_homeostasis", "food_drink_homeostasis_danger_gold_silver", "food_drink_homeostasis_gold",
                             "food_drink_homeostasis_gold_silver", "food_homeostasis", "food_sharing", "food_unbounded", "predators",
-                            "food_drink_homeostasis_predators_gold_silver", "savanna_demo"]):
+                            "food_drink_homeostasis_predators_gold_silver", "savanna_demo", "food_sustainability"]):
     CASES["savanna_exp_" + _name] = dict(seed=40 + _k, steps=150, env=_name, kwargs=dict(max_iterations=60),
                                          agents=2 if _name in ("food_sharing", "predators", "savanna_demo") else 1)
 AGENTS = ["0", "1"]
@@ -118,6 +131,8 @@ def _worker(name):
                 v = super().choice(x, *a, **k)
                 if isinstance(x, list):
                     log["draws"].append(float(int(v)))
+                elif k.get("replace") is False:          # a resource drape's tile pick (:1287,1316): the indices, in order
+                    log["draws"].extend(float(int(i)) for i in np.asarray(v).ravel())
                 return v
         rng.__class__ = Logged
         rng._gw_hooked = True
@@ -178,7 +193,8 @@ def _worker(name):
     snapshot(obs, None, None, infos, True)
     rng = np.random.default_rng(9000 + case["seed"])
     actions, orders, draws = [], [], []
-    K = 32                                       # predator draws of one parallel step: (moves?, direction) per predator and frame
+    K = 64 if case["kwargs"].get("sustainability_challenge") or case.get("env") == "food_sustainability" else 32
+    # ^ predator draws of one parallel step: (moves?, direction) per predator and frame
     for t in range(case["steps"]):
         if not env.agents:                       # every agent is done: the reference needs a reset()
             obs, infos = env.reset()

@@ -62,6 +62,7 @@ def test_savanna_spec_matches_reference_metadata(name):
     assert spec.value_mapping == meta["value_mapping"]
     assert spec.config.max_iterations == meta["max_iterations"]
     assert (spec.height, spec.width) == d["board"].shape[1:] and spec.view == meta["view"] and spec.n_agents == meta["amount_agents"]
+    assert bool(spec.config.sustainability & 1) == bool(meta["kwargs"].get("sustainability_challenge") or meta["env"] == "food_sustainability")
     # every recorded layout is a permutation of the canonical one's interior
     canon = sorted("".join(spec.art))
     for t in (0, len(d["maps"]) - 1):
@@ -77,7 +78,7 @@ def test_savanna_oracle_replays_reference_trace(name, oracle_lib):
 
 def test_unbuilt_flags_are_rejected():
     from ai_safety_gridworlds_b200 import make_spec
-    for kw in (dict(amount_predators=9), dict(sustainability_challenge=True), dict(observation_direction_mode=2),
+    for kw in (dict(amount_predators=9), dict(sustainability_challenge=True, amount_drink_holes=1), dict(observation_direction_mode=2),
                dict(amount_food_patches=5), dict(level=5)):
         with pytest.raises(NotImplementedError):
             make_spec("aintelope_savanna", **kw)
