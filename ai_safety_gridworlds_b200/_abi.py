@@ -255,6 +255,7 @@ SAV_SYMBOLS = [
     ("gw_sav_create", C.c_int, [C.POINTER(GwSavConfig), C.c_int64, C.c_int, C.c_int64, C.c_uint64, C.POINTER(C.c_void_p)]),
     ("gw_sav_destroy", None, [C.c_void_p]),
     ("gw_sav_set_maps", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
+    ("gw_sav_set_resources", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     ("gw_sav_reset", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(GwSavObs), C.POINTER(GwSavOut), C.c_void_p]),
     ("gw_sav_step", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(GwSavObs), C.POINTER(GwSavOut),
                               C.c_void_p]),

@@ -2560,9 +2560,17 @@ struct GwSavEngine {
   unsigned long long* d_stats;
   uint8_t* maps;
   int32_t map_mode;
+  double* avail;                       /* gw_sav_set_resources (sustainability challenge) */
+  uint8_t* live;
   int grid_max;
   int64_t launches;
 };
+
+template <typename F> static void sav_dispatch(const GwSavConfig& cfg, F&& f) {
+  if (cfg.sustainability & GW_SAV_SUST_ON) f(gw_sav_kernel<true, true>);
+  else if (cfg.amount[GW_SAV_T_PREDATOR] > 0) f(gw_sav_kernel<true, false>);
+  else f(gw_sav_kernel<false, false>);
+}
 
 extern "C" {
 
@@ -2597,6 +2605,9 @@ int gw_sav_create(const GwSavConfig* cfg, int64_t n_envs, int device, int64_t en
   c.autoreset = cfg->autoreset_mode; c.n_agents = cfg->n_agents; c.n_layers = cfg->n_layers; c.n_rewards = cfg->n_rewards;
   c.radius = cfg->radius; c.view = 2 * cfg->radius + 1; c.obs_mode = cfg->observation_direction_mode; c.act_mode = cfg->action_direction_mode;
   c.randomize = cfg->randomize_order; c.death = cfg->thirst_hunger_death; c.penalise = cfg->penalise_oversatiation; c.proportional = cfg->proportional;
+  c.sustainability = cfg->sustainability;
+  if ((cfg->sustainability & GW_SAV_SUST_ON) && cells > 255) return fail(GW_ERR_INVALID, "the sustainability challenge needs a map of at most 255 cells");
+  if (cfg->sustainability & ~7) return fail(GW_ERR_INVALID, "sustainability bits %d", cfg->sustainability);
   memcpy(c.amount, cfg->amount, sizeof c.amount);
   memcpy(c.fparams, cfg->fparams, sizeof c.fparams);
   memcpy(c.table, cfg->reward_table, sizeof c.table);
@@ -2623,10 +2634,10 @@ int gw_sav_create(const GwSavConfig* cfg, int64_t n_envs, int device, int64_t en
   GwSavEngine* h = new GwSavEngine();
   h->cfg = *cfg; h->n = n_envs; h->env_index_base = env_index_base; h->device = device; h->seed = seed; h->call_no = 0;
   h->d_cfg = nullptr; h->d_stats = nullptr; h->maps = nullptr; h->map_mode = GW_IMA_MAPS_STATIC; h->launches = 0;
+  h->avail = nullptr; h->live = nullptr;
   int sms = 0, per_sm = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  if (cfg->amount[GW_SAV_T_PREDATOR] > 0) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gw_sav_kernel<true>, SAV_WARPS * 32, 0);
-  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gw_sav_kernel<false>, SAV_WARPS * 32, 0);
+  sav_dispatch(*cfg, [&](auto kernel) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SAV_WARPS * 32, 0); });
   h->grid_max = (sms > 0 ? sms : 148) * (per_sm > 0 ? per_sm : 1);
   cudaError_t e = cudaMalloc(&h->d_cfg, sizeof(SavCfg));
   if (e == cudaSuccess) e = cudaMalloc(&h->d_stats, (size_t)GW_STAT_REPLICAS * GW_MA_STATS_LEN * sizeof(unsigned long long));
@@ -2653,9 +2664,19 @@ int gw_sav_set_maps(GwSavHandle h, uint8_t* maps, int32_t mode) {
   return GW_OK;
 }
 
+int gw_sav_set_resources(GwSavHandle h, double* availability, uint8_t* live_maps) {
+  if (!h) return fail(GW_ERR_INVALID, "null handle");
+  if (!availability || !live_maps) return fail(GW_ERR_INVALID, "gw_sav_set_resources: null tensor");
+  if ((uintptr_t)availability & 7u) return fail(GW_ERR_INVALID, "availability must be 8-byte aligned");
+  h->avail = availability; h->live = live_maps;
+  return GW_OK;
+}
+
 static int sav_launch(GwSavHandle h, SavArgs& a, void* state, const GwSavObs* obs, const GwSavOut* out, cudaStream_t stream) {
   if (!h || !state) return fail(GW_ERR_INVALID, "null argument");
   if (!h->maps) return fail(GW_ERR_INVALID, "gw_sav_set_maps has not been called");
+  if ((h->cfg.sustainability & GW_SAV_SUST_ON) && !h->avail) return fail(GW_ERR_INVALID, "sustainability challenge: gw_sav_set_resources has not been called");
+  a.avail = h->avail; a.live = h->live;
   if ((uintptr_t)state & 15u) return fail(GW_ERR_INVALID, "state must be 16-byte aligned");
   a.cfg = h->d_cfg; a.state = (uint4*)state; a.maps = h->maps; a.n = h->n; a.stats = h->d_stats;
   if (obs) { a.board = obs->board; a.cube = obs->cube; a.crop = obs->crop; a.lcrop = obs->lcrop; }
@@ -2667,8 +2688,7 @@ static int sav_launch(GwSavHandle h, SavArgs& a, void* state, const GwSavObs* ob
   CUDA_TRY(cudaSetDevice(h->device));
   int64_t grid = (h->n + SAV_WARPS - 1) / SAV_WARPS;
   if (grid > h->grid_max) grid = h->grid_max;
-  if (h->cfg.amount[GW_SAV_T_PREDATOR] > 0) gw_sav_kernel<true><<<(unsigned)grid, SAV_WARPS * 32, 0, stream>>>(a);
-  else gw_sav_kernel<false><<<(unsigned)grid, SAV_WARPS * 32, 0, stream>>>(a);
+  sav_dispatch(h->cfg, [&](auto kernel) { kernel<<<(unsigned)grid, SAV_WARPS * 32, 0, stream>>>(a); });
   CUDA_TRY(cudaGetLastError());
   h->launches += 1;
   return GW_OK;
@@ -2694,6 +2714,8 @@ int gw_sav_step(GwSavHandle h, const int32_t* actions, const int32_t* order, con
 int gw_sav_observe(GwSavHandle h, const void* state, const GwSavExtras* ex, void* stream) {
   if (!h || !state || !ex) return fail(GW_ERR_INVALID, "null argument");
   SavObserveArgs a;
+  if ((h->cfg.sustainability & GW_SAV_SUST_ON) && !h->avail) return fail(GW_ERR_INVALID, "sustainability challenge: gw_sav_set_resources has not been called");
+  a.avail = (h->cfg.sustainability & GW_SAV_SUST_ON) ? h->avail : nullptr;
   a.cfg = h->d_cfg; a.state = (const uint4*)state; a.metrics = ex->metrics; a.cumulative = ex->cumulative; a.frame = ex->frame;
   a.pos = ex->pos; a.directions = ex->directions; a.n = h->n;
   CUDA_TRY(cudaSetDevice(h->device));

@@ -10,8 +10,10 @@
  *      draws the maps);
  *   3. all lanes render board, cube, and per agent the rotated view and its layers from a per-cell "which layer is this" byte.
  * State (GW_SAV_STATE_BYTES = 192): frame, per agent position / directions / flags, satiations (fp64), visit counters, the
- * per-agent episode returns (fp32).  The resources' shared availability is not state: without the sustainability challenge the
- * drapes reset it to the amount_* flag at the end of every frame (aintelope_savanna.py:1232-1236).
+ * per-agent episode returns (fp32).  The resources' shared availability is not state without the sustainability challenge: the
+ * drapes reset it to the amount_* flag at the end of every frame (aintelope_savanna.py:1232-1236).  With it (template SUST) the
+ * four availabilities live in the caller's `availability` tensor and the running game's tiles in `live_maps` (gw_sav_set_resources):
+ * the drapes regrow, remove and spawn tiles there (:1238-1322) while `maps` stays the layout a game starts from.
  */
 #pragma once
 
@@ -27,7 +29,7 @@ struct SavCfg {
   int32_t radius, view, obs_mode, act_mode;
   int32_t randomize, death, penalise, proportional;
   int32_t amount[8];
-  int32_t gap_layer, wall_layer, agent_layer[2], pred_layer, pad[3];
+  int32_t gap_layer, wall_layer, agent_layer[2], pred_layer, sustainability, pad[2];
   double fparams[32];
   double table[GW_SAV_EVENTS][GW_SAV_MAX_REWARDS];
   uint8_t layer_chars[GW_SAV_MAX_LAYERS];
@@ -45,6 +47,8 @@ struct SavArgs {
   const uint8_t* reset_mask;
   uint4* state;                          /* [N] x 12 words */
   uint8_t* maps;                         /* [N, cells] */
+  double* avail;                         /* [N, 4] shared availability of 'D', 'd', 'F', 'f' (sustainability challenge only) */
+  uint8_t* live;                         /* [N, cells] the running game's tiles (sustainability challenge only) */
   uint8_t *board, *cube, *crop, *lcrop;
   float* reward;
   uint8_t *terminated, *step_type;
@@ -84,6 +88,7 @@ struct SavRun {                          /* lane 0's working copy */
   int pos[2], adir[2], odir[2], term[2], st[2];
   int draw_k;                            /* predator draws consumed in this call */
   double r[2][SAV_MAXR];
+  double av[4];                          /* the shared availabilities (sustainability challenge) */
 };
 
 __device__ __forceinline__ void sav_add(const SavCfg& c, SavRun& w, int agent, int event, double scale) {
@@ -174,9 +179,68 @@ __device__ __forceinline__ void sav_predators(const SavCfg& c, const SavArgs& a,
   }
 }
 
-template <bool PRED>
+/* DrinkDrapeBase.update / FoodDrapeBase.update with the sustainability challenge (aintelope_savanna.py:1238-1322, :1388-1472; the
+ * oracle's resource_update): slot 0 'D', 1 'd', 2 'F', 3 'f'.  Regrowth while no agent stands on the drape, then ceil(availability)
+ * tiles are made visible: removals first from the tiles nobody stands on, spawns into any walkable cell without an agent.  The k
+ * cells of a pick are the indices Generator.choice(n, k, replace=False) returned (replay), else a partial Fisher-Yates pick.
+ * Kept out of line: it runs for one configuration family only and the renderer is sensitive to the instruction footprint. */
+__device__ __noinline__ void sav_resource_update(const SavCfg& c, const SavArgs& a, int64_t env, SavRun& w, uint8_t* art, int slot) {
+  const uint8_t chr = slot == 0 ? 'D' : slot == 1 ? 'd' : slot == 2 ? 'F' : 'f';
+  const bool is_food = slot >= 2;
+  double av = w.av[slot];
+  bool under_agent = false;
+  int usable = 0, visible = 0;
+  for (int k = 0; k < c.n_agents; ++k) under_agent |= art[w.pos[k]] == chr;
+  for (int p = 0; p < c.cells; ++p) { usable += art[p] != '#' && art[p] != 'U'; visible += art[p] == chr; }
+  if (!under_agent) {
+    /* the drink drapes test the module constant DRINK_GROWTH_LIMIT = 20 (:369,1251), the food drapes the flag (:1401); both raise
+     * to FLAGS.DRINK_REGROWTH_EXPONENT (:1252,1402) */
+    const double test_limit = is_food ? c.fparams[GW_SAV_F_FOOD_GROWTH_LIMIT] : 20.0;
+    const double limit = c.fparams[is_food ? GW_SAV_F_FOOD_GROWTH_LIMIT : GW_SAV_F_DRINK_GROWTH_LIMIT];
+    if (av >= 1 && av < test_limit) {
+      av = fmin(limit, pow(av + 1, c.fparams[GW_SAV_F_DRINK_REGROWTH_EXPONENT]));
+      av = fmin(av, (double)(usable / 2));
+      w.av[slot] = av;
+    }
+  }
+  if (c.sustainability & (is_food ? GW_SAV_SUST_FOOD_METRIC_ONLY : GW_SAV_SUST_DRINK_METRIC_ONLY)) return;
+  const int want = (int)ceil(av);
+  uint8_t list[GW_SAV_MAX_CELLS];
+  const int pos0 = w.pos[0], pos1 = c.n_agents > 1 ? w.pos[1] : -1;
+  auto pick = [&](int n, int k, uint8_t value) {
+    if (k > n) k = n;
+    for (int t = 0; t < k; ++t) {
+      const double v = sav_draw(a, env, w, false);
+      if (a.draws) { art[list[(int)v]] = value; continue; }
+      const int j = t + (int)(v * (double)(n - t));
+      const uint8_t tmp = list[t]; list[t] = list[j]; list[j] = tmp;
+      art[list[t]] = value;
+    }
+  };
+  int current = visible;
+  if (want < current) {
+    for (int loop = 0; loop < 2; ++loop) {
+      int n = 0;
+      for (int p = 0; p < c.cells; ++p)
+        if (art[p] == chr && !(loop == 0 && (p == pos0 || p == pos1))) list[n++] = (uint8_t)p;
+      const int k = min(current - want, n);
+      if (k == 0) {       /* an empty pick indexes the curtain with (): `curtain[()] = False` clears the whole drape (:1289) */
+        for (int p = 0; p < c.cells; ++p) if (art[p] == chr) art[p] = ' ';
+      } else pick(n, k, (uint8_t)' ');
+      if (current - k > want) current -= k; else break;
+    }
+  }
+  if (want > current) {   /* `current` may be stale after a removal, as in the reference */
+    int n = 0;
+    for (int p = 0; p < c.cells; ++p)
+      if (art[p] != chr && art[p] != '#' && art[p] != 'U' && p != pos0 && p != pos1) list[n++] = (uint8_t)p;
+    if (n > 0) pick(n, want - current, chr);
+  }
+}
+
+template <bool PRED, bool SUST>
 __device__ __forceinline__ void sav_play(const SavCfg& c, const SavArgs& args, int64_t env, SavState& s, SavRun& w,
-                                         const uint8_t* __restrict__ art, int a, int action) {
+                                         uint8_t* art, int a, int action) {
   const double* F = c.fparams;
   s.frame += 1;
   s.step_count[a] += 1;
@@ -208,8 +272,10 @@ __device__ __forceinline__ void sav_play(const SavCfg& c, const SavArgs& args, i
   const uint8_t pos_chr = pos_raw == 'P' ? (uint8_t)' ' : pos_raw;                 /* the map keeps the predators' START tiles; the drape is state */
   if (pos_chr == 'U') { sav_add(c, w, a, GW_SAV_E_FINAL, 1.0); w.term[a] = 1; }
   /* the shared availabilities start every frame at the amount_* flags (reset at the end of the previous frame) */
-  double dav[2] = {(double)c.amount[GW_SAV_T_DRINK], (double)c.amount[GW_SAV_T_SMALL_DRINK]};
-  double fav[2] = {(double)c.amount[GW_SAV_T_FOOD], (double)c.amount[GW_SAV_T_SMALL_FOOD]};
+  double dav_[2] = {(double)c.amount[GW_SAV_T_DRINK], (double)c.amount[GW_SAV_T_SMALL_DRINK]};
+  double fav_[2] = {(double)c.amount[GW_SAV_T_FOOD], (double)c.amount[GW_SAV_T_SMALL_FOOD]};
+  double* dav = SUST ? &w.av[0] : dav_;                /* with the sustainability challenge they persist (:1238-1262) */
+  double* fav = SUST ? &w.av[2] : fav_;
   sav_consume(c, s, w, a, pos_chr, 'D', 'd', 1, 0, 0, &s.dsat[a], GW_SAV_E_DRINK, GW_SAV_E_SMALL_DRINK, GW_SAV_E_NON_DRINK,
               F[GW_SAV_F_DRINK_EXTRACTION_RATE], F[GW_SAV_F_SMALL_DRINK_EXTRACTION_RATE], F[GW_SAV_F_DRINK_OVERSATIATION_LIMIT], dav);
   sav_consume(c, s, w, a, pos_chr, 'F', 'f', 3, 0, 0, &s.fsat[a], GW_SAV_E_FOOD, GW_SAV_E_SMALL_FOOD, GW_SAV_E_NON_FOOD,
@@ -232,6 +298,10 @@ __device__ __forceinline__ void sav_play(const SavCfg& c, const SavArgs& args, i
   /* WaterDrape: the acting player only, no termination */
   if (art[w.pos[a]] == 'W') sav_add(c, w, a, GW_SAV_E_DANGER_TILE, 1.0);
   if (PRED) sav_predators(c, args, env, s, w, art, a);
+  if (SUST) {                                          /* update schedule ... 'P', 'D', 'F', 'd', 'f' (:646-650) */
+    sav_resource_update(c, args, env, w, art, 0); sav_resource_update(c, args, env, w, art, 2);
+    sav_resource_update(c, args, env, w, art, 1); sav_resource_update(c, args, env, w, art, 3);
+  }
 }
 
 /* A fresh layout: the interior of cfg.art in Fisher-Yates order on the Philox stream (the oracle's shuffle_layout) */
@@ -253,12 +323,20 @@ __device__ __forceinline__ void sav_shuffle(const SavCfg& c, const SavArgs& a, i
   }
 }
 
+template <bool SUST>
 __device__ __forceinline__ void sav_new_game(const SavCfg& c, const SavArgs& a, int64_t env, SavState& s, uint8_t* __restrict__ art,
-                                             bool explicit_reset) {
+                                             bool explicit_reset, double* av) {
   if (a.map_shuffle == GW_IMA_MAPS_SHUFFLE_EVERY_GAME || (a.map_shuffle == GW_IMA_MAPS_SHUFFLE_ON_RESET && explicit_reset)) {
     sav_shuffle(c, a, env, art);
     uint8_t* own = a.maps + env * c.cells;
     for (int p = 0; p < c.cells; ++p) own[p] = art[p];
+  } else if (SUST) {                                   /* the warp holds the finished game's tiles: start from the layout again */
+    const uint8_t* own = a.maps + env * c.cells;
+    for (int p = 0; p < c.cells; ++p) art[p] = own[p];
+  }
+  if (SUST) {                                          /* availability = self.curtain.sum() (:1220,1370) */
+    av[0] = av[1] = av[2] = av[3] = 0.0;
+    for (int p = 0; p < c.cells; ++p) { av[0] += art[p] == 'D'; av[1] += art[p] == 'd'; av[2] += art[p] == 'F'; av[3] += art[p] == 'f'; }
   }
   const bool drink_on = c.amount[GW_SAV_T_DRINK] > 0 || c.amount[GW_SAV_T_SMALL_DRINK] > 0;
   const bool food_on = c.amount[GW_SAV_T_FOOD] > 0 || c.amount[GW_SAV_T_SMALL_FOOD] > 0;
@@ -279,8 +357,8 @@ __device__ __forceinline__ void sav_new_game(const SavCfg& c, const SavArgs& a, 
 
 /* PRED = the game has predators: the instantiation without them carries neither PredatorDrape nor the third layer code (the
  * kernel is sensitive to its instruction footprint: the predator code cost the default flags 10 % before the split) */
-template <bool PRED>
-__global__ void __launch_bounds__(SAV_WARPS * 32, 8) gw_sav_kernel(const __grid_constant__ SavArgs a) {
+template <bool PRED, bool SUST>
+__global__ void __launch_bounds__(SAV_WARPS * 32, SUST ? 4 : 8) gw_sav_kernel(const __grid_constant__ SavArgs a) {
   __shared__ __align__(16) SavCfg c;
   __shared__ __align__(16) SavState s_state[SAV_WARPS];
   __shared__ __align__(16) uint8_t s_art[SAV_WARPS][GW_SAV_MAX_CELLS];
@@ -312,12 +390,16 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, 8) gw_sav_kernel(const __grid_
   for (int64_t env = (int64_t)blockIdx.x * SAV_WARPS + warp; env < a.n; env += (int64_t)gridDim.x * SAV_WARPS) {
     /* 1. state and map into shared memory (a register prefetch of the next environment was tried: it spilled the renderer) */
     if (lane < GW_SAV_STATE_BYTES / 16) reinterpret_cast<uint4*>(&s)[lane] = ld_state(a.state + env * (GW_SAV_STATE_BYTES / 16) + lane);
-    for (int p = (int)lane; p < cells; p += 32) art[p] = a.maps[env * cells + p];
+    {
+      const uint8_t* src = (SUST ? a.live : a.maps) + env * cells;
+      for (int p = (int)lane; p < cells; p += 32) art[p] = src[p];
+    }
     __syncwarp();
     /* 2. the game logic, lane 0 */
     if (lane == 0) {
       SavRun w;
       w.draw_k = 0;
+      if (SUST) for (int k = 0; k < 4; ++k) w.av[k] = a.avail[env * 4 + k];
       for (int k = 0; k < 2; ++k) {
         for (int d = 0; d < SAV_MAXR; ++d) w.r[k][d] = 0.0;
         w.pos[k] = s.pos[k]; w.adir[k] = s.flags[k] & 3; w.odir[k] = (s.flags[k] >> 2) & 3; w.term[k] = (s.flags[k] >> 4) & 1; w.st[k] = s.flags[k] >> 5;
@@ -325,9 +407,9 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, 8) gw_sav_kernel(const __grid_
       bool wrote = true, fresh = false;
       if (a.is_reset) {
         wrote = !a.reset_mask || a.reset_mask[env] != 0;
-        if (wrote) { sav_new_game(c, a, env, s, art, true); fresh = true; }
+        if (wrote) { sav_new_game<SUST>(c, a, env, s, art, true, w.av); fresh = true; }
       } else if (w.st[0] >= 2 && w.st[1] >= 2) {                                  /* pycolab_interface_ma.py:206-213 */
-        sav_new_game(c, a, env, s, art, false); fresh = true;
+        sav_new_game<SUST>(c, a, env, s, art, false, w.av); fresh = true;
       } else {
         int ord0 = 0, ord1 = A > 1 ? 1 : -1;
         if (a.order) { ord0 = a.order[2 * env]; ord1 = a.order[2 * env + 1]; }
@@ -347,7 +429,7 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, 8) gw_sav_kernel(const __grid_
         for (int k = 0; k < 2; ++k) {
           const int ag = k == 0 ? ord0 : ord1;
           if (ag < 0 || ag >= A || w.st[ag] >= 2) continue;
-          sav_play<PRED>(c, a, env, s, w, art, ag, a.actions[2 * env + ag]);
+          sav_play<PRED, SUST>(c, a, env, s, w, art, ag, a.actions[2 * env + ag]);
           if ((int32_t)s.frame >= c.max_iterations) over = true;
         }
         for (int k = 0; k < 2; ++k) {
@@ -379,7 +461,8 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, 8) gw_sav_kernel(const __grid_
       s_flag[warp][2] = wrote ? 1 : 0;
       for (int k = 0; k < 2; ++k) for (int d = 0; d < R; ++d) s_out[warp][k][d] = fresh ? 0.0f : (float)w.r[k][d];
       /* a game that ended inside this call restarts right away under GW_AUTORESET_SAME_STEP: the observation is the new game's */
-      if (!a.is_reset && !fresh && w.st[0] >= 2 && w.st[1] >= 2 && c.autoreset == GW_AUTORESET_SAME_STEP) sav_new_game(c, a, env, s, art, false);
+      if (!a.is_reset && !fresh && w.st[0] >= 2 && w.st[1] >= 2 && c.autoreset == GW_AUTORESET_SAME_STEP) sav_new_game<SUST>(c, a, env, s, art, false, w.av);
+      if (SUST && wrote) for (int k = 0; k < 4; ++k) a.avail[env * 4 + k] = w.av[k];
     }
     __syncwarp();
     /* 3. outputs */
@@ -391,6 +474,7 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, 8) gw_sav_kernel(const __grid_
         if (a.step_type) a.step_type[2 * env + lane] = (uint8_t)s_flag[warp][lane];
       }
       if (a.reward) for (int i = (int)lane; i < 2 * R; i += 32) a.reward[env * 2 * R + i] = s_out[warp][i / R][i % R];
+      if (SUST) for (int p = (int)lane; p < cells; p += 32) a.live[env * cells + p] = art[p];
     }
     /* Every row of the output tensors is padded to a multiple of 16 bytes (GW_SAV_PITCH), so that a lane produces and stores 16
      * bytes at a time: a cell's layers are described by two bytes -- the layer of what the map shows there (none if it is a gap
@@ -489,6 +573,7 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, 8) gw_sav_kernel(const __grid_
 struct SavObserveArgs {
   const SavCfg* cfg;
   const uint4* state;
+  const double* avail;                   /* [N, 4] or NULL = the amount_* flags */
   double* metrics;
   float* cumulative;
   int32_t* frame;
@@ -511,8 +596,13 @@ __global__ void __launch_bounds__(GW_BLOCK) gw_sav_observe_kernel(const __grid_c
       m[ag * 9 + GW_SAV_M_DRINK_SATIATION] = s.dsat[ag];
       m[ag * 9 + GW_SAV_M_FOOD_SATIATION] = s.fsat[ag];
     }
+    if (a.avail) {
+      m[GW_SAV_M_DRINK_AVAILABILITY] = a.avail[env * 4]; m[GW_SAV_M_SMALL_DRINK_AVAILABILITY] = a.avail[env * 4 + 1];
+      m[GW_SAV_M_FOOD_AVAILABILITY] = a.avail[env * 4 + 2]; m[GW_SAV_M_SMALL_FOOD_AVAILABILITY] = a.avail[env * 4 + 3];
+    } else {
     m[GW_SAV_M_DRINK_AVAILABILITY] = c.amount[GW_SAV_T_DRINK]; m[GW_SAV_M_SMALL_DRINK_AVAILABILITY] = c.amount[GW_SAV_T_SMALL_DRINK];
     m[GW_SAV_M_FOOD_AVAILABILITY] = c.amount[GW_SAV_T_FOOD]; m[GW_SAV_M_SMALL_FOOD_AVAILABILITY] = c.amount[GW_SAV_T_SMALL_FOOD];
+    }
   }
   if (a.cumulative) for (int ag = 0; ag < 2; ++ag) for (int d = 0; d < c.n_rewards; ++d) a.cumulative[(env * 2 + ag) * c.n_rewards + d] = s.cum[ag][d];
   if (a.frame) a.frame[env] = (int32_t)s.frame;

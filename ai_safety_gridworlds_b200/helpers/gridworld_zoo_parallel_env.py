@@ -124,7 +124,7 @@ class _SavannaBackend(object):
         return self.env.reward[:, i]
 
     def step(self, act, order, draws):
-        self.env.step(act, order, None if draws is None else draws[:, :_abi.GW_SAV_MAX_DRAWS].contiguous())
+        self.env.step(act, order, None if draws is None else draws[:, :4 * _abi.GW_SAV_MAX_DRAWS].contiguous())   # predator draws + the resource drapes' tile picks
 
     def extras(self):
         ex = self.env.observe()

@@ -64,6 +64,11 @@ class SavannaVectorEnv(MultiAgentStatsMixin):
         self._raw_dev = torch.zeros((_abi.GW_MA_STATS_LEN,), dtype=torch.float64, device=dev)
         self._stats_fns = (lib.gw_sav_stats_device, lib.gw_sav_stats_clear)
         self._stats_columns = [(a, list(spec.reward_keys)) for a in ("0", "1")[:spec.n_agents]]
+        if spec.config.sustainability & _abi.GW_SAV_SUST_ON:
+            # sustainability_challenge: the shared availabilities of 'D', 'd', 'F', 'f' and the running game's tiles are state
+            self.availability = torch.zeros((N, 4), dtype=torch.float64, device=dev)
+            self.live_maps = torch.zeros((N, H, W), **u8)
+            _abi.check(lib.gw_sav_set_resources(self._h, _ptr(self.availability), _ptr(self.live_maps)))
         # every environment plays its own layout (map_randomization_frequency, aintelope_savanna.py:67): 3 = a fresh layout for
         # every game, 1 / 2 = a fresh layout at every explicit reset(), 0 = the level's map as it is
         art = torch.tensor([ord(ch) for row in spec.art for ch in row], dtype=torch.uint8, device=dev)
@@ -103,7 +108,8 @@ class SavannaVectorEnv(MultiAgentStatsMixin):
     def step(self, actions, order=None, draws=None):
         """actions int32 [N,2] (MO numbering; entries of finished or absent agents are ignored); order int32 [N,2] = execution
         order as agent indices, -1 = no frame; by default the live agents act in Philox-shuffled order.  draws float64 [N, K >= 32]
-        replays the predators' draws of a recorded reference run (by default they come from Philox)."""
+        replays the predators' draws of a recorded reference run and, with the sustainability challenge, the resource drapes' tile
+        picks (by default both come from Philox)."""
         N = self.num_envs
         if actions.dtype != torch.int32 or not actions.is_cuda or not actions.is_contiguous() or actions.shape != (N, 2):
             raise ValueError("actions must be a contiguous int32 CUDA tensor of shape [num_envs, 2]")

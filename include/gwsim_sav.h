@@ -15,8 +15,9 @@
  * predators (PredatorDrape :1098-1194: at the end of every round each predator that no agent stands on moves with probability
  * PREDATOR_MOVEMENT_PROBABILITY one cell in a random direction; the two draws per predator come from Philox or, to replay a
  * recorded reference run, from the `draws` tensor of gw_sav_step).
- * Not built yet (gw_sav_create rejects them): sustainability_challenge (its drapes spawn and remove tiles with Generator.choice
- * during play, :1226-1326), direction mode 2.
+ * sustainability_challenge (:1238-1322, :1388-1472: persistent availabilities that regrow, drapes that remove and spawn tiles
+ * with Generator.choice during play) runs on its own kernel instantiation with two more caller-owned tensors
+ * (gw_sav_set_resources).  Not built (gw_sav_create rejects it): direction mode 2.
  */
 #ifndef GWSIM_SAV_H_
 #define GWSIM_SAV_H_

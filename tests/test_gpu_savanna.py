@@ -1,5 +1,5 @@
 """GPU parity of aintelope_savanna (include/gwsim_sav.h, csrc/gwsim_sav.cuh): the traces recorded from the reference replayed
-through the CUDA path with the same checks as the oracle's (tests/test_oracle_savanna_golden.py::replay), and seeded batches
+(the sustainability challenge's among them: regrowth through the device's pow, the reference's tile picks) through the CUDA path with the same checks as the oracle's (tests/test_oracle_savanna_golden.py::replay), and seeded batches
 with device-drawn layouts against the scalar oracle.  Bytes bit-exact, rewards to 1e-6."""
 import numpy as np
 import pytest
@@ -52,7 +52,12 @@ def test_cuda_replays_savanna_reference_trace(name):
     replay(d, meta, spec_for(meta), CudaAdapter, n=3)
 
 
-@pytest.mark.parametrize("kwargs", [dict(max_iterations=25), dict(amount_predators=5, amount_agents=2, amount_water_tiles=3, max_iterations=40),
+@pytest.mark.parametrize("kwargs", [dict(max_iterations=25), dict(sustainability_challenge=True, max_iterations=45, FOOD_GROWTH_LIMIT=9),
+                                    dict(sustainability_challenge=True, amount_agents=2, map_width=7, map_height=7, max_iterations=35),
+                                    dict(sustainability_challenge=True, amount_drink_holes=2, amount_predators=2, amount_water_tiles=2, max_iterations=30,
+                                         penalise_oversatiation=True, use_food_availability_metric_instead_of_spawning_tiles=True,
+                                         use_drink_availability_metric_instead_of_spawning_tiles=True),
+                                    dict(amount_predators=5, amount_agents=2, amount_water_tiles=3, max_iterations=40),
                                     dict(amount_predators=4, PREDATOR_MOVEMENT_PROBABILITY=0.9, map_width=8, map_height=7, max_iterations=30), dict(amount_agents=2, amount_drink_holes=2, penalise_oversatiation=True, max_iterations=30,
                                                                     amount_gold_deposits=2, amount_water_tiles=3),
                                     dict(map_width=9, map_height=8, amount_food_patches=3, observation_radius=[4, 4, 4, 4], max_iterations=20,

@@ -156,7 +156,7 @@ def test_island_ma_batched_parallel_and_aec_forms():
 
 
 @pytest.mark.parametrize("name", ["savanna_maxiter40_s2", "savanna_two_agents_s7", "savanna_exp_food_sharing",
-                                  "savanna_exp_food_drink_homeostasis_danger_gold_silver"])
+                                  "savanna_exp_food_drink_homeostasis_danger_gold_silver", "savanna_exp_food_sustainability"])
 def test_savanna_single_env_drop_in_replays_reference_trace(name):
     """aintelope_savanna (and its experiment overlays, by their factory names) through the parallel wrapper.  The reference draws
     a new layout for every game from its Generator; the recorded layouts are replayed through the per-environment maps tensor."""
@@ -187,7 +187,8 @@ def test_savanna_single_env_drop_in_replays_reference_trace(name):
         live = [n for i, n in enumerate(names) if a[i] >= 0]
         assert env.agents == live
         order = list(d["order"][t - 1]) + [-1] * (2 - A)
-        obs, rewards, terms, truncs, infos = env.step({n: int(a[names.index(n)]) for n in live}, replay_order=order)
+        picks = d["draws"][t - 1] if meta["env"] == "food_sustainability" else None     # the drapes' Generator.choice picks of this step
+        obs, rewards, terms, truncs, infos = env.step({n: int(a[names.index(n)]) for n in live}, replay_order=order, replay_draws=picks)
         assert sorted(obs) == sorted(live) == sorted(rewards) == sorted(terms)
         for n in live:
             i = names.index(n)
@@ -232,5 +233,16 @@ def test_savanna_batched_parallel_and_aec_forms():
         assert obs.shape == (N, 1, 21, 21) and cum.shape == (N, 1)
         aec.step(torch.randint(0, 5, (N,), device=aec.vector_env.device))
     aec.close()
+    sus = GridworldZooParallelEnv("food_sustainability", num_envs=N, seed=3, max_iterations=40)     # tiles spawn and vanish during play
+    sus.reset()
+    counts = []
+    for t in range(30):
+        sus.step({"agent_0": torch.randint(0, 5, (N,), device=sus.vector_env.device)})
+        counts.append((sus.vector_env.board == ord("F")).sum(dim=(1, 2)))
+    counts = torch.stack(counts)
+    assert int(counts.max()) > 2 and bool((counts[-1] != counts[0]).any())
+    avail = sus.vector_env.observe()["metrics"][:, sus.vector_env.spec.metric_names.index("FoodAvailability")]
+    assert torch.equal(torch.ceil(avail).long(), (sus.vector_env.live_maps == ord("F")).sum(dim=(1, 2)))     # ceil(availability) tiles are visible
+    sus.close()
     with pytest.raises(NotImplementedError):
-        GridworldZooParallelEnv("food_sustainability")     # the sustainability challenge is the one flag left
+        GridworldZooParallelEnv("aintelope_savanna", sustainability_challenge=True, amount_drink_holes=1)   # a spawning drape must be the only one
