@@ -2591,7 +2591,7 @@ int gw_sav_create(const GwSavConfig* cfg, int64_t n_envs, int device, int64_t en
     return fail(GW_ERR_INVALID, "layers / reward dimensions out of range (at most %d layers, %d dimensions)", GW_SAV_MAX_LAYERS, SAV_MAXR);
   if (cfg->radius < 0 || cfg->radius > GW_SAV_MAX_RADIUS) return fail(GW_ERR_INVALID, "observation radius %d outside 0..%d", cfg->radius, GW_SAV_MAX_RADIUS);
   if (cfg->max_iterations < 1 || cfg->max_iterations > 65535) return fail(GW_ERR_INVALID, "max_iterations %d outside 1..65535", cfg->max_iterations);
-  if ((cfg->observation_direction_mode | cfg->action_direction_mode) & ~1) return fail(GW_ERR_INVALID, "direction mode 2 is not built (0 and 1 are)");
+  if (cfg->observation_direction_mode < 0 || cfg->observation_direction_mode > 2) return fail(GW_ERR_INVALID, "direction mode %d outside 0..2", cfg->observation_direction_mode);
   if (cfg->observation_direction_mode != cfg->action_direction_mode) return fail(GW_ERR_INVALID, "the two direction modes must agree");
   if (cfg->amount[GW_SAV_T_PREDATOR] < 0 || cfg->amount[GW_SAV_T_PREDATOR] > GW_SAV_MAX_PREDATORS) return fail(GW_ERR_INVALID, "amount_predators %d outside 0..%d", cfg->amount[GW_SAV_T_PREDATOR], GW_SAV_MAX_PREDATORS);
   if (cfg->amount[GW_SAV_T_PREDATOR] > 0 && cells > 255) return fail(GW_ERR_INVALID, "predators need a map of at most 255 cells");

@@ -84,6 +84,14 @@ __device__ __forceinline__ int sav_relative_to_absolute(int action, int dir) {  
   return turn_right[dir];
 }
 
+__device__ __forceinline__ int sav_turned(int action, int dir) {                      /* direction mode 2: the TURN_* actions (safety_game_ma.py:607-640) */
+  const int opposite[4] = {GW_DIR_RIGHT, GW_DIR_LEFT, GW_DIR_DOWN, GW_DIR_UP};
+  if (action == GW_ACT_TURN_LEFT_90) return sav_relative_to_absolute(GW_ACT_LEFT, dir);
+  if (action == GW_ACT_TURN_RIGHT_90) return sav_relative_to_absolute(GW_ACT_RIGHT, dir);
+  if (action == GW_ACT_TURN_LEFT_180 || action == GW_ACT_TURN_RIGHT_180) return opposite[dir];
+  return dir;
+}
+
 struct SavRun {                          /* lane 0's working copy */
   int pos[2], adir[2], odir[2], term[2], st[2];
   int draw_k;                            /* predator draws consumed in this call */
@@ -245,9 +253,11 @@ __device__ __forceinline__ void sav_play(const SavCfg& c, const SavArgs& args, i
   s.frame += 1;
   s.step_count[a] += 1;
   if (action != GW_ACT_NOOP && c.obs_mode == 1) w.odir[a] = sav_relative_to_absolute(action, w.odir[a]);
-  if (action != GW_ACT_NOOP) {
+  if (c.obs_mode == 2) w.odir[a] = sav_turned(action, w.odir[a]);
+  if (c.act_mode == 2 && action >= GW_ACT_TURN_LEFT_90) w.adir[a] = sav_turned(action, w.adir[a]);      /* a turn moves nothing */
+  else if (action != GW_ACT_NOOP) {
     int dir;
-    if (c.act_mode == 1) dir = sav_relative_to_absolute(action, w.adir[a]);
+    if (c.act_mode >= 1) dir = sav_relative_to_absolute(action, w.adir[a]);
     else dir = action == GW_ACT_LEFT ? GW_DIR_LEFT : action == GW_ACT_RIGHT ? GW_DIR_RIGHT : action == GW_ACT_UP ? GW_DIR_UP : GW_DIR_DOWN;
     const int dr = dir == GW_DIR_UP ? -1 : dir == GW_DIR_DOWN ? 1 : 0, dc = dir == GW_DIR_LEFT ? -1 : dir == GW_DIR_RIGHT ? 1 : 0;
     const int nr = w.pos[a] / c.width + dr, nc = w.pos[a] % c.width + dc;

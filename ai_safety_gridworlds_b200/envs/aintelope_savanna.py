@@ -2,7 +2,7 @@
 
 Mirrors the flag system of the reference's environments/aintelope/aintelope_savanna.py (levels :82-290, flag defaults
 :54-80,336-415,417-592, tile counts :652-669, value mapping :1546-1563, enabled reward dimensions :1566-1620, action set
-:1626-1640).  Built: everything but direction mode 2 and tile-spawning sustainability on maps with several drape kinds, which raise NotImplementedError
+:1626-1640).  Built: everything but differing direction modes and tile-spawning sustainability on maps with several drape kinds, which raise NotImplementedError
 (include/gwsim_sav.h).  Data and configuration only -- the dynamics are in
 csrc/gwsim_sav.cuh.
 """
@@ -179,10 +179,10 @@ def compile_spec(autoreset_mode: int = _abi.GW_AUTORESET_NEXT_STEP, **kwargs) ->
     if not (0 <= flags["amount_predators"] <= 8):
         raise NotImplementedError("the CUDA backend keeps at most 8 predators per environment")
     for mode in ("observation_direction_mode", "action_direction_mode"):
-        if flags[mode] not in (0, 1):
-            raise NotImplementedError("%s 2 (separate turning actions) is not built" % mode)
+        if flags[mode] not in (0, 1, 2):
+            raise ValueError("%s must be 0, 1 or 2" % mode)
     if flags["observation_direction_mode"] != flags["action_direction_mode"]:
-        raise NotImplementedError("observation_direction_mode and action_direction_mode must agree (both 0 or both 1)")
+        raise NotImplementedError("observation_direction_mode and action_direction_mode must agree (both 0, both 1 or both 2)")
     radius = flags["observation_radius"]
     radius = [radius] * 4 if isinstance(radius, int) else list(radius)
     if len(set(radius)) != 1 or not (0 <= radius[0] <= 10):
@@ -345,6 +345,8 @@ def compile_spec(autoreset_mode: int = _abi.GW_AUTORESET_NEXT_STEP, **kwargs) ->
     lo, hi = (1, 1) if level == 2 else (1, 2) if level in (3, 4) else (1, 4)              # :1626-1633
     if flags["noops"]:
         lo = 0
+    if flags["observation_direction_mode"] == 2 or flags["action_direction_mode"] == 2:      # the TURN_* actions 5..8 (:1646-1647)
+        hi = 8
     flags = dict(flags, _resized=resized)
     return SavSpec(NAME, cfg, list(art), height, width, keys, layer_order, metric_names, metric_slots, value_mapping, (lo, hi), n_agents,
                    2 * int(radius[0]) + 1, flags)

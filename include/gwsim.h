@@ -87,6 +87,7 @@ enum GwAutoreset {
 
 /* shared/safety_game_mo_base.py:76-93 (the MO/MA action numbering) */
 enum GwAction { GW_ACT_NOOP = 0, GW_ACT_LEFT = 1, GW_ACT_RIGHT = 2, GW_ACT_UP = 3, GW_ACT_DOWN = 4,
+                GW_ACT_TURN_LEFT_90 = 5, GW_ACT_TURN_RIGHT_90 = 6, GW_ACT_TURN_LEFT_180 = 7, GW_ACT_TURN_RIGHT_180 = 8,   /* direction mode 2 (aintelope_savanna) */
                 GW_ACT_QUIT = 9 };
 /* shared/safety_game.py:42-55: the ORIGINAL suite numbers its actions differently */
 enum GwClassicAction { GW_CACT_NOOP = 0, GW_CACT_UP = 1, GW_CACT_DOWN = 2, GW_CACT_LEFT = 3, GW_CACT_RIGHT = 4,

@@ -17,7 +17,7 @@
  * recorded reference run, from the `draws` tensor of gw_sav_step).
  * sustainability_challenge (:1238-1322, :1388-1472: persistent availabilities that regrow, drapes that remove and spawn tiles
  * with Generator.choice during play) runs on its own kernel instantiation with two more caller-owned tensors
- * (gw_sav_set_resources).  Not built (gw_sav_create rejects it): direction mode 2.
+ * (gw_sav_set_resources).  Not built (gw_sav_create rejects it): observation and action direction modes that differ.
  */
 #ifndef GWSIM_SAV_H_
 #define GWSIM_SAV_H_
@@ -76,7 +76,8 @@ typedef struct GwSavConfig {
   int32_t n_agents;                    /* amount_agents: 1 or 2 ('0', '1') */
   int32_t n_layers, n_rewards;
   int32_t radius;                      /* observation_radius [r, r, r, r]: (2r + 1)^2 agent views */
-  int32_t observation_direction_mode, action_direction_mode;   /* 0 fixed, 1 relative to the last move */
+  int32_t observation_direction_mode, action_direction_mode;   /* 0 fixed, 1 relative to the last move, 2 relative, turned by the
+                                                                  TURN_* actions only (safety_game_ma.py:515-768); both must agree */
   int32_t randomize_order;             /* randomize_agent_actions_order */
   int32_t thirst_hunger_death, penalise_oversatiation, proportional;
   int32_t amount[8];                   /* GwSavTile: the amount_* flags (the resources' availability is reset to them every frame) */

@@ -102,6 +102,15 @@ static int relative_to_absolute(int action, int dir) {
   return turn_right[dir];
 }
 
+/* direction mode 2 (safety_game_ma.py:607-640, :672-706, :734-764): only the TURN_* actions change a direction */
+static int turned(int action, int dir) {
+  static const int opposite[4] = {GW_DIR_RIGHT, GW_DIR_LEFT, GW_DIR_DOWN, GW_DIR_UP};
+  if (action == GW_ACT_TURN_LEFT_90) return relative_to_absolute(GW_ACT_LEFT, dir);
+  if (action == GW_ACT_TURN_RIGHT_90) return relative_to_absolute(GW_ACT_RIGHT, dir);
+  if (action == GW_ACT_TURN_LEFT_180 || action == GW_ACT_TURN_RIGHT_180) return opposite[dir];
+  return dir;
+}
+
 /* one resource tile under the agent (:871-960): `big` is 'D' / 'F', `small` 'd' / 'f' */
 static void consume(const VOracle* o, VEnv* e, int a, uint8_t pos_chr, uint8_t big, uint8_t small, int visit_slot, int avail_slot,
                     double* satiation, int e_big, int e_small, int e_none, double rate_big, double rate_small, double limit,
@@ -308,9 +317,11 @@ static void play(const VOracle* o, VEnv* e, int a, int action, double r[NA][MAXR
   e->step_count[a] += 1;
   /* AgentSprite.update (:1030-1046): the observation direction turns first (safety_game_ma.py:650-709) */
   if (action != GW_ACT_NOOP && obs_mode == 1) e->odir[a] = relative_to_absolute(action, e->odir[a]);
-  if (action != GW_ACT_NOOP) {                                                                 /* AgentSafetySprite.update (safety_game_ma.py:769-809) */
+  if (obs_mode == 2) e->odir[a] = turned(action, e->odir[a]);
+  if (act_mode == 2 && action >= GW_ACT_TURN_LEFT_90) e->adir[a] = turned(action, e->adir[a]);  /* a turn moves nothing (:547-548) */
+  else if (action != GW_ACT_NOOP) {                                                            /* AgentSafetySprite.update (safety_game_ma.py:769-809) */
     int dir;
-    if (act_mode == 1) dir = relative_to_absolute(action, e->adir[a]);
+    if (act_mode >= 1) dir = relative_to_absolute(action, e->adir[a]);
     else dir = action == GW_ACT_LEFT ? GW_DIR_LEFT : action == GW_ACT_RIGHT ? GW_DIR_RIGHT : action == GW_ACT_UP ? GW_DIR_UP : GW_DIR_DOWN;
     const int dr = dir == GW_DIR_UP ? -1 : dir == GW_DIR_DOWN ? 1 : 0, dc = dir == GW_DIR_LEFT ? -1 : dir == GW_DIR_RIGHT ? 1 : 0;
     const int nr = e->pos[a] / c->width + dr, nc = e->pos[a] % c->width + dc;

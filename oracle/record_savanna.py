@@ -70,6 +70,12 @@ CASES = {
     "savanna_sustainability_metric_only_s21": dict(seed=21, steps=300, kwargs=dict(
         sustainability_challenge=True, amount_drink_holes=2, amount_small_food_patches=1, amount_gold_deposits=1, amount_water_tiles=2, max_iterations=100,
         use_food_availability_metric_instead_of_spawning_tiles=True, use_drink_availability_metric_instead_of_spawning_tiles=True, **HOMEOSTASIS)),
+    # direction mode 2: moves relative to a direction only the TURN_* actions change (safety_game_ma.py:515-768)
+    "savanna_turning_actions_s22": dict(seed=22, steps=300, kwargs=dict(observation_direction_mode=2, action_direction_mode=2, max_iterations=80,
+                                                                       amount_water_tiles=2)),
+    "savanna_turning_actions_two_agents_s23": dict(seed=23, steps=300, kwargs=dict(observation_direction_mode=2, action_direction_mode=2, amount_agents=2,
+                                                                                  amount_predators=3, amount_drink_holes=1, max_iterations=60,
+                                                                                  observation_radius=[4, 4, 4, 4], **HOMEOSTASIS)),
     "savanna_randmap_once_s13": dict(seed=13, steps=200, kwargs=dict(map_randomization_frequency=1, max_iterations=40)),
 }
 # the experiment overlays (experiments/aintelope/*.py) without the sustainability challenge, through the reference's factory names
@@ -203,7 +209,8 @@ def _worker(name):
             snapshot(obs, None, None, infos, True)
             continue
         live = [nm in env.agents for nm in names]
-        a = [int(rng.integers(0, 5)) if live[i] else -1 for i in range(A)]
+        n_act = 9 if case["kwargs"].get("action_direction_mode") == 2 else 5            # mode 2 adds TURN_LEFT_90 .. TURN_RIGHT_180 = 5..8
+        a = [int(rng.integers(0, n_act)) if live[i] else -1 for i in range(A)]
         log["order"] = None
         del log["draws"][:]
         obs, rewards, terms, truncs, infos = env.step({nm: a[i] for i, nm in enumerate(names) if live[i]})

@@ -58,6 +58,8 @@ def test_cuda_replays_savanna_reference_trace(name):
                                          penalise_oversatiation=True, use_food_availability_metric_instead_of_spawning_tiles=True,
                                          use_drink_availability_metric_instead_of_spawning_tiles=True),
                                     dict(amount_predators=5, amount_agents=2, amount_water_tiles=3, max_iterations=40),
+                                    dict(observation_direction_mode=2, action_direction_mode=2, amount_agents=2, amount_predators=2, max_iterations=40,
+                                         observation_radius=[5, 5, 5, 5]),
                                     dict(amount_predators=4, PREDATOR_MOVEMENT_PROBABILITY=0.9, map_width=8, map_height=7, max_iterations=30), dict(amount_agents=2, amount_drink_holes=2, penalise_oversatiation=True, max_iterations=30,
                                                                     amount_gold_deposits=2, amount_water_tiles=3),
                                     dict(map_width=9, map_height=8, amount_food_patches=3, observation_radius=[4, 4, 4, 4], max_iterations=20,
@@ -78,7 +80,7 @@ def test_savanna_batch_matches_oracle(kwargs, mode, oracle_lib):
     games = 0
     for t in range(120):
         if t > 0:
-            a = rng.integers(0, 5, size=(N, 2)).astype(np.int32)
+            a = rng.integers(0, 9 if kwargs.get("action_direction_mode") == 2 else 5, size=(N, 2)).astype(np.int32)   # mode 2: TURN_* = 5..8
             env.step(torch.from_numpy(a).to(env.device))
             orc.step(a)
         ctx = "t=%d" % t
