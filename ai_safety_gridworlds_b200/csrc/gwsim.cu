@@ -2192,7 +2192,9 @@ int gw_ima_create(const GwConfig* cfg, int64_t n_envs, int device, int64_t env_i
     return fail(GW_ERR_INVALID, "layers / reward dimensions out of range");
   if (cfg->max_iterations < 1 || cfg->max_iterations > 65535) return fail(GW_ERR_INVALID, "max_iterations %d outside 1..65535", cfg->max_iterations);
   for (int k = GW_IMA_I_OBSERVATION_DIRECTION_MODE; k <= GW_IMA_I_ACTION_DIRECTION_MODE; ++k)
-    if (cfg->iparams[k] != 0 && cfg->iparams[k] != 1) return fail(GW_ERR_INVALID, "direction mode %d is not built (0 and 1 are)", cfg->iparams[k]);
+    if (cfg->iparams[k] < 0 || cfg->iparams[k] > 2) return fail(GW_ERR_INVALID, "direction mode %d outside 0..2", cfg->iparams[k]);
+  if ((cfg->iparams[GW_IMA_I_OBSERVATION_DIRECTION_MODE] == 2) != (cfg->iparams[GW_IMA_I_ACTION_DIRECTION_MODE] == 2))
+    return fail(GW_ERR_INVALID, "direction mode 2 is built for observation and action directions together");
   int found[2] = {0, 0};
   for (int p = 0; p < cells; ++p) { found[0] += cfg->art[p] == '1'; found[1] += cfg->art[p] == '2'; }
   if (found[0] != 1 || found[1] != 1) return fail(GW_ERR_INVALID, "the map must hold exactly one '1' and one '2'");

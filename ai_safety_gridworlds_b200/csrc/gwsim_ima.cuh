@@ -230,10 +230,16 @@ __device__ __forceinline__ void ima_play(const ImaCfg& c, const uint8_t* __restr
   s.frame += 1;
   ImaAgent me = a ? s.ag[1] : s.ag[0];
   const int32_t other_pos = a ? s.ag[0].pos : s.ag[1].pos;
-  if (action != GW_ACT_NOOP) {
+  if (c.act_mode == 2 && action >= GW_ACT_TURN_LEFT_90) {                                      /* direction mode 2: a TURN_* action turns both
+                                                                                                  directions and moves nothing (safety_game_ma.py:607-640) */
+    const int rel = action == GW_ACT_TURN_LEFT_90 ? GW_ACT_LEFT : action == GW_ACT_TURN_RIGHT_90 ? GW_ACT_RIGHT : GW_ACT_DOWN;
+    me.adir = ima_relative(rel, me.adir);
+    if (c.obs_mode == 2) me.odir = ima_relative(rel, me.odir);
+    IMA_ADD(fr, GW_ISL_E_MOVEMENT, 1.0);                                                       /* any step but NOOP pays it (:568-572) */
+  } else if (action != GW_ACT_NOOP) {
     if (c.obs_mode == 1 && c.act_mode == 1) me.odir = ima_relative(action, me.odir);           /* AgentSprite.update (:698-705) */
     int dir;
-    if (c.act_mode == 1) dir = ima_relative(action, me.adir);
+    if (c.act_mode >= 1) dir = ima_relative(action, me.adir);
     else dir = action == GW_ACT_LEFT ? GW_DIR_LEFT : action == GW_ACT_RIGHT ? GW_DIR_RIGHT : action == GW_ACT_UP ? GW_DIR_UP : GW_DIR_DOWN;
     const int dr = dir == GW_DIR_UP ? -1 : dir == GW_DIR_DOWN ? 1 : 0, dc = dir == GW_DIR_LEFT ? -1 : dir == GW_DIR_RIGHT ? 1 : 0;
     const int nr = me.pos / c.width + dr, nc = me.pos % c.width + dc;

@@ -106,8 +106,10 @@ def compile_spec(autoreset_mode: int = _abi.GW_AUTORESET_NEXT_STEP, **kwargs) ->
     if radius != 2 and list(radius if isinstance(radius, (list, tuple)) else []) != [2, 2, 2, 2]:
         raise NotImplementedError("the CUDA backend is built for observation_radius [2, 2, 2, 2] (5x5 agent views)")
     for mode in ("observation_direction_mode", "action_direction_mode"):
-        if flags[mode] not in (0, 1):
-            raise NotImplementedError("%s 2 (separate turning actions) is not built" % mode)
+        if flags[mode] not in (0, 1, 2):
+            raise ValueError("%s must be 0, 1 or 2" % mode)
+    if (flags["observation_direction_mode"] == 2) != (flags["action_direction_mode"] == 2):
+        raise NotImplementedError("direction mode 2 (separate turning actions) is built for observation and action directions together")
     if flags["map_randomization_frequency"] not in (0, 1, 2, 3):
         raise ValueError("map_randomization_frequency")                       # safety_game_mo_base.py:979
     level_art = art = LEVELS[level]
@@ -217,4 +219,6 @@ def compile_spec(autoreset_mode: int = _abi.GW_AUTORESET_NEXT_STEP, **kwargs) ->
         cfg.metric_slots[i] = _METRIC_SLOT[n]
 
     action_range = (0, 4) if flags["noops"] else (1, 4)
+    if flags["action_direction_mode"] == 2:                                  # TURN_LEFT_90 .. TURN_RIGHT_180 (:944-945)
+        action_range = (action_range[0], 8)
     return EnvSpec(NAME, cfg, list(art), height, width, keys, layer_order, metric_names, value_mapping, action_range, flags)

@@ -156,6 +156,15 @@ static void resource_update(const IOracle* o, const IEnv* e, uint8_t chr, double
   }
 }
 
+/* direction mode 2 (safety_game_ma.py:607-640, :672-706, :734-764): only the TURN_* actions change a direction */
+static int turned(int action, int dir) {
+  static const int opposite[4] = {GW_DIR_RIGHT, GW_DIR_LEFT, GW_DIR_DOWN, GW_DIR_UP};
+  if (action == GW_ACT_TURN_LEFT_90) return relative_to_absolute(GW_ACT_LEFT, dir);
+  if (action == GW_ACT_TURN_RIGHT_90) return relative_to_absolute(GW_ACT_RIGHT, dir);
+  if (action == GW_ACT_TURN_LEFT_180 || action == GW_ACT_TURN_RIGHT_180) return opposite[dir];
+  return dir;
+}
+
 /* One Engine.play({agent: action}) */
 static void play(const IOracle* o, IEnv* e, int a, int action, double r[NA][MAXR]) {
   const GwConfig* c = &o->cfg;
@@ -164,10 +173,12 @@ static void play(const IOracle* o, IEnv* e, int a, int action, double r[NA][MAXR
   e->frame += 1;
   /* AgentSprite.update (:698-712): the observation direction turns first (safety_game_ma.py:640-698) */
   if (action != GW_ACT_NOOP && obs_mode == 1 && act_mode == 1) e->odir[a] = relative_to_absolute(action, e->odir[a]);
+  if (obs_mode == 2) e->odir[a] = turned(action, e->odir[a]);
   /* AgentSafetySprite.update (safety_game_ma.py:769-809) */
-  if (action != GW_ACT_NOOP) {
+  if (act_mode == 2 && action >= GW_ACT_TURN_LEFT_90) e->adir[a] = turned(action, e->adir[a]);     /* a turn moves nothing (:547-548) */
+  else if (action != GW_ACT_NOOP) {
     int dir;
-    if (act_mode == 1) dir = relative_to_absolute(action, e->adir[a]);
+    if (act_mode >= 1) dir = relative_to_absolute(action, e->adir[a]);
     else dir = action == GW_ACT_LEFT ? GW_DIR_LEFT : action == GW_ACT_RIGHT ? GW_DIR_RIGHT : action == GW_ACT_UP ? GW_DIR_UP : GW_DIR_DOWN;
     const int dr = dir == GW_DIR_UP ? -1 : dir == GW_DIR_DOWN ? 1 : 0, dc = dir == GW_DIR_LEFT ? -1 : dir == GW_DIR_RIGHT ? 1 : 0;
     const int nr = e->pos[a] / c->width + dr, nc = e->pos[a] % c->width + dc;

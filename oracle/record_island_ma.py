@@ -53,6 +53,11 @@ CASES = {
     "islandma_resized_6x7_s15": dict(seed=15, steps=160, kwargs=dict(map_randomization_frequency=3, map_width=7, map_height=6, max_iterations=30)),
     "islandma_resized_7x9_once_s16": dict(seed=16, steps=120, kwargs=dict(map_randomization_frequency=1, map_width=9, map_height=7, level=8,
                                                                           penalise_oversatiation=True, max_iterations=40)),
+    # direction mode 2: TURN_* actions 5..8 turn, moves are relative to the kept direction (safety_game_ma.py:515-768)
+    "islandma_turning_actions_s17": dict(seed=17, steps=160, kwargs=dict(observation_direction_mode=2, action_direction_mode=2)),
+    "islandma_turning_actions_level4_s18": dict(seed=18, steps=160, kwargs=dict(observation_direction_mode=2, action_direction_mode=2, level=4,
+                                                                               penalise_oversatiation=True, sustainability_challenge=True,
+                                                                               map_randomization_frequency=3, max_iterations=40)),
     "islandma_level2_s11": dict(seed=11, steps=120, kwargs=dict(level=2, penalise_oversatiation=True, thirst_hunger_death=True,
                                                                  sustainability_challenge=True, max_iterations=60)),
 }
@@ -188,7 +193,7 @@ def _worker(name):
     hook_rng()
     snapshot(obs, None, None, infos, True)
     rng = np.random.default_rng(9000 + case["seed"])
-    lo, hi = (0, 4)
+    lo, hi = (0, 8) if case["kwargs"].get("action_direction_mode") == 2 else (0, 4)
     actions, orders = [], []
     for t in range(case["steps"]):
         if not env.agents:                       # every agent is done: the reference needs a reset()

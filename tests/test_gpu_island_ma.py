@@ -50,6 +50,7 @@ def test_cuda_replays_island_ma_reference_trace(name):
     (dict(penalise_oversatiation=True, use_satiation_proportional_reward=True, level=10), 0, 1000),
     (dict(level=4, max_iterations=30, observation_direction_mode=0), 1, 777),
     (dict(level=0, action_direction_mode=0, observation_direction_mode=0, randomize_agent_actions_order=False), 1, 96),
+    (dict(level=6, action_direction_mode=2, observation_direction_mode=2, penalise_oversatiation=True), 1, 1500 + 3),   # TURN_* actions 5..8
 ])
 def test_island_ma_matches_oracle_with_philox_order(kwargs, mode, n, oracle_lib):
     from ai_safety_gridworlds_b200 import IslandMaVectorEnv, make_spec
@@ -63,7 +64,7 @@ def test_island_ma_matches_oracle_with_philox_order(kwargs, mode, n, oracle_lib)
     run = np.zeros((n, 2, R))                     # episode return so far, rebuilt from the oracle's reward rows
     want = dict(env_steps=0, episodes=0, length_sum=0, agent_finishes=0, ret=np.zeros((2, R)))
     for t in range(80):
-        a = rng.integers(0, 5, size=(n, 2)).astype(np.int32)
+        a = rng.integers(0, 9 if kwargs.get("action_direction_mode") == 2 else 5, size=(n, 2)).astype(np.int32)
         # a call that only restarts a finished game (GW_AUTORESET_NEXT_STEP) plays no step
         want["env_steps"] += int((~(orc.step_type >= 2).all(axis=1)).sum()) if (t and mode == 0) else n
         env.step(torch.from_numpy(a).to(env.device))
