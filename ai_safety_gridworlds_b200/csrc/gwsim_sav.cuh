@@ -372,17 +372,14 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, SUST ? 4 : 8) gw_sav_kernel(co
   __shared__ __align__(16) SavCfg c;
   __shared__ __align__(16) SavState s_state[SAV_WARPS];
   __shared__ __align__(16) uint8_t s_art[SAV_WARPS][GW_SAV_MAX_CELLS];
-  __shared__ __align__(16) uint8_t s_prim[SAV_WARPS][GW_SAV_MAX_CELLS];    /* per cell: layer of what the map shows there, 255 = none */
-  __shared__ __align__(16) uint8_t s_sec[SAV_WARPS][GW_SAV_MAX_CELLS];     /* per cell: layer of the agent standing there, 255 = none */
-  __shared__ __align__(16) uint8_t s_ter[SAV_WARPS][GW_SAV_MAX_CELLS];     /* per cell: the predator layer if one stands there, 255 = none */
-  __shared__ __align__(16) uint8_t s_vter[SAV_WARPS][SAV_VPITCH];
+  __shared__ __align__(16) uint16_t s_cmask[SAV_WARPS][GW_SAV_MAX_CELLS];  /* per cell: bit l = layer l shows something there */
   __shared__ __align__(16) uint8_t s_bchr[SAV_WARPS][GW_SAV_MAX_CELLS];    /* per cell: the rendered character */
-  __shared__ __align__(16) uint8_t s_vprim[SAV_WARPS][SAV_VPITCH];         /* the same three for the cells of the current agent's view */
-  __shared__ __align__(16) uint8_t s_vsec[SAV_WARPS][SAV_VPITCH];
+  __shared__ __align__(16) uint16_t s_vmask[SAV_WARPS][SAV_VPITCH];        /* the same two for the cells of the current agent's view */
   __shared__ __align__(16) uint8_t s_vchr[SAV_WARPS][SAV_VPITCH];
   __shared__ float s_out[SAV_WARPS][2][SAV_MAXR];
   __shared__ int32_t s_flag[SAV_WARPS][4];                                   /* out step types [2], "obs only" flag */
-  __shared__ uint8_t s_vi[SAV_VPITCH], s_vj[SAV_VPITCH];                     /* view cell -> (row, column): no division per cell */
+  __shared__ uint16_t s_vmap[4][SAV_VPITCH];   /* [observation direction][view cell] -> source (row | column << 8) inside the crop:
+                                                  np.rot90 as a table, no division and no branch per cell */
   {
     const uint32_t words = (uint32_t)(sizeof(SavCfg) / 4);
     const uint32_t* src = reinterpret_cast<const uint32_t*>(a.cfg);
@@ -390,7 +387,11 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, SUST ? 4 : 8) gw_sav_kernel(co
   }
   for (int ij = (int)threadIdx.x; ij < SAV_VPITCH; ij += (int)blockDim.x) {
     const int v = 2 * a.cfg->radius + 1;
-    s_vi[ij] = (uint8_t)(ij / v); s_vj[ij] = (uint8_t)(ij % v);
+    const int i = ij / v, j = ij % v;                                        /* out[i][j] = in[si][sj] */
+    s_vmap[GW_DIR_UP][ij] = (uint16_t)(i | (j << 8));
+    s_vmap[GW_DIR_DOWN][ij] = (uint16_t)(((v - 1 - i) & 255) | (((v - 1 - j) & 255) << 8));
+    s_vmap[GW_DIR_LEFT][ij] = (uint16_t)(((v - 1 - j) & 255) | (i << 8));
+    s_vmap[GW_DIR_RIGHT][ij] = (uint16_t)(j | (((v - 1 - i) & 255) << 8));
   }
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -487,46 +488,39 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, SUST ? 4 : 8) gw_sav_kernel(co
       if (SUST) for (int p = (int)lane; p < cells; p += 32) a.live[env * cells + p] = art[p];
     }
     /* Every row of the output tensors is padded to a multiple of 16 bytes (GW_SAV_PITCH), so that a lane produces and stores 16
-     * bytes at a time: a cell's layers are described by two bytes -- the layer of what the map shows there (none if it is a gap
-     * an agent stands on) and the layer of the agent standing there (none otherwise) -- and 16 cells of a layer plane are
-     * two byte-wise compares of 16 such codes against the layer index. */
+     * bytes at a time.  A cell's layers are one 16-bit mask -- the layer of what the map shows there (none if it is a gap
+     * something stands on), the layer of the agent and the predator layer -- and 4 cells of layer plane l are two shifts, two
+     * ANDs and one byte permute of two words holding four masks. */
     const int pos0 = s.pos[0], pos1 = A > 1 ? (int)s.pos[1] : -1;
     const int cpitch = (cells + 15) & ~15, vpitch = (V2 + 15) & ~15;
-    uint8_t* prim = s_prim[warp];
-    uint8_t* sec = s_sec[warp];
+    uint16_t* cmask = s_cmask[warp];
     uint8_t* bchr = s_bchr[warp];
-    uint8_t* ter = s_ter[warp];
     constexpr bool has_pred = PRED;
+    const uint32_t abit0 = c.agent_layer[0] >= 0 ? 1u << c.agent_layer[0] : 0u, abit1 = c.agent_layer[1] >= 0 ? 1u << c.agent_layer[1] : 0u;
+    const uint32_t pbit = c.pred_layer >= 0 ? 1u << c.pred_layer : 0u, wbit = 1u << c.wall_layer;
     for (int p = (int)lane; p < cpitch; p += 32) {
-      uint8_t pr = 255, se = 255, te = 255, ch = 0;
+      uint32_t mk = 0;
+      uint8_t ch = 0;
       if (p < cells) {
         uint8_t m = art[p];
         if (m == 'P' || m == '0' || m == '1') m = ' ';             /* start tiles: sprites and the predator drape are state */
         const int ly = c.layer_of[m & 127];
         const bool a0 = p == pos0, a1 = p == pos1, pd = has_pred && sav_pred_here(s, p);
-        pr = (uint8_t)((ly == c.gap_layer && (a0 || a1 || pd)) ? 255 : ly);
-        se = a0 ? (uint8_t)c.agent_layer[0] : a1 ? (uint8_t)c.agent_layer[1] : (uint8_t)255;
-        te = pd ? (uint8_t)c.pred_layer : (uint8_t)255;
+        if (ly >= 0 && !(ly == c.gap_layer && (a0 || a1 || pd))) mk = 1u << ly;
+        mk |= a0 ? abit0 : a1 ? abit1 : 0u;
+        if (pd) mk |= pbit;
         /* z-order W, P, D, F, d, f, G, S, agents (:643-645): a predator hides water and bare ground only */
         ch = a0 ? (uint8_t)'0' : a1 ? (uint8_t)'1' : (pd && (m == ' ' || m == 'W' || m == 'U')) ? (uint8_t)'P' : m;
       }
-      prim[p] = pr; sec[p] = se; ter[p] = te; bchr[p] = ch;
+      cmask[p] = (uint16_t)mk; bchr[p] = ch;
     }
     __syncwarp();
-    auto plane16 = [&](const uint8_t* pr, const uint8_t* se, const uint8_t* te, int l, int chunk) -> uint4 {
-      const uint4 a4 = *reinterpret_cast<const uint4*>(pr + 16 * chunk), b4 = *reinterpret_cast<const uint4*>(se + 16 * chunk);
-      const uint32_t lv = (uint32_t)l * 0x01010101u;
-      uint4 o;
-      o.x = __vcmpeq4(a4.x, lv) | __vcmpeq4(b4.x, lv);
-      o.y = __vcmpeq4(a4.y, lv) | __vcmpeq4(b4.y, lv);
-      o.z = __vcmpeq4(a4.z, lv) | __vcmpeq4(b4.z, lv);
-      o.w = __vcmpeq4(a4.w, lv) | __vcmpeq4(b4.w, lv);
-      if (has_pred && l == c.pred_layer) {                    /* the third code only ever names the predator layer */
-        const uint4 c4 = *reinterpret_cast<const uint4*>(te + 16 * chunk);
-        o.x |= __vcmpeq4(c4.x, lv); o.y |= __vcmpeq4(c4.y, lv); o.z |= __vcmpeq4(c4.z, lv); o.w |= __vcmpeq4(c4.w, lv);
-      }
-      o.x &= 0x01010101u; o.y &= 0x01010101u; o.z &= 0x01010101u; o.w &= 0x01010101u;
-      return o;
+    auto plane16 = [&](const uint16_t* mk, int l, int chunk) -> uint4 {      /* 16 cells of layer plane l */
+      const uint4 m0 = *reinterpret_cast<const uint4*>(mk + 16 * chunk), m1 = *reinterpret_cast<const uint4*>(mk + 16 * chunk + 8);
+      auto four = [&](uint32_t w01, uint32_t w23) -> uint32_t {
+        return __byte_perm((w01 >> l) & 0x00010001u, (w23 >> l) & 0x00010001u, 0x6420);
+      };
+      return make_uint4(four(m0.x, m0.y), four(m0.z, m0.w), four(m1.x, m1.y), four(m1.z, m1.w));
     };
     const int cch = cpitch >> 4, vch = vpitch >> 4;
     if (a.board) {
@@ -535,32 +529,31 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, SUST ? 4 : 8) gw_sav_kernel(co
     }
     if (a.cube) {
       uint4* dst = reinterpret_cast<uint4*>(a.cube + env * (int64_t)L * cpitch);
-      for (int i = (int)lane; i < L * cch; i += 32) st_stream(dst + i, plane16(prim, sec, ter, i / cch, i % cch));
+      const uint32_t inv = 65536u / (uint32_t)cch + 1u;             /* i / cch for i < 256 without a division per piece */
+      for (int i = (int)lane; i < L * cch; i += 32) {
+        const int l = (int)(((uint32_t)i * inv) >> 16);
+        st_stream(dst + i, plane16(cmask, l, i - l * cch));
+      }
     }
     if (a.crop || a.lcrop) {
-      uint8_t* vprim = s_vprim[warp];
-      uint8_t* vsec = s_vsec[warp];
+      uint16_t* vmask = s_vmask[warp];
       uint8_t* vchr = s_vchr[warp];
-      uint8_t* vter = s_vter[warp];
       for (int ag = 0; ag < A; ++ag) {                       /* the columns of an agent the game does not have are never written */
         const int pa = ag == 0 ? pos0 : pos1;
         const int r0 = pa / c.width - c.radius, c0 = pa % c.width - c.radius;
         const int dir = c.obs_mode ? (s.flags[ag] >> 2) & 3 : GW_DIR_UP;
+        const uint16_t* vmap = s_vmap[dir];
         /* get_agent_perspective (safety_game_moma.py:1996-2101): crop, '#' outside the board, np.rot90 by the observation direction */
         for (int ij = (int)lane; ij < vpitch; ij += 32) {
-          uint8_t pr = 255, se = 255, te = 255, ch = 0;
+          uint32_t mk = 0;
+          uint8_t ch = 0;
           if (ij < V2) {
-            const int i = s_vi[ij], j = s_vj[ij];
-            int si = i, sj = j;
-            if (dir == GW_DIR_DOWN) { si = V - 1 - i; sj = V - 1 - j; }
-            else if (dir == GW_DIR_LEFT) { si = V - 1 - j; sj = i; }
-            else if (dir == GW_DIR_RIGHT) { si = j; sj = V - 1 - i; }
-            const int r = r0 + si, cc = c0 + sj;
-            if (r >= 0 && r < c.height && cc >= 0 && cc < c.width) { const int p = r * c.width + cc; pr = prim[p]; se = sec[p]; ch = bchr[p]; if (has_pred) te = ter[p]; }
-            else { pr = (uint8_t)c.wall_layer; ch = (uint8_t)'#'; }
+            const uint32_t t = vmap[ij];
+            const int r = r0 + (int)(t & 255u), cc = c0 + (int)(t >> 8);
+            if ((unsigned)r < (unsigned)c.height && (unsigned)cc < (unsigned)c.width) { const int p = r * c.width + cc; mk = cmask[p]; ch = bchr[p]; }
+            else { mk = wbit; ch = (uint8_t)'#'; }
           }
-          vprim[ij] = pr; vsec[ij] = se; vchr[ij] = ch;
-          if (has_pred) vter[ij] = te;
+          vmask[ij] = (uint16_t)mk; vchr[ij] = ch;
         }
         __syncwarp();
         if (a.crop) {
@@ -570,8 +563,8 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, SUST ? 4 : 8) gw_sav_kernel(co
         if (a.lcrop) {
           uint4* dst = reinterpret_cast<uint4*>(a.lcrop + (env * 2 + ag) * (int64_t)L * vpitch);
           if (vch <= 32) {                                 /* one 16-byte piece per lane and layer: no index arithmetic */
-            if ((int)lane < vch) for (int l = 0; l < L; ++l) st_stream(dst + l * vch + lane, plane16(vprim, vsec, vter, l, (int)lane));
-          } else for (int i = (int)lane; i < L * vch; i += 32) st_stream(dst + i, plane16(vprim, vsec, vter, i / vch, i % vch));
+            if ((int)lane < vch) for (int l = 0; l < L; ++l) st_stream(dst + l * vch + lane, plane16(vmask, l, (int)lane));
+          } else for (int i = (int)lane; i < L * vch; i += 32) st_stream(dst + i, plane16(vmask, i / vch, i % vch));
         }
         __syncwarp();
       }
