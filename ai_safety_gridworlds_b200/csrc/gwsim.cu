@@ -2688,7 +2688,7 @@ static int sav_launch(GwSavHandle h, SavArgs& a, void* state, const GwSavObs* ob
   a.seed = h->seed; a.call_no = ++h->call_no; a.env_index_base = h->env_index_base;
   a.map_shuffle = h->map_mode;
   CUDA_TRY(cudaSetDevice(h->device));
-  int64_t grid = (h->n + SAV_WARPS - 1) / SAV_WARPS;
+  int64_t grid = ((h->n + SAV_EPW - 1) / SAV_EPW + SAV_WARPS - 1) / SAV_WARPS;     /* a warp takes SAV_EPW environments per pass */
   if (grid > h->grid_max) grid = h->grid_max;
   sav_dispatch(h->cfg, [&](auto kernel) { kernel<<<(unsigned)grid, SAV_WARPS * 32, 0, stream>>>(a); });
   CUDA_TRY(cudaGetLastError());

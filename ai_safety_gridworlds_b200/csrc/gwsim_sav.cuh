@@ -20,6 +20,7 @@
 #include "../../include/gwsim_sav.h"
 
 #define SAV_WARPS 4
+#define SAV_EPW 4                        /* environments per warp and pass: lanes 0, 8, 16, 24 play one game each */
 #define SAV_VPITCH 448                   /* (2 * GW_SAV_MAX_RADIUS + 1)^2 = 441 rounded up to 16 */
 #define SAV_MAXR 14                      /* 2 * R must fit the raw statistics vector (GW_MA_STATS_LEN - 4) */
 
@@ -370,14 +371,14 @@ __device__ __forceinline__ void sav_new_game(const SavCfg& c, const SavArgs& a, 
 template <bool PRED, bool SUST>
 __global__ void __launch_bounds__(SAV_WARPS * 32, SUST ? 4 : 8) gw_sav_kernel(const __grid_constant__ SavArgs a) {
   __shared__ __align__(16) SavCfg c;
-  __shared__ __align__(16) SavState s_state[SAV_WARPS];
-  __shared__ __align__(16) uint8_t s_art[SAV_WARPS][GW_SAV_MAX_CELLS];
+  __shared__ __align__(16) SavState s_state[SAV_WARPS][SAV_EPW];
+  __shared__ __align__(16) uint8_t s_art[SAV_WARPS][SAV_EPW * GW_SAV_MAX_CELLS];   /* the pass's maps back to back, `cells` bytes each */
   __shared__ __align__(16) uint16_t s_cmask[SAV_WARPS][GW_SAV_MAX_CELLS];  /* per cell: bit l = layer l shows something there */
   __shared__ __align__(16) uint8_t s_bchr[SAV_WARPS][GW_SAV_MAX_CELLS];    /* per cell: the rendered character */
   __shared__ __align__(16) uint16_t s_vmask[SAV_WARPS][SAV_VPITCH];        /* the same two for the cells of the current agent's view */
   __shared__ __align__(16) uint8_t s_vchr[SAV_WARPS][SAV_VPITCH];
-  __shared__ float s_out[SAV_WARPS][2][SAV_MAXR];
-  __shared__ int32_t s_flag[SAV_WARPS][4];                                   /* out step types [2], "obs only" flag */
+  __shared__ float s_out[SAV_WARPS][SAV_EPW][2][SAV_MAXR];
+  __shared__ int32_t s_flag[SAV_WARPS][SAV_EPW][4];                                   /* out step types [2], "obs only" flag */
   __shared__ uint16_t s_vmap[4][SAV_VPITCH];   /* [observation direction][view cell] -> source (row | column << 8) inside the crop:
                                                   np.rot90 as a table, no division and no branch per cell */
   {
@@ -395,19 +396,32 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, SUST ? 4 : 8) gw_sav_kernel(co
   }
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  SavState& s = s_state[warp];
-  uint8_t* art = s_art[warp];
   const int cells = c.cells, L = c.n_layers, V = c.view, V2 = V * V, R = c.n_rewards, A = c.n_agents;
-  for (int64_t env = (int64_t)blockIdx.x * SAV_WARPS + warp; env < a.n; env += (int64_t)gridDim.x * SAV_WARPS) {
-    /* 1. state and map into shared memory (a register prefetch of the next environment was tried: it spilled the renderer) */
-    if (lane < GW_SAV_STATE_BYTES / 16) reinterpret_cast<uint4*>(&s)[lane] = ld_state(a.state + env * (GW_SAV_STATE_BYTES / 16) + lane);
+  /* A warp takes SAV_EPW consecutive environments per pass: the game logic is a serial chain of dependent latencies, so four
+   * lanes play four games side by side (one instruction stream where their control flow agrees); the lanes then render the
+   * four games one after the other. */
+  for (int64_t grp = (int64_t)blockIdx.x * SAV_WARPS + warp; grp * SAV_EPW < a.n; grp += (int64_t)gridDim.x * SAV_WARPS) {
+    const int64_t base = grp * SAV_EPW;
+    const int ne = (int)(a.n - base < (int64_t)SAV_EPW ? a.n - base : (int64_t)SAV_EPW);
+    /* 1. states and maps into shared memory: both are contiguous over consecutive environments */
     {
-      const uint8_t* src = (SUST ? a.live : a.maps) + env * cells;
-      for (int p = (int)lane; p < cells; p += 32) art[p] = src[p];
+      uint4* dstw = reinterpret_cast<uint4*>(&s_state[warp][0]);
+      const uint4* srcw = a.state + base * (GW_SAV_STATE_BYTES / 16);
+      for (int i = (int)lane; i < ne * (GW_SAV_STATE_BYTES / 16); i += 32) dstw[i] = ld_state(srcw + i);
+      const uint8_t* src = (SUST ? a.live : a.maps) + base * cells;          /* base is a multiple of 4: word aligned */
+      const int bytes = ne * cells, words = bytes >> 2;
+      for (int i = (int)lane; i < words; i += 32) reinterpret_cast<uint32_t*>(s_art[warp])[i] = reinterpret_cast<const uint32_t*>(src)[i];
+      for (int i = 4 * words + (int)lane; i < bytes; i += 32) s_art[warp][i] = src[i];
     }
     __syncwarp();
-    /* 2. the game logic, lane 0 */
-    if (lane == 0) {
+    /* 2. the game logic, one lane per environment of the pass */
+    if ((lane & (32 / SAV_EPW - 1)) == 0 && (int)(lane / (32 / SAV_EPW)) < ne) {
+      const int slot = (int)(lane / (32 / SAV_EPW));
+      const int64_t env = base + slot;
+      SavState& s = s_state[warp][slot];
+      uint8_t* art = s_art[warp] + slot * cells;
+      int32_t* flag = s_flag[warp][slot];
+      float (*outr)[SAV_MAXR] = s_out[warp][slot];
       SavRun w;
       w.draw_k = 0;
       if (SUST) for (int k = 0; k < 4; ++k) w.av[k] = a.avail[env * 4 + k];
@@ -467,24 +481,29 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, SUST ? 4 : 8) gw_sav_kernel(co
           }
         }
       }
-      s_flag[warp][0] = fresh ? (int32_t)(s.flags[0] >> 5) : w.st[0];
-      s_flag[warp][1] = fresh ? (int32_t)(s.flags[1] >> 5) : w.st[1];
-      s_flag[warp][2] = wrote ? 1 : 0;
-      for (int k = 0; k < 2; ++k) for (int d = 0; d < R; ++d) s_out[warp][k][d] = fresh ? 0.0f : (float)w.r[k][d];
+      flag[0] = fresh ? (int32_t)(s.flags[0] >> 5) : w.st[0];
+      flag[1] = fresh ? (int32_t)(s.flags[1] >> 5) : w.st[1];
+      flag[2] = wrote ? 1 : 0;
+      for (int k = 0; k < 2; ++k) for (int d = 0; d < R; ++d) outr[k][d] = fresh ? 0.0f : (float)w.r[k][d];
       /* a game that ended inside this call restarts right away under GW_AUTORESET_SAME_STEP: the observation is the new game's */
       if (!a.is_reset && !fresh && w.st[0] >= 2 && w.st[1] >= 2 && c.autoreset == GW_AUTORESET_SAME_STEP) sav_new_game<SUST>(c, a, env, s, art, false, w.av);
       if (SUST && wrote) for (int k = 0; k < 4; ++k) a.avail[env * 4 + k] = w.av[k];
     }
     __syncwarp();
-    /* 3. outputs */
-    const bool wrote = s_flag[warp][2] != 0;
+    /* 3. outputs, one environment of the pass after the other */
+    for (int slot = 0; slot < ne; ++slot) {
+    const int64_t env = base + slot;
+    SavState& s = s_state[warp][slot];
+    const uint8_t* art = s_art[warp] + slot * cells;
+    const int32_t* flag = s_flag[warp][slot];
+    const bool wrote = flag[2] != 0;
     if (wrote) {
       if (lane < GW_SAV_STATE_BYTES / 16) st_state(a.state + env * (GW_SAV_STATE_BYTES / 16) + lane, reinterpret_cast<const uint4*>(&s)[lane]);
       if (lane < 2) {
-        if (a.terminated) a.terminated[2 * env + lane] = (uint8_t)(s_flag[warp][lane] >= 2);
-        if (a.step_type) a.step_type[2 * env + lane] = (uint8_t)s_flag[warp][lane];
+        if (a.terminated) a.terminated[2 * env + lane] = (uint8_t)(flag[lane] >= 2);
+        if (a.step_type) a.step_type[2 * env + lane] = (uint8_t)flag[lane];
       }
-      if (a.reward) for (int i = (int)lane; i < 2 * R; i += 32) a.reward[env * 2 * R + i] = s_out[warp][i / R][i % R];
+      if (a.reward) for (int i = (int)lane; i < 2 * R; i += 32) a.reward[env * 2 * R + i] = s_out[warp][slot][i / R][i % R];
       if (SUST) for (int p = (int)lane; p < cells; p += 32) a.live[env * cells + p] = art[p];
     }
     /* Every row of the output tensors is padded to a multiple of 16 bytes (GW_SAV_PITCH), so that a lane produces and stores 16
@@ -570,6 +589,7 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, SUST ? 4 : 8) gw_sav_kernel(co
       }
     }
     __syncwarp();
+    }
   }
 }
 
