@@ -377,7 +377,6 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, SUST ? 4 : 8) gw_sav_kernel(co
   __shared__ __align__(16) uint8_t s_bchr[SAV_WARPS][GW_SAV_MAX_CELLS];    /* per cell: the rendered character */
   __shared__ __align__(16) uint16_t s_vmask[SAV_WARPS][SAV_VPITCH];        /* the same two for the cells of the current agent's view */
   __shared__ __align__(16) uint8_t s_vchr[SAV_WARPS][SAV_VPITCH];
-  __shared__ float s_out[SAV_WARPS][SAV_EPW][2][SAV_MAXR];
   __shared__ int32_t s_flag[SAV_WARPS][SAV_EPW][4];                                   /* out step types [2], "obs only" flag */
   __shared__ uint16_t s_vmap[4][SAV_VPITCH];   /* [observation direction][view cell] -> source (row | column << 8) inside the crop:
                                                   np.rot90 as a table, no division and no branch per cell */
@@ -400,7 +399,10 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, SUST ? 4 : 8) gw_sav_kernel(co
   /* A warp takes SAV_EPW consecutive environments per pass: the game logic is a serial chain of dependent latencies, so SAV_EPW
    * lanes play that many games side by side (one instruction stream where their control flow agrees); the lanes then render
    * the games one after the other.  Measured at 131,072 environments: 1 per pass 0.64 ms, 4 per pass 0.45 ms, 8 per pass
-   * 0.41 ms (34.9 KB of shared memory per CTA: 6 CTAs per SM instead of 8); 16 do not fit the 48 KB of static shared memory. */
+   * 0.41 ms (34.9 KB of shared memory per CTA: 6 CTAs per SM instead of 8), 0.38 ms with the reward rows written straight to
+   * global memory (31.4 KB, 7 CTAs); 16 per pass do not fit the 48 KB of static shared memory.  Trimming to 28.0 KB for 8 CTAs
+   * (configuration without its layout, one view-cell table + a per-direction transform, packed flags) was correct but not
+   * faster (0.39 ms): dropped. */
   for (int64_t grp = (int64_t)blockIdx.x * SAV_WARPS + warp; grp * SAV_EPW < a.n; grp += (int64_t)gridDim.x * SAV_WARPS) {
     const int64_t base = grp * SAV_EPW;
     const int ne = (int)(a.n - base < (int64_t)SAV_EPW ? a.n - base : (int64_t)SAV_EPW);
@@ -422,7 +424,6 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, SUST ? 4 : 8) gw_sav_kernel(co
       SavState& s = s_state[warp][slot];
       uint8_t* art = s_art[warp] + slot * cells;
       int32_t* flag = s_flag[warp][slot];
-      float (*outr)[SAV_MAXR] = s_out[warp][slot];
       SavRun w;
       w.draw_k = 0;
       if (SUST) for (int k = 0; k < 4; ++k) w.av[k] = a.avail[env * 4 + k];
@@ -485,7 +486,8 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, SUST ? 4 : 8) gw_sav_kernel(co
       flag[0] = fresh ? (int32_t)(s.flags[0] >> 5) : w.st[0];
       flag[1] = fresh ? (int32_t)(s.flags[1] >> 5) : w.st[1];
       flag[2] = wrote ? 1 : 0;
-      for (int k = 0; k < 2; ++k) for (int d = 0; d < R; ++d) outr[k][d] = fresh ? 0.0f : (float)w.r[k][d];
+      /* the reward rows go straight to global memory from the playing lane (a staging buffer in shared memory cost a CTA per SM) */
+      if (wrote && a.reward) for (int k = 0; k < 2; ++k) for (int d = 0; d < R; ++d) a.reward[(env * 2 + k) * R + d] = fresh ? 0.0f : (float)w.r[k][d];
       /* a game that ended inside this call restarts right away under GW_AUTORESET_SAME_STEP: the observation is the new game's */
       if (!a.is_reset && !fresh && w.st[0] >= 2 && w.st[1] >= 2 && c.autoreset == GW_AUTORESET_SAME_STEP) sav_new_game<SUST>(c, a, env, s, art, false, w.av);
       if (SUST && wrote) for (int k = 0; k < 4; ++k) a.avail[env * 4 + k] = w.av[k];
@@ -504,7 +506,6 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, SUST ? 4 : 8) gw_sav_kernel(co
         if (a.terminated) a.terminated[2 * env + lane] = (uint8_t)(flag[lane] >= 2);
         if (a.step_type) a.step_type[2 * env + lane] = (uint8_t)flag[lane];
       }
-      if (a.reward) for (int i = (int)lane; i < 2 * R; i += 32) a.reward[env * 2 * R + i] = s_out[warp][slot][i / R][i % R];
       if (SUST) for (int p = (int)lane; p < cells; p += 32) a.live[env * cells + p] = art[p];
     }
     /* Every row of the output tensors is padded to a multiple of 16 bytes (GW_SAV_PITCH), so that a lane produces and stores 16
