@@ -536,12 +536,14 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, SUST ? 4 : 8) gw_sav_kernel(co
       cmask[p] = (uint16_t)mk; bchr[p] = ch;
     }
     __syncwarp();
-    auto plane16 = [&](const uint16_t* mk, int l, int chunk) -> uint4 {      /* 16 cells of layer plane l */
-      const uint4 m0 = *reinterpret_cast<const uint4*>(mk + 16 * chunk), m1 = *reinterpret_cast<const uint4*>(mk + 16 * chunk + 8);
+    auto plane16m = [&](const uint4& m0, const uint4& m1, int l) -> uint4 {    /* 16 cells of layer plane l from their 16 masks */
       auto four = [&](uint32_t w01, uint32_t w23) -> uint32_t {
         return __byte_perm((w01 >> l) & 0x00010001u, (w23 >> l) & 0x00010001u, 0x6420);
       };
       return make_uint4(four(m0.x, m0.y), four(m0.z, m0.w), four(m1.x, m1.y), four(m1.z, m1.w));
+    };
+    auto plane16 = [&](const uint16_t* mk, int l, int chunk) -> uint4 {
+      return plane16m(*reinterpret_cast<const uint4*>(mk + 16 * chunk), *reinterpret_cast<const uint4*>(mk + 16 * chunk + 8), l);
     };
     const int cch = cpitch >> 4, vch = vpitch >> 4;
     if (a.board) {
@@ -584,7 +586,11 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, SUST ? 4 : 8) gw_sav_kernel(co
         if (a.lcrop) {
           uint4* dst = reinterpret_cast<uint4*>(a.lcrop + (env * 2 + ag) * (int64_t)L * vpitch);
           if (vch <= 32) {                                 /* one 16-byte piece per lane and layer: no index arithmetic */
-            if ((int)lane < vch) for (int l = 0; l < L; ++l) st_stream(dst + l * vch + lane, plane16(vmask, l, (int)lane));
+            if ((int)lane < vch) {                         /* the lane's 16 masks are loaded once for all layers */
+              const uint4 m0 = *reinterpret_cast<const uint4*>(vmask + 16 * lane), m1 = *reinterpret_cast<const uint4*>(vmask + 16 * lane + 8);
+              uint4* out = dst + lane;
+              for (int l = 0; l < L; ++l, out += vch) st_stream(out, plane16m(m0, m1, l));
+            }
           } else for (int i = (int)lane; i < L * vch; i += 32) st_stream(dst + i, plane16(vmask, i / vch, i % vch));
         }
         __syncwarp();
