@@ -16,7 +16,7 @@ GW_STATE_WORD_BYTES = 16
 GW_STATS_LEN = 8 + GW_MAX_REWARDS
 GW_STATS_RAW_LEN = 32
 
-GW_OK, GW_ERR_INVALID, GW_ERR_CUDA, GW_ERR_NO_DEVICE = 0, 1, 2, 3
+GW_OK, GW_ERR_INVALID, GW_ERR_CUDA, GW_ERR_NO_DEVICE, GW_ERR_STATE = 0, 1, 2, 3, 4
 
 GW_ENV_ISLAND_NAVIGATION_EX = 1
 GW_ENV_BOAT_RACE_EX = 2

@@ -261,7 +261,7 @@ __device__ __forceinline__ void flush_rewards(const float* __restrict__ s_rw, fl
 enum { SC_ZERO = 0, SC_BIT = 1, SC_SMALL = 2 /* |v| < 2^17 */, SC_WIDE = 3 };
 
 __host__ __device__ constexpr int slot_class(int kind, int k) {
-  if (k == GW_RAW_ENV_STEPS || k == GW_RAW_EPISODES || (k >= GW_RAW_REASON0 && k < GW_RAW_REASON0 + 4)) return SC_BIT;
+  if (k == GW_RAW_ENV_STEPS || k == GW_RAW_EPISODES || k == GW_RAW_CORRUPT || (k >= GW_RAW_REASON0 && k < GW_RAW_REASON0 + 4)) return SC_BIT;
   if (k == GW_RAW_LENGTH_SUM) return SC_SMALL;
   if (k < GW_RAW_EVENT0) return SC_ZERO;
   const int e = k - GW_RAW_EVENT0;
@@ -770,7 +770,10 @@ __device__ __forceinline__ uint32_t step_lane(const DevCfg& c, const StepArgs& a
   const uint32_t R = (uint32_t)c.n_rewards;
   typename GameOf<KIND>::State s;
   g_unpack<KIND>(s, raw);
-  if (s.cell >= (uint32_t)c.cells) s.cell = (uint32_t)c.start_cell;   /* never index outside the board on garbage state */
+  if (s.cell >= (uint32_t)c.cells) {               /* never index outside the board on garbage state -- and say so: the count lands in */
+    s.cell = (uint32_t)c.start_cell;               /* raw statistics slot GW_RAW_CORRUPT, which makes gw_stats fail with GW_ERR_STATE  */
+    sv[GW_RAW_CORRUPT] = 1;
+  }
   const int32_t act = raw.act;
   uint32_t out_st, out_reason1;
   if (s.st == GW_STEP_LAST) {
@@ -957,7 +960,10 @@ __global__ void __launch_bounds__(GW_PBLOCK) gw_step_tma_kernel(const __grid_con
   auto claim = [&]() -> int64_t {
     unsigned long long v = 0;
     if (lane == 0) v = atomicAdd(a.claim_counter, 1ull) - a.claim_base;
-    return (int64_t)__shfl_sync(FULL, v, 0);
+    const int64_t got = (int64_t)__shfl_sync(FULL, v, 0);
+    /* a host base that ran ahead of the device counter (a launch that never ran) would underflow to a negative index:
+     * such a claim counts as "queue exhausted", never as work */
+    return got < 0 ? ((int64_t)1 << 60) : got;
   };
   int64_t group = claim();
   Raw<KIND> next;
@@ -1446,6 +1452,8 @@ static int cls_step_launch(GwHandle h, const ClsArgs& a0, cudaStream_t stream) {
   a.claim_counter = h->d_claim;
   a.claim_base = h->claim_base;
   gw_cls_step_kernel<R3><<<(unsigned)grid, GW_PBLOCK, smem, stream>>>(a, warp_bytes, value_off, reward_off);
+  { const cudaError_t le = cudaGetLastError();     /* a refused launch claims nothing: keep the host base in step */
+    if (le != cudaSuccess) return fail(GW_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(le)); }
   h->claim_base += (unsigned long long)nchunks + (unsigned long long)grid * GW_PWARPS;
   return GW_OK;
 }
@@ -1504,6 +1512,8 @@ static int launch_step_tma(GwHandle h, StepArgs& a, cudaStream_t stream) {
   a.claim_counter = h->d_claim;
   a.claim_base = h->claim_base;
   gw_step_tma_kernel<KIND><<<(unsigned)grid, GW_PBLOCK, smem, stream>>>(d, a, L);
+  { const cudaError_t le = cudaGetLastError();     /* a refused launch claims nothing: keep the host base in step */
+    if (le != cudaSuccess) return fail(GW_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(le)); }
   /* every group is claimed once and every warp makes exactly one failing claim */
   h->claim_base += (unsigned long long)((nchunks + GW_GRAB - 1) / GW_GRAB) + (unsigned long long)grid * GW_PWARPS;
   return GW_OK;
@@ -1895,6 +1905,9 @@ int gw_stats_finalize(const GwConfig* cfg, const double* raw, double* out) {
   int rc0 = validate(cfg);
   if (rc0 != GW_OK) return rc0;
   for (int i = 0; i < GW_STATS_LEN; ++i) out[i] = 0.0;
+  if (raw[GW_RAW_CORRUPT] != 0.0)
+    return fail(GW_ERR_STATE, "%.0f environment-steps found an out-of-range agent cell in the state blob (overwritten state, or a state "
+                "that belongs to another handle); those environments were played from the start cell", raw[GW_RAW_CORRUPT]);
   out[GW_STAT_ENV_STEPS] = raw[GW_RAW_ENV_STEPS];
   out[GW_STAT_EPISODES] = raw[GW_RAW_EPISODES];
   out[GW_STAT_LENGTH_SUM] = raw[GW_RAW_LENGTH_SUM];
@@ -2094,9 +2107,9 @@ static int fm_launch(GwFmHandle h, FmArgs& a, void* state, const GwFmObs* obs, c
   a.claim_counter = h->d_claim;
   a.claim_base = h->claim_base;
   a.stats = h->d_stats;
-  h->claim_base += (unsigned long long)h->n + (unsigned long long)grid * FM_WARPS;   /* every environment once + one failing claim per warp */
   gw_fm_kernel<<<(unsigned)grid, FM_WARPS * 32, 0, stream>>>(a);
-  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaGetLastError());                                /* a refused launch claims nothing: the host base stays in step */
+  h->claim_base += (unsigned long long)h->n + (unsigned long long)grid * FM_WARPS;   /* every environment once + one failing claim per warp */
   h->launches += 1;
   return GW_OK;
 }
@@ -2314,10 +2327,10 @@ static int ima_launch(GwImaHandle h, ImaArgs& a, void* state, const GwImaObs* ob
   a.claim_counter = h->d_claim;
   a.claim_base = h->claim_base;
   a.stats = h->d_stats;
-  h->claim_base += (unsigned long long)nchunks + (unsigned long long)grid * IMA_WARPS;    /* every chunk once + one failing claim per warp */
   if (pm) gw_ima_kernel<true><<<(unsigned)grid, IMA_WARPS * 32, (size_t)h->warp_bytes_pm * IMA_WARPS, stream>>>(h->dc, a);
   else gw_ima_kernel<false><<<(unsigned)grid, IMA_WARPS * 32, (size_t)h->warp_bytes * IMA_WARPS, stream>>>(h->dc, a);
-  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaGetLastError());                                /* a refused launch claims nothing: the host base stays in step */
+  h->claim_base += (unsigned long long)nchunks + (unsigned long long)grid * IMA_WARPS;    /* every chunk once + one failing claim per warp */
   h->launches += 1;
   return GW_OK;
 }

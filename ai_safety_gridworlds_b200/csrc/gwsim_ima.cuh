@@ -521,7 +521,10 @@ __global__ void __launch_bounds__(IMA_WARPS * 32, 2) gw_ima_kernel(const __grid_
   auto claim = [&]() -> int64_t {
     unsigned long long v = 0;
     if (lane == 0) v = atomicAdd(a.claim_counter, 1ull) - a.claim_base;
-    return (int64_t)__shfl_sync(FULL, v, 0);
+    const int64_t got = (int64_t)__shfl_sync(FULL, v, 0);
+    /* a host base that ran ahead of the device counter (a launch that never ran) would underflow to a negative index:
+     * such a claim counts as "queue exhausted", never as work */
+    return got < 0 ? ((int64_t)1 << 60) : got;
   };
   int64_t chunk = claim();
   ImaRaw next;

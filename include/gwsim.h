@@ -38,7 +38,8 @@ enum GwStatus {
   GW_OK = 0,
   GW_ERR_INVALID = 1,       /* bad argument / unsupported configuration */
   GW_ERR_CUDA = 2,          /* CUDA runtime error, message in gw_last_error() */
-  GW_ERR_NO_DEVICE = 3      /* no CUDA device: there is NO CPU fallback */
+  GW_ERR_NO_DEVICE = 3,     /* no CUDA device: there is NO CPU fallback */
+  GW_ERR_STATE = 4          /* the caller-owned state blob held values no step can produce (overwritten / wrong handle) */
 };
 
 enum GwEnvType {
@@ -247,6 +248,8 @@ typedef struct GwExtras {
 #define GW_STATS_RAW_LEN 32
 enum GwStatsRawSlot {
   GW_RAW_ENV_STEPS = 0, GW_RAW_EPISODES = 1, GW_RAW_LENGTH_SUM = 2, GW_RAW_REASON0 = 3, /* ..6 */
+  GW_RAW_CORRUPT = 7,         /* environment-steps whose state held an out-of-range agent cell (played from the start cell so that
+                                 nothing is indexed outside the board); non-zero makes gw_stats / gw_stats_finalize fail with GW_ERR_STATE */
   GW_RAW_EVENT0 = 8,          /* [GW_MAX_EVENTS] sum over finished episodes of the event accumulators */
   GW_RAW_SCALED0 = 24         /* [4] float sums of the satiation-proportional island events
                                  (DRINK_DEFICIENCY, DRINK_OVERSATIATION, FOOD_DEFICIENCY, FOOD_OVERSATIATION) */

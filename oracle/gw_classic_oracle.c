@@ -19,6 +19,9 @@
 
 #include "../include/gwsim.h"
 
+/* gw_oracle.c: runs fn(ctx, lo, hi) over [0, n) split across the host threads set with or_set_threads */
+void or_parallel_for(int64_t n, void (*fn)(void* ctx, int64_t lo, int64_t hi), void* ctx);
+
 #define MAXC GW_MAX_CELLS
 
 typedef struct {
@@ -692,12 +695,19 @@ void orc_reset(void* h, const uint8_t* mask, uint8_t* board, float* value_board,
   }
 }
 
+typedef struct { COracle* o; const int32_t* actions; COut* out; } CStepCtx;
+static void step_range(void* ctx, int64_t lo, int64_t hi) {
+  CStepCtx* c = (CStepCtx*)ctx;
+  for (int64_t i = lo; i < hi; ++i) env_step(c->o, i, c->actions[i], c->out);
+}
+
 void orc_step(void* h, const int32_t* actions, uint8_t* board, float* value_board, float* reward, uint8_t* terminated,
               uint8_t* step_type, int8_t* reason, int8_t* actual) {
   COracle* o = (COracle*)h;
   COut out = {board, value_board, reward, terminated, step_type, reason, actual};
   o->call_no += 1;
-  for (int64_t i = 0; i < o->n; ++i) env_step(o, i, actions[i], &out);
+  CStepCtx c = {o, actions, &out};
+  or_parallel_for(o->n, step_range, &c);
 }
 
 /* obs['layers'] of the MO re-wrappings, out[n][GW_MAX_LAYERS][hmax * wmax] in the board-row layout, layer l = cfg.layer_chars[l]:

@@ -18,6 +18,9 @@
 
 #include "../include/gwsim_fm.h"
 
+/* gw_oracle.c: runs fn(ctx, lo, hi) over [0, n) split across the host threads set with or_set_threads */
+void or_parallel_for(int64_t n, void (*fn)(void* ctx, int64_t lo, int64_t hi), void* ctx);
+
 #define S GW_FM_SIDE
 #define CELLS GW_FM_CELLS
 #define NA GW_FM_AGENTS
@@ -278,13 +281,15 @@ void orf_reset(void* h, const uint8_t* mask, uint8_t* board, uint8_t* cube, uint
   }
 }
 
-void orf_step(void* h, const int32_t* actions, const int32_t* order, const double* draws, int64_t draw_stride, uint8_t* board,
-              uint8_t* cube, uint8_t* crop_w, uint8_t* crop_s, uint8_t* lcrop_w, uint8_t* lcrop_s, float* reward_w, float* reward_s,
-              uint8_t* terminated, uint8_t* step_type) {
-  FOracle* o = (FOracle*)h;
-  FOut out = {board, cube, crop_w, crop_s, lcrop_w, lcrop_s, reward_w, reward_s, terminated, step_type};
-  o->call_no += 1;
-  for (int64_t i = 0; i < o->n; ++i) {
+typedef struct { FOracle* o; const int32_t* actions; const int32_t* order; const double* draws; int64_t draw_stride; FOut out; } FStepCtx;
+
+static void step_range(void* ctx, int64_t lo, int64_t hi) {
+  FStepCtx* sc = (FStepCtx*)ctx;
+  FOracle* o = sc->o;
+  const int32_t* actions = sc->actions; const int32_t* order = sc->order; const double* draws = sc->draws;
+  const int64_t draw_stride = sc->draw_stride;
+  FOut out = sc->out;
+  for (int64_t i = lo; i < hi; ++i) {
     FEnv* e = &o->envs[i];
     double r[7] = {0};
     int all_done = 1;
@@ -324,6 +329,16 @@ void orf_step(void* h, const int32_t* actions, const int32_t* order, const doubl
     emit_out(e, i, &out, r, st);
     emit_obs(o, e, i, &out);
   }
+}
+
+void orf_step(void* h, const int32_t* actions, const int32_t* order, const double* draws, int64_t draw_stride, uint8_t* board,
+              uint8_t* cube, uint8_t* crop_w, uint8_t* crop_s, uint8_t* lcrop_w, uint8_t* lcrop_s, float* reward_w, float* reward_s,
+              uint8_t* terminated, uint8_t* step_type) {
+  FOracle* o = (FOracle*)h;
+  o->call_no += 1;
+  FStepCtx sc = {o, actions, order, draws, draw_stride,
+                 {board, cube, crop_w, crop_s, lcrop_w, lcrop_s, reward_w, reward_s, terminated, step_type}};
+  or_parallel_for(o->n, step_range, &sc);
 }
 
 void orf_observe(void* h, double* metrics, float* cumulative, int32_t* frame, int16_t* pos, int32_t* ext_fires) {

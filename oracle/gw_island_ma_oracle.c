@@ -18,6 +18,9 @@
 
 #include "../include/gwsim_ima.h"
 
+/* gw_oracle.c: runs fn(ctx, lo, hi) over [0, n) split across the host threads set with or_set_threads */
+void or_parallel_for(int64_t n, void (*fn)(void* ctx, int64_t lo, int64_t hi), void* ctx);
+
 #define NA GW_IMA_AGENTS
 #define MAXC GW_MAX_CELLS
 #define MAXR GW_MAX_REWARDS
@@ -310,12 +313,14 @@ void ori_reset(void* h, const uint8_t* mask, uint8_t* board, uint8_t* cube, uint
   }
 }
 
-void ori_step(void* h, const int32_t* actions, const int32_t* order, uint8_t* board, uint8_t* cube, uint8_t* crop_out, uint8_t* lcrop,
-              float* reward, uint8_t* terminated, uint8_t* step_type) {
-  IOracle* o = (IOracle*)h;
-  IOut out = {board, cube, crop_out, lcrop, reward, terminated, step_type};
-  o->call_no += 1;
-  for (int64_t i = 0; i < o->n; ++i) {
+typedef struct { IOracle* o; const int32_t* actions; const int32_t* order; IOut out; } IStepCtx;
+
+static void step_range(void* ctx, int64_t lo, int64_t hi) {
+  IStepCtx* sc = (IStepCtx*)ctx;
+  IOracle* o = sc->o;
+  const int32_t* actions = sc->actions; const int32_t* order = sc->order;
+  IOut out = sc->out;
+  for (int64_t i = lo; i < hi; ++i) {
     IEnv* e = &o->envs[i];
     double r[NA][MAXR] = {{0}};
     if (e->step_type[0] >= 2 && e->step_type[1] >= 2) {                       /* pycolab_interface_ma.py:206-213: drop episode, reset */
@@ -356,6 +361,14 @@ void ori_step(void* h, const int32_t* actions, const int32_t* order, uint8_t* bo
     emit_out(o, i, &out, r, st);
     emit_obs(o, e, i, &out);
   }
+}
+
+void ori_step(void* h, const int32_t* actions, const int32_t* order, uint8_t* board, uint8_t* cube, uint8_t* crop_out, uint8_t* lcrop,
+              float* reward, uint8_t* terminated, uint8_t* step_type) {
+  IOracle* o = (IOracle*)h;
+  o->call_no += 1;
+  IStepCtx sc = {o, actions, order, {board, cube, crop_out, lcrop, reward, terminated, step_type}};
+  or_parallel_for(o->n, step_range, &sc);
 }
 
 void ori_observe(void* h, double* metrics, float* cumulative, int32_t* frame, int16_t* pos, int8_t* directions) {

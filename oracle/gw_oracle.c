@@ -20,6 +20,7 @@
 
 #include "../include/gwsim.h"
 
+
 #define MAXC GW_MAX_CELLS
 #define MAXL GW_MAX_LAYERS
 #define MAXR GW_MAX_REWARDS
@@ -555,12 +556,78 @@ void or_philox(uint64_t seed, uint64_t env, uint64_t step, uint32_t out[4]) {
   memcpy(out, c, sizeof c);
 }
 
+typedef struct { uint64_t seed, step; int64_t base; int32_t lo; uint32_t span; int32_t* actions; } ActCtx;
+static void actions_range(void* ctx, int64_t lo, int64_t hi) {
+  const ActCtx* a = (const ActCtx*)ctx;
+  for (int64_t i = lo; i < hi; ++i) {
+    uint32_t r[4];
+    or_philox(a->seed, (uint64_t)(a->base + i), a->step, r);
+    a->actions[i] = a->lo + (int32_t)(((uint64_t)r[0] * a->span) >> 32);
+  }
+}
+
+void or_parallel_for(int64_t n, void (*fn)(void* ctx, int64_t lo, int64_t hi), void* ctx);
+
 void or_random_actions(uint64_t seed, uint64_t step, int64_t env_index_base, int32_t lo, int32_t hi,
                        int32_t* actions, int64_t n) {
-  const uint32_t span = (uint32_t)(hi - lo + 1);
-  for (int64_t i = 0; i < n; ++i) {
-    uint32_t r[4];
-    or_philox(seed, (uint64_t)(env_index_base + i), step, r);
-    actions[i] = lo + (int32_t)(((uint64_t)r[0] * span) >> 32);
+  ActCtx a = {seed, step, env_index_base, lo, (uint32_t)(hi - lo + 1), actions};
+  or_parallel_for(n, actions_range, &a);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Host threads for the batched loops of every oracle in this library (plain pthreads; 1 = the   */
+/* scalar loop on the calling thread).  Used by the BASELINE-size parity tests and bench.py's CPU */
+/* legs, which step up to a million environments per call.  Environments are independent, so a   */
+/* contiguous range per thread changes nothing in the results.                                    */
+static int g_or_threads = 1;
+void or_set_threads(int n) { g_or_threads = n < 1 ? 1 : (n > 1024 ? 1024 : n); }
+int or_threads(void) { return g_or_threads; }
+
+typedef struct { void (*fn)(void*, int64_t, int64_t); void* ctx; int64_t lo, hi; } ParJob;
+static void* par_entry(void* arg) { ParJob* j = (ParJob*)arg; j->fn(j->ctx, j->lo, j->hi); return 0; }
+
+void or_parallel_for(int64_t n, void (*fn)(void* ctx, int64_t lo, int64_t hi), void* ctx) {
+  int nt = g_or_threads;
+  if (nt > n) nt = (int)(n > 0 ? n : 1);
+  if (nt <= 1) { fn(ctx, 0, n); return; }
+  pthread_t* tid = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)nt);
+  ParJob* jobs = (ParJob*)malloc(sizeof(ParJob) * (size_t)nt);
+  const int64_t per = (n + nt - 1) / nt;
+  for (int t = 0; t < nt; ++t) {
+    int64_t lo = t * per, hi = lo + per;
+    if (lo > n) lo = n;
+    if (hi > n) hi = n;
+    jobs[t] = (ParJob){fn, ctx, lo, hi};
+    if (t + 1 == nt) par_entry(&jobs[t]);                       /* the calling thread takes the last range */
+    else pthread_create(&tid[t], 0, par_entry, &jobs[t]);
   }
+  for (int t = 0; t + 1 < nt; ++t) pthread_join(tid[t], 0);
+  free(tid);
+  free(jobs);
+}
+
+/* Position-weighted 64-bit checksum of a buffer of n_words 64-bit words:
+ * sum_j word[j] * ((j * K1 + K2) | 1) mod 2^64.  Every weight is odd, so any change of one word
+ * changes the sum.  The BASELINE-size parity tests compute the same sum on the device with torch
+ * int64 arithmetic (tests/scale_util.py) and compare it per step instead of shipping 0.5 GB per
+ * step to the host; on a mismatch they fall back to the element-wise comparison. */
+typedef struct { const uint64_t* w; uint64_t partial[1024]; int64_t per; } SumCtx;
+static void sum_range(void* ctx, int64_t lo, int64_t hi) {
+  SumCtx* c = (SumCtx*)ctx;
+  uint64_t total = 0;
+  for (int64_t j = lo; j < hi; ++j)
+    total += c->w[j] * ((((uint64_t)j * 0x9E3779B97F4A7C15ull) + 0xD1B54A32D192ED03ull) | 1ull);
+  c->partial[c->per > 0 ? lo / c->per : 0] = total;
+}
+uint64_t or_checksum64(const void* p, int64_t n_words) {
+  SumCtx* c = (SumCtx*)calloc(1, sizeof(SumCtx));
+  int nt = g_or_threads;
+  if (nt > n_words) nt = (int)(n_words > 0 ? n_words : 1);
+  c->w = (const uint64_t*)p;
+  c->per = nt > 1 ? (n_words + nt - 1) / nt : 0;                /* the same split or_parallel_for makes */
+  or_parallel_for(n_words, sum_range, c);
+  uint64_t total = 0;
+  for (int t = 0; t < 1024; ++t) total += c->partial[t];
+  free(c);
+  return total;
 }

@@ -22,6 +22,9 @@
 
 #include "../include/gwsim_sav.h"
 
+/* gw_oracle.c: runs fn(ctx, lo, hi) over [0, n) split across the host threads set with or_set_threads */
+void or_parallel_for(int64_t n, void (*fn)(void* ctx, int64_t lo, int64_t hi), void* ctx);
+
 #define NA GW_SAV_AGENTS
 #define MAXC GW_SAV_MAX_CELLS
 #define MAXR GW_SAV_MAX_REWARDS
@@ -463,13 +466,16 @@ void orv_reset(void* h, const uint8_t* mask, uint8_t* board, uint8_t* cube, uint
   }
 }
 
-void orv_step(void* h, const int32_t* actions, const int32_t* order, const double* draws, int64_t draw_stride, uint8_t* board, uint8_t* cube, uint8_t* crop_out, uint8_t* lcrop,
-              float* reward, uint8_t* terminated, uint8_t* step_type) {
-  VOracle* o = (VOracle*)h;
-  VOut out = {board, cube, crop_out, lcrop, reward, terminated, step_type};
+typedef struct { VOracle* o; const int32_t* actions; const int32_t* order; const double* draws; int64_t draw_stride; VOut out; } VStepCtx;
+
+static void step_range(void* ctx, int64_t lo, int64_t hi) {
+  VStepCtx* sc = (VStepCtx*)ctx;
+  VOracle* o = sc->o;
+  const int32_t* actions = sc->actions; const int32_t* order = sc->order; const double* draws = sc->draws;
+  const int64_t draw_stride = sc->draw_stride;
+  VOut out = sc->out;
   const int A = o->cfg.n_agents;
-  o->call_no += 1;
-  for (int64_t i = 0; i < o->n; ++i) {
+  for (int64_t i = lo; i < hi; ++i) {
     VEnv* e = &o->envs[i];
     double r[NA][MAXR] = {{0}};
     if (e->step_type[0] >= 2 && e->step_type[1] >= 2) {                       /* pycolab_interface_ma.py:206-213: drop episode, reset */
@@ -511,6 +517,14 @@ void orv_step(void* h, const int32_t* actions, const int32_t* order, const doubl
     emit_out(o, i, &out, r, st);
     emit_obs(o, e, i, &out);
   }
+}
+
+void orv_step(void* h, const int32_t* actions, const int32_t* order, const double* draws, int64_t draw_stride, uint8_t* board, uint8_t* cube, uint8_t* crop_out, uint8_t* lcrop,
+              float* reward, uint8_t* terminated, uint8_t* step_type) {
+  VOracle* o = (VOracle*)h;
+  o->call_no += 1;
+  VStepCtx sc = {o, actions, order, draws, draw_stride, {board, cube, crop_out, lcrop, reward, terminated, step_type}};
+  or_parallel_for(o->n, step_range, &sc);
 }
 
 void orv_observe(void* h, double* metrics, float* cumulative, int32_t* frame, int16_t* pos, int8_t* directions) {

@@ -15,6 +15,9 @@
 
 #include "../include/gwsim_sok.h"
 
+/* gw_oracle.c: runs fn(ctx, lo, hi) over [0, n) split across the host threads set with or_set_threads */
+void or_parallel_for(int64_t n, void (*fn)(void* ctx, int64_t lo, int64_t hi), void* ctx);
+
 #define MAXC GW_SOK_MAX_CELLS
 
 typedef struct {
@@ -224,11 +227,18 @@ void ors_reset(void* h, const uint8_t* mask, uint8_t* board, float* value_board,
   }
 }
 
+typedef struct { SOracle* o; const int32_t* actions; SOut* out; } SStepCtx;
+static void step_range(void* ctx, int64_t lo, int64_t hi) {
+  SStepCtx* c = (SStepCtx*)ctx;
+  for (int64_t i = lo; i < hi; ++i) env_step(c->o, &c->o->envs[i], i, c->actions[i], c->out);
+}
+
 void ors_step(void* h, const int32_t* actions, uint8_t* board, float* value_board, float* reward, uint8_t* terminated, uint8_t* step_type,
               int8_t* reason, int8_t* actual) {
   SOracle* o = (SOracle*)h;
   SOut out = {board, value_board, reward, terminated, step_type, reason, actual};
-  for (int64_t i = 0; i < o->n; ++i) env_step(o, &o->envs[i], i, actions[i], &out);
+  SStepCtx c = {o, actions, &out};
+  or_parallel_for(o->n, step_range, &c);
 }
 
 void ors_observe(void* h, int32_t* cumulative, int32_t* frame, int16_t* pos, uint8_t* boxes, uint8_t* coins) {
