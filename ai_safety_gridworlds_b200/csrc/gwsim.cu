@@ -2054,6 +2054,12 @@ int gw_fm_create(const GwFmConfig* cfg, int64_t n_envs, int device, int64_t env_
     if (ch == 'W') { f |= FM_F_WORKSHOP; base = 'W'; }
     if (ch == 'B') { f |= FM_F_BUTTON; base = 'B'; }
     st.flags[p] = f; st.base_chr[p] = base;
+    const uint32_t bit = 1u << (p & 31);
+    if (f == 0) st.lay_static[FM_SL_GAP][p >> 5] |= bit;
+    if (f & FM_F_WALL) st.lay_static[FM_SL_WALL][p >> 5] |= bit;
+    if (f & FM_F_TERRITORY) st.lay_static[FM_SL_TERRITORY][p >> 5] |= bit;
+    if (f & FM_F_BUTTON) st.lay_static[FM_SL_BUTTON][p >> 5] |= bit;
+    if (f & FM_F_WORKSHOP) st.lay_static[FM_SL_WORKSHOP][p >> 5] |= bit;
   }
   for (int dr = -2; dr <= 2; ++dr)
     for (int dc = -2; dc <= 2; ++dc) {
@@ -2061,6 +2067,21 @@ int gw_fm_create(const GwFmConfig* cfg, int64_t n_envs, int device, int64_t env_
       const double rel = (dist - 1) / (cfg->fire_spread_exclusive_max_distance - 1 + 1e-15);
       st.spread_p[(dr + 2) * 5 + dc + 2] = (1 - rel) * cfg->fire_spread_probability_at_distance_one;
     }
+  {
+    double worst = 1.0, cmin = 1.0;
+    for (int i = 0; i < 25; ++i) {
+      st.spread_c[i] = 1.0 - st.spread_p[i];
+      if (i != 12) { worst *= st.spread_c[i]; if (st.spread_c[i] < cmin) cmin = st.spread_c[i]; }
+      if (i != 12 && !(st.spread_p[i] >= 0.0 && st.spread_p[i] < 1.0)) { delete h; return fail(GW_ERR_INVALID, "fire spread probability out of [0, 1)"); }
+    }
+    /* the kernel accumulates (1 - P) as a running product, which is bit-identical to the reference's recurrence while the
+     * product stays >= 0.5: all 24 neighbours burning plus the two working workers is the worst case */
+    if (worst * cmin * cmin < 0.51) {
+      delete h;
+      return fail(GW_ERR_INVALID, "fire_spread_probability_at_distance_one %g: the spread product of a full neighbourhood falls below 0.5",
+                  cfg->fire_spread_probability_at_distance_one);
+    }
+  }
   st.cont_p = cfg->fire_continuation_probability;
   memcpy(st.rewards, cfg->rewards, sizeof st.rewards);
   st.max_iterations = cfg->max_iterations; st.autoreset = cfg->autoreset_mode; st.randomize = cfg->randomize_order;

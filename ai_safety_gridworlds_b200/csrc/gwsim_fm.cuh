@@ -36,6 +36,7 @@ enum { FM_F_WALL = 1, FM_F_WORKSHOP = 2, FM_F_BUTTON = 4, FM_F_TERRITORY = 8 };
 
 struct alignas(16) FmStatic {           /* per-handle tables: device memory -> shared memory per CTA */
   double spread_p[25];                  /* by (dr + 2) * 5 + (dc + 2), firemaker_ex_ma.py:595-598 */
+  double spread_c[25];                  /* 1 - spread_p, rounded once as the reference's (1 - p) is */
   double cont_p;
   double rewards[8];
   int32_t start[4];
@@ -44,7 +45,10 @@ struct alignas(16) FmStatic {           /* per-handle tables: device memory -> s
                                                 and static2 = the art's '2' tile, a backdrop character whose layer reads 1 */
   uint8_t base_chr[FM_CELLS + 15];      /* render without fire and agents: '#', ' ', '-', 'W', 'B' */
   uint8_t flags[FM_CELLS + 15];
+  uint32_t lay_static[5][12];           /* flat 289-bit maps (bit cell & 31 of word cell >> 5): cells with no flag at all (the gap layer before
+                                           fire and agents), walls, territory, stop button, workshop */
 };
+enum { FM_SL_GAP = 0, FM_SL_WALL = 1, FM_SL_TERRITORY = 2, FM_SL_BUTTON = 3, FM_SL_WORKSHOP = 4 };
 
 struct FmArgs {
   const FmStatic* st;
@@ -66,17 +70,26 @@ struct FmArgs {
 };
 
 
-__device__ __forceinline__ double fm_uniform(const FmArgs& a, int64_t env, uint32_t k) {
+/* Draw k of environment `env` in this call: Philox4x32-10 keyed by the seed, counter (global environment index, call * 65536 + k / 2);
+ * one evaluation yields TWO 53-bit uniforms -- draw 2 j from words (x, y), draw 2 j + 1 from (z, w). */
+__device__ __forceinline__ uint4 fm_philox(const FmArgs& a, int64_t env, uint32_t call_index) {
   const uint64_t g = (uint64_t)(a.env_index_base + env);
-  const uint64_t step = a.call_no * 65536ull + k;
-  const uint4 r = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)step, (uint32_t)(step >> 32)),
-                                (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
-  return (double)((((unsigned long long)r.x << 32) | r.y) >> 11) * (1.0 / 9007199254740992.0);
+  const uint64_t step = a.call_no * 65536ull + call_index;
+  return philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)step, (uint32_t)(step >> 32)),
+                       (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+}
+__device__ __forceinline__ double fm_u53(uint32_t hi, uint32_t lo) {
+  return (double)((((unsigned long long)hi << 32) | lo) >> 11) * (1.0 / 9007199254740992.0);
+}
+__device__ __forceinline__ double fm_uniform(const FmArgs& a, int64_t env, uint32_t k) {
+  const uint4 r = fm_philox(a, env, k >> 1);
+  return (k & 1u) ? fm_u53(r.z, r.w) : fm_u53(r.x, r.y);
 }
 
 /* per-warp scratch words of the fire update */
 enum { FM_X_ROWMASK = 0, FM_X_NEAR = FM_B + 3, FM_X_CAND = FM_X_NEAR + FM_S + 1, FM_X_PRE = FM_X_CAND + FM_SLOTS,
-       FM_X_NEW = FM_X_PRE + FM_SLOTS + 1, FM_X_WORDS = FM_X_NEW + FM_SLOTS + 1 };
+       FM_X_NEW = FM_X_PRE + FM_SLOTS + 1, FM_X_PREB = FM_X_NEW + FM_SLOTS + 1, FM_X_WORDS = FM_X_PREB + FM_SLOTS + 2 };
+#define FM_UBUF 296                     /* draws of one frame: every cell is a candidate or burning or neither (<= 289) */
 
 /* k-th (0-based) set bit of the FM_SLOTS-word bitmap `bits`, given the exclusive prefix popcounts `pre`: returns the cell */
 __device__ __forceinline__ int fm_select(const uint32_t* __restrict__ bits, const uint32_t* __restrict__ pre, uint32_t k) {
@@ -107,7 +120,7 @@ __device__ __forceinline__ uint32_t fm_prefix(const uint32_t* __restrict__ bits,
 __device__ __forceinline__ int fm_fire_update(const FmStatic& S, const FmArgs& a, int64_t env, uint32_t* __restrict__ fw,
                                               uint32_t* __restrict__ x, const uint32_t* __restrict__ s_allowed,
                                               const uint32_t* __restrict__ s_extw, const int32_t* pos, const bool* at_w,
-                                              int32_t countdown, uint32_t& k, uint32_t lane) {
+                                              int32_t countdown, uint32_t& k, uint32_t lane, double* __restrict__ ub) {
   uint32_t* __restrict__ rowmask = x + FM_X_ROWMASK;   /* bordered: row r + 2, bit c + 2 */
   uint32_t* __restrict__ near = x + FM_X_NEAR;
   uint32_t* __restrict__ cand = x + FM_X_CAND;
@@ -167,56 +180,77 @@ __device__ __forceinline__ int fm_fire_update(const FmStatic& S, const FmArgs& a
   }
   __syncwarp();
   const uint32_t lt = (1u << lane) - 1u;
-  uint32_t base = k;
-  /* pass 1: one lane per candidate */
+  uint32_t* __restrict__ preb = x + FM_X_PREB;
   const uint32_t C = fm_prefix(cand, pre, lane);
+  const uint32_t B = fm_prefix(fw, preb, lane);
+  /* the frame's draws, in the order the reference consumes them: one per candidate with P > 0 (row-major), then one per cell
+   * that was burning (row-major).  At most C + B are needed; they are produced in bulk, two per Philox evaluation, one
+   * evaluation per lane and round -- or read from the replay trace. */
+  const uint32_t T = C + B;
+  if (a.draws) {
+    for (uint32_t i = lane; i < T; i += 32) {
+      const uint32_t idx = k + i;
+      ub[i] = (int64_t)idx < a.draw_stride ? a.draws[env * a.draw_stride + idx] : 2.0;
+    }
+  } else {
+    const uint32_t c0 = k >> 1, ncalls = ((k + T + 1u) >> 1) - c0;
+#pragma unroll 1
+    for (uint32_t j = lane; j < ncalls; j += 32) {
+      const uint4 r = fm_philox(a, env, c0 + j);
+      const int32_t i0 = (int32_t)(2u * (c0 + j)) - (int32_t)k;
+      if (i0 >= 0 && i0 < (int32_t)T) ub[i0] = fm_u53(r.x, r.y);
+      if (i0 + 1 >= 0 && i0 + 1 < (int32_t)T) ub[i0 + 1] = fm_u53(r.z, r.w);
+    }
+  }
+  __syncwarp();
+  /* pass 1: one lane per candidate.  P = 1 - (1 - P)(1 - p) over the sources in row-major order (:600-611).  While the running
+   * product U = (1 - P) stays in [0.5, 1] every subtraction from 1 is exact (Sterbenz), so the reference's three rounded
+   * operations per source equal ONE rounded multiply U <- U * (1 - p) and P = 1 - U at the end is exact: bit-identical, a third
+   * of the fp64 work (gw_fm_create checks the bound for the configured probabilities).  The 24 neighbours are visited
+   * unconditionally with predicated multiplies -- no data-dependent loop, no divergence between the lanes. */
+  uint32_t base = 0;
+  const int vr0 = vs0 >= 0 ? vs0 / FM_S : -100, vc0 = vs0 >= 0 ? vs0 % FM_S : -100;
+  const int vr1 = vs1 >= 0 ? vs1 / FM_S : -100, vc1 = vs1 >= 0 ? vs1 % FM_S : -100;
 #pragma unroll 1
   for (uint32_t j = 0; j < C; j += 32) {
     const uint32_t kk = j + lane;
-    double p = 0.0;
+    double u = 1.0;
     int cell = 0;
     if (kk < C) {
       cell = fm_select(cand, pre, kk);
       const int tr = cell / FM_S, tc = cell % FM_S;
-      if ((near[tr] >> tc) & 31u) {
-        /* burning sources in row-major order: rows tr-2..tr+2, within a row ascending column (bit q <-> dc = q - 2) */
 #pragma unroll 1
-        for (int dr = 0; dr < 5; ++dr) {
-          uint32_t m = (rowmask[tr + dr] >> tc) & 31u;
-          while (m) {
-            const int q = __ffs((int)m) - 1;
-            m &= m - 1;
-            p = 1.0 - (1.0 - p) * (1.0 - S.spread_p[dr * 5 + q]);
-          }
-        }
+      for (int dr = 0; dr < 5; ++dr) {                       /* rolled: keeps the 25 constants out of registers and the code small */
+        const uint32_t m = rowmask[tr + dr] >> tc;           /* bit q <-> source column tc + q - 2; the target's own bit is 0 (not burning) */
+        const double* __restrict__ c = S.spread_c + dr * 5;
+#pragma unroll
+        for (int q = 0; q < 5; ++q)
+          if ((m >> q) & 1u) u *= c[q];
       }
-      if (vs0 >= 0) { const int dr = vs0 / FM_S - tr, dc = vs0 % FM_S - tc; if (dr >= -2 && dr <= 2 && dc >= -2 && dc <= 2) p = 1.0 - (1.0 - p) * (1.0 - S.spread_p[(dr + 2) * 5 + dc + 2]); }
-      if (vs1 >= 0) { const int dr = vs1 / FM_S - tr, dc = vs1 % FM_S - tc; if (dr >= -2 && dr <= 2 && dc >= -2 && dc <= 2) p = 1.0 - (1.0 - p) * (1.0 - S.spread_p[(dr + 2) * 5 + dc + 2]); }
+      { const int dr = vr0 - tr, dc = vc0 - tc; if (dr >= -2 && dr <= 2 && dc >= -2 && dc <= 2) u *= S.spread_c[(dr + 2) * 5 + dc + 2]; }
+      { const int dr = vr1 - tr, dc = vc1 - tc; if (dr >= -2 && dr <= 2 && dc >= -2 && dc <= 2) u *= S.spread_c[(dr + 2) * 5 + dc + 2]; }
     }
+    const double p = 1.0 - u;
     const bool need = p > 0.0;
     const uint32_t m = __ballot_sync(FULL, need);
     if (need) {
       const uint32_t idx = base + __popc(m & lt);
-      const double u = a.draws ? ((int64_t)idx < a.draw_stride ? a.draws[env * a.draw_stride + idx] : 2.0) : fm_uniform(a, env, idx);
-      if (u < p) atomicOr(&newf[cell >> 5], 1u << (cell & 31));
+      if (ub[idx] < p) atomicOr(&newf[cell >> 5], 1u << (cell & 31));
     }
     base += __popc(m);
   }
-  /* pass 2: continuation of the fires that were burning (:619-621), one lane per burning cell */
+  /* pass 2: continuation of the fires that were burning (:619-621); cell 32 s + lane draws number base + its row-major rank */
   __syncwarp();
-  const uint32_t B = fm_prefix(fw, pre, lane);
 #pragma unroll 1
-  for (uint32_t j = 0; j < B; j += 32) {
-    const uint32_t kk = j + lane;
-    if (kk < B) {
-      const int cell = fm_select(fw, pre, kk);
-      const uint32_t idx = base + kk;
-      const double u = a.draws ? ((int64_t)idx < a.draw_stride ? a.draws[env * a.draw_stride + idx] : 2.0) : fm_uniform(a, env, idx);
-      if (u < S.cont_p) atomicOr(&newf[cell >> 5], 1u << (cell & 31));
-    }
+  for (int sl = 0; sl < FM_SLOTS; ++sl) {
+    const uint32_t w = fw[sl];
+    if (w == 0u) continue;
+    const bool burning = (w >> lane) & 1u;
+    const uint32_t idx = base + preb[sl] + (uint32_t)__popc(w & lt);
+    const uint32_t kept = __ballot_sync(FULL, burning && ub[burning ? idx : 0u] < S.cont_p);
+    if (lane == 0) newf[sl] |= kept;
   }
-  base += B;
-  k = base;
+  k += base + B;
   __syncwarp();
   uint32_t ext = 0;
   if (lane < FM_SLOTS) { const uint32_t v = newf[lane]; fw[lane] = v; ext = (uint32_t)__popc(v & s_extw[lane]); }
@@ -224,8 +258,24 @@ __device__ __forceinline__ int fm_fire_update(const FmStatic& S, const FmArgs& a
   return (int)__reduce_add_sync(FULL, ext);                /* fires outside the workshop territory */
 }
 
-#define FM_PLANES (1 + GW_FM_LAYERS)            /* plane 0 = rendered board, 1..9 = layers */
-#define FM_PLANE_BYTES (16 + FM_CELLS + 32 + GW_FM_LAYERS * FM_CELLS + 6)    /* board plane and layer planes, each placed at the 16-byte phase of its destination */
+/* ---- observation emission -------------------------------------------------------------------------------------------------
+ * Every layer is a 289-bit map (the format of the fire curtain in the state), so the 0/1 layer tensors are BIT STRINGS expanded
+ * to bytes at store time: 8 bits -> 8 bytes through a 256-entry table in shared memory, 32 bits -> two 16-byte global stores.
+ *
+ *   cube  [9][289]      = the nine layer maps concatenated at a pitch of 289 bits (2601 bits)
+ *   lcrop_s [9][33][33] = 297 view rows of 33 bits.  The supervisor's view is the board shifted so that 'S' sits at (16,16): in
+ *                         the FLAT view of one layer the board's rows land 33 bits apart starting at bit org = ilo * 33 + jlo, and
+ *                         everything else is the layer's padding value (1 for '#', else 0; safety_game_moma.py:1996-2101).  So the
+ *                         string is a per-handle constant template with 17 rows of 17 bits XOR-ed in per layer.
+ *
+ * The destinations are dense (env * 2601 and env * 9801 bytes into tensors of arbitrary base): the strings are read at the bit
+ * offset of the destination's 16-byte phase (funnel shift), the ragged head and tail use byte stores.  Character tensors (board,
+ * the agents' ASCII views) keep one byte plane of the rendered board. */
+#define FM_LAY_PITCH 11                                   /* words per layer map in shared memory: 10 + a zero word for the funnel shifts */
+#define FM_CB_WORDS 84                                    /* 2601 bits + read-ahead */
+#define FM_G_WORDS 308                                    /* 9801 bits + read-ahead */
+#define FM_EM_WORDS (GW_FM_LAYERS * FM_LAY_PITCH + FM_CB_WORDS + FM_G_WORDS + 1)
+#define FM_PB_BYTES (16 + FM_CELLS + 15)                  /* the board plane, placed at the 16-byte phase of its destination */
 
 /* copies `count` bytes from shared to global memory; src and dst have the SAME address modulo 16, so the
  * body moves 16 bytes per lane (ld.shared.v4 -> st.global.v4) and only the ragged head and tail use byte stores */
@@ -240,58 +290,103 @@ __device__ __forceinline__ void fm_copy16(uint8_t* __restrict__ dst, const uint8
   if (tail < count) dst[tail] = src[tail];
 }
 
-/* fills dst[0, count) with `lo` except bytes [one_lo, one_hi), which get `hi`: 16-byte stores of a constant,
- * byte stores for the ragged ends and for the (at most two) chunks that straddle a boundary */
-__device__ __forceinline__ void fm_fill16(uint8_t* __restrict__ dst, int count, int one_lo, int one_hi, uint8_t lo, uint8_t hi, uint32_t lane) {
+/* fills dst[0, count) with the byte `v`: 16-byte stores, byte stores for the ragged ends */
+__device__ __forceinline__ void fm_fill16(uint8_t* __restrict__ dst, int count, uint8_t v, uint32_t lane) {
   const int head = min(count, (int)((16u - ((uint32_t)(uintptr_t)dst & 15u)) & 15u));
-  if ((int)lane < head) dst[lane] = ((int)lane >= one_lo && (int)lane < one_hi) ? hi : lo;
+  if ((int)lane < head) dst[lane] = v;
   const int chunks = (count - head) >> 4;
   uint4* __restrict__ d = reinterpret_cast<uint4*>(dst + head);
-  const uint32_t wlo = 0x01010101u * lo, whi = 0x01010101u * hi;
-  for (int k = (int)lane; k < chunks; k += 32) {
-    const int b = head + 16 * k;
-    if (b + 15 < one_lo || b >= one_hi) d[k] = make_uint4(wlo, wlo, wlo, wlo);
-    else if (b >= one_lo && b + 15 < one_hi) d[k] = make_uint4(whi, whi, whi, whi);
-    else
-      for (int i = b; i < b + 16; ++i) dst[i] = (i >= one_lo && i < one_hi) ? hi : lo;
-  }
+  const uint32_t w = 0x01010101u * v;
+  for (int k = (int)lane; k < chunks; k += 32) d[k] = make_uint4(w, w, w, w);
   const int tail = head + 16 * chunks + (int)lane;
-  if (tail < count) dst[tail] = (tail >= one_lo && tail < one_hi) ? hi : lo;
+  if (tail < count) dst[tail] = v;
 }
 
-/* Renders the board (pb) and the nine layers (pl, 289 bytes each) of the environment once into shared
- * memory; every observation tensor is then a copy or a window of these planes. */
-__device__ __forceinline__ void fm_build_planes(const FmStatic& S, const uint32_t* __restrict__ fw, const int32_t* pos, uint8_t* __restrict__ pb,
-                                                uint8_t* __restrict__ pl, uint32_t lane) {
-  for (int cell = (int)lane; cell < FM_CELLS; cell += 32) {
-    const uint8_t f = S.flags[cell];
-    const bool burning = (fw[cell >> 5] >> lane) & 1u;                       /* cell = 32 k + lane: bit `lane` of word k */
-    const bool a0 = cell == pos[0], a1 = cell == pos[1], a2 = cell == pos[2];
-    pb[cell] = a2 ? (uint8_t)'S' : a1 ? (uint8_t)'2' : a0 ? (uint8_t)'1' : burning ? (uint8_t)'F' : S.base_chr[cell];
-    pl[0 * FM_CELLS + cell] = f == 0 && !burning && !a0 && !a1 && !a2;       /* ' ': gap AND NOT any other layer */
-    pl[1 * FM_CELLS + cell] = (f & FM_F_WALL) != 0;
-    pl[2 * FM_CELLS + cell] = (f & FM_F_TERRITORY) != 0;
-    pl[3 * FM_CELLS + cell] = a0;
-    pl[4 * FM_CELLS + cell] = a1 || cell == S.static2;
-    pl[5 * FM_CELLS + cell] = (f & FM_F_BUTTON) != 0;
-    pl[6 * FM_CELLS + cell] = burning;
-    pl[7 * FM_CELLS + cell] = a2;
-    pl[8 * FM_CELLS + cell] = (f & FM_F_WORKSHOP) != 0;
+/* dst[i] = bit i of the string `bits` (0 / 1 bytes) for i < count: 32 bits per lane and iteration -> four table look-ups ->
+ * two 16-byte stores.  `bits` must be readable one word beyond the string. */
+__device__ __forceinline__ void fm_expand_bits(uint8_t* __restrict__ dst, const uint32_t* __restrict__ bits, int count,
+                                               const uint2* __restrict__ lut, uint32_t lane) {
+  const int head = min(count, (int)((16u - ((uint32_t)(uintptr_t)dst & 15u)) & 15u));
+  if ((int)lane < head) dst[lane] = (uint8_t)((bits[0] >> lane) & 1u);
+  const int nblk = (count - head) >> 5;
+  uint4* __restrict__ d = reinterpret_cast<uint4*>(dst + head);
+  for (int b = (int)lane; b < nblk; b += 32) {
+    const uint32_t v = __funnelshift_r(bits[b], bits[b + 1], (uint32_t)head);      /* string bits [head + 32 b, head + 32 b + 32) */
+    const uint2 t0 = lut[v & 0xffu], t1 = lut[(v >> 8) & 0xffu], t2 = lut[(v >> 16) & 0xffu], t3 = lut[v >> 24];
+    d[2 * b] = make_uint4(t0.x, t0.y, t1.x, t1.y);
+    d[2 * b + 1] = make_uint4(t2.x, t2.y, t3.x, t3.y);
   }
-  __syncwarp();
+  const int tail = head + 32 * nblk + (int)lane;
+  if (tail < count) dst[tail] = (uint8_t)((bits[tail >> 5] >> (tail & 31)) & 1u);
 }
 
 __device__ __forceinline__ void fm_emit_obs(const FmStatic& S, const FmArgs& a, int64_t env, const uint32_t* __restrict__ fire, const int32_t* pos,
-                                            uint8_t* __restrict__ planes, const uint16_t* __restrict__ wtab, uint32_t lane) {
-  /* the board plane and the block of layer planes sit at the 16-byte phase of their destinations (env * 289 and
-   * env * 2601 bytes into tensors of arbitrary base), so that the global board and cube are 16-byte copies */
+                                            uint8_t* __restrict__ pbuf, uint32_t* __restrict__ em, const uint32_t* __restrict__ gtmpl,
+                                            const uint2* __restrict__ lut, const uint16_t* __restrict__ wtab, uint32_t lane) {
+  uint32_t* __restrict__ lay = em;                                            /* [9][FM_LAY_PITCH] */
+  uint32_t* __restrict__ cb = em + GW_FM_LAYERS * FM_LAY_PITCH;               /* cube bit string */
+  uint32_t* __restrict__ g = cb + FM_CB_WORDS;                                /* supervisor layer-view bit string */
   uint8_t* gboard = a.board ? a.board + env * FM_CELLS : nullptr;
-  uint8_t* gcube = a.cube ? a.cube + env * (GW_FM_LAYERS * FM_CELLS) : nullptr;
-  uint8_t* pb = planes + ((uint32_t)(uintptr_t)gboard & 15u);
-  uint8_t* pl = planes + 16 + FM_CELLS + 16 + ((uint32_t)(uintptr_t)gcube & 15u) - ((16 + FM_CELLS) & 15);
-  fm_build_planes(S, fire, pos, pb, pl, lane);
+  uint8_t* pb = pbuf + ((uint32_t)(uintptr_t)gboard & 15u);                   /* at the 16-byte phase of its destination */
+  /* the nine layer maps, word k by lane k (safety_game_moma.py layers: ' ' = gap AND NOT any other layer) */
+  if (lane < FM_LAY_PITCH) {
+    const uint32_t k = lane;
+    const uint32_t f = k < FM_SLOTS ? fire[k] : 0u;
+    const uint32_t a0 = (uint32_t)(pos[0] >> 5) == k ? 1u << (pos[0] & 31) : 0u;
+    const uint32_t a1 = (uint32_t)(pos[1] >> 5) == k ? 1u << (pos[1] & 31) : 0u;       /* 0xffff (no worker '2') matches no word */
+    const uint32_t a2 = (uint32_t)(pos[2] >> 5) == k ? 1u << (pos[2] & 31) : 0u;
+    const uint32_t s2 = (S.static2 >= 0 && (uint32_t)(S.static2 >> 5) == k) ? 1u << (S.static2 & 31) : 0u;
+    const bool in = k < FM_SLOTS;
+    lay[0 * FM_LAY_PITCH + k] = in ? S.lay_static[FM_SL_GAP][k] & ~(f | a0 | a1 | a2) : 0u;
+    lay[1 * FM_LAY_PITCH + k] = in ? S.lay_static[FM_SL_WALL][k] : 0u;
+    lay[2 * FM_LAY_PITCH + k] = in ? S.lay_static[FM_SL_TERRITORY][k] : 0u;
+    lay[3 * FM_LAY_PITCH + k] = a0;
+    lay[4 * FM_LAY_PITCH + k] = a1 | s2;
+    lay[5 * FM_LAY_PITCH + k] = in ? S.lay_static[FM_SL_BUTTON][k] : 0u;
+    lay[6 * FM_LAY_PITCH + k] = f;
+    lay[7 * FM_LAY_PITCH + k] = a2;
+    lay[8 * FM_LAY_PITCH + k] = in ? S.lay_static[FM_SL_WORKSHOP][k] : 0u;
+  }
+  /* the rendered board as characters (z-order: agents over fire over the static drapes) */
+  for (int cell = (int)lane; cell < FM_CELLS; cell += 32) {
+    const bool burning = (fire[cell >> 5] >> lane) & 1u;                       /* cell = 32 k + lane: bit `lane` of word k */
+    pb[cell] = cell == pos[2] ? (uint8_t)'S' : cell == pos[1] ? (uint8_t)'2' : cell == pos[0] ? (uint8_t)'1' : burning ? (uint8_t)'F' : S.base_chr[cell];
+  }
+  if (a.cube) for (int w = (int)lane; w < FM_CB_WORDS; w += 32) cb[w] = 0u;
+  if (a.lcrop_s) for (int w = (int)lane; w < FM_G_WORDS; w += 32) g[w] = gtmpl[w];
+  __syncwarp();
   if (gboard) fm_copy16(gboard, pb, FM_CELLS, lane);
-  if (gcube) fm_copy16(gcube, pl, GW_FM_LAYERS * FM_CELLS, lane);
+  if (a.cube) {
+    /* layer l's ten words go to bit 289 l of the cube string */
+#pragma unroll 1
+    for (int p = (int)lane; p < GW_FM_LAYERS * FM_SLOTS; p += 32) {
+      const int l = p / FM_SLOTS, k = p - l * FM_SLOTS;
+      const uint32_t w = lay[l * FM_LAY_PITCH + k];
+      if (w) {
+        const int o = FM_CELLS * l + 32 * k, wi = o >> 5, sh = o & 31;
+        atomicOr(&cb[wi], w << sh);
+        if (sh) atomicOr(&cb[wi + 1], w >> (32 - sh));
+      }
+    }
+  }
+  const int side = GW_FM_SCROP, area = side * side;
+  const int ilo = (FM_S - 1) - pos[2] / FM_S, jlo = (FM_S - 1) - pos[2] % FM_S;    /* view coordinates of board cell (0,0) */
+  const int org = ilo * side + jlo;
+  if (a.lcrop_s) {
+    /* board row r of layer l: 17 bits at bit 1089 l + org + 33 r of the view string; the template holds the padding value there */
+#pragma unroll 1
+    for (int p = (int)lane; p < GW_FM_LAYERS * FM_S; p += 32) {
+      const int l = p / FM_S, r = p - l * FM_S;
+      const int b = FM_S * r, bw = b >> 5;
+      const uint32_t row = __funnelshift_r(lay[l * FM_LAY_PITCH + bw], lay[l * FM_LAY_PITCH + bw + 1], (uint32_t)(b & 31)) & 0x1ffffu;
+      const uint32_t x = l == 1 ? row ^ 0x1ffffu : row;
+      if (x) {
+        const int o = area * l + org + side * r, wi = o >> 5, sh = o & 31;
+        atomicXor(&g[wi], x << sh);
+        if (sh > 15) atomicXor(&g[wi + 1], x >> (32 - sh));
+      }
+    }
+  }
   /* get_agent_perspective, mode 0: crop around the agent, '#' outside the board; a layer pads with (chr == '#').
    * Lane j < 25 owns view cell (j / 5, j % 5) of every plane. */
   if (a.crop_w || a.lcrop_w) {
@@ -306,33 +401,23 @@ __device__ __forceinline__ void fm_emit_obs(const FmStatic& S, const FmArgs& a, 
         if (a.crop_w) a.crop_w[(env * 2 + w) * 25 + lane] = inb ? pb[cell] : (uint8_t)'#';
         if (a.lcrop_w) {
           uint8_t* dst = a.lcrop_w + (env * 2 + w) * (GW_FM_LAYERS * 25) + lane;
+          const uint32_t* lw = lay + (cell >> 5);
+          const uint32_t sh = (uint32_t)cell & 31u;
 #pragma unroll
-          for (int l = 0; l < GW_FM_LAYERS; ++l) dst[l * 25] = inb ? pl[l * FM_CELLS + cell] : (uint8_t)(l == 1);
+          for (int l = 0; l < GW_FM_LAYERS; ++l) dst[l * 25] = inb ? (uint8_t)((lw[l * FM_LAY_PITCH] >> sh) & 1u) : (uint8_t)(l == 1);
         }
       }
     }
   }
-  {
-    /* The supervisor's 33x33 view is the whole board shifted so that 'S' sits at (16,16): constant
-     * padding everywhere except one 17x17 window per plane.  Fill, then overwrite the window. */
-    const int side = GW_FM_SCROP, area = side * side;
-    const int ilo = (FM_S - 1) - pos[2] / FM_S, jlo = (FM_S - 1) - pos[2] % FM_S;    /* view coordinates of board cell (0,0) */
-    uint8_t* gcs = a.crop_s ? a.crop_s + env * area : nullptr;
-    uint8_t* gls = a.lcrop_s ? a.lcrop_s + env * (int64_t)(GW_FM_LAYERS * area) : nullptr;
-    if (gcs) fm_fill16(gcs, area, 0, 0, (uint8_t)'#', (uint8_t)'#', lane);
-    if (gls) fm_fill16(gls, GW_FM_LAYERS * area, area, 2 * area, 0, 1, lane);       /* only the '#' layer pads with 1 */
-    __syncwarp();                                   /* the window stores below overwrite bytes of the fills above */
-    /* board cell j = 32 s + lane lands at view offset wtab[j] = (j / 17) * 33 + j % 17 from the window origin, in every plane */
-    const int org = ilo * side + jlo;
+  uint8_t* gcs = a.crop_s ? a.crop_s + env * area : nullptr;
+  if (gcs) fm_fill16(gcs, area, (uint8_t)'#', lane);
+  __syncwarp();                                   /* the strings are complete; the window stores below overwrite bytes of the fill above */
+  if (a.cube) fm_expand_bits(a.cube + env * (GW_FM_LAYERS * FM_CELLS), cb, GW_FM_LAYERS * FM_CELLS, lut, lane);
+  if (a.lcrop_s) fm_expand_bits(a.lcrop_s + env * (int64_t)(GW_FM_LAYERS * area), g, GW_FM_LAYERS * area, lut, lane);
+  if (gcs) {
+    /* board cell j = 32 s + lane lands at view offset wtab[j] = (j / 17) * 33 + j % 17 from the window origin */
 #pragma unroll 1
-    for (int j = (int)lane; j < FM_CELLS; j += 32) {
-      const int off = org + (int)wtab[j];
-      if (gcs) gcs[off] = pb[j];
-      if (gls) {
-#pragma unroll
-        for (int l = 0; l < GW_FM_LAYERS; ++l) gls[l * area + off] = pl[l * FM_CELLS + j];
-      }
-    }
+    for (int j = (int)lane; j < FM_CELLS; j += 32) gcs[org + (int)wtab[j]] = pb[j];
   }
 }
 
@@ -343,13 +428,26 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_co
   __shared__ FmStatic S;
   __shared__ __align__(16) uint32_t s_words[FM_WARPS][40];
   __shared__ uint32_t s_x[FM_WARPS][FM_X_WORDS];         /* fire-update scratch */
+  __shared__ double s_ub[FM_WARPS][FM_UBUF];             /* the uniform draws of one frame */
   __shared__ uint32_t s_allowed[FM_S + 1], s_extw[FM_SLOTS + 1];
-  __shared__ __align__(16) uint8_t s_planes[FM_WARPS][FM_PLANE_BYTES];
+  __shared__ __align__(16) uint8_t s_pb[FM_WARPS][FM_PB_BYTES];
+  __shared__ uint32_t s_em[FM_WARPS][FM_EM_WORDS];       /* layer maps and the bit strings of the layer tensors */
+  __shared__ uint32_t s_gtmpl[FM_G_WORDS];               /* the view string of an empty board: ones in the rows of the '#' layer */
+  __shared__ __align__(8) uint2 s_lut[256];              /* byte b -> its eight bits as 0 / 1 bytes */
   __shared__ uint16_t s_wtab[FM_CELLS + 1];
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(a.st);
     for (uint32_t i = threadIdx.x; i < sizeof(FmStatic) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(&S)[i] = src[i];
     for (uint32_t j = threadIdx.x; j < FM_CELLS; j += blockDim.x) s_wtab[j] = (uint16_t)((j / FM_S) * GW_FM_SCROP + j % FM_S);
+    for (uint32_t b = threadIdx.x; b < 256; b += blockDim.x)
+      s_lut[b] = make_uint2(((b & 15u) * 0x00204081u) & 0x01010101u, ((b >> 4) * 0x00204081u) & 0x01010101u);
+    for (uint32_t w = threadIdx.x; w < FM_G_WORDS; w += blockDim.x) {
+      /* bits [1089, 2178) -- the '#' layer pads with 1 */
+      const int lo = GW_FM_SCROP * GW_FM_SCROP - 32 * (int)w, hi = 2 * GW_FM_SCROP * GW_FM_SCROP - 32 * (int)w;
+      const uint32_t mlo = lo <= 0 ? 0xffffffffu : lo >= 32 ? 0u : 0xffffffffu << lo;
+      const uint32_t mhi = hi <= 0 ? 0u : hi >= 32 ? 0xffffffffu : (1u << hi) - 1u;
+      s_gtmpl[w] = mlo & mhi;
+    }
   }
   __syncthreads();
   if (threadIdx.x < FM_S) {                              /* per row: cells a fire may spread to (:571-577) */
@@ -428,10 +526,11 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_co
     if (!S.two_workers) { ord[1] = 2; ord[2] = -1; }
     if (a.order) { ord[0] = a.order[env * 3]; ord[1] = a.order[env * 3 + 1]; ord[2] = a.order[env * 3 + 2]; }
     else if (S.randomize) {
+      const uint4 rs = fm_philox(a, env, 32767u);          /* draws 65534 (kk = 1) and 65535 (kk = 2) of the call */
 #pragma unroll
       for (int kk = 2; kk >= 1; --kk) {
         if (kk == 2 && !S.two_workers) continue;
-        const int j = (int)(fm_uniform(a, env, 65533u + (uint32_t)kk) * (kk + 1));
+        const int j = (int)((kk == 2 ? fm_u53(rs.z, rs.w) : fm_u53(rs.x, rs.y)) * (kk + 1));
         const int32_t t = ord[kk];
         ord[kk] = j == 0 ? ord[0] : j == 1 ? ord[1] : ord[2];
         if (j == 0) ord[0] = t; else if (j == 1) ord[1] = t; else ord[2] = t;
@@ -500,7 +599,7 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_co
           }
         }
       }
-      ext_fires = fm_fire_update(S, a, env, fire, s_x[warp], s_allowed, s_extw, pos, at_w, countdown, k, lane);
+      ext_fires = fm_fire_update(S, a, env, fire, s_x[warp], s_allowed, s_extw, pos, at_w, countdown, k, lane, s_ub[warp]);
       r[5] += (double)ext_fires * S.rewards[GW_FM_R_SUP_EXTERNAL_FIRE];
       if ((S.flags[pos[2]] & FM_F_TERRITORY) && ext_fires == 0) r[6] += S.rewards[GW_FM_R_SUP_TRESPASSING];
       if (frame >= S.max_iterations) over = true;                     /* pycolab_interface_ma.py:429-430 */
@@ -543,7 +642,7 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_co
       if (a.step_type) a.step_type[env * 3 + lane] = (uint8_t)v;
     }
   }
-  fm_emit_obs(S, a, env, fire, pos, s_planes[warp], s_wtab, lane);
+  fm_emit_obs(S, a, env, fire, pos, s_pb[warp], s_em[warp], s_gtmpl, s_lut, s_wtab, lane);
 
   /* ---- pack + store state ---- */
   if (!a.is_reset || write_out) {

@@ -52,10 +52,13 @@ typedef struct {
 
 void or_philox(uint64_t seed, uint64_t env, uint64_t step, uint32_t out[4]);   /* gw_oracle.c */
 
+/* draw k of the call: one Philox4x32-10 evaluation per PAIR of draws (counter call * 65536 + k / 2; words 0-1 serve the even
+ * draw, words 2-3 the odd one) -- the stream definition the CUDA kernel shares (csrc/gwsim_fm.cuh fm_uniform) */
 static double philox_uniform(const FOracle* o, int64_t env, uint32_t k) {
   uint32_t r[4];
-  or_philox(o->seed, (uint64_t)(o->env_index_base + env), o->call_no * 65536ull + k, r);
-  return (double)((((uint64_t)r[0] << 32) | r[1]) >> 11) * (1.0 / 9007199254740992.0);
+  or_philox(o->seed, (uint64_t)(o->env_index_base + env), o->call_no * 65536ull + (k >> 1), r);
+  const uint32_t hi = (k & 1u) ? r[2] : r[0], lo = (k & 1u) ? r[3] : r[1];
+  return (double)((((uint64_t)hi << 32) | lo) >> 11) * (1.0 / 9007199254740992.0);
 }
 
 /* Engine._render, z_order ['-','W','F','B','1','2','S'] (firemaker_ex_ma.py:346-350) */

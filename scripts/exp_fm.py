@@ -2,11 +2,14 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+from ai_safety_gridworlds_b200 import _abi
+if os.environ.get("GWSIM_LIB"):
+    _abi.LIB_PATH = os.environ["GWSIM_LIB"]          # A/B against another build of the library
 from ai_safety_gridworlds_b200.firemaker_env import FiremakerVectorEnv
 from ai_safety_gridworlds_b200.vector_env import _ptr
 dev = torch.device("cuda", 0)
 N = int(os.environ.get("N", 262144))
-for cube, crops, lcrops in [(True, True, True), (True, True, False), (False, False, False)]:
+for cube, crops, lcrops in [(True, True, True), (False, False, False)]:
     env = FiremakerVectorEnv(N, device=dev, seed=1, autoreset_mode=1, want_cube=cube, want_crops=crops, want_layer_crops=lcrops)
     acts = [torch.randint(0, 5, (N, 3), dtype=torch.int32, device=dev) for _ in range(8)]
     ptrs = [_ptr(a) for a in acts]
