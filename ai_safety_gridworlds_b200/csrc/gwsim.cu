@@ -2096,7 +2096,8 @@ int gw_fm_create(const GwFmConfig* cfg, int64_t n_envs, int device, int64_t env_
   if (ce == cudaSuccess) ce = cudaMemset(h->d_claim, 0, sizeof(unsigned long long));
   if (ce == cudaSuccess) ce = ma_stats_alloc(&h->d_stats);
   int per_sm = 0, sms = 0;
-  if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gw_fm_kernel, FM_WARPS * 32, 0);
+  if (ce == cudaSuccess) ce = cudaFuncSetAttribute(gw_fm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FM_DYN_BYTES);
+  if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gw_fm_kernel, FM_WARPS * 32, (size_t)FM_DYN_BYTES);
   if (ce == cudaSuccess) ce = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   if (ce != cudaSuccess) { cudaFree(h->d_static); cudaFree(h->d_claim); cudaFree(h->d_stats); delete h; return fail(GW_ERR_CUDA, "firemaker tables: %s", cudaGetErrorString(ce)); }
   h->grid = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 1);
@@ -2123,14 +2124,15 @@ static int fm_launch(GwFmHandle h, FmArgs& a, void* state, const GwFmObs* obs, c
   if (out) { a.reward_w = out->reward_workers; a.reward_s = out->reward_supervisor; a.terminated = out->terminated; a.step_type = out->step_type; }
   a.seed = h->seed; a.call_no = ++h->call_no; a.env_index_base = h->env_index_base; a.n = h->n;
   CUDA_TRY(cudaSetDevice(h->device));
-  int64_t grid = (h->n + FM_WARPS - 1) / FM_WARPS;
-  if (grid > h->grid) grid = h->grid;                           /* persistent: one wave, warps claim environments */
+  const int64_t nbatches = (h->n + FM_BATCH - 1) / FM_BATCH;
+  int64_t grid = (nbatches + FM_WARPS - 1) / FM_WARPS;
+  if (grid > h->grid) grid = h->grid;                           /* persistent: one wave, warps claim batches of FM_BATCH games */
   a.claim_counter = h->d_claim;
   a.claim_base = h->claim_base;
   a.stats = h->d_stats;
-  gw_fm_kernel<<<(unsigned)grid, FM_WARPS * 32, 0, stream>>>(a);
+  gw_fm_kernel<<<(unsigned)grid, FM_WARPS * 32, (size_t)FM_DYN_BYTES, stream>>>(a);
   CUDA_TRY(cudaGetLastError());                                /* a refused launch claims nothing: the host base stays in step */
-  h->claim_base += (unsigned long long)h->n + (unsigned long long)grid * FM_WARPS;   /* every environment once + one failing claim per warp */
+  h->claim_base += (unsigned long long)nbatches + (unsigned long long)grid * FM_WARPS;   /* every batch once + one failing claim per warp */
   h->launches += 1;
   return GW_OK;
 }

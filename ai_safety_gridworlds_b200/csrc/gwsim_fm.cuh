@@ -31,6 +31,8 @@
 #define FM_B 21                         /* bordered side: 17 + 2 + 2 */
 #define FM_SLOTS 10                     /* ceil(289 / 32) */
 #define FM_WARPS 8
+#define FM_BATCH 16                     /* games per warp batch: the scalar game logic runs lane per game */
+#define FM_BST 44                       /* words between the states of a batch in shared memory (40 + padding against bank conflicts) */
 
 enum { FM_F_WALL = 1, FM_F_WORKSHOP = 2, FM_F_BUTTON = 4, FM_F_TERRITORY = 8 };
 
@@ -421,17 +423,25 @@ __device__ __forceinline__ void fm_emit_obs(const FmStatic& S, const FmArgs& a, 
   }
 }
 
+/* byte offsets of a warp's working set in dynamic shared memory (16-byte aligned pieces) */
+#define FM_UP16(x) (((x) + 15) & ~15)
+#define FM_OFF_BST 0
+#define FM_OFF_BR (FM_OFF_BST + FM_UP16(FM_BATCH * FM_BST * 4))
+#define FM_OFF_X (FM_OFF_BR + FM_UP16(FM_BATCH * 7 * 8))
+#define FM_OFF_UB (FM_OFF_X + FM_UP16(FM_X_WORDS * 4))          /* the draws (fire update) and the emission strings are never */
+#define FM_OFF_EM FM_OFF_UB                                       /* live at the same time: they share one region                */
+#define FM_OFF_PB (FM_OFF_EM + FM_UP16(FM_EM_WORDS * 4))
+#define FM_WARP_BYTES (FM_OFF_PB + FM_UP16(FM_PB_BYTES) > FM_OFF_UB + FM_UP16(FM_UBUF * 8) ? FM_OFF_PB + FM_UP16(FM_PB_BYTES) : FM_OFF_UB + FM_UP16(FM_UBUF * 8))
+#define FM_DYN_BYTES (FM_WARPS * FM_WARP_BYTES)
+
 /* state words (AoS, GW_FM_STATE_WORDS = 10 x 16 bytes per environment):
  *   w0: frame | countdown << 16 | st0 << 24 | st1 << 26 | st2 << 28 ; pos0 | pos1 << 16 ; pos2 | ext_fires << 16 ; spare
  *   w1, w2, w3.xy: fire bits (289), w3.zw spare;  w4, w5: 15 visit counters (u16);  w6..w9: 7 cumulative rewards (f64) */
-__global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_constant__ FmArgs a) {
+__global__ void __launch_bounds__(FM_WARPS * 32, 3) gw_fm_kernel(const __grid_constant__ FmArgs a) {
   __shared__ FmStatic S;
-  __shared__ __align__(16) uint32_t s_words[FM_WARPS][40];
-  __shared__ uint32_t s_x[FM_WARPS][FM_X_WORDS];         /* fire-update scratch */
-  __shared__ double s_ub[FM_WARPS][FM_UBUF];             /* the uniform draws of one frame */
+  /* per-warp working set in dynamic shared memory (FM_WARP_BYTES each; more than the 48 KB a kernel may declare statically) */
+  extern __shared__ __align__(16) uint8_t fm_dyn[];
   __shared__ uint32_t s_allowed[FM_S + 1], s_extw[FM_SLOTS + 1];
-  __shared__ __align__(16) uint8_t s_pb[FM_WARPS][FM_PB_BYTES];
-  __shared__ uint32_t s_em[FM_WARPS][FM_EM_WORDS];       /* layer maps and the bit strings of the layer tensors */
   __shared__ uint32_t s_gtmpl[FM_G_WORDS];               /* the view string of an empty board: ones in the rows of the '#' layer */
   __shared__ __align__(8) uint2 s_lut[256];              /* byte b -> its eight bits as 0 / 1 bytes */
   __shared__ uint16_t s_wtab[FM_CELLS + 1];
@@ -466,12 +476,23 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_co
   }
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  uint32_t* words = s_words[warp];
-  uint32_t* fire = words + 4;                          /* the fire curtain: 289 bits, bit cell & 31 of word cell >> 5 (state words 1-3) */
-  /* Persistent warps, dynamic environment queue: a warp claims one environment at a time with one atomicAdd
-   * (environments with many fires take several times longer than quiet ones; with a static assignment the
-   * warps of a CTA idle until its slowest environment is done).  The counter is never reset: the host passes
-   * the value it has after all earlier launches, and every warp makes exactly one failing claim per launch. */
+  uint8_t* const wmem = fm_dyn + warp * FM_WARP_BYTES;
+  uint32_t* __restrict__ bst = reinterpret_cast<uint32_t*>(wmem + FM_OFF_BST);   /* the batch's state words: environment e at bst + e * FM_BST */
+  double* __restrict__ br = reinterpret_cast<double*>(wmem + FM_OFF_BR);         /* the batch's step rewards: environment e at br + e * 7 */
+  double* const w_ub = reinterpret_cast<double*>(wmem + FM_OFF_UB);              /* the uniform draws of one frame */
+  uint32_t* const w_x = reinterpret_cast<uint32_t*>(wmem + FM_OFF_X);            /* fire-update scratch */
+  uint32_t* const w_em = reinterpret_cast<uint32_t*>(wmem + FM_OFF_EM);          /* layer maps and the bit strings of the layer tensors */
+  uint8_t* const w_pb = wmem + FM_OFF_PB;                                        /* the rendered board as characters */
+  /* Persistent warps, dynamic queue of FM_BATCH-environment batches (one atomicAdd per batch; the counter is never reset: the
+   * host passes the value it has after all earlier launches, and every warp makes exactly one failing claim per launch).
+   *
+   * Inside a batch the work is split by what it parallelises over:
+   *   - everything scalar per game -- the acting agent's move, visit counters, stop button, workshop, rewards, step types,
+   *     the shuffle -- runs LANE PER ENVIRONMENT (lane e plays environment e of the batch), so one warp instruction serves
+   *     FM_BATCH games instead of one;
+   *   - the fire update and the observation emission need the whole warp for one game (a 5x5 stencil over 289 cells, 14 KB of
+   *     output): the warp walks over the batch's games in turn, the scalars of game e broadcast from lane e.  Games with no
+   *     fire and no working worker skip the fire update altogether. */
   auto claim = [&]() -> int64_t {
     unsigned long long v = 0;
     if (lane == 0) v = atomicAdd(a.claim_counter, 1ull) - a.claim_base;
@@ -480,69 +501,87 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_co
      * such a claim counts as "queue exhausted", never as work */
     return got < 0 ? ((int64_t)1 << 60) : got;
   };
+  const int64_t nbatches = (a.n + FM_BATCH - 1) / FM_BATCH;
   long long stat_acc = 0;                              /* lane k accumulates raw statistics slot k of this warp's environments */
-  int64_t env_next = claim();
+  int64_t batch_next = claim();
 #pragma unroll 1
   for (;;) {
-  const int64_t env = env_next;
-  if (env >= a.n) break;
-  env_next = claim();                                  /* consumed after this environment: the atomic's latency is hidden */
+  const int64_t batch = batch_next;
+  if (batch >= nbatches) break;
+  batch_next = claim();                                /* consumed after this batch: the atomic's latency is hidden */
+  const int64_t env0 = batch * FM_BATCH;
+  const int nb = (int)min((int64_t)FM_BATCH, a.n - env0);
+  const bool mine = (int)lane < nb;
+  const int64_t env = env0 + (mine ? (int64_t)lane : 0);
 
-  /* ---- load + decode ---- */
-  if (lane < GW_FM_STATE_WORDS) reinterpret_cast<uint4*>(words)[lane] = a.state[env * GW_FM_STATE_WORDS + lane];
+  /* ---- load (coalesced: the batch's states are nb * 160 contiguous bytes) + decode, lane per environment ---- */
   __syncwarp();
-  if (lane == 0) { fire[FM_SLOTS - 1] &= (1u << (FM_CELLS - 32 * (FM_SLOTS - 1))) - 1u; fire[FM_SLOTS] = 0u; fire[FM_SLOTS + 1] = 0u; }   /* garbage state never sets bits beyond the board */
-  int32_t frame = (int32_t)(words[0] & 0xffff), countdown = (int32_t)((words[0] >> 16) & 0xff);
-  int32_t st[3] = {(int32_t)((words[0] >> 24) & 3u), (int32_t)((words[0] >> 26) & 3u), (int32_t)((words[0] >> 28) & 3u)};
-  int32_t pos[3] = {(int32_t)(words[1] & 0xffff), (int32_t)(words[1] >> 16), (int32_t)(words[2] & 0xffff)};
-  int32_t ext_fires = (int32_t)(words[2] >> 16);
+  for (int i = (int)lane; i < nb * GW_FM_STATE_WORDS; i += 32) {
+    const int e = i / GW_FM_STATE_WORDS, q = i - e * GW_FM_STATE_WORDS;
+    reinterpret_cast<uint4*>(bst + e * FM_BST)[q] = a.state[env0 * GW_FM_STATE_WORDS + i];
+  }
+  __syncwarp();
+  uint32_t* __restrict__ words = bst + (mine ? lane : 0u) * FM_BST;
+  uint32_t* __restrict__ fire = words + 4;             /* the fire curtain: 289 bits, bit cell & 31 of word cell >> 5 (state words 1-3) */
+  double* __restrict__ r = br + (mine ? lane : 0u) * 7;
+  int32_t frame = 0, countdown = 0, ext_fires = 0;
+  int32_t st[3] = {0, 0, 0}, pos[3] = {0, 0, 0};
+  if (mine) {
+    fire[FM_SLOTS - 1] &= (1u << (FM_CELLS - 32 * (FM_SLOTS - 1))) - 1u; fire[FM_SLOTS] = 0u; fire[FM_SLOTS + 1] = 0u;   /* garbage state never sets bits beyond the board */
+    frame = (int32_t)(words[0] & 0xffff); countdown = (int32_t)((words[0] >> 16) & 0xff);
+    st[0] = (int32_t)((words[0] >> 24) & 3u); st[1] = (int32_t)((words[0] >> 26) & 3u); st[2] = (int32_t)((words[0] >> 28) & 3u);
+    pos[0] = (int32_t)(words[1] & 0xffff); pos[1] = (int32_t)(words[1] >> 16); pos[2] = (int32_t)(words[2] & 0xffff);
+    ext_fires = (int32_t)(words[2] >> 16);
 #pragma unroll
-  for (int k = 0; k < 3; ++k) if (pos[k] >= FM_CELLS) pos[k] = S.start[k];      /* garbage state never indexes outside the board */
-  if (!S.two_workers) pos[1] = 0xffff;                                           /* no worker '2': matches no cell */
-  /* the 15 visit counters (words 16..23) and the 7 cumulative rewards (words 24..37) stay in the shared-memory
-   * copy of the state and are updated in place by lane 0: keeping them out of registers doubles the occupancy */
-  __syncwarp();
-
+    for (int k = 0; k < 3; ++k) if (pos[k] >= FM_CELLS) pos[k] = S.start[k];      /* garbage state never indexes outside the board */
+    if (!S.two_workers) pos[1] = 0xffff;                                           /* no worker '2': matches no cell */
+#pragma unroll
+    for (int q = 0; q < 7; ++q) r[q] = 0.0;
+  }
+  /* the 15 visit counters (words 16..23) and the 7 cumulative rewards (words 24..37) stay in the shared-memory copy of the
+   * state and are updated in place by the lane that plays the game */
   auto do_reset = [&]() {
     frame = 0; countdown = 0; ext_fires = 0;
 #pragma unroll
     for (int k = 0; k < 3; ++k) { pos[k] = S.start[k]; st[k] = 0; }
-    __syncwarp();
-    if (lane < 24) words[16 + lane] = 0;
-    if (lane < FM_SLOTS + 2) fire[lane] = 0;
-    __syncwarp();
+    for (int q = 4; q < 40; ++q) words[q] = 0;
   };
 
-  double r[7] = {0, 0, 0, 0, 0, 0, 0};
   int32_t out_st[3] = {0, 0, 0};
-  bool write_out = true;
-  if (a.is_reset) {
-    write_out = !a.reset_mask || a.reset_mask[env] != 0;
-    if (write_out) do_reset();
-  } else if (st[0] >= 2 && (st[1] >= 2 || !S.two_workers) && st[2] >= 2) {
-    do_reset();                                        /* rl/pycolab_interface_ma.py:206-213: every agent is done -> new game, FIRST */
-  } else {
-    int32_t ord[3] = {0, 1, 2};
-    if (!S.two_workers) { ord[1] = 2; ord[2] = -1; }
-    if (a.order) { ord[0] = a.order[env * 3]; ord[1] = a.order[env * 3 + 1]; ord[2] = a.order[env * 3 + 2]; }
-    else if (S.randomize) {
-      const uint4 rs = fm_philox(a, env, 32767u);          /* draws 65534 (kk = 1) and 65535 (kk = 2) of the call */
+  bool write_out = mine, play = false, over = false;
+  int32_t ord[3] = {0, 1, 2};
+  if (mine) {
+    if (a.is_reset) {
+      write_out = !a.reset_mask || a.reset_mask[env] != 0;
+      if (write_out) do_reset();
+    } else if (st[0] >= 2 && (st[1] >= 2 || !S.two_workers) && st[2] >= 2) {
+      do_reset();                                      /* rl/pycolab_interface_ma.py:206-213: every agent is done -> new game, FIRST */
+    } else {
+      play = true;
+      if (!S.two_workers) { ord[1] = 2; ord[2] = -1; }
+      if (a.order) { ord[0] = a.order[env * 3]; ord[1] = a.order[env * 3 + 1]; ord[2] = a.order[env * 3 + 2]; }
+      else if (S.randomize) {
+        const uint4 rs = fm_philox(a, env, 32767u);    /* draws 65534 (kk = 1) and 65535 (kk = 2) of the call */
 #pragma unroll
-      for (int kk = 2; kk >= 1; --kk) {
-        if (kk == 2 && !S.two_workers) continue;
-        const int j = (int)((kk == 2 ? fm_u53(rs.z, rs.w) : fm_u53(rs.x, rs.y)) * (kk + 1));
-        const int32_t t = ord[kk];
-        ord[kk] = j == 0 ? ord[0] : j == 1 ? ord[1] : ord[2];
-        if (j == 0) ord[0] = t; else if (j == 1) ord[1] = t; else ord[2] = t;
+        for (int kk = 2; kk >= 1; --kk) {
+          if (kk == 2 && !S.two_workers) continue;
+          const int j = (int)((kk == 2 ? fm_u53(rs.z, rs.w) : fm_u53(rs.x, rs.y)) * (kk + 1));
+          const int32_t t = ord[kk];
+          ord[kk] = j == 0 ? ord[0] : j == 1 ? ord[1] : ord[2];
+          if (j == 0) ord[0] = t; else if (j == 1) ord[1] = t; else ord[2] = t;
+        }
       }
     }
-    uint32_t k = 0;
-    bool over = false;
+  }
+  uint32_t k = 0;                                      /* running draw index of this lane's game within the call */
 #pragma unroll 1
-    for (int t = 0; t < 3; ++t) {
-      if (ord[t] < 0) continue;                          /* sub-step left out: an AEC step plays ONE agent's frame (order = {agent, -1, -1}) */
-      const int ag = ord[t] > 2 ? t : ord[t];
-      if (ag == 1 && !S.two_workers) continue;           /* no worker '2' in this game */
+  for (int t = 0; t < 3; ++t) {
+    const int32_t o = t == 0 ? ord[0] : t == 1 ? ord[1] : ord[2];
+    /* sub-step left out: an AEC step plays ONE agent's frame (order = {agent, -1, -1}); no worker '2' in a two-agent game */
+    const int ag = o > 2 ? t : o;
+    const bool playing = play && o >= 0 && !(ag == 1 && !S.two_workers);
+    bool at_w[3] = {false, false, false};
+    if (playing) {
       const int32_t act = a.actions[env * 3 + ag];
       frame += 1;
       /* the acting agent: MazeWalker against '#' and the other agents (:399-400), then update_reward (:430-463) */
@@ -559,22 +598,16 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_co
         }
       }
       if (ag == 0) pos[0] = np; else if (ag == 1) pos[1] = np; else pos[2] = np;
-      const int roff = ag == 0 ? 0 : ag == 1 ? 2 : 4;
-      if (act != GW_ACT_NOOP) {
-        const double mv = ag == 2 ? S.rewards[GW_FM_R_SUP_MOVEMENT] : S.rewards[GW_FM_R_AGENT_MOVEMENT];
-        if (roff == 0) r[0] += mv; else if (roff == 2) r[2] += mv; else r[4] += mv;
-      }
+      if (act != GW_ACT_NOOP) r[ag * 2] += ag == 2 ? S.rewards[GW_FM_R_SUP_MOVEMENT] : S.rewards[GW_FM_R_AGENT_MOVEMENT];
       {
         const uint8_t f = S.flags[np];
-        const int32_t burning = (int32_t)((fire[np >> 5] >> (np & 31)) & 1u);
-        if (lane == 0) {
-          const uint32_t inc[5] = {np != S.static2 ? 1u : 0u, (f & FM_F_TERRITORY) ? 1u : 0u, (f & FM_F_WORKSHOP) ? 1u : 0u, (uint32_t)burning, (f & FM_F_BUTTON) ? 1u : 0u};
+        const uint32_t burning = (fire[np >> 5] >> (np & 31)) & 1u;
+        const uint32_t inc[5] = {np != S.static2 ? 1u : 0u, (f & FM_F_TERRITORY) ? 1u : 0u, (f & FM_F_WORKSHOP) ? 1u : 0u, burning, (f & FM_F_BUTTON) ? 1u : 0u};
 #pragma unroll
-          for (int j = 0; j < 5; ++j) {
-            const int q = ag * 5 + j, sh = (q & 1) * 16;
-            const uint32_t w = words[16 + (q >> 1)];
-            words[16 + (q >> 1)] = (w & ~(0xffffu << sh)) | ((((w >> sh) + inc[j]) & 0xffffu) << sh);
-          }
+        for (int j = 0; j < 5; ++j) {
+          const int q = ag * 5 + j, sh = (q & 1) * 16;
+          const uint32_t w = words[16 + (q >> 1)];
+          words[16 + (q >> 1)] = (w & ~(0xffffu << sh)) | ((((w >> sh) + inc[j]) & 0xffffu) << sh);
         }
       }
       /* StopButtonDrape.update */
@@ -586,7 +619,6 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_co
         }
       countdown = max(0, countdown - 1);
       /* WorkshopDrape.update */
-      bool at_w[3];
 #pragma unroll
       for (int p = 0; p < 3; ++p) {
         at_w[p] = pos[p] < FM_CELLS && (S.flags[pos[p]] & FM_F_WORKSHOP) != 0;
@@ -595,71 +627,107 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_co
           else if (countdown == 0) {
             r[1] += S.rewards[GW_FM_R_WORKSHOP_WORK];
             if (S.two_workers) r[3] += S.rewards[GW_FM_R_WORKSHOP_WORK];          /* firemaker_ex_ma.py:512-513 */
-            if (p == 0) r[0] += S.rewards[GW_FM_R_WORKSHOP_ENERGY]; else if (p == 1) r[2] += S.rewards[GW_FM_R_WORKSHOP_ENERGY]; else r[4] += S.rewards[GW_FM_R_WORKSHOP_ENERGY];
+            r[p * 2] += S.rewards[GW_FM_R_WORKSHOP_ENERGY];
           }
         }
       }
-      ext_fires = fm_fire_update(S, a, env, fire, s_x[warp], s_allowed, s_extw, pos, at_w, countdown, k, lane, s_ub[warp]);
+    }
+    /* FireDrape.update: the whole warp, one game at a time.  A game with no fire and no working worker has no candidates and
+     * nothing burning: no draws, zero external fires (the early exit of fm_fire_update). */
+    bool burning_any = false;
+    if (playing) {
+      uint32_t acc = 0;
+#pragma unroll
+      for (int q = 0; q < FM_SLOTS; ++q) acc |= fire[q];
+      burning_any = acc != 0u;
+    }
+    const bool fire_call = playing && (burning_any || (countdown == 0 && (at_w[0] || at_w[1])));
+    if (playing && !fire_call) ext_fires = 0;
+    uint32_t todo = __ballot_sync(FULL, fire_call);
+#pragma unroll 1
+    while (todo) {
+      const int e = __ffs((int)todo) - 1;
+      todo &= todo - 1u;
+      const int32_t pe[3] = {__shfl_sync(FULL, pos[0], e), __shfl_sync(FULL, pos[1], e), __shfl_sync(FULL, pos[2], e)};
+      const uint32_t aw = __shfl_sync(FULL, (uint32_t)at_w[0] | ((uint32_t)at_w[1] << 1) | ((uint32_t)at_w[2] << 2), e);
+      const bool awe[3] = {(aw & 1u) != 0u, (aw & 2u) != 0u, (aw & 4u) != 0u};
+      const int32_t cde = __shfl_sync(FULL, countdown, e);
+      uint32_t ke = __shfl_sync(FULL, k, e);
+      const int ext = fm_fire_update(S, a, env0 + e, bst + e * FM_BST + 4, w_x, s_allowed, s_extw, pe, awe, cde, ke, lane, w_ub);
+      if ((int)lane == e) { ext_fires = ext; k = ke; }
+    }
+    __syncwarp();
+    if (playing) {
       r[5] += (double)ext_fires * S.rewards[GW_FM_R_SUP_EXTERNAL_FIRE];
       if ((S.flags[pos[2]] & FM_F_TERRITORY) && ext_fires == 0) r[6] += S.rewards[GW_FM_R_SUP_TRESPASSING];
       if (frame >= S.max_iterations) over = true;                     /* pycolab_interface_ma.py:429-430 */
     }
-    if (lane == 0) {
+  }
+  if (play) {
 #pragma unroll
-      for (int q = 0; q < 7; ++q) {
-        const uint2 v = d2u(u2d(words[24 + 2 * q], words[25 + 2 * q]) + r[q]);
-        words[24 + 2 * q] = v.x; words[25 + 2 * q] = v.y;
-      }
+    for (int q = 0; q < 7; ++q) {
+      const uint2 v = d2u(u2d(words[24 + 2 * q], words[25 + 2 * q]) + r[q]);
+      words[24 + 2 * q] = v.x; words[25 + 2 * q] = v.y;
     }
 #pragma unroll
     for (int p = 0; p < 3; ++p) {                                     /* :232-239 */
       st[p] = (p == 1 && !S.two_workers) ? 0 : over ? ((st[p] == 0 || st[p] == 1) ? 2 : 3) : 1;
       out_st[p] = st[p];
     }
-    /* rollout statistics: exact integer sums (returns in 1/65536), one slot per lane */
-    __syncwarp();
-    if (lane == 0) stat_acc += 1;
-    if (over) {
-      if (lane == 1) stat_acc += 1;
-      if (lane == 2) stat_acc += frame;
-      if (lane == 3) stat_acc += S.two_workers ? 3 : 2;
-      if (lane >= GW_MA_STATS_RETURN0 && lane < GW_MA_STATS_RETURN0 + 7) {
-        const uint32_t q = lane - GW_MA_STATS_RETURN0;
-        stat_acc += __double2ll_rn(u2d(words[24 + 2 * q], words[25 + 2 * q]) * GW_MA_STATS_SCALE);
+  }
+  /* rollout statistics: exact integer sums (returns in 1/65536), slot q accumulated by lane q */
+  {
+    const uint32_t played = __ballot_sync(FULL, play), ended = __ballot_sync(FULL, play && over);
+    if (lane == 0) stat_acc += __popc(played);
+    if (ended) {
+      const int frames = __reduce_add_sync(FULL, (play && over) ? frame : 0);
+      if (lane == 1) stat_acc += __popc(ended);
+      if (lane == 2) stat_acc += frames;
+      if (lane == 3) stat_acc += (S.two_workers ? 3 : 2) * __popc(ended);
+#pragma unroll 1
+      for (int q = 0; q < 7; ++q) {
+        long long v = (play && over) ? __double2ll_rn(u2d(words[24 + 2 * q], words[25 + 2 * q]) * GW_MA_STATS_SCALE) : 0ll;
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) v += __shfl_xor_sync(FULL, v, sft);
+        if ((int)lane == GW_MA_STATS_RETURN0 + q) stat_acc += v;
       }
     }
-    __syncwarp();
-    if (over && S.autoreset == GW_AUTORESET_SAME_STEP) do_reset();
   }
+  if (play && over && S.autoreset == GW_AUTORESET_SAME_STEP) do_reset();
 
-  /* ---- outputs ---- */
+  /* ---- outputs: rewards and flags lane per environment, observations by the whole warp game after game ---- */
   if (write_out) {
-    if (a.reward_w && lane < 4) a.reward_w[env * 4 + lane] = (float)(lane == 0 ? r[0] : lane == 1 ? r[1] : lane == 2 ? r[2] : r[3]);
-    if (a.reward_s && lane < 3) a.reward_s[env * 3 + lane] = (float)(lane == 0 ? r[4] : lane == 1 ? r[5] : r[6]);
-    if (lane < 3) {
-      const int32_t v = lane == 0 ? out_st[0] : lane == 1 ? out_st[1] : out_st[2];
-      if (a.terminated) a.terminated[env * 3 + lane] = (uint8_t)(v >= 2);
-      if (a.step_type) a.step_type[env * 3 + lane] = (uint8_t)v;
+    if (a.reward_w) reinterpret_cast<float4*>(a.reward_w)[env] = make_float4((float)r[0], (float)r[1], (float)r[2], (float)r[3]);
+    if (a.reward_s) { a.reward_s[env * 3] = (float)r[4]; a.reward_s[env * 3 + 1] = (float)r[5]; a.reward_s[env * 3 + 2] = (float)r[6]; }
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+      if (a.terminated) a.terminated[env * 3 + p] = (uint8_t)(out_st[p] >= 2);
+      if (a.step_type) a.step_type[env * 3 + p] = (uint8_t)out_st[p];
     }
   }
-  fm_emit_obs(S, a, env, fire, pos, s_pb[warp], s_em[warp], s_gtmpl, s_lut, s_wtab, lane);
-
-  /* ---- pack + store state ---- */
-  if (!a.is_reset || write_out) {
-    __syncwarp();
-    if (lane == 0) {
-      words[0] = (uint32_t)frame | ((uint32_t)countdown << 16) | ((uint32_t)st[0] << 24) | ((uint32_t)st[1] << 26) | ((uint32_t)st[2] << 28);
-      words[1] = (uint32_t)pos[0] | ((uint32_t)pos[1] << 16);
-      words[2] = (uint32_t)pos[2] | ((uint32_t)ext_fires << 16);
-      words[3] = 0;
-      words[14] = 0; words[15] = 0;                      /* words 4..13 already hold the fire curtain */
-      words[38] = 0; words[39] = 0;
-    }
-    __syncwarp();
-    if (lane < GW_FM_STATE_WORDS) a.state[env * GW_FM_STATE_WORDS + lane] = reinterpret_cast<const uint4*>(words)[lane];
+  /* pack (the fire curtain, counters and cumulative rewards are already in place) */
+  if (mine) {
+    words[0] = (uint32_t)frame | ((uint32_t)countdown << 16) | ((uint32_t)st[0] << 24) | ((uint32_t)st[1] << 26) | ((uint32_t)st[2] << 28);
+    words[1] = (uint32_t)pos[0] | ((uint32_t)pos[1] << 16);
+    words[2] = (uint32_t)pos[2] | ((uint32_t)ext_fires << 16);
+    words[3] = 0;
+    words[14] = 0; words[15] = 0;
+    words[38] = 0; words[39] = 0;
   }
   __syncwarp();
-  }  /* environment queue */
+#pragma unroll 1
+  for (int e = 0; e < nb; ++e) {
+    const int32_t pe[3] = {__shfl_sync(FULL, pos[0], e), __shfl_sync(FULL, pos[1], e), __shfl_sync(FULL, pos[2], e)};
+    fm_emit_obs(S, a, env0 + e, bst + e * FM_BST + 4, pe, w_pb, w_em, s_gtmpl, s_lut, s_wtab, lane);
+    __syncwarp();
+  }
+  /* ---- store the states (a masked-out environment of a reset call keeps its state untouched) ---- */
+  const uint32_t keep = __ballot_sync(FULL, mine && (!a.is_reset || write_out));
+  for (int i = (int)lane; i < nb * GW_FM_STATE_WORDS; i += 32) {
+    const int e = i / GW_FM_STATE_WORDS, q = i - e * GW_FM_STATE_WORDS;
+    if ((keep >> e) & 1u) a.state[env0 * GW_FM_STATE_WORDS + i] = reinterpret_cast<const uint4*>(bst + e * FM_BST)[q];
+  }
+  }  /* batch queue */
   if (a.stats && lane < GW_MA_STATS_LEN && stat_acc != 0)
     atomicAdd(a.stats + (blockIdx.x & (GW_STAT_REPLICAS - 1)) * GW_MA_STATS_LEN + lane, (unsigned long long)stat_acc);
 }
