@@ -211,35 +211,51 @@ __device__ __forceinline__ int fm_fire_update(const FmStatic& S, const FmArgs& a
    * of the fp64 work (gw_fm_create checks the bound for the configured probabilities).  The 24 neighbours are visited
    * unconditionally with predicated multiplies -- no data-dependent loop, no divergence between the lanes. */
   uint32_t base = 0;
+  /* the candidates' cells in row-major order: the lane that owns candidate bit `lane` of word s writes its cell at its rank */
+  uint16_t* __restrict__ clist = reinterpret_cast<uint16_t*>(ub + FM_UBUF);
+#pragma unroll 1
+  for (int sl = 0; sl < FM_SLOTS; ++sl) {
+    const uint32_t w = cand[sl];
+    if ((w >> lane) & 1u) clist[pre[sl] + (uint32_t)__popc(w & lt)] = (uint16_t)(32 * sl + (int)lane);
+  }
+  __syncwarp();
   const int vr0 = vs0 >= 0 ? vs0 / FM_S : -100, vc0 = vs0 >= 0 ? vs0 % FM_S : -100;
   const int vr1 = vs1 >= 0 ? vs1 / FM_S : -100, vc1 = vs1 >= 0 ? vs1 % FM_S : -100;
 #pragma unroll 1
-  for (uint32_t j = 0; j < C; j += 32) {
-    const uint32_t kk = j + lane;
-    double u = 1.0;
-    int cell = 0;
-    if (kk < C) {
-      cell = fm_select(cand, pre, kk);
-      const int tr = cell / FM_S, tc = cell % FM_S;
+  for (uint32_t j = 0; j < C; j += 64) {
+    /* two candidates per lane and iteration (ranks j + lane and j + 32 + lane): two independent multiply chains in flight */
+    const uint32_t kkA = j + lane, kkB = kkA + 32u;
+    const bool okA = kkA < C, okB = kkB < C;
+    double uA = 1.0, uB = 1.0;
+    const int cellA = okA ? (int)clist[kkA] : 0, cellB = okB ? (int)clist[kkB] : 0;
+    const int trA = cellA / FM_S, tcA = cellA % FM_S, trB = cellB / FM_S, tcB = cellB % FM_S;
 #pragma unroll 1
-      for (int dr = 0; dr < 5; ++dr) {                       /* rolled: keeps the 25 constants out of registers and the code small */
-        const uint32_t m = rowmask[tr + dr] >> tc;           /* bit q <-> source column tc + q - 2; the target's own bit is 0 (not burning) */
-        const double* __restrict__ c = S.spread_c + dr * 5;
+    for (int dr = 0; dr < 5; ++dr) {                         /* rolled: keeps the 25 constants out of registers and the code small */
+      /* bit q <-> source column tc + q - 2; the target's own bit is 0 (a candidate is not burning) */
+      const uint32_t mA = okA ? rowmask[trA + dr] >> tcA : 0u, mB = okB ? rowmask[trB + dr] >> tcB : 0u;
+      const double* __restrict__ c = S.spread_c + dr * 5;
 #pragma unroll
-        for (int q = 0; q < 5; ++q)
-          if ((m >> q) & 1u) u *= c[q];
+      for (int q = 0; q < 5; ++q) {
+        const double cq = c[q];
+        if ((mA >> q) & 1u) uA *= cq;
+        if ((mB >> q) & 1u) uB *= cq;
       }
-      { const int dr = vr0 - tr, dc = vc0 - tc; if (dr >= -2 && dr <= 2 && dc >= -2 && dc <= 2) u *= S.spread_c[(dr + 2) * 5 + dc + 2]; }
-      { const int dr = vr1 - tr, dc = vc1 - tc; if (dr >= -2 && dr <= 2 && dc >= -2 && dc <= 2) u *= S.spread_c[(dr + 2) * 5 + dc + 2]; }
     }
-    const double p = 1.0 - u;
-    const bool need = p > 0.0;
-    const uint32_t m = __ballot_sync(FULL, need);
-    if (need) {
-      const uint32_t idx = base + __popc(m & lt);
-      if (ub[idx] < p) atomicOr(&newf[cell >> 5], 1u << (cell & 31));
+    if (okA) {
+      { const int dr = vr0 - trA, dc = vc0 - tcA; if (dr >= -2 && dr <= 2 && dc >= -2 && dc <= 2) uA *= S.spread_c[(dr + 2) * 5 + dc + 2]; }
+      { const int dr = vr1 - trA, dc = vc1 - tcA; if (dr >= -2 && dr <= 2 && dc >= -2 && dc <= 2) uA *= S.spread_c[(dr + 2) * 5 + dc + 2]; }
     }
-    base += __popc(m);
+    if (okB) {
+      { const int dr = vr0 - trB, dc = vc0 - tcB; if (dr >= -2 && dr <= 2 && dc >= -2 && dc <= 2) uB *= S.spread_c[(dr + 2) * 5 + dc + 2]; }
+      { const int dr = vr1 - trB, dc = vc1 - tcB; if (dr >= -2 && dr <= 2 && dc >= -2 && dc <= 2) uB *= S.spread_c[(dr + 2) * 5 + dc + 2]; }
+    }
+    const double pA = 1.0 - uA, pB = 1.0 - uB;
+    const bool needA = pA > 0.0, needB = pB > 0.0;
+    const uint32_t bA = __ballot_sync(FULL, needA), bB = __ballot_sync(FULL, needB);
+    if (needA && ub[base + __popc(bA & lt)] < pA) atomicOr(&newf[cellA >> 5], 1u << (cellA & 31));
+    base += __popc(bA);
+    if (needB && ub[base + __popc(bB & lt)] < pB) atomicOr(&newf[cellB >> 5], 1u << (cellB & 31));
+    base += __popc(bB);
   }
   /* pass 2: continuation of the fires that were burning (:619-621); cell 32 s + lane draws number base + its row-major rank */
   __syncwarp();
@@ -277,7 +293,7 @@ __device__ __forceinline__ int fm_fire_update(const FmStatic& S, const FmArgs& a
 #define FM_CB_WORDS 84                                    /* 2601 bits + read-ahead */
 #define FM_G_WORDS 308                                    /* 9801 bits + read-ahead */
 #define FM_EM_WORDS (GW_FM_LAYERS * FM_LAY_PITCH + FM_CB_WORDS + FM_G_WORDS + 1)
-#define FM_PB_BYTES (16 + FM_CELLS + 15)                  /* the board plane, placed at the 16-byte phase of its destination */
+#define FM_PB_BYTES (FM_CELLS + 3 + 32)                   /* the board plane (16-byte aligned) + read-ahead of the shifted copy */
 
 /* copies `count` bytes from shared to global memory; src and dst have the SAME address modulo 16, so the
  * body moves 16 bytes per lane (ld.shared.v4 -> st.global.v4) and only the ragged head and tail use byte stores */
@@ -288,6 +304,24 @@ __device__ __forceinline__ void fm_copy16(uint8_t* __restrict__ dst, const uint8
   uint4* __restrict__ d = reinterpret_cast<uint4*>(dst + head);
   const uint4* __restrict__ q = reinterpret_cast<const uint4*>(src + head);
   for (int k = (int)lane; k < chunks; k += 32) d[k] = q[k];
+  const int tail = head + 16 * chunks + (int)lane;
+  if (tail < count) dst[tail] = src[tail];
+}
+
+/* copies `count` bytes from a 16-byte aligned shared-memory source to a global destination of ANY alignment: the body moves 16
+ * bytes per lane, read as five words and shifted by the byte phase (funnel shifts); byte stores for the ragged head and tail.
+ * The source must be readable up to 16 bytes beyond `count`. */
+__device__ __forceinline__ void fm_copy_shift(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, int count, uint32_t lane) {
+  const int head = min(count, (int)((16u - ((uint32_t)(uintptr_t)dst & 15u)) & 15u));
+  if ((int)lane < head) dst[lane] = src[lane];
+  const int chunks = (count - head) >> 4;
+  uint4* __restrict__ d = reinterpret_cast<uint4*>(dst + head);
+  const uint32_t* __restrict__ q = reinterpret_cast<const uint32_t*>(src) + (head >> 2);
+  const uint32_t sh = ((uint32_t)head & 3u) * 8u;
+  for (int k = (int)lane; k < chunks; k += 32) {
+    const uint32_t w0 = q[4 * k], w1 = q[4 * k + 1], w2 = q[4 * k + 2], w3 = q[4 * k + 3], w4 = q[4 * k + 4];
+    d[k] = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+  }
   const int tail = head + 16 * chunks + (int)lane;
   if (tail < count) dst[tail] = src[tail];
 }
@@ -312,6 +346,7 @@ __device__ __forceinline__ void fm_expand_bits(uint8_t* __restrict__ dst, const 
   if ((int)lane < head) dst[lane] = (uint8_t)((bits[0] >> lane) & 1u);
   const int nblk = (count - head) >> 5;
   uint4* __restrict__ d = reinterpret_cast<uint4*>(dst + head);
+#pragma unroll 2
   for (int b = (int)lane; b < nblk; b += 32) {
     const uint32_t v = __funnelshift_r(bits[b], bits[b + 1], (uint32_t)head);      /* string bits [head + 32 b, head + 32 b + 32) */
     const uint2 t0 = lut[v & 0xffu], t1 = lut[(v >> 8) & 0xffu], t2 = lut[(v >> 16) & 0xffu], t3 = lut[v >> 24];
@@ -329,7 +364,7 @@ __device__ __forceinline__ void fm_emit_obs(const FmStatic& S, const FmArgs& a, 
   uint32_t* __restrict__ cb = em + GW_FM_LAYERS * FM_LAY_PITCH;               /* cube bit string */
   uint32_t* __restrict__ g = cb + FM_CB_WORDS;                                /* supervisor layer-view bit string */
   uint8_t* gboard = a.board ? a.board + env * FM_CELLS : nullptr;
-  uint8_t* pb = pbuf + ((uint32_t)(uintptr_t)gboard & 15u);                   /* at the 16-byte phase of its destination */
+  uint8_t* __restrict__ pb = pbuf;
   /* the nine layer maps, word k by lane k (safety_game_moma.py layers: ' ' = gap AND NOT any other layer) */
   if (lane < FM_LAY_PITCH) {
     const uint32_t k = lane;
@@ -349,15 +384,25 @@ __device__ __forceinline__ void fm_emit_obs(const FmStatic& S, const FmArgs& a, 
     lay[7 * FM_LAY_PITCH + k] = a2;
     lay[8 * FM_LAY_PITCH + k] = in ? S.lay_static[FM_SL_WORKSHOP][k] : 0u;
   }
-  /* the rendered board as characters (z-order: agents over fire over the static drapes) */
-  for (int cell = (int)lane; cell < FM_CELLS; cell += 32) {
-    const bool burning = (fire[cell >> 5] >> lane) & 1u;                       /* cell = 32 k + lane: bit `lane` of word k */
-    pb[cell] = cell == pos[2] ? (uint8_t)'S' : cell == pos[1] ? (uint8_t)'2' : cell == pos[0] ? (uint8_t)'1' : burning ? (uint8_t)'F' : S.base_chr[cell];
+  /* the rendered board as characters (z-order: agents over fire over the static drapes), four cells per lane and round */
+  {
+    const uint32_t* __restrict__ base4 = reinterpret_cast<const uint32_t*>(S.base_chr);
+    uint32_t* __restrict__ pb4 = reinterpret_cast<uint32_t*>(pb);
+#pragma unroll 1
+    for (int j = (int)lane; j < (FM_CELLS + 3) / 4; j += 32) {
+      const uint32_t nib = (fire[j >> 3] >> ((j & 7) * 4)) & 15u;               /* cells 4 j .. 4 j + 3 */
+      const uint32_t m = ((nib * 0x00204081u) & 0x01010101u) * 0xffu;
+      uint32_t w = (base4[j] & ~m) | (0x46464646u & m);                         /* 'F' */
+      if ((pos[0] >> 2) == j) { const uint32_t sh = (uint32_t)(pos[0] & 3) * 8u; w = (w & ~(0xffu << sh)) | ((uint32_t)'1' << sh); }
+      if ((pos[1] >> 2) == j) { const uint32_t sh = (uint32_t)(pos[1] & 3) * 8u; w = (w & ~(0xffu << sh)) | ((uint32_t)'2' << sh); }
+      if ((pos[2] >> 2) == j) { const uint32_t sh = (uint32_t)(pos[2] & 3) * 8u; w = (w & ~(0xffu << sh)) | ((uint32_t)'S' << sh); }
+      pb4[j] = w;
+    }
   }
   if (a.cube) for (int w = (int)lane; w < FM_CB_WORDS; w += 32) cb[w] = 0u;
   if (a.lcrop_s) for (int w = (int)lane; w < FM_G_WORDS; w += 32) g[w] = gtmpl[w];
   __syncwarp();
-  if (gboard) fm_copy16(gboard, pb, FM_CELLS, lane);
+  if (gboard) fm_copy_shift(gboard, pb, FM_CELLS, lane);
   if (a.cube) {
     /* layer l's ten words go to bit 289 l of the cube string */
 #pragma unroll 1
@@ -431,13 +476,14 @@ __device__ __forceinline__ void fm_emit_obs(const FmStatic& S, const FmArgs& a, 
 #define FM_OFF_UB (FM_OFF_X + FM_UP16(FM_X_WORDS * 4))          /* the draws (fire update) and the emission strings are never */
 #define FM_OFF_EM FM_OFF_UB                                       /* live at the same time: they share one region                */
 #define FM_OFF_PB (FM_OFF_EM + FM_UP16(FM_EM_WORDS * 4))
-#define FM_WARP_BYTES (FM_OFF_PB + FM_UP16(FM_PB_BYTES) > FM_OFF_UB + FM_UP16(FM_UBUF * 8) ? FM_OFF_PB + FM_UP16(FM_PB_BYTES) : FM_OFF_UB + FM_UP16(FM_UBUF * 8))
+#define FM_FIRE_BYTES FM_UP16(FM_UBUF * 8 + FM_UBUF * 2)          /* the draws + the candidate list (u16 cells) behind them */
+#define FM_WARP_BYTES (FM_OFF_PB + FM_UP16(FM_PB_BYTES) > FM_OFF_UB + FM_FIRE_BYTES ? FM_OFF_PB + FM_UP16(FM_PB_BYTES) : FM_OFF_UB + FM_FIRE_BYTES)
 #define FM_DYN_BYTES (FM_WARPS * FM_WARP_BYTES)
 
 /* state words (AoS, GW_FM_STATE_WORDS = 10 x 16 bytes per environment):
  *   w0: frame | countdown << 16 | st0 << 24 | st1 << 26 | st2 << 28 ; pos0 | pos1 << 16 ; pos2 | ext_fires << 16 ; spare
  *   w1, w2, w3.xy: fire bits (289), w3.zw spare;  w4, w5: 15 visit counters (u16);  w6..w9: 7 cumulative rewards (f64) */
-__global__ void __launch_bounds__(FM_WARPS * 32, 3) gw_fm_kernel(const __grid_constant__ FmArgs a) {
+__global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_constant__ FmArgs a) {
   __shared__ FmStatic S;
   /* per-warp working set in dynamic shared memory (FM_WARP_BYTES each; more than the 48 KB a kernel may declare statically) */
   extern __shared__ __align__(16) uint8_t fm_dyn[];
