@@ -345,13 +345,17 @@ __device__ __forceinline__ void fm_expand_bits(uint8_t* __restrict__ dst, const 
   const int head = min(count, (int)((16u - ((uint32_t)(uintptr_t)dst & 15u)) & 15u));
   if ((int)lane < head) dst[lane] = (uint8_t)((bits[0] >> lane) & 1u);
   const int nblk = (count - head) >> 5;
-  uint4* __restrict__ d = reinterpret_cast<uint4*>(dst + head);
+  uint4* __restrict__ d = reinterpret_cast<uint4*>(dst + head) + 2 * lane;
+  const uint32_t* __restrict__ bp = bits + lane;
+  const char* __restrict__ lb = reinterpret_cast<const char*>(lut);
 #pragma unroll 2
-  for (int b = (int)lane; b < nblk; b += 32) {
-    const uint32_t v = __funnelshift_r(bits[b], bits[b + 1], (uint32_t)head);      /* string bits [head + 32 b, head + 32 b + 32) */
-    const uint2 t0 = lut[v & 0xffu], t1 = lut[(v >> 8) & 0xffu], t2 = lut[(v >> 16) & 0xffu], t3 = lut[v >> 24];
-    d[2 * b] = make_uint4(t0.x, t0.y, t1.x, t1.y);
-    d[2 * b + 1] = make_uint4(t2.x, t2.y, t3.x, t3.y);
+  for (int b = (int)lane; b < nblk; b += 32, d += 64, bp += 32) {
+    const uint32_t v = __funnelshift_r(bp[0], bp[1], (uint32_t)head);              /* string bits [head + 32 b, head + 32 b + 32) */
+    /* table entries are 8 bytes: byte offset = (bits << 3) & 0x7f8, one shift + one mask per look-up */
+    const uint2 t0 = *reinterpret_cast<const uint2*>(lb + ((v << 3) & 0x7f8u)), t1 = *reinterpret_cast<const uint2*>(lb + ((v >> 5) & 0x7f8u)),
+                t2 = *reinterpret_cast<const uint2*>(lb + ((v >> 13) & 0x7f8u)), t3 = *reinterpret_cast<const uint2*>(lb + ((v >> 21) & 0x7f8u));
+    d[0] = make_uint4(t0.x, t0.y, t1.x, t1.y);
+    d[1] = make_uint4(t2.x, t2.y, t3.x, t3.y);
   }
   const int tail = head + 32 * nblk + (int)lane;
   if (tail < count) dst[tail] = (uint8_t)((bits[tail >> 5] >> (tail & 31)) & 1u);
@@ -590,7 +594,8 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_co
     frame = 0; countdown = 0; ext_fires = 0;
 #pragma unroll
     for (int k = 0; k < 3; ++k) { pos[k] = S.start[k]; st[k] = 0; }
-    for (int q = 4; q < 40; ++q) words[q] = 0;
+#pragma unroll 1
+    for (int q = 4; q < 40; ++q) words[q] = 0;          /* rolled: the lambda is inlined three times */
   };
 
   int32_t out_st[3] = {0, 0, 0};
