@@ -288,6 +288,7 @@ SYMBOLS = [
     ("gw_stats", C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_void_p]),
     ("gw_stats_clear", C.c_int, [C.c_void_p, C.c_void_p]),
     ("gw_random_actions", C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    ("gw_render_rgb", C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     ("gw_launch_count", C.c_int64, [C.c_void_p]),
 ]
 

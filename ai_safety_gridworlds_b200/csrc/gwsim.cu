@@ -1966,6 +1966,45 @@ int gw_random_actions(GwHandle h, uint64_t seed, uint64_t step, int32_t lo, int3
   return GW_OK;
 }
 
+/* rgb[i][c][cell] = lut[3 * board[i][cell] + c]: one thread per (environment, 4 cells); the 768-byte table sits in shared memory */
+__global__ void __launch_bounds__(GW_BLOCK) gw_render_rgb_kernel(const uint8_t* __restrict__ board, int64_t n, int32_t cells, int64_t pitch,
+                                                                 const uint8_t* __restrict__ lut, uint8_t* __restrict__ rgb) {
+  __shared__ uint8_t s_lut[768];
+  for (uint32_t i = threadIdx.x; i < 768; i += blockDim.x) s_lut[i] = lut[i];
+  __syncthreads();
+  const int32_t quads = (cells + 3) >> 2;
+  const int64_t total = n * quads;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t env = t / quads;
+    const int32_t c0 = (int32_t)(t - env * quads) * 4;
+    const uint8_t* src = board + env * pitch + c0;
+    uint8_t* dst = rgb + env * 3 * (int64_t)cells + c0;
+    const int32_t m = min(4, cells - c0);
+    for (int32_t j = 0; j < m; ++j) {
+      const uint32_t ch = src[j];
+      dst[j] = s_lut[3 * ch]; dst[cells + j] = s_lut[3 * ch + 1]; dst[2 * cells + j] = s_lut[3 * ch + 2];
+    }
+  }
+}
+
+int gw_render_rgb(const uint8_t* board, int64_t n, int32_t cells, int64_t board_pitch, const uint8_t* lut, uint8_t* rgb,
+                  int device, void* stream) {
+  if (!board || !lut || !rgb) return fail(GW_ERR_INVALID, "null argument");
+  if (n <= 0 || cells <= 0 || board_pitch < cells) return fail(GW_ERR_INVALID, "n, cells must be positive and board_pitch >= cells");
+  int count = 0;
+  cudaError_t ce = cudaGetDeviceCount(&count);
+  if (ce != cudaSuccess || count == 0)
+    return fail(GW_ERR_NO_DEVICE, "no CUDA device (%s); libgwsim has no CPU fallback", ce == cudaSuccess ? "device count 0" : cudaGetErrorString(ce));
+  if (device < 0 || device >= count) return fail(GW_ERR_INVALID, "device %d out of range (%d devices)", device, count);
+  CUDA_TRY(cudaSetDevice(device));
+  const int64_t total = n * ((cells + 3) >> 2);
+  int64_t grid = (total + GW_BLOCK - 1) / GW_BLOCK;
+  if (grid > 148 * 16) grid = 148 * 16;
+  gw_render_rgb_kernel<<<(unsigned)grid, GW_BLOCK, 0, (cudaStream_t)stream>>>(board, n, cells, board_pitch, lut, rgb);
+  CUDA_TRY(cudaGetLastError());
+  return GW_OK;
+}
+
 int64_t gw_launch_count(GwHandle h) { return h ? h->launches : 0; }
 
 }  /* extern "C" */

@@ -50,13 +50,6 @@ INFO_OBSERVATION_LAYERS_DICT = "info_observation_layers_dict"
 INFO_OBSERVATION_LAYERS_ORDER = "info_observation_layers_order"
 INFO_OBSERVATION_LAYERS_CUBE = "info_observation_layers_cube"
 
-# constructor arguments of the reference wrapper that do not change what the kernel computes
-_WRAPPER_ONLY = ("render_animation_delay", "ascii_observation_format", "ascii_attributes_format",
-                 "attribute_coordinates_in_observation", "layers_in_attribute_observation", "occlusion_in_atribute_layers",
-                 "observable_attribute_categories", "observable_attribute_value_mapping", "use_multi_discrete_action_space",
-                 "agent_character", "np_random", "pre_reset_callback", "post_reset_callback", "pre_step_callback",
-                 "post_step_callback", "render_mode")
-
 
 class DiscreteActionSpace(object):
     """gym.spaces.Discrete(n, start=min_action) as the reference builds it (gridworld_gym_env.py:885-896)."""
@@ -101,8 +94,20 @@ class GridworldGymEnv(object):
                  device=None, scalarise=False, log_columns=None, log_dir="logs", log_filename_comment="", log_arguments=None,
                  log_arguments_to_separate_file=True, gzip_log=False, env_layout_seed=1, trial_no=None, episode_no=None,
                  log_env_index=0, **kwargs):
-        for k in _WRAPPER_ONLY:
-            kwargs.pop(k, None)
+        # the reference wrapper's own constructor arguments (gridworld_gym_env.py:99-133) are honoured or refused, never dropped
+        for k in ("ascii_attributes_format", "layers_in_attribute_observation", "occlusion_in_atribute_layers",
+                  "use_multi_discrete_action_space"):
+            if kwargs.pop(k, False):
+                raise NotImplementedError("%s is not built (agent attributes / multi-discrete actions)" % k)
+        if kwargs.pop("observable_attribute_value_mapping", None):
+            raise NotImplementedError("observable_attribute_value_mapping is not built")
+        if kwargs.pop("agent_character", None) is not None:
+            raise NotImplementedError("agent_character: the Gym wrapper of the CUDA backend serves the single-agent games")
+        self.render_mode = kwargs.pop("render_mode", None)
+        self._callbacks = {k: kwargs.pop(k, None) for k in ("pre_reset_callback", "post_reset_callback", "pre_step_callback", "post_step_callback")}
+        for k in ("render_animation_delay", "ascii_observation_format", "attribute_coordinates_in_observation",
+                  "observable_attribute_categories", "np_random"):
+            kwargs.pop(k, None)     # no effect on these games: no viewer; MO observations are the float board (:191); no attributes
         # CSV logging of SafetyEnvironmentMo (safety_game_mo.py:727-807,1110-1215): one row per played step of environment
         # `log_env_index` (the batch has one log, like the reference's class-level file handle)
         self._logger, self._log_env = None, int(log_env_index)
@@ -133,11 +138,11 @@ class GridworldGymEnv(object):
         self._object_coordinates = bool(object_coordinates_in_observation)
         self._layers_in_observation = bool(layers_in_observation)
         order = list(layers_order_in_cube) if layers_order_in_cube else list(self._spec.layer_order)
-        unknown = [ch for ch in order if ch not in self._spec.layer_order]
-        if unknown:
-            raise ValueError("layers_order_in_cube names layers the environment does not have: %r" % unknown)
+        # a name the game does not have gives an all-zero plane ("cross-environment observation format compatibility",
+        # safety_game_mo.py:497-503)
         self._layers_order = order
-        self._layer_index = torch.tensor([self._spec.layer_order.index(ch) for ch in order], device=self._env.device)
+        self._layer_index = torch.tensor([self._spec.layer_order.index(ch) if ch in self._spec.layer_order else -1 for ch in order],
+                                         dtype=torch.long, device=self._env.device)
         lo, hi = self._spec.action_range
         self.action_space = DiscreteActionSpace(lo, hi, seed)
         vals = list(self._spec.value_mapping.values())
@@ -166,11 +171,11 @@ class GridworldGymEnv(object):
         if self._mo_rewrap:
             self._object_coordinates, self._layers_in_observation = object_coordinates, layers_in_observation
             order = list(layers_order_in_cube) if layers_order_in_cube else list(self._spec.layer_order)
-            unknown = [ch for ch in order if ch not in self._spec.layer_order]
-            if unknown:
-                raise ValueError("layers_order_in_cube names layers the environment does not have: %r" % unknown)
+            # a name the game does not have gives an all-zero plane ("cross-environment observation format compatibility",
+            # safety_game_mo.py:497-503)
             self._layers_order = order
-            self._layer_index = torch.tensor([self._spec.layer_order.index(ch) for ch in order], device=self._env.device)
+            self._layer_index = torch.tensor([self._spec.layer_order.index(ch) if ch in self._spec.layer_order else -1 for ch in order],
+                                             dtype=torch.long, device=self._env.device)
         else:
             self._object_coordinates = self._layers_in_observation = False   # the original suite exposes no layers
             self._layers_order = []
@@ -251,6 +256,10 @@ class GridworldGymEnv(object):
 
     # ------------------------------------------------------------------ stepping
     def reset(self, seed=None, return_info=False, options=None, *args, **kwargs):
+        if self._callbacks["pre_reset_callback"] is not None:          # gridworld_gym_env.py:590-593
+            (allow_reset, seed, args, kwargs) = self._callbacks["pre_reset_callback"](seed, *args, **kwargs)
+            if not allow_reset:
+                return
         if seed is not None:
             self.seed(seed)
         if self._logger is not None:
@@ -263,9 +272,14 @@ class GridworldGymEnv(object):
         self._last_board = None
         obs = self._observation()
         info = self._compute_info(first=True)
-        return self._finish(obs, None, info)[::3]            # (obs, info)
+        obs, info = self._finish(obs, None, info)[::3]       # (obs, info)
+        if self._callbacks["post_reset_callback"] is not None:
+            self._callbacks["post_reset_callback"](obs, info)
+        return obs, info
 
     def step(self, action, *args, **kwargs):
+        if self._callbacks["pre_step_callback"] is not None:           # :470-471
+            action = self._callbacks["pre_step_callback"](action, *args, **kwargs)
         env = self._env
         if self._batched:
             a = action if torch.is_tensor(action) else torch.as_tensor(np.asarray(action), device=env.device)
@@ -282,16 +296,26 @@ class GridworldGymEnv(object):
         info = self._compute_info(first=False)
         obs, reward, terminated, info = self._finish(obs, env.reward, info)
         truncated = torch.zeros_like(env.terminated, dtype=torch.bool) if self._batched else False   # gridworld_gym_env.py:576-577
+        if self._callbacks["post_step_callback"] is not None:
+            self._callbacks["post_step_callback"](action, obs, reward, terminated, truncated, info, *args, **kwargs)
         return obs, reward, terminated, truncated, info
 
     # ------------------------------------------------------------------ helpers
+    def _select_layers(self, cube):
+        """[N, L, H, W] uint8 in the kernel's layer order -> bool [N, len(layers_order_in_cube), H, W]"""
+        idx = self._layer_index
+        out = cube.index_select(1, idx.clamp(min=0)).bool()
+        if bool((idx < 0).any()):
+            out = out & ~(idx < 0).view(1, -1, 1, 1)
+        return out
+
     def _observation(self):
         vb = self._env.value_board
         if self._classic:
             vb = crop_board(vb, self._spec)
         board = vb.unsqueeze(1).clone()                                # state = board[np.newaxis] is a copy (:525-536)
         if self._use_transitions:
-            prev = board if self._last_board is None else self._last_board
+            prev = torch.zeros_like(board) if self._last_board is None else self._last_board     # np.zeros_like(board) at reset (:618-620)
             self._last_board = board
             board = torch.cat([prev, board], dim=1)
         if self._flatten:
@@ -319,7 +343,7 @@ class GridworldGymEnv(object):
         }
         if self._layers_in_observation:
             info[INFO_OBSERVATION_LAYERS_ORDER] = list(self._layers_order)
-            info[INFO_OBSERVATION_LAYERS_CUBE] = crop_board(ex["layers"], spec).index_select(1, self._layer_index).bool()
+            info[INFO_OBSERVATION_LAYERS_CUBE] = self._select_layers(crop_board(ex["layers"], spec))
         if self._object_coordinates:
             info[INFO_OBSERVATION_COORDINATES] = None
         return info
@@ -361,7 +385,7 @@ class GridworldGymEnv(object):
         }
         if self._layers_in_observation:
             info[INFO_OBSERVATION_LAYERS_ORDER] = list(self._layers_order)
-            info[INFO_OBSERVATION_LAYERS_CUBE] = env.cube.index_select(1, self._layer_index).bool()
+            info[INFO_OBSERVATION_LAYERS_CUBE] = self._select_layers(env.cube)
         if self._object_coordinates:
             info[INFO_OBSERVATION_COORDINATES] = None        # materialised lazily for the single-environment form
         return info
@@ -436,7 +460,17 @@ class GridworldGymEnv(object):
         return obs[0].cpu().numpy(), r, bool(env.terminated[0].item()), out
 
     def render(self, mode="ansi"):
-        board = crop_board(self._env.board[0], self._spec).cpu().numpy()
+        """helpers/gridworld_gym_env.py:718-750 of the reference: "ansi" = the board as text (characters joined by blanks),
+        "rgb_array" = the distiller's RGB observation, uint8 [3, H, W] (batched form: a CUDA tensor [N, 3, H, W])
+        (observation_distiller_ex.py:147-189).  "human" (the curses viewer) is out of scope."""
         if mode == "ansi":
-            return "\n".join("".join(chr(c) for c in row) for row in board)
-        raise NotImplementedError("render mode %r (RGB and curses rendering are out of scope, DESIGN.md section 7)" % mode)
+            board = crop_board(self._env.board[0], self._spec).cpu().numpy()
+            return "\n".join(" ".join(chr(c) for c in row) for row in board)
+        if mode == "rgb_array":
+            from .. import render as _render
+            if getattr(self, "_rgb_lut", None) is None:
+                self._rgb_lut = torch.from_numpy(_render.rgb_lut(self._env_name)).to(self._env.device)
+            rgb = _render.render_rgb(crop_board(self._env.board, self._spec).contiguous(), self._rgb_lut)
+            return rgb if self._batched else rgb[0].cpu().numpy()
+        raise NotImplementedError("render mode %r (the curses viewer is out of scope, DESIGN.md section 7)" % mode)
+

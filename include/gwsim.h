@@ -353,6 +353,15 @@ int gw_random_actions(GwHandle h, uint64_t seed, uint64_t step, int32_t lo, int3
 /* Number of kernels this library has launched through this handle (bench.py's gpu_launches). */
 int64_t gw_launch_count(GwHandle h);
 
+/* The `RGB` observation (ObservationToArrayWithRGBEx.__call__, environments/shared/observation_distiller_ex.py:147-189 over
+ * pycolab/rendering.py:491-549 ObservationToArray): rgb[i][c][cell] = lut[3 * board[i][cell] + c], uint8 [n][3][cells], for ANY
+ * of this library's boards (every kernel's `board` tensor holds ASCII codes).  `board_pitch` = bytes between the boards of two
+ * environments (>= cells: the padded rows of the savanna / sokoban / classic tensors).  `lut` = uint8[256][3] in device memory:
+ * the game's colour table already scaled as the reference scales it, (colour / 999.0 * 255.0) truncated to uint8.  Needs no
+ * handle (the table is the caller's); asynchronous on `stream` of device `device`. */
+int gw_render_rgb(const uint8_t* board, int64_t n, int32_t cells, int64_t board_pitch, const uint8_t* lut, uint8_t* rgb,
+                  int device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

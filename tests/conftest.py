@@ -23,7 +23,7 @@ def _all_golden():
 
 def golden_names():
     """Traces of the multi-objective games (island_navigation_ex, boat_race_ex)."""
-    return [n for n in _all_golden() if not n.startswith(("classic_", "firemaker_", "islandma_", "sokoban_big_", "savanna_"))]
+    return [n for n in _all_golden() if not n.startswith(("classic_", "firemaker_", "islandma_", "sokoban_big_", "savanna_", "rgb_", "zoo_"))]
 
 
 def firemaker_golden_names():
@@ -54,6 +54,16 @@ def sokoban_golden_names():
 def savanna_golden_names():
     """Traces of aintelope_savanna through the parallel wrapper (oracle/record_savanna.py)."""
     return [n for n in _all_golden() if n.startswith("savanna_")]
+
+
+def rgb_golden_names():
+    """Boards + RGB observations recorded from the reference's distiller (oracle/record_rgb.py)."""
+    return [n for n in _all_golden() if n.startswith("rgb_")]
+
+
+def zoo_golden_names():
+    """Traces recorded through the reference's PettingZoo parallel wrapper with its wrapper-side options (oracle/record_zoo_wrapper.py)."""
+    return [n for n in _all_golden() if n.startswith("zoo_")]
 
 
 def load_golden(name):
