@@ -123,7 +123,12 @@ class GridworldGymEnv(object):
             raise NotImplementedError("occlusion_in_layers=True: the MO environments force it off (safety_game_mo_base.py)")
         self._batched = num_envs is not None
         n = int(num_envs) if self._batched else 1
-        mode = _abi.GW_AUTORESET_SAME_STEP if self._batched else _abi.GW_AUTORESET_NEXT_STEP
+        # Batched form: a finished environment restarts inside the wrapper's step() -- but AFTER the step's info has been read, so
+        # that `info` (cumulative / average reward, metrics, frame, termination reason) describes the episode that just ENDED, the
+        # way `reward` and `terminated` do, while the returned observation already is the first one of the next episode (the
+        # Gymnasium vector convention; the ended episode's last observation travels as info['final_observation']).  The kernel
+        # therefore runs with the reference's own reset semantics and the wrapper issues the masked gw_reset itself.
+        mode = _abi.GW_AUTORESET_NEXT_STEP
         self._spec = make_spec(env_name, autoreset_mode=mode, **kwargs)      # raises NotImplementedError like factory.py:199-201
         self._flatten = bool(flatten_observations)
         self._sokoban_big = isinstance(self._spec, SokSpec)              # side_effects_sokoban levels 1-3: the gw_sok_* path
@@ -292,9 +297,15 @@ class GridworldGymEnv(object):
             # the call after a terminal timestep restarted the game: the environment stands at a FIRST timestep again
             self._played = int(env.step_type[self._log_env]) != _abi.GW_STEP_FIRST
             self._log_step()
-        obs = self._observation()
         info = self._compute_info(first=False)
-        obs, reward, terminated, info = self._finish(obs, env.reward, info)
+        reward_t, term_t = env.reward, env.terminated
+        if self._batched:
+            reward_t, term_t = env.reward.clone(), env.terminated.clone()
+            vb = crop_board(env.value_board, self._spec) if self._classic else env.value_board
+            info["final_observation"] = vb.unsqueeze(1).clone()        # meaningful where `terminated`
+            env.reset(term_t)                                          # masked gw_reset: new episodes, observations re-rendered
+        obs = self._observation()
+        obs, reward, terminated, info = self._finish(obs, reward_t, info, term_t)
         truncated = torch.zeros_like(env.terminated, dtype=torch.bool) if self._batched else False   # gridworld_gym_env.py:576-577
         if self._callbacks["post_step_callback"] is not None:
             self._callbacks["post_step_callback"](action, obs, reward, terminated, truncated, info, *args, **kwargs)
@@ -400,8 +411,9 @@ class GridworldGymEnv(object):
         d[env.step_type == _abi.GW_STEP_FIRST] = float("nan")
         return d
 
-    def _finish(self, obs, reward, info):
+    def _finish(self, obs, reward, info, terminated=None):
         env = self._env
+        terminated = env.terminated if terminated is None else terminated
         mo_rewrap = self._classic and self._mo_rewrap
         if mo_rewrap and reward is not None:
             reward = reward[:, :1].double()                            # the vector of the one dimension 'REWARD'
@@ -413,7 +425,7 @@ class GridworldGymEnv(object):
             reward = reward.double().sum(dim=1)
         if self._batched:
             r = None if reward is None else reward.double()
-            return obs, r, env.terminated.bool(), info
+            return obs, r, terminated.bool(), info
         # drop-in single environment: numpy, reference shapes
         def host(x):
             if torch.is_tensor(x):

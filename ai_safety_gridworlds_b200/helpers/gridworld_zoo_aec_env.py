@@ -45,7 +45,7 @@ class GridworldZooAecEnv(object):
 
     def __init__(self, env_name, ascii_observation_format=True, seed=None, num_envs=None, device=None, **kwargs):
         self._par = GridworldZooParallelEnv(env_name, ascii_observation_format=ascii_observation_format, seed=seed,
-                                            num_envs=num_envs, device=device, **kwargs)
+                                            num_envs=num_envs, device=device, final_info=False, **kwargs)
         self._batched = num_envs is not None
         self.possible_agents = list(self._par.possible_agents)
         self.agent_name_mapping = dict(self._par.agent_name_mapping)

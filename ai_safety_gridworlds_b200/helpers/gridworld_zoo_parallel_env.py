@@ -181,7 +181,7 @@ class GridworldZooParallelEnv(object):
                  occlusion_in_atribute_layers=False, observable_attribute_categories=None, observable_attribute_value_mapping=None,
                  use_multi_discrete_action_space=False, np_random=None, seed=None, test_death=False, test_death_probability=0.33,
                  pre_reset_callback=None, post_reset_callback=None, pre_step_callback=None, post_step_callback=None,
-                 render_mode=None, num_envs=None, device=None, **kwargs):
+                 render_mode=None, num_envs=None, device=None, final_info=True, **kwargs):
         # the wrapper-side options of the reference's constructor (:100-135) are honoured or refused -- never dropped
         if occlusion_in_layers:
             raise NotImplementedError("occlusion_in_layers=True is not built (the reference's own occluded branch is unfinished: "
@@ -200,7 +200,13 @@ class GridworldZooParallelEnv(object):
         self._env_name = env_name
         self._batched = num_envs is not None
         n = int(num_envs) if self._batched else 1
-        mode = _abi.GW_AUTORESET_SAME_STEP if self._batched else _abi.GW_AUTORESET_NEXT_STEP
+        # Batched form with final_info (default): a finished game restarts inside step(), but after the step's infos were read -- the
+        # infos (cumulative rewards, metrics, frame, the boards and views they carry) describe the game that just ended, like the
+        # rewards and terminateds do, and the returned observations already belong to the next game.  The kernel then runs with the
+        # reference's own reset semantics and the wrapper issues the masked reset.  final_info=False leaves the restart to the kernel
+        # (auto-reset inside the ending launch; the AEC wrapper steps the backend that way).
+        self._final_info = self._batched and bool(final_info)
+        mode = _abi.GW_AUTORESET_SAME_STEP if (self._batched and not self._final_info) else _abi.GW_AUTORESET_NEXT_STEP
         self._spec = make_spec(env_name, autoreset_mode=mode, **kwargs)
         self._backend = _backend_for(env_name)(n, device, 0 if seed is None else seed, mode, self._spec)
         self._env = self._backend.env
@@ -385,7 +391,7 @@ class GridworldZooParallelEnv(object):
             dr[0, :len(replay_draws)] = replay_draws
             draws = torch.from_numpy(dr).to(env.device)
         self._backend.step(act, order, draws)
-        obs, infos = self._observations(stepped), self._infos(stepped)
+        infos = self._infos(stepped, clone=self._final_info)
         rewards, terms, truncs = {}, {}, {}
         for i, a in enumerate(self.possible_agents):
             if a not in stepped:
@@ -398,6 +404,13 @@ class GridworldZooParallelEnv(object):
                 rewards[a], terms[a], truncs[a] = r[0].double().cpu().numpy(), bool(t[0].item()), False
         if self._test_death:
             self._apply_test_death(stepped, rewards, terms, replay_death_draws)
+        if self._batched:
+            over = (env.step_type[:, be.cols] >= 2).all(dim=1)          # every agent of the game is done (LAST / DEAD)
+            if self._death_mask is not None:
+                self._death_mask[over] = False                           # a new game: nobody is (virtually) dead
+            if self._final_info:
+                env.reset(over)                                          # restart it now that its final infos are out
+        obs = self._observations(stepped)
         if not self._batched:
             self._dones.update(terms)
         result = (obs, rewards, terms, truncs, infos)
@@ -431,8 +444,6 @@ class GridworldZooParallelEnv(object):
         n, A = self.num_envs, len(self.possible_agents)
         for i, a in enumerate(self.possible_agents):
             col = self._backend.cols[i]
-            restarted = env.step_type[:, col] == 0
-            self._death_mask[:, i] &= ~restarted
             u = _philox_uniform(self._death_seed ^ 0x7e57dea7, getattr(env, "env_index_base", 0), n, self._death_step * A + i, env.device)
             newly = (~self._death_mask[:, i]) & (~terms[a]) & (u < self._test_death_probability)
             rewards[a] = torch.where(self._death_mask[:, i].unsqueeze(-1), torch.zeros_like(rewards[a]), rewards[a])
@@ -478,8 +489,10 @@ class GridworldZooParallelEnv(object):
         """{layer: [(row, col), ...]} of a bool [L, h, w] cube (calculate_observation_coordinates, safety_game_moma.py:583-601)"""
         return {ch: [tuple(c) for c in np.argwhere(layers[k]).tolist()] for k, ch in enumerate(names)}
 
-    def _infos(self, agents=None):
+    def _infos(self, agents=None, clone=False):
+        """`clone`: the board / view tensors are copied (the caller is about to restart finished games in place)"""
         env, spec = self._env, self._spec
+        keep = (lambda t: t.clone()) if clone else (lambda t: t)
         ex = self._backend.extras()
         have = list(spec.layer_order)
         infos = {}
@@ -488,12 +501,12 @@ class GridworldZooParallelEnv(object):
             if agents is not None and a not in agents:
                 continue
             info = {
-                "ascii_codes": env.board,
-                INFO_AGENT_OBSERVATIONS: self._crop(i),
+                "ascii_codes": keep(env.board),
+                INFO_AGENT_OBSERVATIONS: keep(self._crop(i)),
                 "cumulative_reward": ex["cumulative_per_agent"][i].double(),
                 "metrics_dict": {n: ex["metrics"][:, j] for j, n in enumerate(spec.metric_names)},
                 "frame": ex["frame"], "agent_positions": ex["pos"],
-                "step_type": env.step_type[:, self._backend.cols[i]],
+                "step_type": keep(env.step_type[:, self._backend.cols[i]]),
             }
             if self._layers_order is not None:
                 info[INFO_OBSERVATION_LAYERS_ORDER] = list(self._layers_order[0])

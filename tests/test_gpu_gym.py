@@ -63,9 +63,8 @@ def test_batched_form_and_transitions():
         assert reward.shape == (N, 10) and reward.dtype == torch.float64
         assert terminated.dtype == torch.bool and not bool(truncated.any())
         total_done += int(terminated.sum())
-        # an environment that terminated already shows the first frame of its next episode
-        started = info["frame"][terminated]
-        assert bool((started == 0).all())
+        # info describes the episode that just ENDED (its last frame), the observation already is the next episode's first one
+        assert bool((info["frame"][terminated] > 0).all())
     assert total_done > 0
     with pytest.raises(NotImplementedError):
         GridworldGymEnv("no_such_environment")
@@ -202,3 +201,44 @@ def test_scalarise_sums_the_reward_dimensions():
         assert isinstance(reward, np.float64) and reward == d["reward"][t].sum()
         assert float(info["cumulative_reward"]) == pytest.approx(d["cumulative"][t].sum(), rel=1e-6)
     env.close()
+
+
+def test_batched_info_describes_the_finished_episode(oracle_lib):
+    """on a terminal step the batched wrapper's `info` (cumulative / average reward, metrics, frame, termination
+    reason, ascii board) must describe the finished episode like `reward` and `terminated` do, while `obs` is the first
+    observation of the next episode and info['final_observation'] the last one of the finished episode.  Checked against the
+    CPU oracle stepped with the reference's semantics plus an explicit masked reset."""
+    from ai_safety_gridworlds_b200 import GridworldGymEnv, make_spec
+    N = 3000
+    for name, kw in (("island_navigation_ex", {}), ("boat_race_ex", {"level": 3, "max_iterations": 30})):
+        env = GridworldGymEnv(name, num_envs=N, **kw)
+        spec = make_spec(name, autoreset_mode=0, **kw)
+        orc = oracle_lib.Oracle(spec, N)
+        orc.reset()
+        obs, info = env.reset()
+        np.testing.assert_array_equal(obs[:, 0].cpu().numpy(), orc.value_board)
+        finished = 0
+        for t in range(130):
+            a = env.vector_env.random_actions(21, t)
+            obs, reward, terminated, truncated, info = env.step(a)
+            orc.step(a.cpu().numpy())
+            ox = orc.observe()
+            ctx = "%s t=%d" % (name, t)
+            term = orc.terminated.astype(bool)
+            np.testing.assert_array_equal(terminated.cpu().numpy(), term, err_msg=ctx)
+            np.testing.assert_allclose(reward.cpu().numpy(), orc.reward, rtol=1e-6, atol=0, err_msg=ctx)
+            # the finished episodes' final values
+            np.testing.assert_array_equal(info["frame"].cpu().numpy(), ox["frame"], err_msg=ctx)
+            np.testing.assert_allclose(info["cumulative_reward"].cpu().numpy(), ox["cumulative"], rtol=1e-6, atol=1e-5, err_msg=ctx)
+            np.testing.assert_array_equal(info["extra_observations"]["termination_reason"].cpu().numpy(), orc.reason, err_msg=ctx)
+            np.testing.assert_array_equal(info["ascii_codes"].cpu().numpy(), orc.board, err_msg=ctx)
+            np.testing.assert_array_equal(info["final_observation"][:, 0].cpu().numpy(), orc.value_board, err_msg=ctx)
+            for j, mname in enumerate(spec.metric_names):
+                np.testing.assert_allclose(info["metrics_dict"][mname].cpu().numpy(), ox["metrics"][:, j], rtol=1e-12, atol=1e-12, err_msg=ctx)
+            assert bool((info["frame"][terminated] > 0).all())
+            finished += int(term.sum())
+            orc.reset(term.astype(np.uint8))                               # the wrapper restarted exactly those environments
+            np.testing.assert_array_equal(obs[:, 0].cpu().numpy(), orc.value_board, err_msg=ctx)
+        assert finished > N // 2
+        env.close()
+        orc.close()

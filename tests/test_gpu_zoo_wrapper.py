@@ -108,15 +108,19 @@ def test_batched_wrapper_spaces_layers_death_quit_and_rgb():
     for t in range(25):
         acts = {a: torch.randint(0, 5, (N,), device=env.vector_env.device, generator=g) for a in env.possible_agents}
         obs, rewards, terms, truncs, infos = env.step(acts)
+        really_all = torch.stack([infos[a]["step_type"] >= 2 for a in env.possible_agents], dim=1)
         for i, a in enumerate(env.possible_agents):
             assert torch.equal(obs[a][:, 0], prev[a])                          # use_transitions: (previous view, view)
             prev[a] = obs[a][:, 1].clone()
             u = _philox_uniform(7 ^ 0x7e57dea7, 0, N, (t + 1) * 3 + i, env.vector_env.device)
-            really = env.vector_env.terminated[:, i].bool()
+            really = really_all[:, i]
             was = dead[a].clone()
             dead[a] = was | ((~was) & (~really) & (u < 0.1))
             assert torch.equal(terms[a], really | dead[a]), (t, a)
             assert not bool(rewards[a][was].any())                                # a dead agent's reward row is zeroed
+        over = really_all.all(dim=1)
+        for a in env.possible_agents:
+            dead[a] &= ~over                                                      # a finished game restarts with everybody alive
         cube = infos["agent_1"]["info_observation_layers_cube"]
         assert infos["agent_1"]["info_observation_layers_order"] == ["F", "zz", "#"] and tuple(cube.shape) == (N, 3, 17, 17)
         assert not bool(cube[:, 1].any())
@@ -129,3 +133,46 @@ def test_batched_wrapper_spaces_layers_death_quit_and_rgb():
     with pytest.raises(NotImplementedError):                                      # QUIT in the batched form is refused, not mis-played
         env.step({a: torch.full((N,), 9, device=env.vector_env.device) for a in env.possible_agents})
     env.close()
+
+
+def test_batched_infos_describe_the_finished_game(oracle_lib):
+    """On the step that ends a game the batched wrapper's infos (cumulative rewards, frame, metrics, the boards and views they
+    carry) describe the finished game, the returned observations belong to the next one -- against the CPU oracle stepped with the
+    reference's semantics plus an explicit masked reset."""
+    from ai_safety_gridworlds_b200 import make_spec
+    from ai_safety_gridworlds_b200.helpers.gridworld_zoo_parallel_env import GridworldZooParallelEnv
+    N = 300
+    env = GridworldZooParallelEnv("firemaker_ex_ma", amount_agents=3, num_envs=N, seed=5, max_iterations=60)
+    spec = make_spec("firemaker_ex_ma", autoreset_mode=0, amount_agents=3, max_iterations=60)
+    orc = oracle_lib.FiremakerOracle(spec, N, seed=5)
+    orc.reset()                                                           # the constructor reset the environments once: the same call count
+    dev = env.vector_env.device
+    rng = np.random.default_rng(2)
+    ended = 0
+    for t in range(50):
+        a = rng.integers(0, 5, size=(N, 3)).astype(np.int32)
+        obs, rewards, terms, truncs, infos = env.step({nm: torch.from_numpy(a[:, i].copy()).to(dev) for i, nm in enumerate(env.possible_agents)})
+        orc.step(a)
+        ox = orc.observe()
+        ctx = "t=%d" % t
+        over = (orc.step_type >= 2).all(axis=1)
+        for i, nm in enumerate(env.possible_agents):
+            np.testing.assert_array_equal(terms[nm].cpu().numpy(), orc.terminated[:, i].astype(bool), err_msg=ctx)
+            want_r = orc.reward_s if i == 2 else orc.reward_w[:, i]
+            np.testing.assert_array_equal(rewards[nm].cpu().numpy(), want_r.astype(np.float64), err_msg=ctx)
+            info = infos[nm]
+            np.testing.assert_array_equal(info["frame"].cpu().numpy(), ox["frame"], err_msg=ctx)
+            np.testing.assert_array_equal(info["ascii_codes"].cpu().numpy(), orc.board, err_msg=ctx)
+            want_c = orc.crop_s if i == 2 else orc.crop_w[:, i]
+            np.testing.assert_array_equal(info["info_agent_observations"].cpu().numpy(), want_c, err_msg=ctx)
+            cum = ox["cumulative"][:, 4:7] if i == 2 else ox["cumulative"][:, 2 * i:2 * i + 2]
+            np.testing.assert_array_equal(info["cumulative_reward"].cpu().numpy(), cum.astype(np.float64), err_msg=ctx)
+        assert bool((infos["agent_1"]["frame"][torch.from_numpy(over).to(dev)] == 60).all())
+        ended += int(over.sum())
+        orc.reset(over.astype(np.uint8))
+        for i, nm in enumerate(env.possible_agents):
+            want_c = orc.crop_s if i == 2 else orc.crop_w[:, i]
+            np.testing.assert_array_equal(obs[nm][:, 0].cpu().numpy(), want_c, err_msg=ctx)
+    assert ended == 2 * N                                                 # 60 frames = 20 parallel steps per game
+    env.close()
+    orc.close()
