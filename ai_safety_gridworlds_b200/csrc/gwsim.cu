@@ -50,6 +50,17 @@
 #define GW_STAT_REPLICAS 64
 #define FULL 0xffffffffu
 
+/* Work queue of the persistent kernels: one counter per handle.  A warp claims the next unit of work with one atomicAdd and
+ * makes exactly ONE failing claim before it leaves, so a launch issues exactly units + warps claims -- and the warp that
+ * draws the LAST ticket knows that nobody will claim again and puts the counter back to zero.  Every launch therefore starts
+ * from a clean queue with nothing kept on the host: a launch that fails, or a CUDA graph that replays a captured launch,
+ * cannot get out of step with the device.  (One launch at a time per handle: launches on a handle must be stream-ordered.) */
+__device__ __forceinline__ unsigned long long queue_claim(unsigned long long* __restrict__ q, unsigned long long units) {
+  const unsigned long long v = atomicAdd(q, 1ull);
+  if (v + 1ull == units + (unsigned long long)gridDim.x * (blockDim.x >> 5)) *q = 0ull;
+  return v;
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* error plumbing                                                                              */
 static thread_local char g_err[512] = "";
@@ -119,7 +130,6 @@ struct StepArgs {
   int8_t* reason;
   unsigned long long* stats;  /* [GW_STAT_REPLICAS][GW_STATS_RAW_LEN]; slots 24..27 hold doubles */
   unsigned long long* claim_counter;  /* dynamic chunk queue of the persistent kernel */
-  unsigned long long claim_base;
   int64_t n;
 };
 
@@ -133,8 +143,7 @@ struct GwEngine {
   int64_t env_index_base;
   void* d_tmpl;                       /* all templates, one allocation */
   unsigned long long* d_stats;
-  unsigned long long* d_claim;        /* chunk-queue counter (monotonic) */
-  unsigned long long claim_base;      /* its value once every launch issued so far has finished */
+  unsigned long long* d_claim;        /* work queue counter (queue_claim) */
   int64_t launches;
   int sm_count;
   /* classic (mixed) handles */
@@ -954,16 +963,13 @@ __global__ void __launch_bounds__(GW_PBLOCK) gw_step_tma_kernel(const __grid_con
   /* Dynamic chunk queue: a warp claims GW_GRAB consecutive chunks at a time with one atomicAdd.
    * Compared with a static grid-stride assignment this keeps the GPU-wide write front tight
    * (warps cannot drift apart), which is worth ~12 % of DRAM write bandwidth on B200
-   * (scripts/wbw.cu: 6.28 -> 7.04 TB/s).  The counter is never reset: the host passes the value
-   * it has after all earlier launches (every warp makes exactly one failing claim per launch). */
+   * (scripts/wbw.cu: 6.28 -> 7.04 TB/s).  The warp that draws the launch's last ticket resets the queue (queue_claim). */
   const int64_t ngroups = (nchunks + GW_GRAB - 1) / GW_GRAB;
   auto claim = [&]() -> int64_t {
     unsigned long long v = 0;
-    if (lane == 0) v = atomicAdd(a.claim_counter, 1ull) - a.claim_base;
+    if (lane == 0) v = queue_claim(a.claim_counter, (unsigned long long)ngroups);
     const int64_t got = (int64_t)__shfl_sync(FULL, v, 0);
-    /* a host base that ran ahead of the device counter (a launch that never ran) would underflow to a negative index:
-     * such a claim counts as "queue exhausted", never as work */
-    return got < 0 ? ((int64_t)1 << 60) : got;
+    return got < 0 ? ((int64_t)1 << 60) : got;           /* a corrupted counter counts as "queue exhausted", never as work */
   };
   int64_t group = claim();
   Raw<KIND> next;
@@ -1450,11 +1456,9 @@ static int cls_step_launch(GwHandle h, const ClsArgs& a0, cudaStream_t stream) {
   const int64_t resident = (int64_t)per_sm * h->sm_count;
   if (grid > resident) grid = resident;
   a.claim_counter = h->d_claim;
-  a.claim_base = h->claim_base;
   gw_cls_step_kernel<R3><<<(unsigned)grid, GW_PBLOCK, smem, stream>>>(a, warp_bytes, value_off, reward_off);
   { const cudaError_t le = cudaGetLastError();     /* a refused launch claims nothing: keep the host base in step */
     if (le != cudaSuccess) return fail(GW_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(le)); }
-  h->claim_base += (unsigned long long)nchunks + (unsigned long long)grid * GW_PWARPS;
   return GW_OK;
 }
 
@@ -1510,12 +1514,9 @@ static int launch_step_tma(GwHandle h, StepArgs& a, cudaStream_t stream) {
   const int64_t resident = (int64_t)per_sm * h->sm_count;
   if (grid > resident) grid = resident;                     /* persistent: one wave, warps claim chunk groups */
   a.claim_counter = h->d_claim;
-  a.claim_base = h->claim_base;
   gw_step_tma_kernel<KIND><<<(unsigned)grid, GW_PBLOCK, smem, stream>>>(d, a, L);
   { const cudaError_t le = cudaGetLastError();     /* a refused launch claims nothing: keep the host base in step */
     if (le != cudaSuccess) return fail(GW_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(le)); }
-  /* every group is claimed once and every warp makes exactly one failing claim */
-  h->claim_base += (unsigned long long)((nchunks + GW_GRAB - 1) / GW_GRAB) + (unsigned long long)grid * GW_PWARPS;
   return GW_OK;
 }
 
@@ -1685,7 +1686,6 @@ int gw_create(const GwConfig* cfg, int64_t n_envs, int device, int64_t env_index
   if (ce == cudaSuccess) ce = cudaMemset(h->d_stats, 0, sbytes);
   if (ce != cudaSuccess) { cudaFree(h->d_tmpl); delete h; return fail(GW_ERR_CUDA, "stats buffer: %s", cudaGetErrorString(ce)); }
   h->d_claim = nullptr;
-  h->claim_base = 0;
   ce = cudaMalloc((void**)&h->d_claim, sizeof(unsigned long long));
   if (ce == cudaSuccess) ce = cudaMemset(h->d_claim, 0, sizeof(unsigned long long));
   if (ce != cudaSuccess) { cudaFree(h->d_tmpl); cudaFree(h->d_stats); delete h; return fail(GW_ERR_CUDA, "claim counter: %s", cudaGetErrorString(ce)); }
@@ -1730,7 +1730,7 @@ int gw_create_mixed(const GwConfig* cfgs, int32_t n_types, const int64_t* counts
   h->cfg = cfgs[0];
   h->n = n; h->device = device; h->env_index_base = env_index_base; h->launches = 0;
   h->d_tmpl = nullptr; h->d_stats = nullptr; h->d_claim = nullptr; h->d_types = nullptr;
-  h->claim_base = 0; h->step_impl = 0; h->is_classic = 1; h->n_types = n_types;
+  h->step_impl = 0; h->is_classic = 1; h->n_types = n_types;
   h->seed = seed; h->call_no = 0; h->coin_override = nullptr; h->dried_override = nullptr;
   h->sm_count = 148;
   cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
@@ -2017,8 +2017,7 @@ struct GwFmEngine {
   int device;
   uint64_t seed, call_no;
   FmStatic* d_static;
-  unsigned long long* d_claim;        /* environment-queue counter (monotonic) */
-  unsigned long long claim_base;      /* its value once every launch issued so far has finished */
+  unsigned long long* d_claim;        /* work queue counter (queue_claim) */
   unsigned long long* d_stats;        /* [GW_STAT_REPLICAS][GW_MA_STATS_LEN] raw rollout statistics */
   int grid;                           /* resident CTAs of the persistent step kernel */
   int64_t launches;
@@ -2130,7 +2129,7 @@ int gw_fm_create(const GwFmConfig* cfg, int64_t n_envs, int device, int64_t env_
   if (!st.two_workers) { st.static2 = st.start[1]; st.start[1] = 0xffff; }
   ce = cudaMalloc((void**)&h->d_static, sizeof(FmStatic));
   if (ce == cudaSuccess) ce = cudaMemcpy(h->d_static, &st, sizeof st, cudaMemcpyHostToDevice);
-  h->d_claim = nullptr; h->claim_base = 0; h->d_stats = nullptr;
+  h->d_claim = nullptr; h->d_stats = nullptr;
   if (ce == cudaSuccess) ce = cudaMalloc((void**)&h->d_claim, sizeof(unsigned long long));
   if (ce == cudaSuccess) ce = cudaMemset(h->d_claim, 0, sizeof(unsigned long long));
   if (ce == cudaSuccess) ce = ma_stats_alloc(&h->d_stats);
@@ -2167,11 +2166,9 @@ static int fm_launch(GwFmHandle h, FmArgs& a, void* state, const GwFmObs* obs, c
   int64_t grid = (nbatches + FM_WARPS - 1) / FM_WARPS;
   if (grid > h->grid) grid = h->grid;                           /* persistent: one wave, warps claim batches of FM_BATCH games */
   a.claim_counter = h->d_claim;
-  a.claim_base = h->claim_base;
   a.stats = h->d_stats;
   gw_fm_kernel<<<(unsigned)grid, FM_WARPS * 32, (size_t)FM_DYN_BYTES, stream>>>(a);
   CUDA_TRY(cudaGetLastError());                                /* a refused launch claims nothing: the host base stays in step */
-  h->claim_base += (unsigned long long)nbatches + (unsigned long long)grid * FM_WARPS;   /* every batch once + one failing claim per warp */
   h->launches += 1;
   return GW_OK;
 }
@@ -2236,7 +2233,6 @@ struct GwImaEngine {
   int device;
   uint64_t seed, call_no;
   unsigned long long* d_claim;
-  unsigned long long claim_base;
   unsigned long long* d_stats;        /* [GW_STAT_REPLICAS][GW_MA_STATS_LEN] raw rollout statistics */
   int grid;
   uint32_t cube_off, board_off, crop_off, lcrop_off, reward_off, warp_bytes;
@@ -2328,7 +2324,7 @@ int gw_ima_create(const GwConfig* cfg, int64_t n_envs, int device, int64_t env_i
   h->warp_bytes_pm = (h->map_off + 32u * (uint32_t)cells + 127u) & ~127u;
   h->maps = nullptr; h->map_mode = GW_IMA_MAPS_STATIC;
   const size_t smem = (size_t)h->warp_bytes * IMA_WARPS, smem_pm = (size_t)h->warp_bytes_pm * IMA_WARPS;
-  h->d_claim = nullptr; h->claim_base = 0; h->d_stats = nullptr;
+  h->d_claim = nullptr; h->d_stats = nullptr;
   ce = cudaFuncSetAttribute(gw_ima_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (ce == cudaSuccess) ce = cudaFuncSetAttribute(gw_ima_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pm);
   if (ce == cudaSuccess) ce = cudaMalloc((void**)&h->d_claim, sizeof(unsigned long long));
@@ -2387,12 +2383,10 @@ static int ima_launch(GwImaHandle h, ImaArgs& a, void* state, const GwImaObs* ob
   a.map_shuffle = pm && (h->map_mode == GW_IMA_MAPS_SHUFFLE_EVERY_GAME || (h->map_mode == GW_IMA_MAPS_SHUFFLE_ON_RESET && a.is_reset)) ? 1 : 0;
   if (pm) a.warp_bytes = h->warp_bytes_pm;
   a.claim_counter = h->d_claim;
-  a.claim_base = h->claim_base;
   a.stats = h->d_stats;
   if (pm) gw_ima_kernel<true><<<(unsigned)grid, IMA_WARPS * 32, (size_t)h->warp_bytes_pm * IMA_WARPS, stream>>>(h->dc, a);
   else gw_ima_kernel<false><<<(unsigned)grid, IMA_WARPS * 32, (size_t)h->warp_bytes * IMA_WARPS, stream>>>(h->dc, a);
   CUDA_TRY(cudaGetLastError());                                /* a refused launch claims nothing: the host base stays in step */
-  h->claim_base += (unsigned long long)nchunks + (unsigned long long)grid * IMA_WARPS;    /* every chunk once + one failing claim per warp */
   h->launches += 1;
   return GW_OK;
 }
@@ -2494,6 +2488,18 @@ int gw_sok_create(const GwSokConfig* cfg, int64_t n_envs, int device, GwSokHandl
   const int cells = cfg->height * cfg->width;
   if (cfg->height < 3 || cfg->width < 3 || cells >= (int)SOK_ABSENT) return fail(GW_ERR_INVALID, "board %dx%d outside 3x3 .. 126 cells", cfg->height, cfg->width);
   if (cfg->max_iterations < 1 || cfg->max_iterations > 65535) return fail(GW_ERR_INVALID, "max_iterations %d outside 1..65535", cfg->max_iterations);
+  {
+    /* the episode return and the hidden return are 16-bit fields of the state word: the largest sum an episode can reach --
+     * every step at the worst per-step reward, plus every coin and the goal once, plus three boxes at the worst wall penalty --
+     * must fit, or the configuration is refused (a silent wrap would corrupt the returns) */
+    auto mag = [](int32_t v) { return (int64_t)(v < 0 ? -(int64_t)v : (int64_t)v); };
+    const int64_t per_step = mag(cfg->movement_reward);
+    int64_t worst_pen = mag(cfg->wall_reward) > mag(cfg->corner_reward) ? mag(cfg->wall_reward) : mag(cfg->corner_reward);
+    const int64_t bound = per_step * cfg->max_iterations + 8 * mag(cfg->coin_reward) + mag(cfg->goal_reward) + 3 * worst_pen;
+    if (bound > 32767)
+      return fail(GW_ERR_INVALID, "max_iterations %d with these rewards lets an episode return reach %lld: beyond the 16-bit return fields "
+                  "of the sokoban state word", cfg->max_iterations, (long long)bound);
+  }
   if (cfg->autoreset_mode != GW_AUTORESET_NEXT_STEP && cfg->autoreset_mode != GW_AUTORESET_SAME_STEP) return fail(GW_ERR_INVALID, "autoreset_mode %d", cfg->autoreset_mode);
   SokCfg c;
   memset(&c, 0, sizeof c);

@@ -71,7 +71,6 @@ struct ClsArgs {
   int8_t* actual;
   unsigned long long* stats;
   unsigned long long* claim_counter;
-  unsigned long long claim_base;
   uint64_t seed, call_no;
   int64_t env_index_base;
   int64_t n;
@@ -640,11 +639,9 @@ __global__ void __launch_bounds__(GW_PBLOCK) gw_cls_step_kernel(const __grid_con
 
   auto claim = [&]() -> int64_t {
     unsigned long long v = 0;
-    if (lane == 0) v = atomicAdd(a.claim_counter, 1ull) - a.claim_base;
+    if (lane == 0) v = queue_claim(a.claim_counter, (unsigned long long)nchunks);
     const int64_t got = (int64_t)__shfl_sync(FULL, v, 0);
-    /* a host base that ran ahead of the device counter (a launch that never ran) would underflow to a negative index:
-     * such a claim counts as "queue exhausted", never as work */
-    return got < 0 ? ((int64_t)1 << 60) : got;
+    return got < 0 ? ((int64_t)1 << 60) : got;           /* a corrupted counter counts as "queue exhausted", never as work */
   };
   int64_t chunk = claim();
   uint4 next_raw = make_uint4(0, 0, 0, 0);

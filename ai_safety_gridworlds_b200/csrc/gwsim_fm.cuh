@@ -67,7 +67,6 @@ struct FmArgs {
   int64_t env_index_base, n;
   int32_t is_reset, pad;
   unsigned long long* claim_counter;    /* dynamic environment queue of the persistent kernel */
-  unsigned long long claim_base;
   unsigned long long* stats;            /* [GW_STAT_REPLICAS][GW_MA_STATS_LEN] raw rollout statistics */
 };
 
@@ -533,8 +532,8 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_co
   uint32_t* const w_x = reinterpret_cast<uint32_t*>(wmem + FM_OFF_X);            /* fire-update scratch */
   uint32_t* const w_em = reinterpret_cast<uint32_t*>(wmem + FM_OFF_EM);          /* layer maps and the bit strings of the layer tensors */
   uint8_t* const w_pb = wmem + FM_OFF_PB;                                        /* the rendered board as characters */
-  /* Persistent warps, dynamic queue of FM_BATCH-environment batches (one atomicAdd per batch; the counter is never reset: the
-   * host passes the value it has after all earlier launches, and every warp makes exactly one failing claim per launch).
+  /* Persistent warps, dynamic queue of FM_BATCH-environment batches (one atomicAdd per batch; every warp makes exactly one
+   * failing claim per launch and the warp that draws the last ticket resets the queue, queue_claim).
    *
    * Inside a batch the work is split by what it parallelises over:
    *   - everything scalar per game -- the acting agent's move, visit counters, stop button, workshop, rewards, step types,
@@ -543,15 +542,13 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_co
    *   - the fire update and the observation emission need the whole warp for one game (a 5x5 stencil over 289 cells, 14 KB of
    *     output): the warp walks over the batch's games in turn, the scalars of game e broadcast from lane e.  Games with no
    *     fire and no working worker skip the fire update altogether. */
+  const int64_t nbatches = (a.n + FM_BATCH - 1) / FM_BATCH;
   auto claim = [&]() -> int64_t {
     unsigned long long v = 0;
-    if (lane == 0) v = atomicAdd(a.claim_counter, 1ull) - a.claim_base;
+    if (lane == 0) v = queue_claim(a.claim_counter, (unsigned long long)nbatches);
     const int64_t got = (int64_t)__shfl_sync(FULL, v, 0);
-    /* a host base that ran ahead of the device counter (a launch that never ran) would underflow to a negative index:
-     * such a claim counts as "queue exhausted", never as work */
-    return got < 0 ? ((int64_t)1 << 60) : got;
+    return got < 0 ? ((int64_t)1 << 60) : got;           /* a corrupted counter counts as "queue exhausted", never as work */
   };
-  const int64_t nbatches = (a.n + FM_BATCH - 1) / FM_BATCH;
   long long stat_acc = 0;                              /* lane k accumulates raw statistics slot k of this warp's environments */
   int64_t batch_next = claim();
 #pragma unroll 1

@@ -52,7 +52,6 @@ struct ImaArgs {
   uint64_t seed, call_no;
   int64_t env_index_base, n;
   unsigned long long* claim_counter;
-  unsigned long long claim_base;
   int32_t is_reset, pad;
   unsigned long long* stats;             /* [GW_STAT_REPLICAS][GW_MA_STATS_LEN] raw rollout statistics */
   uint8_t* maps;                         /* [N, cells] per-environment ascii art (map randomisation), NULL = cfg art for all */
@@ -520,11 +519,9 @@ __global__ void __launch_bounds__(IMA_WARPS * 32, 2) gw_ima_kernel(const __grid_
   const int64_t nchunks = (a.n + 31) >> 5;
   auto claim = [&]() -> int64_t {
     unsigned long long v = 0;
-    if (lane == 0) v = atomicAdd(a.claim_counter, 1ull) - a.claim_base;
+    if (lane == 0) v = queue_claim(a.claim_counter, (unsigned long long)nchunks);
     const int64_t got = (int64_t)__shfl_sync(FULL, v, 0);
-    /* a host base that ran ahead of the device counter (a launch that never ran) would underflow to a negative index:
-     * such a claim counts as "queue exhausted", never as work */
-    return got < 0 ? ((int64_t)1 << 60) : got;
+    return got < 0 ? ((int64_t)1 << 60) : got;           /* a corrupted counter counts as "queue exhausted", never as work */
   };
   int64_t chunk = claim();
   ImaRaw next;

@@ -139,7 +139,7 @@ __device__ __forceinline__ void sok_frame(Sok& s, const SokCfg& c, int32_t actio
   }
   /* group 2, the coin drape: no update.  group 3, the agent (AgentSafetySprite.update, safety_game.py:400-432) */
   if (action == GW_CACT_QUIT) { s.reason1 = GW_REASON_QUIT + 1; term = true; return; }
-  s.actual1 = (uint32_t)action + 1u;
+  s.actual1 = ((uint32_t)action + 1u) & 15u;                                     /* a 4-bit field of the state word (actions are validated to 0..9 below) */
   s.agent = sok_walk(c, s, s.agent, action, 1u | 2u);                           /* impassable: '#', '1'-'3', 'X' (:181) */
   if (action == GW_CACT_NOOP) return;                                           /* update_reward :186-212 */
   reward += c.r_move; hid += c.r_move;

@@ -255,3 +255,39 @@ def test_bad_arguments_fail_loudly():
     rc = env._lib.gw_step(env._h, None, C.c_void_p(env.state.data_ptr()), None, None, None)
     assert rc == _abi.GW_ERR_INVALID and b"null actions" in env._lib.gw_last_error()
     env.close()
+
+
+def test_step_is_cuda_graph_capturable(oracle_lib):
+    """gw_step captured once in a CUDA graph and replayed gives what the same launches give eagerly: the persistent kernels
+    keep no launch-to-launch state on the host (the work queue resets itself on the device), so a replay is a full step.
+    Checked against the oracle for the single-agent kernel, the classic mixed batch and firemaker_ex_ma."""
+    from ai_safety_gridworlds_b200 import make_spec
+    from ai_safety_gridworlds_b200.vector_env import _ptr
+    dev = torch.device("cuda", 0)
+    N, K, ROUNDS = 5000, 6, 4
+    spec = make_spec("boat_race_ex", autoreset_mode=1, level=3)
+    env = _venv(spec, N, 1)
+    orc = oracle_lib.Oracle(spec, N)
+    orc.reset()
+    ring = torch.stack([env.random_actions(31, r) for r in range(K)])
+    ptrs = [_ptr(ring[r]) for r in range(K)]
+    side = torch.cuda.Stream(dev)
+    graph = torch.cuda.CUDAGraph()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            for r in range(K):
+                assert env.step_raw(ptrs[r]) == 0
+    torch.cuda.synchronize()                       # capture executes nothing: the environments still stand at reset
+    for rnd in range(ROUNDS):
+        graph.replay()
+        torch.cuda.synchronize()
+        for r in range(K):
+            orc.step(_np(ring[r]))
+        np.testing.assert_array_equal(_np(env.board), orc.board, err_msg="round %d" % rnd)
+        np.testing.assert_array_equal(_np(env.cube), orc.cube, err_msg="round %d" % rnd)
+        np.testing.assert_allclose(_np(env.reward), orc.reward, rtol=1e-6, atol=0)
+        np.testing.assert_array_equal(_np(env.step_type), orc.step_type)
+    assert env.stats()["env_steps"] == N * K * ROUNDS
+    env.close()
+    orc.close()
