@@ -142,6 +142,8 @@ FM_SYMBOLS = [
     ("gw_fm_stats_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     ("gw_fm_stats_clear", C.c_int, [C.c_void_p, C.c_void_p]),
     ("gw_fm_launch_count", C.c_int64, [C.c_void_p]),
+    ("gw_fm_call_count", C.c_int64, [C.c_void_p]),
+    ("gw_fm_set_call_count", C.c_int, [C.c_void_p, C.c_int64]),
 ]
 GW_MA_STATS_LEN, GW_MA_STATS_RETURN0, GW_MA_STATS_SCALE = 32, 4, 65536.0
 
@@ -173,6 +175,8 @@ IMA_SYMBOLS = [
     ("gw_ima_stats_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     ("gw_ima_stats_clear", C.c_int, [C.c_void_p, C.c_void_p]),
     ("gw_ima_launch_count", C.c_int64, [C.c_void_p]),
+    ("gw_ima_call_count", C.c_int64, [C.c_void_p]),
+    ("gw_ima_set_call_count", C.c_int, [C.c_void_p, C.c_int64]),
 ]
 
 # ---- include/gwsim_sok.h: side_effects_sokoban on its big maps (levels 1-3) ----
@@ -263,6 +267,8 @@ SAV_SYMBOLS = [
     ("gw_sav_stats_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     ("gw_sav_stats_clear", C.c_int, [C.c_void_p, C.c_void_p]),
     ("gw_sav_launch_count", C.c_int64, [C.c_void_p]),
+    ("gw_sav_call_count", C.c_int64, [C.c_void_p]),
+    ("gw_sav_set_call_count", C.c_int, [C.c_void_p, C.c_int64]),
 ]
 
 # every symbol include/gwsim.h declares: (name, restype, argtypes)
@@ -288,6 +294,8 @@ SYMBOLS = [
     ("gw_stats", C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_void_p]),
     ("gw_stats_clear", C.c_int, [C.c_void_p, C.c_void_p]),
     ("gw_random_actions", C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    ("gw_call_count", C.c_int64, [C.c_void_p]),
+    ("gw_set_call_count", C.c_int, [C.c_void_p, C.c_int64]),
     ("gw_render_rgb", C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     ("gw_launch_count", C.c_int64, [C.c_void_p]),
 ]

@@ -104,6 +104,16 @@ class ClassicVectorEnv(object):
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def state_dict(self):
+        """Checkpoint of this batch as a dict of host tensors and ints (checkpoint.py); torch.save-able."""
+        from . import checkpoint
+        return checkpoint.state_dict(self)
+
+    def load_state_dict(self, d):
+        """Restores a checkpoint made by state_dict() of a batch built with the same game, flags, size, seed and index base."""
+        from . import checkpoint
+        checkpoint.load_state_dict(self, d)
+
     def set_coin_override(self, coins):
         """coins: uint8 CUDA tensor [N] (0/1 force the next episode's draw of that environment, 255 = draw) or None."""
         if coins is not None and (coins.dtype != torch.uint8 or not coins.is_cuda or coins.shape != (self.num_envs,)):

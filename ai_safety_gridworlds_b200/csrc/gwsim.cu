@@ -1565,8 +1565,20 @@ int gw_create(const GwConfig* cfg, int64_t n_envs, int device, int64_t env_index
   h->dried_override = nullptr;
   h->sm_count = 148;
   cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+  /* Which step kernel: the persistent TMA kernel pays a per-launch cost (every warp fills its staging templates, ~14 KB) that
+   * only amortises over several chunks per warp.  Below two 32-environment chunks per resident warp (3 CTAs x 4 warps per SM;
+   * 113,664 environments on 148 SMs -- BASELINE config 2's 65,536 boat_race_ex environments are such a batch) the direct-store
+   * kernel, one warp per chunk and no staging, is faster (14.4 vs 16.9 us per step, scripts/exp_small.py).
+   * GWSIM_STEP_IMPL=direct|tma overrides. */
   const char* impl = getenv("GWSIM_STEP_IMPL");
-  h->step_impl = (impl && strcmp(impl, "direct") == 0) ? 1 : 0;
+  {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const int64_t nchunks = (n_envs + 31) / 32;
+    h->step_impl = nchunks < 2 * (int64_t)sms * 3 * GW_PWARPS ? 1 : 0;
+  }
+  if (impl && strcmp(impl, "direct") == 0) h->step_impl = 1;
+  if (impl && strcmp(impl, "tma") == 0) h->step_impl = 0;
   h->d_tmpl = nullptr;
   h->d_stats = nullptr;
 
@@ -2006,6 +2018,12 @@ int gw_render_rgb(const uint8_t* board, int64_t n, int32_t cells, int64_t board_
 }
 
 int64_t gw_launch_count(GwHandle h) { return h ? h->launches : 0; }
+int64_t gw_call_count(GwHandle h) { return h ? (int64_t)h->call_no : -1; }
+int gw_set_call_count(GwHandle h, int64_t calls) {
+  if (!h || calls < 0) return fail(GW_ERR_INVALID, "null handle or negative call count");
+  h->call_no = (uint64_t)calls;
+  return GW_OK;
+}
 
 }  /* extern "C" */
 
@@ -2221,6 +2239,12 @@ int gw_fm_stats_clear(GwFmHandle h, void* stream) {
 }
 
 int64_t gw_fm_launch_count(GwFmHandle h) { return h ? h->launches : 0; }
+int64_t gw_fm_call_count(GwFmHandle h) { return h ? (int64_t)h->call_no : -1; }
+int gw_fm_set_call_count(GwFmHandle h, int64_t calls) {
+  if (!h || calls < 0) return fail(GW_ERR_INVALID, "null handle or negative call count");
+  h->call_no = (uint64_t)calls;
+  return GW_OK;
+}
 
 }  /* extern "C" */
 
@@ -2438,6 +2462,12 @@ int gw_ima_stats_clear(GwImaHandle h, void* stream) {
 }
 
 int64_t gw_ima_launch_count(GwImaHandle h) { return h ? h->launches : 0; }
+int64_t gw_ima_call_count(GwImaHandle h) { return h ? (int64_t)h->call_no : -1; }
+int gw_ima_set_call_count(GwImaHandle h, int64_t calls) {
+  if (!h || calls < 0) return fail(GW_ERR_INVALID, "null handle or negative call count");
+  h->call_no = (uint64_t)calls;
+  return GW_OK;
+}
 
 }  /* extern "C" */
 
@@ -2826,5 +2856,11 @@ int gw_sav_stats_clear(GwSavHandle h, void* stream) {
 }
 
 int64_t gw_sav_launch_count(GwSavHandle h) { return h ? h->launches : 0; }
+int64_t gw_sav_call_count(GwSavHandle h) { return h ? (int64_t)h->call_no : -1; }
+int gw_sav_set_call_count(GwSavHandle h, int64_t calls) {
+  if (!h || calls < 0) return fail(GW_ERR_INVALID, "null handle or negative call count");
+  h->call_no = (uint64_t)calls;
+  return GW_OK;
+}
 
 }  /* extern "C" */

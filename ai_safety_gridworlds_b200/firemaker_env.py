@@ -81,6 +81,16 @@ class FiremakerVectorEnv(MultiAgentStatsMixin):
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def state_dict(self):
+        """Checkpoint of this batch as a dict of host tensors and ints (checkpoint.py); torch.save-able."""
+        from . import checkpoint
+        return checkpoint.state_dict(self)
+
+    def load_state_dict(self, d):
+        """Restores a checkpoint made by state_dict() of a batch built with the same game, flags, size, seed and index base."""
+        from . import checkpoint
+        checkpoint.load_state_dict(self, d)
+
     def reset(self, mask=None):
         m = None if mask is None else mask.to(device=self.device, dtype=torch.uint8).contiguous()
         _abi.check(self._lib.gw_fm_reset(self._h, _ptr(m), _ptr(self.state), C.byref(self._obs), C.byref(self._out), self._stream()))

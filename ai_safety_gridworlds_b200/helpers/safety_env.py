@@ -152,7 +152,7 @@ class SafetyEnvironment(object):
         out = {"board": ArraySpec((spec.height, spec.width), np.float32, name="board"),
                EXTRA_OBSERVATIONS: {}}
         if self._mo:
-            out["RGB"] = ArraySpec((3, spec.height, spec.width), np.uint8, name="RGB")    # declared, not rendered
+            out["RGB"] = ArraySpec((3, spec.height, spec.width), np.uint8, name="RGB")    # observation_distiller_ex.py:147-189
         return out
 
     # ------------------------------------------------------------------ reference accessors
@@ -253,6 +253,8 @@ class SafetyEnvironment(object):
                     "info_observation_layers_order"):
             if key in info:
                 observation[key] = info[key]
+        # the distiller's RGB entry (observation_distiller_ex.py:187-189): uint8 [3, H, W], colour / 999 * 255 per character
+        observation["RGB"] = self._gym.render("rgb_array")
         if "ascii_codes" in observation:
             observation["ascii"] = np.vectorize(chr)(observation["ascii_codes"]) if observation["ascii_codes"].size else observation["ascii_codes"]
         if step_type is StepType.LAST:
@@ -296,3 +298,84 @@ _CLASSES = [
 ENVIRONMENT_CLASSES = {}
 for _cls, _env, _ref in _CLASSES:
     globals()[_cls] = ENVIRONMENT_CLASSES[_env] = _make_class(_cls, _env, "The reference's %s (%s) on the CUDA backend." % (_cls, _ref))
+
+
+class SafetyEnvironmentMa(object):
+    """The reference's multi-agent core environments (SafetyEnvironmentMoMa, environments/shared/safety_game_moma.py:151,984) on
+    the CUDA backend: `step({agent_chr: action | {"step": action}})` -> TimeStep whose step_type / reward fields are dicts keyed
+    by the agent CHARACTER (rl/pycolab_interface_ma.py:173-246), observation = the global observation dict.  One object is one
+    game; the per-agent views travel in observation['agent_observations'].  Built on the PettingZoo parallel wrapper's
+    single-environment form, so the kernels, the done-agent rules (stepping a finished agent raises ValueError) and the
+    infos are the ones tests/test_gpu_zoo*.py replay against the reference."""
+    ENV_NAME = None
+
+    def __init__(self, *args, **kwargs):
+        if args:
+            raise TypeError("%s takes keyword arguments only" % type(self).__name__)
+        from .gridworld_zoo_parallel_env import GridworldZooParallelEnv
+        name = kwargs.pop("env_name", None) or self.ENV_NAME
+        self._name = name
+        self._zoo = GridworldZooParallelEnv(name, **kwargs)
+        self._chars = [self._zoo.agent_name_mapping[a] for a in self._zoo.possible_agents]
+        self._episode_return = None
+
+    @property
+    def environment_data(self):
+        return {}
+
+    def action_spec(self):
+        lo, hi = self._zoo._spec.action_range
+        return {ch: BoundedArraySpec((1,), np.int32, lo, hi, name="discrete") for ch in self._chars}
+
+    def observation_spec(self, agent_chr=None):
+        spec = self._zoo._spec
+        if agent_chr is not None:
+            i = self._chars.index(agent_chr)
+            h, w = self._zoo._backend.crop(i).shape[1:]
+            return {"board": ArraySpec((h, w), np.float32, name="board"), "ascii": ArraySpec((h, w), np.dtype("<U1"), name="ascii")}
+        return {"board": ArraySpec((spec.height, spec.width), np.float32, name="board"),
+                "RGB": ArraySpec((3, spec.height, spec.width), np.uint8, name="RGB"), EXTRA_OBSERVATIONS: {}}
+
+    def close(self):
+        self._zoo.close()
+
+    def _timestep(self, obs, rewards, infos, first):
+        zoo = self._zoo
+        any_info = next(iter(infos.values())) if infos else {}
+        step_type = {}
+        for a, ch in zip(zoo.possible_agents, self._chars):
+            if a in infos:
+                step_type[ch] = StepType(int(infos[a]["step_type"]))
+        observation = {"ascii_codes": any_info.get("ascii_codes"), "RGB": zoo.render("rgb_array"),
+                       "agent_observations": {zoo.agent_name_mapping[a]: o[0] for a, o in obs.items()},
+                       "metrics_dict": any_info.get("metrics_dict"),
+                       "cumulative_reward": {zoo.agent_name_mapping[a]: i["cumulative_reward"] for a, i in infos.items()}}
+        for key in ("info_observation_layers_cube", "info_observation_layers_order"):
+            if key in any_info:
+                observation[key] = any_info[key]
+        if first:
+            return TimeStep(step_type, None, None, observation)
+        reward = {zoo.agent_name_mapping[a]: np.asarray(r, np.float64) for a, r in rewards.items()}
+        return TimeStep(step_type, reward, 1.0, observation)
+
+    def reset(self, *args, **kwargs):
+        obs, infos = self._zoo.reset(*args, **kwargs)
+        return self._timestep(obs, None, infos, True)
+
+    def step(self, agents_actions, *args, **kwargs):
+        acts = {}
+        for ch, v in agents_actions.items():
+            acts[self._zoo.agent_name_reverse_mapping[ch]] = v
+        obs, rewards, terms, truncs, infos = self._zoo.step(acts, *args, **kwargs)
+        return self._timestep(obs, rewards, infos, False)
+
+
+_MA_CLASSES = [
+    ("FiremakerExMa", "firemaker_ex_ma", "environments/firemaker_ex_ma.py:719"),
+    ("IslandNavigationEnvironmentExMa", "island_navigation_ex_ma", "environments/island_navigation_ex_ma.py:841"),
+    ("AIntelopeSavannaEnvironmentMa", "aintelope_savanna", "environments/aintelope/aintelope_savanna.py:1504"),
+]
+MA_ENVIRONMENT_CLASSES = {}
+for _cls, _env, _ref in _MA_CLASSES:
+    globals()[_cls] = MA_ENVIRONMENT_CLASSES[_env] = type(_cls, (SafetyEnvironmentMa,), {
+        "ENV_NAME": _env, "__doc__": "The reference's %s (%s) on the CUDA backend." % (_cls, _ref)})

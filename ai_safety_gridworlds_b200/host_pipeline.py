@@ -58,7 +58,7 @@ class HostPipeline(object):
             d = [getattr(env, name) for name in self.returns]
             self.d_out.append(d)
             self.h_out.append([torch.zeros(t.shape, dtype=t.dtype, pin_memory=True) for t in d])
-        self.spec = self.envs[0].spec
+        self.spec = getattr(self.envs[0], "spec", None)          # a mixed classic batch has one spec per type (`specs`)
         torch.cuda.synchronize(self.device)            # construction / reset ran on the current stream
         self._pending = [False] * parts
 
@@ -115,6 +115,8 @@ class HostPipeline(object):
 
     def value_board(self, board_host):
         """The reference's float32 observation from the uint8 ASCII board, on the host (value_mapping[chr])."""
+        if self.spec is None:
+            raise ValueError("a mixed batch has one value mapping per type: map the slices yourself")
         lut = np.zeros(256, np.float32)
         for ch, v in self.spec.value_mapping.items():
             lut[ord(ch)] = v

@@ -91,6 +91,16 @@ class SavannaVectorEnv(MultiAgentStatsMixin):
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def state_dict(self):
+        """Checkpoint of this batch as a dict of host tensors and ints (checkpoint.py); torch.save-able."""
+        from . import checkpoint
+        return checkpoint.state_dict(self)
+
+    def load_state_dict(self, d):
+        """Restores a checkpoint made by state_dict() of a batch built with the same game, flags, size, seed and index base."""
+        from . import checkpoint
+        checkpoint.load_state_dict(self, d)
+
     def set_maps(self, maps, mode=_abi.GW_IMA_MAPS_STATIC):
         """maps: uint8 CUDA tensor [N, H, W], the ascii art of every environment's game, kept by reference: rewrite it between
         calls to replay given layouts (mode STATIC); the library rewrites it in the shuffle modes."""

@@ -77,6 +77,16 @@ class SokobanVectorEnv(object):
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def state_dict(self):
+        """Checkpoint of this batch as a dict of host tensors and ints (checkpoint.py); torch.save-able."""
+        from . import checkpoint
+        return checkpoint.state_dict(self)
+
+    def load_state_dict(self, d):
+        """Restores a checkpoint made by state_dict() of a batch built with the same game, flags, size, seed and index base."""
+        from . import checkpoint
+        checkpoint.load_state_dict(self, d)
+
     def boards(self, which="board"):
         return crop_rows(getattr(self, which), self.spec)
 

@@ -95,6 +95,16 @@ class VectorEnv(object):
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def state_dict(self):
+        """Checkpoint of this batch as a dict of host tensors and ints (checkpoint.py); torch.save-able."""
+        from . import checkpoint
+        return checkpoint.state_dict(self)
+
+    def load_state_dict(self, d):
+        """Restores a checkpoint made by state_dict() of a batch built with the same game, flags, size, seed and index base."""
+        from . import checkpoint
+        checkpoint.load_state_dict(self, d)
+
     # ------------------------------------------------------------------ stepping
     def reset(self, mask=None):
         """New episode in every environment (or where `mask` is non-zero); renders the observation.

@@ -459,11 +459,38 @@ def run_ours(args):
         # (nearly) the same time on all GPUs and the host-side launch skew of the ranks is not in the timed region
         dist.all_reduce(align, op=dist.ReduceOp.SUM)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
-    for t in range(args.steps):
-        rc = env.step_raw(ring_ptrs[t % ACTION_RING])
-    ev1.record(stream)
-    step_launches = env.launch_count - launches0
+    graph = None
+    if args.graph_steps > 0:
+        # small batches (BASELINE config 2: a 15 us kernel) are bound by the host's launch rate through ctypes, not by the kernel:
+        # G consecutive step launches are captured ONCE in a CUDA graph (the kernels keep no launch-to-launch state on the host)
+        # and the timed region replays it.  The same kernels run, K steps in total.
+        G = max(ACTION_RING, args.graph_steps // ACTION_RING * ACTION_RING)
+        if args.steps % G:
+            raise SystemExit("--steps must be a multiple of --graph-steps (rounded to the action ring: %d)" % G)
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(dev)
+        torch.cuda.synchronize(dev)
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(graph, stream=side):
+                for t in range(G):
+                    rc = env.step_raw(ring_ptrs[t % ACTION_RING])
+        torch.cuda.synchronize(dev)
+        graph.replay()                                   # warm
+        torch.cuda.synchronize(dev)
+        env.clear_stats()
+        launches0 = env.launch_count
+        barrier()
+        ev0.record(stream)
+        for t in range(args.steps // G):
+            graph.replay()
+        ev1.record(stream)
+        step_launches = args.steps
+    else:
+        ev0.record(stream)
+        for t in range(args.steps):
+            rc = env.step_raw(ring_ptrs[t % ACTION_RING])
+        ev1.record(stream)
+        step_launches = env.launch_count - launches0
     raw = env.stats_raw_device()                     # end-of-rollout statistics (+ NCCL all-reduce)
     if world > 1:
         raw = raw.clone()
@@ -567,7 +594,7 @@ def run_ours(args):
                                 "per-agent ASCII crops u8[25+25+1089] + reward rows f32[7] + terminated u8[3] per env, pinned host"
                                 if firemaker else "ASCII board u8 (the reference's ascii_codes observation; value-mapped to float32 "
                                                   "lazily on the host) + reward row f32 + terminated u8 per env, pinned host")},
-            "gpu_launches": step_launches,
+            "gpu_launches": step_launches, "cuda_graph_steps": args.graph_steps if graph is not None else 0,
             "clocks": clocks,
             "episodes_finished": stats["episodes"], "mean_episode_length": stats.get("mean_length"),
         }
@@ -592,6 +619,9 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: the workload's batch per GPU (default); strong: the workload's batch in total, split over the GPUs")
     ap.add_argument("--envs-per-gpu", type=int, default=None)
+    ap.add_argument("--graph-steps", type=int, default=0,
+                    help="capture this many consecutive step launches in one CUDA graph and replay it (0 = plain launches); for "
+                         "small batches whose kernel is shorter than the host's launch overhead")
     ap.add_argument("--e2e-steps", type=int, default=30)
     ap.add_argument("--e2e-parts", type=int, default=4, help="slices of the split-batch double buffering of the e2e leg")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="budget of the oracle-port CPU baseline (N=1 only)")

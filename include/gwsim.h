@@ -353,6 +353,13 @@ int gw_random_actions(GwHandle h, uint64_t seed, uint64_t step, int32_t lo, int3
 /* Number of kernels this library has launched through this handle (bench.py's gpu_launches). */
 int64_t gw_launch_count(GwHandle h);
 
+/* Checkpointing (safety_game_mo.py:406-419 / safety_game_moma.py:414-427 pickle the environment): everything a handle's
+ * future depends on is the caller-owned state blob plus this call counter, which keys the
+ * Philox streams (shuffle order, in-game draws).  Saving both and restoring them into a handle created with the same
+ * configuration, seed and env_index_base continues the run bit for bit. */
+int64_t gw_call_count(GwHandle h);            /* classic handles draw per-episode / per-frame numbers; 0 for the MO games */
+int gw_set_call_count(GwHandle h, int64_t calls);
+
 /* The `RGB` observation (ObservationToArrayWithRGBEx.__call__, environments/shared/observation_distiller_ex.py:147-189 over
  * pycolab/rendering.py:491-549 ObservationToArray): rgb[i][c][cell] = lut[3 * board[i][cell] + c], uint8 [n][3][cells], for ANY
  * of this library's boards (every kernel's `board` tensor holds ASCII codes).  `board_pitch` = bytes between the boards of two

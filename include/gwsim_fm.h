@@ -127,6 +127,13 @@ int gw_fm_stats_device(GwFmHandle h, double* device_raw_out, void* stream);
 int gw_fm_stats_clear(GwFmHandle h, void* stream);
 int64_t gw_fm_launch_count(GwFmHandle h);
 
+/* Checkpointing (safety_game_mo.py:406-419 / safety_game_moma.py:414-427 pickle the environment): everything a handle's
+ * future depends on is the caller-owned state blob (and maps / resources tensors) plus this call counter, which keys the
+ * Philox streams (shuffle order, in-game draws).  Saving both and restoring them into a handle created with the same
+ * configuration, seed and env_index_base continues the run bit for bit. */
+int64_t gw_fm_call_count(GwFmHandle h);
+int gw_fm_set_call_count(GwFmHandle h, int64_t calls);
+
 #ifdef __cplusplus
 }
 #endif

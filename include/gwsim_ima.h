@@ -113,6 +113,13 @@ int gw_ima_stats_device(GwImaHandle h, double* device_raw_out, void* stream);
 int gw_ima_stats_clear(GwImaHandle h, void* stream);
 int64_t gw_ima_launch_count(GwImaHandle h);
 
+/* Checkpointing (safety_game_mo.py:406-419 / safety_game_moma.py:414-427 pickle the environment): everything a handle's
+ * future depends on is the caller-owned state blob (and maps / resources tensors) plus this call counter, which keys the
+ * Philox streams (shuffle order, in-game draws).  Saving both and restoring them into a handle created with the same
+ * configuration, seed and env_index_base continues the run bit for bit. */
+int64_t gw_ima_call_count(GwImaHandle h);
+int gw_ima_set_call_count(GwImaHandle h, int64_t calls);
+
 #ifdef __cplusplus
 }
 #endif

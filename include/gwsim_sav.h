@@ -162,6 +162,13 @@ int gw_sav_stats_device(GwSavHandle h, double* device_raw_out /* [GW_MA_STATS_LE
 int gw_sav_stats_clear(GwSavHandle h, void* stream);
 int64_t gw_sav_launch_count(GwSavHandle h);
 
+/* Checkpointing (safety_game_mo.py:406-419 / safety_game_moma.py:414-427 pickle the environment): everything a handle's
+ * future depends on is the caller-owned state blob (and maps / resources tensors) plus this call counter, which keys the
+ * Philox streams (shuffle order, in-game draws).  Saving both and restoring them into a handle created with the same
+ * configuration, seed and env_index_base continues the run bit for bit. */
+int64_t gw_sav_call_count(GwSavHandle h);
+int gw_sav_set_call_count(GwSavHandle h, int64_t calls);
+
 #ifdef __cplusplus
 }
 #endif

@@ -158,3 +158,29 @@ def test_core_api_replays_reference_traces(name):
         if not np.isnan(d["perf"][t]):
             assert float(np.sum(env.get_last_performance())) == d["perf"][t], ctx
     env.close()
+
+
+def test_factory_serves_the_multi_agent_games():
+    """helpers/factory.py:185-201 serves EVERY environment: the multi-agent games come back as core environments whose TimeStep
+    fields are dicts keyed by the agent character (rl/pycolab_interface_ma.py:173-246)."""
+    import numpy as np
+    from ai_safety_gridworlds_b200.helpers import factory
+    from ai_safety_gridworlds_b200.helpers.safety_env import StepType
+    assert {"firemaker_ex_ma", "island_navigation_ex_ma", "aintelope_savanna", "food_sharing", "island_navigation_ex", "whisky_gold"} <= set(factory.environment_names())
+    for name, kw, chars in (("firemaker_ex_ma", {"amount_agents": 3}, ["1", "2", "S"]), ("island_navigation_ex_ma", {}, ["1", "2"]),
+                            ("aintelope_savanna", {}, ["0"]), ("food_sharing", {}, None)):
+        env = factory.get_environment_obj(name, **kw)
+        ts = env.reset()
+        chars = chars or sorted(ts.step_type)
+        assert sorted(ts.step_type) == sorted(chars) and all(st is StepType.FIRST for st in ts.step_type.values())
+        assert ts.reward is None and ts.observation["RGB"].dtype == np.uint8 and ts.observation["RGB"].shape[0] == 3
+        assert sorted(env.action_spec()) == sorted(chars)
+        for t in range(5):
+            ts = env.step({ch: {"step": 1 + (t + i) % 4} for i, ch in enumerate(chars)})
+            assert sorted(ts.reward) == sorted(chars) and all(st is StepType.MID for st in ts.step_type.values())
+            assert sorted(ts.observation["agent_observations"]) == sorted(chars)
+        env.close()
+    ids = [r[0] for r in factory.gym_registrations()]
+    assert "IslandNavigationEx-v0" in ids and "ai_safety_gridworlds.boat_race_ex-v0" in ids and "SushiGoal2-v0" in ids
+    with pytest.raises(NotImplementedError):
+        factory.get_environment_obj("no_such_environment")

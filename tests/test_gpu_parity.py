@@ -25,9 +25,11 @@ def _np(t):
 
 
 @pytest.mark.parametrize("name", golden_names())
-def test_cuda_replays_reference_trace(name):
+def test_cuda_replays_reference_trace(name, monkeypatch):
     """Every recorded reference trace, replayed on the GPU with the stored actions (N=3 copies of
-    the same environment so that a ragged, partial warp is exercised too)."""
+    the same environment so that a ragged, partial warp is exercised too); the persistent TMA kernel is
+    forced (a 3-environment batch would get the direct-store kernel, which the random-batch test covers)."""
+    monkeypatch.setenv("GWSIM_STEP_IMPL", "tma")
     d, meta = load_golden(name)
     spec = spec_for(meta)
     env = _venv(spec, 3, 0)
@@ -83,12 +85,16 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("impl", ["tma", "direct"])
 @pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("case", range(len(CASES)))
-def test_cuda_matches_oracle_on_random_batches(case, mode, oracle_lib):
+def test_cuda_matches_oracle_on_random_batches(case, mode, impl, oracle_lib, monkeypatch):
     """1000 environments (31 full warps + a ragged one), 150 steps of Philox actions: every output
-    tensor, the extras and the rollout statistics against the scalar CPU oracle."""
+    tensor, the extras and the rollout statistics against the scalar CPU oracle -- through both step
+    kernels (gw_create picks the direct-store kernel for small batches and the persistent TMA kernel
+    for large ones; GWSIM_STEP_IMPL forces one)."""
     from ai_safety_gridworlds_b200 import make_spec
+    monkeypatch.setenv("GWSIM_STEP_IMPL", impl)
     name, kwargs, lo, hi = CASES[case]
     spec = make_spec(name, autoreset_mode=mode, **kwargs)
     N, T = 1000, 150
@@ -257,13 +263,14 @@ def test_bad_arguments_fail_loudly():
     env.close()
 
 
-def test_step_is_cuda_graph_capturable(oracle_lib):
+def test_step_is_cuda_graph_capturable(oracle_lib, monkeypatch):
     """gw_step captured once in a CUDA graph and replayed gives what the same launches give eagerly: the persistent kernels
     keep no launch-to-launch state on the host (the work queue resets itself on the device), so a replay is a full step.
     Checked against the oracle for the single-agent kernel, the classic mixed batch and firemaker_ex_ma."""
     from ai_safety_gridworlds_b200 import make_spec
     from ai_safety_gridworlds_b200.vector_env import _ptr
     dev = torch.device("cuda", 0)
+    monkeypatch.setenv("GWSIM_STEP_IMPL", "tma")       # the kernel with the device-side work queue
     N, K, ROUNDS = 5000, 6, 4
     spec = make_spec("boat_race_ex", autoreset_mode=1, level=3)
     env = _venv(spec, N, 1)
