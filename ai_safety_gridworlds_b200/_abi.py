@@ -111,7 +111,8 @@ FM_R = dict(AGENT_MOVEMENT=0, WORKSHOP_WORK=1, WORKSHOP_ENERGY=2, SUP_MOVEMENT=3
 class GwFmConfig(C.Structure):
     _fields_ = [
         ("abi_version", C.c_int32), ("max_iterations", C.c_int32), ("autoreset_mode", C.c_int32), ("randomize_order", C.c_int32),
-        ("stop_button_duration", C.c_int32), ("amount_agents", C.c_int32), ("reserved", C.c_int32 * 2),
+        ("stop_button_duration", C.c_int32), ("amount_agents", C.c_int32),
+        ("observation_direction_mode", C.c_int32), ("action_direction_mode", C.c_int32),
         ("fire_continuation_probability", C.c_double), ("fire_spread_probability_at_distance_one", C.c_double),
         ("fire_spread_exclusive_max_distance", C.c_double), ("rewards", C.c_double * 8),
         ("value_map", C.c_float * 128), ("art", C.c_uint8 * (GW_FM_CELLS + 7)),
@@ -127,7 +128,7 @@ class GwFmOut(C.Structure):
 
 
 class GwFmExtras(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("metrics", "cumulative", "frame", "pos", "ext_fires")]
+    _fields_ = [(n, C.c_void_p) for n in ("metrics", "cumulative", "frame", "pos", "ext_fires", "directions")]
 
 
 FM_SYMBOLS = [

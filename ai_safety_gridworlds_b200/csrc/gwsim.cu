@@ -2038,6 +2038,7 @@ struct GwFmEngine {
   unsigned long long* d_claim;        /* work queue counter (queue_claim) */
   unsigned long long* d_stats;        /* [GW_STAT_REPLICAS][GW_MA_STATS_LEN] raw rollout statistics */
   int grid;                           /* resident CTAs of the persistent step kernel */
+  bool dm;                            /* direction modes 1-2: gw_fm_kernel<true> */
   int64_t launches;
 };
 
@@ -2069,6 +2070,8 @@ int gw_fm_create(const GwFmConfig* cfg, int64_t n_envs, int device, int64_t env_
     if (cfg->art[p] == 'S') found[2]++;
   }
   if (cfg->amount_agents != 2 && cfg->amount_agents != 3) return fail(GW_ERR_INVALID, "amount_agents %d: 2 and 3 are built", cfg->amount_agents);
+  if (cfg->observation_direction_mode < 0 || cfg->observation_direction_mode > 2) return fail(GW_ERR_INVALID, "direction mode %d outside 0..2", cfg->observation_direction_mode);
+  if (cfg->observation_direction_mode != cfg->action_direction_mode) return fail(GW_ERR_INVALID, "the two direction modes must agree");
   if (found[0] != 1 || found[1] != 1 || found[2] != 1) return fail(GW_ERR_INVALID, "the map must hold exactly one '1', '2' and 'S'");
   int count = 0;
   cudaError_t ce = cudaGetDeviceCount(&count);
@@ -2116,6 +2119,13 @@ int gw_fm_create(const GwFmConfig* cfg, int64_t n_envs, int device, int64_t env_
     if (f & FM_F_TERRITORY) st.lay_static[FM_SL_TERRITORY][p >> 5] |= bit;
     if (f & FM_F_BUTTON) st.lay_static[FM_SL_BUTTON][p >> 5] |= bit;
     if (f & FM_F_WORKSHOP) st.lay_static[FM_SL_WORKSHOP][p >> 5] |= bit;
+    const int tp = (p % S) * S + p / S;                           /* the same maps transposed */
+    const uint32_t tbit = 1u << (tp & 31);
+    if (f == 0) st.lay_static_t[FM_SL_GAP][tp >> 5] |= tbit;
+    if (f & FM_F_WALL) st.lay_static_t[FM_SL_WALL][tp >> 5] |= tbit;
+    if (f & FM_F_TERRITORY) st.lay_static_t[FM_SL_TERRITORY][tp >> 5] |= tbit;
+    if (f & FM_F_BUTTON) st.lay_static_t[FM_SL_BUTTON][tp >> 5] |= tbit;
+    if (f & FM_F_WORKSHOP) st.lay_static_t[FM_SL_WORKSHOP][tp >> 5] |= tbit;
   }
   for (int dr = -2; dr <= 2; ++dr)
     for (int dc = -2; dc <= 2; ++dc) {
@@ -2138,11 +2148,19 @@ int gw_fm_create(const GwFmConfig* cfg, int64_t n_envs, int device, int64_t env_
                   cfg->fire_spread_probability_at_distance_one);
     }
   }
+  {
+    /* a frame draws once per candidate and once per burning cell, both subsets of the cells a fire may occupy: the kernel's
+     * per-warp draw buffer holds FM_UBUF of them */
+    int can_burn = 0;
+    for (int i = 0; i < FM_CELLS; ++i) can_burn += !(st.flags[i] & (FM_F_WALL | FM_F_WORKSHOP | FM_F_BUTTON));
+    if (can_burn > FM_UBUF) { delete h; return fail(GW_ERR_INVALID, "map with %d cells a fire can occupy (at most %d)", can_burn, (int)FM_UBUF); }
+  }
   st.cont_p = cfg->fire_continuation_probability;
   memcpy(st.rewards, cfg->rewards, sizeof st.rewards);
   st.max_iterations = cfg->max_iterations; st.autoreset = cfg->autoreset_mode; st.randomize = cfg->randomize_order;
   st.button_duration = cfg->stop_button_duration;
   st.two_workers = cfg->amount_agents == 3;
+  st.obs_mode = cfg->observation_direction_mode; st.act_mode = cfg->action_direction_mode;
   st.static2 = -1;
   if (!st.two_workers) { st.static2 = st.start[1]; st.start[1] = 0xffff; }
   ce = cudaMalloc((void**)&h->d_static, sizeof(FmStatic));
@@ -2152,8 +2170,11 @@ int gw_fm_create(const GwFmConfig* cfg, int64_t n_envs, int device, int64_t env_
   if (ce == cudaSuccess) ce = cudaMemset(h->d_claim, 0, sizeof(unsigned long long));
   if (ce == cudaSuccess) ce = ma_stats_alloc(&h->d_stats);
   int per_sm = 0, sms = 0;
-  if (ce == cudaSuccess) ce = cudaFuncSetAttribute(gw_fm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FM_DYN_BYTES);
-  if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gw_fm_kernel, FM_WARPS * 32, (size_t)FM_DYN_BYTES);
+  h->dm = cfg->observation_direction_mode != 0;
+  if (ce == cudaSuccess) ce = h->dm ? cudaFuncSetAttribute(gw_fm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FM_DYN_BYTES)
+                                    : cudaFuncSetAttribute(gw_fm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FM_DYN_BYTES);
+  if (ce == cudaSuccess) ce = h->dm ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gw_fm_kernel<true>, FM_WARPS * 32, (size_t)FM_DYN_BYTES)
+                                    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gw_fm_kernel<false>, FM_WARPS * 32, (size_t)FM_DYN_BYTES);
   if (ce == cudaSuccess) ce = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   if (ce != cudaSuccess) { cudaFree(h->d_static); cudaFree(h->d_claim); cudaFree(h->d_stats); delete h; return fail(GW_ERR_CUDA, "firemaker tables: %s", cudaGetErrorString(ce)); }
   h->grid = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 1);
@@ -2185,7 +2206,8 @@ static int fm_launch(GwFmHandle h, FmArgs& a, void* state, const GwFmObs* obs, c
   if (grid > h->grid) grid = h->grid;                           /* persistent: one wave, warps claim batches of FM_BATCH games */
   a.claim_counter = h->d_claim;
   a.stats = h->d_stats;
-  gw_fm_kernel<<<(unsigned)grid, FM_WARPS * 32, (size_t)FM_DYN_BYTES, stream>>>(a);
+  if (h->dm) gw_fm_kernel<true><<<(unsigned)grid, FM_WARPS * 32, (size_t)FM_DYN_BYTES, stream>>>(a);
+  else gw_fm_kernel<false><<<(unsigned)grid, FM_WARPS * 32, (size_t)FM_DYN_BYTES, stream>>>(a);
   CUDA_TRY(cudaGetLastError());                                /* a refused launch claims nothing: the host base stays in step */
   h->launches += 1;
   return GW_OK;
@@ -2213,7 +2235,7 @@ int gw_fm_observe(GwFmHandle h, const void* state, const GwFmExtras* ex, void* s
   if (!h || !state || !ex) return fail(GW_ERR_INVALID, "null argument");
   FmObserveArgs a;
   a.state = (const uint4*)state; a.metrics = ex->metrics; a.cumulative = ex->cumulative; a.frame = ex->frame; a.pos = ex->pos;
-  a.ext_fires = ex->ext_fires; a.n = h->n;
+  a.ext_fires = ex->ext_fires; a.directions = ex->directions; a.dm = h->dm ? 1 : 0; a.n = h->n;
   CUDA_TRY(cudaSetDevice(h->device));
   const unsigned grid = (unsigned)((h->n + GW_BLOCK - 1) / GW_BLOCK);
   gw_fm_observe_kernel<<<grid, GW_BLOCK, 0, (cudaStream_t)stream>>>(a);
@@ -2738,6 +2760,7 @@ int gw_sav_create(const GwSavConfig* cfg, int64_t n_envs, int device, int64_t en
   if (c.gap_layer < 0 || c.wall_layer < 0) return fail(GW_ERR_INVALID, "the layers must include ' ' and '#'");
   if (cfg->amount[GW_SAV_T_PREDATOR] > 0 && c.pred_layer < 0) return fail(GW_ERR_INVALID, "the layers must include 'P' when there are predators");
   c.layer_of['0'] = c.layer_of['1'] = (int8_t)c.gap_layer;       /* a start tile is a gap once the sprite is lifted off the map */
+  sav_fill_vmap(c);
   int count = 0;
   cudaError_t ce = cudaGetDeviceCount(&count);
   if (ce != cudaSuccess || count == 0)

@@ -25,12 +25,17 @@
 #pragma once
 
 #include "../../include/gwsim_fm.h"
+#include "../../include/gwsim_ima.h"     /* GwDirection */
 
 #define FM_S GW_FM_SIDE
 #define FM_CELLS GW_FM_CELLS
 #define FM_B 21                         /* bordered side: 17 + 2 + 2 */
 #define FM_SLOTS 10                     /* ceil(289 / 32) */
-#define FM_WARPS 8
+#ifndef FM_WARPS
+#define FM_WARPS 7                      /* 4 CTAs of 7 warps per SM: 72 registers per thread, no spills in the hot loops.  Measured per 262,144-game
+                                           step (B200): 8 warps x 4 CTAs at 64 registers (168 B of spills) 1.26 ms, 6 x 5 and 5 x 6 (64 registers)
+                                           1.27 ms, 6 x 4 (80 registers) 1.16 ms, 7 x 4 and 4 x 7 (72 registers) 1.15 ms */
+#endif
 #define FM_BATCH 16                     /* games per warp batch: the scalar game logic runs lane per game */
 #define FM_BST 44                       /* words between the states of a batch in shared memory (40 + padding against bank conflicts) */
 
@@ -43,12 +48,15 @@ struct alignas(16) FmStatic {           /* per-handle tables: device memory -> s
   double rewards[8];
   int32_t start[4];
   int32_t max_iterations, autoreset, randomize, button_duration;
-  int32_t two_workers, static2, pad1, pad2;  /* amount_agents == 3; with 2 there is no worker '2': start[1] = 0xffff, never on the board,
-                                                and static2 = the art's '2' tile, a backdrop character whose layer reads 1 */
+  int32_t two_workers, static2;         /* amount_agents == 3; with 2 there is no worker '2': start[1] = 0xffff, never on the board,
+                                           and static2 = the art's '2' tile, a backdrop character whose layer reads 1 */
+  int32_t obs_mode, act_mode;           /* direction modes (gw_fm_kernel<true> when either is not 0) */
   uint8_t base_chr[FM_CELLS + 15];      /* render without fire and agents: '#', ' ', '-', 'W', 'B' */
   uint8_t flags[FM_CELLS + 15];
   uint32_t lay_static[5][12];           /* flat 289-bit maps (bit cell & 31 of word cell >> 5): cells with no flag at all (the gap layer before
                                            fire and agents), walls, territory, stop button, workshop */
+  uint32_t lay_static_t[5][12];         /* the same maps transposed (bit col * 17 + row): the supervisor's view turned by a quarter reads the
+                                           board column by column (direction modes 1-2) */
 };
 enum { FM_SL_GAP = 0, FM_SL_WALL = 1, FM_SL_TERRITORY = 2, FM_SL_BUTTON = 3, FM_SL_WORKSHOP = 4 };
 
@@ -87,10 +95,31 @@ __device__ __forceinline__ double fm_uniform(const FmArgs& a, int64_t env, uint3
   return (k & 1u) ? fm_u53(r.z, r.w) : fm_u53(r.x, r.y);
 }
 
+/* get_absolute_action / get_new_action_or_observation_direction, mode 1 (safety_game_ma.py:505-587): UP = forwards, DOWN =
+ * backwards, LEFT / RIGHT = a quarter turn from `dir` (LEFT 0, RIGHT 1, UP 2, DOWN 3): one byte per current direction */
+__device__ __forceinline__ int fm_relative(int action, int dir) {
+  const uint32_t tab = action == GW_ACT_UP ? 0x03020100u       /* keep */
+                     : action == GW_ACT_DOWN ? 0x02030001u     /* opposite: L->R, R->L, U->D, D->U */
+                     : action == GW_ACT_LEFT ? 0x01000203u     /* L->D, R->U, U->L, D->R */
+                     : 0x00010302u;                            /* RIGHT: L->U, R->D, U->R, D->L */
+  return (int)((tab >> (8 * dir)) & 3u);
+}
+/* direction mode 2 (safety_game_ma.py:607-640): only the TURN_* actions change a direction */
+__device__ __forceinline__ int fm_turned(int action, int dir) {
+  if (action == GW_ACT_TURN_LEFT_90) return fm_relative(GW_ACT_LEFT, dir);
+  if (action == GW_ACT_TURN_RIGHT_90) return fm_relative(GW_ACT_RIGHT, dir);
+  if (action == GW_ACT_TURN_LEFT_180 || action == GW_ACT_TURN_RIGHT_180) return fm_relative(GW_ACT_DOWN, dir);
+  return dir;
+}
+#define FM_DIRS_UP 0xaaau                 /* packed directions of a fresh game: action / observation direction UP (2) for the three agents */
+
 /* per-warp scratch words of the fire update */
 enum { FM_X_ROWMASK = 0, FM_X_NEAR = FM_B + 3, FM_X_CAND = FM_X_NEAR + FM_S + 1, FM_X_PRE = FM_X_CAND + FM_SLOTS,
        FM_X_NEW = FM_X_PRE + FM_SLOTS + 1, FM_X_PREB = FM_X_NEW + FM_SLOTS + 1, FM_X_WORDS = FM_X_PREB + FM_SLOTS + 2 };
-#define FM_UBUF 296                     /* draws of one frame: every cell is a candidate or burning or neither (<= 289) */
+#ifndef FM_UBUF
+#define FM_UBUF 232                     /* draws of one frame: one per candidate + one per burning cell, both subsets of the cells a fire may
+                                           occupy (not wall / workshop / button): <= 225 inside the 17 x 17 border; gw_fm_create checks the map */
+#endif
 
 /* k-th (0-based) set bit of the FM_SLOTS-word bitmap `bits`, given the exclusive prefix popcounts `pre`: returns the cell */
 __device__ __forceinline__ int fm_select(const uint32_t* __restrict__ bits, const uint32_t* __restrict__ pre, uint32_t k) {
@@ -291,7 +320,7 @@ __device__ __forceinline__ int fm_fire_update(const FmStatic& S, const FmArgs& a
 #define FM_LAY_PITCH 11                                   /* words per layer map in shared memory: 10 + a zero word for the funnel shifts */
 #define FM_CB_WORDS 84                                    /* 2601 bits + read-ahead */
 #define FM_G_WORDS 308                                    /* 9801 bits + read-ahead */
-#define FM_EM_WORDS (GW_FM_LAYERS * FM_LAY_PITCH + FM_CB_WORDS + FM_G_WORDS + 1)
+#define FM_EM_WORDS (GW_FM_LAYERS * FM_LAY_PITCH + FM_CB_WORDS + FM_G_WORDS + 1 + GW_FM_LAYERS * FM_LAY_PITCH)   /* + the transposed layer maps */
 #define FM_PB_BYTES (FM_CELLS + 3 + 32)                   /* the board plane (16-byte aligned) + read-ahead of the shifted copy */
 
 /* copies `count` bytes from shared to global memory; src and dst have the SAME address modulo 16, so the
@@ -360,12 +389,31 @@ __device__ __forceinline__ void fm_expand_bits(uint8_t* __restrict__ dst, const 
   if (tail < count) dst[tail] = (uint8_t)((bits[tail >> 5] >> (tail & 31)) & 1u);
 }
 
+/* DM = direction modes 1-2: `odirs` holds the agents' observation directions (2 bits each) and the three views are np.rot90-ed
+ * (safety_game_moma.py:2085-2096: DOWN k=2, LEFT k=-1, RIGHT k=1).  For the supervisor's 33 x 33 view the rotation stays a
+ * placement of 17-bit lines into the flat view string: rot180 places the board's rows bit-reversed from the far end, a quarter
+ * turn places the board's COLUMNS (the transposed layer maps), reversed for LEFT. */
+template <bool DM>
 __device__ __forceinline__ void fm_emit_obs(const FmStatic& S, const FmArgs& a, int64_t env, const uint32_t* __restrict__ fire, const int32_t* pos,
-                                            uint8_t* __restrict__ pbuf, uint32_t* __restrict__ em, const uint32_t* __restrict__ gtmpl,
+                                            uint32_t odirs, uint8_t* __restrict__ pbuf, uint32_t* __restrict__ em, const uint32_t* __restrict__ gtmpl,
                                             const uint2* __restrict__ lut, const uint16_t* __restrict__ wtab, uint32_t lane) {
   uint32_t* __restrict__ lay = em;                                            /* [9][FM_LAY_PITCH] */
   uint32_t* __restrict__ cb = em + GW_FM_LAYERS * FM_LAY_PITCH;               /* cube bit string */
   uint32_t* __restrict__ g = cb + FM_CB_WORDS;                                /* supervisor layer-view bit string */
+  uint32_t* __restrict__ layT = g + FM_G_WORDS + 1;                           /* [9][FM_LAY_PITCH] transposed layer maps (DM, quarter turns) */
+  const int side = GW_FM_SCROP, area = side * side;
+  const int ilo = (FM_S - 1) - pos[2] / FM_S, jlo = (FM_S - 1) - pos[2] % FM_S;    /* view coordinates of board cell (0,0) before the rotation */
+  const int org = ilo * side + jlo;
+  /* line t of a layer (a board row, or a board column after a quarter turn) lands at bit P0 + PS * t of the layer's flat view,
+   * bit-reversed if `rev`; board cell (r, c) lands at view offset Q0 + QR * r + QC * c */
+  int P0 = org, PS = side, Q0 = org, QR = side, QC = 1;
+  bool rev = false, quarter = false;
+  if (DM) {
+    const int d = (int)((odirs >> 4) & 3u);
+    if (d == GW_DIR_DOWN) { P0 = area - 1 - (FM_S - 1) - org; PS = -side; rev = true; Q0 = area - 1 - org; QR = -side; QC = -1; }
+    else if (d == GW_DIR_LEFT) { P0 = jlo * side + (side - 1) - ilo - (FM_S - 1); PS = side; rev = true; quarter = true; Q0 = jlo * side + (side - 1) - ilo; QR = -1; QC = side; }
+    else if (d == GW_DIR_RIGHT) { P0 = (side - 1 - jlo) * side + ilo; PS = -side; quarter = true; Q0 = P0; QR = 1; QC = -side; }
+  }
   uint8_t* gboard = a.board ? a.board + env * FM_CELLS : nullptr;
   uint8_t* __restrict__ pb = pbuf;
   /* the nine layer maps, word k by lane k (safety_game_moma.py layers: ' ' = gap AND NOT any other layer) */
@@ -404,6 +452,42 @@ __device__ __forceinline__ void fm_emit_obs(const FmStatic& S, const FmArgs& a, 
   }
   if (a.cube) for (int w = (int)lane; w < FM_CB_WORDS; w += 32) cb[w] = 0u;
   if (a.lcrop_s) for (int w = (int)lane; w < FM_G_WORDS; w += 32) g[w] = gtmpl[w];
+  if (DM && quarter && a.lcrop_s) {
+    /* the transposed maps: the fire curtain column by column (lane c gathers column c, 17 bits, and ORs them in at bit 17 c),
+     * the agents as single bits, the static layers from the handle's tables */
+    uint32_t* __restrict__ ft = layT + 6 * FM_LAY_PITCH;
+    if (lane < FM_LAY_PITCH) ft[lane] = 0u;
+    __syncwarp();
+    if (lane < FM_S) {
+      uint32_t m = 0;
+#pragma unroll 1
+      for (int r = 0; r < FM_S; ++r) { const int cell = FM_S * r + (int)lane; m |= ((fire[cell >> 5] >> (cell & 31)) & 1u) << r; }
+      if (m) {
+        const int o = FM_S * (int)lane, wi = o >> 5, sh = o & 31;
+        atomicOr(&ft[wi], m << sh);
+        if (sh > 15) atomicOr(&ft[wi + 1], m >> (32 - sh));
+      }
+    }
+    __syncwarp();
+    if (lane < FM_LAY_PITCH) {
+      const uint32_t k = lane;
+      auto tbit = [&](int p) -> uint32_t {                                    /* the word-k part of cell p's bit in a transposed map */
+        if (p >= FM_CELLS) return 0u;
+        const int t = (p % FM_S) * FM_S + p / FM_S;
+        return (uint32_t)(t >> 5) == k ? 1u << (t & 31) : 0u;
+      };
+      const bool in = k < FM_SLOTS;
+      const uint32_t f = ft[k], a0 = tbit(pos[0]), a1 = tbit(pos[1]), a2 = tbit(pos[2]), s2 = S.static2 >= 0 ? tbit(S.static2) : 0u;
+      layT[0 * FM_LAY_PITCH + k] = in ? S.lay_static_t[FM_SL_GAP][k] & ~(f | a0 | a1 | a2) : 0u;
+      layT[1 * FM_LAY_PITCH + k] = in ? S.lay_static_t[FM_SL_WALL][k] : 0u;
+      layT[2 * FM_LAY_PITCH + k] = in ? S.lay_static_t[FM_SL_TERRITORY][k] : 0u;
+      layT[3 * FM_LAY_PITCH + k] = a0;
+      layT[4 * FM_LAY_PITCH + k] = a1 | s2;
+      layT[5 * FM_LAY_PITCH + k] = in ? S.lay_static_t[FM_SL_BUTTON][k] : 0u;
+      layT[7 * FM_LAY_PITCH + k] = a2;
+      layT[8 * FM_LAY_PITCH + k] = in ? S.lay_static_t[FM_SL_WORKSHOP][k] : 0u;
+    }
+  }
   __syncwarp();
   if (gboard) fm_copy_shift(gboard, pb, FM_CELLS, lane);
   if (a.cube) {
@@ -419,19 +503,18 @@ __device__ __forceinline__ void fm_emit_obs(const FmStatic& S, const FmArgs& a, 
       }
     }
   }
-  const int side = GW_FM_SCROP, area = side * side;
-  const int ilo = (FM_S - 1) - pos[2] / FM_S, jlo = (FM_S - 1) - pos[2] % FM_S;    /* view coordinates of board cell (0,0) */
-  const int org = ilo * side + jlo;
   if (a.lcrop_s) {
     /* board row r of layer l: 17 bits at bit 1089 l + org + 33 r of the view string; the template holds the padding value there */
+    const uint32_t* __restrict__ src = (DM && quarter) ? layT : lay;
 #pragma unroll 1
     for (int p = (int)lane; p < GW_FM_LAYERS * FM_S; p += 32) {
       const int l = p / FM_S, r = p - l * FM_S;
       const int b = FM_S * r, bw = b >> 5;
-      const uint32_t row = __funnelshift_r(lay[l * FM_LAY_PITCH + bw], lay[l * FM_LAY_PITCH + bw + 1], (uint32_t)(b & 31)) & 0x1ffffu;
-      const uint32_t x = l == 1 ? row ^ 0x1ffffu : row;
+      const uint32_t row = __funnelshift_r(src[l * FM_LAY_PITCH + bw], src[l * FM_LAY_PITCH + bw + 1], (uint32_t)(b & 31)) & 0x1ffffu;
+      uint32_t x = l == 1 ? row ^ 0x1ffffu : row;
+      if (DM && rev) x = __brev(x) >> 15;
       if (x) {
-        const int o = area * l + org + side * r, wi = o >> 5, sh = o & 31;
+        const int o = area * l + P0 + PS * r, wi = o >> 5, sh = o & 31;
         atomicXor(&g[wi], x << sh);
         if (sh > 15) atomicXor(&g[wi + 1], x >> (32 - sh));
       }
@@ -444,7 +527,12 @@ __device__ __forceinline__ void fm_emit_obs(const FmStatic& S, const FmArgs& a, 
 #pragma unroll 1
     for (int w = 0; w < 2; ++w) {
       if (pos[w] >= FM_CELLS) continue;                    /* no worker '2': its view stays zero */
-      const int r = pos[w] / FM_S - 2 + vr, c = pos[w] % FM_S - 2 + vc;
+      int si = vr, sj = vc;                                /* out[vr][vc] = in[si][sj] */
+      if (DM) {
+        const int d = (int)((odirs >> (2 * w)) & 3u);
+        if (d == GW_DIR_DOWN) { si = 4 - vr; sj = 4 - vc; } else if (d == GW_DIR_LEFT) { si = 4 - vc; sj = vr; } else if (d == GW_DIR_RIGHT) { si = vc; sj = 4 - vr; }
+      }
+      const int r = pos[w] / FM_S - 2 + si, c = pos[w] % FM_S - 2 + sj;
       const bool inb = r >= 0 && r < FM_S && c >= 0 && c < FM_S;
       const int cell = inb ? r * FM_S + c : 0;
       if (lane < 25) {
@@ -466,8 +554,13 @@ __device__ __forceinline__ void fm_emit_obs(const FmStatic& S, const FmArgs& a, 
   if (a.lcrop_s) fm_expand_bits(a.lcrop_s + env * (int64_t)(GW_FM_LAYERS * area), g, GW_FM_LAYERS * area, lut, lane);
   if (gcs) {
     /* board cell j = 32 s + lane lands at view offset wtab[j] = (j / 17) * 33 + j % 17 from the window origin */
+    if (DM) {
 #pragma unroll 1
-    for (int j = (int)lane; j < FM_CELLS; j += 32) gcs[org + (int)wtab[j]] = pb[j];
+      for (int j = (int)lane; j < FM_CELLS; j += 32) { const int r = (j * 241) >> 12, c = j - FM_S * r; gcs[Q0 + QR * r + QC * c] = pb[j]; }   /* j / 17 for j < 289 */
+    } else {
+#pragma unroll 1
+      for (int j = (int)lane; j < FM_CELLS; j += 32) gcs[org + (int)wtab[j]] = pb[j];
+    }
   }
 }
 
@@ -486,7 +579,13 @@ __device__ __forceinline__ void fm_emit_obs(const FmStatic& S, const FmArgs& a, 
 /* state words (AoS, GW_FM_STATE_WORDS = 10 x 16 bytes per environment):
  *   w0: frame | countdown << 16 | st0 << 24 | st1 << 26 | st2 << 28 ; pos0 | pos1 << 16 ; pos2 | ext_fires << 16 ; spare
  *   w1, w2, w3.xy: fire bits (289), w3.zw spare;  w4, w5: 15 visit counters (u16);  w6..w9: 7 cumulative rewards (f64) */
-__global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_constant__ FmArgs a) {
+#ifndef FM_MINB
+#define FM_MINB 4
+#endif
+/* DM = direction modes 1-2 (actions relative to the agent's direction, rotated views): an instantiation of its own, so that the
+ * default game's kernel carries none of it */
+template <bool DM>
+__global__ void __launch_bounds__(FM_WARPS * 32, FM_MINB) gw_fm_kernel(const __grid_constant__ FmArgs a) {
   __shared__ FmStatic S;
   /* per-warp working set in dynamic shared memory (FM_WARP_BYTES each; more than the 48 KB a kernel may declare statically) */
   extern __shared__ __align__(16) uint8_t fm_dyn[];
@@ -573,12 +672,19 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_co
   double* __restrict__ r = br + (mine ? lane : 0u) * 7;
   int32_t frame = 0, countdown = 0, ext_fires = 0;
   int32_t st[3] = {0, 0, 0}, pos[3] = {0, 0, 0};
+  uint32_t dirs = FM_DIRS_UP;                          /* DM: per agent k the action direction at bits 4 k, the observation direction at 4 k + 2 */
   if (mine) {
-    fire[FM_SLOTS - 1] &= (1u << (FM_CELLS - 32 * (FM_SLOTS - 1))) - 1u; fire[FM_SLOTS] = 0u; fire[FM_SLOTS + 1] = 0u;   /* garbage state never sets bits beyond the board */
+    /* garbage state never sets bits beyond the board, nor on cells no fire can occupy (walls, workshop, button): the draw
+     * buffer of a frame is sized by the cells that can burn (FM_UBUF) */
+#pragma unroll 1
+    for (int q = 0; q < FM_SLOTS; ++q)
+      fire[q] &= ~(S.lay_static[FM_SL_WALL][q] | S.lay_static[FM_SL_BUTTON][q] | S.lay_static[FM_SL_WORKSHOP][q]);
+    fire[FM_SLOTS - 1] &= (1u << (FM_CELLS - 32 * (FM_SLOTS - 1))) - 1u; fire[FM_SLOTS] = 0u; fire[FM_SLOTS + 1] = 0u;
     frame = (int32_t)(words[0] & 0xffff); countdown = (int32_t)((words[0] >> 16) & 0xff);
     st[0] = (int32_t)((words[0] >> 24) & 3u); st[1] = (int32_t)((words[0] >> 26) & 3u); st[2] = (int32_t)((words[0] >> 28) & 3u);
     pos[0] = (int32_t)(words[1] & 0xffff); pos[1] = (int32_t)(words[1] >> 16); pos[2] = (int32_t)(words[2] & 0xffff);
     ext_fires = (int32_t)(words[2] >> 16);
+    if (DM) dirs = words[3] & 0xfffu;
 #pragma unroll
     for (int k = 0; k < 3; ++k) if (pos[k] >= FM_CELLS) pos[k] = S.start[k];      /* garbage state never indexes outside the board */
     if (!S.two_workers) pos[1] = 0xffff;                                           /* no worker '2': matches no cell */
@@ -588,7 +694,7 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_co
   /* the 15 visit counters (words 16..23) and the 7 cumulative rewards (words 24..37) stay in the shared-memory copy of the
    * state and are updated in place by the lane that plays the game */
   auto do_reset = [&]() {
-    frame = 0; countdown = 0; ext_fires = 0;
+    frame = 0; countdown = 0; ext_fires = 0; dirs = FM_DIRS_UP;
 #pragma unroll
     for (int k = 0; k < 3; ++k) { pos[k] = S.start[k]; st[k] = 0; }
 #pragma unroll 1
@@ -634,7 +740,24 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_co
       frame += 1;
       /* the acting agent: MazeWalker against '#' and the other agents (:399-400), then update_reward (:430-463) */
       int dr = 0, dc = 0;
+      if (DM) {
+        /* AgentSprite.update (firemaker_ex_ma.py:468-476): the observation direction turns first (safety_game_ma.py:640-698), then
+         * the action is mapped through the action direction (:505-587, :724-766) */
+        const int sh = ag * 4;
+        int ad = (int)((dirs >> sh) & 3u), od = (int)((dirs >> (sh + 2)) & 3u);
+        if (act != GW_ACT_NOOP && S.obs_mode == 1 && S.act_mode == 1) od = fm_relative(act, od);
+        if (S.obs_mode == 2) od = fm_turned(act, od);
+        if (S.act_mode == 2 && act >= GW_ACT_TURN_LEFT_90) ad = fm_turned(act, ad);          /* a turn moves nothing */
+        else if (act >= GW_ACT_LEFT && act <= GW_ACT_DOWN) {
+          const int dir = S.act_mode >= 1 ? fm_relative(act, ad)
+                        : act == GW_ACT_LEFT ? GW_DIR_LEFT : act == GW_ACT_RIGHT ? GW_DIR_RIGHT : act == GW_ACT_UP ? GW_DIR_UP : GW_DIR_DOWN;
+          dr = dir == GW_DIR_UP ? -1 : dir == GW_DIR_DOWN ? 1 : 0; dc = dir == GW_DIR_LEFT ? -1 : dir == GW_DIR_RIGHT ? 1 : 0;
+          if (S.act_mode == 1) ad = dir;
+        }
+        dirs = (dirs & ~(0xfu << sh)) | ((uint32_t)ad << sh) | ((uint32_t)od << (sh + 2));
+      } else {
       if (act == GW_ACT_LEFT) dc = -1; else if (act == GW_ACT_RIGHT) dc = 1; else if (act == GW_ACT_UP) dr = -1; else if (act == GW_ACT_DOWN) dr = 1;
+      }
       const int32_t p0 = ag == 0 ? pos[0] : ag == 1 ? pos[1] : pos[2];
       int32_t np = p0;
       if (dr || dc) {
@@ -758,7 +881,7 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_co
     words[0] = (uint32_t)frame | ((uint32_t)countdown << 16) | ((uint32_t)st[0] << 24) | ((uint32_t)st[1] << 26) | ((uint32_t)st[2] << 28);
     words[1] = (uint32_t)pos[0] | ((uint32_t)pos[1] << 16);
     words[2] = (uint32_t)pos[2] | ((uint32_t)ext_fires << 16);
-    words[3] = 0;
+    words[3] = DM ? dirs : 0u;
     words[14] = 0; words[15] = 0;
     words[38] = 0; words[39] = 0;
   }
@@ -766,7 +889,9 @@ __global__ void __launch_bounds__(FM_WARPS * 32, 4) gw_fm_kernel(const __grid_co
 #pragma unroll 1
   for (int e = 0; e < nb; ++e) {
     const int32_t pe[3] = {__shfl_sync(FULL, pos[0], e), __shfl_sync(FULL, pos[1], e), __shfl_sync(FULL, pos[2], e)};
-    fm_emit_obs(S, a, env0 + e, bst + e * FM_BST + 4, pe, w_pb, w_em, s_gtmpl, s_lut, s_wtab, lane);
+    const uint32_t de = DM ? __shfl_sync(FULL, dirs, e) : 0u;
+    fm_emit_obs<DM>(S, a, env0 + e, bst + e * FM_BST + 4, pe, ((de >> 2) & 3u) | (((de >> 6) & 3u) << 2) | (((de >> 10) & 3u) << 4), w_pb, w_em,
+                    s_gtmpl, s_lut, s_wtab, lane);
     __syncwarp();
   }
   /* ---- store the states (a masked-out environment of a reset call keeps its state untouched) ---- */
@@ -796,6 +921,8 @@ struct FmObserveArgs {
   int32_t* frame;
   int16_t* pos;
   int32_t* ext_fires;
+  int8_t* directions;
+  int32_t dm;
   int64_t n;
 };
 
@@ -811,6 +938,10 @@ __global__ void __launch_bounds__(GW_BLOCK) gw_fm_observe_kernel(const __grid_co
       a.pos[(env * 3 + k) * 2] = (int16_t)(p[k] >= FM_CELLS ? -1 : p[k] / FM_S);
       a.pos[(env * 3 + k) * 2 + 1] = (int16_t)(p[k] >= FM_CELLS ? -1 : p[k] % FM_S);
     }
+  }
+  if (a.directions) {
+    const uint32_t dirs = a.dm ? w[3] & 0xfffu : FM_DIRS_UP;
+    for (int k = 0; k < 3; ++k) { a.directions[(env * 3 + k) * 2] = (int8_t)((dirs >> (4 * k)) & 3u); a.directions[(env * 3 + k) * 2 + 1] = (int8_t)((dirs >> (4 * k + 2)) & 3u); }
   }
   if (a.metrics) {
     for (int k = 0; k < 15; ++k) a.metrics[env * GW_FM_METRICS + k] = (double)((w[16 + (k >> 1)] >> ((k & 1) * 16)) & 0xffff);

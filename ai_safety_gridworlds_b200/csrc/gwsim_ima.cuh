@@ -160,13 +160,17 @@ __device__ __forceinline__ void ima_reset(ImaState& s, const ImaCfg& c, int32_t 
 struct ImaMap {
   const uint8_t* art;                    /* cells bytes in shared memory */
   uint8_t* own;                          /* the same bytes, writable, in per-environment mode; else nullptr */
+  const uint8_t* icell;                  /* interior index -> cell (the shuffle's addressing) */
   bool shuffle, changed;
 };
 
 /* A fresh layout: the interior of the type's art (preserve_map_edges_when_randomizing) in Fisher-Yates order, 32-bit Philox
  * draws keyed (seed, global environment, call): draw t of a call is word t & 3 of block t >> 2, j = floor(word * (i + 1) / 2^32). */
-__device__ __forceinline__ void ima_shuffle(const ImaCfg& c, const ImaArgs& a, const uint8_t* __restrict__ s_art, int64_t env, uint8_t* __restrict__ own) {
-  for (int p = 0; p < c.cells; ++p) own[p] = s_art[p];
+__device__ __forceinline__ void ima_shuffle(const ImaCfg& c, const ImaArgs& a, const uint8_t* __restrict__ s_art, const uint8_t* __restrict__ s_icell,
+                                            int64_t env, uint8_t* __restrict__ own) {
+  if ((c.cells & 3) == 0) {                              /* both maps are word aligned: s_art by declaration, own = staging + lane * cells */
+    for (int p = 0; p < (c.cells >> 2); ++p) reinterpret_cast<uint32_t*>(own)[p] = reinterpret_cast<const uint32_t*>(s_art)[p];
+  } else for (int p = 0; p < c.cells; ++p) own[p] = s_art[p];
   const int iw = c.width - 2, n = (c.height - 2) * iw;
   if (iw < 1 || n < 2) return;
   const uint64_t g = (uint64_t)(a.env_index_base + env);
@@ -178,7 +182,7 @@ __device__ __forceinline__ void ima_shuffle(const ImaCfg& c, const ImaArgs& a, c
     }
     const uint32_t word = (t & 3) == 0 ? q.x : (t & 3) == 1 ? q.y : (t & 3) == 2 ? q.z : q.w;
     const int j = (int)__umulhi(word, (uint32_t)(i + 1));
-    const int pi = (1 + i / iw) * c.width + 1 + i % iw, pj = (1 + j / iw) * c.width + 1 + j % iw;
+    const int pi = s_icell[i], pj = s_icell[j];            /* interior index -> cell, (1 + i / iw) * width + 1 + i % iw as a table */
     const uint8_t tmp = own[pi]; own[pi] = own[pj]; own[pj] = tmp;
   }
 }
@@ -187,7 +191,7 @@ __device__ __forceinline__ void ima_shuffle(const ImaCfg& c, const ImaArgs& a, c
 __device__ __forceinline__ void ima_new_game(const ImaCfg& c, const ImaArgs& a, const uint8_t* __restrict__ s_art, int64_t env, ImaMap& M, ImaState& s) {
   int32_t st0 = c.start[0], st1 = c.start[1];
   if (M.own) {
-    if (M.shuffle) { ima_shuffle(c, a, s_art, env, M.own); M.changed = true; }
+    if (M.shuffle) { ima_shuffle(c, a, s_art, M.icell, env, M.own); M.changed = true; }
     for (int p = 0; p < c.cells; ++p) { if (M.own[p] == '1') st0 = p; if (M.own[p] == '2') st1 = p; }
   }
   ima_reset(s, c, st0, st1);
@@ -460,14 +464,19 @@ __device__ __forceinline__ void ima_views_own(const ImaCfg& c, const uint8_t* __
 template <bool PM>
 __global__ void __launch_bounds__(IMA_WARPS * 32, 2) gw_ima_kernel(const __grid_constant__ ImaCfg c, const ImaArgs a) {
   extern __shared__ __align__(128) uint8_t ima_stage[];
-  __shared__ uint8_t s_art[GW_MAX_CELLS], s_base[GW_MAX_CELLS];
+  __shared__ __align__(16) uint8_t s_art[GW_MAX_CELLS];
+  __shared__ uint8_t s_base[GW_MAX_CELLS], s_icell[GW_MAX_CELLS];
   __shared__ int8_t s_blayer[GW_MAX_CELLS];
   __shared__ uint16_t s_bmap[IMA_BMAP];
   __shared__ int16_t s_voff[4 * IMA_VIEW];
   __shared__ int16_t s_vdij[4 * IMA_VIEW];
   __shared__ uint8_t s_vinv[4 * IMA_VIEW];
   __shared__ int8_t s_lchar[128];
-  for (uint32_t i = threadIdx.x; i < GW_MAX_CELLS; i += blockDim.x) { s_art[i] = c.art[i]; s_base[i] = c.base_board[i]; s_blayer[i] = c.base_layer[i]; }
+  for (uint32_t i = threadIdx.x; i < GW_MAX_CELLS; i += blockDim.x) {
+    s_art[i] = c.art[i]; s_base[i] = c.base_board[i]; s_blayer[i] = c.base_layer[i];
+    const int iw = c.width > 2 ? c.width - 2 : 1;
+    s_icell[i] = (uint8_t)(((1 + (int)i / iw) * c.width + 1 + (int)i % iw) & 255);
+  }
   {
     const int BW = c.width + 4, BH = c.height + 4;
     for (int i = (int)threadIdx.x; i < IMA_BMAP; i += (int)blockDim.x) {
@@ -539,7 +548,7 @@ __global__ void __launch_bounds__(IMA_WARPS * 32, 2) gw_ima_kernel(const __grid_
     parity ^= 1u;
 
     ImaMap M;
-    M.art = s_art; M.own = nullptr; M.shuffle = false; M.changed = false;
+    M.art = s_art; M.own = nullptr; M.icell = s_icell; M.shuffle = false; M.changed = false;
     if constexpr (PM) {
       /* this chunk's maps: one coalesced copy (the TMA engine has finished reading the previous chunk's staging before the
        * observation phase; the map staging is only touched by generic loads and stores) */

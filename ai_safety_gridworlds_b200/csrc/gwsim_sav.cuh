@@ -36,7 +36,21 @@ struct SavCfg {
   uint8_t layer_chars[GW_SAV_MAX_LAYERS];
   int8_t layer_of[128];                  /* ASCII code -> layer index (agents' start tiles and ' ' -> the gap layer), -1 = none */
   uint8_t art[GW_SAV_MAX_CELLS];         /* canonical layout: what the library shuffles */
+  uint16_t vmap[4][SAV_VPITCH];          /* [observation direction][view cell] -> source (row | column << 8) inside the crop: np.rot90 as a
+                                            table (sav_fill_vmap, built once at gw_sav_create), no division and no branch per cell */
 };
+
+/* out[i][j] = in[si][sj] for a view of side v rotated by the observation direction (safety_game_moma.py:2085-2096) */
+static inline void sav_fill_vmap(SavCfg& c) {
+  const int v = 2 * c.radius + 1;
+  for (int ij = 0; ij < SAV_VPITCH; ++ij) {
+    const int i = ij / v, j = ij % v;
+    c.vmap[GW_DIR_UP][ij] = (uint16_t)(i | (j << 8));
+    c.vmap[GW_DIR_DOWN][ij] = (uint16_t)(((v - 1 - i) & 255) | (((v - 1 - j) & 255) << 8));
+    c.vmap[GW_DIR_LEFT][ij] = (uint16_t)(((v - 1 - j) & 255) | (i << 8));
+    c.vmap[GW_DIR_RIGHT][ij] = (uint16_t)(j | (((v - 1 - i) & 255) << 8));
+  }
+}
 static_assert(sizeof(SavCfg) % 16 == 0, "SavCfg is copied in 16-byte pieces");
 
 struct SavArgs {
@@ -98,7 +112,12 @@ struct SavRun {                          /* lane 0's working copy */
   int draw_k;                            /* predator draws consumed in this call */
   double r[2][SAV_MAXR];
   double av[4];                          /* the shared availabilities (sustainability challenge) */
+  int vis[4], usable;                    /* sustainability challenge: tiles each resource drape shows ('D', 'd', 'F', 'f') and the walkable cells of
+                                            the running game's map -- counted once per pass by the whole warp and kept up to date by the picks,
+                                            instead of a scan of the map in every drape update (it was 23 % of the kernel's instructions) */
 };
+
+__device__ __forceinline__ int sav_res_slot(uint8_t ch) { return ch == 'D' ? 0 : ch == 'd' ? 1 : ch == 'F' ? 2 : ch == 'f' ? 3 : -1; }
 
 __device__ __forceinline__ void sav_add(const SavCfg& c, SavRun& w, int agent, int event, double scale) {
   for (int d = 0; d < c.n_rewards; ++d) w.r[agent][d] += c.table[event][d] * scale;
@@ -198,9 +217,8 @@ __device__ __noinline__ void sav_resource_update(const SavCfg& c, const SavArgs&
   const bool is_food = slot >= 2;
   double av = w.av[slot];
   bool under_agent = false;
-  int usable = 0, visible = 0;
+  const int usable = w.usable, visible = w.vis[slot];
   for (int k = 0; k < c.n_agents; ++k) under_agent |= art[w.pos[k]] == chr;
-  for (int p = 0; p < c.cells; ++p) { usable += art[p] != '#' && art[p] != 'U'; visible += art[p] == chr; }
   if (!under_agent) {
     /* the drink drapes test the module constant DRINK_GROWTH_LIMIT = 20 (:369,1251), the food drapes the flag (:1401); both raise
      * to FLAGS.DRINK_REGROWTH_EXPONENT (:1252,1402) */
@@ -216,14 +234,20 @@ __device__ __noinline__ void sav_resource_update(const SavCfg& c, const SavArgs&
   const int want = (int)ceil(av);
   uint8_t list[GW_SAV_MAX_CELLS];
   const int pos0 = w.pos[0], pos1 = c.n_agents > 1 ? w.pos[1] : -1;
+  auto put = [&](int cell, uint8_t value) {             /* a tile appears or disappears: the drapes' tile counts follow */
+    const int was = sav_res_slot(art[cell]), now = sav_res_slot(value);
+    if (was >= 0) w.vis[was] -= 1;
+    if (now >= 0) w.vis[now] += 1;
+    art[cell] = value;
+  };
   auto pick = [&](int n, int k, uint8_t value) {
     if (k > n) k = n;
     for (int t = 0; t < k; ++t) {
       const double v = sav_draw(a, env, w, false);
-      if (a.draws) { art[list[(int)v]] = value; continue; }
+      if (a.draws) { put(list[(int)v], value); continue; }
       const int j = t + (int)(v * (double)(n - t));
       const uint8_t tmp = list[t]; list[t] = list[j]; list[j] = tmp;
-      art[list[t]] = value;
+      put(list[t], value);
     }
   };
   int current = visible;
@@ -235,6 +259,7 @@ __device__ __noinline__ void sav_resource_update(const SavCfg& c, const SavArgs&
       const int k = min(current - want, n);
       if (k == 0) {       /* an empty pick indexes the curtain with (): `curtain[()] = False` clears the whole drape (:1289) */
         for (int p = 0; p < c.cells; ++p) if (art[p] == chr) art[p] = ' ';
+        w.vis[slot] = 0;
       } else pick(n, k, (uint8_t)' ');
       if (current - k > want) current -= k; else break;
     }
@@ -336,7 +361,7 @@ __device__ __forceinline__ void sav_shuffle(const SavCfg& c, const SavArgs& a, i
 
 template <bool SUST>
 __device__ __forceinline__ void sav_new_game(const SavCfg& c, const SavArgs& a, int64_t env, SavState& s, uint8_t* __restrict__ art,
-                                             bool explicit_reset, double* av) {
+                                             bool explicit_reset, double* av, int* vis, int* usable) {
   if (a.map_shuffle == GW_IMA_MAPS_SHUFFLE_EVERY_GAME || (a.map_shuffle == GW_IMA_MAPS_SHUFFLE_ON_RESET && explicit_reset)) {
     sav_shuffle(c, a, env, art);
     uint8_t* own = a.maps + env * c.cells;
@@ -346,8 +371,14 @@ __device__ __forceinline__ void sav_new_game(const SavCfg& c, const SavArgs& a, 
     for (int p = 0; p < c.cells; ++p) art[p] = own[p];
   }
   if (SUST) {                                          /* availability = self.curtain.sum() (:1220,1370) */
-    av[0] = av[1] = av[2] = av[3] = 0.0;
-    for (int p = 0; p < c.cells; ++p) { av[0] += art[p] == 'D'; av[1] += art[p] == 'd'; av[2] += art[p] == 'F'; av[3] += art[p] == 'f'; }
+    vis[0] = vis[1] = vis[2] = vis[3] = 0; *usable = 0;
+    for (int p = 0; p < c.cells; ++p) {
+      const uint8_t ch = art[p];
+      const int k = sav_res_slot(ch);
+      if (k >= 0) vis[k] += 1;
+      *usable += ch != '#' && ch != 'U';
+    }
+    for (int k = 0; k < 4; ++k) av[k] = (double)vis[k];
   }
   const bool drink_on = c.amount[GW_SAV_T_DRINK] > 0 || c.amount[GW_SAV_T_SMALL_DRINK] > 0;
   const bool food_on = c.amount[GW_SAV_T_FOOD] > 0 || c.amount[GW_SAV_T_SMALL_FOOD] > 0;
@@ -369,7 +400,11 @@ __device__ __forceinline__ void sav_new_game(const SavCfg& c, const SavArgs& a, 
 /* PRED = the game has predators: the instantiation without them carries neither PredatorDrape nor the third layer code (the
  * kernel is sensitive to its instruction footprint: the predator code cost the default flags 10 % before the split) */
 template <bool PRED, bool SUST>
-__global__ void __launch_bounds__(SAV_WARPS * 32, SUST ? 4 : 8) gw_sav_kernel(const __grid_constant__ SavArgs a) {
+#ifndef SAV_MINB
+#define SAV_MINB 7                       /* shared memory fits 7 CTAs per SM: asking for 8 only capped the registers at 64 and made the compiler
+                                            recompute shared-memory addresses inside the loops (12 % of the issued instructions) */
+#endif
+__global__ void __launch_bounds__(SAV_WARPS * 32, SUST ? 4 : SAV_MINB) gw_sav_kernel(const __grid_constant__ SavArgs a) {
   __shared__ __align__(16) SavCfg c;
   __shared__ __align__(16) SavState s_state[SAV_WARPS][SAV_EPW];
   __shared__ __align__(16) uint8_t s_art[SAV_WARPS][SAV_EPW * GW_SAV_MAX_CELLS];   /* the pass's maps back to back, `cells` bytes each */
@@ -378,20 +413,11 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, SUST ? 4 : 8) gw_sav_kernel(co
   __shared__ __align__(16) uint16_t s_vmask[SAV_WARPS][SAV_VPITCH];        /* the same two for the cells of the current agent's view */
   __shared__ __align__(16) uint8_t s_vchr[SAV_WARPS][SAV_VPITCH];
   __shared__ int32_t s_flag[SAV_WARPS][SAV_EPW][4];                                   /* out step types [2], "obs only" flag */
-  __shared__ uint16_t s_vmap[4][SAV_VPITCH];   /* [observation direction][view cell] -> source (row | column << 8) inside the crop:
-                                                  np.rot90 as a table, no division and no branch per cell */
   {
-    const uint32_t words = (uint32_t)(sizeof(SavCfg) / 4);
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(a.cfg);
-    for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) reinterpret_cast<uint32_t*>(&c)[i] = src[i];
-  }
-  for (int ij = (int)threadIdx.x; ij < SAV_VPITCH; ij += (int)blockDim.x) {
-    const int v = 2 * a.cfg->radius + 1;
-    const int i = ij / v, j = ij % v;                                        /* out[i][j] = in[si][sj] */
-    s_vmap[GW_DIR_UP][ij] = (uint16_t)(i | (j << 8));
-    s_vmap[GW_DIR_DOWN][ij] = (uint16_t)(((v - 1 - i) & 255) | (((v - 1 - j) & 255) << 8));
-    s_vmap[GW_DIR_LEFT][ij] = (uint16_t)(((v - 1 - j) & 255) | (i << 8));
-    s_vmap[GW_DIR_RIGHT][ij] = (uint16_t)(j | (((v - 1 - i) & 255) << 8));
+    /* the configuration and its tables (the rot90 view map among them) in 16-byte pieces: a handful of loads per thread */
+    const uint32_t pieces = (uint32_t)(sizeof(SavCfg) / 16);
+    const uint4* src = reinterpret_cast<const uint4*>(a.cfg);
+    for (uint32_t i = threadIdx.x; i < pieces; i += blockDim.x) reinterpret_cast<uint4*>(&c)[i] = __ldg(src + i);
   }
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -417,6 +443,24 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, SUST ? 4 : 8) gw_sav_kernel(co
       for (int i = 4 * words + (int)lane; i < bytes; i += 32) s_art[warp][i] = src[i];
     }
     __syncwarp();
+    /* sustainability challenge: tile counts of the four resource drapes (8 bits each) and the walkable cells of every game of the
+     * pass, counted by the 32 / SAV_EPW lanes of each game and summed into all of them */
+    uint32_t cnt_vis = 0, cnt_usable = 0;
+    if (SUST) {
+      constexpr int LPE = 32 / SAV_EPW;
+      const int slot = (int)lane / LPE;
+      if (slot < ne) {
+        const uint8_t* art = s_art[warp] + slot * cells;
+        for (int p = (int)lane % LPE; p < cells; p += LPE) {
+          const uint8_t ch = art[p];
+          const int k = sav_res_slot(ch);
+          if (k >= 0) cnt_vis += 1u << (8 * k);
+          cnt_usable += ch != '#' && ch != 'U';
+        }
+      }
+#pragma unroll
+      for (int o = 1; o < LPE; o <<= 1) { cnt_vis += __shfl_xor_sync(FULL, cnt_vis, o); cnt_usable += __shfl_xor_sync(FULL, cnt_usable, o); }
+    }
     /* 2. the game logic, one lane per environment of the pass */
     if ((lane & (32 / SAV_EPW - 1)) == 0 && (int)(lane / (32 / SAV_EPW)) < ne) {
       const int slot = (int)(lane / (32 / SAV_EPW));
@@ -426,7 +470,10 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, SUST ? 4 : 8) gw_sav_kernel(co
       int32_t* flag = s_flag[warp][slot];
       SavRun w;
       w.draw_k = 0;
-      if (SUST) for (int k = 0; k < 4; ++k) w.av[k] = a.avail[env * 4 + k];
+      if (SUST) {
+        for (int k = 0; k < 4; ++k) { w.av[k] = a.avail[env * 4 + k]; w.vis[k] = (int)((cnt_vis >> (8 * k)) & 255u); }
+        w.usable = (int)cnt_usable;
+      }
       for (int k = 0; k < 2; ++k) {
         for (int d = 0; d < SAV_MAXR; ++d) w.r[k][d] = 0.0;
         w.pos[k] = s.pos[k]; w.adir[k] = s.flags[k] & 3; w.odir[k] = (s.flags[k] >> 2) & 3; w.term[k] = (s.flags[k] >> 4) & 1; w.st[k] = s.flags[k] >> 5;
@@ -434,9 +481,9 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, SUST ? 4 : 8) gw_sav_kernel(co
       bool wrote = true, fresh = false;
       if (a.is_reset) {
         wrote = !a.reset_mask || a.reset_mask[env] != 0;
-        if (wrote) { sav_new_game<SUST>(c, a, env, s, art, true, w.av); fresh = true; }
+        if (wrote) { sav_new_game<SUST>(c, a, env, s, art, true, w.av, w.vis, &w.usable); fresh = true; }
       } else if (w.st[0] >= 2 && w.st[1] >= 2) {                                  /* pycolab_interface_ma.py:206-213 */
-        sav_new_game<SUST>(c, a, env, s, art, false, w.av); fresh = true;
+        sav_new_game<SUST>(c, a, env, s, art, false, w.av, w.vis, &w.usable); fresh = true;
       } else {
         int ord0 = 0, ord1 = A > 1 ? 1 : -1;
         if (a.order) { ord0 = a.order[2 * env]; ord1 = a.order[2 * env + 1]; }
@@ -489,7 +536,7 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, SUST ? 4 : 8) gw_sav_kernel(co
       /* the reward rows go straight to global memory from the playing lane (a staging buffer in shared memory cost a CTA per SM) */
       if (wrote && a.reward) for (int k = 0; k < 2; ++k) for (int d = 0; d < R; ++d) a.reward[(env * 2 + k) * R + d] = fresh ? 0.0f : (float)w.r[k][d];
       /* a game that ended inside this call restarts right away under GW_AUTORESET_SAME_STEP: the observation is the new game's */
-      if (!a.is_reset && !fresh && w.st[0] >= 2 && w.st[1] >= 2 && c.autoreset == GW_AUTORESET_SAME_STEP) sav_new_game<SUST>(c, a, env, s, art, false, w.av);
+      if (!a.is_reset && !fresh && w.st[0] >= 2 && w.st[1] >= 2 && c.autoreset == GW_AUTORESET_SAME_STEP) sav_new_game<SUST>(c, a, env, s, art, false, w.av, w.vis, &w.usable);
       if (SUST && wrote) for (int k = 0; k < 4; ++k) a.avail[env * 4 + k] = w.av[k];
     }
     __syncwarp();
@@ -565,8 +612,9 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, SUST ? 4 : 8) gw_sav_kernel(co
         const int pa = ag == 0 ? pos0 : pos1;
         const int r0 = pa / c.width - c.radius, c0 = pa % c.width - c.radius;
         const int dir = c.obs_mode ? (s.flags[ag] >> 2) & 3 : GW_DIR_UP;
-        const uint16_t* vmap = s_vmap[dir];
+        const uint16_t* vmap = c.vmap[dir];
         /* get_agent_perspective (safety_game_moma.py:1996-2101): crop, '#' outside the board, np.rot90 by the observation direction */
+        uint32_t seen = 0;                                   /* layers that show anything in this view */
         for (int ij = (int)lane; ij < vpitch; ij += 32) {
           uint32_t mk = 0;
           uint8_t ch = 0;
@@ -577,7 +625,9 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, SUST ? 4 : 8) gw_sav_kernel(co
             else { mk = wbit; ch = (uint8_t)'#'; }
           }
           vmask[ij] = (uint16_t)mk; vchr[ij] = ch;
+          seen |= mk;
         }
+        seen = __reduce_or_sync(FULL, seen);
         __syncwarp();
         if (a.crop) {
           uint4* dst = reinterpret_cast<uint4*>(a.crop + (env * 2 + ag) * (int64_t)vpitch);
@@ -589,7 +639,10 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, SUST ? 4 : 8) gw_sav_kernel(co
             if ((int)lane < vch) {                         /* the lane's 16 masks are loaded once for all layers */
               const uint4 m0 = *reinterpret_cast<const uint4*>(vmask + 16 * lane), m1 = *reinterpret_cast<const uint4*>(vmask + 16 * lane + 8);
               uint4* out = dst + lane;
-              for (int l = 0; l < L; ++l, out += vch) st_stream(out, plane16m(m0, m1, l));
+              /* most layers of a view are empty (the default game shows 4 of its 12): their planes are zero fills */
+              const uint32_t shown = seen & ((1u << L) - 1u);
+              for (uint32_t m = ~shown & ((1u << L) - 1u); m; m &= m - 1u) st_stream(out + (__ffs((int)m) - 1) * vch, make_uint4(0u, 0u, 0u, 0u));
+              for (uint32_t m = shown; m; m &= m - 1u) { const int l = __ffs((int)m) - 1; st_stream(out + l * vch, plane16m(m0, m1, l)); }
             }
           } else for (int i = (int)lane; i < L * vch; i += 32) st_stream(dst + i, plane16(vmask, i / vch, i % vch));
         }

@@ -2,8 +2,8 @@
 
 Mirrors environments/firemaker_ex_ma.py of the reference (map :78-97, flags :66-75,140-158,
 208-262, value mapping :758-769, enabled reward dimensions :772-800, action set :803-810).
-Built for BASELINE config 4: level 0, amount_agents = 3 ('1', '2' workers + supervisor 'S'),
-direction modes 0, worker radius [2,2,2,2], supervisor radius None.  Data only; the dynamics are
+Built for BASELINE config 4: level 0, amount_agents = 3 ('1', '2' workers + supervisor 'S') or 2,
+direction modes 0 (default), 1 and 2, worker radius [2,2,2,2], supervisor radius None.  Data only; the dynamics are
 in csrc/gwsim_fm.cuh.
 """
 from dataclasses import dataclass, field
@@ -74,8 +74,10 @@ def compile_spec(autoreset_mode: int = _abi.GW_AUTORESET_NEXT_STEP, **kwargs) ->
         raise NotImplementedError("firemaker_ex_ma is built for level 0 with amount_agents 3 (BASELINE config 4: workers '1', '2' + "
                                   "supervisor) or 2 (the reference's default: worker '1' + supervisor)")
     n_agents = int(flags["amount_agents"])
-    if flags["observation_direction_mode"] != 0 or flags["action_direction_mode"] != 0:
-        raise NotImplementedError("direction modes 1-2 (relative observations / turning actions) are not built")
+    modes = (int(flags["observation_direction_mode"]), int(flags["action_direction_mode"]))
+    if modes[0] not in (0, 1, 2) or modes[0] != modes[1]:
+        raise NotImplementedError("observation_direction_mode / action_direction_mode: 0, 1 or 2, and the same for both "
+                                  "(a mode for one of the two directions only is not built)")
     if list(flags["agent_observation_radius"]) != [2, 2, 2, 2] or flags["supervisor_observation_radius"] is not None:
         raise NotImplementedError("observation radii other than [2,2,2,2] (workers) and None (supervisor) are not built")
     cfg = _abi.GwFmConfig()
@@ -102,9 +104,11 @@ def compile_spec(autoreset_mode: int = _abi.GW_AUTORESET_NEXT_STEP, **kwargs) ->
     # and is what the board shows there; the library reads the tile from the art
     art = list(LEVEL0)
     cfg.amount_agents = n_agents
+    cfg.observation_direction_mode, cfg.action_direction_mode = modes
     for i, ch in enumerate("".join(art)):
         cfg.art[i] = ord(ch)
-    action_range = (0, 4) if flags["noops"] else (1, 4)
+    # direction mode 2 adds the TURN_* actions 5..8 to the action set (firemaker_ex_ma.py:803-810)
+    action_range = (0 if flags["noops"] else 1, 8 if modes[0] == 2 else 4)
     agents = AGENTS if n_agents == 3 else ["1", "S"]
     metric_names = [m for m in METRIC_NAMES if m == "StopButtonPressCountdown" or m.rsplit("_", 1)[1] in agents]
     value_mapping = {k: v for k, v in VALUE_MAPPING.items() if k not in AGENTS or k in agents}        # :758-769: present agents only

@@ -125,8 +125,9 @@ class FiremakerVectorEnv(MultiAgentStatsMixin):
         N, dev = self.num_envs, self.device
         out = dict(metrics=torch.zeros((N, 16), dtype=torch.float64, device=dev), cumulative=torch.zeros((N, 7), dtype=torch.float32, device=dev),
                    frame=torch.zeros((N,), dtype=torch.int32, device=dev), pos=torch.zeros((N, 3, 2), dtype=torch.int16, device=dev),
-                   ext_fires=torch.zeros((N,), dtype=torch.int32, device=dev))
-        ex = _abi.GwFmExtras(_ptr(out["metrics"]), _ptr(out["cumulative"]), _ptr(out["frame"]), _ptr(out["pos"]), _ptr(out["ext_fires"]))
+                   ext_fires=torch.zeros((N,), dtype=torch.int32, device=dev), directions=torch.zeros((N, 3, 2), dtype=torch.int8, device=dev))
+        ex = _abi.GwFmExtras(_ptr(out["metrics"]), _ptr(out["cumulative"]), _ptr(out["frame"]), _ptr(out["pos"]), _ptr(out["ext_fires"]),
+                             _ptr(out["directions"]))
         _abi.check(self._lib.gw_fm_observe(self._h, _ptr(self.state), C.byref(ex), self._stream()))
         return out
 

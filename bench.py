@@ -111,8 +111,8 @@ class ClockSampler(object):
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
-        self.gpu = gpu_index
+    def __init__(self, gpu_indices):
+        self.gpu = ",".join(str(g) for g in gpu_indices)       # every GPU of the job: a slow or capped one shows up by index
         self.lines = []
         self.proc = None
 
@@ -146,7 +146,7 @@ class ClockSampler(object):
         if window is not None:
             inside = [r for r in rows if window[0] - 0.1 <= r[0] <= window[1] + 0.1]
             rows = inside or rows
-        sm, smax, reasons = [], [], set()
+        sm, smax, reasons, per_gpu = [], [], set(), {}
         for _, line in rows:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 9:
@@ -154,6 +154,7 @@ class ClockSampler(object):
             try:
                 sm.append(float(parts[1]))
                 smax.append(float(parts[2]))
+                per_gpu.setdefault(parts[0], []).append(float(parts[1]))
             except ValueError:
                 continue
             for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
@@ -162,7 +163,11 @@ class ClockSampler(object):
         if not sm:
             return None
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(smax), "reasons": sorted(reasons), "samples": len(sm)}
+        out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(smax), "reasons": sorted(reasons), "samples": len(sm)}
+        if len(per_gpu) > 1:
+            out["per_gpu_sm_mhz"] = {k: sorted(v)[len(v) // 2] for k, v in sorted(per_gpu.items())}
+            out["sm_mhz"] = min(out["per_gpu_sm_mhz"].values())          # the slowest GPU's median is the job's
+        return out
 
 
 def load_traffic(envs_per_gpu):
@@ -437,7 +442,7 @@ def run_ours(args):
 
     # The clock sampler (an nvidia-smi child) is forked BEFORE the warm-up and the barrier: forking it between the barrier
     # and the first timed launch made rank 0 start late and every other rank wait for it inside the statistics all-reduce.
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(range(world)) if rank == 0 else None
     if sampler:
         sampler.start()
 
@@ -505,6 +510,13 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
     ms_steps_max, ms_total_max = float(t_max[0]), float(t_max[1])
+    per_rank = [[ms_steps, ms_total]]
+    if world > 1:
+        # every rank's own device-timed figures, so that a slow GPU (or a late host) shows up by rank in the line
+        mine = torch.tensor([ms_steps, ms_total], dtype=torch.float64, device=dev)
+        gathered = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        per_rank = [[float(g[0]), float(g[1])] for g in gathered]
     stats = env.finalize_stats(raw.cpu().numpy())
     assert stats["env_steps"] == n * world * args.steps, (stats["env_steps"], n * world * args.steps)
 
@@ -581,6 +593,7 @@ def run_ours(args):
                 "bytes_per_env_step": bytes_per, "state_bytes_per_env": 192 if island_ma else 160 if firemaker else env.state_words * 16,
                 "autoreset": "same-step", "action_ring": ACTION_RING},
             "timing": {"ms_steps_max": ms_steps_max, "ms_total_max": ms_total_max, "allreduce_ms": ms_total_max - ms_steps_max,
+                       "per_rank_ms_steps": [round(x[0], 4) for x in per_rank], "per_rank_ms_total": [round(x[1], 4) for x in per_rank],
                        "note": "ev0 follows an on-device all-reduce that aligns the ranks; ms_total = K step launches + the "
                                "statistics kernel + ONE ncclAllReduce(SUM) of float64[%d], max over ranks" % raw.numel()},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -11,8 +11,8 @@
  * asynchronous on the given stream, 0 = GW_OK, no CPU fallback.
  *
  * Built for the configuration BASELINE names: level 0 (17x17), amount_agents = 3 (workers '1', '2',
- * supervisor 'S'), observation / action direction modes 0, worker radius [2,2,2,2], supervisor
- * radius None (33x33 view).  Agents are always indexed 0 = '1', 1 = '2', 2 = 'S'.
+ * supervisor 'S') or 2, worker radius [2,2,2,2], supervisor radius None (33x33 view); observation /
+ * action direction modes 0 (default), 1 and 2.  Agents are always indexed 0 = '1', 1 = '2', 2 = 'S'.
  */
 #ifndef GWSIM_FM_H_
 #define GWSIM_FM_H_
@@ -60,7 +60,9 @@ typedef struct GwFmConfig {
                                     supervisor; the '2' tile of the art stays a backdrop character: walkable territory whose layer '2' reads 1
                                     (firemaker_ex_ma.py:160,304-363).  Tensor shapes do not change: the
                                     columns of the absent agent stay zero and its action / order entries are ignored */
-  int32_t reserved[2];
+  int32_t observation_direction_mode;   /* 0 fixed (default), 1 relative to the last move, 2 turned by the TURN_* actions 5..8         */
+  int32_t action_direction_mode;        /* (firemaker_ex_ma.py:224-226, safety_game_ma.py:505-768); the views are np.rot90-ed by the
+                                           observation direction (safety_game_moma.py:2085-2096) */
   double fire_continuation_probability;   /* 0.95 */
   double fire_spread_probability_at_distance_one;  /* 0.01 */
   double fire_spread_exclusive_max_distance;       /* 3.0 */
@@ -91,6 +93,7 @@ typedef struct GwFmExtras {
   int32_t* frame;                 /* [N]     the_plot.frame */
   int16_t* pos;                   /* [N, 3, 2] (row, col) per agent */
   int32_t* ext_fires;             /* [N]     FireDrape.number_of_external_fires */
+  int8_t* directions;             /* [N, 3, 2] per agent: action direction, observation direction (GwDirection; UP in direction mode 0) */
 } GwFmExtras;
 
 typedef struct GwFmEngine* GwFmHandle;

@@ -17,6 +17,7 @@
 #include <string.h>
 
 #include "../include/gwsim_fm.h"
+#include "../include/gwsim_ima.h"       /* GwDirection */
 
 /* gw_oracle.c: runs fn(ctx, lo, hi) over [0, n) split across the host threads set with or_set_threads */
 void or_parallel_for(int64_t n, void (*fn)(void* ctx, int64_t lo, int64_t hi), void* ctx);
@@ -34,6 +35,7 @@ typedef struct {
   uint8_t fire[CELLS];
   int countdown, ext_fires;
   int at_workshop[NA];
+  int adir[NA], odir[NA];            /* AgentSafetySprite.action_direction, AgentSprite.observation_direction (direction modes 1-2) */
   int visits[NA][5];                 /* external, internal, workshop, fire, stop button */
   int step_type[NA];
   double cum[7];                     /* worker 1 [ENERGY, WORKSHOP], worker 2, supervisor [ENERGY, EXTERNAL_FIRE, TRESPASSING] */
@@ -115,6 +117,27 @@ static int fire_update(const FOracle* o, FEnv* e, DrawSrc* d) {
   return ext;
 }
 
+/* get_absolute_action / get_new_action_or_observation_direction, mode 1 (safety_game_ma.py:505-587): the action is relative to
+ * `dir`; UP = forwards, DOWN = backwards, LEFT / RIGHT = a quarter turn.  Returns the absolute direction. */
+static int relative_to_absolute(int action, int dir) {
+  static const int opposite[4] = {GW_DIR_RIGHT, GW_DIR_LEFT, GW_DIR_DOWN, GW_DIR_UP};
+  static const int turn_left[4] = {GW_DIR_DOWN, GW_DIR_UP, GW_DIR_LEFT, GW_DIR_RIGHT};     /* by current LEFT, RIGHT, UP, DOWN */
+  static const int turn_right[4] = {GW_DIR_UP, GW_DIR_DOWN, GW_DIR_RIGHT, GW_DIR_LEFT};
+  if (action == GW_ACT_UP) return dir;
+  if (action == GW_ACT_DOWN) return opposite[dir];
+  if (action == GW_ACT_LEFT) return turn_left[dir];
+  return turn_right[dir];
+}
+
+/* direction mode 2 (safety_game_ma.py:607-640, :672-706, :734-764): only the TURN_* actions change a direction */
+static int turned(int action, int dir) {
+  static const int opposite[4] = {GW_DIR_RIGHT, GW_DIR_LEFT, GW_DIR_DOWN, GW_DIR_UP};
+  if (action == GW_ACT_TURN_LEFT_90) return relative_to_absolute(GW_ACT_LEFT, dir);
+  if (action == GW_ACT_TURN_RIGHT_90) return relative_to_absolute(GW_ACT_RIGHT, dir);
+  if (action == GW_ACT_TURN_LEFT_180 || action == GW_ACT_TURN_RIGHT_180) return opposite[dir];
+  return dir;
+}
+
 /* one Engine.play({agent: action}); has_action = 0 is the frame-0 pass of its_showtime */
 static void play(const FOracle* o, FEnv* e, int has_action, int agent, int action, double r[7], DrawSrc* d) {
   const double* R = o->cfg.rewards;
@@ -122,8 +145,19 @@ static void play(const FOracle* o, FEnv* e, int has_action, int agent, int actio
   e->frame += 1;
   if (has_action) {                                                           /* the acting agent's sprite */
     int dr = 0, dc = 0;
-    if (action == GW_ACT_LEFT) dc = -1; else if (action == GW_ACT_RIGHT) dc = 1;
-    else if (action == GW_ACT_UP) dr = -1; else if (action == GW_ACT_DOWN) dr = 1;
+    const int obs_mode = o->cfg.observation_direction_mode, act_mode = o->cfg.action_direction_mode;
+    /* AgentSprite.update (firemaker_ex_ma.py:468-476): the observation direction turns first (safety_game_ma.py:640-698), then
+     * AgentSafetySpriteMo.update maps the action through the action direction (:769-809) */
+    if (action != GW_ACT_NOOP && obs_mode == 1 && act_mode == 1) e->odir[agent] = relative_to_absolute(action, e->odir[agent]);
+    if (obs_mode == 2) e->odir[agent] = turned(action, e->odir[agent]);
+    if (act_mode == 2 && action >= GW_ACT_TURN_LEFT_90) e->adir[agent] = turned(action, e->adir[agent]);   /* a turn moves nothing */
+    else if (action >= GW_ACT_LEFT && action <= GW_ACT_DOWN) {
+      int dir;
+      if (act_mode >= 1) dir = relative_to_absolute(action, e->adir[agent]);
+      else dir = action == GW_ACT_LEFT ? GW_DIR_LEFT : action == GW_ACT_RIGHT ? GW_DIR_RIGHT : action == GW_ACT_UP ? GW_DIR_UP : GW_DIR_DOWN;
+      dr = dir == GW_DIR_UP ? -1 : dir == GW_DIR_DOWN ? 1 : 0; dc = dir == GW_DIR_LEFT ? -1 : dir == GW_DIR_RIGHT ? 1 : 0;
+      if (act_mode == 1) e->adir[agent] = dir;                                  /* map_action_to_action_direction (:724-766) */
+    }
     if (dr || dc) {
       const int nr = e->pos[agent] / S + dr, nc = e->pos[agent] % S + dc;
       if (nr >= 0 && nr < S && nc >= 0 && nc < S) {
@@ -166,7 +200,7 @@ static void play(const FOracle* o, FEnv* e, int has_action, int agent, int actio
 
 static void env_reset(const FOracle* o, FEnv* e) {
   memset(e, 0, sizeof *e);
-  for (int a = 0; a < NA; ++a) e->pos[a] = o->start[a];
+  for (int a = 0; a < NA; ++a) { e->pos[a] = o->start[a]; e->adir[a] = e->odir[a] = GW_DIR_UP; }
   e->frame = -1;
   render(o, e);
   double r[7] = {0};
@@ -199,14 +233,20 @@ static uint8_t layer_bit(const FOracle* o, const FEnv* e, int l, int p) {
   }
 }
 
-/* get_agent_perspective, observation_direction_mode 0 (safety_game_moma.py:1996-2101): crop around the
- * agent, what_lies_outside ('#') beyond the board; a layer pads with (layer chr == '#') */
+/* get_agent_perspective (safety_game_moma.py:1996-2101): crop around the agent, what_lies_outside ('#') beyond the board; a
+ * layer pads with (layer chr == '#'); then np.rot90 by the observation direction (DOWN k=2, LEFT k=-1, RIGHT k=1) unless the
+ * observation direction mode is 0 */
 static void crop(const FOracle* o, const FEnv* e, int agent, int radius, uint8_t* board_out, uint8_t* layers_out) {
   if (e->pos[agent] < 0) return;                     /* amount_agents = 2: no worker '2', its columns stay as they are (zero) */
   const int side = 2 * radius + 1, r0 = e->pos[agent] / S - radius, c0 = e->pos[agent] % S - radius;
+  const int dir = o->cfg.observation_direction_mode ? e->odir[agent] : GW_DIR_UP;
   for (int i = 0; i < side; ++i)
     for (int j = 0; j < side; ++j) {
-      const int r = r0 + i, c = c0 + j;
+      int si = i, sj = j;                                                      /* out[i][j] = in[si][sj] */
+      if (dir == GW_DIR_DOWN) { si = side - 1 - i; sj = side - 1 - j; }
+      else if (dir == GW_DIR_LEFT) { si = side - 1 - j; sj = i; }               /* rot90 k=-1 (clockwise) */
+      else if (dir == GW_DIR_RIGHT) { si = j; sj = side - 1 - i; }              /* rot90 k=1 (counterclockwise) */
+      const int r = r0 + si, c = c0 + sj;
       const int inside = r >= 0 && r < S && c >= 0 && c < S;
       if (board_out) board_out[i * side + j] = inside ? e->board[r * S + c] : (uint8_t)'#';
       if (layers_out)
@@ -342,6 +382,12 @@ void orf_step(void* h, const int32_t* actions, const int32_t* order, const doubl
   FStepCtx sc = {o, actions, order, draws, draw_stride,
                  {board, cube, crop_w, crop_s, lcrop_w, lcrop_s, reward_w, reward_s, terminated, step_type}};
   or_parallel_for(o->n, step_range, &sc);
+}
+
+void orf_directions(void* h, int8_t* directions) {          /* [N, 3, 2]: action direction, observation direction */
+  FOracle* o = (FOracle*)h;
+  for (int64_t i = 0; i < o->n; ++i)
+    for (int a = 0; a < NA; ++a) { directions[(i * NA + a) * 2] = (int8_t)o->envs[i].adir[a]; directions[(i * NA + a) * 2 + 1] = (int8_t)o->envs[i].odir[a]; }
 }
 
 void orf_observe(void* h, double* metrics, float* cumulative, int32_t* frame, int16_t* pos, int32_t* ext_fires) {

@@ -412,6 +412,9 @@ class FiremakerOracle(object):
         out = dict(metrics=np.zeros((n, 16), np.float64), cumulative=np.zeros((n, 7), np.float32), frame=np.zeros(n, np.int32),
                    pos=np.zeros((n, 3, 2), np.int16), ext_fires=np.zeros(n, np.int32))
         lib().orf_observe(self._h, _p(out["metrics"]), _p(out["cumulative"]), _p(out["frame"]), _p(out["pos"]), _p(out["ext_fires"]))
+        out["directions"] = np.zeros((n, 3, 2), np.int8)          # action direction, observation direction per agent
+        lib().orf_directions.argtypes = [C.c_void_p, C.c_void_p]
+        lib().orf_directions(self._h, _p(out["directions"]))
         return out
 
 

@@ -48,6 +48,13 @@ CASES = {
     # (firemaker_ex_ma.py:160,304-363); recorded with columns of agent '2' left at zero
     "firemaker_2agents_s5": dict(seed=5, steps=450, kwargs={}, lo=0, hi=4, amount_agents=2),
     "firemaker_2agents_maxiter40_s6": dict(seed=6, steps=90, kwargs={"max_iterations": 40}, lo=0, hi=4, amount_agents=2),
+    # direction modes (firemaker_ex_ma.py:224-226): 1 = actions and views relative to the last move, 2 = turned by the TURN_* actions
+    "firemaker_dir1_s7": dict(seed=7, steps=120, kwargs={"observation_direction_mode": 1, "action_direction_mode": 1}, lo=0, hi=4),
+    "firemaker_dir2_s8": dict(seed=8, steps=120, kwargs={"observation_direction_mode": 2, "action_direction_mode": 2}, lo=0, hi=8),
+    "firemaker_dir1_2agents_s9": dict(seed=9, steps=100, kwargs={"observation_direction_mode": 1, "action_direction_mode": 1, "max_iterations": 90},
+                                      lo=0, hi=4, amount_agents=2),
+    "firemaker_dir2_maxiter45_s10": dict(seed=10, steps=60, kwargs={"observation_direction_mode": 2, "action_direction_mode": 2, "max_iterations": 45},
+                                         lo=0, hi=8),
 }
 AGENTS = ["1", "2", "S"]
 
@@ -97,7 +104,7 @@ def _worker(name):
         rng._gw_hooked = True
 
     rec = {k: [] for k in ("board", "cube", "crop1", "crop2", "cropS", "lcrop1", "lcrop2", "lcropS", "reward1", "reward2", "rewardS",
-                           "cum1", "cum2", "cumS", "done", "step_type", "metrics", "pos", "frame", "countdown", "ext_fires")}
+                           "cum1", "cum2", "cumS", "done", "step_type", "metrics", "pos", "frame", "countdown", "ext_fires", "dirs")}
     meta = {}
     names = ["agent_1", "agent_2", "agent_S"]
 
@@ -135,6 +142,8 @@ def _worker(name):
         rec["metrics"].append(np.array([float(v) for v in i1["metrics_dict"].values()], dtype=np.float64))
         game = core._current_game
         rec["pos"].append(np.array([[game.things[a].position.row, game.things[a].position.col] if a in present else [-1, -1] for a in AGENTS], dtype=np.int16))
+        rec["dirs"].append(np.array([[int(game.things[a].action_direction), int(game.things[a].observation_direction)] if a in present else [2, 2]
+                                     for a in AGENTS], dtype=np.int8))    # Directions: LEFT 0, RIGHT 1, UP 2, DOWN 3
         rec["frame"].append(int(game.the_plot.frame))
         rec["countdown"].append(int(core.environment_data["stop_button_press_countdown"]))
         rec["ext_fires"].append(int(getattr(game.things["F"], "number_of_external_fires", 0)))

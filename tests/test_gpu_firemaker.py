@@ -78,9 +78,45 @@ def test_firemaker_matches_oracle_with_philox_draws(mode, agents, oracle_lib):
     orc.close()
 
 
+@pytest.mark.parametrize("dmode,agents,autoreset", [(1, 3, 1), (2, 3, 0), (1, 2, 0), (2, 2, 1)])
+def test_firemaker_direction_modes_match_oracle_with_philox_draws(dmode, agents, autoreset, oracle_lib):
+    """Direction modes 1 (relative to the last move) and 2 (TURN_* actions 5..8): gw_fm_kernel<true> against the oracle on 150
+    environments -- the three rotated views and their layers, the sprites' directions, everything else as in mode 0."""
+    from ai_safety_gridworlds_b200 import make_spec
+    from ai_safety_gridworlds_b200.firemaker_env import FiremakerVectorEnv
+    spec = make_spec("firemaker_ex_ma", autoreset_mode=autoreset, max_iterations=150, amount_agents=agents,
+                     observation_direction_mode=dmode, action_direction_mode=dmode)
+    assert spec.action_range == (0, 8 if dmode == 2 else 4)
+    N = 150
+    env = FiremakerVectorEnv(N, env_index_base=7, seed=11, autoreset_mode=autoreset, spec=spec)
+    orc = oracle_lib.FiremakerOracle(spec, N, env_index_base=7, seed=11)
+    orc.reset()
+    rng = np.random.default_rng(3)
+    turned = set()
+    for t in range(80):
+        a = rng.integers(0, spec.action_range[1] + 1, size=(N, 3)).astype(np.int32)
+        env.step(torch.from_numpy(a).to(env.device))
+        orc.step(a)
+        ctx = "dmode=%d agents=%d t=%d" % (dmode, agents, t)
+        for name, got, want in (("board", env.board, orc.board), ("cube", env.cube, orc.cube), ("crop_w", env.crop_workers, orc.crop_w),
+                                ("crop_s", env.crop_supervisor, orc.crop_s), ("lcrop_w", env.lcrop_workers, orc.lcrop_w),
+                                ("lcrop_s", env.lcrop_supervisor, orc.lcrop_s), ("reward_w", env.reward_workers, orc.reward_w),
+                                ("reward_s", env.reward_supervisor, orc.reward_s), ("step_type", env.step_type, orc.step_type),
+                                ("terminated", env.terminated, orc.terminated)):
+            np.testing.assert_array_equal(_np(got), want, err_msg=ctx + " " + name)
+        ex, ox = env.observe(), orc.observe()
+        for key in ("metrics", "cumulative", "frame", "pos", "ext_fires", "directions"):
+            np.testing.assert_array_equal(_np(ex[key]), ox[key], err_msg=ctx + " " + key)
+        turned |= set(np.unique(ox["directions"][:, 2, 1]).tolist())
+    assert turned == {0, 1, 2, 3}                     # the supervisor's 33 x 33 view was emitted in all four rotations
+    env.close()
+    orc.close()
+
+
 def test_firemaker_rejects_unsupported_configurations():
     from ai_safety_gridworlds_b200 import make_spec
-    for kw in ({"amount_agents": 4}, {"amount_agents": 1}, {"observation_direction_mode": 1}, {"agent_observation_radius": [1, 1, 1, 1]},
+    for kw in ({"amount_agents": 4}, {"amount_agents": 1}, {"observation_direction_mode": 1}, {"observation_direction_mode": 3, "action_direction_mode": 3},
+               {"agent_observation_radius": [1, 1, 1, 1]},
                {"FIRE_SPREAD_EXCLUSIVE_MAX_DISTANCE": 4.0}, {"AGENT_MOVEMENT_REWARD": "{'OTHER': -1}"}):
         with pytest.raises(NotImplementedError):
             make_spec("firemaker_ex_ma", **kw)

@@ -42,6 +42,8 @@ def check_against_trace(view, ox, d, meta, t, ctx):
     np.testing.assert_array_equal(view["reward_s"], d["rewardS"][t], err_msg=ctx)
     assert ox["frame"] == d["frame"][t], ctx
     np.testing.assert_array_equal(ox["pos"], d["pos"][t], err_msg=ctx)
+    if "dirs" in d and "directions" in ox:                               # traces of the direction modes carry the sprites' directions
+        np.testing.assert_array_equal(ox["directions"], d["dirs"][t], err_msg=ctx)
     assert ox["ext_fires"] == d["ext_fires"][t], ctx
     from ai_safety_gridworlds_b200.envs.firemaker_ex_ma import METRIC_NAMES
     cols = [METRIC_NAMES.index(m) for m in meta["metric_names"]]         # amount_agents = 2: no columns of worker '2'
