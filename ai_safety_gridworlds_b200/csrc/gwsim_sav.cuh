@@ -563,7 +563,8 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, SUST ? 4 : SAV_MINB) gw_sav_ke
     const int cpitch = (cells + 15) & ~15, vpitch = (V2 + 15) & ~15;
     uint16_t* cmask = s_cmask[warp];
     uint8_t* bchr = s_bchr[warp];
-    constexpr bool has_pred = PRED;
+    const bool has_pred = PRED && s.pred[0] != 255;    /* the predator slots fill from 0: none there = none at all (the sustainability
+                                                          instantiation is compiled with PRED and mostly runs without predators) */
     const uint32_t abit0 = c.agent_layer[0] >= 0 ? 1u << c.agent_layer[0] : 0u, abit1 = c.agent_layer[1] >= 0 ? 1u << c.agent_layer[1] : 0u;
     const uint32_t pbit = c.pred_layer >= 0 ? 1u << c.pred_layer : 0u, wbit = 1u << c.wall_layer;
     for (int p = (int)lane; p < cpitch; p += 32) {

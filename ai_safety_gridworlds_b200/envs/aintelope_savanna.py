@@ -189,8 +189,6 @@ def compile_spec(autoreset_mode: int = _abi.GW_AUTORESET_NEXT_STEP, **kwargs) ->
         raise NotImplementedError("the CUDA backend is built for symmetric observation radii 0..10")
     if flags["map_randomization_frequency"] not in (0, 1, 2, 3):
         raise ValueError("map_randomization_frequency")
-    if flags["remove_unused_tile_types_from_layers"]:
-        raise NotImplementedError("remove_unused_tile_types_from_layers is not built")
     level_art = LEVELS[level]
     counts = {ch: int(flags[f]) for ch, f in TILES}
     if flags["map_randomization_frequency"] == 0:
@@ -275,6 +273,10 @@ def compile_spec(autoreset_mode: int = _abi.GW_AUTORESET_NEXT_STEP, **kwargs) ->
         DRINK_OVERSATIATION=above("DRINK", drink_on, on_map["D"] or on_map["d"]), FOOD_OVERSATIATION=above("FOOD", food_on, on_map["F"] or on_map["f"]))
 
     layer_order = sorted({GAP_CHR, WALL_CHR} | set(DRAPE_CHARS) | set(AGENTS) | ({"U"} if on_map["U"] else set()))
+    if flags["remove_unused_tile_types_from_layers"]:
+        # safety_game_mo_base.py:1076-1085,1123-1129: sprites and drapes whose character is not on the (count-adjusted) map are
+        # dropped from the game, so the observation's layers are the characters of the board (+ what_lies_beneath)
+        layer_order = sorted(set(flat) | {GAP_CHR})
     value_mapping = {"#": 0.0, " ": 1.0, "W": 2.0, "P": 3.0, "U": 4.0, "D": 5.0, "F": 6.0, "d": 6.0, "f": 7.0, "G": 8.0, "S": 9.0}   # :1546-1558
     value_mapping.update({AGENTS[k]: float(len(value_mapping) + k) for k in range(n_agents)})                                    # :1560-1562
     if len(layer_order) > _abi.GW_SAV_MAX_LAYERS or 2 * len(keys) > _abi.GW_MA_STATS_LEN - 4:

@@ -459,6 +459,14 @@ def run_ours(args):
     launches0 = env.launch_count
     barrier()
     t_wall0 = time.perf_counter()
+
+    def host_gate():
+        # ~2 ms of spinning on the stream AHEAD of the timed region: the host enqueues the region's launches while the GPU is
+        # still busy, so a descheduled host thread (8 ranks wake up together after the barrier) cannot leave the GPU idle
+        # between ev0 and ev1; with K = 20 steps of 0.11 ms one such hiccup on one rank was 8 % of the max-over-ranks time
+        if hasattr(torch.cuda, "_sleep"):
+            torch.cuda._sleep(4000000)
+    host_gate()
     if world > 1:
         # on-device alignment: the stream of every rank passes this tiny all-reduce at the same moment, so ev0 is taken at
         # (nearly) the same time on all GPUs and the host-side launch skew of the ranks is not in the timed region
@@ -485,6 +493,7 @@ def run_ours(args):
         env.clear_stats()
         launches0 = env.launch_count
         barrier()
+        host_gate()
         ev0.record(stream)
         for t in range(args.steps // G):
             graph.replay()

@@ -77,6 +77,13 @@ CASES = {
                                                                                   amount_predators=3, amount_drink_holes=1, max_iterations=60,
                                                                                   observation_radius=[4, 4, 4, 4], **HOMEOSTASIS)),
     "savanna_randmap_once_s13": dict(seed=13, steps=200, kwargs=dict(map_randomization_frequency=1, max_iterations=40)),
+    # remove_unused_tile_types_from_layers (safety_game_mo_base.py:1076-1085,1123-1129): tile types that are not on the map lose their
+    # sprites / drapes, so the layers of the observation are the characters of the board only
+    "savanna_remove_unused_s24": dict(seed=24, steps=200, kwargs=dict(remove_unused_tile_types_from_layers=True, max_iterations=50,
+                                                                     amount_water_tiles=2)),
+    "savanna_remove_unused_two_agents_s25": dict(seed=25, steps=200, kwargs=dict(remove_unused_tile_types_from_layers=True, amount_agents=2,
+                                                                                amount_predators=2, amount_drink_holes=1, max_iterations=50,
+                                                                                **HOMEOSTASIS)),
 }
 # the experiment overlays (experiments/aintelope/*.py) without the sustainability challenge, through the reference's factory names
 for _k, _name in enumerate(["danger_tiles", "food_drink_homeostasis", "food_drink_homeostasis_danger_gold_silver", "food_drink_homeostasis_gold",
@@ -191,7 +198,8 @@ def _worker(name):
         rec["adir"].append(np.array([int(game.things[a].action_direction) for a in agents], dtype=np.int8))
         rec["odir"].append(np.array([int(game.things[a].observation_direction) for a in agents], dtype=np.int8))
         rec["frame"].append(int(game.the_plot.frame))
-        rec["pred"].append(np.array(game.things["P"].curtain, dtype=np.uint8))
+        rec["pred"].append(np.array(game.things["P"].curtain, dtype=np.uint8) if "P" in game.things
+                           else np.zeros(np.array(infos[names[0]]["ascii_codes"]).shape, np.uint8))   # drape removed from the game
         rec["maps"].append(np.array([[ord(ch) for ch in row] for row in core.environment_data["ascii_art"]], dtype=np.uint8))
 
     obs, infos = env.reset(seed=case["seed"])

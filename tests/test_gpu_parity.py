@@ -62,7 +62,12 @@ def test_cuda_replays_reference_trace(name, monkeypatch):
         for col, vec in ((0, d["reward"][t]), (1, d["cumulative"][t])):
             if np.ptp(vec) <= 1e-9 * max(1.0, np.abs(vec).max()):
                 got_s[col] = want_s[col] = 0.0
-        np.testing.assert_allclose(got_s, want_s, rtol=2e-5, atol=1e-4, err_msg=ctx)
+        # columns 1, 3, 4 (cumulative Gini, variances of the cumulative and the average reward) come from the state's exact
+        # event accumulators in fp64: BASELINE.json's 1e-6.  Columns 0 and 2 (Gini / variance of THIS step's reward) are
+        # recomputed from the emitted float32 reward row, whose rounding (6e-8 relative per entry) a difference-over-mean
+        # statistic amplifies: 2e-5.
+        np.testing.assert_allclose(got_s[[1, 3, 4]], want_s[[1, 3, 4]], rtol=1e-6, atol=1e-6, err_msg=ctx)
+        np.testing.assert_allclose(got_s[[0, 2]], want_s[[0, 2]], rtol=2e-5, atol=1e-4, err_msg=ctx)
         if meta["metric_names"]:
             got, want = _np(ex["metrics"][0]), d["metrics"][t]
             for j, is_int in enumerate(integer_metric):
