@@ -2282,7 +2282,8 @@ struct GwImaEngine {
   unsigned long long* d_stats;        /* [GW_STAT_REPLICAS][GW_MA_STATS_LEN] raw rollout statistics */
   int grid;
   uint32_t cube_off, board_off, crop_off, lcrop_off, reward_off, warp_bytes;
-  uint32_t map_off, warp_bytes_pm;     /* per-environment-map variant: + 32 maps of staging per warp */
+  uint32_t map_off, warp_bytes_pm;     /* per-environment-map variant: its own layout (bit strings for the layer tensors) + 32 maps per warp */
+  uint32_t pm_cube_off, pm_board_off, pm_crop_off, pm_lcrop_off, pm_reward_off;
   uint8_t* maps;                        /* caller-owned [N, cells] tensor or NULL */
   int32_t map_mode;                     /* GwImaMapMode */
   int grid_pm;
@@ -2366,10 +2367,17 @@ int gw_ima_create(const GwConfig* cfg, int64_t n_envs, int device, int64_t env_i
   h->crop_off = h->board_off + 32u * (uint32_t)cells;
   h->reward_off = h->crop_off + 32u * 2u * IMA_VIEW;
   h->warp_bytes = (h->reward_off + 2u * 128u * 2u * (uint32_t)cfg->n_rewards + 127u) & ~127u;
-  h->map_off = h->warp_bytes;
-  h->warp_bytes_pm = (h->map_off + 32u * (uint32_t)cells + 127u) & ~127u;
+  /* per-environment maps: the byte tensors that leave through the TMA engine first, then the chunk's maps, then the 0 / 1 layer
+   * tensors as bit strings (32 * Sc and 32 * Sl BITS = Sc and Sl words, + one word of read-ahead each) */
+  h->pm_board_off = 0;
+  h->pm_crop_off = h->pm_board_off + 32u * (uint32_t)cells;
+  h->pm_reward_off = (h->pm_crop_off + 32u * 2u * IMA_VIEW + 15u) & ~15u;
+  h->map_off = (h->pm_reward_off + 2u * 128u * 2u * (uint32_t)cfg->n_rewards + 15u) & ~15u;
+  h->pm_cube_off = (h->map_off + 32u * (uint32_t)cells + 15u) & ~15u;
+  h->pm_lcrop_off = (h->pm_cube_off + 4u * (Sc + 1u) + 15u) & ~15u;
+  h->warp_bytes_pm = (h->pm_lcrop_off + 4u * (Sl + 1u) + 127u) & ~127u;
   h->maps = nullptr; h->map_mode = GW_IMA_MAPS_STATIC;
-  const size_t smem = (size_t)h->warp_bytes * IMA_WARPS, smem_pm = (size_t)h->warp_bytes_pm * IMA_WARPS;
+  const size_t smem = (size_t)h->warp_bytes * IMA_WARPS, smem_pm = (size_t)h->warp_bytes_pm * IMA_WARPS_PM;
   h->d_claim = nullptr; h->d_stats = nullptr;
   ce = cudaFuncSetAttribute(gw_ima_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (ce == cudaSuccess) ce = cudaFuncSetAttribute(gw_ima_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pm);
@@ -2379,7 +2387,7 @@ int gw_ima_create(const GwConfig* cfg, int64_t n_envs, int device, int64_t env_i
   int per_sm = 0, sms = 0;
   int per_sm_pm = 0;
   if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gw_ima_kernel<false>, IMA_WARPS * 32, smem);
-  if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_pm, gw_ima_kernel<true>, IMA_WARPS * 32, smem_pm);
+  if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_pm, gw_ima_kernel<true>, IMA_WARPS_PM * 32, smem_pm);
   if (ce == cudaSuccess) ce = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   if (ce != cudaSuccess || per_sm < 1 || per_sm_pm < 1) {
     cudaFree(h->d_claim); cudaFree(h->d_stats); delete h;
@@ -2422,15 +2430,20 @@ static int ima_launch(GwImaHandle h, ImaArgs& a, void* state, const GwImaObs* ob
   a.reward_off = h->reward_off; a.warp_bytes = h->warp_bytes;
   CUDA_TRY(cudaSetDevice(h->device));
   const int64_t nchunks = (h->n + 31) / 32;
-  int64_t grid = (nchunks + IMA_WARPS - 1) / IMA_WARPS;
   const bool pm = h->maps != nullptr;
+  const int warps = pm ? IMA_WARPS_PM : IMA_WARPS;
+  int64_t grid = (nchunks + warps - 1) / warps;
   if (grid > (pm ? h->grid_pm : h->grid)) grid = pm ? h->grid_pm : h->grid;
   a.maps = h->maps; a.map_off = (int32_t)h->map_off;
   a.map_shuffle = pm && (h->map_mode == GW_IMA_MAPS_SHUFFLE_EVERY_GAME || (h->map_mode == GW_IMA_MAPS_SHUFFLE_ON_RESET && a.is_reset)) ? 1 : 0;
-  if (pm) a.warp_bytes = h->warp_bytes_pm;
+  if (pm) {
+    a.warp_bytes = h->warp_bytes_pm;
+    a.cube_off = h->pm_cube_off; a.board_off = h->pm_board_off; a.crop_off = h->pm_crop_off; a.lcrop_off = h->pm_lcrop_off;
+    a.reward_off = h->pm_reward_off;
+  }
   a.claim_counter = h->d_claim;
   a.stats = h->d_stats;
-  if (pm) gw_ima_kernel<true><<<(unsigned)grid, IMA_WARPS * 32, (size_t)h->warp_bytes_pm * IMA_WARPS, stream>>>(h->dc, a);
+  if (pm) gw_ima_kernel<true><<<(unsigned)grid, IMA_WARPS_PM * 32, (size_t)h->warp_bytes_pm * IMA_WARPS_PM, stream>>>(h->dc, a);
   else gw_ima_kernel<false><<<(unsigned)grid, IMA_WARPS * 32, (size_t)h->warp_bytes * IMA_WARPS, stream>>>(h->dc, a);
   CUDA_TRY(cudaGetLastError());                                /* a refused launch claims nothing: the host base stays in step */
   h->launches += 1;

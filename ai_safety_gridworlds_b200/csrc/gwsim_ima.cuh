@@ -21,7 +21,13 @@
 
 #include "../../include/gwsim_ima.h"
 
-#define IMA_WARPS 3                      /* ~33 KB of staging per warp: 2 CTAs of 3 warps per SM */
+#define IMA_WARPS 3                      /* shared layouts: ~33 KB of byte staging per warp, 2 CTAs of 3 warps per SM (255 registers) */
+#define IMA_WARPS_PM 4                   /* per-environment maps: the 0 / 1 layer tensors are staged as bit strings (~12 KB per warp), 3 CTAs of
+                                            4 warps per SM at 168 registers.  Measured per 1,048,576-environment step: 6 warps 1.11 ms, 8 warps
+                                            0.86 ms, 12 warps (4 x 3 or 6 x 2) 0.80 ms, 16 warps at 128 registers 0.81 ms; the byte staging ran
+                                            at 0.93 ms.  The shared-layout kernel is the other way round: its patched templates need no per-cell
+                                            work, and the bit strings' atomics and expansion cost it 10 % even at twice the warps (0.47 ms
+                                            against 0.43 ms) */
 #define IMA_NW 12                        /* state words (16 B) per environment */
 #define IMA_VIEW (GW_IMA_CROP * GW_IMA_CROP)
 
@@ -384,6 +390,13 @@ __device__ __forceinline__ bool ima_step_lane(const ImaCfg& c, const ImaArgs& a,
 
 #define IMA_BMAP 352                     /* bordered map entries: (H + 4) * (W + 4) <= 352 for H * W <= 64 */
 
+/* Per-environment maps (PM): the 0 / 1 layer tensors (cube [32][L][cells], lcrop [32][2][L][25]) are staged as dense BIT STRINGS in
+ * shared memory -- one bit per output byte, environment e's bits at e * (bits per environment) -- and expanded to bytes when they are
+ * stored (fm_expand_bits: 8 bits -> 8 bytes through a 256-entry table, 32 bits -> two coalesced 16-byte stores): 1.7 + 1.8 KB per warp
+ * instead of 13.8 + 14.4 KB of byte staging.  Neighbouring environments share words at their boundaries (432 or 450 bits each), so
+ * the bits are set with shared-memory atomics. */
+__device__ __forceinline__ void ima_bit_set(uint32_t* __restrict__ bits, uint32_t pos) { atomicOr(&bits[pos >> 5], 1u << (pos & 31u)); }
+
 /* The agents' views of one environment into crop[2][25] / lcrop[2][L][25] (lcrop pre-zeroed).
  * get_agent_perspective (safety_game_moma.py:1996-2101): 5x5 crop around the agent, what_lies_outside ('W') beyond the
  * board, np.rot90 by the observation direction (DOWN k=2, LEFT k=-1, RIGHT k=1).  The map is held with a 2-cell border
@@ -430,13 +443,14 @@ __device__ __forceinline__ void ima_views(const ImaCfg& c, const uint16_t* __res
  * s_vdij[dir][v] = (si - 2) & 0xff | (sj - 2) << 8 is the source offset of view cell v, s_lchar[chr] the layer of a character. */
 __device__ __forceinline__ void ima_views_own(const ImaCfg& c, const uint8_t* __restrict__ art, const int16_t* __restrict__ s_vdij,
                                               const int8_t* __restrict__ s_lchar, int pos0, int pos1, int odir0, int odir1,
-                                              uint8_t* __restrict__ crop, uint8_t* __restrict__ lcrop) {
+                                              uint8_t* __restrict__ crop, uint32_t* __restrict__ lbits, uint32_t lbase) {
   const int L = c.n_layers;
 #pragma unroll 1
   for (int ag = 0; ag < 2; ++ag) {
     const int pos = ag ? pos1 : pos0, pr = pos / c.width, pc = pos % c.width;
     const int16_t* __restrict__ dij = s_vdij + (c.obs_mode ? (ag ? odir1 : odir0) : GW_DIR_UP) * IMA_VIEW;
-    uint8_t* __restrict__ lc = lcrop ? lcrop + ag * L * IMA_VIEW : nullptr;
+    const bool lc = lbits != nullptr;
+    const uint32_t lb = lbase + (uint32_t)(ag * L * IMA_VIEW);     /* bit (lb + l * 25 + v) <-> lcrop[ag][l][v] of this lane's environment */
 #pragma unroll 5
     for (int v = 0; v < IMA_VIEW; ++v) {
       const int e = dij[v], r = pr + (int)(int8_t)(e & 0xff), cc = pc + (int)(int8_t)(e >> 8);
@@ -452,8 +466,8 @@ __device__ __forceinline__ void ima_views_own(const ImaCfg& c, const uint8_t* __
       }
       if (crop) crop[ag * IMA_VIEW + v] = (uint8_t)ch;
       if (lc) {
-        if (l0 >= 0) lc[l0 * IMA_VIEW + v] = 1;
-        if (l1 >= 0) lc[l1 * IMA_VIEW + v] = 1;
+        if (l0 >= 0) ima_bit_set(lbits, lb + (uint32_t)(l0 * IMA_VIEW + v));
+        if (l1 >= 0) ima_bit_set(lbits, lb + (uint32_t)(l1 * IMA_VIEW + v));
       }
     }
   }
@@ -462,7 +476,7 @@ __device__ __forceinline__ void ima_views_own(const ImaCfg& c, const uint8_t* __
 /* PM = per-environment maps (map randomisation): the art is read from (and, after a shuffle, written back to) a.maps, and board
  * and cube are rendered from it for every chunk instead of being a patched template. */
 template <bool PM>
-__global__ void __launch_bounds__(IMA_WARPS * 32, 2) gw_ima_kernel(const __grid_constant__ ImaCfg c, const ImaArgs a) {
+__global__ void __launch_bounds__((PM ? IMA_WARPS_PM : IMA_WARPS) * 32, PM ? 3 : 2) gw_ima_kernel(const __grid_constant__ ImaCfg c, const ImaArgs a) {
   extern __shared__ __align__(128) uint8_t ima_stage[];
   __shared__ __align__(16) uint8_t s_art[GW_MAX_CELLS];
   __shared__ uint8_t s_base[GW_MAX_CELLS], s_icell[GW_MAX_CELLS];
@@ -472,6 +486,11 @@ __global__ void __launch_bounds__(IMA_WARPS * 32, 2) gw_ima_kernel(const __grid_
   __shared__ int16_t s_vdij[4 * IMA_VIEW];
   __shared__ uint8_t s_vinv[4 * IMA_VIEW];
   __shared__ int8_t s_lchar[128];
+  __shared__ __align__(8) uint2 s_lut[PM ? 256 : 1];      /* PM: byte b -> its eight bits as 0 / 1 bytes (fm_expand_bits) */
+  if constexpr (PM) {
+    for (uint32_t b = threadIdx.x; b < 256; b += blockDim.x)
+      s_lut[b] = make_uint2(((b & 15u) * 0x00204081u) & 0x01010101u, ((b >> 4) * 0x00204081u) & 0x01010101u);
+  }
   for (uint32_t i = threadIdx.x; i < GW_MAX_CELLS; i += blockDim.x) {
     s_art[i] = c.art[i]; s_base[i] = c.base_board[i]; s_blayer[i] = c.base_layer[i];
     const int iw = c.width > 2 ? c.width - 2 : 1;
@@ -513,9 +532,13 @@ __global__ void __launch_bounds__(IMA_WARPS * 32, 2) gw_ima_kernel(const __grid_
   uint8_t* s_board = wbuf + a.board_off;
   uint8_t* s_crop = wbuf + a.crop_off;
   uint8_t* s_lcrop = wbuf + a.lcrop_off;
+  uint32_t* s_cbits = reinterpret_cast<uint32_t*>(s_cube);      /* PM: the chunk's cube as 32 * Sc bits (+ one word of read-ahead) */
+  uint32_t* s_lbits = reinterpret_cast<uint32_t*>(s_lcrop);     /* PM: the chunk's layer views as 32 * Sl bits (+ one word) */
   uint8_t* s_map = wbuf + a.map_off;             /* PM: the chunk's 32 maps, [32][cells] as in a.maps */
   uint32_t parity = 0;                           /* reward rows are double-buffered: the previous chunk's may still be in flight */
-  if constexpr (!PM) {
+  if constexpr (PM) {
+    if (lane == 0) { s_cbits[Sc] = 0u; s_lbits[Sl] = 0u; }      /* the read-ahead words of the expansion */
+  } else {
     /* agent-free templates of this lane's staged environment */
     for (uint32_t p = 0; p < cells; ++p) {
       s_board[lane * cells + p] = s_base[p];
@@ -598,20 +621,21 @@ __global__ void __launch_bounds__(IMA_WARPS * 32, 2) gw_ima_kernel(const __grid_
       }
       /* render board and cube of this lane's environment from its own map */
       if (a.cube) {
-        uint4* z = reinterpret_cast<uint4*>(s_cube);
-        for (uint32_t q = lane; q < (32u * Sc) >> 4; q += 32) z[q] = make_uint4(0u, 0u, 0u, 0u);
+        for (uint32_t w = lane; w < Sc; w += 32) s_cbits[w] = 0u;
         __syncwarp();
       }
       if (lane < nvalid) {
         const uint8_t* art = M.art;
+        const uint32_t cb = lane * Sc;
+        const bool wc = a.cube != nullptr;
         for (uint32_t p = 0; p < cells; ++p) {
           uint32_t ch = art[p];
           if (ch == '1' || ch == '2') ch = ' ';
           int l = s_lchar[ch & 127u];
-          if ((int32_t)p == p0) { ch = '1'; if (l == c.layer_gap) l = -1; if (c.layer_a0 >= 0) s_cube[lane * Sc + c.layer_a0 * cells + p] = 1; }
-          if ((int32_t)p == p1) { ch = '2'; if (l == c.layer_gap) l = -1; if (c.layer_a1 >= 0) s_cube[lane * Sc + c.layer_a1 * cells + p] = 1; }
+          if ((int32_t)p == p0) { ch = '1'; if (l == c.layer_gap) l = -1; if (c.layer_a0 >= 0 && wc) ima_bit_set(s_cbits, cb + (uint32_t)c.layer_a0 * cells + p); }
+          if ((int32_t)p == p1) { ch = '2'; if (l == c.layer_gap) l = -1; if (c.layer_a1 >= 0 && wc) ima_bit_set(s_cbits, cb + (uint32_t)c.layer_a1 * cells + p); }
           s_board[lane * cells + p] = (uint8_t)ch;
-          if (l >= 0) s_cube[lane * Sc + l * cells + p] = 1;
+          if (l >= 0 && wc) ima_bit_set(s_cbits, cb + (uint32_t)l * cells + p);
         }
       }
     } else
@@ -634,15 +658,19 @@ __global__ void __launch_bounds__(IMA_WARPS * 32, 2) gw_ima_kernel(const __grid_
       staged0 = p0; staged1 = p1;
     }
     if (a.lcrop) {
-      uint4* z = reinterpret_cast<uint4*>(s_lcrop);
-      for (uint32_t q = lane; q < (32u * Sl) >> 4; q += 32) z[q] = make_uint4(0u, 0u, 0u, 0u);
+      if constexpr (PM) {
+        for (uint32_t w = lane; w < Sl; w += 32) s_lbits[w] = 0u;
+      } else {
+        uint4* z = reinterpret_cast<uint4*>(s_lcrop);
+        for (uint32_t q = lane; q < (32u * Sl) >> 4; q += 32) z[q] = make_uint4(0u, 0u, 0u, 0u);
+      }
       __syncwarp();
     }
     if (a.crop || a.lcrop) {
       if constexpr (PM) {
         if (lane < nvalid)
           ima_views_own(c, M.art, s_vdij, s_lchar, p0, p1, s.ag[0].odir, s.ag[1].odir, a.crop ? s_crop + lane * Sv : nullptr,
-                        a.lcrop ? s_lcrop + lane * Sl : nullptr);
+                        a.lcrop ? s_lbits : nullptr, lane * Sl);
       } else {
         ima_views(c, s_bmap, s_voff, s_vinv, p0, p1, s.ag[0].odir, s.ag[1].odir, a.crop ? s_crop + lane * Sv : nullptr,
                   a.lcrop ? s_lcrop + lane * Sl : nullptr);
@@ -653,21 +681,34 @@ __global__ void __launch_bounds__(IMA_WARPS * 32, 2) gw_ima_kernel(const __grid_
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   /* generic-proxy writes -> visible to the TMA */
       __syncwarp();
       if (lane == 0) {
-        if (a.cube) bulk_store(a.cube + env0 * (int64_t)Sc, s_cube, 32u * Sc);
-        if (a.lcrop) bulk_store(a.lcrop + env0 * (int64_t)Sl, s_lcrop, 32u * Sl);
+        if constexpr (!PM) {
+          if (a.cube) bulk_store(a.cube + env0 * (int64_t)Sc, s_cube, 32u * Sc);
+          if (a.lcrop) bulk_store(a.lcrop + env0 * (int64_t)Sl, s_lcrop, 32u * Sl);
+        }
         if (a.board) bulk_store(a.board + env0 * (int64_t)cells, s_board, 32u * cells);
         if (a.crop) bulk_store(a.crop + env0 * (int64_t)Sv, s_crop, 32u * Sv);
         if (a.reward) bulk_store(a.reward + env0 * (int64_t)R2, s_rw, 128u * R2);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      if constexpr (PM) {
+        /* the bit strings leave through the table: 32 bits -> 32 bytes per lane and iteration, coalesced 16-byte stores */
+        if (a.cube) fm_expand_bits(a.cube + env0 * (int64_t)Sc, s_cbits, (int)(32u * Sc), s_lut, lane);
+        if (a.lcrop) fm_expand_bits(a.lcrop + env0 * (int64_t)Sl, s_lbits, (int)(32u * Sl), s_lut, lane);
+        __syncwarp();                                /* the next chunk clears the strings */
       }
     } else {
       /* ragged last chunk / masked reset: plain stores, each lane its own environment */
       __syncwarp();
       if (lane < nvalid) {
         if (a.board) for (uint32_t i = 0; i < cells; ++i) a.board[env * cells + i] = s_board[lane * cells + i];
-        if (a.cube) for (uint32_t i = 0; i < Sc; ++i) a.cube[env * (int64_t)Sc + i] = s_cube[lane * Sc + i];
+        if constexpr (PM) {
+          if (a.cube) for (uint32_t i = 0; i < Sc; ++i) { const uint32_t b = lane * Sc + i; a.cube[env * (int64_t)Sc + i] = (uint8_t)((s_cbits[b >> 5] >> (b & 31u)) & 1u); }
+          if (a.lcrop) for (uint32_t i = 0; i < Sl; ++i) { const uint32_t b = lane * Sl + i; a.lcrop[env * (int64_t)Sl + i] = (uint8_t)((s_lbits[b >> 5] >> (b & 31u)) & 1u); }
+        } else {
+          if (a.cube) for (uint32_t i = 0; i < Sc; ++i) a.cube[env * (int64_t)Sc + i] = s_cube[lane * Sc + i];
+          if (a.lcrop) for (uint32_t i = 0; i < Sl; ++i) a.lcrop[env * (int64_t)Sl + i] = s_lcrop[lane * Sl + i];
+        }
         if (a.crop) for (uint32_t i = 0; i < Sv; ++i) a.crop[env * (int64_t)Sv + i] = s_crop[lane * Sv + i];
-        if (a.lcrop) for (uint32_t i = 0; i < Sl; ++i) a.lcrop[env * (int64_t)Sl + i] = s_lcrop[lane * Sl + i];
         if (a.reward && wrote) for (uint32_t i = 0; i < R2; ++i) a.reward[env * (int64_t)R2 + i] = s_rw[lane * R2 + i];
       }
       __syncwarp();
