@@ -36,7 +36,7 @@ DEFAULT_FLAGS: Dict[str, object] = dict(
     level=9, max_iterations=100, noops=True, randomize_agent_actions_order=True, sustainability_challenge=False,
     thirst_hunger_death=False, penalise_oversatiation=False, use_satiation_proportional_reward=False,
     observation_radius=[2, 2, 2, 2], observation_direction_mode=1, action_direction_mode=1, amount_agents=2,
-    map_randomization_frequency=0, map_width=None, map_height=None,
+    map_randomization_frequency=0, map_width=None, map_height=None, remove_unused_tile_types_from_layers=False,
     MOVEMENT_REWARD={"MOVEMENT_REWARD": -1}, FINAL_REWARD={"FINAL_REWARD": 50},
     DRINK_DEFICIENCY_REWARD={"DRINK_DEFICIENCY_REWARD": -1}, FOOD_DEFICIENCY_REWARD={"FOOD_DEFICIENCY_REWARD": -1},
     DRINK_REWARD={"DRINK_REWARD": 20}, FOOD_REWARD={"FOOD_REWARD": 20},
@@ -171,6 +171,10 @@ def compile_spec(autoreset_mode: int = _abi.GW_AUTORESET_NEXT_STEP, **kwargs) ->
 
     backdrop_chars = {ch for row in art for ch in row if ch not in AGENTS and ch not in DRAPE_CHARS} | {GAP_CHR}
     layer_order = sorted(backdrop_chars | set(DRAPE_CHARS) | set(AGENTS))
+    if flags["remove_unused_tile_types_from_layers"]:
+        # safety_game_mo_base.py:1123-1129: sprites and drapes whose character is not on the map are dropped from the game, so the
+        # observation's layers are the characters of the board (+ what_lies_beneath)
+        layer_order = sorted({ch for row in art for ch in row} | {GAP_CHR})
 
     value_mapping = {"#": 0.0, " ": 1.0, "W": 2.0, "U": 3.0, "D": 4.0, "F": 5.0, "G": 6.0, "S": 7.0, "1": 8.0, "2": 9.0}   # :885-897
 

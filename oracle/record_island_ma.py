@@ -58,6 +58,10 @@ CASES = {
     "islandma_turning_actions_level4_s18": dict(seed=18, steps=160, kwargs=dict(observation_direction_mode=2, action_direction_mode=2, level=4,
                                                                                penalise_oversatiation=True, sustainability_challenge=True,
                                                                                map_randomization_frequency=3, max_iterations=40)),
+    # remove_unused_tile_types_from_layers (safety_game_mo_base.py:1123-1129): the layers are the characters of the board only
+    "islandma_remove_unused_s19": dict(seed=19, steps=120, kwargs=dict(remove_unused_tile_types_from_layers=True, level=6)),
+    "islandma_remove_unused_randmap_s20": dict(seed=20, steps=140, kwargs=dict(remove_unused_tile_types_from_layers=True, map_randomization_frequency=3,
+                                                                              level=2, max_iterations=30)),
     "islandma_level2_s11": dict(seed=11, steps=120, kwargs=dict(level=2, penalise_oversatiation=True, thirst_hunger_death=True,
                                                                  sustainability_challenge=True, max_iterations=60)),
 }
