@@ -119,11 +119,21 @@ struct SavRun {                          /* lane 0's working copy */
 
 __device__ __forceinline__ int sav_res_slot(uint8_t ch) { return ch == 'D' ? 0 : ch == 'd' ? 1 : ch == 'F' ? 2 : ch == 'f' ? 3 : -1; }
 
-__device__ __forceinline__ void sav_add(const SavCfg& c, SavRun& w, int agent, int event, double scale) {
+/* SAV_COLD: the game logic runs in 8 of a warp's 32 lanes and is a small share of the time, but inlined at every call site it
+ * was most of the kernel's code (119 KB for the default instantiation, 255 KB with the sustainability challenge) */
+#ifndef SAV_BIG
+#define SAV_COLD __noinline__
+#define SAV_ROLL _Pragma("unroll 1")
+#else                                    /* the fully inlined build, for A/B runs */
+#define SAV_COLD __forceinline__
+#define SAV_ROLL
+#endif
+__device__ SAV_COLD void sav_add(const SavCfg& c, SavRun& w, int agent, int event, double scale) {
+  SAV_ROLL
   for (int d = 0; d < c.n_rewards; ++d) w.r[agent][d] += c.table[event][d] * scale;
 }
 
-__device__ __forceinline__ void sav_consume(const SavCfg& c, SavState& s, SavRun& w, int a, uint8_t pos_chr, uint8_t big, uint8_t small,
+__device__ SAV_COLD void sav_consume(const SavCfg& c, SavState& s, SavRun& w, int a, uint8_t pos_chr, uint8_t big, uint8_t small,
                                             int visit_slot, int tile_big, int tile_small, double* satiation, int e_big, int e_small,
                                             int e_none, double rate_big, double rate_small, double limit, double* avail /*[2]*/) {
   if (pos_chr == big || pos_chr == small) {
@@ -167,11 +177,11 @@ __device__ __forceinline__ double sav_draw(const SavArgs& a, int64_t env, SavRun
  * frame began, a predator under an agent penalises it (the acting one only) and stays; at the end of a round (every live agent
  * has stepped equally often, safety_game_ma.py:1022-1041) the others move with PREDATOR_MOVEMENT_PROBABILITY one cell in a
  * drawn direction unless another predator or a wall is there */
-__device__ __forceinline__ void sav_predators(const SavCfg& c, const SavArgs& a, int64_t env, SavState& s, SavRun& w,
+__device__ SAV_COLD void sav_predators(const SavCfg& c, const SavArgs& a, int64_t env, SavState& s, SavRun& w,
                                               const uint8_t* __restrict__ art, int ag) {
   int mx = -1, mn = 1 << 30;
   bool last = true;
-  for (int k = 0; k < c.n_agents; ++k) {
+  SAV_ROLL for (int k = 0; k < c.n_agents; ++k) {
     if (w.term[k]) continue;
     mn = min(mn, (int)s.step_count[k]); mx = max(mx, (int)s.step_count[k]);
     if (mn != mx) last = false;
@@ -179,18 +189,18 @@ __device__ __forceinline__ void sav_predators(const SavCfg& c, const SavArgs& a,
   last = last && mx > 0;
   uint8_t from[GW_SAV_MAX_PREDATORS];
   int n = 0;
-  for (int k = 0; k < GW_SAV_MAX_PREDATORS; ++k) if (s.pred[k] != 255) from[n++] = s.pred[k];
-  for (int i = 1; i < n; ++i) {                                                   /* np.where(curtain): ascending cell order */
+  SAV_ROLL for (int k = 0; k < GW_SAV_MAX_PREDATORS; ++k) if (s.pred[k] != 255) from[n++] = s.pred[k];
+  SAV_ROLL for (int i = 1; i < n; ++i) {                                                   /* np.where(curtain): ascending cell order */
     const uint8_t v = from[i];
     int j = i - 1;
     while (j >= 0 && from[j] > v) { from[j + 1] = from[j]; --j; }
     from[j + 1] = v;
   }
-  for (int k = 0; k < GW_SAV_MAX_PREDATORS; ++k) s.pred[k] = k < n ? from[k] : (uint8_t)255;   /* slot k follows predator k of the snapshot */
-  for (int k = 0; k < n; ++k) {
+  SAV_ROLL for (int k = 0; k < GW_SAV_MAX_PREDATORS; ++k) s.pred[k] = k < n ? from[k] : (uint8_t)255;   /* slot k follows predator k of the snapshot */
+  SAV_ROLL for (int k = 0; k < n; ++k) {
     const int p = from[k];
     bool collision = false;
-    for (int b = 0; b < c.n_agents && !collision; ++b)
+    SAV_ROLL for (int b = 0; b < c.n_agents && !collision; ++b)
       if (w.pos[b] == p) { if (b == ag) sav_add(c, w, b, GW_SAV_E_PREDATOR, 1.0); collision = true; }
     if (collision || !last) continue;
     if (sav_draw(a, env, w, false) >= c.fparams[GW_SAV_F_PREDATOR_MOVEMENT_PROBABILITY]) continue;
@@ -218,7 +228,7 @@ __device__ __noinline__ void sav_resource_update(const SavCfg& c, const SavArgs&
   double av = w.av[slot];
   bool under_agent = false;
   const int usable = w.usable, visible = w.vis[slot];
-  for (int k = 0; k < c.n_agents; ++k) under_agent |= art[w.pos[k]] == chr;
+  SAV_ROLL for (int k = 0; k < c.n_agents; ++k) under_agent |= art[w.pos[k]] == chr;
   if (!under_agent) {
     /* the drink drapes test the module constant DRINK_GROWTH_LIMIT = 20 (:369,1251), the food drapes the flag (:1401); both raise
      * to FLAGS.DRINK_REGROWTH_EXPONENT (:1252,1402) */
@@ -242,7 +252,7 @@ __device__ __noinline__ void sav_resource_update(const SavCfg& c, const SavArgs&
   };
   auto pick = [&](int n, int k, uint8_t value) {
     if (k > n) k = n;
-    for (int t = 0; t < k; ++t) {
+    SAV_ROLL for (int t = 0; t < k; ++t) {
       const double v = sav_draw(a, env, w, false);
       if (a.draws) { put(list[(int)v], value); continue; }
       const int j = t + (int)(v * (double)(n - t));
@@ -252,13 +262,13 @@ __device__ __noinline__ void sav_resource_update(const SavCfg& c, const SavArgs&
   };
   int current = visible;
   if (want < current) {
-    for (int loop = 0; loop < 2; ++loop) {
+    SAV_ROLL for (int loop = 0; loop < 2; ++loop) {
       int n = 0;
-      for (int p = 0; p < c.cells; ++p)
+      SAV_ROLL for (int p = 0; p < c.cells; ++p)
         if (art[p] == chr && !(loop == 0 && (p == pos0 || p == pos1))) list[n++] = (uint8_t)p;
       const int k = min(current - want, n);
       if (k == 0) {       /* an empty pick indexes the curtain with (): `curtain[()] = False` clears the whole drape (:1289) */
-        for (int p = 0; p < c.cells; ++p) if (art[p] == chr) art[p] = ' ';
+        SAV_ROLL for (int p = 0; p < c.cells; ++p) if (art[p] == chr) art[p] = ' ';
         w.vis[slot] = 0;
       } else pick(n, k, (uint8_t)' ');
       if (current - k > want) current -= k; else break;
@@ -266,14 +276,14 @@ __device__ __noinline__ void sav_resource_update(const SavCfg& c, const SavArgs&
   }
   if (want > current) {   /* `current` may be stale after a removal, as in the reference */
     int n = 0;
-    for (int p = 0; p < c.cells; ++p)
+    SAV_ROLL for (int p = 0; p < c.cells; ++p)
       if (art[p] != chr && art[p] != '#' && art[p] != 'U' && p != pos0 && p != pos1) list[n++] = (uint8_t)p;
     if (n > 0) pick(n, want - current, chr);
   }
 }
 
 template <bool PRED, bool SUST>
-__device__ __forceinline__ void sav_play(const SavCfg& c, const SavArgs& args, int64_t env, SavState& s, SavRun& w,
+__device__ SAV_COLD void sav_play(const SavCfg& c, const SavArgs& args, int64_t env, SavState& s, SavRun& w,
                                          uint8_t* art, int a, int action) {
   const double* F = c.fparams;
   s.frame += 1;
@@ -341,7 +351,7 @@ __device__ __forceinline__ void sav_play(const SavCfg& c, const SavArgs& args, i
 }
 
 /* A fresh layout: the interior of cfg.art in Fisher-Yates order on the Philox stream (the oracle's shuffle_layout) */
-__device__ __forceinline__ void sav_shuffle(const SavCfg& c, const SavArgs& a, int64_t env, uint8_t* __restrict__ own) {
+__device__ SAV_COLD void sav_shuffle(const SavCfg& c, const SavArgs& a, int64_t env, uint8_t* __restrict__ own) {
   for (int p = 0; p < c.cells; ++p) own[p] = c.art[p];
   const int iw = c.width - 2, n = (c.height - 2) * iw;
   if (iw < 1 || n < 2) return;
@@ -360,40 +370,127 @@ __device__ __forceinline__ void sav_shuffle(const SavCfg& c, const SavArgs& a, i
 }
 
 template <bool SUST>
-__device__ __forceinline__ void sav_new_game(const SavCfg& c, const SavArgs& a, int64_t env, SavState& s, uint8_t* __restrict__ art,
+__device__ SAV_COLD void sav_new_game(const SavCfg& c, const SavArgs& a, int64_t env, SavState& s, uint8_t* __restrict__ art,
                                              bool explicit_reset, double* av, int* vis, int* usable) {
   if (a.map_shuffle == GW_IMA_MAPS_SHUFFLE_EVERY_GAME || (a.map_shuffle == GW_IMA_MAPS_SHUFFLE_ON_RESET && explicit_reset)) {
     sav_shuffle(c, a, env, art);
     uint8_t* own = a.maps + env * c.cells;
-    for (int p = 0; p < c.cells; ++p) own[p] = art[p];
+    SAV_ROLL for (int p = 0; p < c.cells; ++p) own[p] = art[p];
   } else if (SUST) {                                   /* the warp holds the finished game's tiles: start from the layout again */
     const uint8_t* own = a.maps + env * c.cells;
-    for (int p = 0; p < c.cells; ++p) art[p] = own[p];
+    SAV_ROLL for (int p = 0; p < c.cells; ++p) art[p] = own[p];
   }
   if (SUST) {                                          /* availability = self.curtain.sum() (:1220,1370) */
     vis[0] = vis[1] = vis[2] = vis[3] = 0; *usable = 0;
-    for (int p = 0; p < c.cells; ++p) {
+    SAV_ROLL for (int p = 0; p < c.cells; ++p) {
       const uint8_t ch = art[p];
       const int k = sav_res_slot(ch);
       if (k >= 0) vis[k] += 1;
       *usable += ch != '#' && ch != 'U';
     }
-    for (int k = 0; k < 4; ++k) av[k] = (double)vis[k];
+    SAV_ROLL for (int k = 0; k < 4; ++k) av[k] = (double)vis[k];
   }
   const bool drink_on = c.amount[GW_SAV_T_DRINK] > 0 || c.amount[GW_SAV_T_SMALL_DRINK] > 0;
   const bool food_on = c.amount[GW_SAV_T_FOOD] > 0 || c.amount[GW_SAV_T_SMALL_FOOD] > 0;
   memset(&s, 0, sizeof s);
   int np = 0;
-  for (int k = 0; k < GW_SAV_MAX_PREDATORS; ++k) s.pred[k] = 255;
-  for (int p = 0; p < c.cells; ++p) {
+  SAV_ROLL for (int k = 0; k < GW_SAV_MAX_PREDATORS; ++k) s.pred[k] = 255;
+  SAV_ROLL for (int p = 0; p < c.cells; ++p) {
     if (art[p] == '0') s.pos[0] = (uint8_t)p;
     if (art[p] == '1') s.pos[1] = (uint8_t)p;
     if (art[p] == 'P' && np < GW_SAV_MAX_PREDATORS) s.pred[np++] = (uint8_t)p;
   }
-  for (int k = 0; k < 2; ++k) {
+  SAV_ROLL for (int k = 0; k < 2; ++k) {
     s.dsat[k] = drink_on ? c.fparams[GW_SAV_F_DRINK_DEFICIENCY_INITIAL] : 0.0;
     s.fsat[k] = food_on ? c.fparams[GW_SAV_F_FOOD_DEFICIENCY_INITIAL] : 0.0;
     s.flags[k] = (uint8_t)(GW_DIR_UP | (GW_DIR_UP << 2) | ((k >= c.n_agents ? 3 : 0) << 5));
+  }
+}
+
+/* The whole game logic of one environment's parallel step, run by the lane that plays it (8 of a warp's 32 lanes): new game / the
+ * frames of the live agents in (shuffled) order / step types, cumulative rewards, rollout statistics, the reward rows.  Out of line:
+ * it is a small share of the time, and inlined into the render loop it made the kernel several times larger than the instruction
+ * cache (`no_instruction` stalls) and competed with the renderer for registers. */
+template <bool PRED, bool SUST>
+__device__ SAV_COLD void sav_lane_step(const SavCfg& c, const SavArgs& a, int64_t env, SavState& s, uint8_t* art, int32_t* flag,
+                                       uint32_t cnt_vis, uint32_t cnt_usable, unsigned long long* stats_row) {
+  const int R = c.n_rewards, A = c.n_agents;
+  SavRun w;
+  w.draw_k = 0;
+  if (SUST) {
+    SAV_ROLL for (int k = 0; k < 4; ++k) { w.av[k] = a.avail[env * 4 + k]; w.vis[k] = (int)((cnt_vis >> (8 * k)) & 255u); }
+    w.usable = (int)cnt_usable;
+  }
+  SAV_ROLL for (int k = 0; k < 2; ++k) {
+    SAV_ROLL for (int d = 0; d < SAV_MAXR; ++d) w.r[k][d] = 0.0;
+    w.pos[k] = s.pos[k]; w.adir[k] = s.flags[k] & 3; w.odir[k] = (s.flags[k] >> 2) & 3; w.term[k] = (s.flags[k] >> 4) & 1; w.st[k] = s.flags[k] >> 5;
+  }
+  bool wrote = true, fresh = false;
+  if (a.is_reset) {
+    wrote = !a.reset_mask || a.reset_mask[env] != 0;
+    if (wrote) { sav_new_game<SUST>(c, a, env, s, art, true, w.av, w.vis, &w.usable); fresh = true; }
+  } else if (w.st[0] >= 2 && w.st[1] >= 2) {                                  /* pycolab_interface_ma.py:206-213 */
+    sav_new_game<SUST>(c, a, env, s, art, false, w.av, w.vis, &w.usable); fresh = true;
+  } else {
+    int ord0 = 0, ord1 = A > 1 ? 1 : -1;
+    if (a.order) { ord0 = a.order[2 * env]; ord1 = a.order[2 * env + 1]; }
+    else {
+      const bool live0 = w.st[0] < 2, live1 = w.st[1] < 2;
+      if (live0 && live1) {
+        if (c.randomize) {
+          const uint64_t g = (uint64_t)(a.env_index_base + env), step = a.call_no * 65536ull + 65534ull;
+          const uint4 q = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)step, (uint32_t)(step >> 32)),
+                                        (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+          const double u = (double)((((unsigned long long)q.x << 32) | q.y) >> 11) * (1.0 / 9007199254740992.0);
+          if ((int)(u * 2.0) == 0) { ord0 = 1; ord1 = 0; }
+        }
+      } else { ord0 = live0 ? 0 : 1; ord1 = -1; }
+    }
+    bool over = false;
+    SAV_ROLL for (int k = 0; k < 2; ++k) {
+      const int ag = k == 0 ? ord0 : ord1;
+      if (ag < 0 || ag >= A || w.st[ag] >= 2) continue;
+      sav_play<PRED, SUST>(c, a, env, s, w, art, ag, a.actions[2 * env + ag]);
+      if ((int32_t)s.frame >= c.max_iterations) over = true;
+    }
+    SAV_ROLL for (int k = 0; k < 2; ++k) {
+      SAV_ROLL for (int d = 0; d < R; ++d) s.cum[k][d] += (float)w.r[k][d];
+      if (k >= A) w.st[k] = 3;
+      else if (over || w.term[k]) w.st[k] = (w.st[k] == 0 || w.st[k] == 1) ? 2 : 3;
+      else w.st[k] = 1;
+      s.pos[k] = (uint8_t)w.pos[k];
+      s.flags[k] = (uint8_t)(w.adir[k] | (w.odir[k] << 2) | (w.term[k] << 4) | (w.st[k] << 5));
+    }
+    if (a.stats) {
+      unsigned long long* row = stats_row;
+      atomicAdd(row + 0, 1ull);
+      int fin = 0;
+      SAV_ROLL for (int k = 0; k < A; ++k) fin += w.st[k] == 2;
+      if (fin) atomicAdd(row + 3, (unsigned long long)fin);
+      if (w.st[0] >= 2 && w.st[1] >= 2) {
+        atomicAdd(row + 1, 1ull);
+        atomicAdd(row + 2, (unsigned long long)s.frame);
+        SAV_ROLL for (int k = 0; k < A; ++k) {
+          SAV_ROLL for (int d = 0; d < R; ++d)
+            if (s.cum[k][d] != 0.0f)
+              atomicAdd(row + GW_MA_STATS_RETURN0 + k * R + d, (unsigned long long)__double2ll_rn((double)s.cum[k][d] * GW_MA_STATS_SCALE));
+        }
+      }
+    }
+  }
+  flag[0] = fresh ? (int32_t)(s.flags[0] >> 5) : w.st[0];
+  flag[1] = fresh ? (int32_t)(s.flags[1] >> 5) : w.st[1];
+  flag[2] = wrote ? 1 : 0;
+  /* the reward rows go straight to global memory from the playing lane (a staging buffer in shared memory cost a CTA per SM) */
+  if (wrote && a.reward) {
+    SAV_ROLL for (int k = 0; k < 2; ++k) {
+      SAV_ROLL for (int d = 0; d < R; ++d) a.reward[(env * 2 + k) * R + d] = fresh ? 0.0f : (float)w.r[k][d];
+    }
+  }
+  /* a game that ended inside this call restarts right away under GW_AUTORESET_SAME_STEP: the observation is the new game's */
+  if (!a.is_reset && !fresh && w.st[0] >= 2 && w.st[1] >= 2 && c.autoreset == GW_AUTORESET_SAME_STEP) sav_new_game<SUST>(c, a, env, s, art, false, w.av, w.vis, &w.usable);
+  if (SUST && wrote) {
+    SAV_ROLL for (int k = 0; k < 4; ++k) a.avail[env * 4 + k] = w.av[k];
   }
 }
 
@@ -421,7 +518,7 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, SUST ? 4 : SAV_MINB) gw_sav_ke
   }
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  const int cells = c.cells, L = c.n_layers, V = c.view, V2 = V * V, R = c.n_rewards, A = c.n_agents;
+  const int cells = c.cells, L = c.n_layers, V = c.view, V2 = V * V, A = c.n_agents;
   /* A warp takes SAV_EPW consecutive environments per pass: the game logic is a serial chain of dependent latencies, so SAV_EPW
    * lanes play that many games side by side (one instruction stream where their control flow agrees); the lanes then render
    * the games one after the other.  Measured at 131,072 environments: 1 per pass 0.64 ms, 4 per pass 0.45 ms, 8 per pass
@@ -464,80 +561,8 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, SUST ? 4 : SAV_MINB) gw_sav_ke
     /* 2. the game logic, one lane per environment of the pass */
     if ((lane & (32 / SAV_EPW - 1)) == 0 && (int)(lane / (32 / SAV_EPW)) < ne) {
       const int slot = (int)(lane / (32 / SAV_EPW));
-      const int64_t env = base + slot;
-      SavState& s = s_state[warp][slot];
-      uint8_t* art = s_art[warp] + slot * cells;
-      int32_t* flag = s_flag[warp][slot];
-      SavRun w;
-      w.draw_k = 0;
-      if (SUST) {
-        for (int k = 0; k < 4; ++k) { w.av[k] = a.avail[env * 4 + k]; w.vis[k] = (int)((cnt_vis >> (8 * k)) & 255u); }
-        w.usable = (int)cnt_usable;
-      }
-      for (int k = 0; k < 2; ++k) {
-        for (int d = 0; d < SAV_MAXR; ++d) w.r[k][d] = 0.0;
-        w.pos[k] = s.pos[k]; w.adir[k] = s.flags[k] & 3; w.odir[k] = (s.flags[k] >> 2) & 3; w.term[k] = (s.flags[k] >> 4) & 1; w.st[k] = s.flags[k] >> 5;
-      }
-      bool wrote = true, fresh = false;
-      if (a.is_reset) {
-        wrote = !a.reset_mask || a.reset_mask[env] != 0;
-        if (wrote) { sav_new_game<SUST>(c, a, env, s, art, true, w.av, w.vis, &w.usable); fresh = true; }
-      } else if (w.st[0] >= 2 && w.st[1] >= 2) {                                  /* pycolab_interface_ma.py:206-213 */
-        sav_new_game<SUST>(c, a, env, s, art, false, w.av, w.vis, &w.usable); fresh = true;
-      } else {
-        int ord0 = 0, ord1 = A > 1 ? 1 : -1;
-        if (a.order) { ord0 = a.order[2 * env]; ord1 = a.order[2 * env + 1]; }
-        else {
-          const bool live0 = w.st[0] < 2, live1 = w.st[1] < 2;
-          if (live0 && live1) {
-            if (c.randomize) {
-              const uint64_t g = (uint64_t)(a.env_index_base + env), step = a.call_no * 65536ull + 65534ull;
-              const uint4 q = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)step, (uint32_t)(step >> 32)),
-                                            (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
-              const double u = (double)((((unsigned long long)q.x << 32) | q.y) >> 11) * (1.0 / 9007199254740992.0);
-              if ((int)(u * 2.0) == 0) { ord0 = 1; ord1 = 0; }
-            }
-          } else { ord0 = live0 ? 0 : 1; ord1 = -1; }
-        }
-        bool over = false;
-        for (int k = 0; k < 2; ++k) {
-          const int ag = k == 0 ? ord0 : ord1;
-          if (ag < 0 || ag >= A || w.st[ag] >= 2) continue;
-          sav_play<PRED, SUST>(c, a, env, s, w, art, ag, a.actions[2 * env + ag]);
-          if ((int32_t)s.frame >= c.max_iterations) over = true;
-        }
-        for (int k = 0; k < 2; ++k) {
-          for (int d = 0; d < R; ++d) s.cum[k][d] += (float)w.r[k][d];
-          if (k >= A) w.st[k] = 3;
-          else if (over || w.term[k]) w.st[k] = (w.st[k] == 0 || w.st[k] == 1) ? 2 : 3;
-          else w.st[k] = 1;
-          s.pos[k] = (uint8_t)w.pos[k];
-          s.flags[k] = (uint8_t)(w.adir[k] | (w.odir[k] << 2) | (w.term[k] << 4) | (w.st[k] << 5));
-        }
-        if (a.stats) {
-          unsigned long long* row = a.stats + ((blockIdx.x * SAV_WARPS + warp) & (GW_STAT_REPLICAS - 1)) * GW_MA_STATS_LEN;
-          atomicAdd(row + 0, 1ull);
-          int fin = 0;
-          for (int k = 0; k < A; ++k) fin += w.st[k] == 2;
-          if (fin) atomicAdd(row + 3, (unsigned long long)fin);
-          if (w.st[0] >= 2 && w.st[1] >= 2) {
-            atomicAdd(row + 1, 1ull);
-            atomicAdd(row + 2, (unsigned long long)s.frame);
-            for (int k = 0; k < A; ++k)
-              for (int d = 0; d < R; ++d)
-                if (s.cum[k][d] != 0.0f)
-                  atomicAdd(row + GW_MA_STATS_RETURN0 + k * R + d, (unsigned long long)__double2ll_rn((double)s.cum[k][d] * GW_MA_STATS_SCALE));
-          }
-        }
-      }
-      flag[0] = fresh ? (int32_t)(s.flags[0] >> 5) : w.st[0];
-      flag[1] = fresh ? (int32_t)(s.flags[1] >> 5) : w.st[1];
-      flag[2] = wrote ? 1 : 0;
-      /* the reward rows go straight to global memory from the playing lane (a staging buffer in shared memory cost a CTA per SM) */
-      if (wrote && a.reward) for (int k = 0; k < 2; ++k) for (int d = 0; d < R; ++d) a.reward[(env * 2 + k) * R + d] = fresh ? 0.0f : (float)w.r[k][d];
-      /* a game that ended inside this call restarts right away under GW_AUTORESET_SAME_STEP: the observation is the new game's */
-      if (!a.is_reset && !fresh && w.st[0] >= 2 && w.st[1] >= 2 && c.autoreset == GW_AUTORESET_SAME_STEP) sav_new_game<SUST>(c, a, env, s, art, false, w.av, w.vis, &w.usable);
-      if (SUST && wrote) for (int k = 0; k < 4; ++k) a.avail[env * 4 + k] = w.av[k];
+      sav_lane_step<PRED, SUST>(c, a, base + slot, s_state[warp][slot], s_art[warp] + slot * cells, s_flag[warp][slot], cnt_vis, cnt_usable,
+                                a.stats ? a.stats + ((blockIdx.x * SAV_WARPS + warp) & (GW_STAT_REPLICAS - 1)) * GW_MA_STATS_LEN : nullptr);
     }
     __syncwarp();
     /* 3. outputs, one environment of the pass after the other */
@@ -636,7 +661,7 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, SUST ? 4 : SAV_MINB) gw_sav_ke
         }
         if (a.lcrop) {
           uint4* dst = reinterpret_cast<uint4*>(a.lcrop + (env * 2 + ag) * (int64_t)L * vpitch);
-          if (vch <= 32) {                                 /* one 16-byte piece per lane and layer: no index arithmetic */
+          {                                                /* vch <= 28 (radius <= 10): one 16-byte piece per lane and layer, no index arithmetic */
             if ((int)lane < vch) {                         /* the lane's 16 masks are loaded once for all layers */
               const uint4 m0 = *reinterpret_cast<const uint4*>(vmask + 16 * lane), m1 = *reinterpret_cast<const uint4*>(vmask + 16 * lane + 8);
               uint4* out = dst + lane;
@@ -645,7 +670,7 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, SUST ? 4 : SAV_MINB) gw_sav_ke
               for (uint32_t m = ~shown & ((1u << L) - 1u); m; m &= m - 1u) st_stream(out + (__ffs((int)m) - 1) * vch, make_uint4(0u, 0u, 0u, 0u));
               for (uint32_t m = shown; m; m &= m - 1u) { const int l = __ffs((int)m) - 1; st_stream(out + l * vch, plane16m(m0, m1, l)); }
             }
-          } else for (int i = (int)lane; i < L * vch; i += 32) st_stream(dst + i, plane16(vmask, i / vch, i % vch));
+          }
         }
         __syncwarp();
       }
