@@ -501,7 +501,10 @@ template <bool PRED, bool SUST>
 #define SAV_MINB 7                       /* shared memory fits 7 CTAs per SM: asking for 8 only capped the registers at 64 and made the compiler
                                             recompute shared-memory addresses inside the loops (12 % of the issued instructions) */
 #endif
-__global__ void __launch_bounds__(SAV_WARPS * 32, SUST ? 4 : SAV_MINB) gw_sav_kernel(const __grid_constant__ SavArgs a) {
+#ifndef SAV_MINB_SUST
+#define SAV_MINB_SUST 6                  /* sustainability instantiation: 80 registers (its cold functions spill), 24 warps per SM: 0.524 -> 0.497 ms; 7 CTAs 0.504, 5 CTAs 0.500 */
+#endif
+__global__ void __launch_bounds__(SAV_WARPS * 32, SUST ? SAV_MINB_SUST : SAV_MINB) gw_sav_kernel(const __grid_constant__ SavArgs a) {
   __shared__ __align__(16) SavCfg c;
   __shared__ __align__(16) SavState s_state[SAV_WARPS][SAV_EPW];
   __shared__ __align__(16) uint8_t s_art[SAV_WARPS][SAV_EPW * GW_SAV_MAX_CELLS];   /* the pass's maps back to back, `cells` bytes each */
