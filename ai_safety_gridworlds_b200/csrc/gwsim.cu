@@ -2773,7 +2773,6 @@ int gw_sav_create(const GwSavConfig* cfg, int64_t n_envs, int device, int64_t en
   if (c.gap_layer < 0 || c.wall_layer < 0) return fail(GW_ERR_INVALID, "the layers must include ' ' and '#'");
   if (cfg->amount[GW_SAV_T_PREDATOR] > 0 && c.pred_layer < 0) return fail(GW_ERR_INVALID, "the layers must include 'P' when there are predators");
   c.layer_of['0'] = c.layer_of['1'] = (int8_t)c.gap_layer;       /* a start tile is a gap once the sprite is lifted off the map */
-  sav_fill_vmap(c);
   int count = 0;
   cudaError_t ce = cudaGetDeviceCount(&count);
   if (ce != cudaSuccess || count == 0)

@@ -19,8 +19,12 @@
 
 #include "../../include/gwsim_sav.h"
 
+#ifndef SAV_WARPS
 #define SAV_WARPS 4
-#define SAV_EPW 8                        /* environments per warp and pass: lanes 0, 4, ..., 28 play one game each */
+#endif
+#ifndef SAV_EPW
+#define SAV_EPW 16                       /* environments per warp and pass: lanes 0, 2, ..., 30 play one game each */
+#endif
 #define SAV_VPITCH 448                   /* (2 * GW_SAV_MAX_RADIUS + 1)^2 = 441 rounded up to 16 */
 #define SAV_MAXR 14                      /* 2 * R must fit the raw statistics vector (GW_MA_STATS_LEN - 4) */
 
@@ -36,21 +40,7 @@ struct SavCfg {
   uint8_t layer_chars[GW_SAV_MAX_LAYERS];
   int8_t layer_of[128];                  /* ASCII code -> layer index (agents' start tiles and ' ' -> the gap layer), -1 = none */
   uint8_t art[GW_SAV_MAX_CELLS];         /* canonical layout: what the library shuffles */
-  uint16_t vmap[4][SAV_VPITCH];          /* [observation direction][view cell] -> source (row | column << 8) inside the crop: np.rot90 as a
-                                            table (sav_fill_vmap, built once at gw_sav_create), no division and no branch per cell */
 };
-
-/* out[i][j] = in[si][sj] for a view of side v rotated by the observation direction (safety_game_moma.py:2085-2096) */
-static inline void sav_fill_vmap(SavCfg& c) {
-  const int v = 2 * c.radius + 1;
-  for (int ij = 0; ij < SAV_VPITCH; ++ij) {
-    const int i = ij / v, j = ij % v;
-    c.vmap[GW_DIR_UP][ij] = (uint16_t)(i | (j << 8));
-    c.vmap[GW_DIR_DOWN][ij] = (uint16_t)(((v - 1 - i) & 255) | (((v - 1 - j) & 255) << 8));
-    c.vmap[GW_DIR_LEFT][ij] = (uint16_t)(((v - 1 - j) & 255) | (i << 8));
-    c.vmap[GW_DIR_RIGHT][ij] = (uint16_t)(j | (((v - 1 - i) & 255) << 8));
-  }
-}
 static_assert(sizeof(SavCfg) % 16 == 0, "SavCfg is copied in 16-byte pieces");
 
 struct SavArgs {
@@ -498,11 +488,10 @@ __device__ SAV_COLD void sav_lane_step(const SavCfg& c, const SavArgs& a, int64_
  * kernel is sensitive to its instruction footprint: the predator code cost the default flags 10 % before the split) */
 template <bool PRED, bool SUST>
 #ifndef SAV_MINB
-#define SAV_MINB 7                       /* shared memory fits 7 CTAs per SM: asking for 8 only capped the registers at 64 and made the compiler
-                                            recompute shared-memory addresses inside the loops (12 % of the issued instructions) */
+#define SAV_MINB 5                       /* 16 environments per pass: 42 KB of shared memory per CTA, 5 CTAs per SM, 96 registers */
 #endif
 #ifndef SAV_MINB_SUST
-#define SAV_MINB_SUST 6                  /* sustainability instantiation: 80 registers (its cold functions spill), 24 warps per SM: 0.524 -> 0.497 ms; 7 CTAs 0.504, 5 CTAs 0.500 */
+#define SAV_MINB_SUST 5                  /* sustainability instantiation: 80 registers (its cold functions spill), 24 warps per SM: 0.524 -> 0.497 ms; 7 CTAs 0.504, 5 CTAs 0.500 */
 #endif
 __global__ void __launch_bounds__(SAV_WARPS * 32, SUST ? SAV_MINB_SUST : SAV_MINB) gw_sav_kernel(const __grid_constant__ SavArgs a) {
   __shared__ __align__(16) SavCfg c;
@@ -512,12 +501,15 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, SUST ? SAV_MINB_SUST : SAV_MIN
   __shared__ __align__(16) uint8_t s_bchr[SAV_WARPS][GW_SAV_MAX_CELLS];    /* per cell: the rendered character */
   __shared__ __align__(16) uint16_t s_vmask[SAV_WARPS][SAV_VPITCH];        /* the same two for the cells of the current agent's view */
   __shared__ __align__(16) uint8_t s_vchr[SAV_WARPS][SAV_VPITCH];
+  __shared__ uint16_t s_rc[GW_SAV_MAX_CELLS];                                         /* cell -> row | column << 8 */
   __shared__ int32_t s_flag[SAV_WARPS][SAV_EPW][4];                                   /* out step types [2], "obs only" flag */
   {
     /* the configuration and its tables (the rot90 view map among them) in 16-byte pieces: a handful of loads per thread */
     const uint32_t pieces = (uint32_t)(sizeof(SavCfg) / 16);
     const uint4* src = reinterpret_cast<const uint4*>(a.cfg);
     for (uint32_t i = threadIdx.x; i < pieces; i += blockDim.x) reinterpret_cast<uint4*>(&c)[i] = __ldg(src + i);
+    const int w = a.cfg->width;
+    for (int p = (int)threadIdx.x; p < GW_SAV_MAX_CELLS; p += (int)blockDim.x) s_rc[p] = (uint16_t)((p / w) | ((p % w) << 8));
   }
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -526,12 +518,17 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, SUST ? SAV_MINB_SUST : SAV_MIN
    * lanes play that many games side by side (one instruction stream where their control flow agrees); the lanes then render
    * the games one after the other.  Measured at 131,072 environments: 1 per pass 0.64 ms, 4 per pass 0.45 ms, 8 per pass
    * 0.41 ms (34.9 KB of shared memory per CTA: 6 CTAs per SM instead of 8), 0.38 ms with the reward rows written straight to
-   * global memory (31.4 KB, 7 CTAs); 16 per pass do not fit the 48 KB of static shared memory.  Trimming to 28.0 KB for 8 CTAs
-   * (configuration without its layout, one view-cell table + a per-direction transform, packed flags) was correct but not
-   * faster (0.39 ms): dropped. */
-  for (int64_t grp = (int64_t)blockIdx.x * SAV_WARPS + warp; grp * SAV_EPW < a.n; grp += (int64_t)gridDim.x * SAV_WARPS) {
-    const int64_t base = grp * SAV_EPW;
-    const int ne = (int)(a.n - base < (int64_t)SAV_EPW ? a.n - base : (int64_t)SAV_EPW);
+   * global memory (31.4 KB, 7 CTAs).  Round 2 (after the game logic went out of line and the rot90 table left shared memory):
+   * 8 per pass 0.325 ms (28 warps per SM), 16 per pass 0.294 ms (42 KB per CTA, 5 CTAs = 20 warps, 96 registers), 32 per pass
+   * 0.387 ms (12 warps); the play phase -- 21 % of a warp's time with 8 of 32 lanes at work -- is what the wider pass halves. */
+  /* Every warp owns ONE contiguous range of environments, the batch divided evenly over the grid's warps in units of 4 (a pass
+   * must start on a multiple of 4: the maps are copied word-wise), and walks it in passes of SAV_EPW: the last pass of a range is
+   * shorter instead of some warps running a whole pass more than others (131,072 environments are 2.77 passes of 16 per warp). */
+  const int64_t n_warps = (int64_t)gridDim.x * SAV_WARPS, my_warp = (int64_t)blockIdx.x * SAV_WARPS + warp, units = (a.n + 3) >> 2;
+  const int64_t range_lo = ((units * my_warp) / n_warps) << 2, range_hi_ = ((units * (my_warp + 1)) / n_warps) << 2;
+  const int64_t range_hi = range_hi_ < a.n ? range_hi_ : a.n;
+  for (int64_t base = range_lo; base < range_hi; base += SAV_EPW) {
+    const int ne = (int)(range_hi - base < (int64_t)SAV_EPW ? range_hi - base : (int64_t)SAV_EPW);
     /* 1. states and maps into shared memory: both are contiguous over consecutive environments */
     {
       uint4* dstw = reinterpret_cast<uint4*>(&s_state[warp][0]);
@@ -641,20 +638,31 @@ __global__ void __launch_bounds__(SAV_WARPS * 32, SUST ? SAV_MINB_SUST : SAV_MIN
         const int pa = ag == 0 ? pos0 : pos1;
         const int r0 = pa / c.width - c.radius, c0 = pa % c.width - c.radius;
         const int dir = c.obs_mode ? (s.flags[ag] >> 2) & 3 : GW_DIR_UP;
-        const uint16_t* vmap = c.vmap[dir];
-        /* get_agent_perspective (safety_game_moma.py:1996-2101): crop, '#' outside the board, np.rot90 by the observation direction */
-        uint32_t seen = 0;                                   /* layers that show anything in this view */
-        for (int ij = (int)lane; ij < vpitch; ij += 32) {
-          uint32_t mk = 0;
-          uint8_t ch = 0;
-          if (ij < V2) {
-            const uint32_t t = vmap[ij];
-            const int r = r0 + (int)(t & 255u), cc = c0 + (int)(t >> 8);
-            if ((unsigned)r < (unsigned)c.height && (unsigned)cc < (unsigned)c.width) { const int p = r * c.width + cc; mk = cmask[p]; ch = bchr[p]; }
-            else { mk = wbit; ch = (uint8_t)'#'; }
+        /* get_agent_perspective (safety_game_moma.py:1996-2101): crop, '#' outside the board, np.rot90 by the observation direction.
+         * Most of a 21 x 21 view of a 13 x 13 board is padding, so the view is FILLED with the padding value in 16-byte stores and the
+         * board's cells are SCATTERED into it: cell (r, c) of the crop window lands at view index A0 + AR * (r - r0) + AC * (c - c0)
+         * (rot90 as an affine map of the index: UP (0, V, 1), DOWN (V^2 - 1, -V, -1), LEFT (V - 1, -1, V), RIGHT ((V - 1) V, 1, -V)) --
+         * 6 passes over the board instead of 14 over the view, and no table */
+        {
+          const uint32_t w2 = wbit | (wbit << 16);
+          for (int q = (int)lane; q < (vpitch >> 3); q += 32) reinterpret_cast<uint4*>(vmask)[q] = make_uint4(w2, w2, w2, w2);
+          for (int q = (int)lane; q < (vpitch >> 4); q += 32) reinterpret_cast<uint4*>(vchr)[q] = make_uint4(0x23232323u, 0x23232323u, 0x23232323u, 0x23232323u);
+        }
+        __syncwarp();
+        if ((int)lane < vpitch - V2) { vmask[V2 + lane] = 0; vchr[V2 + lane] = 0; }       /* the row padding behind the view stays zero */
+        const int AR = dir == GW_DIR_UP ? V : dir == GW_DIR_DOWN ? -V : dir == GW_DIR_LEFT ? -1 : 1;
+        const int AC = dir == GW_DIR_UP ? 1 : dir == GW_DIR_DOWN ? -1 : dir == GW_DIR_LEFT ? V : -V;
+        const int B0 = (dir == GW_DIR_UP ? 0 : dir == GW_DIR_DOWN ? V2 - 1 : dir == GW_DIR_LEFT ? V - 1 : (V - 1) * V) - AR * r0 - AC * c0;
+        uint32_t seen = wbit;                                /* layers that show anything in this view */
+        for (int p = (int)lane; p < cells; p += 32) {
+          const uint32_t rc = s_rc[p];
+          const int r = (int)(rc & 255u), cc = (int)(rc >> 8);
+          if ((unsigned)(r - r0) < (unsigned)V && (unsigned)(cc - c0) < (unsigned)V) {
+            const int idx = B0 + AR * r + AC * cc;
+            const uint32_t mk = cmask[p];
+            vmask[idx] = (uint16_t)mk; vchr[idx] = bchr[p];
+            seen |= mk;
           }
-          vmask[ij] = (uint16_t)mk; vchr[ij] = ch;
-          seen |= mk;
         }
         seen = __reduce_or_sync(FULL, seen);
         __syncwarp();
