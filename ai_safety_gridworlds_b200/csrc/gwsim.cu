@@ -2284,6 +2284,7 @@ struct GwImaEngine {
   uint32_t cube_off, board_off, crop_off, lcrop_off, reward_off, warp_bytes;
   uint32_t map_off, warp_bytes_pm;     /* per-environment-map variant: its own layout (bit strings for the layer tensors) + 32 maps per warp */
   uint32_t pm_cube_off, pm_board_off, pm_crop_off, pm_lcrop_off, pm_reward_off;
+  bool rm8;                             /* n_rewards <= 8: the instantiations with 8-wide reward rows */
   uint8_t* maps;                        /* caller-owned [N, cells] tensor or NULL */
   int32_t map_mode;                     /* GwImaMapMode */
   int grid_pm;
@@ -2379,15 +2380,20 @@ int gw_ima_create(const GwConfig* cfg, int64_t n_envs, int device, int64_t env_i
   h->maps = nullptr; h->map_mode = GW_IMA_MAPS_STATIC;
   const size_t smem = (size_t)h->warp_bytes * IMA_WARPS, smem_pm = (size_t)h->warp_bytes_pm * IMA_WARPS_PM;
   h->d_claim = nullptr; h->d_stats = nullptr;
-  ce = cudaFuncSetAttribute(gw_ima_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (ce == cudaSuccess) ce = cudaFuncSetAttribute(gw_ima_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pm);
+  h->rm8 = cfg->n_rewards <= 8;             /* the kernels are compiled for reward rows of 8 (the default flags) and of GW_MAX_REWARDS */
+  ce = h->rm8 ? cudaFuncSetAttribute(gw_ima_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+              : cudaFuncSetAttribute(gw_ima_kernel<false, GW_MAX_REWARDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (ce == cudaSuccess) ce = h->rm8 ? cudaFuncSetAttribute(gw_ima_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pm)
+                                     : cudaFuncSetAttribute(gw_ima_kernel<true, GW_MAX_REWARDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pm);
   if (ce == cudaSuccess) ce = cudaMalloc((void**)&h->d_claim, sizeof(unsigned long long));
   if (ce == cudaSuccess) ce = cudaMemset(h->d_claim, 0, sizeof(unsigned long long));
   if (ce == cudaSuccess) ce = ma_stats_alloc(&h->d_stats);
   int per_sm = 0, sms = 0;
   int per_sm_pm = 0;
-  if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gw_ima_kernel<false>, IMA_WARPS * 32, smem);
-  if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_pm, gw_ima_kernel<true>, IMA_WARPS_PM * 32, smem_pm);
+  if (ce == cudaSuccess) ce = h->rm8 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gw_ima_kernel<false, 8>, IMA_WARPS * 32, smem)
+                                     : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gw_ima_kernel<false, GW_MAX_REWARDS>, IMA_WARPS * 32, smem);
+  if (ce == cudaSuccess) ce = h->rm8 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_pm, gw_ima_kernel<true, 8>, IMA_WARPS_PM * 32, smem_pm)
+                                     : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_pm, gw_ima_kernel<true, GW_MAX_REWARDS>, IMA_WARPS_PM * 32, smem_pm);
   if (ce == cudaSuccess) ce = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   if (ce != cudaSuccess || per_sm < 1 || per_sm_pm < 1) {
     cudaFree(h->d_claim); cudaFree(h->d_stats); delete h;
@@ -2443,8 +2449,10 @@ static int ima_launch(GwImaHandle h, ImaArgs& a, void* state, const GwImaObs* ob
   }
   a.claim_counter = h->d_claim;
   a.stats = h->d_stats;
-  if (pm) gw_ima_kernel<true><<<(unsigned)grid, IMA_WARPS_PM * 32, (size_t)h->warp_bytes_pm * IMA_WARPS_PM, stream>>>(h->dc, a);
-  else gw_ima_kernel<false><<<(unsigned)grid, IMA_WARPS * 32, (size_t)h->warp_bytes * IMA_WARPS, stream>>>(h->dc, a);
+  if (pm && h->rm8) gw_ima_kernel<true, 8><<<(unsigned)grid, IMA_WARPS_PM * 32, (size_t)h->warp_bytes_pm * IMA_WARPS_PM, stream>>>(h->dc, a);
+  else if (pm) gw_ima_kernel<true, GW_MAX_REWARDS><<<(unsigned)grid, IMA_WARPS_PM * 32, (size_t)h->warp_bytes_pm * IMA_WARPS_PM, stream>>>(h->dc, a);
+  else if (h->rm8) gw_ima_kernel<false, 8><<<(unsigned)grid, IMA_WARPS * 32, (size_t)h->warp_bytes * IMA_WARPS, stream>>>(h->dc, a);
+  else gw_ima_kernel<false, GW_MAX_REWARDS><<<(unsigned)grid, IMA_WARPS * 32, (size_t)h->warp_bytes * IMA_WARPS, stream>>>(h->dc, a);
   CUDA_TRY(cudaGetLastError());                                /* a refused launch claims nothing: the host base stays in step */
   h->launches += 1;
   return GW_OK;

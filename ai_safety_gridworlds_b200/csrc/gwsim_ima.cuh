@@ -217,7 +217,7 @@ __device__ __forceinline__ int ima_relative(int action, int dir) {
 #define IMA_ADD(vec, e, scale)                                                                   \
   do {                                                                                           \
     if ((c.event_nonzero >> (e)) & 1u) {                                                         \
-      _Pragma("unroll") for (int d_ = 0; d_ < GW_MAX_REWARDS; ++d_) vec[d_] += c.table[e][d_] * (scale); \
+      _Pragma("unroll") for (int d_ = 0; d_ < RM; ++d_) vec[d_] += c.table[e][d_] * (scale); \
     }                                                                                            \
   } while (0)
 
@@ -233,6 +233,9 @@ __device__ __forceinline__ void ima_resource(const ImaCfg& c, int32_t frame, boo
 }
 
 /* One Engine.play({agent: action}); `fr` collects the acting agent's rewards, danger[p] counts WaterDrape hits */
+/* RM = the reward-row width the kernel is compiled for (8 covers the game's default flags, 12 = GW_MAX_REWARDS): the rows live in
+ * registers and every reward event is an unrolled multiply-add over them */
+template <int RM>
 __device__ __forceinline__ void ima_play(const ImaCfg& c, const uint8_t* __restrict__ s_art, ImaState& s, int a, int action, double* fr,
                                          int32_t* danger) {
   const double* F = c.fparams;
@@ -308,14 +311,15 @@ __device__ __forceinline__ void ima_play(const ImaCfg& c, const uint8_t* __restr
 
 /* One lane = one environment: the whole parallel step.  Writes the reward rows ([2][R] floats) to `rw` and returns the
  * agents' output step types. */
+template <int RM>
 __device__ __forceinline__ bool ima_step_lane(const ImaCfg& c, const ImaArgs& a, const uint8_t* __restrict__ s_type_art, ImaMap& M, int64_t env,
                                               const ImaRaw& raw, ImaState& s, float* __restrict__ rw, int32_t* out_st,
                                               unsigned long long* __restrict__ s_stats) {
   const uint8_t* __restrict__ s_art = M.art;
   ima_unpack(s, raw, c);
-  double r0[GW_MAX_REWARDS], r1[GW_MAX_REWARDS];
+  double r0[RM], r1[RM];
 #pragma unroll
-  for (int d = 0; d < GW_MAX_REWARDS; ++d) { r0[d] = 0.0; r1[d] = 0.0; }
+  for (int d = 0; d < RM; ++d) { r0[d] = 0.0; r1[d] = 0.0; }
   bool played = false;
   if (s.ag[0].st >= 2 && s.ag[1].st >= 2) {
     ima_new_game(c, a, s_type_art, env, M, s);                 /* every agent is done: new game, FIRST (pycolab_interface_ma.py:206-213) */
@@ -343,16 +347,16 @@ __device__ __forceinline__ bool ima_step_lane(const ImaCfg& c, const ImaArgs& a,
       const int ag = k == 0 ? ord0 : ord1;
       if (ag < 0 || ag > 1) continue;
       if ((ag ? s.ag[1].st : s.ag[0].st) >= 2) continue;       /* no frame for a finished agent */
-      double fr[GW_MAX_REWARDS];
+      double fr[RM];
 #pragma unroll
-      for (int d = 0; d < GW_MAX_REWARDS; ++d) fr[d] = 0.0;
-      ima_play(c, s_art, s, ag, ag ? raw.act1 : raw.act0, fr, danger);
+      for (int d = 0; d < RM; ++d) fr[d] = 0.0;
+      ima_play<RM>(c, s_art, s, ag, ag ? raw.act1 : raw.act0, fr, danger);
 #pragma unroll
-      for (int d = 0; d < GW_MAX_REWARDS; ++d) { if (ag) r1[d] += fr[d]; else r0[d] += fr[d]; }
+      for (int d = 0; d < RM; ++d) { if (ag) r1[d] += fr[d]; else r0[d] += fr[d]; }
       if (s.frame >= c.max_iterations) over = true;            /* pycolab_interface_ma.py:429-430 */
     }
 #pragma unroll
-    for (int d = 0; d < GW_MAX_REWARDS; ++d) {
+    for (int d = 0; d < RM; ++d) {
       r0[d] += c.table[GW_ISL_E_DANGER_TILE][d] * (double)danger[0];
       r1[d] += c.table[GW_ISL_E_DANGER_TILE][d] * (double)danger[1];
       s.cum[0][d] += (float)r0[d];
@@ -373,7 +377,7 @@ __device__ __forceinline__ bool ima_step_lane(const ImaCfg& c, const ImaArgs& a,
         atomicAdd(&s_stats[1], 1ull);
         atomicAdd(&s_stats[2], (unsigned long long)s.frame);
 #pragma unroll
-        for (int d = 0; d < GW_MAX_REWARDS; ++d)
+        for (int d = 0; d < RM; ++d)
           if (d < c.n_rewards) {
             if (s.cum[0][d] != 0.0f) atomicAdd(&s_stats[GW_MA_STATS_RETURN0 + d], (unsigned long long)__double2ll_rn((double)s.cum[0][d] * GW_MA_STATS_SCALE));
             if (s.cum[1][d] != 0.0f) atomicAdd(&s_stats[GW_MA_STATS_RETURN0 + c.n_rewards + d], (unsigned long long)__double2ll_rn((double)s.cum[1][d] * GW_MA_STATS_SCALE));
@@ -383,7 +387,7 @@ __device__ __forceinline__ bool ima_step_lane(const ImaCfg& c, const ImaArgs& a,
     }
   }
 #pragma unroll
-  for (int d = 0; d < GW_MAX_REWARDS; ++d)
+  for (int d = 0; d < RM; ++d)
     if (d < c.n_rewards) { rw[d] = (float)r0[d]; rw[c.n_rewards + d] = (float)r1[d]; }
   return played;
 }
@@ -475,7 +479,7 @@ __device__ __forceinline__ void ima_views_own(const ImaCfg& c, const uint8_t* __
 
 /* PM = per-environment maps (map randomisation): the art is read from (and, after a shuffle, written back to) a.maps, and board
  * and cube are rendered from it for every chunk instead of being a patched template. */
-template <bool PM>
+template <bool PM, int RM>
 __global__ void __launch_bounds__((PM ? IMA_WARPS_PM : IMA_WARPS) * 32, PM ? 3 : 2) gw_ima_kernel(const __grid_constant__ ImaCfg c, const ImaArgs a) {
   extern __shared__ __align__(128) uint8_t ima_stage[];
   __shared__ __align__(16) uint8_t s_art[GW_MAX_CELLS];
@@ -592,7 +596,7 @@ __global__ void __launch_bounds__((PM ? IMA_WARPS_PM : IMA_WARPS) * 32, PM ? 3 :
         if (wrote) ima_new_game(c, a, s_art, env, M, s);
         for (uint32_t d = 0; d < R2; ++d) s_rw[lane * R2 + d] = 0.0f;
       } else {
-        played = ima_step_lane(c, a, s_art, M, env, raw, s, s_rw + lane * R2, out_st, s_stats);
+        played = ima_step_lane<RM>(c, a, s_art, M, env, raw, s, s_rw + lane * R2, out_st, s_stats);
       }
       if (wrote) {
         ima_store(s, a.state, a.n, env);
