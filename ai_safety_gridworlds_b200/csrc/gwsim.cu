@@ -2767,6 +2767,8 @@ int gw_sav_create(const GwSavConfig* cfg, int64_t n_envs, int device, int64_t en
   memcpy(c.amount, cfg->amount, sizeof c.amount);
   memcpy(c.fparams, cfg->fparams, sizeof c.fparams);
   memcpy(c.table, cfg->reward_table, sizeof c.table);
+  for (int e = 0; e < GW_SAV_EVENTS; ++e)
+    for (int d = 0; d < GW_SAV_MAX_REWARDS; ++d) if (c.table[e][d] != 0.0) c.event_nonzero |= 1u << e;
   memcpy(c.layer_chars, cfg->layer_chars, sizeof c.layer_chars);
   memcpy(c.art, cfg->art, sizeof c.art);
   c.gap_layer = c.wall_layer = c.agent_layer[0] = c.agent_layer[1] = c.pred_layer = -1;

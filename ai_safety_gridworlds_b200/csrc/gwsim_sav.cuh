@@ -34,7 +34,9 @@ struct SavCfg {
   int32_t radius, view, obs_mode, act_mode;
   int32_t randomize, death, penalise, proportional;
   int32_t amount[8];
-  int32_t gap_layer, wall_layer, agent_layer[2], pred_layer, sustainability, pad[2];
+  int32_t gap_layer, wall_layer, agent_layer[2], pred_layer, sustainability;
+  uint32_t event_nonzero;                /* bit e: reward_table[e] has a non-zero entry (an all-zero row adds +-0 to the reward rows: skipped) */
+  int32_t pad;
   double fparams[32];
   double table[GW_SAV_EVENTS][GW_SAV_MAX_REWARDS];
   uint8_t layer_chars[GW_SAV_MAX_LAYERS];
@@ -119,6 +121,7 @@ __device__ __forceinline__ int sav_res_slot(uint8_t ch) { return ch == 'D' ? 0 :
 #define SAV_ROLL
 #endif
 __device__ SAV_COLD void sav_add(const SavCfg& c, SavRun& w, int agent, int event, double scale) {
+  if (!((c.event_nonzero >> event) & 1u)) return;       /* NON_DRINK / NON_FOOD / GAP pay nothing with the default flags */
   SAV_ROLL
   for (int d = 0; d < c.n_rewards; ++d) w.r[agent][d] += c.table[event][d] * scale;
 }
