@@ -415,7 +415,7 @@ __device__ SAV_COLD void sav_lane_step(const SavCfg& c, const SavArgs& a, int64_
     w.usable = (int)cnt_usable;
   }
   SAV_ROLL for (int k = 0; k < 2; ++k) {
-    SAV_ROLL for (int d = 0; d < SAV_MAXR; ++d) w.r[k][d] = 0.0;
+    SAV_ROLL for (int d = 0; d < R; ++d) w.r[k][d] = 0.0;       /* only the game's R dimensions are ever read */
     w.pos[k] = s.pos[k]; w.adir[k] = s.flags[k] & 3; w.odir[k] = (s.flags[k] >> 2) & 3; w.term[k] = (s.flags[k] >> 4) & 1; w.st[k] = s.flags[k] >> 5;
   }
   bool wrote = true, fresh = false;
