@@ -220,3 +220,54 @@ def test_random_savanna_configurations_match_the_oracle(seed, oracle_lib):
             _same(ctx, [(k, ex[k], ox[k]) for k in ("frame", "pos", "directions")])
     env.close()
     orc.close()
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 17, 33, 63])
+def test_tiny_and_odd_batches_match_the_oracle(n, oracle_lib):
+    """Batches smaller than a warp pass and sizes that are no multiple of anything (the savanna kernel splits the batch into one
+    contiguous range per warp in units of 4 environments, the lane-per-environment kernels run a ragged last chunk)."""
+    from ai_safety_gridworlds_b200 import IslandMaVectorEnv, make_spec
+    from ai_safety_gridworlds_b200.savanna_env import SavannaVectorEnv
+    from ai_safety_gridworlds_b200.firemaker_env import FiremakerVectorEnv
+    rng = np.random.default_rng(n)
+    spec = make_spec("aintelope_savanna", autoreset_mode=1, amount_agents=2, amount_predators=2, max_iterations=12)
+    env = SavannaVectorEnv(n, spec=spec, env_index_base=5, seed=2, autoreset_mode=1)
+    orc = oracle_lib.SavannaOracle(spec.with_autoreset(1), n, env_index_base=5, seed=2)
+    orc.set_maps(orc.maps, 1)
+    orc.reset()
+    for t in range(30):
+        a = rng.integers(0, 5, size=(n, 2)).astype(np.int32)
+        env.step(torch.from_numpy(a).to(env.device))
+        orc.step(a)
+        ctx = "savanna n=%d t=%d" % (n, t)
+        _same(ctx, (("maps", env.maps.reshape(n, -1), orc.maps), ("board", env.board, orc.board), ("cube", env.cube, orc.cube), ("crop", env.crop, orc.crop),
+                    ("lcrop", env.lcrop, orc.lcrop), ("step_type", env.step_type, orc.step_type)))
+        np.testing.assert_allclose(_np(env.reward), orc.reward, rtol=1e-6, atol=1e-6, err_msg=ctx)
+    env.close(); orc.close()
+    spec = make_spec("island_navigation_ex_ma", autoreset_mode=1, map_randomization_frequency=3, max_iterations=12)
+    env = IslandMaVectorEnv(n, device="cuda:0", seed=4, autoreset_mode=1, spec=spec, env_index_base=9)
+    orc = oracle_lib.IslandMaOracle(spec, n, env_index_base=9, seed=4)
+    art = np.array([[ord(ch) for ch in row] for row in spec.art], np.uint8)
+    omaps = np.repeat(art[None], n, axis=0).copy()
+    orc.set_maps(omaps, 1)
+    orc.reset()
+    for t in range(30):
+        a = rng.integers(0, 5, size=(n, 2)).astype(np.int32)
+        env.step(torch.from_numpy(a).to(env.device))
+        orc.step(a)
+        ctx = "island_ma n=%d t=%d" % (n, t)
+        _same(ctx, (("maps", env.maps, omaps), ("board", env.board, orc.board), ("cube", env.cube, orc.cube), ("crop", env.crop, orc.crop),
+                    ("lcrop", env.lcrop, orc.lcrop), ("step_type", env.step_type, orc.step_type)))
+    env.close(); orc.close()
+    spec = make_spec("firemaker_ex_ma", autoreset_mode=1, amount_agents=3, max_iterations=30, observation_direction_mode=1, action_direction_mode=1)
+    env = FiremakerVectorEnv(n, env_index_base=3, seed=6, autoreset_mode=1, spec=spec)
+    orc = oracle_lib.FiremakerOracle(spec, n, env_index_base=3, seed=6)
+    orc.reset()
+    for t in range(30):
+        a = rng.integers(0, 5, size=(n, 3)).astype(np.int32)
+        env.step(torch.from_numpy(a).to(env.device))
+        orc.step(a)
+        ctx = "firemaker n=%d t=%d" % (n, t)
+        _same(ctx, (("board", env.board, orc.board), ("cube", env.cube, orc.cube), ("crop_s", env.crop_supervisor, orc.crop_s),
+                    ("lcrop_s", env.lcrop_supervisor, orc.lcrop_s), ("lcrop_w", env.lcrop_workers, orc.lcrop_w), ("step_type", env.step_type, orc.step_type)))
+    env.close(); orc.close()
