@@ -79,8 +79,9 @@ struct FmArgs {
 };
 
 
-/* Draw k of environment `env` in this call: Philox4x32-10 keyed by the seed, counter (global environment index, call * 65536 + k / 2);
- * one evaluation yields TWO 53-bit uniforms -- draw 2 j from words (x, y), draw 2 j + 1 from (z, w). */
+/* Philox4x32-10 keyed by the seed, counter (global environment index, call * 65536 + evaluation index).  The FireDrape draws take one
+ * 32-bit word each (draw d = word d & 3 of evaluation d >> 2, u = word / 2^32); the shuffle of the agents' order takes the two 53-bit
+ * uniforms of evaluation 32767 (words (x, y) and (z, w)). */
 __device__ __forceinline__ uint4 fm_philox(const FmArgs& a, int64_t env, uint32_t call_index) {
   const uint64_t g = (uint64_t)(a.env_index_base + env);
   const uint64_t step = a.call_no * 65536ull + call_index;
@@ -89,10 +90,6 @@ __device__ __forceinline__ uint4 fm_philox(const FmArgs& a, int64_t env, uint32_
 }
 __device__ __forceinline__ double fm_u53(uint32_t hi, uint32_t lo) {
   return (double)((((unsigned long long)hi << 32) | lo) >> 11) * (1.0 / 9007199254740992.0);
-}
-__device__ __forceinline__ double fm_uniform(const FmArgs& a, int64_t env, uint32_t k) {
-  const uint4 r = fm_philox(a, env, k >> 1);
-  return (k & 1u) ? fm_u53(r.z, r.w) : fm_u53(r.x, r.y);
 }
 
 /* get_absolute_action / get_new_action_or_observation_direction, mode 1 (safety_game_ma.py:505-587): UP = forwards, DOWN =
@@ -223,13 +220,17 @@ __device__ __forceinline__ int fm_fire_update(const FmStatic& S, const FmArgs& a
       ub[i] = (int64_t)idx < a.draw_stride ? a.draws[env * a.draw_stride + idx] : 2.0;
     }
   } else {
-    const uint32_t c0 = k >> 1, ncalls = ((k + T + 1u) >> 1) - c0;
+    /* FireDrape draw d of the call = word d & 3 of Philox evaluation d >> 2, u = word / 2^32: four draws per evaluation (a burning
+     * game draws for every cell that can burn, ~225 per frame: at two 53-bit draws per evaluation Philox was ~30 % of its fire update) */
+    const uint32_t c0 = k >> 2, ncalls = ((k + T + 3u) >> 2) - c0;
 #pragma unroll 1
     for (uint32_t j = lane; j < ncalls; j += 32) {
       const uint4 r = fm_philox(a, env, c0 + j);
-      const int32_t i0 = (int32_t)(2u * (c0 + j)) - (int32_t)k;
-      if (i0 >= 0 && i0 < (int32_t)T) ub[i0] = fm_u53(r.x, r.y);
-      if (i0 + 1 >= 0 && i0 + 1 < (int32_t)T) ub[i0 + 1] = fm_u53(r.z, r.w);
+      const int32_t i0 = (int32_t)(4u * (c0 + j)) - (int32_t)k;
+      const uint32_t wd[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (i0 + q >= 0 && i0 + q < (int32_t)T) ub[i0 + q] = (double)wd[q] * (1.0 / 4294967296.0);
     }
   }
   __syncwarp();

@@ -54,13 +54,19 @@ typedef struct {
 
 void or_philox(uint64_t seed, uint64_t env, uint64_t step, uint32_t out[4]);   /* gw_oracle.c */
 
-/* draw k of the call: one Philox4x32-10 evaluation per PAIR of draws (counter call * 65536 + k / 2; words 0-1 serve the even
- * draw, words 2-3 the odd one) -- the stream definition the CUDA kernel shares (csrc/gwsim_fm.cuh fm_uniform) */
-static double philox_uniform(const FOracle* o, int64_t env, uint32_t k) {
+/* The Philox streams the CUDA kernel shares (csrc/gwsim_fm.cuh): counter (global environment, call * 65536 + evaluation index).
+ * philox_pair: the two 53-bit uniforms of an evaluation (the shuffle of the agents' order: draw k = half k & 1 of evaluation k >> 1);
+ * philox_uniform: the FireDrape draws, one 32-bit word each (draw k = word k & 3 of evaluation k >> 2, u = word / 2^32). */
+static double philox_pair(const FOracle* o, int64_t env, uint32_t k) {
   uint32_t r[4];
   or_philox(o->seed, (uint64_t)(o->env_index_base + env), o->call_no * 65536ull + (k >> 1), r);
   const uint32_t hi = (k & 1u) ? r[2] : r[0], lo = (k & 1u) ? r[3] : r[1];
   return (double)((((uint64_t)hi << 32) | lo) >> 11) * (1.0 / 9007199254740992.0);
+}
+static double philox_uniform(const FOracle* o, int64_t env, uint32_t k) {
+  uint32_t r[4];
+  or_philox(o->seed, (uint64_t)(o->env_index_base + env), o->call_no * 65536ull + (k >> 2), r);
+  return (double)r[k & 3u] * (1.0 / 4294967296.0);
 }
 
 /* Engine._render, z_order ['-','W','F','B','1','2','S'] (firemaker_ex_ma.py:346-350) */
@@ -349,7 +355,7 @@ static void step_range(void* ctx, int64_t lo, int64_t hi) {
     if (order) { for (int a = 0; a < NA; ++a) ord[a] = order[i * NA + a]; }
     else if (o->cfg.randomize_order) {                                        /* Fisher-Yates on the Philox stream */
       for (int k = (two_agents ? 1 : NA - 1); k >= 1; --k) {
-        const int j = (int)(philox_uniform(o, i, 65533u + (uint32_t)k) * (k + 1));
+        const int j = (int)(philox_pair(o, i, 65533u + (uint32_t)k) * (k + 1));
         const int t = ord[k]; ord[k] = ord[j]; ord[j] = t;
       }
     }
