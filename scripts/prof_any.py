@@ -1,4 +1,4 @@
-"""ncu / timing target for the secondary kernels: WHICH = fm | sav | sav_sust | ima | ima_randmap, N environments, STEPS launches.
+"""ncu / timing target for the secondary kernels: WHICH = fm | fm_dm1 | fm_dm2 | sav | sav_pred | sav_sust | ima | ima_randmap, N environments, STEPS launches.
 With TIME=1 the launches are timed with CUDA events (never under ncu) and one line is printed."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -9,15 +9,20 @@ from ai_safety_gridworlds_b200.vector_env import _ptr
 dev = torch.device("cuda", 0)
 which = os.environ.get("WHICH", "fm")
 steps = int(os.environ.get("STEPS", 30))
-if which == "fm":
+hi = 5
+if which.startswith("fm"):
     from ai_safety_gridworlds_b200.firemaker_env import FiremakerVectorEnv
     N = int(os.environ.get("N", 1 << 18))
-    env = FiremakerVectorEnv(N, device=dev, seed=1, autoreset_mode=1, spec=make_spec("firemaker_ex_ma", autoreset_mode=1, amount_agents=3))
+    dm = int(which[-1]) if which.startswith("fm_dm") else 0
+    hi = 9 if dm == 2 else 5
+    env = FiremakerVectorEnv(N, device=dev, seed=1, autoreset_mode=1, spec=make_spec("firemaker_ex_ma", autoreset_mode=1, amount_agents=3,
+                                                                                   observation_direction_mode=dm, action_direction_mode=dm))
     na = 3
-elif which in ("sav", "sav_sust"):
+elif which in ("sav", "sav_sust", "sav_pred"):
     from ai_safety_gridworlds_b200.savanna_env import SavannaVectorEnv
     N = int(os.environ.get("N", 1 << 17))
-    spec = make_spec("food_sustainability" if which == "sav_sust" else "aintelope_savanna", autoreset_mode=1)
+    spec = make_spec("food_sustainability" if which == "sav_sust" else "aintelope_savanna", autoreset_mode=1,
+                     **(dict(amount_predators=4, amount_agents=2) if which == "sav_pred" else {}))
     env = SavannaVectorEnv(N, device=dev, seed=1, autoreset_mode=1, spec=spec)
     na = 2
 else:
@@ -26,7 +31,7 @@ else:
     kw = dict(map_randomization_frequency=3) if which == "ima_randmap" else {}
     env = IslandMaVectorEnv(N, device=dev, seed=1, autoreset_mode=1, spec=make_spec("island_navigation_ex_ma", autoreset_mode=1, **kw))
     na = 2
-acts = [torch.randint(0, 5, (N, na), dtype=torch.int32, device=dev) for _ in range(8)]
+acts = [torch.randint(0, hi, (N, na), dtype=torch.int32, device=dev) for _ in range(8)]
 for i in range(steps):
     env.step_raw(_ptr(acts[i & 7]))
 torch.cuda.synchronize()
