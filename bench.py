@@ -644,6 +644,9 @@ def main():
     ap.add_argument("--graph-steps", type=int, default=0,
                     help="capture this many consecutive step launches in one CUDA graph and replay it (0 = plain launches); for "
                          "small batches whose kernel is shorter than the host's launch overhead")
+    ap.add_argument("--action-ring", type=int, default=0,
+                    help="distinct steps of pre-generated actions the rollout cycles through (0 = 8 for the single-agent workloads, 64 for the "
+                         "multi-agent ones)")
     ap.add_argument("--e2e-steps", type=int, default=30)
     ap.add_argument("--e2e-parts", type=int, default=4, help="slices of the split-batch double buffering of the e2e leg")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="budget of the oracle-port CPU baseline (N=1 only)")
@@ -658,6 +661,14 @@ def main():
     ENV_NAME, ENV_KWARGS, ENVS_PER_GPU, WORKLOAD_TEXT, OUTPUTS_TEXT = WORKLOADS[args.workload]
     if args.envs_per_gpu is None:
         args.envs_per_gpu = ENVS_PER_GPU if args.scaling == "weak" else max(32, ENVS_PER_GPU // max(1, args.gpus))
+    global ACTION_RING
+    if args.action_ring:
+        ACTION_RING = max(1, args.action_ring)
+    elif ENV_NAME in ("firemaker_ex_ma", "island_navigation_ex_ma", "aintelope_savanna"):
+        # Long games (firemaker: 333 parallel steps) under a SHORT periodic action sequence are a different workload: with a ring of 8
+        # the firemaker workers oscillate in place and a quarter of the games burn at step 150, against two thirds under fresh random
+        # actions.  64 distinct steps of actions keep the rollout statistically like the fresh-random one.
+        ACTION_RING = 64
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
